@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the per-step hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--envs E] [--config anymal_c_rough]
+
+Metric: env-steps/s of the fused post-physics step.  One "step" = one pass of the hot path over one
+batch of synthetic PhysX state = 1x _compute_torques + the post_physics_step body (derive, heading,
+187-point height scan, termination, the reward registry, observations with in-kernel noise, history)
+-- SURVEY.md section 8d.  Workload at N=1: BASELINE configs[1], anymal_c_rough, 4096 envs, one B200.
+For N>1 the envs shard across ranks with no data-path collective (weak scaling: 4096 envs per GPU);
+episode statistics are reduced with one NCCL all-reduce per timed region.
+
+  value     device-resident throughput: K steps (2 kernels each) replayed from one CUDA graph, CUDA events,
+            max over ranks.  Every step works on a different replica of the state (R replicas, > 2x L2 in
+            total) so no step finds its inputs in L2.
+  e2e       the same step through the public Python API (LeggedRobot._compute_torques + post_physics_step)
+            with the PhysX state in pinned HOST memory: H2D of the state + actions and D2H of obs / rew /
+            reset inside the timed region, every step.
+  roofline  step kernel alone (same graph technique), algorithmic bytes of SURVEY.md section 8d over its
+            mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline  the oracle port of the reference's torch-CPU implementation on this box's host cores.
+
+--impl reference runs ONLY that CPU implementation (all host threads) and prints the same line shape.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+import torch  # noqa: E402
+
+METRIC = "env-steps/s of fused post-physics step"
+UNIT = "env-steps/s"
+L2_BYTES = 126 * 1024 * 1024
+
+
+# ----------------------------------------------------------------------------------------------
+def algorithmic_bytes_per_env(D, F, P, T, H, O, R, C_, heading):
+    """every distinct tensor element the reference reads / writes, counted once."""
+    reads = 4 * (13 + 2 * D + 3 * (T + P + F) + 6 * F + D + D + D + 6 + 6 + C_ + 2 * F + R) + F + 8
+    writes = 4 * (D + 9 + 6 + 6 * F + (1 if heading else 0) + H + 1 + R + 2 * F + O + D + D + 6) + F + 2 + 8
+    return reads, writes
+
+
+def case_for(config):
+    import common
+    return {"anymal_c_rough": "anymal_c_rough", "anymal_c_flat": "anymal_c_flat", "a1": "a1_rough", "a1_rough": "a1_rough",
+            "go2_rough": "go2_rough", "go2": "go2_rough"}[config], common
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+def cpu_reference_run(case, common, n_envs, steps, warmup, threads):
+    """The reference's torch-CPU implementation (oracle port) of the same step on the host cores."""
+    from oracle.legged_oracle import LeggedOracle
+    from extended_legged_gym_b200 import synthetic
+    torch.set_num_threads(threads)
+    cfg, spec, st = common.make_case_state(case, n_envs, seed=0)
+    hf = synthetic.make_height_field(seed=0)
+    ora = LeggedOracle(cfg, spec, st, hf)
+    for _ in range(warmup):
+        ora.hot_step()
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        ora.hot_step()
+        ts.append(time.perf_counter() - t0)
+    ts.sort()
+    med = ts[len(ts) // 2]
+    return n_envs / med, med, sum(ts)
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    case, common = case_for(args.config)
+    threads = os.cpu_count() or 1
+    steps = max(args.steps, 3)
+    value, med, _ = cpu_reference_run(case, common, args.envs, min(steps, 200), max(args.warmup, 3), threads)
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 200),
+            "warmup": max(args.warmup, 3), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config} post-physics step, {args.envs} envs, torch-CPU (oracle port of the reference)",
+                       "num_envs": args.envs},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"full workload: {args.envs} envs x {min(steps, 200)} steps, median step"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+# ----------------------------------------------------------------------------------------------
+def build_replicas(case, common, n_envs, n_rep, dev):
+    from extended_legged_gym_b200 import _lib, synthetic
+    from extended_legged_gym_b200.envs import LeggedRobot
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    hf = synthetic.make_height_field(seed=0).to(dev)
+    envs = []
+    for r in range(n_rep):
+        cfg, spec, st = common.make_case_state(case, n_envs, seed=r)
+        cfg.env.num_envs = n_envs
+        sim = SyntheticSim(cfg, n_envs, dev, spec=spec, height_samples=hf, state=st)
+        env = LeggedRobot(cfg, None, sim, dev, True)
+        env.set_env_state(st)
+        env.noise_u = None           # in-kernel Philox noise (0 algorithmic bytes)
+        env._sync_native()
+        envs.append(env)
+    return envs
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="anymal_c_rough")
+    ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
+    ap.add_argument("--e2e-steps", type=int, default=200)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    from extended_legged_gym_b200 import _lib
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = f"cuda:{local_rank}"
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device(dev))
+    W = max(args.warmup, 3)
+    K = args.steps
+    case, common = case_for(args.config)
+    lib = _lib.load()
+
+    n_envs = args.envs
+    probe = build_replicas(case, common, n_envs, 1, dev)[0]
+    D, F = probe.num_dof, len(probe.feet_indices)
+    P, T = len(probe.penalised_contact_indices), len(probe.termination_contact_indices)
+    H, O, C_ = probe.num_height_points, probe.num_obs, probe.cfg.commands.num_commands
+    R_terms = len(probe.reward_names)
+    rd, wr = algorithmic_bytes_per_env(D, F, P, T, H, O, R_terms, C_, probe.cfg.commands.heading_command)
+    hf_bytes = probe.height_samples.numel() * 2 if probe.height_samples is not None else 0
+    bytes_per_step = (rd + wr) * n_envs + hf_bytes
+    n_rep = max(2, -(-2 * L2_BYTES // bytes_per_step) + 1)
+    envs = [probe] + build_replicas(case, common, n_envs, n_rep, dev)[1:]
+    stream = torch.cuda.Stream(device=dev)
+
+    def enqueue(env, step, with_torques=True):
+        p = env._params
+        p.noise_mode, p.noise_offset, p.clip_observations = _lib.NOISE_PHILOX, step, 100.0
+        s = torch.cuda.current_stream(dev).cuda_stream
+        if with_torques:
+            rc = lib.elg_compute_torques(C.byref(env._dims), C.byref(p), env.actions.data_ptr(), env.dof_state.data_ptr(),
+                                         env.last_dof_vel.data_ptr(), env.p_gains.data_ptr(), env.d_gains.data_ptr(),
+                                         env.torque_limits.data_ptr(), env.default_dof_pos.data_ptr(), env.torques.data_ptr(), None, 0, s)
+            _lib.check(rc)
+        _lib.check(lib.elg_post_physics_step(C.byref(env._dims), C.byref(p), C.byref(env._bufs), _lib.PHASE_FUSED, s))
+
+    def capture(n_steps, with_torques):
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            for i in range(3):
+                enqueue(envs[i % n_rep], i, with_torques)
+            stream.synchronize()
+            with torch.cuda.graph(g, stream=stream):
+                for i in range(n_steps):
+                    enqueue(envs[i % n_rep], i, with_torques)
+        return g
+
+    def timed_replay(g, reps=1):
+        with torch.cuda.stream(stream):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            if dist:
+                dist.barrier()
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(reps):
+                g.replay()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            if dist:
+                dist.barrier()
+        return e0.elapsed_time(e1) * 1e-3
+
+    g_warm = capture(W, True)
+    g_full = capture(K, True)
+    g_step = capture(K, False)
+    timed_replay(g_warm)
+    with ClockSampler(local_rank) as clk:
+        t_full = timed_replay(g_full)
+        t_step_only = timed_replay(g_step)
+        # keep the sampler busy long enough to see clocks under load
+        t_more = [timed_replay(g_full) for _ in range(5)]
+    t_full = min([t_full] + t_more)
+    if dist:
+        tt = torch.tensor([t_full, t_step_only], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_full, t_step_only = tt.tolist()
+        # episode statistics: the one genuine reduction on this path
+        stats = torch.stack([probe._episode_sums_all.sum(dim=1).double().sum(), torch.tensor(float(n_envs), device=dev, dtype=torch.float64)])
+        dist.all_reduce(stats)
+    total_envs = n_envs * world
+    value = total_envs * K / t_full
+    ms_per_step = t_full / K * 1e3
+    peak, peak_src = peaks()
+    t_kernel = t_step_only / K
+    achieved = bytes_per_step / t_kernel / 1e9
+
+    # ---- e2e: public Python API, PhysX state in pinned host memory, H2D + D2H every step
+    env = envs[0]
+    host_in = {k: getattr(env, k).detach().cpu().pin_memory() for k in ("root_states", "dof_state", "rigid_body_state", "actions")}
+    host_in["contact_forces"] = env._contact_forces_flat.detach().cpu().pin_memory()
+    dev_in = {"root_states": env.root_states, "dof_state": env.dof_state, "rigid_body_state": env.rigid_body_state,
+              "actions": env.actions, "contact_forces": env._contact_forces_flat}
+    host_out = {"obs": torch.empty(n_envs, O).pin_memory(), "rew": torch.empty(n_envs).pin_memory(),
+                "reset": torch.empty(n_envs, dtype=torch.bool).pin_memory()}
+    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
+    d2h = sum(t.numel() * t.element_size() for t in host_out.values())
+    env.cfg.domain_rand.push_robots = False
+    env._obs_clip_for_step = 100.0
+
+    def e2e_step():
+        for k, t in host_in.items():
+            dev_in[k].copy_(t, non_blocking=True)
+        env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+        env.post_physics_step()
+        host_out["obs"].copy_(env.obs_buf, non_blocking=True)
+        host_out["rew"].copy_(env.rew_buf, non_blocking=True)
+        host_out["reset"].copy_(env.reset_buf, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(W):
+        e2e_step()
+    if dist:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    e1.record()
+    torch.cuda.synchronize()
+    t_e2e = e0.elapsed_time(e1) * 1e-3
+    if dist:
+        tt = torch.tensor([t_e2e], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        t_e2e = tt.item()
+    e2e_value = total_envs * args.e2e_steps / t_e2e
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config} post-physics step (torques+derive+heights+termination+rewards+obs+noise+history), "
+                               f"{n_envs} envs per GPU", "num_envs_per_gpu": n_envs, "num_envs_total": total_envs,
+                   "sharding": f"envs x{world}, no data-path collective", "height_points": H, "num_obs": O, "reward_terms": R_terms,
+                   "l2_policy": f"inputs larger than L2: {n_rep} state replicas x {bytes_per_step / 1e6:.1f} MB rotated per step",
+                   "noise": "in-kernel Philox4x32-10", "launch": "CUDA graph of K steps, 2 kernels per step"},
+        "gpu_launches": 2 * K,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
+                "ms_per_step": t_e2e / args.e2e_steps * 1e3, "api": "LeggedRobot._compute_torques + post_physics_step, pinned host state"},
+        "roofline": {"bound": "hbm", "kernel": "elg_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                     "algorithmic_bytes_per_launch": bytes_per_step, "bytes_per_env": rd + wr, "us_per_launch": t_kernel * 1e6,
+                     "frac_of_nominal_8TBs": achieved / 8000.0},
+        "clocks": clk.summary(),
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        v, med, tot = cpu_reference_run(case, common, n_envs, 20, 3, threads)
+        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                                "sample": f"full workload: {n_envs} envs x 20 steps (median step {med * 1e3:.1f} ms) of oracle/legged_oracle.py hot_step"}
+    if rank == 0:
+        print(json.dumps(line))
+    if dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

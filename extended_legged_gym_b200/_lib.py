@@ -1,0 +1,117 @@
+"""ctypes binding of ``include/elg_b200.h`` -- the thin layer between the Python host classes and
+the hand-written sm_100a kernels.  No CPU fallback: if the shared library is missing it is built
+(nvcc), and if that is impossible loading raises.
+"""
+import ctypes as C
+import os
+from typing import Optional
+
+from . import build as _build
+
+MAX_DOF, MAX_FEET, MAX_PENALISED, MAX_TERMINATION = 32, 8, 16, 8
+
+REWARD_TERMS = [
+    "action_rate", "ang_vel_xy", "base_foot_height", "base_height", "collision", "dof_acc", "dof_pos_limits", "dof_vel",
+    "dof_vel_limits", "feet_air_time", "feet_contact_forces", "feet_slip", "feet_stumble", "feet_stumble_liftup",
+    "four_footup", "gait_2_step", "gait_scheduler", "jump_air", "lin_vel_z", "orientation", "stand_still", "termination",
+    "torque_limits", "torques", "tracking_ang_vel", "tracking_lin_vel"]
+NUM_REWARD_TERMS = len(REWARD_TERMS)
+TERM_ID = {n: i for i, n in enumerate(REWARD_TERMS)}
+assert REWARD_TERMS == sorted(REWARD_TERMS)
+
+CONTROL_TYPES = {"P": 0, "V": 1, "T": 2}
+NOISE_OFF, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
+PHASE_PRE, PHASE_POST, PHASE_FUSED = 1, 2, 3
+
+
+class ElgDims(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("num_envs", "num_dof", "num_bodies", "num_feet", "num_penalised", "num_termination",
+                                          "num_height_points", "num_obs", "num_commands")] + [
+        ("feet_idx", C.c_int32 * MAX_FEET), ("penalised_idx", C.c_int32 * MAX_PENALISED),
+        ("termination_idx", C.c_int32 * MAX_TERMINATION)]
+
+
+class ElgStepParams(C.Structure):
+    _fields_ = [
+        ("dt", C.c_float), ("sim_dt", C.c_float), ("acc_ema", C.c_float), ("acc_ema_c", C.c_float),
+        ("max_episode_length", C.c_int64),
+        ("control_type", C.c_int32), ("action_scale", C.c_float),
+        ("heading_command", C.c_int32), ("measure_heights", C.c_int32), ("terrain_is_plane", C.c_int32),
+        ("only_positive_rewards", C.c_int32), ("noise_mode", C.c_int32), ("clip_observations", C.c_float),
+        ("gravity_vec", C.c_float * 3),
+        ("obs_scale_lin_vel", C.c_float), ("obs_scale_ang_vel", C.c_float), ("obs_scale_dof_pos", C.c_float),
+        ("obs_scale_dof_vel", C.c_float), ("obs_scale_height", C.c_float),
+        ("commands_scale", C.c_float * 3),
+        ("border_size", C.c_float), ("horizontal_scale", C.c_float), ("vertical_scale", C.c_float),
+        ("hf_rows", C.c_int32), ("hf_cols", C.c_int32), ("height_points_env_stride", C.c_int32),
+        ("reward_mask", C.c_uint32), ("reward_scales", C.c_float * NUM_REWARD_TERMS),
+        ("tracking_sigma", C.c_float), ("base_height_target", C.c_float), ("max_contact_force", C.c_float),
+        ("soft_dof_vel_limit", C.c_float), ("soft_torque_limit", C.c_float), ("speed_min", C.c_float),
+        ("stand_still_threshold", C.c_float),
+        ("gait_increment", C.c_float), ("gait_swing_height", C.c_float), ("gait_foot_phases", C.c_float * MAX_FEET),
+        ("noise_seed", C.c_uint64), ("noise_offset", C.c_uint64)]
+
+
+_BUF_FIELDS = [
+    "root_states", "dof_state", "contact_forces", "rigid_body_state", "actions", "torques", "default_dof_pos",
+    "dof_pos_limits", "dof_vel_limits", "torque_limits", "height_samples", "height_points", "noise_scale_vec", "noise_u",
+    "extra_reward",
+    "last_actions", "last_dof_vel", "last_root_vel", "base_lin_acc", "base_ang_acc", "commands", "feet_air_time",
+    "feet_contact_time", "last_contacts", "episode_length_buf", "episode_sums", "gait_idx", "gait_prev_foot_z",
+    "base_lin_vel", "base_ang_vel", "projected_gravity", "foot_positions", "foot_velocities", "measured_heights",
+    "reset_buf", "time_out_buf", "rew_buf", "obs_buf"]
+
+
+class ElgStepBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _BUF_FIELDS]
+
+
+class ElgError(RuntimeError):
+    pass
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load (building first if needed) the CUDA library; raises if it cannot be had."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = _build.LIB_PATH
+    if not os.path.exists(path) or os.environ.get("ELG_REBUILD") == "1":
+        path = _build.build()
+    lib = C.CDLL(path)
+    lib.elg_last_error.restype = C.c_char_p
+    lib.elg_reward_term_name.restype = C.c_char_p
+    lib.elg_reward_term_name.argtypes = [C.c_int]
+    for fn, st in (("elg_sizeof_dims", ElgDims), ("elg_sizeof_step_params", ElgStepParams), ("elg_sizeof_step_buffers", ElgStepBuffers)):
+        got = getattr(lib, fn)()
+        if got != C.sizeof(st):
+            raise ElgError(f"ABI mismatch: {fn}() = {got}, python mirror = {C.sizeof(st)}")
+    for i, name in enumerate(REWARD_TERMS):
+        if lib.elg_reward_term_name(i).decode() != name:
+            raise ElgError(f"reward registry mismatch at id {i}")
+    vp, i64 = C.c_void_p, C.c_int64
+    lib.elg_compute_torques.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 9 + [i64, vp]
+    lib.elg_post_physics_step.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams), C.POINTER(ElgStepBuffers), C.c_uint32, vp]
+    lib.elg_get_heights.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 5 + [vp]
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "") -> None:
+    if rc != 0:
+        msg = load().elg_last_error().decode()
+        if rc == -1 and "controller type" in msg:
+            raise NameError(msg)          # same exception type as the reference (legged_robot.py:447)
+        raise ElgError(f"{what or 'elg call'} failed ({rc}): {msg}")
+
+
+def ptr(t) -> Optional[int]:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

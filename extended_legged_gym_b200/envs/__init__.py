@@ -1,0 +1,13 @@
+"""Environment classes and configs on the hot path (mirrors ``legged_gym.envs`` for the BASELINE configs)."""
+from .base.legged_robot_config import LeggedRobotCfg, LeggedRobotCfgPPO
+from .base.legged_robot import LeggedRobot
+from .anymal_c.anymal_c_config import AnymalCRoughCfg, AnymalCRoughCfgPPO, AnymalCFlatCfg, AnymalCFlatCfgPPO
+from .a1.a1_config import A1RoughCfg, A1RoughCfgPPO
+from .go2.go2_config import Go2RoughCfg, Go2RoughCfgPPO
+
+TASKS = {
+    "anymal_c_rough": (LeggedRobot, AnymalCRoughCfg, AnymalCRoughCfgPPO),
+    "anymal_c_flat": (LeggedRobot, AnymalCFlatCfg, AnymalCFlatCfgPPO),
+    "a1": (LeggedRobot, A1RoughCfg, A1RoughCfgPPO),
+    "go2_rough": (LeggedRobot, Go2RoughCfg, Go2RoughCfgPPO),
+}

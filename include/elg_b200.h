@@ -1,0 +1,227 @@
+/*
+ * elg_b200.h -- C ABI of the B200-native per-step hot path of extended_legged_gym.
+ *
+ * The reference (MasterYip/extended_legged_gym) is pure Python and has no FFI layer of its
+ * own: its boundary is the Python class API.  This header is the
+ * boundary a maintainer binds from Python with ctypes: every entry
+ * point replaces one group of reference methods, cited below as file:line relative to
+ * legged_gym/legged_gym/ in the reference tree.
+ *
+ * Conventions
+ *   - extern "C", plain pointers and sizes; no torch / C++ types cross the boundary.
+ *   - every pointer is a DEVICE pointer borrowed from the caller (a torch tensor or a
+ *     PhysX-owned tensor); the library never allocates, frees or synchronises, except the
+ *     opaque mesh handle (elg_mesh_*) which owns its BVH.
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued on it and are CUDA
+ *     graph capturable (no host reads).
+ *   - return value: 0 on success, negative ElgStatus on error; elg_last_error() describes it.
+ *   - dtypes: fp32; int64 episode_length_buf; int16 height_samples; uint8 for torch.bool.
+ *   - quaternions are xyzw (Isaac Gym convention).
+ */
+#ifndef ELG_B200_H
+#define ELG_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ELG_ABI_VERSION 1
+
+#define ELG_MAX_DOF 32
+#define ELG_MAX_FEET 8
+#define ELG_MAX_PENALISED 16
+#define ELG_MAX_TERMINATION 8
+
+typedef enum ElgStatus {
+  ELG_OK = 0,
+  ELG_ERR_INVALID_ARGUMENT = -1,
+  ELG_ERR_UNSUPPORTED = -2,
+  ELG_ERR_CUDA = -3,
+  ELG_ERR_NULL_POINTER = -4
+} ElgStatus;
+
+/* Reward registry: ids are the ALPHABETICAL order of the reference's `_reward_*` names, which is
+ * the order `class_to_dict(cfg.rewards.scales)` yields and therefore the fp32 summation order of
+ * compute_reward (utils/helpers.py:43-58, envs/base/legged_robot.py:215-232,
+ * envs/base/legged_robot_rew_mixin.py:41-234, envs/anymal_c/anymal.py:112-114). */
+typedef enum ElgRewardTerm {
+  ELG_REW_ACTION_RATE = 0,
+  ELG_REW_ANG_VEL_XY,
+  ELG_REW_BASE_FOOT_HEIGHT,
+  ELG_REW_BASE_HEIGHT,
+  ELG_REW_COLLISION,
+  ELG_REW_DOF_ACC,
+  ELG_REW_DOF_POS_LIMITS,
+  ELG_REW_DOF_VEL,
+  ELG_REW_DOF_VEL_LIMITS,
+  ELG_REW_FEET_AIR_TIME,
+  ELG_REW_FEET_CONTACT_FORCES,
+  ELG_REW_FEET_SLIP,
+  ELG_REW_FEET_STUMBLE,
+  ELG_REW_FEET_STUMBLE_LIFTUP,
+  ELG_REW_FOUR_FOOTUP,
+  ELG_REW_GAIT_2_STEP,
+  ELG_REW_GAIT_SCHEDULER,
+  ELG_REW_JUMP_AIR,
+  ELG_REW_LIN_VEL_Z,
+  ELG_REW_ORIENTATION,
+  ELG_REW_STAND_STILL,
+  ELG_REW_TERMINATION, /* added after the only-positive clip (legged_robot.py:228-232) */
+  ELG_REW_TORQUE_LIMITS,
+  ELG_REW_TORQUES,
+  ELG_REW_TRACKING_ANG_VEL,
+  ELG_REW_TRACKING_LIN_VEL,
+  ELG_NUM_REWARD_TERMS
+} ElgRewardTerm;
+
+/* returns the reference name of a term ("action_rate", ...) or NULL */
+const char* elg_reward_term_name(int term);
+
+typedef enum ElgControlType { ELG_CONTROL_P = 0, ELG_CONTROL_V = 1, ELG_CONTROL_T = 2 } ElgControlType;
+
+typedef enum ElgNoiseMode {
+  ELG_NOISE_OFF = 0,    /* cfg.noise.add_noise == False */
+  ELG_NOISE_TENSOR = 1, /* uniform [0,1) samples supplied by the caller (parity mode, = torch.rand_like) */
+  ELG_NOISE_PHILOX = 2  /* generated in-kernel: Philox4x32-10 keyed by (seed, step), counter (env, obs/4) */
+} ElgNoiseMode;
+
+/* Sections of post_physics_step (legged_robot.py:113-150), OR-ed into `phase`.  The reset path
+ * (reset_idx, host side) sits between ELG_PHASE_PRE and ELG_PHASE_POST. */
+#define ELG_PHASE_DERIVE 1u       /* episode counter, base-frame state, feet gather, heading cmd, heights (:122-139) */
+#define ELG_PHASE_TERMINATION 2u  /* check_termination (:155-160) */
+#define ELG_PHASE_REWARD 4u       /* compute_reward + registry (:215-232) */
+#define ELG_PHASE_OBS 8u          /* compute_observations (+noise, +clip) (:234-252) */
+#define ELG_PHASE_HISTORY 16u     /* last_actions / last_dof_vel / last_root_vel (:148-150) */
+#define ELG_PHASE_PRE (ELG_PHASE_DERIVE | ELG_PHASE_TERMINATION | ELG_PHASE_REWARD)
+#define ELG_PHASE_POST (ELG_PHASE_OBS | ELG_PHASE_HISTORY)
+#define ELG_PHASE_FUSED (ELG_PHASE_PRE | ELG_PHASE_POST)
+
+typedef struct ElgDims {
+  int32_t num_envs;          /* N */
+  int32_t num_dof;           /* D  (== num_actions) */
+  int32_t num_bodies;        /* B */
+  int32_t num_feet;          /* F */
+  int32_t num_penalised;     /* P */
+  int32_t num_termination;   /* T */
+  int32_t num_height_points; /* H (0 when cfg.terrain.measure_heights is False) */
+  int32_t num_obs;           /* O */
+  int32_t num_commands;      /* C */
+  int32_t feet_idx[ELG_MAX_FEET];
+  int32_t penalised_idx[ELG_MAX_PENALISED];
+  int32_t termination_idx[ELG_MAX_TERMINATION];
+} ElgDims;
+
+/* cfg scalars baked by the host (legged_robot.py:_parse_cfg :847-860, _prepare_reward_function :649-674) */
+typedef struct ElgStepParams {
+  float dt;                  /* control.decimation * sim.dt */
+  float sim_dt;
+  float acc_ema;             /* 0.9 (legged_robot.py:85) */
+  float acc_ema_c;           /* fp32(1 - acc_ema), evaluated in double like the Python expression */
+  int64_t max_episode_length; /* floor(np.ceil(episode_length_s / dt)); time_out = ep_len > this */
+  int32_t control_type;      /* ElgControlType */
+  float action_scale;
+  int32_t heading_command;
+  int32_t measure_heights;
+  int32_t terrain_is_plane;  /* mesh_type == 'plane' -> heights are zeros (legged_robot.py:913-914) */
+  int32_t only_positive_rewards;
+  int32_t noise_mode;        /* ElgNoiseMode */
+  float clip_observations;   /* <= 0: no clip; > 0: step()'s clip fused (legged_robot.py:107-108) */
+  float gravity_vec[3];      /* normalised gravity, (0,0,-1) */
+  float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_dof_pos, obs_scale_dof_vel, obs_scale_height;
+  float commands_scale[3];
+  /* terrain (legged_robot.py:925-938) */
+  float border_size, horizontal_scale, vertical_scale;
+  int32_t hf_rows, hf_cols;
+  int32_t height_points_env_stride; /* 0: one [H,3] grid shared by all envs; else elements between envs */
+  /* rewards */
+  uint32_t reward_mask;                    /* bit t set <=> term t has a non-zero scale */
+  float reward_scales[ELG_NUM_REWARD_TERMS]; /* fp32(scale * dt) */
+  float tracking_sigma, base_height_target, max_contact_force;
+  float soft_dof_vel_limit, soft_torque_limit, speed_min;
+  float stand_still_threshold;             /* speed_min in the base mixin (:221) */
+  /* gait scheduler (utils/gait_scheduler.py:63-81, anymal.py:60-66) */
+  float gait_increment;      /* fp32(dt / period) */
+  float gait_swing_height;
+  float gait_foot_phases[ELG_MAX_FEET];
+  /* in-kernel noise */
+  uint64_t noise_seed;
+  uint64_t noise_offset;     /* step counter, so successive steps draw fresh numbers */
+} ElgStepParams;
+
+typedef struct ElgStepBuffers {
+  /* ---- PhysX-owned state, read only (legged_robot.py:575-584) ---- */
+  const float* root_states;      /* [N,13] */
+  const float* dof_state;        /* [N*D,2] */
+  const float* contact_forces;   /* [N*B,3] */
+  const float* rigid_body_state; /* [N*B,13] */
+  /* ---- per-step inputs ---- */
+  const float* actions;          /* [N,D] */
+  const float* torques;          /* [N,D] (output of elg_compute_torques) */
+  const float* default_dof_pos;  /* [D] */
+  const float* dof_pos_limits;   /* [D,2] */
+  const float* dof_vel_limits;   /* [D] */
+  const float* torque_limits;    /* [D] */
+  const int16_t* height_samples; /* [rows, cols] or NULL */
+  const float* height_points;    /* [H,3] (or [N,H,3] with height_points_env_stride) or NULL */
+  const float* noise_scale_vec;  /* [O] or NULL */
+  const float* noise_u;          /* [N,O] uniform samples for ELG_NOISE_TENSOR, else NULL */
+  const float* extra_reward;     /* [N] pre-scaled sum of user-defined Python terms, added before the clip; or NULL */
+  /* ---- env-owned state, read + written ---- */
+  float* last_actions;           /* [N,D] */
+  float* last_dof_vel;           /* [N,D] */
+  float* last_root_vel;          /* [N,6] */
+  float* base_lin_acc;           /* [N,3] */
+  float* base_ang_acc;           /* [N,3] */
+  float* commands;               /* [N,C] */
+  float* feet_air_time;          /* [N,F] */
+  float* feet_contact_time;      /* [N,F] */
+  uint8_t* last_contacts;        /* [N,F] bool */
+  int64_t* episode_length_buf;   /* [N] */
+  float* episode_sums;           /* [ELG_NUM_REWARD_TERMS, N]; row t only touched if term t enabled */
+  float* gait_idx;               /* [N] or NULL */
+  float* gait_prev_foot_z;       /* [N,F] foot z handed to GaitScheduler.step last step, or NULL */
+  /* ---- outputs ---- */
+  float* base_lin_vel;           /* [N,3] */
+  float* base_ang_vel;           /* [N,3] */
+  float* projected_gravity;      /* [N,3] */
+  float* foot_positions;         /* [N,F,3] */
+  float* foot_velocities;        /* [N,F,3] */
+  float* measured_heights;       /* [N,H] or NULL */
+  uint8_t* reset_buf;            /* [N] bool */
+  uint8_t* time_out_buf;         /* [N] bool */
+  float* rew_buf;                /* [N] */
+  float* obs_buf;                /* [N,O] */
+} ElgStepBuffers;
+
+/* ABI self-description so the Python mirror structs can be checked at load time */
+int elg_abi_version(void);
+int elg_sizeof_dims(void);
+int elg_sizeof_step_params(void);
+int elg_sizeof_step_buffers(void);
+const char* elg_last_error(void);
+
+/* LeggedRobot._compute_torques (envs/base/legged_robot.py:425-448; rollout twin
+ * envs/batch_rollout/robot_batch_rollout.py:1016-1037).  dof_state is the interleaved [N*D,2]
+ * PhysX tensor (dof_pos/dof_vel are its stride-2 views).  env_ids == NULL: all N envs;
+ * otherwise num_ids rows selected by int64 index (rollout variant). */
+int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const float* actions, const float* dof_state,
+                        const float* last_dof_vel, const float* p_gains, const float* d_gains, const float* torque_limits,
+                        const float* default_dof_pos, float* torques, const int64_t* env_ids, int64_t num_ids, void* stream);
+
+/* LeggedRobot.post_physics_step body (envs/base/legged_robot.py:122-150) with
+ * _post_physics_step_callback's heading + heights (:394-401), check_termination (:155-160),
+ * compute_reward (:215-232) + the _reward_* registry, compute_observations (:234-252) and the
+ * history copies (:148-150), as ONE kernel.  `phase` is an OR of ELG_PHASE_* sections. */
+int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const ElgStepBuffers* buf, uint32_t phase, void* stream);
+
+/* LeggedRobot._get_heights (envs/base/legged_robot.py:900-938), standalone. cells_out (optional,
+ * int32 [N,H,2]) receives the clipped (px, py) terrain cell of every point for index parity tests. */
+int elg_get_heights(const ElgDims* dims, const ElgStepParams* prm, const float* root_states, const int16_t* height_samples,
+                    const float* height_points, float* measured_heights, int32_t* cells_out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* ELG_B200_H */
