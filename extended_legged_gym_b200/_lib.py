@@ -21,7 +21,10 @@ assert REWARD_TERMS == sorted(REWARD_TERMS)
 
 CONTROL_TYPES = {"P": 0, "V": 1, "T": 2}
 NOISE_OFF, NOISE_TENSOR, NOISE_PHILOX = 0, 1, 2
-PHASE_PRE, PHASE_POST, PHASE_FUSED = 1, 2, 3
+PHASE_DERIVE, PHASE_TERMINATION, PHASE_REWARD, PHASE_OBS, PHASE_HISTORY = 1, 2, 4, 8, 16
+PHASE_PRE = PHASE_DERIVE | PHASE_TERMINATION | PHASE_REWARD
+PHASE_POST = PHASE_OBS | PHASE_HISTORY
+PHASE_FUSED = PHASE_PRE | PHASE_POST
 
 
 class ElgDims(C.Structure):

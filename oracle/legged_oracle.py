@@ -346,20 +346,7 @@ class LeggedOracle:
         # terrain bookkeeping used by reset_idx (legged_robot.py:817-844)
         self.base_init_state = torch.tensor(cfg.init_state.pos + cfg.init_state.rot + cfg.init_state.lin_vel + cfg.init_state.ang_vel,
                                             dtype=torch.float)
-        self.custom_origins = cfg.terrain.mesh_type in ("heightfield", "trimesh", "confined_trimesh")
-        self.env_origins = torch.zeros(N, 3)
-        if self.custom_origins:
-            nrow, ncol = cfg.terrain.num_rows, cfg.terrain.num_cols
-            g = torch.Generator().manual_seed(1234)
-            to = torch.zeros(nrow, ncol, 3)
-            to[..., 0] = (torch.arange(nrow).float().view(-1, 1) + 0.5) * cfg.terrain.terrain_length
-            to[..., 1] = (torch.arange(ncol).float().view(1, -1) + 0.5) * cfg.terrain.terrain_width
-            self.terrain_origins = to
-            self.max_terrain_level = nrow
-            self.terrain_levels = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (N,), generator=g)
-            self.terrain_types = torch.div(torch.arange(N), (N / ncol), rounding_mode="floor").to(torch.long)
-            self.env_origins = self.terrain_origins[self.terrain_levels, self.terrain_types].clone()
-            self.env_length = cfg.terrain.terrain_length
+        self._get_env_origins()
         # gait scheduler (anymal.py:60-79, gait_scheduler.py)
         self.use_gait_scheduler = use_gait_scheduler
         if use_gait_scheduler:
@@ -368,6 +355,36 @@ class LeggedOracle:
             self.gait_phases = [torch.remainder(self.gait_idx + p, 1.0) for p in self.gait_cfg.foot_phases]
             self.gait_foot_pos = self.foot_positions
         self.prepare_reward_function()
+
+    # ---- env origins (legged_robot.py:817-844); terrain tile centres follow the synthetic contract of
+    # oracle/ref_harness.synthetic_terrain_origins; levels are drawn from a forked, seeded global RNG
+    def _get_env_origins(self):
+        cfg, N = self.cfg, self.num_envs
+        self.env_origins = torch.zeros(N, 3)
+        if cfg.terrain.mesh_type in ("heightfield", "trimesh", "confined_trimesh"):
+            self.custom_origins = True
+            nrow, ncol = cfg.terrain.num_rows, cfg.terrain.num_cols
+            to = torch.zeros(nrow, ncol, 3)
+            to[..., 0] = (torch.arange(nrow).float().view(-1, 1) + 0.5) * cfg.terrain.terrain_length
+            to[..., 1] = (torch.arange(ncol).float().view(1, -1) + 0.5) * cfg.terrain.terrain_width
+            max_init = cfg.terrain.max_init_terrain_level if cfg.terrain.curriculum else nrow - 1
+            with torch.random.fork_rng():
+                torch.manual_seed(1234)
+                self.terrain_levels = torch.randint(0, max_init + 1, (N,))
+            self.terrain_types = torch.div(torch.arange(N), (N / ncol), rounding_mode="floor").to(torch.long)
+            self.max_terrain_level = nrow
+            self.terrain_origins = to
+            self.env_origins[:] = self.terrain_origins[self.terrain_levels, self.terrain_types]
+            self.env_length = cfg.terrain.terrain_length
+        else:
+            self.custom_origins = False
+            num_cols = np.floor(np.sqrt(N))
+            num_rows = np.ceil(N / num_cols)
+            xx, yy = torch.meshgrid(torch.arange(num_rows), torch.arange(num_cols), indexing="ij")
+            spacing = cfg.env.env_spacing
+            self.env_origins[:, 0] = spacing * xx.flatten()[:N]
+            self.env_origins[:, 1] = spacing * yy.flatten()[:N]
+            self.env_origins[:, 2] = 0.0
 
     # ---- reward bookkeeping (legged_robot_rew_mixin.py:15-38, legged_robot.py:649-674) -------
     def _stage_scales(self, stage):

@@ -107,6 +107,16 @@ def reference_classes():
 # ---------------------------------------------------------------------------------------------
 # Reference env on synthetic state: the reference's OWN LeggedRobot methods on a synthetic self
 # ---------------------------------------------------------------------------------------------
+def synthetic_terrain_origins(cfg):
+    """[rows, cols, 3] tile centres, the data contract of Terrain.env_origins (utils/terrain.py)."""
+    import torch
+    nrow, ncol = cfg.terrain.num_rows, cfg.terrain.num_cols
+    to = torch.zeros(nrow, ncol, 3)
+    to[..., 0] = (torch.arange(nrow).float().view(-1, 1) + 0.5) * cfg.terrain.terrain_length
+    to[..., 1] = (torch.arange(ncol).float().view(1, -1) + 0.5) * cfg.terrain.terrain_width
+    return to
+
+
 def make_reference_env(cfg, spec, state, height_samples=None, cls=None, terrain_origins=None):
     """Build an instance of the reference ``LeggedRobot`` (or subclass ``cls``) WITHOUT PhysX.
 
@@ -176,24 +186,15 @@ def make_reference_env(cfg, spec, state, height_samples=None, cls=None, terrain_
     if mesh_type in ("heightfield", "trimesh", "confined_trimesh"):
         assert height_samples is not None
         env.height_samples = height_samples
-        env.terrain = _types.SimpleNamespace(cfg=cfg.terrain, env_length=cfg.terrain.terrain_length,
-                                             env_width=cfg.terrain.terrain_width)
-        env.custom_origins = True
-        g = torch.Generator().manual_seed(1234)
         nrow, ncol = cfg.terrain.num_rows, cfg.terrain.num_cols
         if terrain_origins is None:
-            to = torch.zeros(nrow, ncol, 3)
-            to[..., 0] = (torch.arange(nrow).float().view(-1, 1) + 0.5) * cfg.terrain.terrain_length
-            to[..., 1] = (torch.arange(ncol).float().view(1, -1) + 0.5) * cfg.terrain.terrain_width
-            terrain_origins = to
-        env.terrain_origins = terrain_origins
-        env.max_terrain_level = nrow
-        env.terrain_levels = torch.randint(0, cfg.terrain.max_init_terrain_level + 1, (N,), generator=g)
-        env.terrain_types = torch.div(torch.arange(N), (N / ncol), rounding_mode="floor").to(torch.long)
-        env.env_origins = env.terrain_origins[env.terrain_levels, env.terrain_types].clone()
-    else:
-        env.custom_origins = False
-        env.env_origins = torch.zeros(N, 3)
+            terrain_origins = synthetic_terrain_origins(cfg)
+        env.terrain = _types.SimpleNamespace(cfg=cfg.terrain, env_length=cfg.terrain.terrain_length,
+                                             env_width=cfg.terrain.terrain_width, env_origins=terrain_origins.numpy())
+    # the reference's own _get_env_origins (legged_robot.py:817-844); it draws terrain levels from the global RNG
+    with torch.random.fork_rng():
+        torch.manual_seed(1234)
+        env._get_env_origins()
     # --- the reference's own _init_buffers with acquire_* returning the synthetic tensors
     env.gym.acquire_actor_root_state_tensor.return_value = state["root_states"]
     env.gym.acquire_dof_state_tensor.return_value = state["dof_state"]
