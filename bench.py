@@ -252,11 +252,12 @@ def main():
     g_step = capture(K, False)
     timed_replay(g_warm)
     with ClockSampler(local_rank) as clk:
-        t_full = timed_replay(g_full)
-        t_step_only = timed_replay(g_step)
-        # keep the sampler busy long enough to see clocks under load
-        t_more = [timed_replay(g_full) for _ in range(5)]
-    t_full = min([t_full] + t_more)
+        timed_replay(g_full)          # first replay uploads the graph; not a measurement
+        timed_replay(g_step)
+        # several replays keep the sampler busy long enough to see clocks under load; the median is reported
+        t_fulls = sorted(timed_replay(g_full) for _ in range(7))
+        t_steps = sorted(timed_replay(g_step) for _ in range(7))
+    t_full, t_step_only = t_fulls[len(t_fulls) // 2], t_steps[len(t_steps) // 2]
     if dist:
         tt = torch.tensor([t_full, t_step_only], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)

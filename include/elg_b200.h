@@ -216,6 +216,11 @@ int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const flo
  * history copies (:148-150), as ONE kernel.  `phase` is an OR of ELG_PHASE_* sections. */
 int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const ElgStepBuffers* buf, uint32_t phase, void* stream);
 
+/* Launch-geometry override of elg_post_physics_step for benchmarking sweeps (no reference counterpart):
+ * envs per chunk (multiple of 4, <= 32), threads per CTA, CTAs per SM; disable_bulk != 0 forces the
+ * element-wise staging path instead of TMA bulk copies.  envs_per_chunk == 0 restores the built-in choice. */
+int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm, int disable_bulk);
+
 /* LeggedRobot._get_heights (envs/base/legged_robot.py:900-938), standalone. cells_out (optional,
  * int32 [N,H,2]) receives the clipped (px, py) terrain cell of every point for index parity tests. */
 int elg_get_heights(const ElgDims* dims, const ElgStepParams* prm, const float* root_states, const int16_t* height_samples,
