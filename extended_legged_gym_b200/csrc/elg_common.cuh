@@ -94,8 +94,9 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-// The uniform sample attached to observation element (env, k) at step `offset`:
-// counter = (env, k mod 32 + 32*(k div 128), offset_lo, offset_hi), key = seed; word = (k div 32) mod 4.
+// The uniform sample attached to observation element (env, k) at step `offset`: with the noise index
+// k' = k for the head (k < 12 + 3D) and 32*ceil(head/32) + p for height point p,
+// counter = (env, k' mod 32 + 32*(k' div 128), offset_lo, offset_hi), key = seed; word = (k' div 32) mod 4.
 __device__ __forceinline__ uint4 noise_block(uint64_t seed, uint64_t offset, uint32_t env, uint32_t lane, uint32_t chunk) {
   return philox4x32_10(make_uint4(env, lane | (chunk << 5), (uint32_t)offset, (uint32_t)(offset >> 32)),
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

@@ -3,21 +3,26 @@
 // One launch of elg_step_kernel replaces the ~100 ATen launches of
 // LeggedRobot.post_physics_step (envs/base/legged_robot.py:113-150 in the reference).
 //
-// Design (v2, see DESIGN.md "step kernel"):
+// Design (v3, see DESIGN.md "step kernel"):
 //   * The environments are cut into CHUNKS of whole quads (4 envs), balanced so that every SM gets
-//     the same number of quads to within one: 4096 envs -> 148 chunks of 24..28 envs, one
-//     1024-thread CTA per SM.  Large N: 256-thread CTAs, 4 per SM, each looping over 16-env chunks.
-//   * TMA in, TMA out.  Because the envs of a chunk are consecutive, every per-env array is ONE
-//     contiguous global range per chunk: thread 0 issues one cp.async.bulk (global -> shared,
-//     mbarrier completion) per input array and, at the end, one cp.async.bulk (shared -> global)
-//     per output array -- including the whole [nenv, 235] observation block and the [nenv, 187]
-//     height block.  The compute code only touches shared memory.
-//   * "state warps" (one per 8 envs) run the O(D + F + B)-per-env work as FLAT (env, item) loops --
-//     (env, rotation), (env, dof), (env, foot), (env, body) -- so every phase uses all 32 lanes;
-//     per-env reductions go through a per-warp shared scratch.  "row warps" (one env at a time)
-//     run the 187-point terrain scan and assemble the observation row; the x/y halves of the
-//     terrain-cell chain are evaluated with the packed FMUL2/FADD2/FFMA2 instructions of sm_100a,
-//     every op individually IEEE-rounded so the cell index stays bit-exact with torch.
+//     the same number of quads to within one: 4096 envs -> 148 chunks of 24..28 envs, one CTA per
+//     SM with one WARP PER ENVIRONMENT.  Large N: 512-thread CTAs, 2 per SM, each looping over
+//     16-env chunks.
+//   * TMA in, TMA out.  The envs of a chunk are consecutive, so every per-env array is ONE
+//     contiguous global range per chunk.  The host builds two copy tables (global base, shared
+//     offset, bytes per env); a chunk is cut into SUB-CHUNKS of 8 envs, each with its own mbarrier:
+//     the first warp of a sub-chunk issues one cp.async.bulk (global -> shared) per table entry,
+//     one entry per lane, and -- once the 8 warps of the sub-chunk have met at a named barrier --
+//     one cp.async.bulk (shared -> global) per output entry, including the [8, 235] observation
+//     block and the [8, 187] height block.  Sub-chunks load, compute and store independently, so
+//     the DRAM latency of one overlaps the arithmetic of the others; no CTA-wide barrier sits
+//     between staging and write-back.
+//   * A warp runs its environment end to end out of shared memory: the 187-point terrain scan
+//     (points lane + 32 j, unrolled by 3 so 9 height-field gathers are in flight per lane; the
+//     x/y halves of the terrain-cell chain use the packed FMUL2/FADD2/FFMA2 of sm_100a, every op
+//     individually IEEE-rounded so the cell index stays bit-exact with torch), then the
+//     O(D + F + B) state work with lane = item (rotation, dof, foot, body) and shuffle
+//     reductions, then the observation row (noise from in-register Philox4x32-10, clip).
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -26,11 +31,12 @@
 
 namespace elg {
 
-constexpr int kGroup = 8;         // environments per state warp
-constexpr int kMaxCap = 32;       // environments per chunk (multiple of 4)
+constexpr int kMaxCap = 32;       // environments per chunk (multiple of 4) == warps per CTA
+constexpr int kSub = 8;           // environments per sub-chunk (own mbarrier, own store group)
+constexpr int kMaxSub = kMaxCap / kSub;
 constexpr int kMaxStepThreads = 1024;
-constexpr int kFeetQ = 10;        // per-foot partial quantities
-constexpr int kDofQ = 8;          // per-dof partial quantities
+constexpr int kMaxIn = 30 + ELG_NUM_REWARD_TERMS;
+constexpr int kMaxOut = 24 + ELG_NUM_REWARD_TERMS;
 
 __device__ __forceinline__ bool term_on(const ElgStepParams& pr, int t) { return (pr.reward_mask >> t) & 1u; }
 
@@ -110,88 +116,28 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// observation post-processing shared by head and height entries (legged_robot.py:250-252, :107-108)
+// shared-memory plan of one chunk, built by the host (elg_post_physics_step below).
+// Offsets are BYTES from the start of dynamic shared memory; every region starts 128-byte aligned.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ float finish_obs(float v, float u, float ns, const ElgStepParams& pr) {
-  if (pr.noise_mode != ELG_NOISE_OFF) v = v + (2.0f * u - 1.0f) * ns;
-  if (pr.clip_observations > 0.0f) v = fminf(fmaxf(v, -pr.clip_observations), pr.clip_observations);
-  return v;
-}
-
-// ---------------------------------------------------------------------------------------------
-// shared-memory plan of one chunk (word offsets; every region starts 16-byte aligned)
-// ---------------------------------------------------------------------------------------------
-struct StepPlan {
-  // staged per-env arrays, [slot][per-env]
-  int root, dof, act, lact, ldv, tq, cf, lrv, vec5, cmd, air, con, lc, ep, gidx, gprev, fpos, fvel;
-  int head, hsum, sums, accs, rew, mh, obs;
-  // CTA-constant tables
-  int q0, plim, vlim, tlim, ns, grid;
-  int scratch, scratch_words;   // per state warp
-  int part_d, part_f;           // pitches inside the scratch
-  int words;
-  // launch geometry
-  int cap, nchunks, nstate, use_bulk, obs_smem, nterms, head_pitch;
-  int8_t term_ids[ELG_NUM_REWARD_TERMS];
+struct CopyDesc {
+  const void* g;   // global base of the array (env 0)
+  int32_t soff;    // shared-memory byte offset of slot 0
+  int32_t bpe;     // bytes per environment
 };
 
-inline int up4(int w) { return (w + 3) & ~3; }
-
-inline StepPlan make_plan(const ElgDims& d, const ElgStepParams& pr, int cap, int nstate, bool obs_smem) {
-  StepPlan L{};
-  const int D = d.num_dof, F = d.num_feet, H = d.num_height_points, O = d.num_obs, B = d.num_bodies, C = d.num_commands;
-  L.cap = cap;
-  L.nstate = nstate;
-  L.obs_smem = obs_smem ? 1 : 0;
-  int nt = 0;
-  for (int t = 0; t < ELG_NUM_REWARD_TERMS; ++t)
-    if ((pr.reward_mask >> t) & 1u) L.term_ids[nt++] = (int8_t)t;
-  L.nterms = nt;
-  const int head = 12 + 3 * D;
-  L.head_pitch = head | 1;   // odd pitch: per-env lanes write columns without bank conflicts
-  int o = 0;
-  auto take = [&](int words) { const int at = o; o += up4(words); return at; };
-  L.root = take(cap * 13);
-  L.dof = take(cap * 2 * D);
-  L.act = take(cap * D);
-  L.lact = take(cap * D);
-  L.ldv = take(cap * D);
-  L.tq = take(cap * D);
-  L.cf = take(cap * B * 3);
-  L.lrv = take(cap * 6);
-  L.vec5 = take(5 * cap * 3);           // base_lin_vel, base_ang_vel, projected_gravity, base_lin_acc, base_ang_acc
-  L.cmd = take(cap * C);
-  L.air = take(cap * F);
-  L.con = take(cap * F);
-  L.lc = take((cap * F + 3) / 4);       // bytes
-  L.ep = take(cap * 2);                 // int64
-  L.gidx = take(cap);
-  L.gprev = take(cap * F);
-  L.fpos = take(cap * F * 3);
-  L.fvel = take(cap * F * 3);
-  L.head = take(cap * L.head_pitch);
-  L.hsum = take(cap);
-  L.sums = take((nt > 0 ? nt : 1) * cap);
-  L.accs = take(ELG_NUM_REWARD_TERMS * cap);
-  L.rew = take(cap);
-  L.mh = take(cap * H);
-  L.obs = take(obs_smem ? cap * O : 0);
-  L.q0 = take(D);
-  L.plim = take(2 * D);
-  L.vlim = take(D);
-  L.tlim = take(D);
-  L.ns = take(O);
-  L.grid = take(4 * H);
-  L.part_d = kGroup * D + 1;
-  L.part_f = kGroup * F + 1;
-  int part = kDofQ * L.part_d;
-  if (kFeetQ * L.part_f > part) part = kFeetQ * L.part_f;
-  if (kGroup * (d.num_penalised + d.num_termination) > part) part = kGroup * (d.num_penalised + d.num_termination);
-  L.scratch_words = up4(part + kFeetQ * kGroup + ELG_NUM_REWARD_TERMS * kGroup);
-  L.scratch = take(nstate * L.scratch_words);
-  L.words = o;
-  return L;
-}
+struct StepPlan {
+  // staged per-env arrays, [slot][per-env]
+  int root, dof, act, lact, ldv, tq, cf, lrv, vec5, cmd, air, con, lc, ep, gidx, gprev, fpos, fvel, sums, rew, mh, obs;
+  // CTA-constant tables and per-warp scratch
+  int q0, plim, vlim, tlim, ns, grid, acc;
+  int bytes;
+  // launch geometry
+  int cap, nchunks, quads_base, quads_rem, use_bulk, obs_smem, nterms, hm;
+  int n_in, n_out, in_bpe;
+  int8_t term_ids[ELG_NUM_REWARD_TERMS];
+  CopyDesc in[kMaxIn];
+  CopyDesc out[kMaxOut];
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
@@ -224,7 +170,10 @@ __device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t by
 }
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // cooperative fallback copies (ragged tail chunk or unaligned caller tensors)
 __device__ __forceinline__ void coop_copy(void* dst, const void* src, uint32_t bytes, int tid, int nthreads) {
@@ -239,53 +188,104 @@ __device__ __forceinline__ void coop_copy(void* dst, const void* src, uint32_t b
   }
 }
 
-// floor(i / d) for 0 <= i < 1024, 1 <= d <= 64
-struct FastDiv {
-  uint32_t m;
-  __device__ explicit FastDiv(int d) : m((65536u + (uint32_t)d - 1u) / (uint32_t)(d > 0 ? d : 1)) {}
-  __device__ __forceinline__ int div(int i) const { return (int)(((uint32_t)i * m) >> 16); }
-};
+// butterfly sums: lane 0 (indeed every lane below the width) ends up with the total of lanes [0, W)
+template <int W>
+__device__ __forceinline__ float bfly_sum(float v) {
+#pragma unroll
+  for (int o = W / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float lanes_sum(float v, int n) {   // n = number of contributing lanes (others hold 0)
+  if (n > 16) return bfly_sum<32>(v);
+  if (n > 8) return bfly_sum<16>(v);
+  if (n > 4) return bfly_sum<8>(v);
+  return bfly_sum<4>(v);
+}
+
+// observation post-processing shared by head and height entries (legged_robot.py:250-252, :107-108)
+__device__ __forceinline__ float finish_obs(float v, float u, float ns, int noise_mode, float clip) {
+  if (noise_mode != ELG_NOISE_OFF) v = v + (2.0f * u - 1.0f) * ns;
+  if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
+  return v;
+}
 
 // ---------------------------------------------------------------------------------------------
-// the fused kernel
+// the fused kernel.  kD / kF > 0 fix the DOF / foot count at compile time (12 / 4 for every
+// quadruped of the BASELINE configs); 0 = take them from ElgDims.
 // ---------------------------------------------------------------------------------------------
+template <int kD, int kF>
 __global__ void __launch_bounds__(kMaxStepThreads, 1)
 elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgStepParams pr,
                 const __grid_constant__ ElgStepBuffers bf, const __grid_constant__ StepPlan L, const uint32_t phase) {
-  extern __shared__ __align__(128) float smem[];
-  __shared__ __align__(8) uint64_t s_bar;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t s_bar[kMaxSub];
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
-  const int nstate = L.nstate, nrow = nwarps - nstate;
-  const int N = dm.num_envs, D = dm.num_dof, B = dm.num_bodies, F = dm.num_feet, H = dm.num_height_points;
-  const int O = dm.num_obs, C = dm.num_commands, P = dm.num_penalised, T = dm.num_termination;
+  const int nthreads = blockDim.x;
+  const int N = dm.num_envs, D = kD ? kD : dm.num_dof, B = dm.num_bodies, F = kF ? kF : dm.num_feet;
+  const int H = dm.num_height_points, O = dm.num_obs, C = dm.num_commands, P = dm.num_penalised, T = dm.num_termination;
   const int cap = L.cap;
-  const int head = 12 + 3 * D, headp = L.head_pitch;
+  const int head = 12 + 3 * D;
   const bool do_derive = phase & ELG_PHASE_DERIVE, do_term = phase & ELG_PHASE_TERMINATION;
   const bool do_reward = phase & ELG_PHASE_REWARD, do_obs = phase & ELG_PHASE_OBS, do_hist = phase & ELG_PHASE_HISTORY;
-  const bool need_hsum = do_reward && term_on(pr, ELG_REW_BASE_HEIGHT) && H > 0;   // CTA-uniform
+  const bool need_hsum = do_reward && term_on(pr, ELG_REW_BASE_HEIGHT) && H > 0;
   const bool gait = bf.gait_idx != nullptr && bf.gait_prev_foot_z != nullptr;
   const bool lim_terms = term_on(pr, ELG_REW_DOF_POS_LIMITS) | term_on(pr, ELG_REW_DOF_VEL_LIMITS) | term_on(pr, ELG_REW_TORQUE_LIMITS);
   const bool heights_live = H > 0 && do_derive && !pr.terrain_is_plane;
   const bool shared_grid = pr.height_points_env_stride == 0;
+  const int noise_mode = pr.noise_mode;
+  const float clip_obs = pr.clip_observations;
 
-  float* s_root = smem + L.root;   float* s_dof = smem + L.dof;    float* s_act = smem + L.act;
-  float* s_lact = smem + L.lact;   float* s_ldv = smem + L.ldv;    float* s_tq = smem + L.tq;
-  float* s_cf = smem + L.cf;       float* s_lrv = smem + L.lrv;    float* s_vec5 = smem + L.vec5;
-  float* s_cmd = smem + L.cmd;     float* s_air = smem + L.air;    float* s_con = smem + L.con;
-  uint8_t* s_lc = reinterpret_cast<uint8_t*>(smem + L.lc);
-  int64_t* s_ep = reinterpret_cast<int64_t*>(smem + L.ep);
-  float* s_gidx = smem + L.gidx;   float* s_gprev = smem + L.gprev;
-  float* s_fpos = smem + L.fpos;   float* s_fvel = smem + L.fvel;
-  float* s_head = smem + L.head;   float* s_hsum = smem + L.hsum;
-  float* s_sums = smem + L.sums;   float* s_accs = smem + L.accs;  float* s_rew = smem + L.rew;
-  float* s_mh = smem + L.mh;       float* s_obs = smem + L.obs;
-  float* s_q0 = smem + L.q0;       float* s_plim = smem + L.plim;  float* s_vlim = smem + L.vlim;
-  float* s_tlim = smem + L.tlim;   float* s_ns = smem + L.ns;
-  float4* s_grid = reinterpret_cast<float4*>(smem + L.grid);
+#define SM_F(off) reinterpret_cast<float*>(smem_raw + (off))
+  float* const s_root = SM_F(L.root);   float* const s_dof = SM_F(L.dof);    float* const s_act = SM_F(L.act);
+  float* const s_lact = SM_F(L.lact);   float* const s_ldv = SM_F(L.ldv);    float* const s_tq = SM_F(L.tq);
+  float* const s_cf = SM_F(L.cf);       float* const s_lrv = SM_F(L.lrv);    float* const s_vec5 = SM_F(L.vec5);
+  float* const s_cmd = SM_F(L.cmd);     float* const s_air = SM_F(L.air);    float* const s_con = SM_F(L.con);
+  uint8_t* const s_lc = smem_raw + L.lc;
+  int64_t* const s_ep = reinterpret_cast<int64_t*>(smem_raw + L.ep);
+  float* const s_gidx = SM_F(L.gidx);   float* const s_gprev = SM_F(L.gprev);
+  float* const s_fpos = SM_F(L.fpos);   float* const s_fvel = SM_F(L.fvel);
+  float* const s_sums = SM_F(L.sums);   float* const s_rew = SM_F(L.rew);
+  float* const s_mh = SM_F(L.mh);       float* const s_obs = SM_F(L.obs);
+  float* const s_q0 = SM_F(L.q0);       float* const s_plim = SM_F(L.plim);  float* const s_vlim = SM_F(L.vlim);
+  float* const s_tlim = SM_F(L.tlim);   float* const s_ns = SM_F(L.ns);
+  float4* const s_grid = reinterpret_cast<float4*>(smem_raw + L.grid);
+  float* const s_acc = SM_F(L.acc) + warp * 32;   // this warp's raw reward terms, indexed by registry id
+#undef SM_F
 
-  // ------------------------------- CTA-constant tables -------------------------------
+  // sub-chunk bookkeeping of this warp: slot == warp, sub-chunk == warp / kSub, leader == first warp of the sub-chunk
+  const int slot = warp;
+  const int sub = warp / kSub;
+  const bool leader = (warp % kSub) == 0;
+  uint64_t* const bar = &s_bar[sub];
+  if (leader && lane == 0) mbar_init(bar, 1);
+  if (leader) __syncwarp();
+
+  // issue the TMA loads of (chunk, this sub-chunk): one table entry per lane
+  auto chunk_range = [&](int chunk, int& env0, int& nenv) {
+    const int q_lo = chunk * L.quads_base + min(chunk, L.quads_rem);
+    const int q_n = L.quads_base + (chunk < L.quads_rem ? 1 : 0);
+    env0 = q_lo * 4;
+    nenv = min(N, (q_lo + q_n) * 4) - env0;
+  };
+  auto issue_loads = [&](int env0, int nenv) {
+    const int s0 = sub * kSub;
+    const int ne = min(kSub, nenv - s0);
+    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(ne * L.in_bpe));
+    __syncwarp();
+    for (int i = lane; i < L.n_in; i += 32) {
+      const CopyDesc d = L.in[i];
+      bulk_g2s(smem_raw + d.soff + s0 * d.bpe, static_cast<const uint8_t*>(d.g) + (size_t)(env0 + s0) * d.bpe, (uint32_t)(ne * d.bpe), bar);
+    }
+  };
+
+  int chunk = blockIdx.x;
+  int env0 = 0, nenv = 0;
+  if (chunk < L.nchunks) chunk_range(chunk, env0, nenv);
+  bool bulk = L.use_bulk && (nenv & 3) == 0;
+  if (chunk < L.nchunks && bulk && leader && slot < nenv) issue_loads(env0, nenv);
+
+  // ------------------------------- CTA-constant tables (overlap the loads in flight) -------------------------------
   for (int j = tid; j < D; j += nthreads) {
     s_q0[j] = __ldg(bf.default_dof_pos + j);
     if (lim_terms) {
@@ -295,259 +295,221 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       s_tlim[j] = __ldg(bf.torque_limits + j) * pr.soft_torque_limit;
     }
   }
-  for (int k = tid; k < O; k += nthreads) s_ns[k] = (bf.noise_scale_vec && pr.noise_mode != ELG_NOISE_OFF) ? __ldg(bf.noise_scale_vec + k) : 0.0f;
+  {
+    const bool ns_on = bf.noise_scale_vec != nullptr && noise_mode != ELG_NOISE_OFF;
+    for (int k = tid; k < O; k += nthreads) s_ns[k] = ns_on ? __ldg(bf.noise_scale_vec + k) : 0.0f;
+  }
   if (H > 0 && shared_grid && bf.height_points)
     for (int p = tid; p < H; p += nthreads) {
       const float bx = __ldg(bf.height_points + 3 * p), by = __ldg(bf.height_points + 3 * p + 1);
       s_grid[p] = make_float4(bx, by, by, bx);
     }
-  if (tid == 0) mbar_init(&s_bar, 1);
-  __syncthreads();
+  __syncthreads();   // tables + mbarrier initialisation visible to every warp
 
-  const long long Q = ((long long)N + 3) >> 2;
-  uint32_t bar_parity = 0;
-  bool stores_pending = false;
+  uint32_t parity = 0;          // phase parity of this warp's sub-chunk barrier
+  bool stores_pending = false;  // leader lanes: a bulk store group of this sub-chunk may still be reading shared memory
 
-  for (int chunk = blockIdx.x; chunk < L.nchunks; chunk += gridDim.x) {
-    const int q_lo = (int)((long long)chunk * Q / L.nchunks), q_hi = (int)((long long)(chunk + 1) * Q / L.nchunks);
-    const int env0 = q_lo * 4;
-    const int nenv = min(N, q_hi * 4) - env0;
-    if (nenv <= 0) continue;
-    const bool bulk = L.use_bulk && (nenv & 3) == 0;
-    const size_t e0 = (size_t)env0;
-
-    if (stores_pending) {   // the previous chunk's TMA stores must have read shared memory before it is overwritten
-      if (tid == 0) bulk_wait_read_all();
-      stores_pending = false;
+  for (; chunk < L.nchunks; chunk += gridDim.x) {
+    if (chunk != (int)blockIdx.x) {
+      chunk_range(chunk, env0, nenv);
+      bulk = L.use_bulk && (nenv & 3) == 0;
+      if (bulk && leader && slot < nenv) {
+        if (stores_pending) bulk_wait_read_all();   // the previous stores have left shared memory
+        stores_pending = false;
+        __syncwarp();
+        issue_loads(env0, nenv);
+      }
     }
-    __syncthreads();
-
-    // ------------------------------- stage inputs -------------------------------
-    auto for_each_input = [&](auto&& f) {
-      f(s_root, bf.root_states + e0 * 13, 4u * nenv * 13);
-      f(s_dof, bf.dof_state + e0 * 2 * D, 4u * nenv * 2 * D);
-      f(s_act, bf.actions + e0 * D, 4u * nenv * D);
-      f(s_lact, bf.last_actions + e0 * D, 4u * nenv * D);
-      f(s_ldv, bf.last_dof_vel + e0 * D, 4u * nenv * D);
-      f(s_tq, bf.torques + e0 * D, 4u * nenv * D);
-      f(s_cf, bf.contact_forces + e0 * B * 3, 4u * nenv * B * 3);
-      f(s_lrv, bf.last_root_vel + e0 * 6, 4u * nenv * 6);
-      f(s_vec5 + 3 * cap * 3, bf.base_lin_acc + e0 * 3, 4u * nenv * 3);
-      f(s_vec5 + 4 * cap * 3, bf.base_ang_acc + e0 * 3, 4u * nenv * 3);
-      if (!do_derive) {
-        f(s_vec5 + 0 * cap * 3, bf.base_lin_vel + e0 * 3, 4u * nenv * 3);
-        f(s_vec5 + 1 * cap * 3, bf.base_ang_vel + e0 * 3, 4u * nenv * 3);
-        f(s_vec5 + 2 * cap * 3, bf.projected_gravity + e0 * 3, 4u * nenv * 3);
-        if (H > 0 && (do_obs || need_hsum)) f(s_mh, bf.measured_heights + e0 * H, 4u * nenv * H);
+    if (!bulk) {
+      if (stores_pending) { bulk_wait_read_all(); stores_pending = false; }
+      __syncthreads();
+      for (int i = 0; i < L.n_in; ++i) {
+        const CopyDesc d = L.in[i];
+        coop_copy(smem_raw + d.soff, static_cast<const uint8_t*>(d.g) + (size_t)env0 * d.bpe, (uint32_t)(nenv * d.bpe), tid, nthreads);
       }
-      f(s_cmd, bf.commands + e0 * C, 4u * nenv * C);
-      if (F > 0) {
-        f(s_air, bf.feet_air_time + e0 * F, 4u * nenv * F);
-        f(s_con, bf.feet_contact_time + e0 * F, 4u * nenv * F);
-        f(s_lc, bf.last_contacts + e0 * F, (uint32_t)(nenv * F));
+    }
+    const bool active = slot < nenv;
+    const int env = env0 + slot;
+    // feet rows of rigid_body_state are a strided gather (52-byte rows, 6 useful floats per row): plain loads, issued
+    // before the wait so that their latency overlaps the bulk copies
+    // (into registers: shared memory may still be read by the previous chunk's bulk stores until the wait below)
+    float feet_v[2] = {0.0f, 0.0f};
+    const bool feet_gather = active && do_derive && F > 0;
+    if (feet_gather) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = lane + 32 * u;
+        if (r < F * 6) {
+          const int f = r / 6, c = r - 6 * f;
+          feet_v[u] = __ldg(bf.rigid_body_state + ((size_t)env * B + dm.feet_idx[f]) * 13 + (c < 3 ? c : c + 4));
+        }
       }
-      f(s_ep, bf.episode_length_buf + e0, 8u * nenv);
-      if (gait) {
-        f(s_gidx, bf.gait_idx + e0, 4u * nenv);
-        f(s_gprev, bf.gait_prev_foot_z + e0 * F, 4u * nenv * F);
-      }
-      if (do_reward)
-        for (int ti = 0; ti < L.nterms; ++ti) f(s_sums + ti * cap, bf.episode_sums + (size_t)L.term_ids[ti] * N + e0, 4u * nenv);
-    };
+    }
     if (bulk) {
-      if (tid == 0) {
-        uint32_t total = 0;
-        for_each_input([&](void*, const void*, uint32_t bytes) { total += bytes; });
-        mbar_expect_tx(&s_bar, total);
-        for_each_input([&](void* s, const void* g, uint32_t bytes) { bulk_g2s(s, g, bytes, &s_bar); });
+      if (active) {
+        mbar_wait(bar, parity);
+        parity ^= 1u;
       }
     } else {
-      for_each_input([&](void* s, const void* g, uint32_t bytes) { coop_copy(s, g, bytes, tid, nthreads); });
+      __syncthreads();
     }
-    // feet rows of rigid_body_state are a strided gather (52-byte rows, 6 useful floats per row): plain loads
-    for (int r = tid; r < nenv * F * 6; r += nthreads) {
-      const int c = r % 6, ef = r / 6;
-      const int e = ef / F, f = ef - e * F;
-      const float v = __ldg(bf.rigid_body_state + ((size_t)(env0 + e) * B + dm.feet_idx[f]) * 13 + (c < 3 ? c : c + 4));
-      (c < 3 ? s_fpos : s_fvel)[ef * 3 + (c < 3 ? c : c - 3)] = v;
+    if (feet_gather) {
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int r = lane + 32 * u;
+        if (r < F * 6) {
+          const int f = r / 6, c = r - 6 * f;
+          (c < 3 ? s_fpos : s_fvel)[(slot * F + f) * 3 + (c < 3 ? c : c - 3)] = feet_v[u];
+        }
+      }
     }
-    if (bulk) {
-      mbar_wait(&s_bar, bar_parity);
-      bar_parity ^= 1u;
-    }
-    __syncthreads();
+    __syncwarp();
 
-    uint4 blk0 = make_uint4(0, 0, 0, 0);   // Philox block 0 of this warp's (single) env, reused by the head pass
-    int blk0_env = -1;
+    if (active) {
+      const float* rs = s_root + slot * 13;
+      const float rootz = rs[2];
+      float hsum = 0.0f;
 
-    if (warp >= nstate) {
-      // =========================== row warps: terrain scan + height part of the observation ===========================
-      if (H > 0 && (do_derive || do_obs || need_hsum)) {
-        const int16_t* __restrict__ hs = bf.height_samples;
-        const int m_lo = head >> 5, m_hi = (head + H - 1) >> 5;
-        const float r_h = __frcp_rn(pr.horizontal_scale);
-        const f32x2 rr = pack2(r_h, r_h), nc = pack2(-pr.horizontal_scale, -pr.horizontal_scale);
-        const f32x2 bord = pack2(pr.border_size, pr.border_size);
-        const int cols = pr.hf_cols, rmax = pr.hf_rows - 2, cmax = pr.hf_cols - 2;
-        const bool philox = do_obs && pr.noise_mode == ELG_NOISE_PHILOX;
-        for (int slot = warp - nstate; slot < nenv; slot += nrow) {
-          const int env = env0 + slot;
-          const float* rs = s_root + slot * 13;
-          const float rootz = rs[2];
-          const float zc = sub_r(rootz, 0.5f);
-          float zz = 0.0f, ww = 1.0f;
-          if (heights_live) {
-            float n = __fsqrt_rn(add_r(mul_r(rs[5], rs[5]), mul_r(rs[6], rs[6])));
-            n = fmaxf(n, 1e-9f);
-            zz = div_r(rs[5], n);
-            ww = div_r(rs[6], n);
-          }
+      // =========================== terrain scan (legged_robot.py:900-938) ===========================
+      if (H > 0 && do_derive) {
+        float* mh = s_mh + slot * H;
+        if (heights_live) {
+          const int16_t* __restrict__ hs = bf.height_samples;
+          const float r_h = __frcp_rn(pr.horizontal_scale);
+          const f32x2 rr = pack2(r_h, r_h), nc = pack2(-pr.horizontal_scale, -pr.horizontal_scale);
+          const f32x2 bord = pack2(pr.border_size, pr.border_size);
+          const int cols = pr.hf_cols, rmax = pr.hf_rows - 2, cmax = pr.hf_cols - 2;
+          float n = __fsqrt_rn(add_r(mul_r(rs[5], rs[5]), mul_r(rs[6], rs[6])));
+          n = fmaxf(n, 1e-9f);
+          const float zz = div_r(rs[5], n), ww = div_r(rs[6], n);
           // t = 2 (q x b) = (-2 zz by, 2 zz bx); 2*RN(x) == RN(2x), so the doubling is folded into the multiplier
           const f32x2 c_t = pack2(-mul_r(zz, 2.0f), mul_r(zz, 2.0f));    // times (by, bx) -> (tx, ty)
           const f32x2 c_ts = pack2(mul_r(zz, 2.0f), -mul_r(zz, 2.0f));   // times (bx, by) -> (ty, tx)
           const f32x2 c_w = pack2(ww, ww), c_u = pack2(-zz, zz), xy = pack2(rs[0], rs[1]);
           const float* hp_env = shared_grid ? nullptr : bf.height_points + (size_t)env * pr.height_points_env_stride;
-          float hsum = 0.0f;
-          uint4 rnd = make_uint4(0, 0, 0, 0);
-          for (int m = m_lo; m <= m_hi; ++m) {
-            const int k = lane + 32 * m;
-            const int p = k - head;
-            if (philox && ((m & 3) == 0 || m == m_lo)) {   // warp-uniform: every lane owns word m&3 of its block
-              rnd = noise_block(pr.noise_seed, pr.noise_offset, env, lane, m >> 2);
-              if ((m >> 2) == 0) { blk0 = rnd; blk0_env = env; }
+          auto cell_of = [&](int p) -> const int16_t* {
+            f32x2 b, bs;
+            if (shared_grid) {
+              const float4 g = s_grid[p];
+              b = pack2(g.x, g.y);
+              bs = pack2(g.z, g.w);
+            } else {
+              const float bx = __ldg(hp_env + 3 * p), by = __ldg(hp_env + 3 * p + 1);
+              b = pack2(bx, by);
+              bs = pack2(by, bx);
             }
-            const bool valid = p >= 0 && p < H;
-            float h = 0.0f;
-            if (heights_live) {
-              if (valid) {
-                f32x2 b, bs;
-                if (shared_grid) {
-                  const float4 g = s_grid[p];
-                  b = pack2(g.x, g.y);
-                  bs = pack2(g.z, g.w);
-                } else {
-                  const float bx = __ldg(hp_env + 3 * p), by = __ldg(hp_env + 3 * p + 1);
-                  b = pack2(bx, by);
-                  bs = pack2(by, bx);
-                }
-                const f32x2 t = mul2(c_t, bs);          // (tx, ty)
-                const f32x2 ts = mul2(c_ts, b);         // (ty, tx)
-                f32x2 pt = add2(b, mul2(c_w, t));       // b + w t
-                pt = add2(pt, mul2(c_u, ts));           // + q_xyz x t = (-zz ty, zz tx)
-                pt = add2(add2(pt, xy), bord);          // + base xy, + border_size
-                // correctly rounded pt / horizontal_scale: q0 = x r, two FMA residual corrections (Markstein)
-                f32x2 q = mul2(pt, rr);
-                f32x2 e = fma2(nc, q, pt);
-                q = fma2(e, rr, q);
-                e = fma2(nc, q, pt);
-                q = fma2(e, rr, q);
-                float qx, qy;
-                unpack2(q, qx, qy);
-                int ix = __float2int_rz(qx), iy = __float2int_rz(qy);
-                ix = min(max(ix, 0), rmax);
-                iy = min(max(iy, 0), cmax);
-                const int16_t* cell = hs + (size_t)ix * cols + iy;
-                const int a0 = __ldg(cell), a1 = __ldg(cell + cols), a2 = __ldg(cell + 1);
-                h = mul_r((float)min(min(a0, a1), a2), pr.vertical_scale);
-              }
-            } else if (!do_derive && valid) {
-              h = s_mh[slot * H + p];
-            }
-            if (valid) {
-              if (do_derive) s_mh[slot * H + p] = h;
-              hsum += sub_r(rootz, h);
-              if (do_obs) {
-                float v = mul_r(fminf(fmaxf(sub_r(zc, h), -1.0f), 1.0f), pr.obs_scale_height);
-                float u = 0.0f;
-                if (pr.noise_mode == ELG_NOISE_TENSOR) u = __ldg(bf.noise_u + (size_t)env * O + k);
-                if (pr.noise_mode == ELG_NOISE_PHILOX) u = u01(pick(rnd, m & 3));
-                v = finish_obs(v, u, s_ns[k], pr);
-                if (L.obs_smem) s_obs[slot * O + k] = v;
-                else bf.obs_buf[(size_t)env * O + k] = v;
-              }
-            }
-          }
-          if (need_hsum) {
+            const f32x2 t = mul2(c_t, bs);          // (tx, ty)
+            const f32x2 ts = mul2(c_ts, b);         // (ty, tx)
+            f32x2 pt = add2(b, mul2(c_w, t));       // b + w t
+            pt = add2(pt, mul2(c_u, ts));           // + q_xyz x t = (-zz ty, zz tx)
+            pt = add2(add2(pt, xy), bord);          // + base xy, + border_size
+            // correctly rounded pt / horizontal_scale: q0 = x r, two FMA residual corrections (Markstein)
+            f32x2 q = mul2(pt, rr);
+            f32x2 e = fma2(nc, q, pt);
+            q = fma2(e, rr, q);
+            e = fma2(nc, q, pt);
+            q = fma2(e, rr, q);
+            float qx, qy;
+            unpack2(q, qx, qy);
+            int ix = __float2int_rz(qx), iy = __float2int_rz(qy);
+            ix = min(max(ix, 0), rmax);
+            iy = min(max(iy, 0), cmax);
+            return hs + ix * cols + iy;
+          };
+          constexpr int kU = 3;
+          for (int p0 = lane; p0 < H; p0 += 32 * kU) {
+            int a0[kU], a1[kU], a2[kU];
 #pragma unroll
-            for (int o = 16; o > 0; o >>= 1) hsum += __shfl_xor_sync(0xffffffffu, hsum, o);
-            if (lane == 0) s_hsum[slot] = hsum;
-          }
-        }
-      }
-      if (need_hsum) __syncthreads();   // (A) heights -> state warps
-    } else {
-      // =========================== state warps: flat (env, item) loops over one group of 8 envs ===========================
-      const int s0 = warp * kGroup;
-      const int ne = min(kGroup, nenv - s0);   // <= 0: this warp only takes part in the barriers
-      float* scratch = smem + L.scratch + warp * L.scratch_words;
-      float* part = scratch;
-      const int part_words = L.scratch_words - kFeetQ * kGroup - ELG_NUM_REWARD_TERMS * kGroup;
-      float* fred = scratch + part_words;                       // [kFeetQ][kGroup]
-      float* rterm = fred + kFeetQ * kGroup;                    // [nterms][kGroup]
-      const FastDiv fdD(D), fdF(F > 0 ? F : 1), fdPT(P + T > 0 ? P + T : 1);
-#define ACC(t, slot) s_accs[(t) * cap + (slot)]
-
-      if (ne > 0) {
-        // ---- episode counter (legged_robot.py:122)
-        if (do_derive && lane < ne) s_ep[s0 + lane] += 1;
-
-        // ---- phase R: (env, rotation) -- base-frame velocities, gravity, acceleration EMAs (:128-134)
-        if (do_derive) {
-          for (int i = lane; i < 5 * kGroup; i += 32) {
-            const int e = i & (kGroup - 1), r = i >> 3;
-            if (e < ne) {
-              const int slot = s0 + e;
-              const float* rs = s_root + slot * 13;
-              const Quat q = {rs[3], rs[4], rs[5], rs[6]};
-              Vec3 v;
-              if (r == 2) {
-                v = Vec3{pr.gravity_vec[0], pr.gravity_vec[1], pr.gravity_vec[2]};
-              } else {
-                const int k = (r == 1 || r == 4) ? 10 : 7;
-                v = Vec3{rs[k], rs[k + 1], rs[k + 2]};
-                if (r >= 3) {
-                  const float* lrv = s_lrv + slot * 6 + (r - 3) * 3;
-                  v.x -= lrv[0]; v.y -= lrv[1]; v.z -= lrv[2];
-                }
+            for (int u = 0; u < kU; ++u) {
+              const int p = p0 + 32 * u;
+              if (p < H) {
+                const int16_t* cell = cell_of(p);
+                a0[u] = __ldg(cell);
+                a1[u] = __ldg(cell + cols);
+                a2[u] = __ldg(cell + 1);
               }
-              Vec3 o = quat_rotate_inverse(q, v);
-              float* dst = s_vec5 + (r * cap + slot) * 3;
-              if (r >= 3) {
-                const float ema = pr.acc_ema, w1 = pr.acc_ema_c;
-                o.x = dst[0] * ema + (w1 * o.x) / pr.dt;
-                o.y = dst[1] * ema + (w1 * o.y) / pr.dt;
-                o.z = dst[2] * ema + (w1 * o.z) / pr.dt;
+            }
+#pragma unroll
+            for (int u = 0; u < kU; ++u) {
+              const int p = p0 + 32 * u;
+              if (p < H) {
+                const float h = mul_r((float)min(min(a0[u], a1[u]), a2[u]), pr.vertical_scale);
+                mh[p] = h;
+                hsum += sub_r(rootz, h);
               }
-              dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
             }
           }
+        } else {
+          for (int p = lane; p < H; p += 32) {
+            mh[p] = 0.0f;
+            hsum += rootz;
+          }
         }
+      } else if (need_hsum) {
+        for (int p = lane; p < H; p += 32) hsum += sub_r(rootz, s_mh[slot * H + p]);
+      }
+      if (need_hsum) hsum = bfly_sum<32>(hsum);
 
-        // ---- phase D: (env, dof) -- per-dof reward partials, observation entries, history (:84-114, :237-244, :148-149)
-        const int nD = ne * D;
-        for (int i = lane; i < nD; i += 32) {
-          const int e = fdD.div(i), j = i - e * D;
-          const int fi = s0 * D + i;
+      // =========================== state work: lane == item ===========================
+      // ---- episode counter (legged_robot.py:122)
+      if (do_derive && lane == 0) s_ep[slot] += 1;
+
+      // ---- lanes 0..4: base-frame velocities, gravity, acceleration EMAs (:128-134)
+      if (do_derive && lane < 5) {
+        const int r = lane;
+        const Quat q = {rs[3], rs[4], rs[5], rs[6]};
+        Vec3 v;
+        if (r == 2) {
+          v = Vec3{pr.gravity_vec[0], pr.gravity_vec[1], pr.gravity_vec[2]};
+        } else {
+          const int k = (r == 1 || r == 4) ? 10 : 7;
+          v = Vec3{rs[k], rs[k + 1], rs[k + 2]};
+          if (r >= 3) {
+            const float* lrv = s_lrv + slot * 6 + (r - 3) * 3;
+            v.x -= lrv[0]; v.y -= lrv[1]; v.z -= lrv[2];
+          }
+        }
+        Vec3 o = quat_rotate_inverse(q, v);
+        float* dst = s_vec5 + (r * cap + slot) * 3;
+        if (r >= 3) {
+          const float ema = pr.acc_ema, w1 = pr.acc_ema_c;
+          o.x = dst[0] * ema + (w1 * o.x) / pr.dt;
+          o.y = dst[1] * ema + (w1 * o.y) / pr.dt;
+          o.z = dst[2] * ema + (w1 * o.z) / pr.dt;
+        }
+        dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
+      }
+      __syncwarp();
+
+      // observation row: raw head entries first, finished in place below.  When the caller's rows are wider than
+      // head + H (user-extended observations) only the head is staged and the finished entries go straight to global.
+      float* orow = s_obs + slot * (L.obs_smem ? O : head);
+      float* hrow = orow;
+
+      // ---- lanes 0..D-1: per-dof reward partials, observation entries, history (:84-114, :237-244, :148-149)
+      {
+        float q_ar = 0.0f, q_da = 0.0f, q_dv = 0.0f, q_tq = 0.0f, q_ss = 0.0f, q_pl = 0.0f, q_vl = 0.0f, q_tl = 0.0f;
+        if (lane < D) {
+          const int j = lane, fi = slot * D + j;
           const float2 pv = *reinterpret_cast<const float2*>(s_dof + 2 * fi);
           const float pos = pv.x, vel = pv.y;
           const float a = s_act[fi], q0 = s_q0[j];
           if (do_reward) {
             const float la = s_lact[fi], lv = s_ldv[fi], tq = s_tq[fi];
             const float da = la - a;
-            part[0 * L.part_d + i] = da * da;
+            q_ar = da * da;
             const float dv = (lv - vel) / pr.dt;
-            part[1 * L.part_d + i] = dv * dv;
-            part[2 * L.part_d + i] = vel * vel;
-            part[3 * L.part_d + i] = tq * tq;
-            part[4 * L.part_d + i] = fabsf(pos - q0);
+            q_da = dv * dv;
+            q_dv = vel * vel;
+            q_tq = tq * tq;
+            q_ss = fabsf(pos - q0);
             if (lim_terms) {
-              part[5 * L.part_d + i] = -fminf(pos - s_plim[2 * j], 0.0f) + fmaxf(pos - s_plim[2 * j + 1], 0.0f);
-              part[6 * L.part_d + i] = fminf(fmaxf(fabsf(vel) - s_vlim[j], 0.0f), 1.0f);
-              part[7 * L.part_d + i] = fmaxf(fabsf(tq) - s_tlim[j], 0.0f);
+              q_pl = -fminf(pos - s_plim[2 * j], 0.0f) + fmaxf(pos - s_plim[2 * j + 1], 0.0f);
+              q_vl = fminf(fmaxf(fabsf(vel) - s_vlim[j], 0.0f), 1.0f);
+              q_tl = fmaxf(fabsf(tq) - s_tlim[j], 0.0f);
             }
           }
           if (do_obs) {
-            float* hrow = s_head + (s0 + e) * headp;
             hrow[12 + j] = (pos - q0) * pr.obs_scale_dof_pos;
             hrow[12 + D + j] = vel * pr.obs_scale_dof_vel;
             hrow[12 + 2 * D + j] = a;
@@ -557,39 +519,27 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
             s_ldv[fi] = vel;
           }
         }
-        __syncwarp();
         if (do_reward) {
-          // registry ids of the 8 per-dof quantities, one byte each
-          const unsigned long long qterm = (unsigned long long)ELG_REW_ACTION_RATE | ((unsigned long long)ELG_REW_DOF_ACC << 8) |
-                                           ((unsigned long long)ELG_REW_DOF_VEL << 16) | ((unsigned long long)ELG_REW_TORQUES << 24) |
-                                           ((unsigned long long)ELG_REW_STAND_STILL << 32) | ((unsigned long long)ELG_REW_DOF_POS_LIMITS << 40) |
-                                           ((unsigned long long)ELG_REW_DOF_VEL_LIMITS << 48) | ((unsigned long long)ELG_REW_TORQUE_LIMITS << 56);
-          const int nq = lim_terms ? kDofQ : 5;
-          for (int i = lane; i < nq * kGroup; i += 32) {
-            const int e = i & (kGroup - 1), qn = i >> 3;
-            if (e < ne) {
-              const float* src = part + qn * L.part_d + e * D;
-              float sum = 0.0f;
-              for (int j = 0; j < D; ++j) sum += src[j];
-              ACC((int)((qterm >> (8 * qn)) & 0xffu), s0 + e) = sum;
-            }
-          }
-          if (!lim_terms && lane < ne) {
-            ACC(ELG_REW_DOF_POS_LIMITS, s0 + lane) = 0.0f;
-            ACC(ELG_REW_DOF_VEL_LIMITS, s0 + lane) = 0.0f;
-            ACC(ELG_REW_TORQUE_LIMITS, s0 + lane) = 0.0f;
-          }
-          __syncwarp();
+          if (term_on(pr, ELG_REW_ACTION_RATE)) { q_ar = lanes_sum(q_ar, D); if (lane == 0) s_acc[ELG_REW_ACTION_RATE] = q_ar; }
+          if (term_on(pr, ELG_REW_DOF_ACC)) { q_da = lanes_sum(q_da, D); if (lane == 0) s_acc[ELG_REW_DOF_ACC] = q_da; }
+          if (term_on(pr, ELG_REW_DOF_VEL)) { q_dv = lanes_sum(q_dv, D); if (lane == 0) s_acc[ELG_REW_DOF_VEL] = q_dv; }
+          if (term_on(pr, ELG_REW_TORQUES)) { q_tq = lanes_sum(q_tq, D); if (lane == 0) s_acc[ELG_REW_TORQUES] = q_tq; }
+          if (term_on(pr, ELG_REW_STAND_STILL)) q_ss = lanes_sum(q_ss, D);   // finished with the command gate below
+          if (term_on(pr, ELG_REW_DOF_POS_LIMITS)) { q_pl = lanes_sum(q_pl, D); if (lane == 0) s_acc[ELG_REW_DOF_POS_LIMITS] = q_pl; }
+          if (term_on(pr, ELG_REW_DOF_VEL_LIMITS)) { q_vl = lanes_sum(q_vl, D); if (lane == 0) s_acc[ELG_REW_DOF_VEL_LIMITS] = q_vl; }
+          if (term_on(pr, ELG_REW_TORQUE_LIMITS)) { q_tl = lanes_sum(q_tl, D); if (lane == 0) s_acc[ELG_REW_TORQUE_LIMITS] = q_tl; }
+        }
 
-          // ---- phase F: (env, foot) (legged_robot_rew_mixin.py:58-81, :121-212; gait_scheduler.py:74-81)
-          // Terms that sort before feet_air_time read the OLD timers, terms after it the updated ones
-          // and the rebound last_contacts.
+        // ---- lanes 0..F-1: feet (legged_robot_rew_mixin.py:58-81, :121-212; gait_scheduler.py:74-81)
+        // Terms that sort before feet_air_time read the OLD timers, terms after it the updated ones
+        // and the rebound last_contacts.
+        float f_tz = 0.0f, f_tn = 0.0f, f_air = 0.0f, f_cf = 0.0f, f_slip = 0.0f, f_lift = 0.0f, f_jump = 0.0f, f_stum = 0.0f,
+              f_down = 0.0f, f_gs = 0.0f;
+        if (do_reward && F > 0) {
           const bool air_on = term_on(pr, ELG_REW_FEET_AIR_TIME);
           const bool gs_on = term_on(pr, ELG_REW_GAIT_SCHEDULER) && gait;
-          const int nF = ne * F;
-          for (int i = lane; i < nF; i += 32) {
-            const int e = fdF.div(i), f = i - e * F;
-            const int slot = s0 + e, fi = s0 * F + i;
+          if (lane < F) {
+            const int f = lane, fi = slot * F + f;
             const float* cf = s_cf + (slot * B + dm.feet_idx[f]) * 3;
             const float fxx = cf[0], fyy = cf[1], fz = cf[2];
             const float pz = s_fpos[fi * 3 + 2];
@@ -598,16 +548,15 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
             const bool last_c = s_lc[fi] != 0;
             const bool contact = fz > 1.0f;
             const bool touching = con > 1e-3f;   // base_foot_height: nanmean over touching feet (old timers)
-            part[0 * L.part_f + i] = touching ? pz : 0.0f;
-            part[1 * L.part_f + i] = touching ? 1.0f : 0.0f;
+            f_tz = touching ? pz : 0.0f;
+            f_tn = touching ? 1.0f : 0.0f;
             bool lc_after = last_c;
-            float r_air = 0.0f;
             if (air_on) {
               const bool filt = contact | last_c;
               const bool first = (air > 0.0f) && filt;
               air += pr.dt;
               con += pr.dt;
-              r_air = (air - 0.5f) * (first ? 1.0f : 0.0f);
+              f_air = (air - 0.5f) * (first ? 1.0f : 0.0f);
               air *= filt ? 0.0f : 1.0f;
               con *= filt ? 1.0f : 0.0f;
               s_air[fi] = air;
@@ -616,113 +565,108 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
               lc_after = contact;
             }
             const bool filt2 = contact | lc_after;
-            part[2 * L.part_f + i] = r_air;
-            part[3 * L.part_f + i] = fmaxf(norm3_t(fxx, fyy, fz) - pr.max_contact_force, 0.0f);
+            f_cf = fmaxf(norm3_t(fxx, fyy, fz) - pr.max_contact_force, 0.0f);
             const float vn = norm2_t(vx, vy);
-            part[4 * L.part_f + i] = (filt2 ? 1.0f : 0.0f) * (vn * vn);
+            f_slip = (filt2 ? 1.0f : 0.0f) * (vn * vn);
             const bool stumble = norm2_t(fxx, fyy) > mul_r(5.0f, fabsf(fz));
-            part[5 * L.part_f + i] = (stumble ? 1.0f : 0.0f) * vz;
-            part[6 * L.part_f + i] = (filt2 ? 0.0f : 1.0f) * (air - 0.5f);
-            part[7 * L.part_f + i] = stumble ? 1.0f : 0.0f;
-            part[8 * L.part_f + i] = fz < 1.0f ? 0.0f : 1.0f;   // number of feet that are NOT up
-            float r_gs = 0.0f;
+            f_lift = (stumble ? 1.0f : 0.0f) * vz;
+            f_jump = (filt2 ? 0.0f : 1.0f) * (air - 0.5f);
+            f_stum = stumble ? 1.0f : 0.0f;
+            f_down = fz < 1.0f ? 0.0f : 1.0f;   // number of feet that are NOT up
             if (gs_on) {
               float ph = s_gidx[slot] + pr.gait_foot_phases[f];
               ph = ph - floorf(ph);                                 // torch.remainder(x, 1.0)
               const float target = ph < 0.5f ? pr.gait_swing_height * sinf(6.283185307179586f * ph) : 0.0f;
               const float dz = target - s_gprev[fi];
-              r_gs = dz * dz;
+              f_gs = dz * dz;
             }
-            part[9 * L.part_f + i] = r_gs;
             if (gait) s_gprev[fi] = pz;   // GaitScheduler.step keeps this step's feet
           }
-          __syncwarp();
-          for (int i = lane; i < kFeetQ * kGroup; i += 32) {
-            const int e = i & (kGroup - 1), qn = i >> 3;
-            if (e < ne) {
-              const float* src = part + qn * L.part_f + e * F;
-              float sum = 0.0f;
-              for (int f = 0; f < F; ++f) sum += src[f];
-              fred[qn * kGroup + e] = sum;
-            }
-          }
-          __syncwarp();
+          if (term_on(pr, ELG_REW_BASE_FOOT_HEIGHT)) { f_tz = lanes_sum(f_tz, F); f_tn = lanes_sum(f_tn, F); }
+          if (air_on) f_air = lanes_sum(f_air, F);
+          if (term_on(pr, ELG_REW_FEET_CONTACT_FORCES)) f_cf = lanes_sum(f_cf, F);
+          if (term_on(pr, ELG_REW_FEET_SLIP)) f_slip = lanes_sum(f_slip, F);
+          if (term_on(pr, ELG_REW_FEET_STUMBLE_LIFTUP)) f_lift = lanes_sum(f_lift, F);
+          if (term_on(pr, ELG_REW_JUMP_AIR)) f_jump = lanes_sum(f_jump, F);
+          if (term_on(pr, ELG_REW_FEET_STUMBLE)) f_stum = lanes_sum(f_stum, F);
+          if (term_on(pr, ELG_REW_FOUR_FOOTUP)) f_down = lanes_sum(f_down, F);
+          if (gs_on) f_gs = lanes_sum(f_gs, F);
         }
 
-        // ---- phase P: (env, body) -- collision count and termination contacts (:117-119, legged_robot.py:155-160)
-        const int PT = P + T;
+        // ---- lanes 0..P+T-1: collision count and termination contacts (:117-119, legged_robot.py:155-160)
+        unsigned hit_mask = 0;
         if (do_term || do_reward) {
-          for (int i = lane; i < ne * PT; i += 32) {
-            const int e = fdPT.div(i), p = i - e * PT;
-            const int body = p < P ? dm.penalised_idx[p] : dm.termination_idx[p - P];
-            const float* f = s_cf + ((s0 + e) * B + body) * 3;
-            part[i] = norm3_t(f[0], f[1], f[2]) > (p < P ? 0.1f : 1.0f) ? 1.0f : 0.0f;
+          bool hit = false;
+          if (lane < P + T) {
+            const int body = lane < P ? dm.penalised_idx[lane] : dm.termination_idx[lane - P];
+            const float* f = s_cf + (slot * B + body) * 3;
+            hit = norm3_t(f[0], f[1], f[2]) > (lane < P ? 0.1f : 1.0f);
           }
-          __syncwarp();
+          hit_mask = __ballot_sync(0xffffffffu, hit);
         }
+        __syncwarp();   // timers / last_contacts written by the foot lanes are read by every lane below
 
-        // ---- phase E: one lane per env -- commands, termination, scalar reward terms, head, root-velocity history
-        if (lane < ne) {
-          const int slot = s0 + lane, env = env0 + slot;
-          const float* rs = s_root + slot * 13;
-          const float* blv = s_vec5 + (0 * cap + slot) * 3;
-          const float* bav = s_vec5 + (1 * cap + slot) * 3;
-          const float* pg = s_vec5 + (2 * cap + slot) * 3;
-          float* cmd = s_cmd + slot * C;
-          if (do_derive && pr.heading_command) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
-            const Quat q = {rs[3], rs[4], rs[5], rs[6]};
-            const float fx = 1.0f + (q.y * (-2.0f * q.y) - q.z * (2.0f * q.z));
-            const float fy = q.w * (2.0f * q.z) + (q.z * 0.0f - q.x * (-2.0f * q.y));
-            const float heading = atan2f(fy, fx);
-            cmd[2] = fminf(fmaxf(0.5f * wrap_to_pi(cmd[3] - heading), -1.0f), 1.0f);
-          }
-          const float cmd0 = cmd[0], cmd1 = cmd[1], cmd2 = cmd[2], cmd3 = C > 3 ? cmd[3] : 0.0f;
-          bool reset = false, time_out = false;
-          if (do_term) {
-            bool contact_term = false;
-            for (int t = 0; t < T; ++t) contact_term |= part[lane * PT + P + t] != 0.0f;
-            time_out = s_ep[slot] > pr.max_episode_length;
-            reset = contact_term | time_out;
+        // ---- every lane (uniform): commands, termination, scalar reward terms, head; lane 0 stores
+        const float* blv = s_vec5 + (0 * cap + slot) * 3;
+        const float* bav = s_vec5 + (1 * cap + slot) * 3;
+        const float* pg = s_vec5 + (2 * cap + slot) * 3;
+        float* cmd = s_cmd + slot * C;
+        float cmd2 = cmd[2];
+        if (do_derive && pr.heading_command) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
+          const Quat q = {rs[3], rs[4], rs[5], rs[6]};
+          const float fx = 1.0f + (q.y * (-2.0f * q.y) - q.z * (2.0f * q.z));
+          const float fy = q.w * (2.0f * q.z) + (q.z * 0.0f - q.x * (-2.0f * q.y));
+          const float heading = atan2f(fy, fx);
+          cmd2 = fminf(fmaxf(0.5f * wrap_to_pi(cmd[3] - heading), -1.0f), 1.0f);
+          __syncwarp();
+          if (lane == 0) cmd[2] = cmd2;
+        }
+        const float cmd0 = cmd[0], cmd1 = cmd[1], cmd3 = C > 3 ? cmd[3] : 0.0f;
+        bool reset = false, time_out = false;
+        if (do_term) {
+          const bool contact_term = (hit_mask >> P) != 0u;
+          time_out = s_ep[slot] > pr.max_episode_length;
+          reset = contact_term | time_out;
+          if (lane == 0) {
             bf.reset_buf[env] = reset ? 1 : 0;
             bf.time_out_buf[env] = time_out ? 1 : 0;
-          } else if (do_reward) {
-            reset = bf.reset_buf[env] != 0;
-            time_out = bf.time_out_buf[env] != 0;
           }
-          if (do_reward) {
-            const float rootz = rs[2];
-            const float cmd_xy = norm2_t(cmd0, cmd1);
-            ACC(ELG_REW_STAND_STILL, slot) *= (cmd_xy < pr.stand_still_threshold ? 1.0f : 0.0f);
-            ACC(ELG_REW_LIN_VEL_Z, slot) = blv[2] * blv[2];
-            ACC(ELG_REW_ANG_VEL_XY, slot) = bav[0] * bav[0] + bav[1] * bav[1];
-            ACC(ELG_REW_ORIENTATION, slot) = pg[0] * pg[0] + pg[1] * pg[1];
-            {
-              const float ex = cmd0 - blv[0], ey = cmd1 - blv[1], ez = cmd2 - bav[2];
-              ACC(ELG_REW_TRACKING_LIN_VEL, slot) = expf(-(ex * ex + ey * ey) / pr.tracking_sigma);
-              ACC(ELG_REW_TRACKING_ANG_VEL, slot) = expf(-(ez * ez) / pr.tracking_sigma);
+        } else if (do_reward) {
+          reset = bf.reset_buf[env] != 0;
+          time_out = bf.time_out_buf[env] != 0;
+        }
+        if (do_reward) {
+          const float cmd_xy = norm2_t(cmd0, cmd1);
+          if (lane == 0) {
+#define ACC(t) s_acc[t]
+            if (term_on(pr, ELG_REW_STAND_STILL)) ACC(ELG_REW_STAND_STILL) = q_ss * (cmd_xy < pr.stand_still_threshold ? 1.0f : 0.0f);
+            if (term_on(pr, ELG_REW_LIN_VEL_Z)) ACC(ELG_REW_LIN_VEL_Z) = blv[2] * blv[2];
+            if (term_on(pr, ELG_REW_ANG_VEL_XY)) ACC(ELG_REW_ANG_VEL_XY) = bav[0] * bav[0] + bav[1] * bav[1];
+            if (term_on(pr, ELG_REW_ORIENTATION)) ACC(ELG_REW_ORIENTATION) = pg[0] * pg[0] + pg[1] * pg[1];
+            if (term_on(pr, ELG_REW_TRACKING_LIN_VEL)) {
+              const float ex = cmd0 - blv[0], ey = cmd1 - blv[1];
+              ACC(ELG_REW_TRACKING_LIN_VEL) = expf(-(ex * ex + ey * ey) / pr.tracking_sigma);
             }
-            ACC(ELG_REW_TERMINATION, slot) = (reset && !time_out) ? 1.0f : 0.0f;
-            {
-              float n = 0.0f;
-              for (int p = 0; p < P; ++p) n += part[lane * PT + p];
-              ACC(ELG_REW_COLLISION, slot) = n;
+            if (term_on(pr, ELG_REW_TRACKING_ANG_VEL)) {
+              const float ez = cmd2 - bav[2];
+              ACC(ELG_REW_TRACKING_ANG_VEL) = expf(-(ez * ez) / pr.tracking_sigma);
             }
-            const float* fr = fred + lane;   // fred[q * kGroup + lane]
-            {
-              const float cnt = fr[1 * kGroup];
-              const float ground = cnt > 0.0f ? fr[0 * kGroup] / cnt : rootz - pr.base_height_target;
+            if (term_on(pr, ELG_REW_TERMINATION)) ACC(ELG_REW_TERMINATION) = (reset && !time_out) ? 1.0f : 0.0f;
+            if (term_on(pr, ELG_REW_COLLISION)) ACC(ELG_REW_COLLISION) = (float)__popc(hit_mask & ((1u << P) - 1u));
+            if (term_on(pr, ELG_REW_BASE_FOOT_HEIGHT)) {
+              const float ground = f_tn > 0.0f ? f_tz / f_tn : rootz - pr.base_height_target;
               const float rel = rootz - ground - pr.base_height_target;
-              ACC(ELG_REW_BASE_FOOT_HEIGHT, slot) = rel * rel;
+              ACC(ELG_REW_BASE_FOOT_HEIGHT) = rel * rel;
             }
-            ACC(ELG_REW_FEET_AIR_TIME, slot) = fr[2 * kGroup] * (cmd_xy > 0.1f ? 1.0f : 0.0f);
-            ACC(ELG_REW_FEET_CONTACT_FORCES, slot) = fr[3 * kGroup];
-            ACC(ELG_REW_FEET_SLIP, slot) = fr[4 * kGroup];
-            ACC(ELG_REW_FEET_STUMBLE_LIFTUP, slot) = fr[5 * kGroup];
-            ACC(ELG_REW_JUMP_AIR, slot) = fmaxf(fr[6 * kGroup] - (float)F / 2.0f, 0.0f);
-            ACC(ELG_REW_FEET_STUMBLE, slot) = fr[7 * kGroup] > 0.0f ? 1.0f : 0.0f;
-            ACC(ELG_REW_FOUR_FOOTUP, slot) = fr[8 * kGroup] == 0.0f ? 0.1f : 0.0f;
-            ACC(ELG_REW_GAIT_SCHEDULER, slot) = fr[9 * kGroup];
-            {
+            if (term_on(pr, ELG_REW_FEET_AIR_TIME)) ACC(ELG_REW_FEET_AIR_TIME) = f_air * (cmd_xy > 0.1f ? 1.0f : 0.0f);
+            if (term_on(pr, ELG_REW_FEET_CONTACT_FORCES)) ACC(ELG_REW_FEET_CONTACT_FORCES) = f_cf;
+            if (term_on(pr, ELG_REW_FEET_SLIP)) ACC(ELG_REW_FEET_SLIP) = f_slip;
+            if (term_on(pr, ELG_REW_FEET_STUMBLE_LIFTUP)) ACC(ELG_REW_FEET_STUMBLE_LIFTUP) = f_lift;
+            if (term_on(pr, ELG_REW_JUMP_AIR)) ACC(ELG_REW_JUMP_AIR) = fmaxf(f_jump - (float)F / 2.0f, 0.0f);
+            if (term_on(pr, ELG_REW_FEET_STUMBLE)) ACC(ELG_REW_FEET_STUMBLE) = f_stum > 0.0f ? 1.0f : 0.0f;
+            if (term_on(pr, ELG_REW_FOUR_FOOTUP)) ACC(ELG_REW_FOUR_FOOTUP) = f_down == 0.0f ? 0.1f : 0.0f;
+            if (term_on(pr, ELG_REW_GAIT_SCHEDULER)) ACC(ELG_REW_GAIT_SCHEDULER) = f_gs;
+            if (term_on(pr, ELG_REW_GAIT_2_STEP)) {
               // gait_2_step (legged_robot_rew_mixin.py:170-206): FL/RR and FR/RL in phase, the rest anti-phase
               const float* ar = s_air + slot * F;
               const float* cn = s_con + slot * F;
@@ -734,138 +678,120 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
                                (sq4(a3, c1) + sq4(c3, a1))) / 4.0f;
               const float yawish = pr.heading_command ? cmd3 : cmd2;
               const bool moving = (cmd_xy > pr.speed_min) | (fabsf(yawish) >= pr.speed_min / 2.0f);
-              ACC(ELG_REW_GAIT_2_STEP, slot) = (s + a) * (moving ? 1.0f : 0.0f);
+              ACC(ELG_REW_GAIT_2_STEP) = (s + a) * (moving ? 1.0f : 0.0f);
             }
-            ACC(ELG_REW_BASE_HEIGHT, slot) = 0.0f;
+            if (term_on(pr, ELG_REW_BASE_HEIGHT)) {
+              const float d = (need_hsum ? hsum / (float)H : 0.0f) - pr.base_height_target;
+              ACC(ELG_REW_BASE_HEIGHT) = need_hsum ? d * d : 0.0f;
+            }
+#undef ACC
             if (gait) {   // GaitScheduler.step (gait_scheduler.py:63-72) runs after the env step
               const float g = s_gidx[slot] + pr.gait_increment;
               s_gidx[slot] = g - floorf(g);
             }
           }
-          if (do_obs) {
-            float* hrow = s_head + slot * headp;
-            hrow[0] = blv[0] * pr.obs_scale_lin_vel; hrow[1] = blv[1] * pr.obs_scale_lin_vel; hrow[2] = blv[2] * pr.obs_scale_lin_vel;
-            hrow[3] = bav[0] * pr.obs_scale_ang_vel; hrow[4] = bav[1] * pr.obs_scale_ang_vel; hrow[5] = bav[2] * pr.obs_scale_ang_vel;
-            hrow[6] = pg[0]; hrow[7] = pg[1]; hrow[8] = pg[2];
-            hrow[9] = cmd0 * pr.commands_scale[0]; hrow[10] = cmd1 * pr.commands_scale[1]; hrow[11] = cmd2 * pr.commands_scale[2];
-          }
-          if (do_hist) {
-            float* lrv = s_lrv + slot * 6;
-#pragma unroll
-            for (int k = 0; k < 6; ++k) lrv[k] = rs[7 + k];
-          }
         }
+        if (do_obs && lane == 0) {
+          hrow[0] = blv[0] * pr.obs_scale_lin_vel; hrow[1] = blv[1] * pr.obs_scale_lin_vel; hrow[2] = blv[2] * pr.obs_scale_lin_vel;
+          hrow[3] = bav[0] * pr.obs_scale_ang_vel; hrow[4] = bav[1] * pr.obs_scale_ang_vel; hrow[5] = bav[2] * pr.obs_scale_ang_vel;
+          hrow[6] = pg[0]; hrow[7] = pg[1]; hrow[8] = pg[2];
+          hrow[9] = cmd0 * pr.commands_scale[0]; hrow[10] = cmd1 * pr.commands_scale[1]; hrow[11] = cmd2 * pr.commands_scale[2];
+        }
+        if (do_hist && lane < 6) s_lrv[slot * 6 + lane] = rs[7 + lane];
         __syncwarp();
-      }
 
-      if (need_hsum) __syncthreads();   // (A)
-      if (ne > 0 && do_reward) {
-        if (need_hsum && lane < ne) {
-          const float d = s_hsum[s0 + lane] / (float)H - pr.base_height_target;
-          ACC(ELG_REW_BASE_HEIGHT, s0 + lane) = d * d;
-        }
-        __syncwarp();
-        // ---- phase W: (term, env) scaled terms + episode sums, then the ordered fp32 sum (legged_robot.py:220-232)
-        for (int i = lane; i < L.nterms * kGroup; i += 32) {
-          const int e = i & (kGroup - 1), ti = i >> 3;
-          if (e < ne) {
-            const int t = L.term_ids[ti];
-            const float r = ACC(t, s0 + e) * pr.reward_scales[t];
-            rterm[ti * kGroup + e] = r;
-            s_sums[ti * cap + s0 + e] += r;
+        // ---- scaled terms + episode sums (lane == term), then the ordered fp32 sum (legged_robot.py:220-232)
+        if (do_reward) {
+          float r = 0.0f;
+          if (lane < L.nterms) {
+            const int t = L.term_ids[lane];
+            r = s_acc[t] * pr.reward_scales[t];
+            s_sums[lane * cap + slot] += r;
           }
-        }
-        __syncwarp();
-        if (lane < ne) {
-          const int slot = s0 + lane;
           float total = 0.0f, r_term = 0.0f;
           for (int ti = 0; ti < L.nterms; ++ti) {
-            const float r = rterm[ti * kGroup + lane];
-            if (L.term_ids[ti] == ELG_REW_TERMINATION) r_term = r;   // added after the clip
-            else total += r;
+            const float v = __shfl_sync(0xffffffffu, r, ti);
+            if (L.term_ids[ti] == ELG_REW_TERMINATION) r_term = v;   // added after the clip
+            else total += v;
           }
-          if (bf.extra_reward) total += bf.extra_reward[env0 + slot];
+          if (bf.extra_reward) total += bf.extra_reward[env];
           if (pr.only_positive_rewards) total = fmaxf(total, 0.0f);
           if (term_on(pr, ELG_REW_TERMINATION)) total += r_term;
-          s_rew[slot] = total;
+          if (lane == 0) s_rew[slot] = total;
         }
       }
-#undef ACC
-    }
 
-    // ------------------------------- observation heads -------------------------------
-    if (do_obs) {
-      __syncthreads();   // (B) observation heads are in shared memory
-      if (warp >= nstate) {
-        for (int slot = warp - nstate; slot < nenv; slot += nrow) {
-          const int env = env0 + slot;
-          uint4 rnd = blk0;
-          for (int k = lane; k < head; k += 32) {
-            float u = 0.0f;
-            if (pr.noise_mode == ELG_NOISE_TENSOR) u = __ldg(bf.noise_u + (size_t)env * O + k);
-            if (pr.noise_mode == ELG_NOISE_PHILOX) {
-              const int m = k >> 5;
-              if (((m & 3) == 0 && (m > 0 || blk0_env != env)) ) rnd = noise_block(pr.noise_seed, pr.noise_offset, env, lane, m >> 2);
-              u = u01(pick(rnd, m & 3));
+      // =========================== observation row: noise + clip (legged_robot.py:234-252, :107-108) ===========================
+      if (do_obs) {
+        // noise index k' of obs element k: k for the head, hm*32 + p for height point p; lane = k' % 32,
+        // Philox block = k' / 128, word = (k' / 32) % 4 -- so one lane consumes whole blocks
+        const int hm = L.hm;
+        const int nm = hm + ((H + 31) >> 5);
+        const float zc = sub_r(rootz, 0.5f);
+        const float* mh = s_mh + slot * H;
+        const bool philox = noise_mode == ELG_NOISE_PHILOX;
+        const bool to_smem = L.obs_smem;
+        float* grow = bf.obs_buf + (size_t)env * O;
+        for (int mb = 0; mb * 4 < nm; ++mb) {
+          uint4 rnd = make_uint4(0, 0, 0, 0);
+          if (philox) rnd = noise_block(pr.noise_seed, pr.noise_offset, env, lane, mb);
+#pragma unroll
+          for (int w = 0; w < 4; ++w) {
+            const int m = mb * 4 + w;
+            if (m >= nm) break;
+            int k;
+            float v;
+            bool valid;
+            if (m < hm) {
+              k = lane + 32 * m;
+              valid = k < head;
+              v = valid ? hrow[k] : 0.0f;
+            } else {
+              const int p = lane + 32 * (m - hm);
+              valid = p < H;
+              k = head + p;
+              v = valid ? mul_r(fminf(fmaxf(sub_r(zc, mh[p]), -1.0f), 1.0f), pr.obs_scale_height) : 0.0f;
             }
-            const float v = finish_obs(s_head[slot * headp + k], u, s_ns[k], pr);
-            if (L.obs_smem) s_obs[slot * O + k] = v;
-            else bf.obs_buf[(size_t)env * O + k] = v;
+            if (valid) {
+              float u = 0.0f;
+              if (noise_mode == ELG_NOISE_TENSOR) u = __ldg(bf.noise_u + (size_t)env * O + k);
+              if (philox) u = u01(w == 0 ? rnd.x : w == 1 ? rnd.y : w == 2 ? rnd.z : rnd.w);
+              v = finish_obs(v, u, s_ns[k], noise_mode, clip_obs);
+              if (to_smem) orow[k] = v;
+              else grow[k] = v;
+            }
           }
         }
       }
     }
 
     // ------------------------------- write back -------------------------------
-    auto for_each_output = [&](auto&& f) {
-      if (do_derive) {
-        f(bf.base_lin_vel + e0 * 3, s_vec5 + 0 * cap * 3, 4u * nenv * 3);
-        f(bf.base_ang_vel + e0 * 3, s_vec5 + 1 * cap * 3, 4u * nenv * 3);
-        f(bf.projected_gravity + e0 * 3, s_vec5 + 2 * cap * 3, 4u * nenv * 3);
-        f(bf.base_lin_acc + e0 * 3, s_vec5 + 3 * cap * 3, 4u * nenv * 3);
-        f(bf.base_ang_acc + e0 * 3, s_vec5 + 4 * cap * 3, 4u * nenv * 3);
-        if (F > 0) {
-          f(bf.foot_positions + e0 * F * 3, s_fpos, 4u * nenv * F * 3);
-          f(bf.foot_velocities + e0 * F * 3, s_fvel, 4u * nenv * F * 3);
-        }
-        if (pr.heading_command) f(bf.commands + e0 * C, s_cmd, 4u * nenv * C);
-        f(bf.episode_length_buf + e0, s_ep, 8u * nenv);
-        if (H > 0) f(bf.measured_heights + e0 * H, s_mh, 4u * nenv * H);
-      }
-      if (do_reward) {
-        if (term_on(pr, ELG_REW_FEET_AIR_TIME) && F > 0) {
-          f(bf.feet_air_time + e0 * F, s_air, 4u * nenv * F);
-          f(bf.feet_contact_time + e0 * F, s_con, 4u * nenv * F);
-          f(bf.last_contacts + e0 * F, s_lc, (uint32_t)(nenv * F));
-        }
-        for (int ti = 0; ti < L.nterms; ++ti) f(bf.episode_sums + (size_t)L.term_ids[ti] * N + e0, s_sums + ti * cap, 4u * nenv);
-        f(bf.rew_buf + e0, s_rew, 4u * nenv);
-        if (gait) {
-          f(bf.gait_idx + e0, s_gidx, 4u * nenv);
-          f(bf.gait_prev_foot_z + e0 * F, s_gprev, 4u * nenv * F);
-        }
-      }
-      if (do_obs && L.obs_smem) f(bf.obs_buf + e0 * O, s_obs, 4u * nenv * O);
-      if (do_hist) {
-        f(bf.last_actions + e0 * D, s_lact, 4u * nenv * D);
-        f(bf.last_dof_vel + e0 * D, s_ldv, 4u * nenv * D);
-        f(bf.last_root_vel + e0 * 6, s_lrv, 4u * nenv * 6);
-      }
-    };
     if (bulk) {
-      fence_async_smem();   // generic-proxy writes of every thread -> visible to the async (TMA) proxy
-      __syncthreads();
-      if (tid == 0) {
-        for_each_output([&](void* g, const void* s, uint32_t bytes) { bulk_s2g(g, s, bytes); });
-        bulk_commit();
+      if (active) {
+        fence_async_smem();   // this thread's generic-proxy writes -> visible to the async (TMA) proxy
+        const int s0 = sub * kSub;
+        const int ne = min(kSub, nenv - s0);
+        if (leader) {
+          named_bar_sync(1 + sub, 32 * ne);
+          for (int i = lane; i < L.n_out; i += 32) {
+            const CopyDesc d = L.out[i];
+            bulk_s2g(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)(env0 + s0) * d.bpe, smem_raw + d.soff + s0 * d.bpe, (uint32_t)(ne * d.bpe));
+          }
+          bulk_commit();
+          stores_pending = true;
+        } else {
+          named_bar_arrive(1 + sub, 32 * ne);
+        }
       }
-      stores_pending = true;
     } else {
       __syncthreads();
-      for_each_output([&](void* g, const void* s, uint32_t bytes) { coop_copy(g, s, bytes, tid, nthreads); });
+      for (int i = 0; i < L.n_out; ++i) {
+        const CopyDesc d = L.out[i];
+        coop_copy(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)env0 * d.bpe, smem_raw + d.soff, (uint32_t)(nenv * d.bpe), tid, nthreads);
+      }
     }
   }
-  if (stores_pending && tid == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  if (stores_pending) bulk_wait_all();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1035,16 +961,12 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
   const int N = dims->num_envs;
   if (N == 0) return ELG_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  // TMA bulk staging needs 16-byte aligned array bases; chunk offsets and sizes are multiples of 16 by construction
-  // (whole quads of envs) when N and the foot count are multiples of 4.  Otherwise: cooperative element-wise staging.
-  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
-  const void* ptrs[] = {buf->root_states, buf->dof_state, buf->actions, buf->last_actions, buf->last_dof_vel, buf->torques,
-                        buf->contact_forces, buf->last_root_vel, buf->base_lin_acc, buf->base_ang_acc, buf->commands,
-                        buf->feet_air_time, buf->feet_contact_time, buf->last_contacts, buf->episode_length_buf, buf->gait_idx,
-                        buf->gait_prev_foot_z, buf->base_lin_vel, buf->base_ang_vel, buf->projected_gravity, buf->foot_positions,
-                        buf->foot_velocities, buf->measured_heights, buf->episode_sums, buf->rew_buf, buf->obs_buf};
-  int use_bulk = (N % 4 == 0) && (dims->num_feet % 4 == 0) && g_tune.no_bulk == 0;
-  for (const void* p : ptrs) use_bulk = use_bulk && a16(p);
+  const int D = dims->num_dof, F = dims->num_feet, B = dims->num_bodies, H = dims->num_height_points, O = dims->num_obs, C = dims->num_commands;
+  const bool do_derive = phase & ELG_PHASE_DERIVE, do_term = phase & ELG_PHASE_TERMINATION, do_reward = phase & ELG_PHASE_REWARD;
+  const bool do_obs = phase & ELG_PHASE_OBS, do_hist = phase & ELG_PHASE_HISTORY;
+  const bool gait = buf->gait_idx && buf->gait_prev_foot_z;
+  const bool need_hsum = do_reward && ((prm->reward_mask >> ELG_REW_BASE_HEIGHT) & 1u) && H > 0;
+  const bool air_on = (prm->reward_mask >> ELG_REW_FEET_AIR_TIME) & 1u;
 
   static int sms = 0;
   if (sms == 0) {
@@ -1053,55 +975,179 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
       return fail(ELG_ERR_CUDA, "cannot query the SM count");
     sms = v;
   }
-  // chunking: whole quads of envs, balanced over the SMs (see the header comment of this file)
+  // ---- chunking: whole quads of envs, one warp per env, balanced over the SMs (see the header comment of this file)
   const long long Q = ((long long)N + 3) / 4;
-  const bool obs_smem = dims->num_obs == head + dims->num_height_points;
-  const int kSmemLimit = 227 * 1024;
-  int cap = 0, threads = 0, grid = 0, nchunks = 0, nstate = 0;
-  elg::StepPlan plan{};
-  auto try_plan = [&](int c, int th, int g, int nch) -> bool {
-    const int ns = (c + elg::kGroup - 1) / elg::kGroup;
-    if (th / 32 - ns < 1) return false;
-    elg::StepPlan pl = elg::make_plan(*dims, *prm, c, ns, obs_smem);
-    if ((size_t)pl.words * 4 + 1024 > (size_t)kSmemLimit) return false;
-    cap = c; threads = th; grid = g; nchunks = nch; nstate = ns; plan = pl;
-    return true;
-  };
-  bool ok = false;
-  if (g_tune.cap > 0) {   // explicit tuning (elg_set_step_tuning): cap envs per chunk, threads per CTA, CTAs per SM
-    const int c = g_tune.cap;
-    long long nch = (Q + c / 4 - 1) / (c / 4);
+  int cap, grid, nchunks;
+  if (g_tune.cap > 0) {   // explicit tuning (elg_set_step_tuning): envs per chunk, CTAs per SM
+    cap = g_tune.cap;
+    long long nch = (Q + cap / 4 - 1) / (cap / 4);
     const long long g = (long long)sms * g_tune.ctas_per_sm;
     if (nch > g) nch = (nch + g - 1) / g * g;
     if (nch > Q) nch = Q;
-    ok = try_plan(c, g_tune.threads, (int)(nch < g ? nch : g), (int)nch);
-  }
-  if (!ok && (Q + 7) / 8 <= sms) {   // at most one chunk per SM: one wide CTA per SM, every chunk <= 32 envs
-    const int nch = (int)(Q < sms ? Q : sms);
-    const int c = 4 * (int)((Q + nch - 1) / nch);
-    const int ns = (c + elg::kGroup - 1) / elg::kGroup;
-    int nrow = c < 32 - ns ? c : 32 - ns;
-    ok = try_plan(c, 32 * (ns + nrow), nch, nch);
-  }
-  for (int c = 16; !ok && c >= 4; c -= 4) {   // many chunks: narrow CTAs, 4 per SM, each looping over its chunks
-    const long long g = (long long)sms * 4;
-    long long nch = (Q + c / 4 - 1) / (c / 4);
+    nchunks = (int)nch;
+    grid = (int)(nch < g ? nch : g);
+  } else if ((Q + 7) / 8 <= sms) {   // at most one chunk per SM, every chunk <= 32 envs
+    nchunks = (int)(Q < sms ? Q : sms);
+    cap = 4 * (int)((Q + nchunks - 1) / nchunks);
+    grid = nchunks;
+  } else {                           // many chunks: 16-env CTAs, 2 per SM, each looping over its chunks
+    cap = 16;
+    const long long g = (long long)sms * 2;
+    long long nch = (Q + 3) / 4;
     if (nch > g) nch = (nch + g - 1) / g * g;
     if (nch > Q) nch = Q;
-    const int ns = (c + elg::kGroup - 1) / elg::kGroup;
-    ok = try_plan(c, 32 * (ns + 6), (int)(nch < g ? nch : g), (int)nch);
+    nchunks = (int)nch;
+    grid = (int)(nch < g ? nch : g);
   }
-  if (!ok) return fail(ELG_ERR_UNSUPPORTED, "robot dimensions do not fit the shared-memory plan of elg_step_kernel");
-  plan.nchunks = nchunks;
-  plan.use_bulk = use_bulk;
-  const size_t smem = (size_t)plan.words * 4;
-  static size_t smem_set = 0;
-  if (smem > smem_set) {
-    if (cudaFuncSetAttribute(elg::elg_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+  const int threads = 32 * cap;
+
+  // ---- shared-memory plan + copy tables
+  elg::StepPlan L{};
+  L.cap = cap;
+  L.nchunks = nchunks;
+  L.quads_base = (int)(Q / nchunks);
+  L.quads_rem = (int)(Q % nchunks);
+  L.obs_smem = (O == head + H) ? 1 : 0;
+  L.hm = (head + 31) / 32;
+  int nt = 0;
+  for (int t = 0; t < ELG_NUM_REWARD_TERMS; ++t)
+    if ((prm->reward_mask >> t) & 1u) L.term_ids[nt++] = (int8_t)t;
+  L.nterms = nt;
+  int off = 0;
+  auto take = [&](int bytes) { const int at = off; off += (bytes + 127) & ~127; return at; };
+  L.root = take(cap * 13 * 4);
+  L.dof = take(cap * 2 * D * 4);
+  L.act = take(cap * D * 4);
+  L.lact = take(cap * D * 4);
+  L.ldv = take(cap * D * 4);
+  L.tq = take(cap * D * 4);
+  L.cf = take(cap * B * 12);
+  L.lrv = take(cap * 24);
+  L.vec5 = take(5 * cap * 12);     // base_lin_vel, base_ang_vel, projected_gravity, base_lin_acc, base_ang_acc
+  L.cmd = take(cap * C * 4);
+  L.air = take(cap * F * 4);
+  L.con = take(cap * F * 4);
+  L.lc = take(cap * F);
+  L.ep = take(cap * 8);
+  L.gidx = take(cap * 4);
+  L.gprev = take(cap * F * 4);
+  L.fpos = take(cap * F * 12);
+  L.fvel = take(cap * F * 12);
+  L.sums = take((nt > 0 ? nt : 1) * cap * 4);
+  L.rew = take(cap * 4);
+  L.mh = take(cap * H * 4);
+  L.obs = take(cap * (L.obs_smem ? O : head) * 4);
+  L.q0 = take(D * 4);
+  L.plim = take(2 * D * 4);
+  L.vlim = take(D * 4);
+  L.tlim = take(D * 4);
+  L.ns = take(O * 4);
+  L.grid = take(H * 16);
+  L.acc = take(cap * 32 * 4);
+  L.bytes = off;
+  if ((size_t)L.bytes + 1024 > (size_t)227 * 1024)
+    return fail(ELG_ERR_UNSUPPORTED, "robot dimensions do not fit the shared-memory plan of elg_step_kernel");
+
+  int n_in = 0, n_out = 0, in_bpe = 0;
+  bool aligned = true;
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  auto in = [&](const void* g, int soff, int bpe) {
+    L.in[n_in++] = elg::CopyDesc{g, soff, bpe};
+    in_bpe += bpe;
+    aligned = aligned && a16(g);
+  };
+  auto out = [&](void* g, int soff, int bpe) {
+    L.out[n_out++] = elg::CopyDesc{g, soff, bpe};
+    aligned = aligned && a16(g);
+  };
+  const int v3 = cap * 12;
+  in(buf->root_states, L.root, 52);
+  in(buf->dof_state, L.dof, 8 * D);
+  in(buf->actions, L.act, 4 * D);
+  if (do_reward) {
+    in(buf->last_actions, L.lact, 4 * D);
+    in(buf->last_dof_vel, L.ldv, 4 * D);
+    in(buf->torques, L.tq, 4 * D);
+  }
+  if (do_term || do_reward) in(buf->contact_forces, L.cf, 12 * B);
+  if (do_derive) {
+    in(buf->last_root_vel, L.lrv, 24);
+    in(buf->base_lin_acc, L.vec5 + 3 * v3, 12);
+    in(buf->base_ang_acc, L.vec5 + 4 * v3, 12);
+  } else {
+    in(buf->base_lin_vel, L.vec5 + 0 * v3, 12);
+    in(buf->base_ang_vel, L.vec5 + 1 * v3, 12);
+    in(buf->projected_gravity, L.vec5 + 2 * v3, 12);
+    if (H > 0 && (do_obs || need_hsum)) in(buf->measured_heights, L.mh, 4 * H);
+    if (F > 0 && do_reward) {
+      in(buf->foot_positions, L.fpos, 12 * F);
+      in(buf->foot_velocities, L.fvel, 12 * F);
+    }
+  }
+  in(buf->commands, L.cmd, 4 * C);
+  if (F > 0 && do_reward) {
+    in(buf->feet_air_time, L.air, 4 * F);
+    in(buf->feet_contact_time, L.con, 4 * F);
+    in(buf->last_contacts, L.lc, F);
+  }
+  if (do_derive || do_term) in(buf->episode_length_buf, L.ep, 8);
+  if (gait && do_reward) {
+    in(buf->gait_idx, L.gidx, 4);
+    in(buf->gait_prev_foot_z, L.gprev, 4 * F);
+  }
+  if (do_reward)
+    for (int ti = 0; ti < nt; ++ti) in(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
+
+  if (do_derive) {
+    out(buf->base_lin_vel, L.vec5 + 0 * v3, 12);
+    out(buf->base_ang_vel, L.vec5 + 1 * v3, 12);
+    out(buf->projected_gravity, L.vec5 + 2 * v3, 12);
+    out(buf->base_lin_acc, L.vec5 + 3 * v3, 12);
+    out(buf->base_ang_acc, L.vec5 + 4 * v3, 12);
+    if (F > 0) {
+      out(buf->foot_positions, L.fpos, 12 * F);
+      out(buf->foot_velocities, L.fvel, 12 * F);
+    }
+    if (prm->heading_command) out(buf->commands, L.cmd, 4 * C);
+    out(buf->episode_length_buf, L.ep, 8);
+    if (H > 0) out(buf->measured_heights, L.mh, 4 * H);
+  }
+  if (do_reward) {
+    if (air_on && F > 0) {
+      out(buf->feet_air_time, L.air, 4 * F);
+      out(buf->feet_contact_time, L.con, 4 * F);
+      out(buf->last_contacts, L.lc, F);
+    }
+    for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
+    out(buf->rew_buf, L.rew, 4);
+    if (gait) {
+      out(buf->gait_idx, L.gidx, 4);
+      out(buf->gait_prev_foot_z, L.gprev, 4 * F);
+    }
+  }
+  if (do_obs && L.obs_smem) out(buf->obs_buf, L.obs, 4 * O);
+  if (do_hist) {
+    out(buf->last_actions, L.lact, 4 * D);
+    out(buf->last_dof_vel, L.ldv, 4 * D);
+    out(buf->last_root_vel, L.lrv, 24);
+  }
+  L.n_in = n_in;
+  L.n_out = n_out;
+  L.in_bpe = in_bpe;
+  // TMA bulk staging needs 16-byte aligned array bases; sub-chunk offsets and sizes are multiples of 16 by construction
+  // (whole quads of envs) when N and the foot count are multiples of 4.  Otherwise: cooperative element-wise staging.
+  L.use_bulk = (N % 4 == 0) && (F % 4 == 0) && aligned && g_tune.no_bulk == 0;
+
+  const size_t smem = (size_t)L.bytes;
+  const bool quad = (D == 12 && F == 4);
+  auto kern = quad ? elg::elg_step_kernel<12, 4> : elg::elg_step_kernel<0, 0>;
+  static size_t smem_set[2] = {0, 0};
+  if (smem > smem_set[quad ? 1 : 0]) {
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return fail(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_step_kernel");
-    smem_set = smem;
+    smem_set[quad ? 1 : 0] = smem;
   }
-  elg::elg_step_kernel<<<grid, threads, smem, st>>>(*dims, *prm, *buf, plan, phase);
+  kern<<<grid, threads, smem, st>>>(*dims, *prm, *buf, L, phase);
   return check_launch("elg_post_physics_step");
 }
 
@@ -1112,8 +1158,7 @@ int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm
   }
   if (envs_per_chunk < 4 || envs_per_chunk > elg::kMaxCap || envs_per_chunk % 4 != 0)
     return fail(ELG_ERR_INVALID_ARGUMENT, "envs_per_chunk must be a multiple of 4 in [4, 32]");
-  if (threads_per_cta < 64 || threads_per_cta > elg::kMaxStepThreads || threads_per_cta % 32 != 0)
-    return fail(ELG_ERR_INVALID_ARGUMENT, "threads_per_cta must be a multiple of 32 in [64, 1024]");
+  (void)threads_per_cta;   // v3: one warp per env, the CTA width follows envs_per_chunk
   if (ctas_per_sm < 1 || ctas_per_sm > 16) return fail(ELG_ERR_INVALID_ARGUMENT, "ctas_per_sm must be in [1, 16]");
   g_tune = StepTune{envs_per_chunk, threads_per_cta, ctas_per_sm, disable_bulk};
   return ELG_OK;

@@ -191,8 +191,9 @@ def _philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def test_in_kernel_philox_noise_is_exact_and_uniform():
-    """ELG_NOISE_PHILOX: the uniform attached to obs element (env, k) is word (k//32)%4 of
-    Philox4x32-10(counter=(env, k%32 + 32*(k//128), offset, 0), key=seed); obs = clean + (2u-1)*scale."""
+    """ELG_NOISE_PHILOX: obs element k has noise index k' = k in the head (k < 12+3D) and 32*ceil(head/32) + p for
+    height point p; its uniform is word (k'//32)%4 of Philox4x32-10(counter=(env, k'%32 + 32*(k'//128), offset, 0),
+    key=seed); obs = clean + (2u-1)*scale."""
     case, n = "anymal_c_rough", 3000
     cfg, spec, st = common.make_case_state(case, n, seed=6)
     hf = synthetic.make_height_field(seed=0)
@@ -207,6 +208,8 @@ def test_in_kernel_philox_noise_is_exact_and_uniform():
     noisy = env.obs_buf.cpu()
     O = env.num_obs
     e, k = np.meshgrid(np.arange(n), np.arange(O), indexing="ij")
+    head = 12 + 3 * env.num_dof
+    k = np.where(k < head, k, 32 * ((head + 31) // 32) + (k - head))
     words = _philox4x32_10(e, (k % 32) + 32 * (k // 128), 12345, 0, env.noise_seed & 0xFFFFFFFF, env.noise_seed >> 32)
     sel = (k // 32) % 4
     w = np.choose(sel, [x.astype(np.uint64) for x in words])
