@@ -57,7 +57,7 @@ class ElgStepParams(C.Structure):
 
 _BUF_FIELDS = [
     "root_states", "dof_state", "contact_forces", "rigid_body_state", "actions", "torques", "default_dof_pos",
-    "dof_pos_limits", "dof_vel_limits", "torque_limits", "height_samples", "height_points", "noise_scale_vec", "noise_u",
+    "dof_pos_limits", "dof_vel_limits", "torque_limits", "height_samples", "height_field_min", "height_points", "noise_scale_vec", "noise_u",
     "extra_reward",
     "last_actions", "last_dof_vel", "last_root_vel", "base_lin_acc", "base_ang_acc", "commands", "feet_air_time",
     "feet_contact_time", "last_contacts", "episode_length_buf", "episode_sums", "gait_idx", "gait_prev_foot_z",
@@ -104,6 +104,7 @@ def load() -> C.CDLL:
     lib.elg_post_physics_step.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams), C.POINTER(ElgStepBuffers), C.c_uint32, vp]
     lib.elg_set_step_tuning.argtypes = [C.c_int] * 4
     lib.elg_get_heights.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 5 + [vp]
+    lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib
     return lib
 

@@ -14,7 +14,7 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 LIB_PATH = os.path.join(PKG_DIR, "libelg_b200.so")
 STAMP = LIB_PATH + ".stamp"
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
+              "-shared", "-Xcompiler", "-fPIC", "-fmad=false", "--use_fast_math=false"]
 
 
 def _sources():

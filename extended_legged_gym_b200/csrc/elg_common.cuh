@@ -94,9 +94,11 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
 }
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
-// The uniform sample attached to observation element (env, k) at step `offset`: with the noise index
-// k' = k for the head (k < 12 + 3D) and 32*ceil(head/32) + p for height point p,
-// counter = (env, k' mod 32 + 32*(k' div 128), offset_lo, offset_hi), key = seed; word = (k' div 32) mod 4.
+// In-kernel observation noise: lane `lane` of the warp that owns env draws 128-bit blocks
+// Philox4x32-10(counter = (env, lane | block << 5, offset_lo, offset_hi), key = seed) and cuts each into eight 16-bit
+// uniforms (sample s = half (s & 1) of word s >> 1).  Height point p = lane + 32 j uses sample j % 8 of block 1 + j / 8;
+// head entry k = lane + 32 m uses sample (nj % 8) + m of block 1 + nj / 8 (nj = ceil(H / 32)) when
+// nj % 8 + ceil(head / 32) <= 8, else sample m % 8 of block m / 8.  obs += (2 s / 65536 - 1) * noise_scale.
 __device__ __forceinline__ uint4 noise_block(uint64_t seed, uint64_t offset, uint32_t env, uint32_t lane, uint32_t chunk) {
   return philox4x32_10(make_uint4(env, lane | (chunk << 5), (uint32_t)offset, (uint32_t)(offset >> 32)),
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));

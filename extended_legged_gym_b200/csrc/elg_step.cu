@@ -3,26 +3,26 @@
 // One launch of elg_step_kernel replaces the ~100 ATen launches of
 // LeggedRobot.post_physics_step (envs/base/legged_robot.py:113-150 in the reference).
 //
-// Design (v3, see DESIGN.md "step kernel"):
+// Design (v4, see DESIGN.md "step kernel"):
 //   * The environments are cut into CHUNKS of whole quads (4 envs), balanced so that every SM gets
 //     the same number of quads to within one: 4096 envs -> 148 chunks of 24..28 envs, one CTA per
-//     SM with one WARP PER ENVIRONMENT.  Large N: 512-thread CTAs, 2 per SM, each looping over
-//     16-env chunks.
+//     SM.  Large N: 12-env chunks, 13-warp CTAs, 2 per SM, each looping over its chunks.
 //   * TMA in, TMA out.  The envs of a chunk are consecutive, so every per-env array is ONE
 //     contiguous global range per chunk.  The host builds two copy tables (global base, shared
-//     offset, bytes per env); a chunk is cut into SUB-CHUNKS of 8 envs, each with its own mbarrier:
-//     the first warp of a sub-chunk issues one cp.async.bulk (global -> shared) per table entry,
-//     one entry per lane, and -- once the 8 warps of the sub-chunk have met at a named barrier --
-//     one cp.async.bulk (shared -> global) per output entry, including the [8, 235] observation
-//     block and the [8, 187] height block.  Sub-chunks load, compute and store independently, so
-//     the DRAM latency of one overlaps the arithmetic of the others; no CTA-wide barrier sits
-//     between staging and write-back.
-//   * A warp runs its environment end to end out of shared memory: the 187-point terrain scan
-//     (points lane + 32 j, unrolled by 3 so 9 height-field gathers are in flight per lane; the
-//     x/y halves of the terrain-cell chain use the packed FMUL2/FADD2/FFMA2 of sm_100a, every op
-//     individually IEEE-rounded so the cell index stays bit-exact with torch), then the
-//     O(D + F + B) state work with lane = item (rotation, dof, foot, body) and shuffle
-//     reductions, then the observation row (noise from in-register Philox4x32-10, clip).
+//     offset, bytes per env); warp 0 issues one cp.async.bulk (global -> shared, mbarrier
+//     completion) per input entry, a lane each, and at the end one cp.async.bulk (shared ->
+//     global) per output entry -- including the whole [n, 235] observation block and the [n, 187]
+//     height block.  The compute code only touches shared memory.
+//   * The step is latency-bound at 28 envs per SM (measured: profiles/README.md), so the work is
+//     laid out for SHORT dependent chains: every (env, foot / rotation / dof / contact body) item
+//     is a lane of a power-of-two segment and all warps take item passes at once (segmented
+//     shuffle butterflies for the per-env sums); then one spare "scalar" warp (lane == env) does
+//     commands, termination, the scalar reward terms and the ordered reward sum WHILE the row
+//     warps (warp == env) run the 187-point terrain scan.  The scan gathers ONE float per point
+//     from a min-of-3 table built once per terrain (elg_prepare_height_field); the x/y halves of
+//     the terrain-cell chain use the packed FMUL2/FADD2/FFMA2 of sm_100a, every op individually
+//     IEEE-rounded so the cell index stays bit-exact with torch.  Observation noise comes from
+//     in-register Philox4x32-10, one 128-bit block per lane per env cut into eight 16-bit samples.
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -32,8 +32,6 @@
 namespace elg {
 
 constexpr int kMaxCap = 32;       // environments per chunk (multiple of 4) == warps per CTA
-constexpr int kSub = 8;           // environments per sub-chunk (own mbarrier, own store group)
-constexpr int kMaxSub = kMaxCap / kSub;
 constexpr int kMaxStepThreads = 1024;
 constexpr int kMaxIn = 30 + ELG_NUM_REWARD_TERMS;
 constexpr int kMaxOut = 24 + ELG_NUM_REWARD_TERMS;
@@ -129,11 +127,12 @@ struct StepPlan {
   // staged per-env arrays, [slot][per-env]
   int root, dof, act, lact, ldv, tq, cf, lrv, vec5, cmd, air, con, lc, ep, gidx, gprev, fpos, fvel, sums, rew, mh, obs;
   // CTA-constant tables and per-warp scratch
-  int q0, plim, vlim, tlim, ns, grid, acc;
+  int q0, plim, vlim, tlim, ns, grid, acc, idx;
   int bytes;
   // launch geometry
   int cap, nchunks, quads_base, quads_rem, use_bulk, obs_smem, nterms, hm;
   int n_in, n_out, in_bpe;
+  long long* dbg;   // diagnostic: clock64 stamps of CTA 0 (elg_set_step_debug), or NULL
   int8_t term_ids[ELG_NUM_REWARD_TERMS];
   CopyDesc in[kMaxIn];
   CopyDesc out[kMaxOut];
@@ -202,39 +201,69 @@ __device__ __forceinline__ float lanes_sum(float v, int n) {   // n = number of 
   return bfly_sum<4>(v);
 }
 
-// observation post-processing shared by head and height entries (legged_robot.py:250-252, :107-108)
-__device__ __forceinline__ float finish_obs(float v, float u, float ns, int noise_mode, float clip) {
-  if (noise_mode != ELG_NOISE_OFF) v = v + (2.0f * u - 1.0f) * ns;
-  if (clip > 0.0f) v = fminf(fmaxf(v, -clip), clip);
-  return v;
+// 16-bit uniform sample s (0..7) of a 128-bit Philox block, as a float in [0, 65535]
+__device__ __forceinline__ float sample16(const uint4& r, int s) {   // s known at compile time after unrolling
+  const uint32_t w = (s >> 1) == 0 ? r.x : (s >> 1) == 1 ? r.y : (s >> 1) == 2 ? r.z : r.w;
+  return (float)((s & 1) ? (w >> 16) : (w & 0xffffu));
 }
+__device__ __forceinline__ float sample16_dyn(const uint4& r, int s) {
+  const int i = s >> 1;
+  const uint32_t w = i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
+  return (float)((w >> (16 * (s & 1))) & 0xffffu);
+}
+
 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel.  kD / kF > 0 fix the DOF / foot count at compile time (12 / 4 for every
 // quadruped of the BASELINE configs); 0 = take them from ElgDims.
+//
+// Stages of one chunk (n <= 32 envs, W = min(32, n + 1) warps):
+//   0  warp 0: one cp.async.bulk per copy-table entry (a lane each) into shared memory; foot lanes prefetch their
+//      strided rigid_body_state rows; everybody waits on the chunk's mbarrier.
+//   1  ITEM PASSES over all warps: every (env, foot), (env, rotation), (env, dof) and (env, contact body) is one lane
+//      in a power-of-two segment (4 / 8 / 16 / 16 lanes per env for a quadruped); per-env reductions are segmented
+//      shuffle butterflies, results land in the per-env accumulator table acc[term][env].
+//   2  the SCALAR warp (warp n, lane == env) evaluates commands, termination, the scalar reward terms, the ordered
+//      fp32 reward sum and the episode sums, while the ROW warps (warp == env) run the terrain scan and the height
+//      part of the observation row.
+//   3  row warps finish the head of the observation row (noise, clip); warp 0 issues one cp.async.bulk per output entry.
 // ---------------------------------------------------------------------------------------------
-template <int kD, int kF>
+template <int kD, int kF, bool kFast>
 __global__ void __launch_bounds__(kMaxStepThreads, 1)
 elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgStepParams pr,
                 const __grid_constant__ ElgStepBuffers bf, const __grid_constant__ StepPlan L, const uint32_t phase) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar[kMaxSub];
+  __shared__ __align__(8) uint64_t s_bar;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int nthreads = blockDim.x;
+  const int nthreads = blockDim.x, nwarps = nthreads >> 5;
+  const bool dbg_on = L.dbg != nullptr && blockIdx.x == 0;
+#define STAMP(i, w) if (dbg_on && warp == (w) && lane == 0) L.dbg[i] = clock64();
+  STAMP(0, 0)
   const int N = dm.num_envs, D = kD ? kD : dm.num_dof, B = dm.num_bodies, F = kF ? kF : dm.num_feet;
   const int H = dm.num_height_points, O = dm.num_obs, C = dm.num_commands, P = dm.num_penalised, T = dm.num_termination;
+  const int PT = P + T;
   const int cap = L.cap;
   const int head = 12 + 3 * D;
-  const bool do_derive = phase & ELG_PHASE_DERIVE, do_term = phase & ELG_PHASE_TERMINATION;
-  const bool do_reward = phase & ELG_PHASE_REWARD, do_obs = phase & ELG_PHASE_OBS, do_hist = phase & ELG_PHASE_HISTORY;
+  // kFast: the whole step in one launch (ELG_PHASE_FUSED) with the common data layout -- one [H,3] grid shared by all
+  // envs, min-of-3 height table present, observation rows exactly head + H wide, every array TMA-aligned.  The flags
+  // below fold at compile time, which keeps the instruction footprint of the hot instantiation inside the
+  // instruction caches; everything else runs through the kFast == false instantiation.
+  const bool do_derive = kFast || (phase & ELG_PHASE_DERIVE), do_term = kFast || (phase & ELG_PHASE_TERMINATION);
+  const bool do_reward = kFast || (phase & ELG_PHASE_REWARD), do_obs = kFast || (phase & ELG_PHASE_OBS);
+  const bool do_hist = kFast || (phase & ELG_PHASE_HISTORY);
   const bool need_hsum = do_reward && term_on(pr, ELG_REW_BASE_HEIGHT) && H > 0;
   const bool gait = bf.gait_idx != nullptr && bf.gait_prev_foot_z != nullptr;
   const bool lim_terms = term_on(pr, ELG_REW_DOF_POS_LIMITS) | term_on(pr, ELG_REW_DOF_VEL_LIMITS) | term_on(pr, ELG_REW_TORQUE_LIMITS);
   const bool heights_live = H > 0 && do_derive && !pr.terrain_is_plane;
-  const bool shared_grid = pr.height_points_env_stride == 0;
+  const bool shared_grid = kFast || pr.height_points_env_stride == 0;
   const int noise_mode = pr.noise_mode;
   const float clip_obs = pr.clip_observations;
+  // lanes per env of the four item types (powers of two, so that a segment never straddles a warp)
+  const int LD = kD ? (kD <= 16 ? 16 : 32) : (D <= 16 ? 16 : 32);
+  const int LF = kF ? (kF <= 4 ? 4 : 8) : (F <= 4 ? 4 : 8);
+  const int LP = PT <= 16 ? 16 : 32;
+  constexpr int LR = 8;
 
 #define SM_F(off) reinterpret_cast<float*>(smem_raw + (off))
   float* const s_root = SM_F(L.root);   float* const s_dof = SM_F(L.dof);    float* const s_act = SM_F(L.act);
@@ -250,42 +279,51 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
   float* const s_q0 = SM_F(L.q0);       float* const s_plim = SM_F(L.plim);  float* const s_vlim = SM_F(L.vlim);
   float* const s_tlim = SM_F(L.tlim);   float* const s_ns = SM_F(L.ns);
   float4* const s_grid = reinterpret_cast<float4*>(smem_raw + L.grid);
-  float* const s_acc = SM_F(L.acc) + warp * 32;   // this warp's raw reward terms, indexed by registry id
+  int* const s_feet = reinterpret_cast<int*>(smem_raw + L.idx);   // feet_idx[8] | contact bodies: penalised then termination [24]
+  int* const s_body = s_feet + ELG_MAX_FEET;
+  float* const s_acc = SM_F(L.acc);     // [kAccRows][32]: raw reward terms by registry id, then helper rows, lane == env
 #undef SM_F
+#define ACC(t, e) s_acc[(t) * 32 + (e)]
+  // helper rows behind the registry ids
+  constexpr int kFootZ = ELG_NUM_REWARD_TERMS, kFootN = kFootZ + 1, kHits = kFootZ + 2, kTermHit = kFootZ + 3, kHsum = kFootZ + 4;
 
-  // sub-chunk bookkeeping of this warp: slot == warp, sub-chunk == warp / kSub, leader == first warp of the sub-chunk
-  const int slot = warp;
-  const int sub = warp / kSub;
-  const bool leader = (warp % kSub) == 0;
-  uint64_t* const bar = &s_bar[sub];
-  if (leader && lane == 0) mbar_init(bar, 1);
-  if (leader) __syncwarp();
-
-  // issue the TMA loads of (chunk, this sub-chunk): one table entry per lane
+  auto feet_of = [&](int f) {   // warp-uniform constant-bank reads, lane-selected (used before the shared table exists)
+    int v = 0;
+    for (int i = 0; i < F; ++i) v = (f == i) ? dm.feet_idx[i] : v;
+    return v;
+  };
   auto chunk_range = [&](int chunk, int& env0, int& nenv) {
     const int q_lo = chunk * L.quads_base + min(chunk, L.quads_rem);
     const int q_n = L.quads_base + (chunk < L.quads_rem ? 1 : 0);
     env0 = q_lo * 4;
     nenv = min(N, (q_lo + q_n) * 4) - env0;
   };
-  auto issue_loads = [&](int env0, int nenv) {
-    const int s0 = sub * kSub;
-    const int ne = min(kSub, nenv - s0);
-    if (lane == 0) mbar_expect_tx(bar, (uint32_t)(ne * L.in_bpe));
-    __syncwarp();
-    for (int i = lane; i < L.n_in; i += 32) {
-      const CopyDesc d = L.in[i];
-      bulk_g2s(smem_raw + d.soff + s0 * d.bpe, static_cast<const uint8_t*>(d.g) + (size_t)(env0 + s0) * d.bpe, (uint32_t)(ne * d.bpe), bar);
-    }
+  auto issue_loads = [&](int env0, int nenv) {   // every warp: lane 0 issues table entries warp, warp + nwarps, ...
+    if (tid == 0) mbar_expect_tx(&s_bar, (uint32_t)(nenv * L.in_bpe));
+    if (lane == 0)
+      for (int i = warp; i < L.n_in; i += nwarps) {
+        const CopyDesc d = L.in[i];
+        bulk_g2s(smem_raw + d.soff, static_cast<const uint8_t*>(d.g) + (size_t)env0 * d.bpe, (uint32_t)(nenv * d.bpe), &s_bar);
+      }
   };
 
   int chunk = blockIdx.x;
   int env0 = 0, nenv = 0;
   if (chunk < L.nchunks) chunk_range(chunk, env0, nenv);
   bool bulk = L.use_bulk && (nenv & 3) == 0;
-  if (chunk < L.nchunks && bulk && leader && slot < nenv) issue_loads(env0, nenv);
+  if (tid == 0) mbar_init(&s_bar, 1);
+  __syncthreads();
+  if (chunk < L.nchunks && bulk) issue_loads(env0, nenv);
 
   // ------------------------------- CTA-constant tables (overlap the loads in flight) -------------------------------
+  // (kernel parameters live in the constant bank: lane-divergent indexing there is serialised, so the index tables
+  //  are copied to shared memory with warp-uniform reads)
+  if (warp == nwarps - 1) {
+    // one warp, once per CTA, off the critical path (everybody else is waiting for the bulk loads)
+    if (lane < F) s_feet[lane] = dm.feet_idx[lane];
+    if (lane < P) s_body[lane] = dm.penalised_idx[lane];
+    if (lane < T) s_body[P + lane] = dm.termination_idx[lane];
+  }
   for (int j = tid; j < D; j += nthreads) {
     s_q0[j] = __ldg(bf.default_dof_pos + j);
     if (lim_terms) {
@@ -304,246 +342,82 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       const float bx = __ldg(bf.height_points + 3 * p), by = __ldg(bf.height_points + 3 * p + 1);
       s_grid[p] = make_float4(bx, by, by, bx);
     }
+  STAMP(1, 0)
   __syncthreads();   // tables + mbarrier initialisation visible to every warp
+  STAMP(2, 0)
 
-  uint32_t parity = 0;          // phase parity of this warp's sub-chunk barrier
-  bool stores_pending = false;  // leader lanes: a bulk store group of this sub-chunk may still be reading shared memory
+  uint32_t parity = 0;
+  bool stores_pending = false;   // lane 0 of every warp: its bulk store group may still be reading shared memory
 
   for (; chunk < L.nchunks; chunk += gridDim.x) {
     if (chunk != (int)blockIdx.x) {
       chunk_range(chunk, env0, nenv);
       bulk = L.use_bulk && (nenv & 3) == 0;
-      if (bulk && leader && slot < nenv) {
-        if (stores_pending) bulk_wait_read_all();   // the previous stores have left shared memory
-        stores_pending = false;
-        __syncwarp();
-        issue_loads(env0, nenv);
-      }
+      if (stores_pending) bulk_wait_read_all();   // this thread's previous stores have left shared memory ...
+      stores_pending = false;
+      __syncthreads();                              // ... and so have everybody else's
+      if (bulk) issue_loads(env0, nenv);
     }
-    if (!bulk) {
-      if (stores_pending) { bulk_wait_read_all(); stores_pending = false; }
-      __syncthreads();
+    const int n = nenv;
+    // item-pass geometry: [foot | rotation | dof | body] passes, one warp each
+    const int wF = (F > 0) ? (n * LF + 31) >> 5 : 0;
+    const int wR = (n * LR + 31) >> 5;
+    const int wD = (n * LD + 31) >> 5;
+    const int wP = (PT > 0) ? (n * LP + 31) >> 5 : 0;
+    const int n_passes = wF + wR + wD + wP;
+
+    // ---- stage 0: foot lanes prefetch their rigid_body_state rows (52-byte rows, 6 useful floats) while the bulk
+    // copies are in flight; kept in registers until the wait below (shared memory may still feed the previous stores)
+    float fr[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
+    const int f_e = (warp * 32 + lane) / LF, f_f = lane & (LF - 1);
+    const bool foot_lane = warp < wF && f_e < n && f_f < F;
+    if (foot_lane && do_derive) {
+      const float* row = bf.rigid_body_state + ((size_t)(env0 + f_e) * B + feet_of(f_f)) * 13;
+      fr[0] = __ldg(row + 0); fr[1] = __ldg(row + 1); fr[2] = __ldg(row + 2);
+      fr[3] = __ldg(row + 7); fr[4] = __ldg(row + 8); fr[5] = __ldg(row + 9);
+    }
+    if (kFast || bulk) {
+      mbar_wait(&s_bar, parity);
+      parity ^= 1u;
+    } else {
       for (int i = 0; i < L.n_in; ++i) {
         const CopyDesc d = L.in[i];
         coop_copy(smem_raw + d.soff, static_cast<const uint8_t*>(d.g) + (size_t)env0 * d.bpe, (uint32_t)(nenv * d.bpe), tid, nthreads);
       }
-    }
-    const bool active = slot < nenv;
-    const int env = env0 + slot;
-    // feet rows of rigid_body_state are a strided gather (52-byte rows, 6 useful floats per row): plain loads, issued
-    // before the wait so that their latency overlaps the bulk copies
-    // (into registers: shared memory may still be read by the previous chunk's bulk stores until the wait below)
-    float feet_v[2] = {0.0f, 0.0f};
-    const bool feet_gather = active && do_derive && F > 0;
-    if (feet_gather) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int r = lane + 32 * u;
-        if (r < F * 6) {
-          const int f = r / 6, c = r - 6 * f;
-          feet_v[u] = __ldg(bf.rigid_body_state + ((size_t)env * B + dm.feet_idx[f]) * 13 + (c < 3 ? c : c + 4));
-        }
-      }
-    }
-    if (bulk) {
-      if (active) {
-        mbar_wait(bar, parity);
-        parity ^= 1u;
-      }
-    } else {
       __syncthreads();
     }
-    if (feet_gather) {
-#pragma unroll
-      for (int u = 0; u < 2; ++u) {
-        const int r = lane + 32 * u;
-        if (r < F * 6) {
-          const int f = r / 6, c = r - 6 * f;
-          (c < 3 ? s_fpos : s_fvel)[(slot * F + f) * 3 + (c < 3 ? c : c - 3)] = feet_v[u];
-        }
-      }
-    }
-    __syncwarp();
 
-    if (active) {
-      const float* rs = s_root + slot * 13;
-      const float rootz = rs[2];
-      float hsum = 0.0f;
-
-      // =========================== terrain scan (legged_robot.py:900-938) ===========================
-      if (H > 0 && do_derive) {
-        float* mh = s_mh + slot * H;
-        if (heights_live) {
-          const int16_t* __restrict__ hs = bf.height_samples;
-          const float r_h = __frcp_rn(pr.horizontal_scale);
-          const f32x2 rr = pack2(r_h, r_h), nc = pack2(-pr.horizontal_scale, -pr.horizontal_scale);
-          const f32x2 bord = pack2(pr.border_size, pr.border_size);
-          const int cols = pr.hf_cols, rmax = pr.hf_rows - 2, cmax = pr.hf_cols - 2;
-          float n = __fsqrt_rn(add_r(mul_r(rs[5], rs[5]), mul_r(rs[6], rs[6])));
-          n = fmaxf(n, 1e-9f);
-          const float zz = div_r(rs[5], n), ww = div_r(rs[6], n);
-          // t = 2 (q x b) = (-2 zz by, 2 zz bx); 2*RN(x) == RN(2x), so the doubling is folded into the multiplier
-          const f32x2 c_t = pack2(-mul_r(zz, 2.0f), mul_r(zz, 2.0f));    // times (by, bx) -> (tx, ty)
-          const f32x2 c_ts = pack2(mul_r(zz, 2.0f), -mul_r(zz, 2.0f));   // times (bx, by) -> (ty, tx)
-          const f32x2 c_w = pack2(ww, ww), c_u = pack2(-zz, zz), xy = pack2(rs[0], rs[1]);
-          const float* hp_env = shared_grid ? nullptr : bf.height_points + (size_t)env * pr.height_points_env_stride;
-          auto cell_of = [&](int p) -> const int16_t* {
-            f32x2 b, bs;
-            if (shared_grid) {
-              const float4 g = s_grid[p];
-              b = pack2(g.x, g.y);
-              bs = pack2(g.z, g.w);
-            } else {
-              const float bx = __ldg(hp_env + 3 * p), by = __ldg(hp_env + 3 * p + 1);
-              b = pack2(bx, by);
-              bs = pack2(by, bx);
-            }
-            const f32x2 t = mul2(c_t, bs);          // (tx, ty)
-            const f32x2 ts = mul2(c_ts, b);         // (ty, tx)
-            f32x2 pt = add2(b, mul2(c_w, t));       // b + w t
-            pt = add2(pt, mul2(c_u, ts));           // + q_xyz x t = (-zz ty, zz tx)
-            pt = add2(add2(pt, xy), bord);          // + base xy, + border_size
-            // correctly rounded pt / horizontal_scale: q0 = x r, two FMA residual corrections (Markstein)
-            f32x2 q = mul2(pt, rr);
-            f32x2 e = fma2(nc, q, pt);
-            q = fma2(e, rr, q);
-            e = fma2(nc, q, pt);
-            q = fma2(e, rr, q);
-            float qx, qy;
-            unpack2(q, qx, qy);
-            int ix = __float2int_rz(qx), iy = __float2int_rz(qy);
-            ix = min(max(ix, 0), rmax);
-            iy = min(max(iy, 0), cmax);
-            return hs + ix * cols + iy;
-          };
-          constexpr int kU = 3;
-          for (int p0 = lane; p0 < H; p0 += 32 * kU) {
-            int a0[kU], a1[kU], a2[kU];
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const int p = p0 + 32 * u;
-              if (p < H) {
-                const int16_t* cell = cell_of(p);
-                a0[u] = __ldg(cell);
-                a1[u] = __ldg(cell + cols);
-                a2[u] = __ldg(cell + 1);
-              }
-            }
-#pragma unroll
-            for (int u = 0; u < kU; ++u) {
-              const int p = p0 + 32 * u;
-              if (p < H) {
-                const float h = mul_r((float)min(min(a0[u], a1[u]), a2[u]), pr.vertical_scale);
-                mh[p] = h;
-                hsum += sub_r(rootz, h);
-              }
-            }
-          }
-        } else {
-          for (int p = lane; p < H; p += 32) {
-            mh[p] = 0.0f;
-            hsum += rootz;
-          }
-        }
-      } else if (need_hsum) {
-        for (int p = lane; p < H; p += 32) hsum += sub_r(rootz, s_mh[slot * H + p]);
-      }
-      if (need_hsum) hsum = bfly_sum<32>(hsum);
-
-      // =========================== state work: lane == item ===========================
-      // ---- episode counter (legged_robot.py:122)
-      if (do_derive && lane == 0) s_ep[slot] += 1;
-
-      // ---- lanes 0..4: base-frame velocities, gravity, acceleration EMAs (:128-134)
-      if (do_derive && lane < 5) {
-        const int r = lane;
-        const Quat q = {rs[3], rs[4], rs[5], rs[6]};
-        Vec3 v;
-        if (r == 2) {
-          v = Vec3{pr.gravity_vec[0], pr.gravity_vec[1], pr.gravity_vec[2]};
-        } else {
-          const int k = (r == 1 || r == 4) ? 10 : 7;
-          v = Vec3{rs[k], rs[k + 1], rs[k + 2]};
-          if (r >= 3) {
-            const float* lrv = s_lrv + slot * 6 + (r - 3) * 3;
-            v.x -= lrv[0]; v.y -= lrv[1]; v.z -= lrv[2];
-          }
-        }
-        Vec3 o = quat_rotate_inverse(q, v);
-        float* dst = s_vec5 + (r * cap + slot) * 3;
-        if (r >= 3) {
-          const float ema = pr.acc_ema, w1 = pr.acc_ema_c;
-          o.x = dst[0] * ema + (w1 * o.x) / pr.dt;
-          o.y = dst[1] * ema + (w1 * o.y) / pr.dt;
-          o.z = dst[2] * ema + (w1 * o.z) / pr.dt;
-        }
-        dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
-      }
-      __syncwarp();
-
-      // observation row: raw head entries first, finished in place below.  When the caller's rows are wider than
-      // head + H (user-extended observations) only the head is staged and the finished entries go straight to global.
-      float* orow = s_obs + slot * (L.obs_smem ? O : head);
-      float* hrow = orow;
-
-      // ---- lanes 0..D-1: per-dof reward partials, observation entries, history (:84-114, :237-244, :148-149)
-      {
-        float q_ar = 0.0f, q_da = 0.0f, q_dv = 0.0f, q_tq = 0.0f, q_ss = 0.0f, q_pl = 0.0f, q_vl = 0.0f, q_tl = 0.0f;
-        if (lane < D) {
-          const int j = lane, fi = slot * D + j;
-          const float2 pv = *reinterpret_cast<const float2*>(s_dof + 2 * fi);
-          const float pos = pv.x, vel = pv.y;
-          const float a = s_act[fi], q0 = s_q0[j];
-          if (do_reward) {
-            const float la = s_lact[fi], lv = s_ldv[fi], tq = s_tq[fi];
-            const float da = la - a;
-            q_ar = da * da;
-            const float dv = (lv - vel) / pr.dt;
-            q_da = dv * dv;
-            q_dv = vel * vel;
-            q_tq = tq * tq;
-            q_ss = fabsf(pos - q0);
-            if (lim_terms) {
-              q_pl = -fminf(pos - s_plim[2 * j], 0.0f) + fmaxf(pos - s_plim[2 * j + 1], 0.0f);
-              q_vl = fminf(fmaxf(fabsf(vel) - s_vlim[j], 0.0f), 1.0f);
-              q_tl = fmaxf(fabsf(tq) - s_tlim[j], 0.0f);
-            }
-          }
-          if (do_obs) {
-            hrow[12 + j] = (pos - q0) * pr.obs_scale_dof_pos;
-            hrow[12 + D + j] = vel * pr.obs_scale_dof_vel;
-            hrow[12 + 2 * D + j] = a;
-          }
-          if (do_hist) {
-            s_lact[fi] = a;
-            s_ldv[fi] = vel;
-          }
-        }
-        if (do_reward) {
-          if (term_on(pr, ELG_REW_ACTION_RATE)) { q_ar = lanes_sum(q_ar, D); if (lane == 0) s_acc[ELG_REW_ACTION_RATE] = q_ar; }
-          if (term_on(pr, ELG_REW_DOF_ACC)) { q_da = lanes_sum(q_da, D); if (lane == 0) s_acc[ELG_REW_DOF_ACC] = q_da; }
-          if (term_on(pr, ELG_REW_DOF_VEL)) { q_dv = lanes_sum(q_dv, D); if (lane == 0) s_acc[ELG_REW_DOF_VEL] = q_dv; }
-          if (term_on(pr, ELG_REW_TORQUES)) { q_tq = lanes_sum(q_tq, D); if (lane == 0) s_acc[ELG_REW_TORQUES] = q_tq; }
-          if (term_on(pr, ELG_REW_STAND_STILL)) q_ss = lanes_sum(q_ss, D);   // finished with the command gate below
-          if (term_on(pr, ELG_REW_DOF_POS_LIMITS)) { q_pl = lanes_sum(q_pl, D); if (lane == 0) s_acc[ELG_REW_DOF_POS_LIMITS] = q_pl; }
-          if (term_on(pr, ELG_REW_DOF_VEL_LIMITS)) { q_vl = lanes_sum(q_vl, D); if (lane == 0) s_acc[ELG_REW_DOF_VEL_LIMITS] = q_vl; }
-          if (term_on(pr, ELG_REW_TORQUE_LIMITS)) { q_tl = lanes_sum(q_tl, D); if (lane == 0) s_acc[ELG_REW_TORQUE_LIMITS] = q_tl; }
-        }
-
-        // ---- lanes 0..F-1: feet (legged_robot_rew_mixin.py:58-81, :121-212; gait_scheduler.py:74-81)
+    STAMP(3, 0)
+    // =========================== stage 1: item passes ===========================
+    for (int wp = warp; wp < n_passes; wp += nwarps) {
+      if (wp < wF) {
+        // ---- (env, foot) (legged_robot_rew_mixin.py:58-81, :121-212; gait_scheduler.py:74-81)
         // Terms that sort before feet_air_time read the OLD timers, terms after it the updated ones
         // and the rebound last_contacts.
+        const int e = (wp * 32 + lane) / LF, f = lane & (LF - 1);
+        const bool ok = e < n && f < F;
+        const int fi = e * F + f;
         float f_tz = 0.0f, f_tn = 0.0f, f_air = 0.0f, f_cf = 0.0f, f_slip = 0.0f, f_lift = 0.0f, f_jump = 0.0f, f_stum = 0.0f,
               f_down = 0.0f, f_gs = 0.0f;
-        if (do_reward && F > 0) {
-          const bool air_on = term_on(pr, ELG_REW_FEET_AIR_TIME);
-          const bool gs_on = term_on(pr, ELG_REW_GAIT_SCHEDULER) && gait;
-          if (lane < F) {
-            const int f = lane, fi = slot * F + f;
-            const float* cf = s_cf + (slot * B + dm.feet_idx[f]) * 3;
+        const bool air_on = term_on(pr, ELG_REW_FEET_AIR_TIME);
+        const bool gs_on = term_on(pr, ELG_REW_GAIT_SCHEDULER) && gait;
+        if (ok) {
+          if (do_derive) {
+            if (wp != warp) {   // not the prefetched pass (only for > 32 * 32 / LF feet lanes): load now
+              const float* row = bf.rigid_body_state + ((size_t)(env0 + e) * B + s_feet[f]) * 13;
+              fr[0] = __ldg(row + 0); fr[1] = __ldg(row + 1); fr[2] = __ldg(row + 2);
+              fr[3] = __ldg(row + 7); fr[4] = __ldg(row + 8); fr[5] = __ldg(row + 9);
+            }
+            s_fpos[fi * 3] = fr[0]; s_fpos[fi * 3 + 1] = fr[1]; s_fpos[fi * 3 + 2] = fr[2];
+            s_fvel[fi * 3] = fr[3]; s_fvel[fi * 3 + 1] = fr[4]; s_fvel[fi * 3 + 2] = fr[5];
+          } else if (do_reward) {
+            fr[2] = s_fpos[fi * 3 + 2];
+            fr[3] = s_fvel[fi * 3]; fr[4] = s_fvel[fi * 3 + 1]; fr[5] = s_fvel[fi * 3 + 2];
+          }
+          if (do_reward) {
+            const float* cf = s_cf + (e * B + s_feet[f]) * 3;
             const float fxx = cf[0], fyy = cf[1], fz = cf[2];
-            const float pz = s_fpos[fi * 3 + 2];
-            const float vx = s_fvel[fi * 3], vy = s_fvel[fi * 3 + 1], vz = s_fvel[fi * 3 + 2];
+            const float pz = fr[2], vx = fr[3], vy = fr[4], vz = fr[5];
             float air = s_air[fi], con = s_con[fi];
             const bool last_c = s_lc[fi] != 0;
             const bool contact = fz > 1.0f;
@@ -574,7 +448,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
             f_stum = stumble ? 1.0f : 0.0f;
             f_down = fz < 1.0f ? 0.0f : 1.0f;   // number of feet that are NOT up
             if (gs_on) {
-              float ph = s_gidx[slot] + pr.gait_foot_phases[f];
+              float ph = s_gidx[e] + pr.gait_foot_phases[f];
               ph = ph - floorf(ph);                                 // torch.remainder(x, 1.0)
               const float target = ph < 0.5f ? pr.gait_swing_height * sinf(6.283185307179586f * ph) : 0.0f;
               const float dz = target - s_gprev[fi];
@@ -582,206 +456,426 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
             }
             if (gait) s_gprev[fi] = pz;   // GaitScheduler.step keeps this step's feet
           }
-          if (term_on(pr, ELG_REW_BASE_FOOT_HEIGHT)) { f_tz = lanes_sum(f_tz, F); f_tn = lanes_sum(f_tn, F); }
-          if (air_on) f_air = lanes_sum(f_air, F);
-          if (term_on(pr, ELG_REW_FEET_CONTACT_FORCES)) f_cf = lanes_sum(f_cf, F);
-          if (term_on(pr, ELG_REW_FEET_SLIP)) f_slip = lanes_sum(f_slip, F);
-          if (term_on(pr, ELG_REW_FEET_STUMBLE_LIFTUP)) f_lift = lanes_sum(f_lift, F);
-          if (term_on(pr, ELG_REW_JUMP_AIR)) f_jump = lanes_sum(f_jump, F);
-          if (term_on(pr, ELG_REW_FEET_STUMBLE)) f_stum = lanes_sum(f_stum, F);
-          if (term_on(pr, ELG_REW_FOUR_FOOTUP)) f_down = lanes_sum(f_down, F);
-          if (gs_on) f_gs = lanes_sum(f_gs, F);
         }
-
-        // ---- lanes 0..P+T-1: collision count and termination contacts (:117-119, legged_robot.py:155-160)
-        unsigned hit_mask = 0;
-        if (do_term || do_reward) {
-          bool hit = false;
-          if (lane < P + T) {
-            const int body = lane < P ? dm.penalised_idx[lane] : dm.termination_idx[lane - P];
-            const float* f = s_cf + (slot * B + body) * 3;
-            hit = norm3_t(f[0], f[1], f[2]) > (lane < P ? 0.1f : 1.0f);
-          }
-          hit_mask = __ballot_sync(0xffffffffu, hit);
+        if (do_reward) {
+          const bool lead = ok && f == 0;
+#define FOOT_RED(on, var, row)                                   \
+  if (on) {                                                      \
+    var = (LF == 4) ? bfly_sum<4>(var) : bfly_sum<8>(var);       \
+    if (lead) ACC(row, e) = var;                                 \
+  }
+          FOOT_RED(term_on(pr, ELG_REW_BASE_FOOT_HEIGHT), f_tz, kFootZ)
+          FOOT_RED(term_on(pr, ELG_REW_BASE_FOOT_HEIGHT), f_tn, kFootN)
+          FOOT_RED(air_on, f_air, ELG_REW_FEET_AIR_TIME)
+          FOOT_RED(term_on(pr, ELG_REW_FEET_CONTACT_FORCES), f_cf, ELG_REW_FEET_CONTACT_FORCES)
+          FOOT_RED(term_on(pr, ELG_REW_FEET_SLIP), f_slip, ELG_REW_FEET_SLIP)
+          FOOT_RED(term_on(pr, ELG_REW_FEET_STUMBLE_LIFTUP), f_lift, ELG_REW_FEET_STUMBLE_LIFTUP)
+          FOOT_RED(term_on(pr, ELG_REW_JUMP_AIR), f_jump, ELG_REW_JUMP_AIR)
+          FOOT_RED(term_on(pr, ELG_REW_FEET_STUMBLE), f_stum, ELG_REW_FEET_STUMBLE)
+          FOOT_RED(term_on(pr, ELG_REW_FOUR_FOOTUP), f_down, ELG_REW_FOUR_FOOTUP)
+          FOOT_RED(gs_on, f_gs, ELG_REW_GAIT_SCHEDULER)
+#undef FOOT_RED
         }
-        __syncwarp();   // timers / last_contacts written by the foot lanes are read by every lane below
-
-        // ---- every lane (uniform): commands, termination, scalar reward terms, head; lane 0 stores
-        const float* blv = s_vec5 + (0 * cap + slot) * 3;
-        const float* bav = s_vec5 + (1 * cap + slot) * 3;
-        const float* pg = s_vec5 + (2 * cap + slot) * 3;
-        float* cmd = s_cmd + slot * C;
-        float cmd2 = cmd[2];
-        if (do_derive && pr.heading_command) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
+      } else if (wp < wF + wR) {
+        // ---- (env, rotation): base-frame velocities, gravity, acceleration EMAs (:128-134); root-velocity history (:150)
+        const int e = ((wp - wF) * 32 + lane) / LR, r = lane & (LR - 1);
+        const bool ok = e < n;
+        const float* rs = s_root + e * 13;
+        if (ok && do_derive && r < 5) {
           const Quat q = {rs[3], rs[4], rs[5], rs[6]};
-          const float fx = 1.0f + (q.y * (-2.0f * q.y) - q.z * (2.0f * q.z));
-          const float fy = q.w * (2.0f * q.z) + (q.z * 0.0f - q.x * (-2.0f * q.y));
-          const float heading = atan2f(fy, fx);
-          cmd2 = fminf(fmaxf(0.5f * wrap_to_pi(cmd[3] - heading), -1.0f), 1.0f);
-          __syncwarp();
-          if (lane == 0) cmd[2] = cmd2;
-        }
-        const float cmd0 = cmd[0], cmd1 = cmd[1], cmd3 = C > 3 ? cmd[3] : 0.0f;
-        bool reset = false, time_out = false;
-        if (do_term) {
-          const bool contact_term = (hit_mask >> P) != 0u;
-          time_out = s_ep[slot] > pr.max_episode_length;
-          reset = contact_term | time_out;
-          if (lane == 0) {
-            bf.reset_buf[env] = reset ? 1 : 0;
-            bf.time_out_buf[env] = time_out ? 1 : 0;
-          }
-        } else if (do_reward) {
-          reset = bf.reset_buf[env] != 0;
-          time_out = bf.time_out_buf[env] != 0;
-        }
-        if (do_reward) {
-          const float cmd_xy = norm2_t(cmd0, cmd1);
-          if (lane == 0) {
-#define ACC(t) s_acc[t]
-            if (term_on(pr, ELG_REW_STAND_STILL)) ACC(ELG_REW_STAND_STILL) = q_ss * (cmd_xy < pr.stand_still_threshold ? 1.0f : 0.0f);
-            if (term_on(pr, ELG_REW_LIN_VEL_Z)) ACC(ELG_REW_LIN_VEL_Z) = blv[2] * blv[2];
-            if (term_on(pr, ELG_REW_ANG_VEL_XY)) ACC(ELG_REW_ANG_VEL_XY) = bav[0] * bav[0] + bav[1] * bav[1];
-            if (term_on(pr, ELG_REW_ORIENTATION)) ACC(ELG_REW_ORIENTATION) = pg[0] * pg[0] + pg[1] * pg[1];
-            if (term_on(pr, ELG_REW_TRACKING_LIN_VEL)) {
-              const float ex = cmd0 - blv[0], ey = cmd1 - blv[1];
-              ACC(ELG_REW_TRACKING_LIN_VEL) = expf(-(ex * ex + ey * ey) / pr.tracking_sigma);
-            }
-            if (term_on(pr, ELG_REW_TRACKING_ANG_VEL)) {
-              const float ez = cmd2 - bav[2];
-              ACC(ELG_REW_TRACKING_ANG_VEL) = expf(-(ez * ez) / pr.tracking_sigma);
-            }
-            if (term_on(pr, ELG_REW_TERMINATION)) ACC(ELG_REW_TERMINATION) = (reset && !time_out) ? 1.0f : 0.0f;
-            if (term_on(pr, ELG_REW_COLLISION)) ACC(ELG_REW_COLLISION) = (float)__popc(hit_mask & ((1u << P) - 1u));
-            if (term_on(pr, ELG_REW_BASE_FOOT_HEIGHT)) {
-              const float ground = f_tn > 0.0f ? f_tz / f_tn : rootz - pr.base_height_target;
-              const float rel = rootz - ground - pr.base_height_target;
-              ACC(ELG_REW_BASE_FOOT_HEIGHT) = rel * rel;
-            }
-            if (term_on(pr, ELG_REW_FEET_AIR_TIME)) ACC(ELG_REW_FEET_AIR_TIME) = f_air * (cmd_xy > 0.1f ? 1.0f : 0.0f);
-            if (term_on(pr, ELG_REW_FEET_CONTACT_FORCES)) ACC(ELG_REW_FEET_CONTACT_FORCES) = f_cf;
-            if (term_on(pr, ELG_REW_FEET_SLIP)) ACC(ELG_REW_FEET_SLIP) = f_slip;
-            if (term_on(pr, ELG_REW_FEET_STUMBLE_LIFTUP)) ACC(ELG_REW_FEET_STUMBLE_LIFTUP) = f_lift;
-            if (term_on(pr, ELG_REW_JUMP_AIR)) ACC(ELG_REW_JUMP_AIR) = fmaxf(f_jump - (float)F / 2.0f, 0.0f);
-            if (term_on(pr, ELG_REW_FEET_STUMBLE)) ACC(ELG_REW_FEET_STUMBLE) = f_stum > 0.0f ? 1.0f : 0.0f;
-            if (term_on(pr, ELG_REW_FOUR_FOOTUP)) ACC(ELG_REW_FOUR_FOOTUP) = f_down == 0.0f ? 0.1f : 0.0f;
-            if (term_on(pr, ELG_REW_GAIT_SCHEDULER)) ACC(ELG_REW_GAIT_SCHEDULER) = f_gs;
-            if (term_on(pr, ELG_REW_GAIT_2_STEP)) {
-              // gait_2_step (legged_robot_rew_mixin.py:170-206): FL/RR and FR/RL in phase, the rest anti-phase
-              const float* ar = s_air + slot * F;
-              const float* cn = s_con + slot * F;
-              const float a0 = F > 0 ? ar[0] : 0.0f, a1 = F > 1 ? ar[1] : 0.0f, a2 = F > 2 ? ar[2] : 0.0f, a3 = F > 3 ? ar[3] : 0.0f;
-              const float c0 = F > 0 ? cn[0] : 0.0f, c1 = F > 1 ? cn[1] : 0.0f, c2 = F > 2 ? cn[2] : 0.0f, c3 = F > 3 ? cn[3] : 0.0f;
-              auto sq4 = [](float a, float b) { const float d = a - b; return fminf(d * d, 4.0f); };
-              const float s = ((sq4(a0, a3) + sq4(c0, c3)) + (sq4(a1, a2) + sq4(c1, c2))) / 2.0f;
-              const float a = ((sq4(a0, c1) + sq4(c0, a1)) + (sq4(a0, c2) + sq4(c0, a2)) + (sq4(a3, c2) + sq4(c3, a2)) +
-                               (sq4(a3, c1) + sq4(c3, a1))) / 4.0f;
-              const float yawish = pr.heading_command ? cmd3 : cmd2;
-              const bool moving = (cmd_xy > pr.speed_min) | (fabsf(yawish) >= pr.speed_min / 2.0f);
-              ACC(ELG_REW_GAIT_2_STEP) = (s + a) * (moving ? 1.0f : 0.0f);
-            }
-            if (term_on(pr, ELG_REW_BASE_HEIGHT)) {
-              const float d = (need_hsum ? hsum / (float)H : 0.0f) - pr.base_height_target;
-              ACC(ELG_REW_BASE_HEIGHT) = need_hsum ? d * d : 0.0f;
-            }
-#undef ACC
-            if (gait) {   // GaitScheduler.step (gait_scheduler.py:63-72) runs after the env step
-              const float g = s_gidx[slot] + pr.gait_increment;
-              s_gidx[slot] = g - floorf(g);
+          Vec3 v;
+          if (r == 2) {
+            v = Vec3{pr.gravity_vec[0], pr.gravity_vec[1], pr.gravity_vec[2]};
+          } else {
+            const int k = (r == 1 || r == 4) ? 10 : 7;
+            v = Vec3{rs[k], rs[k + 1], rs[k + 2]};
+            if (r >= 3) {
+              const float* lrv = s_lrv + e * 6 + (r - 3) * 3;
+              v.x -= lrv[0]; v.y -= lrv[1]; v.z -= lrv[2];
             }
           }
+          Vec3 o = quat_rotate_inverse(q, v);
+          float* dst = s_vec5 + (r * cap + e) * 3;
+          if (r >= 3) {
+            const float ema = pr.acc_ema, w1 = pr.acc_ema_c;
+            o.x = dst[0] * ema + (w1 * o.x) / pr.dt;
+            o.y = dst[1] * ema + (w1 * o.y) / pr.dt;
+            o.z = dst[2] * ema + (w1 * o.z) / pr.dt;
+          }
+          dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
         }
-        if (do_obs && lane == 0) {
-          hrow[0] = blv[0] * pr.obs_scale_lin_vel; hrow[1] = blv[1] * pr.obs_scale_lin_vel; hrow[2] = blv[2] * pr.obs_scale_lin_vel;
-          hrow[3] = bav[0] * pr.obs_scale_ang_vel; hrow[4] = bav[1] * pr.obs_scale_ang_vel; hrow[5] = bav[2] * pr.obs_scale_ang_vel;
-          hrow[6] = pg[0]; hrow[7] = pg[1]; hrow[8] = pg[2];
-          hrow[9] = cmd0 * pr.commands_scale[0]; hrow[10] = cmd1 * pr.commands_scale[1]; hrow[11] = cmd2 * pr.commands_scale[2];
-        }
-        if (do_hist && lane < 6) s_lrv[slot * 6 + lane] = rs[7 + lane];
         __syncwarp();
-
-        // ---- scaled terms + episode sums (lane == term), then the ordered fp32 sum (legged_robot.py:220-232)
+        if (ok && do_hist && r < 6) s_lrv[e * 6 + r] = rs[7 + r];
+        if (ok && do_derive && r == 7) s_ep[e] += 1;   // episode counter (legged_robot.py:122)
+      } else if (wp < wF + wR + wD) {
+        // ---- (env, dof): per-dof reward partials, observation entries, history (:84-114, :237-244, :148-149)
+        const int e = ((wp - wF - wR) * 32 + lane) / LD, j = lane & (LD - 1);
+        const bool ok = e < n && j < D;
+        float q_ar = 0.0f, q_da = 0.0f, q_dv = 0.0f, q_tq = 0.0f, q_ss = 0.0f, q_pl = 0.0f, q_vl = 0.0f, q_tl = 0.0f;
+        if (ok) {
+          const int fi = e * D + j;
+          const float2 pv = *reinterpret_cast<const float2*>(s_dof + 2 * fi);
+          const float pos = pv.x, vel = pv.y;
+          const float a = s_act[fi], q0 = s_q0[j];
+          if (do_reward) {
+            const float la = s_lact[fi], lv = s_ldv[fi], tq = s_tq[fi];
+            const float da = la - a;
+            q_ar = da * da;
+            const float dv = (lv - vel) / pr.dt;
+            q_da = dv * dv;
+            q_dv = vel * vel;
+            q_tq = tq * tq;
+            q_ss = fabsf(pos - q0);
+            if (lim_terms) {
+              q_pl = -fminf(pos - s_plim[2 * j], 0.0f) + fmaxf(pos - s_plim[2 * j + 1], 0.0f);
+              q_vl = fminf(fmaxf(fabsf(vel) - s_vlim[j], 0.0f), 1.0f);
+              q_tl = fmaxf(fabsf(tq) - s_tlim[j], 0.0f);
+            }
+          }
+          if (do_obs) {
+            float* hrow = s_obs + e * (L.obs_smem ? O : head);
+            hrow[12 + j] = (pos - q0) * pr.obs_scale_dof_pos;
+            hrow[12 + D + j] = vel * pr.obs_scale_dof_vel;
+            hrow[12 + 2 * D + j] = a;
+          }
+          if (do_hist) {
+            s_lact[fi] = a;
+            s_ldv[fi] = vel;
+          }
+        }
         if (do_reward) {
-          float r = 0.0f;
-          if (lane < L.nterms) {
-            const int t = L.term_ids[lane];
-            r = s_acc[t] * pr.reward_scales[t];
-            s_sums[lane * cap + slot] += r;
-          }
-          float total = 0.0f, r_term = 0.0f;
-          for (int ti = 0; ti < L.nterms; ++ti) {
-            const float v = __shfl_sync(0xffffffffu, r, ti);
-            if (L.term_ids[ti] == ELG_REW_TERMINATION) r_term = v;   // added after the clip
-            else total += v;
-          }
-          if (bf.extra_reward) total += bf.extra_reward[env];
-          if (pr.only_positive_rewards) total = fmaxf(total, 0.0f);
-          if (term_on(pr, ELG_REW_TERMINATION)) total += r_term;
-          if (lane == 0) s_rew[slot] = total;
+          const bool lead = e < n && j == 0;
+#define DOF_RED(t, var)                                            \
+  if (term_on(pr, t)) {                                            \
+    var = (LD == 16) ? bfly_sum<16>(var) : bfly_sum<32>(var);      \
+    if (lead) ACC(t, e) = var;                                     \
+  }
+          DOF_RED(ELG_REW_ACTION_RATE, q_ar)
+          DOF_RED(ELG_REW_DOF_ACC, q_da)
+          DOF_RED(ELG_REW_DOF_VEL, q_dv)
+          DOF_RED(ELG_REW_TORQUES, q_tq)
+          DOF_RED(ELG_REW_STAND_STILL, q_ss)
+          DOF_RED(ELG_REW_DOF_POS_LIMITS, q_pl)
+          DOF_RED(ELG_REW_DOF_VEL_LIMITS, q_vl)
+          DOF_RED(ELG_REW_TORQUE_LIMITS, q_tl)
+#undef DOF_RED
+        }
+      } else {
+        // ---- (env, body): collision count and termination contacts (:117-119, legged_robot.py:155-160)
+        const int e = ((wp - wF - wR - wD) * 32 + lane) / LP, b = lane & (LP - 1);
+        bool hit = false;
+        if (e < n && b < PT && (do_term || do_reward)) {
+          const int body = s_body[b];
+          const float* f = s_cf + (e * B + body) * 3;
+          hit = norm3_t(f[0], f[1], f[2]) > (b < P ? 0.1f : 1.0f);
+        }
+        unsigned m = __ballot_sync(0xffffffffu, hit);
+        if (LP == 16) m = (m >> (lane & 16)) & 0xffffu;
+        if (e < n && b == 0) {
+          ACC(kHits, e) = (float)__popc(m & ((1u << P) - 1u));
+          ACC(kTermHit, e) = (m >> P) != 0u ? 1.0f : 0.0f;
         }
       }
+    }
+    STAMP(4, 0)
+    __syncthreads();   // (B1) derived state, accumulators, raw observation heads are in shared memory
+    STAMP(5, 0)
 
-      // =========================== observation row: noise + clip (legged_robot.py:234-252, :107-108) ===========================
+    const int ewarp = (n < nwarps) ? n : 0;   // the scalar warp: a spare warp when there is one
+    const int slot = warp;
+    const bool row_warp = slot < n;
+    const int env = env0 + slot;
+    float hsum = 0.0f;
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    int blk_id = -1;
+    const int nj = (H + 31) >> 5;
+    const bool philox = do_obs && noise_mode == ELG_NOISE_PHILOX;
+    const bool obs_to_smem = kFast || L.obs_smem;
+    float* const orow = s_obs + slot * (obs_to_smem ? O : head);   // staged observation row (head only when rows are user-extended)
+    float* const grow = bf.obs_buf + (size_t)env * O;
+
+    // =========================== stage 2a: scalar warp, lane == env ===========================
+    bool scalar_pending = warp == ewarp && do_reward | do_obs | do_term | do_derive;
+    auto scalar_stage = [&]() {
+      const int e = lane;
+      if (e >= n) return;
+      const int genv = env0 + e;
+      const float* rs = s_root + e * 13;
+      const float rootz = rs[2];
+      const float* blv = s_vec5 + (0 * cap + e) * 3;
+      const float* bav = s_vec5 + (1 * cap + e) * 3;
+      const float* pg = s_vec5 + (2 * cap + e) * 3;
+      float* cmd = s_cmd + e * C;
+      float cmd2 = cmd[2];
+      if (do_derive && pr.heading_command) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
+        const Quat q = {rs[3], rs[4], rs[5], rs[6]};
+        const float fx = 1.0f + (q.y * (-2.0f * q.y) - q.z * (2.0f * q.z));
+        const float fy = q.w * (2.0f * q.z) + (q.z * 0.0f - q.x * (-2.0f * q.y));
+        const float heading = atan2f(fy, fx);
+        cmd2 = fminf(fmaxf(0.5f * wrap_to_pi(cmd[3] - heading), -1.0f), 1.0f);
+        cmd[2] = cmd2;
+      }
+      const float cmd0 = cmd[0], cmd1 = cmd[1], cmd3 = C > 3 ? cmd[3] : 0.0f;
+      bool reset = false, time_out = false;
+      if (do_term) {
+        const bool contact_term = PT > 0 && ACC(kTermHit, e) != 0.0f;
+        time_out = s_ep[e] > pr.max_episode_length;
+        reset = contact_term | time_out;
+        bf.reset_buf[genv] = reset ? 1 : 0;
+        bf.time_out_buf[genv] = time_out ? 1 : 0;
+      } else if (do_reward) {
+        reset = bf.reset_buf[genv] != 0;
+        time_out = bf.time_out_buf[genv] != 0;
+      }
       if (do_obs) {
-        // noise index k' of obs element k: k for the head, hm*32 + p for height point p; lane = k' % 32,
-        // Philox block = k' / 128, word = (k' / 32) % 4 -- so one lane consumes whole blocks
-        const int hm = L.hm;
-        const int nm = hm + ((H + 31) >> 5);
-        const float zc = sub_r(rootz, 0.5f);
-        const float* mh = s_mh + slot * H;
-        const bool philox = noise_mode == ELG_NOISE_PHILOX;
-        const bool to_smem = L.obs_smem;
-        float* grow = bf.obs_buf + (size_t)env * O;
-        for (int mb = 0; mb * 4 < nm; ++mb) {
-          uint4 rnd = make_uint4(0, 0, 0, 0);
-          if (philox) rnd = noise_block(pr.noise_seed, pr.noise_offset, env, lane, mb);
+        float* hrow = s_obs + e * (obs_to_smem ? O : head);
+        hrow[0] = blv[0] * pr.obs_scale_lin_vel; hrow[1] = blv[1] * pr.obs_scale_lin_vel; hrow[2] = blv[2] * pr.obs_scale_lin_vel;
+        hrow[3] = bav[0] * pr.obs_scale_ang_vel; hrow[4] = bav[1] * pr.obs_scale_ang_vel; hrow[5] = bav[2] * pr.obs_scale_ang_vel;
+        hrow[6] = pg[0]; hrow[7] = pg[1]; hrow[8] = pg[2];
+        hrow[9] = cmd0 * pr.commands_scale[0]; hrow[10] = cmd1 * pr.commands_scale[1]; hrow[11] = cmd2 * pr.commands_scale[2];
+      }
+      if (!do_reward) return;
+      const float cmd_xy = norm2_t(cmd0, cmd1);
+      if (term_on(pr, ELG_REW_STAND_STILL)) ACC(ELG_REW_STAND_STILL, e) *= (cmd_xy < pr.stand_still_threshold ? 1.0f : 0.0f);
+      if (term_on(pr, ELG_REW_LIN_VEL_Z)) ACC(ELG_REW_LIN_VEL_Z, e) = blv[2] * blv[2];
+      if (term_on(pr, ELG_REW_ANG_VEL_XY)) ACC(ELG_REW_ANG_VEL_XY, e) = bav[0] * bav[0] + bav[1] * bav[1];
+      if (term_on(pr, ELG_REW_ORIENTATION)) ACC(ELG_REW_ORIENTATION, e) = pg[0] * pg[0] + pg[1] * pg[1];
+      if (term_on(pr, ELG_REW_TRACKING_LIN_VEL)) {
+        const float ex = cmd0 - blv[0], ey = cmd1 - blv[1];
+        ACC(ELG_REW_TRACKING_LIN_VEL, e) = expf(-(ex * ex + ey * ey) / pr.tracking_sigma);
+      }
+      if (term_on(pr, ELG_REW_TRACKING_ANG_VEL)) {
+        const float ez = cmd2 - bav[2];
+        ACC(ELG_REW_TRACKING_ANG_VEL, e) = expf(-(ez * ez) / pr.tracking_sigma);
+      }
+      if (term_on(pr, ELG_REW_TERMINATION)) ACC(ELG_REW_TERMINATION, e) = (reset && !time_out) ? 1.0f : 0.0f;
+      if (term_on(pr, ELG_REW_COLLISION)) ACC(ELG_REW_COLLISION, e) = PT > 0 ? ACC(kHits, e) : 0.0f;
+      if (term_on(pr, ELG_REW_BASE_FOOT_HEIGHT)) {
+        const float cnt = ACC(kFootN, e);
+        const float ground = cnt > 0.0f ? ACC(kFootZ, e) / cnt : rootz - pr.base_height_target;
+        const float rel = rootz - ground - pr.base_height_target;
+        ACC(ELG_REW_BASE_FOOT_HEIGHT, e) = rel * rel;
+      }
+      if (term_on(pr, ELG_REW_FEET_AIR_TIME)) ACC(ELG_REW_FEET_AIR_TIME, e) *= (cmd_xy > 0.1f ? 1.0f : 0.0f);
+      if (term_on(pr, ELG_REW_JUMP_AIR)) ACC(ELG_REW_JUMP_AIR, e) = fmaxf(ACC(ELG_REW_JUMP_AIR, e) - (float)F / 2.0f, 0.0f);
+      if (term_on(pr, ELG_REW_FEET_STUMBLE)) ACC(ELG_REW_FEET_STUMBLE, e) = ACC(ELG_REW_FEET_STUMBLE, e) > 0.0f ? 1.0f : 0.0f;
+      if (term_on(pr, ELG_REW_FOUR_FOOTUP)) ACC(ELG_REW_FOUR_FOOTUP, e) = ACC(ELG_REW_FOUR_FOOTUP, e) == 0.0f ? 0.1f : 0.0f;
+      if (term_on(pr, ELG_REW_GAIT_SCHEDULER) && !gait) ACC(ELG_REW_GAIT_SCHEDULER, e) = 0.0f;
+      if (term_on(pr, ELG_REW_GAIT_2_STEP)) {
+        // gait_2_step (legged_robot_rew_mixin.py:170-206): FL/RR and FR/RL in phase, the rest anti-phase
+        const float* ar = s_air + e * F;
+        const float* cn = s_con + e * F;
+        const float a0 = F > 0 ? ar[0] : 0.0f, a1 = F > 1 ? ar[1] : 0.0f, a2 = F > 2 ? ar[2] : 0.0f, a3 = F > 3 ? ar[3] : 0.0f;
+        const float c0 = F > 0 ? cn[0] : 0.0f, c1 = F > 1 ? cn[1] : 0.0f, c2 = F > 2 ? cn[2] : 0.0f, c3 = F > 3 ? cn[3] : 0.0f;
+        auto sq4 = [](float a, float b) { const float d = a - b; return fminf(d * d, 4.0f); };
+        const float s = ((sq4(a0, a3) + sq4(c0, c3)) + (sq4(a1, a2) + sq4(c1, c2))) / 2.0f;
+        const float a = ((sq4(a0, c1) + sq4(c0, a1)) + (sq4(a0, c2) + sq4(c0, a2)) + (sq4(a3, c2) + sq4(c3, a2)) +
+                         (sq4(a3, c1) + sq4(c3, a1))) / 4.0f;
+        const float yawish = pr.heading_command ? cmd3 : cmd2;
+        const bool moving = (cmd_xy > pr.speed_min) | (fabsf(yawish) >= pr.speed_min / 2.0f);
+        ACC(ELG_REW_GAIT_2_STEP, e) = (s + a) * (moving ? 1.0f : 0.0f);
+      }
+      if (term_on(pr, ELG_REW_BASE_HEIGHT)) {
+        const float d = (need_hsum ? ACC(kHsum, e) / (float)H : 0.0f) - pr.base_height_target;
+        ACC(ELG_REW_BASE_HEIGHT, e) = need_hsum ? d * d : 0.0f;
+      }
+      if (gait) {   // GaitScheduler.step (gait_scheduler.py:63-72) runs after the env step
+        const float g = s_gidx[e] + pr.gait_increment;
+        s_gidx[e] = g - floorf(g);
+      }
+      // scaled terms + episode sums, then the fp32 sum in registry (alphabetical) order (legged_robot.py:220-232)
+      float total = 0.0f, r_term = 0.0f;
+      for (int ti = 0; ti < L.nterms; ++ti) {
+        const int t = L.term_ids[ti];
+        const float r = ACC(t, e) * pr.reward_scales[t];
+        s_sums[ti * cap + e] += r;
+        if (t == ELG_REW_TERMINATION) r_term = r;   // added after the clip
+        else total += r;
+      }
+      if (bf.extra_reward) total += bf.extra_reward[genv];
+      if (pr.only_positive_rewards) total = fmaxf(total, 0.0f);
+      if (term_on(pr, ELG_REW_TERMINATION)) total += r_term;
+      s_rew[e] = total;
+    };
+#pragma unroll 1
+    for (int round = 0; round < 2; ++round) {
+      if (scalar_pending && (round == 1 || !need_hsum)) { scalar_stage(); scalar_pending = false; }
+      STAMP(6 + 6 * round, ewarp)
+      if (round == 1) break;
+
+    // =========================== stage 2b: row warps -- terrain scan (legged_robot.py:900-938) + height observations ===========================
+    // Height point p = lane + 32 j.  Noise: 16-bit samples, 8 per Philox block; point j uses sample j % 8 of block
+    // 1 + j / 8 of this lane; the head entries (below) use the free samples of the last height block when they fit.
+      if (row_warp && H > 0 && (do_derive || do_obs || need_hsum)) {
+      const float* rs = s_root + slot * 13;
+      const float rootz = rs[2];
+      const float zc = sub_r(rootz, 0.5f);
+      float* mh = s_mh + slot * H;
+      const int16_t* __restrict__ hs = bf.height_samples;
+      const float* __restrict__ hmin = bf.height_field_min;
+      const int cols = pr.hf_cols, rmax = pr.hf_rows - 2, cmax = pr.hf_cols - 2;
+      f32x2 rr = 0, nc = 0, bord = 0, c_t = 0, c_ts = 0, c_w = 0, c_u = 0, xy = 0;
+      if (heights_live) {
+        const float r_h = __frcp_rn(pr.horizontal_scale);
+        rr = pack2(r_h, r_h);
+        nc = pack2(-pr.horizontal_scale, -pr.horizontal_scale);
+        bord = pack2(pr.border_size, pr.border_size);
+        float nrm = __fsqrt_rn(add_r(mul_r(rs[5], rs[5]), mul_r(rs[6], rs[6])));
+        nrm = fmaxf(nrm, 1e-9f);
+        const float zz = div_r(rs[5], nrm), ww = div_r(rs[6], nrm);
+        // t = 2 (q x b) = (-2 zz by, 2 zz bx); 2*RN(x) == RN(2x), so the doubling is folded into the multiplier
+        c_t = pack2(-mul_r(zz, 2.0f), mul_r(zz, 2.0f));    // times (by, bx) -> (tx, ty)
+        c_ts = pack2(mul_r(zz, 2.0f), -mul_r(zz, 2.0f));   // times (bx, by) -> (ty, tx)
+        c_w = pack2(ww, ww);
+        c_u = pack2(-zz, zz);
+        xy = pack2(rs[0], rs[1]);
+      }
+      const float* hp_env = shared_grid ? nullptr : bf.height_points + (size_t)env * pr.height_points_env_stride;
+      auto cell_of = [&](int p) -> int {
+        f32x2 b, bs;
+        if (shared_grid) {
+          const float4 g = s_grid[p];
+          b = pack2(g.x, g.y);
+          bs = pack2(g.z, g.w);
+        } else {
+          const float bx = __ldg(hp_env + 3 * p), by = __ldg(hp_env + 3 * p + 1);
+          b = pack2(bx, by);
+          bs = pack2(by, bx);
+        }
+        const f32x2 t = mul2(c_t, bs);          // (tx, ty)
+        const f32x2 ts = mul2(c_ts, b);         // (ty, tx)
+        f32x2 pt = add2(b, mul2(c_w, t));       // b + w t
+        pt = add2(pt, mul2(c_u, ts));           // + q_xyz x t = (-zz ty, zz tx)
+        pt = add2(add2(pt, xy), bord);          // + base xy, + border_size
+        // correctly rounded pt / horizontal_scale: q0 = x r, two FMA residual corrections (Markstein)
+        f32x2 q = mul2(pt, rr);
+        f32x2 er = fma2(nc, q, pt);
+        q = fma2(er, rr, q);
+        er = fma2(nc, q, pt);
+        q = fma2(er, rr, q);
+        float qx, qy;
+        unpack2(q, qx, qy);
+        int ix = __float2int_rz(qx), iy = __float2int_rz(qy);
+        ix = min(max(ix, 0), rmax);
+        iy = min(max(iy, 0), cmax);
+        return ix * cols + iy;
+      };
+      for (int jb = 0; jb < nj; jb += 8) {
+        if (philox) {
+          blk_id = 1 + (jb >> 3);
+          blk = noise_block(pr.noise_seed, pr.noise_offset, env, lane, blk_id);
+        }
 #pragma unroll
-          for (int w = 0; w < 4; ++w) {
-            const int m = mb * 4 + w;
-            if (m >= nm) break;
-            int k;
-            float v;
-            bool valid;
-            if (m < hm) {
-              k = lane + 32 * m;
-              valid = k < head;
-              v = valid ? hrow[k] : 0.0f;
+        for (int half = 0; half < 2; ++half) {
+          const int j0 = jb + 4 * half;
+          if (j0 >= nj) break;
+          float hv[4];
+          if (heights_live) {
+            if (kFast || hmin) {            // precomputed fp32 min-of-3 field (elg_prepare_height_field): one gather per point
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int p = lane + 32 * (j0 + u);
+                hv[u] = (p < H) ? __ldg(hmin + cell_of(p)) : 0.0f;
+              }
             } else {
-              const int p = lane + 32 * (m - hm);
-              valid = p < H;
-              k = head + p;
-              v = valid ? mul_r(fminf(fmaxf(sub_r(zc, mh[p]), -1.0f), 1.0f), pr.obs_scale_height) : 0.0f;
+              int a0[4], a1[4], a2[4];
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                const int p = lane + 32 * (j0 + u);
+                a0[u] = a1[u] = a2[u] = 0;
+                if (p < H) {
+                  const int16_t* cell = hs + cell_of(p);
+                  a0[u] = __ldg(cell);
+                  a1[u] = __ldg(cell + cols);
+                  a2[u] = __ldg(cell + 1);
+                }
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) hv[u] = mul_r((float)min(min(a0[u], a1[u]), a2[u]), pr.vertical_scale);
             }
-            if (valid) {
-              float u = 0.0f;
-              if (noise_mode == ELG_NOISE_TENSOR) u = __ldg(bf.noise_u + (size_t)env * O + k);
-              if (philox) u = u01(w == 0 ? rnd.x : w == 1 ? rnd.y : w == 2 ? rnd.z : rnd.w);
-              v = finish_obs(v, u, s_ns[k], noise_mode, clip_obs);
-              if (to_smem) orow[k] = v;
-              else grow[k] = v;
+          } else {
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int p = lane + 32 * (j0 + u);
+              hv[u] = (!do_derive && p < H) ? mh[p] : 0.0f;   // plane terrain: zeros (legged_robot.py:913-914)
             }
           }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int p = lane + 32 * (j0 + u);
+            if (p < H) {
+              const float h = hv[u];
+              if (do_derive) mh[p] = h;
+              hsum += sub_r(rootz, h);
+              if (do_obs) {
+                const int k = head + p;
+                float v = mul_r(fminf(fmaxf(sub_r(zc, h), -1.0f), 1.0f), pr.obs_scale_height);
+                if (noise_mode != ELG_NOISE_OFF) {
+                  float t;
+                  if (philox) t = fmaf(sample16(blk, 4 * half + u), 1.0f / 32768.0f, -1.0f);       // 2u - 1, exact
+                  else t = 2.0f * __ldg(bf.noise_u + (size_t)env * O + k) - 1.0f;
+                  v = v + t * s_ns[k];
+                }
+                if (clip_obs > 0.0f) v = fminf(fmaxf(v, -clip_obs), clip_obs);
+                if (kFast || obs_to_smem) orow[k] = v;
+                else grow[k] = v;
+              }
+            }
+          }
+        }
+      }
+      if (need_hsum) {
+        hsum = bfly_sum<32>(hsum);
+        if (lane == 0) ACC(kHsum, slot) = hsum;
+      }
+    }
+      STAMP(7, 0)
+      __syncthreads();   // (B2) terrain scan done (and the scalar stage, unless it needs the height sums)
+      STAMP(8, 0)
+    }
+    if (need_hsum) __syncthreads();
+
+    // =========================== stage 3: observation head: noise + clip (legged_robot.py:234-252, :107-108) ===========================
+    if (row_warp && do_obs) {
+      const int hm = L.hm;
+      // head entry k = lane + 32 m uses sample (nj % 8) + m of the last height block when hm fits behind the height samples
+      const bool share = (nj & 7) + hm <= 8;
+      const int bid = share ? 1 + (nj >> 3) : 0;
+      const int s0 = share ? (nj & 7) : 0;
+      for (int m = 0; m < hm; ++m) {
+        const int k = lane + 32 * m;
+        if (philox && ((m & 7) == 0) && !(m == 0 && blk_id == bid)) {
+          blk_id = bid + (m >> 3);
+          blk = noise_block(pr.noise_seed, pr.noise_offset, env, lane, blk_id);
+        }
+        if (k < head) {
+          float v = orow[k];
+          if (noise_mode != ELG_NOISE_OFF) {
+            float t;
+            if (philox) t = fmaf(sample16_dyn(blk, (s0 + m) & 7), 1.0f / 32768.0f, -1.0f);
+            else t = 2.0f * __ldg(bf.noise_u + (size_t)env * O + k) - 1.0f;
+            v = v + t * s_ns[k];
+          }
+          if (clip_obs > 0.0f) v = fminf(fmaxf(v, -clip_obs), clip_obs);
+          if (kFast || obs_to_smem) orow[k] = v;
+          else grow[k] = v;
         }
       }
     }
 
+    STAMP(9, 0)
     // ------------------------------- write back -------------------------------
-    if (bulk) {
-      if (active) {
-        fence_async_smem();   // this thread's generic-proxy writes -> visible to the async (TMA) proxy
-        const int s0 = sub * kSub;
-        const int ne = min(kSub, nenv - s0);
-        if (leader) {
-          named_bar_sync(1 + sub, 32 * ne);
-          for (int i = lane; i < L.n_out; i += 32) {
-            const CopyDesc d = L.out[i];
-            bulk_s2g(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)(env0 + s0) * d.bpe, smem_raw + d.soff + s0 * d.bpe, (uint32_t)(ne * d.bpe));
-          }
-          bulk_commit();
-          stores_pending = true;
-        } else {
-          named_bar_arrive(1 + sub, 32 * ne);
+    if (kFast || bulk) {
+      fence_async_smem();   // this thread's generic-proxy writes -> visible to the async (TMA) proxy
+      __syncthreads();
+      if (lane == 0) {
+        for (int i = warp; i < L.n_out; i += nwarps) {
+          const CopyDesc d = L.out[i];
+          bulk_s2g(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)env0 * d.bpe, smem_raw + d.soff, (uint32_t)(nenv * d.bpe));
         }
+        bulk_commit();
+        stores_pending = true;
+        STAMP(10, 0)
       }
     } else {
       __syncthreads();
@@ -789,9 +883,13 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         const CopyDesc d = L.out[i];
         coop_copy(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)env0 * d.bpe, smem_raw + d.soff, (uint32_t)(nenv * d.bpe), tid, nthreads);
       }
+      __syncthreads();
     }
   }
   if (stores_pending) bulk_wait_all();
+  STAMP(11, 0)
+#undef STAMP
+#undef ACC
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -854,14 +952,26 @@ elg_heights_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ E
   }
 }
 
+// min-of-3 cells as fp32 metres, tabulated once per terrain (legged_robot.py:932-938)
+__global__ void __launch_bounds__(256)
+elg_height_min_kernel(const int16_t* __restrict__ hs, const int rows, const int cols, const float vs, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * cols) return;
+  const int r = i / cols, c = i - r * cols;
+  float v = 0.0f;
+  if (r <= rows - 2 && c <= cols - 2) v = mul_r((float)min(min((int)hs[i], (int)hs[i + cols]), (int)hs[i + 1]), vs);
+  out[i] = v;
+}
+
 }  // namespace elg
 
 // =================================================================================================
 // C ABI
 // =================================================================================================
 namespace {
-struct StepTune { int cap, threads, ctas_per_sm, no_bulk; };
-StepTune g_tune = {0, 0, 0, 0};
+struct StepTune { int cap, threads, ctas_per_sm, no_bulk, no_fast; };
+StepTune g_tune = {0, 0, 0, 0, 0};
+long long* g_step_dbg = nullptr;
 thread_local char g_err[256] = "";
 int fail(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
@@ -990,16 +1100,16 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
     nchunks = (int)(Q < sms ? Q : sms);
     cap = 4 * (int)((Q + nchunks - 1) / nchunks);
     grid = nchunks;
-  } else {                           // many chunks: 16-env CTAs, 2 per SM, each looping over its chunks
-    cap = 16;
+  } else {                           // many chunks: 12-env CTAs (13 warps), 2 per SM, each looping over its chunks
+    cap = 12;
     const long long g = (long long)sms * 2;
-    long long nch = (Q + 3) / 4;
+    long long nch = (Q + 2) / 3;
     if (nch > g) nch = (nch + g - 1) / g * g;
     if (nch > Q) nch = Q;
     nchunks = (int)nch;
     grid = (int)(nch < g ? nch : g);
   }
-  const int threads = 32 * cap;
+  const int threads = 32 * (cap < 32 ? cap + 1 : 32);   // one row warp per env + the scalar warp
 
   // ---- shared-memory plan + copy tables
   elg::StepPlan L{};
@@ -1043,7 +1153,8 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
   L.tlim = take(D * 4);
   L.ns = take(O * 4);
   L.grid = take(H * 16);
-  L.acc = take(cap * 32 * 4);
+  L.acc = take((ELG_NUM_REWARD_TERMS + 5) * 32 * 4);
+  L.idx = take((ELG_MAX_FEET + ELG_MAX_PENALISED + ELG_MAX_TERMINATION) * 4);
   L.bytes = off;
   if ((size_t)L.bytes + 1024 > (size_t)227 * 1024)
     return fail(ELG_ERR_UNSUPPORTED, "robot dimensions do not fit the shared-memory plan of elg_step_kernel");
@@ -1131,6 +1242,7 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
     out(buf->last_dof_vel, L.ldv, 4 * D);
     out(buf->last_root_vel, L.lrv, 24);
   }
+  L.dbg = g_step_dbg;
   L.n_in = n_in;
   L.n_out = n_out;
   L.in_bpe = in_bpe;
@@ -1140,28 +1252,44 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
 
   const size_t smem = (size_t)L.bytes;
   const bool quad = (D == 12 && F == 4);
-  auto kern = quad ? elg::elg_step_kernel<12, 4> : elg::elg_step_kernel<0, 0>;
-  static size_t smem_set[2] = {0, 0};
-  if (smem > smem_set[quad ? 1 : 0]) {
+  const bool fast = quad && phase == ELG_PHASE_FUSED && L.use_bulk && L.obs_smem && prm->height_points_env_stride == 0 &&
+                    (H == 0 || prm->terrain_is_plane || buf->height_field_min != nullptr) && g_tune.no_fast == 0;
+  auto kern = fast ? elg::elg_step_kernel<12, 4, true> : quad ? elg::elg_step_kernel<12, 4, false> : elg::elg_step_kernel<0, 0, false>;
+  const int which = fast ? 2 : quad ? 1 : 0;
+  static size_t smem_set[3] = {0, 0, 0};
+  if (smem > smem_set[which]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return fail(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_step_kernel");
-    smem_set[quad ? 1 : 0] = smem;
+    smem_set[which] = smem;
   }
   kern<<<grid, threads, smem, st>>>(*dims, *prm, *buf, L, phase);
   return check_launch("elg_post_physics_step");
 }
 
+int elg_set_step_debug(long long* device_stamps) {
+  g_step_dbg = device_stamps;
+  return ELG_OK;
+}
+
 int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm, int disable_bulk) {
   if (envs_per_chunk == 0) {
-    g_tune = StepTune{0, 0, 0, disable_bulk};
+    g_tune = StepTune{0, 0, 0, disable_bulk & 1, (disable_bulk >> 1) & 1};
     return ELG_OK;
   }
   if (envs_per_chunk < 4 || envs_per_chunk > elg::kMaxCap || envs_per_chunk % 4 != 0)
     return fail(ELG_ERR_INVALID_ARGUMENT, "envs_per_chunk must be a multiple of 4 in [4, 32]");
   (void)threads_per_cta;   // v3: one warp per env, the CTA width follows envs_per_chunk
   if (ctas_per_sm < 1 || ctas_per_sm > 16) return fail(ELG_ERR_INVALID_ARGUMENT, "ctas_per_sm must be in [1, 16]");
-  g_tune = StepTune{envs_per_chunk, threads_per_cta, ctas_per_sm, disable_bulk};
+  g_tune = StepTune{envs_per_chunk, threads_per_cta, ctas_per_sm, disable_bulk & 1, (disable_bulk >> 1) & 1};
   return ELG_OK;
+}
+
+int elg_prepare_height_field(const int16_t* height_samples, int32_t rows, int32_t cols, float vertical_scale, float* out, void* stream) {
+  if (!height_samples || !out) return fail(ELG_ERR_NULL_POINTER, "height_samples/out is NULL");
+  if (rows < 2 || cols < 2 || (long long)rows * cols > 0x7fffffffLL) return fail(ELG_ERR_INVALID_ARGUMENT, "rows, cols must be >= 2 and rows*cols < 2^31");
+  const int n = rows * cols;
+  elg::elg_height_min_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream>>>(height_samples, rows, cols, vertical_scale, out);
+  return check_launch("elg_prepare_height_field");
 }
 
 int elg_get_heights(const ElgDims* dims, const ElgStepParams* prm, const float* root_states, const int16_t* height_samples,

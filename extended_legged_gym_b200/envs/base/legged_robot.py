@@ -370,6 +370,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         put("dof_vel_limits", self.dof_vel_limits, f32)
         put("torque_limits", self.torque_limits, f32)
         put("height_samples", self.height_samples, torch.int16)
+        put("height_field_min", self._height_field_min(), f32)
         put("height_points", self.height_points if self._user_height_points else self._height_grid, f32)
         put("noise_scale_vec", self.noise_scale_vec, f32)
         put("noise_u", self.noise_u, f32)
@@ -384,6 +385,23 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         put("reset_buf", self._reset_bool, torch.bool)
         put("time_out_buf", self.time_out_buf, torch.bool)
         return b
+
+    def _height_field_min(self):
+        """fp32 min-of-3-cells table of the (static) terrain, built once by elg_prepare_height_field and rebuilt
+        when ``height_samples`` is rebound; ``measure_heights`` off or plane terrain: None."""
+        hs = self.height_samples
+        if hs is None or not self.measure_heights or self.cfg.terrain.mesh_type == "plane":
+            return None
+        key = (hs.data_ptr(), tuple(hs.shape), float(self.cfg.terrain.vertical_scale))
+        if getattr(self, "_hmin_key", None) != key:
+            out = torch.empty(hs.shape, dtype=torch.float, device=hs.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(self._lib.elg_prepare_height_field(hs.data_ptr(), hs.shape[0], hs.shape[1],
+                                                          float(self.cfg.terrain.vertical_scale), out.data_ptr(), stream),
+                       "elg_prepare_height_field")
+            object.__setattr__(self, "_hmin", out)
+            object.__setattr__(self, "_hmin_key", key)
+        return self._hmin
 
     def _sync_native(self):
         if getattr(self, "_dims", None) is None:

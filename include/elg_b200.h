@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ELG_ABI_VERSION 1
+#define ELG_ABI_VERSION 2
 
 #define ELG_MAX_DOF 32
 #define ELG_MAX_FEET 8
@@ -84,7 +84,7 @@ typedef enum ElgControlType { ELG_CONTROL_P = 0, ELG_CONTROL_V = 1, ELG_CONTROL_
 typedef enum ElgNoiseMode {
   ELG_NOISE_OFF = 0,    /* cfg.noise.add_noise == False */
   ELG_NOISE_TENSOR = 1, /* uniform [0,1) samples supplied by the caller (parity mode, = torch.rand_like) */
-  ELG_NOISE_PHILOX = 2  /* generated in-kernel: Philox4x32-10 keyed by (seed, step), counter (env, obs/4) */
+  ELG_NOISE_PHILOX = 2  /* generated in-kernel: Philox4x32-10 keyed by seed, counter (env, lane | block << 5, step); 16-bit samples */
 } ElgNoiseMode;
 
 /* Sections of post_physics_step (legged_robot.py:113-150), OR-ed into `phase`.  The reset path
@@ -164,6 +164,7 @@ typedef struct ElgStepBuffers {
   const float* dof_vel_limits;   /* [D] */
   const float* torque_limits;    /* [D] */
   const int16_t* height_samples; /* [rows, cols] or NULL */
+  const float* height_field_min; /* [rows, cols] fp32 from elg_prepare_height_field, or NULL (kernel gathers the 3 int16 cells) */
   const float* height_points;    /* [H,3] (or [N,H,3] with height_points_env_stride) or NULL */
   const float* noise_scale_vec;  /* [O] or NULL */
   const float* noise_u;          /* [N,O] uniform samples for ELG_NOISE_TENSOR, else NULL */
@@ -221,10 +222,20 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
  * element-wise staging path instead of TMA bulk copies.  envs_per_chunk == 0 restores the built-in choice. */
 int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm, int disable_bulk);
 
+/* Diagnostic (no reference counterpart): when set to a device buffer of >= 16 int64, CTA 0 of every following
+ * elg_post_physics_step launch records clock64() at its stage boundaries there; NULL switches it off. */
+int elg_set_step_debug(long long* device_stamps);
+
 /* LeggedRobot._get_heights (envs/base/legged_robot.py:900-938), standalone. cells_out (optional,
  * int32 [N,H,2]) receives the clipped (px, py) terrain cell of every point for index parity tests. */
 int elg_get_heights(const ElgDims* dims, const ElgStepParams* prm, const float* root_states, const int16_t* height_samples,
                     const float* height_points, float* measured_heights, int32_t* cells_out, void* stream);
+
+/* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =
+ * fp32(min(hs[i][j], hs[i+1][j], hs[i][j+1])) * vertical_scale for i <= rows-2, j <= cols-2 (0 elsewhere) -- the
+ * value the reference computes per height point, tabulated once per (static) terrain so the step kernel gathers one
+ * float instead of three int16.  Bit-identical to the per-point evaluation. */
+int elg_prepare_height_field(const int16_t* height_samples, int32_t rows, int32_t cols, float vertical_scale, float* out, void* stream);
 
 #ifdef __cplusplus
 }

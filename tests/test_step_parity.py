@@ -191,9 +191,10 @@ def _philox4x32_10(c0, c1, c2, c3, k0, k1):
 
 
 def test_in_kernel_philox_noise_is_exact_and_uniform():
-    """ELG_NOISE_PHILOX: obs element k has noise index k' = k in the head (k < 12+3D) and 32*ceil(head/32) + p for
-    height point p; its uniform is word (k'//32)%4 of Philox4x32-10(counter=(env, k'%32 + 32*(k'//128), offset, 0),
-    key=seed); obs = clean + (2u-1)*scale."""
+    """ELG_NOISE_PHILOX (csrc/elg_common.cuh): lane l of env's warp draws Philox4x32-10(counter=(env, l | block<<5,
+    offset, 0), key=seed) and cuts it into eight 16-bit samples.  Height point p = l + 32 j: sample j%8 of block
+    1 + j//8; head entry k = l + 32 m: sample nj%8 + m of block 1 + nj//8 (fits for 12 DOF / 187 points).
+    obs = clean + (2 s/65536 - 1) * scale."""
     case, n = "anymal_c_rough", 3000
     cfg, spec, st = common.make_case_state(case, n, seed=6)
     hf = synthetic.make_height_field(seed=0)
@@ -206,16 +207,21 @@ def test_in_kernel_philox_noise_is_exact_and_uniform():
     env._launch(_lib.PHASE_OBS)
     torch.cuda.synchronize()
     noisy = env.obs_buf.cpu()
-    O = env.num_obs
-    e, k = np.meshgrid(np.arange(n), np.arange(O), indexing="ij")
+    O, H = env.num_obs, env.num_height_points
     head = 12 + 3 * env.num_dof
-    k = np.where(k < head, k, 32 * ((head + 31) // 32) + (k - head))
-    words = _philox4x32_10(e, (k % 32) + 32 * (k // 128), 12345, 0, env.noise_seed & 0xFFFFFFFF, env.noise_seed >> 32)
-    sel = (k // 32) % 4
-    w = np.choose(sel, [x.astype(np.uint64) for x in words])
-    u = ((w >> np.uint64(8)).astype(np.float32) * np.float32(1.0 / 16777216.0))
-    want = clean + (2 * torch.from_numpy(u) - 1) * env.noise_scale_vec.cpu()
+    nj, hm = (H + 31) // 32, (head + 31) // 32
+    assert nj % 8 + hm <= 8
+    e, k = np.meshgrid(np.arange(n), np.arange(O), indexing="ij")
+    is_head = k < head
+    p = k - head
+    lane = np.where(is_head, k % 32, p % 32)
+    block = np.where(is_head, 1 + nj // 8, 1 + (p // 32) // 8)
+    samp = np.where(is_head, nj % 8 + k // 32, (p // 32) % 8)
+    words = _philox4x32_10(e, lane | (block << 5), 12345, 0, env.noise_seed & 0xFFFFFFFF, env.noise_seed >> 32)
+    w = np.choose(samp >> 1, [x.astype(np.uint64) for x in words])
+    s16 = ((w >> (np.uint64(16) * (samp & 1).astype(np.uint64))) & np.uint64(0xFFFF)).astype(np.float32)
+    want = clean + torch.from_numpy(s16 / np.float32(32768.0) - np.float32(1.0)) * env.noise_scale_vec.cpu()
     assert torch.allclose(noisy, want, rtol=1e-6, atol=1e-6)
     nz = env.noise_scale_vec.cpu() > 0
-    uu = torch.from_numpy(u)[:, nz]
+    uu = torch.from_numpy(s16 / np.float32(65536.0))[:, nz]
     assert abs(float(uu.mean()) - 0.5) < 2e-3 and abs(float(uu.var()) - 1 / 12) < 2e-3
