@@ -40,7 +40,7 @@ class ElgStepParams(C.Structure):
         ("max_episode_length", C.c_int64),
         ("control_type", C.c_int32), ("action_scale", C.c_float),
         ("heading_command", C.c_int32), ("measure_heights", C.c_int32), ("terrain_is_plane", C.c_int32),
-        ("only_positive_rewards", C.c_int32), ("noise_mode", C.c_int32), ("clip_observations", C.c_float),
+        ("only_positive_rewards", C.c_int32), ("noise_mode", C.c_int32), ("rollout_mode", C.c_int32), ("clip_observations", C.c_float),
         ("gravity_vec", C.c_float * 3),
         ("obs_scale_lin_vel", C.c_float), ("obs_scale_ang_vel", C.c_float), ("obs_scale_dof_pos", C.c_float),
         ("obs_scale_dof_vel", C.c_float), ("obs_scale_height", C.c_float),
@@ -69,6 +69,19 @@ class ElgStepBuffers(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _BUF_FIELDS]
 
 
+MAX_CLONE_FIELDS = 24
+CLONE_SYNC, CLONE_CACHE, CLONE_RESTORE = 0, 1, 2
+
+
+class ElgCloneField(C.Structure):
+    _fields_ = [("base", C.c_void_p), ("cache", C.c_void_p), ("row_bytes", C.c_int32), ("reserved", C.c_int32)]
+
+
+class ElgCloneTable(C.Structure):
+    _fields_ = [("num_fields", C.c_int32), ("num_main", C.c_int32), ("rollouts_per_main", C.c_int32), ("drift_field", C.c_int32),
+                ("fields", ElgCloneField * MAX_CLONE_FIELDS)]
+
+
 class ElgError(RuntimeError):
     pass
 
@@ -92,7 +105,8 @@ def load() -> C.CDLL:
     lib.elg_last_error.restype = C.c_char_p
     lib.elg_reward_term_name.restype = C.c_char_p
     lib.elg_reward_term_name.argtypes = [C.c_int]
-    for fn, st in (("elg_sizeof_dims", ElgDims), ("elg_sizeof_step_params", ElgStepParams), ("elg_sizeof_step_buffers", ElgStepBuffers)):
+    for fn, st in (("elg_sizeof_dims", ElgDims), ("elg_sizeof_step_params", ElgStepParams), ("elg_sizeof_step_buffers", ElgStepBuffers),
+                   ("elg_sizeof_clone_table", ElgCloneTable)):
         got = getattr(lib, fn)()
         if got != C.sizeof(st):
             raise ElgError(f"ABI mismatch: {fn}() = {got}, python mirror = {C.sizeof(st)}")
@@ -104,6 +118,12 @@ def load() -> C.CDLL:
     lib.elg_post_physics_step.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams), C.POINTER(ElgStepBuffers), C.c_uint32, vp]
     lib.elg_set_step_tuning.argtypes = [C.c_int] * 4
     lib.elg_get_heights.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 5 + [vp]
+    lib.elg_clone_rows.argtypes = [C.POINTER(ElgCloneTable), C.c_int, C.c_float, vp, C.c_uint64, C.c_uint64, vp]
+    lib.elg_set_step_debug.argtypes = [vp]
+    lib.elg_mesh_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(vp)]
+    lib.elg_mesh_free.argtypes = [vp]
+    lib.elg_mesh_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
+    lib.elg_raycast.argtypes = [vp, vp, vp, i64, C.c_float, vp, vp, vp, vp, vp]
     lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib
     return lib

@@ -9,6 +9,11 @@ namespace elg {
 
 constexpr int kWarp = 32;
 
+// host-side error plumbing shared by the translation units (defined in elg_step.cu)
+int set_error(int code, const char* msg);   // records msg for elg_last_error(), returns code
+int check_launch(const char* what);         // cudaGetLastError() -> ELG_OK / ELG_ERR_CUDA
+int sm_count();                             // SMs of the current device (0 on failure)
+
 // ---------------------------------------------------------------------------------------------
 // Individually rounded fp32 ops.  torch evaluates the reference expression one ATen op at a
 // time, so every intermediate is rounded to fp32; where an integer / boolean output depends on

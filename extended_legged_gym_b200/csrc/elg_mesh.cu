@@ -1,0 +1,455 @@
+// elg_mesh.cu -- triangle-mesh BVH, ray casting, depth camera and signed-distance queries for sm_100a.
+//
+// Replaces what the reference delegates to NVIDIA Warp 1.7 through a GPU -> CPU numpy -> Warp -> CPU -> GPU round
+// trip every call (paths relative to legged_gym/legged_gym/ in the reference):
+//   utils/ray_caster.py:45-92   raycast_mesh_kernel   (wp.mesh_query_ray)            -> elg_raycast
+//   utils/ray_caster.py:29-42   convert_to_warp_mesh  (wp.Mesh: BVH build)           -> elg_mesh_create / elg_mesh_free
+//   utils/depth_camera.py:402-499 DepthCameraWarp.update_depth_buffer                 -> elg_depth_camera (fused)
+//   utils/mesh_sdf.py:38-116    query_sdf_kernel (wp.mesh_query_point_sign_normal)    -> elg_sdf_query
+//
+// Data structure: a 4-wide BVH.  The host builds a binary tree top-down with binned SAH (16 bins, leaves of <= 4
+// triangles -- the terrain is static, the build runs once at init), collapses it to 4 children per node and uploads
+//   nodes   128 bytes each: child boxes as SoA float4 rows (lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4]),
+//           int4 child codes (>= 0 inner node, < 0 leaf: ~(first << 2 | count - 1), INT_MIN empty)
+//   tris    48 bytes each, in leaf order: v0, v1, v2 as fp32 + the caller's triangle id
+// so one node visit is eight 16-byte loads from one 128-byte line and a leaf is a contiguous run.  The default
+// terrain (1.6 M triangles) is 77 MB of triangles + 17 MB of nodes: resident in the 126 MB L2 while rays stay local.
+//
+// Numerics: box tests are fp32 and conservative (boxes padded at build time, far plane scaled by 1 + 2^-21); the
+// triangle tests run in fp64 with individually rounded operations in the same order as the numpy oracle
+// (oracle/mesh_oracle.py), so hit distances agree with the float64 brute force to the last fp32 bit instead of
+// carrying the ~4e-6 m cancellation error of an fp32 test at terrain coordinates of tens of metres.
+#include <cuda_runtime.h>
+#include <float.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "elg_common.cuh"
+
+struct ElgMesh {
+  int32_t num_vertices, num_triangles, num_nodes;
+  float4* nodes;      // device, 8 float4 per node
+  float4* tris;       // device, 3 float4 per triangle (leaf order)
+  float lo[3], hi[3]; // scene bounds
+  double avg_edge;    // mean edge length (mesh_query_point_sign_normal's epsilon is relative to it)
+  int device;
+};
+
+namespace elg {
+
+constexpr int kStack = 48;
+constexpr int kEmpty = INT32_MIN;
+
+struct Hit {
+  double t;
+  int tri;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fp64 Moeller-Trumbore, two-sided, every operation rounded on its own (matches oracle/mesh_oracle.py)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double dmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double dadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double dsub(double a, double b) { return __dsub_rn(a, b); }
+
+__device__ __forceinline__ bool ray_triangle(const double ox, const double oy, const double oz, const double dx, const double dy,
+                                             const double dz, const float4 a, const float4 b, const float4 c, double& t_out) {
+  const double v0x = a.x, v0y = a.y, v0z = a.z, v1x = a.w, v1y = b.x, v1z = b.y, v2x = b.z, v2y = b.w, v2z = c.x;
+  const double e1x = dsub(v1x, v0x), e1y = dsub(v1y, v0y), e1z = dsub(v1z, v0z);
+  const double e2x = dsub(v2x, v0x), e2y = dsub(v2y, v0y), e2z = dsub(v2z, v0z);
+  const double px = dsub(dmul(dy, e2z), dmul(dz, e2y));
+  const double py = dsub(dmul(dz, e2x), dmul(dx, e2z));
+  const double pz = dsub(dmul(dx, e2y), dmul(dy, e2x));
+  const double det = dadd(dadd(dmul(e1x, px), dmul(e1y, py)), dmul(e1z, pz));
+  if (det == 0.0) return false;
+  const double inv = 1.0 / det;
+  const double sx = dsub(ox, v0x), sy = dsub(oy, v0y), sz = dsub(oz, v0z);
+  const double u = dmul(dadd(dadd(dmul(sx, px), dmul(sy, py)), dmul(sz, pz)), inv);
+  if (!(u >= 0.0 && u <= 1.0)) return false;
+  const double qx = dsub(dmul(sy, e1z), dmul(sz, e1y));
+  const double qy = dsub(dmul(sz, e1x), dmul(sx, e1z));
+  const double qz = dsub(dmul(sx, e1y), dmul(sy, e1x));
+  const double v = dmul(dadd(dadd(dmul(dx, qx), dmul(dy, qy)), dmul(dz, qz)), inv);
+  if (!(v >= 0.0 && dadd(u, v) <= 1.0)) return false;
+  const double t = dmul(dadd(dadd(dmul(e2x, qx), dmul(e2y, qy)), dmul(e2z, qz)), inv);
+  if (!(t >= 0.0)) return false;
+  t_out = t;
+  return true;
+}
+
+// closest hit of one ray with t in [0, max_t); returns false on a miss
+__device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float ox, const float oy,
+                                      const float oz, const float dx, const float dy, const float dz, const float max_t, Hit& hit) {
+  const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
+  const double Ox = ox, Oy = oy, Oz = oz, Dx = dx, Dy = dy, Dz = dz;
+  double t_best = (double)max_t;
+  float t_cull = max_t;
+  int best_tri = -1;
+  int stack_c[kStack];
+  float stack_t[kStack];
+  int sp = 0;
+  stack_c[sp] = 0;
+  stack_t[sp++] = 0.0f;
+  while (sp > 0) {
+    --sp;
+    const int code = stack_c[sp];
+    if (stack_t[sp] > t_cull) continue;
+    if (code < 0) {   // leaf
+      const int first = (~code) >> 2, count = ((~code) & 3) + 1;
+      for (int i = 0; i < count; ++i) {
+        const float4* tp = tris + 3 * (size_t)(first + i);
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+        double t;
+        if (ray_triangle(Ox, Oy, Oz, Dx, Dy, Dz, a, b, c, t) && t < t_best) {
+          t_best = t;
+          best_tri = __float_as_int(c.y);
+          t_cull = __double2float_ru(t);
+        }
+      }
+      continue;
+    }
+    const float4* np = nodes + 8 * (size_t)code;
+    const float4 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(np + 6));
+    float tn[4];
+    int cc[4] = {ch.x, ch.y, ch.z, ch.w};
+    const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
+    const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      // slab test; fminf / fmaxf drop the NaN of 0 * inf when the origin lies on a slab plane of an axis-parallel ray
+      const float ax = (lox[c] - ox) * ix, bx = (hix[c] - ox) * ix;
+      const float ay = (loy[c] - oy) * iy, by = (hiy[c] - oy) * iy;
+      const float az = (loz[c] - oz) * iz, bz = (hiz[c] - oz) * iz;
+      const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
+      const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_cull)) * 1.0000005f;
+      tn[c] = (cc[c] != kEmpty && t0 <= t1) ? t0 : FLT_MAX;
+    }
+    // sort the four children by entry distance (5-comparator network), push far to near
+#define CSWAP(i, j)                                   \
+  if (tn[i] > tn[j]) {                                \
+    const float tt = tn[i]; tn[i] = tn[j]; tn[j] = tt; \
+    const int ct = cc[i]; cc[i] = cc[j]; cc[j] = ct;  \
+  }
+    CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
+#undef CSWAP
+#pragma unroll
+    for (int c = 3; c >= 0; --c)
+      if (tn[c] != FLT_MAX && sp < kStack) {
+        stack_c[sp] = cc[c];
+        stack_t[sp++] = tn[c];
+      }
+  }
+  hit.t = t_best;
+  hit.tri = best_tri;
+  return best_tri >= 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// raycast_mesh (utils/ray_caster.py:45-92): one thread per ray
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+elg_raycast_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ origins,
+                   const float* __restrict__ dirs, const long long n, const float max_dist, float* __restrict__ hits,
+                   uint8_t* __restrict__ found, float* __restrict__ dist_out, int* __restrict__ tri_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float ox = origins[3 * i], oy = origins[3 * i + 1], oz = origins[3 * i + 2];
+  const float dx = dirs[3 * i], dy = dirs[3 * i + 1], dz = dirs[3 * i + 2];
+  Hit h;
+  const bool ok = trace(nodes, tris, ox, oy, oz, dx, dy, dz, max_dist, h);
+  const float t = ok ? (float)h.t : max_dist;   // miss: the ray end point (ray_caster.py:88-92)
+  hits[3 * i] = add_r(ox, mul_r(t, dx));
+  hits[3 * i + 1] = add_r(oy, mul_r(t, dy));
+  hits[3 * i + 2] = add_r(oz, mul_r(t, dz));
+  found[i] = ok ? 1 : 0;
+  if (dist_out) dist_out[i] = t;
+  if (tri_out) tri_out[i] = ok ? h.tri : -1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: binned-SAH binary build, collapse to 4-wide, upload
+// ---------------------------------------------------------------------------------------------
+struct Box {
+  float lo[3], hi[3];
+  void reset() { lo[0] = lo[1] = lo[2] = FLT_MAX; hi[0] = hi[1] = hi[2] = -FLT_MAX; }
+  void grow(const float* p) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], p[k]); hi[k] = std::max(hi[k], p[k]); } }
+  void grow(const Box& b) { for (int k = 0; k < 3; ++k) { lo[k] = std::min(lo[k], b.lo[k]); hi[k] = std::max(hi[k], b.hi[k]); } }
+  double area() const {
+    const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+    return (dx < 0 || dy < 0 || dz < 0) ? 0.0 : 2.0 * (dx * dy + dy * dz + dz * dx);
+  }
+};
+struct BNode {
+  Box box;
+  int left, right;   // children (inner) or -1
+  int first, count;  // triangle range (leaf)
+};
+
+struct Builder {
+  const float* V;
+  const int32_t* T;
+  int M;
+  std::vector<Box> tbox;
+  std::vector<float> cen;   // 3 per triangle
+  std::vector<int> order;
+  std::vector<BNode> nodes;
+
+  void run() {
+    tbox.resize(M);
+    cen.resize(3 * (size_t)M);
+    order.resize(M);
+    for (int i = 0; i < M; ++i) {
+      Box b;
+      b.reset();
+      for (int k = 0; k < 3; ++k) b.grow(V + 3 * (size_t)T[3 * (size_t)i + k]);
+      tbox[i] = b;
+      for (int k = 0; k < 3; ++k) cen[3 * (size_t)i + k] = 0.5f * (b.lo[k] + b.hi[k]);
+      order[i] = i;
+    }
+    nodes.reserve(M);
+    nodes.push_back(BNode{});
+    struct Job { int node, first, count; };
+    std::vector<Job> todo;
+    todo.push_back({0, 0, M});
+    constexpr int kBins = 16;
+    while (!todo.empty()) {
+      const Job j = todo.back();
+      todo.pop_back();
+      Box nb, cb;
+      nb.reset();
+      cb.reset();
+      for (int i = j.first; i < j.first + j.count; ++i) {
+        nb.grow(tbox[order[i]]);
+        cb.grow(&cen[3 * (size_t)order[i]]);
+      }
+      BNode& N = nodes[j.node];
+      N.box = nb;
+      N.left = N.right = -1;
+      N.first = j.first;
+      N.count = j.count;
+      if (j.count <= 4) continue;
+      // best binned split over the three axes
+      int best_axis = -1, best_bin = -1;
+      double best_cost = DBL_MAX;
+      for (int ax = 0; ax < 3; ++ax) {
+        const float lo = cb.lo[ax], ext = cb.hi[ax] - cb.lo[ax];
+        if (!(ext > 0.0f)) continue;
+        Box bb[kBins];
+        int bc[kBins];
+        for (int b = 0; b < kBins; ++b) { bb[b].reset(); bc[b] = 0; }
+        const float scale = kBins / ext;
+        for (int i = j.first; i < j.first + j.count; ++i) {
+          const int t = order[i];
+          int b = (int)((cen[3 * (size_t)t + ax] - lo) * scale);
+          b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+          bb[b].grow(tbox[t]);
+          bc[b]++;
+        }
+        double la[kBins], ra[kBins];
+        int lc[kBins], rc[kBins];
+        Box acc;
+        acc.reset();
+        int c = 0;
+        for (int b = 0; b < kBins; ++b) { acc.grow(bb[b]); c += bc[b]; la[b] = acc.area(); lc[b] = c; }
+        acc.reset();
+        c = 0;
+        for (int b = kBins - 1; b >= 0; --b) { acc.grow(bb[b]); c += bc[b]; ra[b] = acc.area(); rc[b] = c; }
+        for (int b = 0; b + 1 < kBins; ++b) {
+          if (lc[b] == 0 || rc[b + 1] == 0) continue;
+          const double cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
+          if (cost < best_cost) { best_cost = cost; best_axis = ax; best_bin = b; }
+        }
+      }
+      int mid;
+      if (best_axis < 0) {   // all centroids coincide: split the range in the middle
+        mid = j.first + j.count / 2;
+      } else {
+        const float lo = cb.lo[best_axis], scale = kBins / (cb.hi[best_axis] - cb.lo[best_axis]);
+        auto it = std::partition(order.begin() + j.first, order.begin() + j.first + j.count, [&](int t) {
+          int b = (int)((cen[3 * (size_t)t + best_axis] - lo) * scale);
+          b = b < 0 ? 0 : (b >= kBins ? kBins - 1 : b);
+          return b <= best_bin;
+        });
+        mid = (int)(it - order.begin());
+        if (mid == j.first || mid == j.first + j.count) mid = j.first + j.count / 2;
+      }
+      const int l = (int)nodes.size();
+      nodes.push_back(BNode{});
+      nodes.push_back(BNode{});
+      nodes[j.node].left = l;
+      nodes[j.node].right = l + 1;
+      todo.push_back({l, j.first, mid - j.first});
+      todo.push_back({l + 1, mid, j.first + j.count - mid});
+    }
+  }
+};
+
+}  // namespace elg
+
+namespace {
+int mfail(int code, const char* msg) { return elg::set_error(code, msg); }
+}  // namespace
+
+extern "C" {
+
+int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, ElgMesh** out) {
+  if (!out) return mfail(ELG_ERR_NULL_POINTER, "out is NULL");
+  *out = nullptr;
+  if (!vertices || !triangles) return mfail(ELG_ERR_NULL_POINTER, "vertices/triangles is NULL (host pointers expected)");
+  if (num_vertices < 3 || num_triangles < 1) return mfail(ELG_ERR_INVALID_ARGUMENT, "a mesh needs >= 3 vertices and >= 1 triangle");
+  if (num_triangles > (1 << 28)) return mfail(ELG_ERR_UNSUPPORTED, "more than 2^28 triangles");
+  for (long long i = 0; i < 3LL * num_triangles; ++i)
+    if (triangles[i] < 0 || triangles[i] >= num_vertices) return mfail(ELG_ERR_INVALID_ARGUMENT, "triangle index out of range");
+  for (long long i = 0; i < 3LL * num_vertices; ++i)
+    if (!std::isfinite(vertices[i])) return mfail(ELG_ERR_INVALID_ARGUMENT, "non-finite vertex coordinate");
+
+  elg::Builder B;
+  B.V = vertices;
+  B.T = triangles;
+  B.M = num_triangles;
+  B.run();
+
+  // collapse: every 4-wide node adopts grandchildren, widest-area child first
+  struct WNode { int child[4]; elg::Box box[4]; };
+  std::vector<WNode> wide;
+  std::vector<int> bin_of;   // binary node of each wide node
+  wide.reserve(B.nodes.size() / 2 + 1);
+  wide.push_back(WNode{});
+  bin_of.push_back(0);
+  const auto leaf_code = [&](const elg::BNode& n) { return ~((n.first << 2) | (n.count - 1)); };
+  for (size_t w = 0; w < wide.size(); ++w) {
+    const int bn = bin_of[w];
+    int slots[4], ns = 0;
+    if (B.nodes[bn].left < 0) {
+      slots[ns++] = bn;   // the root itself is a leaf (tiny mesh)
+    } else {
+      slots[ns++] = B.nodes[bn].left;
+      slots[ns++] = B.nodes[bn].right;
+      while (ns < 4) {
+        int pick = -1;
+        double best = -1.0;
+        for (int s = 0; s < ns; ++s)
+          if (B.nodes[slots[s]].left >= 0 && B.nodes[slots[s]].box.area() > best) { best = B.nodes[slots[s]].box.area(); pick = s; }
+        if (pick < 0) break;
+        const int p = slots[pick];
+        slots[pick] = B.nodes[p].left;
+        slots[ns++] = B.nodes[p].right;
+      }
+    }
+    WNode wn;
+    for (int s = 0; s < 4; ++s) {
+      wn.child[s] = elg::kEmpty;
+      wn.box[s].reset();
+    }
+    for (int s = 0; s < ns; ++s) {
+      const elg::BNode& c = B.nodes[slots[s]];
+      wn.box[s] = c.box;
+      if (c.left < 0) {
+        wn.child[s] = leaf_code(c);
+      } else {
+        wn.child[s] = (int)wide.size();
+        wide.push_back(WNode{});
+        bin_of.push_back(slots[s]);
+      }
+    }
+    wide[w] = wn;
+  }
+
+  // pack
+  elg::Box scene = B.nodes[0].box;
+  float ext = 0.0f;
+  for (int k = 0; k < 3; ++k) ext = std::max(ext, std::max(fabsf(scene.lo[k]), fabsf(scene.hi[k])));
+  const float pad = 4e-7f * ext + 1e-30f;   // > 3 ulp of the largest coordinate: the fp32 slab test stays conservative
+  std::vector<float> hn(32 * wide.size());
+  for (size_t w = 0; w < wide.size(); ++w) {
+    float* p = hn.data() + 32 * w;
+    for (int s = 0; s < 4; ++s) {
+      const bool e = wide[w].child[s] == elg::kEmpty;
+      for (int k = 0; k < 3; ++k) {
+        p[4 * k + s] = e ? FLT_MAX : wide[w].box[s].lo[k] - pad;
+        p[12 + 4 * k + s] = e ? -FLT_MAX : wide[w].box[s].hi[k] + pad;
+      }
+      memcpy(p + 24 + s, &wide[w].child[s], 4);
+    }
+    for (int s = 28; s < 32; ++s) p[s] = 0.0f;
+  }
+  std::vector<float> ht(12 * (size_t)num_triangles);
+  double edge_sum = 0.0;
+  for (int i = 0; i < num_triangles; ++i) {
+    const int t = B.order[i];
+    float* p = ht.data() + 12 * (size_t)i;
+    const float* v[3];
+    for (int k = 0; k < 3; ++k) v[k] = vertices + 3 * (size_t)triangles[3 * (size_t)t + k];
+    for (int k = 0; k < 3; ++k) { p[k] = v[0][k]; p[3 + k] = v[1][k]; p[6 + k] = v[2][k]; }
+    memcpy(p + 9, &t, 4);
+    p[10] = p[11] = 0.0f;
+    for (int e = 0; e < 3; ++e) {
+      const float* a = v[e];
+      const float* b = v[(e + 1) % 3];
+      edge_sum += sqrt(((double)a[0] - b[0]) * ((double)a[0] - b[0]) + ((double)a[1] - b[1]) * ((double)a[1] - b[1]) +
+                       ((double)a[2] - b[2]) * ((double)a[2] - b[2]));
+    }
+  }
+
+  ElgMesh* m = new ElgMesh();
+  m->num_vertices = num_vertices;
+  m->num_triangles = num_triangles;
+  m->num_nodes = (int)wide.size();
+  m->avg_edge = edge_sum / (3.0 * num_triangles);
+  for (int k = 0; k < 3; ++k) { m->lo[k] = scene.lo[k]; m->hi[k] = scene.hi[k]; }
+  m->nodes = nullptr;
+  m->tris = nullptr;
+  cudaGetDevice(&m->device);
+  if (cudaMalloc(&m->nodes, hn.size() * 4) != cudaSuccess || cudaMalloc(&m->tris, ht.size() * 4) != cudaSuccess ||
+      cudaMemcpy(m->nodes, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
+      cudaMemcpy(m->tris, ht.data(), ht.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaGetLastError();
+    if (m->nodes) cudaFree(m->nodes);
+    if (m->tris) cudaFree(m->tris);
+    delete m;
+    return mfail(ELG_ERR_CUDA, "elg_mesh_create: cannot allocate / upload the BVH (is a CUDA device present?)");
+  }
+  *out = m;
+  return ELG_OK;
+}
+
+int elg_mesh_free(ElgMesh* mesh) {
+  if (!mesh) return ELG_OK;
+  cudaFree(mesh->nodes);
+  cudaFree(mesh->tris);
+  delete mesh;
+  return ELG_OK;
+}
+
+int elg_mesh_info(const ElgMesh* mesh, int32_t* num_triangles, int32_t* num_nodes, float* bounds6) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "mesh is NULL");
+  if (num_triangles) *num_triangles = mesh->num_triangles;
+  if (num_nodes) *num_nodes = mesh->num_nodes;
+  if (bounds6)
+    for (int k = 0; k < 3; ++k) { bounds6[k] = mesh->lo[k]; bounds6[3 + k] = mesh->hi[k]; }
+  return ELG_OK;
+}
+
+int elg_raycast(const ElgMesh* mesh, const float* ray_origins, const float* ray_directions, int64_t num_rays, float max_dist,
+                float* ray_hits, uint8_t* hits_found, float* hit_distance, int32_t* hit_triangle, void* stream) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "Mesh cannot be None");
+  if (num_rays < 0) return mfail(ELG_ERR_INVALID_ARGUMENT, "num_rays < 0");
+  if (num_rays == 0) return ELG_OK;
+  if (!ray_origins || !ray_directions || !ray_hits || !hits_found) return mfail(ELG_ERR_NULL_POINTER, "a ray buffer is NULL");
+  if (!(max_dist >= 0.0f)) return mfail(ELG_ERR_INVALID_ARGUMENT, "max_dist must be >= 0");
+  const int threads = 128;
+  const long long blocks = (num_rays + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many rays for one launch");
+  elg::elg_raycast_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(mesh->nodes, mesh->tris, ray_origins, ray_directions,
+                                                                                  num_rays, max_dist, ray_hits, hits_found, hit_distance,
+                                                                                  hit_triangle);
+  return elg::check_launch("elg_raycast");
+}
+
+}  // extern "C"

@@ -255,7 +255,9 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
   const bool need_hsum = do_reward && term_on(pr, ELG_REW_BASE_HEIGHT) && H > 0;
   const bool gait = bf.gait_idx != nullptr && bf.gait_prev_foot_z != nullptr;
   const bool lim_terms = term_on(pr, ELG_REW_DOF_POS_LIMITS) | term_on(pr, ELG_REW_DOF_VEL_LIMITS) | term_on(pr, ELG_REW_TORQUE_LIMITS);
-  const bool heights_live = H > 0 && do_derive && !pr.terrain_is_plane;
+  const bool rollout = !kFast && pr.rollout_mode != 0;
+  const bool heights_live = H > 0 && do_derive && !pr.terrain_is_plane && !rollout;
+  const bool mh_given = !do_derive || rollout;   // measured_heights is an input of this launch
   const bool shared_grid = kFast || pr.height_points_env_stride == 0;
   const int noise_mode = pr.noise_mode;
   const float clip_obs = pr.clip_observations;
@@ -264,6 +266,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
   const int LF = kF ? (kF <= 4 ? 4 : 8) : (F <= 4 ? 4 : 8);
   const int LP = PT <= 16 ? 16 : 32;
   constexpr int LR = 8;
+  const int lgD = LD == 16 ? 4 : 5, lgF = LF == 4 ? 2 : 3, lgP = LP == 16 ? 4 : 5;
 
 #define SM_F(off) reinterpret_cast<float*>(smem_raw + (off))
   float* const s_root = SM_F(L.root);   float* const s_dof = SM_F(L.dof);    float* const s_act = SM_F(L.act);
@@ -324,6 +327,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
     if (lane < P) s_body[lane] = dm.penalised_idx[lane];
     if (lane < T) s_body[P + lane] = dm.termination_idx[lane];
   }
+#pragma unroll 1
   for (int j = tid; j < D; j += nthreads) {
     s_q0[j] = __ldg(bf.default_dof_pos + j);
     if (lim_terms) {
@@ -335,9 +339,11 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
   }
   {
     const bool ns_on = bf.noise_scale_vec != nullptr && noise_mode != ELG_NOISE_OFF;
+#pragma unroll 1
     for (int k = tid; k < O; k += nthreads) s_ns[k] = ns_on ? __ldg(bf.noise_scale_vec + k) : 0.0f;
   }
   if (H > 0 && shared_grid && bf.height_points)
+#pragma unroll 1
     for (int p = tid; p < H; p += nthreads) {
       const float bx = __ldg(bf.height_points + 3 * p), by = __ldg(bf.height_points + 3 * p + 1);
       s_grid[p] = make_float4(bx, by, by, bx);
@@ -360,16 +366,16 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
     }
     const int n = nenv;
     // item-pass geometry: [foot | rotation | dof | body] passes, one warp each
-    const int wF = (F > 0) ? (n * LF + 31) >> 5 : 0;
+    const int wF = (F > 0) ? ((n << lgF) + 31) >> 5 : 0;
     const int wR = (n * LR + 31) >> 5;
-    const int wD = (n * LD + 31) >> 5;
-    const int wP = (PT > 0) ? (n * LP + 31) >> 5 : 0;
+    const int wD = ((n << lgD) + 31) >> 5;
+    const int wP = (PT > 0) ? ((n << lgP) + 31) >> 5 : 0;
     const int n_passes = wF + wR + wD + wP;
 
     // ---- stage 0: foot lanes prefetch their rigid_body_state rows (52-byte rows, 6 useful floats) while the bulk
     // copies are in flight; kept in registers until the wait below (shared memory may still feed the previous stores)
     float fr[6] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
-    const int f_e = (warp * 32 + lane) / LF, f_f = lane & (LF - 1);
+    const int f_e = (warp * 32 + lane) >> lgF, f_f = lane & (LF - 1);
     const bool foot_lane = warp < wF && f_e < n && f_f < F;
     if (foot_lane && do_derive) {
       const float* row = bf.rigid_body_state + ((size_t)(env0 + f_e) * B + feet_of(f_f)) * 13;
@@ -394,7 +400,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         // ---- (env, foot) (legged_robot_rew_mixin.py:58-81, :121-212; gait_scheduler.py:74-81)
         // Terms that sort before feet_air_time read the OLD timers, terms after it the updated ones
         // and the rebound last_contacts.
-        const int e = (wp * 32 + lane) / LF, f = lane & (LF - 1);
+        const int e = (wp * 32 + lane) >> lgF, f = lane & (LF - 1);
         const bool ok = e < n && f < F;
         const int fi = e * F + f;
         float f_tz = 0.0f, f_tn = 0.0f, f_air = 0.0f, f_cf = 0.0f, f_slip = 0.0f, f_lift = 0.0f, f_jump = 0.0f, f_stum = 0.0f,
@@ -478,7 +484,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         }
       } else if (wp < wF + wR) {
         // ---- (env, rotation): base-frame velocities, gravity, acceleration EMAs (:128-134); root-velocity history (:150)
-        const int e = ((wp - wF) * 32 + lane) / LR, r = lane & (LR - 1);
+        const int e = ((wp - wF) * 32 + lane) >> 3, r = lane & (LR - 1);
         const bool ok = e < n;
         const float* rs = s_root + e * 13;
         if (ok && do_derive && r < 5) {
@@ -506,10 +512,10 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         }
         __syncwarp();
         if (ok && do_hist && r < 6) s_lrv[e * 6 + r] = rs[7 + r];
-        if (ok && do_derive && r == 7) s_ep[e] += 1;   // episode counter (legged_robot.py:122)
+        if (ok && do_derive && !rollout && r == 7) s_ep[e] += 1;   // episode counter (legged_robot.py:122)
       } else if (wp < wF + wR + wD) {
         // ---- (env, dof): per-dof reward partials, observation entries, history (:84-114, :237-244, :148-149)
-        const int e = ((wp - wF - wR) * 32 + lane) / LD, j = lane & (LD - 1);
+        const int e = ((wp - wF - wR) * 32 + lane) >> lgD, j = lane & (LD - 1);
         const bool ok = e < n && j < D;
         float q_ar = 0.0f, q_da = 0.0f, q_dv = 0.0f, q_tq = 0.0f, q_ss = 0.0f, q_pl = 0.0f, q_vl = 0.0f, q_tl = 0.0f;
         if (ok) {
@@ -562,7 +568,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         }
       } else {
         // ---- (env, body): collision count and termination contacts (:117-119, legged_robot.py:155-160)
-        const int e = ((wp - wF - wR - wD) * 32 + lane) / LP, b = lane & (LP - 1);
+        const int e = ((wp - wF - wR - wD) * 32 + lane) >> lgP, b = lane & (LP - 1);
         bool hit = false;
         if (e < n && b < PT && (do_term || do_reward)) {
           const int body = s_body[b];
@@ -607,7 +613,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       const float* pg = s_vec5 + (2 * cap + e) * 3;
       float* cmd = s_cmd + e * C;
       float cmd2 = cmd[2];
-      if (do_derive && pr.heading_command) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
+      if (do_derive && !rollout && pr.heading_command) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
         const Quat q = {rs[3], rs[4], rs[5], rs[6]};
         const float fx = 1.0f + (q.y * (-2.0f * q.y) - q.z * (2.0f * q.z));
         const float fy = q.w * (2.0f * q.z) + (q.z * 0.0f - q.x * (-2.0f * q.y));
@@ -688,7 +694,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       for (int ti = 0; ti < L.nterms; ++ti) {
         const int t = L.term_ids[ti];
         const float r = ACC(t, e) * pr.reward_scales[t];
-        s_sums[ti * cap + e] += r;
+        if (!rollout) s_sums[ti * cap + e] += r;
         if (t == ELG_REW_TERMINATION) r_term = r;   // added after the clip
         else total += r;
       }
@@ -797,7 +803,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const int p = lane + 32 * (j0 + u);
-              hv[u] = (!do_derive && p < H) ? mh[p] : 0.0f;   // plane terrain: zeros (legged_robot.py:913-914)
+              hv[u] = (mh_given && p < H) ? mh[p] : 0.0f;   // plane terrain: zeros (legged_robot.py:913-914)
             }
           }
 #pragma unroll
@@ -805,7 +811,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
             const int p = lane + 32 * (j0 + u);
             if (p < H) {
               const float h = hv[u];
-              if (do_derive) mh[p] = h;
+              if (!mh_given) mh[p] = h;
               hsum += sub_r(rootz, h);
               if (do_obs) {
                 const int k = head + p;
@@ -968,12 +974,9 @@ elg_height_min_kernel(const int16_t* __restrict__ hs, const int rows, const int 
 // =================================================================================================
 // C ABI
 // =================================================================================================
-namespace {
-struct StepTune { int cap, threads, ctas_per_sm, no_bulk, no_fast; };
-StepTune g_tune = {0, 0, 0, 0, 0};
-long long* g_step_dbg = nullptr;
+namespace elg {
 thread_local char g_err[256] = "";
-int fail(int code, const char* msg) {
+int set_error(int code, const char* msg) {
   snprintf(g_err, sizeof(g_err), "%s", msg);
   return code;
 }
@@ -985,6 +988,23 @@ int check_launch(const char* what) {
   }
   return ELG_OK;
 }
+int sm_count() {
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 0;
+    sms = v;
+  }
+  return sms;
+}
+}  // namespace elg
+
+namespace {
+struct StepTune { int cap, threads, ctas_per_sm, no_bulk, no_fast; };
+StepTune g_tune = {0, 0, 0, 0, 0};
+long long* g_step_dbg = nullptr;
+int fail(int code, const char* msg) { return elg::set_error(code, msg); }
+int check_launch(const char* what) { return elg::check_launch(what); }
 const char* kTermNames[ELG_NUM_REWARD_TERMS] = {
     "action_rate", "ang_vel_xy", "base_foot_height", "base_height", "collision", "dof_acc", "dof_pos_limits", "dof_vel",
     "dof_vel_limits", "feet_air_time", "feet_contact_forces", "feet_slip", "feet_stumble", "feet_stumble_liftup",
@@ -1014,7 +1034,7 @@ int elg_abi_version(void) { return ELG_ABI_VERSION; }
 int elg_sizeof_dims(void) { return (int)sizeof(ElgDims); }
 int elg_sizeof_step_params(void) { return (int)sizeof(ElgStepParams); }
 int elg_sizeof_step_buffers(void) { return (int)sizeof(ElgStepBuffers); }
-const char* elg_last_error(void) { return g_err; }
+const char* elg_last_error(void) { return elg::g_err; }
 const char* elg_reward_term_name(int term) { return (term >= 0 && term < ELG_NUM_REWARD_TERMS) ? kTermNames[term] : nullptr; }
 
 int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const float* actions, const float* dof_state,
@@ -1077,6 +1097,7 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
   const bool gait = buf->gait_idx && buf->gait_prev_foot_z;
   const bool need_hsum = do_reward && ((prm->reward_mask >> ELG_REW_BASE_HEIGHT) & 1u) && H > 0;
   const bool air_on = (prm->reward_mask >> ELG_REW_FEET_AIR_TIME) & 1u;
+  const bool rollout = prm->rollout_mode != 0;
 
   static int sms = 0;
   if (sms == 0) {
@@ -1185,6 +1206,7 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
     in(buf->last_root_vel, L.lrv, 24);
     in(buf->base_lin_acc, L.vec5 + 3 * v3, 12);
     in(buf->base_ang_acc, L.vec5 + 4 * v3, 12);
+    if (rollout && H > 0 && (do_obs || need_hsum)) in(buf->measured_heights, L.mh, 4 * H);
   } else {
     in(buf->base_lin_vel, L.vec5 + 0 * v3, 12);
     in(buf->base_ang_vel, L.vec5 + 1 * v3, 12);
@@ -1201,12 +1223,12 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
     in(buf->feet_contact_time, L.con, 4 * F);
     in(buf->last_contacts, L.lc, F);
   }
-  if (do_derive || do_term) in(buf->episode_length_buf, L.ep, 8);
+  if ((do_derive && !rollout) || do_term) in(buf->episode_length_buf, L.ep, 8);
   if (gait && do_reward) {
     in(buf->gait_idx, L.gidx, 4);
     in(buf->gait_prev_foot_z, L.gprev, 4 * F);
   }
-  if (do_reward)
+  if (do_reward && !rollout)
     for (int ti = 0; ti < nt; ++ti) in(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
 
   if (do_derive) {
@@ -1219,9 +1241,9 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
       out(buf->foot_positions, L.fpos, 12 * F);
       out(buf->foot_velocities, L.fvel, 12 * F);
     }
-    if (prm->heading_command) out(buf->commands, L.cmd, 4 * C);
-    out(buf->episode_length_buf, L.ep, 8);
-    if (H > 0) out(buf->measured_heights, L.mh, 4 * H);
+    if (prm->heading_command && !rollout) out(buf->commands, L.cmd, 4 * C);
+    if (!rollout) out(buf->episode_length_buf, L.ep, 8);
+    if (H > 0 && !rollout) out(buf->measured_heights, L.mh, 4 * H);
   }
   if (do_reward) {
     if (air_on && F > 0) {
@@ -1229,7 +1251,8 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
       out(buf->feet_contact_time, L.con, 4 * F);
       out(buf->last_contacts, L.lc, F);
     }
-    for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
+    if (!rollout)
+      for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
     out(buf->rew_buf, L.rew, 4);
     if (gait) {
       out(buf->gait_idx, L.gidx, 4);
@@ -1252,7 +1275,7 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
 
   const size_t smem = (size_t)L.bytes;
   const bool quad = (D == 12 && F == 4);
-  const bool fast = quad && phase == ELG_PHASE_FUSED && L.use_bulk && L.obs_smem && prm->height_points_env_stride == 0 &&
+  const bool fast = quad && phase == ELG_PHASE_FUSED && !rollout && L.use_bulk && L.obs_smem && prm->height_points_env_stride == 0 &&
                     (H == 0 || prm->terrain_is_plane || buf->height_field_min != nullptr) && g_tune.no_fast == 0;
   auto kern = fast ? elg::elg_step_kernel<12, 4, true> : quad ? elg::elg_step_kernel<12, 4, false> : elg::elg_step_kernel<0, 0, false>;
   const int which = fast ? 2 : quad ? 1 : 0;

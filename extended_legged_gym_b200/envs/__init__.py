@@ -4,6 +4,8 @@ from .base.legged_robot import LeggedRobot
 from .anymal_c.anymal_c_config import AnymalCRoughCfg, AnymalCRoughCfgPPO, AnymalCFlatCfg, AnymalCFlatCfgPPO
 from .a1.a1_config import A1RoughCfg, A1RoughCfgPPO
 from .go2.go2_config import Go2RoughCfg, Go2RoughCfgPPO
+from .batch_rollout.robot_batch_rollout import RobotBatchRollout
+from .batch_rollout.robot_batch_rollout_config import RobotBatchRolloutCfg, RobotBatchRolloutCfgPPO
 
 TASKS = {
     "anymal_c_rough": (LeggedRobot, AnymalCRoughCfg, AnymalCRoughCfgPPO),

@@ -413,10 +413,11 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             self._bufs = self._native_buffers()
             object.__setattr__(self, "_ptrs_dirty", False)
 
-    def _launch(self, phase: int, clip_obs: float = 0.0):
+    def _launch(self, phase: int, clip_obs: float = 0.0, rollout: bool = False):
         self._sync_native()
         p = self._params
         p.clip_observations = clip_obs
+        p.rollout_mode = int(rollout)
         if not self.add_noise:
             p.noise_mode = _lib.NOISE_OFF
         else:

@@ -1,0 +1,219 @@
+"""``RobotBatchRollout`` -- main/rollout env layout for sampling-based MPC, host side.
+
+Same layout and API as the reference class (envs/batch_rollout/robot_batch_rollout.py in
+/root/reference/legged_gym/legged_gym): ``num_main_envs = cfg.env.num_envs`` main envs, each followed by
+``cfg.env.rollout_envs`` rollout envs (main k at row k (1 + R), :119-164).  What the reference does with a Python
+loop over the mains plus 14 gather/scatter pairs per call is ONE launch of ``elg_clone_rows`` here:
+
+  _sync_main_to_rollout()     :1447-1535  -> elg_clone_rows(ELG_CLONE_SYNC)   (+ optional position drift)
+  _cache_main_env_states()    :1537-1583  -> elg_clone_rows(ELG_CLONE_CACHE)
+  _restore_main_env_states()  :1585-1640  -> elg_clone_rows(ELG_CLONE_RESTORE)
+  step(actions)               :535-600    main-env actions in, main-env rows out
+  step_rollout(actions)       :602-716    rollout-env actions in, rollout rows out, mains restored
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from ... import _lib
+from ..base.legged_robot import LeggedRobot
+
+# fields copied main -> rollout (robot_batch_rollout.py:1474-1502).  base_pos / base_quat are views of root_states and
+# dof_pos / dof_vel views of dof_state, so the underlying tensors are passed once.
+SYNC_FIELDS = ("root_states", "dof_state", "actions", "last_actions", "last_dof_vel", "last_root_vel", "base_lin_vel",
+               "base_ang_vel", "projected_gravity", "feet_air_time", "feet_contact_time", "last_contacts")
+# fields cached / restored for the main rows (:1546-1583): the sync set + the acceleration EMAs
+CACHE_FIELDS = SYNC_FIELDS + ("base_lin_acc", "base_ang_acc")
+
+
+class RobotBatchRollout(LeggedRobot):
+    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True):
+        self.num_main_envs = cfg.env.num_envs
+        self.num_rollout_per_main = cfg.env.rollout_envs
+        self.total_num_envs = self.num_main_envs * (1 + self.num_rollout_per_main)
+        self.original_num_envs = cfg.env.num_envs
+        cfg.env.num_envs = self.total_num_envs          # every per-env tensor covers mains + rollouts (:77-80)
+        try:
+            super().__init__(cfg, sim_params, physics_engine, sim_device, headless)
+        finally:
+            cfg.env.num_envs = self.original_num_envs
+        self._init_env_indices()
+        self.t_main = 0.0
+        self.t_rollout = 0.0
+        self.main_env_cache = None
+        self.drift_u = None          # [num_rollout, 3] uniform samples for parity with torch.rand_like, else in-kernel Philox
+        self._clone_calls = 0
+
+    def _parse_cfg(self, cfg):
+        super()._parse_cfg(cfg)
+        # robot_batch_rollout.py:1646-1651: episode length in whole steps, integer push interval
+        self.max_episode_length_s = self.max_episode_length * self.dt
+        self.cfg.domain_rand.push_interval = int(self.cfg.domain_rand.push_interval_s / self.dt)
+
+    # ------------------------------------------------------------------------------------------
+    # env layout (robot_batch_rollout.py:119-164) -- closed form instead of the reference's loops
+    # ------------------------------------------------------------------------------------------
+    def _init_env_indices(self):
+        dev, R = self.device, self.num_rollout_per_main
+        total = self.total_num_envs
+        ar = torch.arange(total, device=dev)
+        self.main_env_indices = torch.arange(0, total, 1 + R, device=dev)
+        self.rollout_to_main_map = (ar // (1 + R)) * (1 + R)
+        self.is_main_env = (ar % (1 + R)) == 0
+        self.is_rollout_env = ~self.is_main_env
+        self.rollout_env_indices = torch.nonzero(self.is_rollout_env).flatten()
+        self.main_to_rollout_indices = [torch.arange(int(m) + 1, int(m) + 1 + R, device=dev) for m in self.main_env_indices.tolist()]
+
+    # ------------------------------------------------------------------------------------------
+    # clone / cache / restore
+    # ------------------------------------------------------------------------------------------
+    def _clone_table(self, fields, with_cache):
+        tb = _lib.ElgCloneTable()
+        tb.num_fields, tb.num_main, tb.rollouts_per_main = len(fields), self.num_main_envs, self.num_rollout_per_main
+        tb.drift_field = -1
+        keep = []
+        for i, name in enumerate(fields):
+            t = getattr(self, name)
+            if not (t.is_cuda and t.is_contiguous()):
+                raise _lib.ElgError(f"clone field '{name}' must be a contiguous CUDA tensor")
+            rows = self.total_num_envs
+            row_bytes = t.numel() * t.element_size() // rows
+            tb.fields[i].base = t.data_ptr()
+            tb.fields[i].row_bytes = row_bytes
+            if with_cache:
+                c = self.main_env_cache[name]
+                tb.fields[i].cache = c.data_ptr()
+                keep.append(c)
+            if name == "root_states":
+                tb.drift_field = i
+            keep.append(t)
+        return tb, keep
+
+    def _clone(self, mode, fields, drift=0.0):
+        tb, keep = self._clone_table(fields, with_cache=mode != _lib.CLONE_SYNC)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        du = self.drift_u
+        if du is not None and not (du.is_cuda and du.is_contiguous() and du.dtype == torch.float):
+            du = du.to(self.device, torch.float).contiguous()
+        rc = self._lib.elg_clone_rows(C.byref(tb), mode, float(drift), _lib.ptr(du), self.noise_seed, self._clone_calls, stream)
+        _lib.check(rc, "elg_clone_rows")
+        self._clone_calls += 1
+        del keep
+
+    def _sync_main_to_rollout(self):
+        if self.num_rollout_per_main == 0:
+            return
+        self._clone(_lib.CLONE_SYNC, SYNC_FIELDS, drift=self.cfg.domain_rand.rollout_envs_sync_pos_drift)
+        self.sim.set_dof_state()
+        self.sim.set_root_state()
+        self.t_rollout = self.t_main
+
+    def _cache_main_env_states(self):
+        if self.main_env_cache is None:
+            self.main_env_cache = {}
+            for name in CACHE_FIELDS:
+                t = getattr(self, name)
+                per_row = t.numel() // self.total_num_envs
+                self.main_env_cache[name] = torch.zeros(self.num_main_envs, per_row, dtype=t.dtype, device=self.device)
+            # views with the reference's cache keys (:1546-1564)
+            c = self.main_env_cache
+            c["dof_pos"] = c["dof_state"].view(self.num_main_envs, self.num_dof, 2)[..., 0]
+            c["dof_vel"] = c["dof_state"].view(self.num_main_envs, self.num_dof, 2)[..., 1]
+            c["base_pos"] = c["root_states"][:, :3]
+            c["base_quat"] = c["root_states"][:, 3:7]
+        self._clone(_lib.CLONE_CACHE, CACHE_FIELDS)
+
+    def _restore_main_env_states(self):
+        if self.main_env_cache is None:
+            print("Warning: Attempted to restore main environment states without cache.")
+            return
+        self._clone(_lib.CLONE_RESTORE, CACHE_FIELDS)
+        self.sim.set_dof_state()
+        self.sim.set_root_state()
+
+    # ------------------------------------------------------------------------------------------
+    # stepping (robot_batch_rollout.py:535-716)
+    # ------------------------------------------------------------------------------------------
+    def _rows(self, idx, clip_obs):
+        obs = torch.clip(self.obs_buf[idx], -clip_obs, clip_obs)
+        priv = None
+        if self.privileged_obs_buf is not None:
+            priv = torch.clip(self.privileged_obs_buf[idx], -clip_obs, clip_obs)
+        extras = {k: (v[idx] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == self.total_num_envs else v)
+                  for k, v in self.extras.items()}
+        return obs, priv, self.rew_buf[idx], self.reset_buf[idx], extras
+
+    def step(self, actions):
+        """actions: [num_main_envs, num_actions]; returns the main-env rows."""
+        full = torch.zeros((self.total_num_envs, self.num_actions), device=self.device)
+        full[self.main_env_indices] = actions.to(self.device)
+        clip_actions = self.cfg.normalization.clip_actions
+        torch.clamp(full, -clip_actions, clip_actions, out=self.actions)
+        self._sync_main_to_rollout()
+        for _ in range(self.cfg.control.decimation):
+            self.torques = self._compute_torques(self.actions).view(self.torques.shape)
+            self.sim.set_dof_actuation_force(self.torques)
+            self.sim.simulate()
+            self.sim.refresh()
+        self.post_physics_step()
+        out = self._rows(self.main_env_indices, self.cfg.normalization.clip_observations)
+        self._cache_main_env_states()
+        self._sync_main_to_rollout()
+        self.t_main += self.dt
+        self.t_rollout = self.t_main
+        return out
+
+    def step_rollout(self, rollout_actions, noise_scales=None):
+        """rollout_actions: [num_rollout_envs, A] (or the legacy [num_main_envs, A] mean actions with optional
+        Gaussian ``noise_scales``, :623-641); returns the rollout-env rows and leaves the main rows restored."""
+        n_roll = len(self.rollout_env_indices)
+        if rollout_actions.shape[0] == self.num_main_envs and self.num_main_envs != n_roll:
+            mean = rollout_actions.to(self.device).repeat_interleave(self.num_rollout_per_main, dim=0)
+            actions = mean + torch.randn_like(mean) * noise_scales.to(self.device) if noise_scales is not None else mean
+        else:
+            actions = rollout_actions
+            if actions.shape[0] != n_roll:
+                raise ValueError(f"Expected actions shape ({n_roll}, {self.num_actions}), got {actions.shape}")
+        clip_actions = self.cfg.normalization.clip_actions
+        self.actions[self.rollout_env_indices] = torch.clip(actions, -clip_actions, clip_actions).to(self.device)
+        for _ in range(self.cfg.control.decimation):
+            self.torques = self._compute_torques(self.actions).view(self.torques.shape)
+            self.sim.set_dof_actuation_force(self.torques)
+            self.sim.simulate()
+            self.sim.refresh()
+        self.post_physics_step_rollout()
+        self._restore_main_env_states()
+        out = self._rows(self.rollout_env_indices, self.cfg.normalization.clip_observations)
+        self.t_rollout += self.dt
+        return out
+
+    def post_physics_step_rollout(self):
+        """robot_batch_rollout.py:763-817: derive + rewards + observations + histories, no episode counter, no
+        termination / reset, no command / height refresh (``_post_physics_step_callback_rollout`` is empty).
+        The kernel runs over every row; main rows are put back by ``_restore_main_env_states`` right after."""
+        self.sim.refresh()
+        P = _lib
+        self._launch(P.PHASE_DERIVE | P.PHASE_REWARD | P.PHASE_OBS | P.PHASE_HISTORY, rollout=True)
+
+    def check_termination(self):
+        """:857-866 -- contact termination everywhere, time-outs only OR-ed into the main rows."""
+        super().check_termination()
+        contact_only = self.reset_buf & ~self.time_out_buf
+        self.reset_buf[self.rollout_env_indices] = contact_only[self.rollout_env_indices]
+
+    def set_commands(self, main_env_idx, commands):
+        lo = int(main_env_idx) * (1 + self.num_rollout_per_main)
+        self.commands[lo:lo + 1 + self.num_rollout_per_main] = commands.to(self.device)
+
+    def set_all_commands(self, commands):
+        self.commands[:] = commands.to(self.device).repeat_interleave(1 + self.num_rollout_per_main, dim=0)
+
+    def get_observations(self):
+        return self.obs_buf[self.main_env_indices]
+
+    def get_observations_rollout(self):
+        return self.obs_buf[self.rollout_env_indices]
+
+    def get_observations_all(self):
+        return self.obs_buf

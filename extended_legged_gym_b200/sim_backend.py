@@ -36,6 +36,7 @@ class SimBackend:
     def set_dof_state_indexed(self, env_ids: torch.Tensor) -> None: ...
     def set_root_state_indexed(self, env_ids: torch.Tensor) -> None: ...
     def set_root_state(self) -> None: ...
+    def set_dof_state(self) -> None: ...
 
 
 class SyntheticSim(SimBackend):
@@ -90,6 +91,9 @@ class SyntheticSim(SimBackend):
         pass
 
     def set_root_state_indexed(self, env_ids) -> None:
+        pass
+
+    def set_dof_state(self) -> None:
         pass
 
     def set_root_state(self) -> None:

@@ -127,6 +127,9 @@ typedef struct ElgStepParams {
   int32_t terrain_is_plane;  /* mesh_type == 'plane' -> heights are zeros (legged_robot.py:913-914) */
   int32_t only_positive_rewards;
   int32_t noise_mode;        /* ElgNoiseMode */
+  int32_t rollout_mode;      /* post_physics_step_rollout (batch_rollout/robot_batch_rollout.py:763-817): with ELG_PHASE_DERIVE no
+                                episode counter, heading command or height scan (measured_heights is an input); rewards do not
+                                accumulate episode sums (compute_reward_rollout :969-985) */
   float clip_observations;   /* <= 0: no clip; > 0: step()'s clip fused (legged_robot.py:107-108) */
   float gravity_vec[3];      /* normalised gravity, (0,0,-1) */
   float obs_scale_lin_vel, obs_scale_ang_vel, obs_scale_dof_pos, obs_scale_dof_vel, obs_scale_height;
@@ -230,6 +233,53 @@ int elg_set_step_debug(long long* device_stamps);
  * int32 [N,H,2]) receives the clipped (px, py) terrain cell of every point for index parity tests. */
 int elg_get_heights(const ElgDims* dims, const ElgStepParams* prm, const float* root_states, const int16_t* height_samples,
                     const float* height_points, float* measured_heights, int32_t* cells_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Main -> rollout state clone (envs/batch_rollout/robot_batch_rollout.py:1447-1535 _sync_main_to_rollout,
+ * :1537-1583 _cache_main_env_states, :1585-1640 _restore_main_env_states; env layout _init_env_indices :119-164:
+ * main env k is row k * (1 + rollouts_per_main) of every per-env tensor, its rollout envs are the rows behind it).
+ * A field is one per-env tensor with a fixed number of bytes per env row; aliasing views of one tensor (base_pos /
+ * base_quat of root_states, dof_pos / dof_vel of dof_state) are passed once, as the underlying tensor. */
+#define ELG_MAX_CLONE_FIELDS 24
+typedef enum ElgCloneMode {
+  ELG_CLONE_SYNC = 0,   /* main row -> each of its rollout rows (+ optional position drift) */
+  ELG_CLONE_CACHE = 1,  /* main rows -> cache tensors [num_main, row] (fields with cache == NULL are skipped) */
+  ELG_CLONE_RESTORE = 2 /* cache tensors -> main rows */
+} ElgCloneMode;
+typedef struct ElgCloneField {
+  void* base;        /* [num_main * (1 + rollouts_per_main), row] */
+  void* cache;       /* [num_main, row] or NULL */
+  int32_t row_bytes;
+  int32_t reserved;
+} ElgCloneField;
+typedef struct ElgCloneTable {
+  int32_t num_fields, num_main, rollouts_per_main;
+  int32_t drift_field; /* index of the field whose first three floats are the base position (root_states), or -1 */
+  ElgCloneField fields[ELG_MAX_CLONE_FIELDS];
+} ElgCloneTable;
+int elg_sizeof_clone_table(void);
+/* drift: cfg.domain_rand.rollout_envs_sync_pos_drift (<= 0: none); drift_u: [num_main * rollouts_per_main, 3] uniform
+ * samples (= torch.rand_like(base_pos[rollout_env_indices]), robot_batch_rollout.py:1493-1497) or NULL for in-kernel
+ * Philox4x32-10 keyed by seed with counter (sample index, offset). */
+int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const float* drift_u, uint64_t seed, uint64_t offset, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Triangle-mesh queries (the reference delegates these to warp-lang 1.7: wp.Mesh / wp.mesh_query_ray /
+ * wp.mesh_query_point_sign_normal).  ElgMesh is the only object the library owns: an opaque handle holding the
+ * device-resident 4-wide BVH of one static mesh, the counterpart of utils/ray_caster.py:29-42 convert_to_warp_mesh. */
+typedef struct ElgMesh ElgMesh;
+/* vertices [V,3] fp32 and triangles [M,3] int32 are HOST pointers (the reference also builds from numpy arrays); the
+ * BVH is built on the host once and uploaded to the current CUDA device. */
+int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, ElgMesh** out);
+int elg_mesh_free(ElgMesh* mesh);
+int elg_mesh_info(const ElgMesh* mesh, int32_t* num_triangles, int32_t* num_nodes, float* bounds6);
+
+/* raycast_mesh + raycast_mesh_kernel (utils/ray_caster.py:45-167): closest hit with t in [0, max_dist) against both
+ * face orientations; ray_hits = origin + t * direction, or the end point origin + max_dist * direction on a miss;
+ * hits_found is torch.bool storage.  hit_distance (t, or max_dist on a miss) and hit_triangle (caller's triangle id, -1 on
+ * a miss) are optional extras.  All ray buffers are device pointers, [num_rays, 3] fp32 contiguous. */
+int elg_raycast(const ElgMesh* mesh, const float* ray_origins, const float* ray_directions, int64_t num_rays, float max_dist,
+                float* ray_hits, uint8_t* hits_found, float* hit_distance, int32_t* hit_triangle, void* stream);
 
 /* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =
  * fp32(min(hs[i][j], hs[i+1][j], hs[i][j+1])) * vertical_scale for i <= rows-2, j <= cols-2 (0 elsewhere) -- the

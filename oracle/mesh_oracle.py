@@ -1,0 +1,149 @@
+"""TEST INFRASTRUCTURE ONLY (oracle) -- the checker, never the product path.  PARITY UNPINNED for the Warp parts.
+
+float64 brute-force restatement of the mesh queries the reference delegates to warp-lang==1.7.0
+(legged_gym/setup.py:17; the wheel is absent from /root/reference and from this image, so its kernels cannot be run):
+
+  raycast_mesh        utils/ray_caster.py:45-167   wp.mesh_query_ray: closest hit with t in [0, max_dist), both face
+                                                    orientations; miss -> end point origin + max_dist * direction
+  sdf_query           utils/mesh_sdf.py:38-116     wp.mesh_query_point_sign_normal + mesh_eval_position
+  ray caster / depth camera host arithmetic        utils/ray_caster.py:558-594, utils/depth_camera.py:402-566 (these are
+                                                    torch code of the reference itself and are restated op by op)
+
+Every float64 expression below is a chain of individually rounded elementwise numpy operations, in the order the
+CUDA kernels use (csrc/elg_mesh.cu), so kernel and oracle agree to the last bit of the fp32 results.  The informal
+known answers of the reference's demo scripts (tests/ray_cast/test_ray_caster.py:134-151 box mesh; tests/mesh_sdf/
+test_mesh_sdf.py:42-47 icosphere) are pinned in tests/test_mesh_oracle.py.
+Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU legs may import this module.
+"""
+import numpy as np
+
+
+def raycast_mesh(origins, directions, max_dist, vertices, triangles, chunk=256):
+    """origins, directions: [R,3] float32; vertices [V,3] float32; triangles [M,3] int.
+    Returns hits [R,3] float32, found [R] bool, t [R] float32 (max_dist on a miss), tri [R] int (-1 on a miss)."""
+    o32 = np.ascontiguousarray(origins, dtype=np.float32).reshape(-1, 3)
+    d32 = np.ascontiguousarray(directions, dtype=np.float32).reshape(-1, 3)
+    V = np.asarray(vertices, dtype=np.float32).astype(np.float64)
+    T = np.asarray(triangles).astype(np.int64)
+    v0, v1, v2 = V[T[:, 0]], V[T[:, 1]], V[T[:, 2]]
+    e1, e2 = v1 - v0, v2 - v0
+    R = o32.shape[0]
+    t_best = np.full(R, np.float64(np.float32(max_dist)))
+    tri = np.full(R, -1, dtype=np.int64)
+    with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+        for a in range(0, R, chunk):
+            o = o32[a:a + chunk].astype(np.float64)[:, None, :]
+            d = d32[a:a + chunk].astype(np.float64)[:, None, :]
+            dx, dy, dz = d[..., 0], d[..., 1], d[..., 2]
+            e1x, e1y, e1z = e1[None, :, 0], e1[None, :, 1], e1[None, :, 2]
+            e2x, e2y, e2z = e2[None, :, 0], e2[None, :, 1], e2[None, :, 2]
+            px = dy * e2z - dz * e2y
+            py = dz * e2x - dx * e2z
+            pz = dx * e2y - dy * e2x
+            det = (e1x * px + e1y * py) + e1z * pz
+            inv = 1.0 / det
+            sx, sy, sz = o[..., 0] - v0[None, :, 0], o[..., 1] - v0[None, :, 1], o[..., 2] - v0[None, :, 2]
+            u = ((sx * px + sy * py) + sz * pz) * inv
+            qx = sy * e1z - sz * e1y
+            qy = sz * e1x - sx * e1z
+            qz = sx * e1y - sy * e1x
+            v = ((dx * qx + dy * qy) + dz * qz) * inv
+            t = ((e2x * qx + e2y * qy) + e2z * qz) * inv
+            ok = (det != 0.0) & (u >= 0.0) & (u <= 1.0) & (v >= 0.0) & ((u + v) <= 1.0) & (t >= 0.0) & (t < t_best[a:a + chunk, None])
+            tt = np.where(ok, t, np.inf)
+            k = np.argmin(tt, axis=1)
+            tb = tt[np.arange(tt.shape[0]), k]
+            hit = np.isfinite(tb)
+            t_best[a:a + chunk] = np.where(hit, tb, t_best[a:a + chunk])
+            tri[a:a + chunk] = np.where(hit, k, -1)
+    found = tri >= 0
+    t32 = t_best.astype(np.float32)
+    hits = o32 + t32[:, None] * d32          # fp32 multiply, fp32 add (ray_caster.py:86)
+    return hits.astype(np.float32), found, t32, tri
+
+
+# ----------------------------------------------------------------------------------------------
+# isaacgym.torch_utils.quat_apply / math_utils.quat_apply_yaw in fp32 numpy, one rounding per torch op
+# ----------------------------------------------------------------------------------------------
+def _cross(a, b):
+    return np.stack([a[..., 1] * b[..., 2] - a[..., 2] * b[..., 1],
+                     a[..., 2] * b[..., 0] - a[..., 0] * b[..., 2],
+                     a[..., 0] * b[..., 1] - a[..., 1] * b[..., 0]], axis=-1).astype(np.float32)
+
+
+def quat_apply(q, b):
+    q = np.asarray(q, dtype=np.float32)
+    b = np.asarray(b, dtype=np.float32)
+    xyz, w = q[..., :3], q[..., 3:4]
+    t = (_cross(xyz, b) * np.float32(2.0)).astype(np.float32)
+    return ((b + w * t).astype(np.float32) + _cross(xyz, t)).astype(np.float32)
+
+
+def quat_apply_yaw(q, b):
+    q = np.array(q, dtype=np.float32, copy=True)
+    q[..., :2] = 0.0
+    n = np.sqrt((q[..., 2] * q[..., 2] + q[..., 3] * q[..., 3]).astype(np.float32)).astype(np.float32)   # x, y are 0
+    q = (q / np.maximum(n, np.float32(1e-9))[..., None]).astype(np.float32)
+    return quat_apply(q, b)
+
+
+def sensor_rays(pattern_origins, pattern_dirs, sensor_pos, sensor_quat, yaw_only):
+    """RayCaster._update_ray_casting (utils/ray_caster.py:566-579): world rays of every (sensor, pattern ray)."""
+    N, n = sensor_pos.shape[0], pattern_dirs.shape[0]
+    q = np.repeat(np.asarray(sensor_quat, np.float32)[:, None, :], n, axis=1)
+    po = np.broadcast_to(np.asarray(pattern_origins, np.float32)[None], (N, n, 3))
+    pd = np.broadcast_to(np.asarray(pattern_dirs, np.float32)[None], (N, n, 3))
+    rot = quat_apply_yaw if yaw_only else quat_apply
+    o = (rot(q, po) + np.asarray(sensor_pos, np.float32)[:, None, :]).astype(np.float32)
+    return o, rot(q, pd)
+
+
+# ----------------------------------------------------------------------------------------------
+# fixture meshes
+# ----------------------------------------------------------------------------------------------
+def box_mesh(lo=(-1.0, -1.0, 1.0), hi=(1.0, 1.0, 2.0)):
+    """8-vertex box like the one in the reference's tests/ray_cast/test_ray_caster.py:96-130."""
+    x0, y0, z0 = lo
+    x1, y1, z1 = hi
+    v = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0], [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], np.float32)
+    t = np.array([[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 5, 1], [0, 4, 5], [1, 6, 2], [1, 5, 6], [2, 7, 3], [2, 6, 7],
+                  [3, 4, 0], [3, 7, 4]], np.int32)
+    return v, t
+
+
+def heightfield_mesh(rows, cols, hscale=0.1, vscale=0.005, seed=0, origin=(0.0, 0.0)):
+    """Grid mesh with the triangulation of isaacgym.terrain_utils.convert_heightfield_to_trimesh (two triangles per
+    cell, vertex (i, j) at (i * hscale, j * hscale, h * vscale)) over a seeded random int16 field of slopes and steps."""
+    rng = np.random.default_rng(seed)
+    ii, jj = np.meshgrid(np.arange(rows), np.arange(cols), indexing="ij")
+    h = (40 * np.sin(ii / 7.0) * np.cos(jj / 5.0) + rng.integers(-6, 7, size=(rows, cols)) + 30 * ((ii // 8 + jj // 8) % 2)).astype(np.int16)
+    v = np.stack([ii * hscale + origin[0], jj * hscale + origin[1], h * vscale], axis=-1).reshape(-1, 3).astype(np.float32)
+    idx = (ii * cols + jj)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel()
+    t = np.concatenate([np.stack([a, d, c], axis=1), np.stack([a, b, d], axis=1)], axis=0).astype(np.int32)
+    return v, t, h
+
+
+def icosphere(subdivisions=2, radius=1.0):
+    """Unit icosphere (tests/mesh_sdf/test_mesh_sdf.py:22-30 uses trimesh.creation.icosphere): outward-facing."""
+    phi = (1.0 + 5.0 ** 0.5) / 2.0
+    v = [(-1, phi, 0), (1, phi, 0), (-1, -phi, 0), (1, -phi, 0), (0, -1, phi), (0, 1, phi), (0, -1, -phi), (0, 1, -phi),
+         (phi, 0, -1), (phi, 0, 1), (-phi, 0, -1), (-phi, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    v = [np.array(p, np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (min(a, b), max(a, b))
+            if key not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[key] = len(v) - 1
+            return cache[key]
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return (np.array(v) * radius).astype(np.float32), np.array(f, np.int32)
