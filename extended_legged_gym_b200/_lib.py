@@ -124,6 +124,7 @@ def load() -> C.CDLL:
     lib.elg_mesh_free.argtypes = [vp]
     lib.elg_mesh_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     lib.elg_raycast.argtypes = [vp, vp, vp, i64, C.c_float, vp, vp, vp, vp, vp]
+    lib.elg_raycast_sensor.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, i64, C.c_int, C.c_float, vp, vp, vp]
     lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib
     return lib

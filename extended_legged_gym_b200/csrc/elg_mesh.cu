@@ -172,6 +172,58 @@ elg_raycast_kernel(const float4* __restrict__ nodes, const float4* __restrict__ 
   if (tri_out) tri_out[i] = ok ? h.tri : -1;
 }
 
+// isaacgym.torch_utils.quat_apply(q, b) = b + w t + xyz x t, t = 2 (xyz x b), every torch op rounded on its own
+__device__ __forceinline__ void quat_apply_r(const float qx, const float qy, const float qz, const float qw, const float bx,
+                                             const float by, const float bz, float& rx, float& ry, float& rz) {
+  const float tx = mul_r(sub_r(mul_r(qy, bz), mul_r(qz, by)), 2.0f);
+  const float ty = mul_r(sub_r(mul_r(qz, bx), mul_r(qx, bz)), 2.0f);
+  const float tz = mul_r(sub_r(mul_r(qx, by), mul_r(qy, bx)), 2.0f);
+  rx = add_r(add_r(bx, mul_r(qw, tx)), sub_r(mul_r(qy, tz), mul_r(qz, ty)));
+  ry = add_r(add_r(by, mul_r(qw, ty)), sub_r(mul_r(qz, tx), mul_r(qx, tz)));
+  rz = add_r(add_r(bz, mul_r(qw, tz)), sub_r(mul_r(qx, ty), mul_r(qy, tx)));
+}
+
+// ---------------------------------------------------------------------------------------------
+// RayCaster._update_ray_casting (utils/ray_caster.py:558-594) fused with the ray cast: the world ray of
+// (sensor, pattern ray) is built in registers -- quat_apply or quat_apply_yaw (utils/math_utils.py:40-44) of the
+// pattern origin / direction by the sensor quaternion, + sensor position -- instead of materialising [N, n, 3]
+// origin and direction tensors.  One thread per (sensor, ray); rays of one sensor share a warp where n >= 32.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+elg_raycast_sensor_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ pat_o,
+                          const float* __restrict__ pat_d, const int n_rays, const float* __restrict__ pos,
+                          const float* __restrict__ quat, const int64_t* __restrict__ env_ids, const long long n_sensors,
+                          const int yaw_only, const float max_dist, float* __restrict__ hits, uint8_t* __restrict__ found) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_sensors * n_rays) return;
+  const long long s = i / n_rays;
+  const int r = (int)(i - s * n_rays);
+  const long long e = env_ids ? env_ids[s] : s;
+  float qx = quat[4 * e], qy = quat[4 * e + 1], qz = quat[4 * e + 2], qw = quat[4 * e + 3];
+  if (yaw_only) {   // normalize((0, 0, qz, qw)), clamp(min=1e-9)
+    float nrm = __fsqrt_rn(add_r(mul_r(qz, qz), mul_r(qw, qw)));
+    nrm = fmaxf(nrm, 1e-9f);
+    qx = 0.0f;
+    qy = 0.0f;
+    qz = div_r(qz, nrm);
+    qw = div_r(qw, nrm);
+  }
+  float ox, oy, oz, dx, dy, dz;
+  quat_apply_r(qx, qy, qz, qw, pat_o[3 * r], pat_o[3 * r + 1], pat_o[3 * r + 2], ox, oy, oz);
+  ox = add_r(ox, pos[3 * e]);
+  oy = add_r(oy, pos[3 * e + 1]);
+  oz = add_r(oz, pos[3 * e + 2]);
+  quat_apply_r(qx, qy, qz, qw, pat_d[3 * r], pat_d[3 * r + 1], pat_d[3 * r + 2], dx, dy, dz);
+  Hit h;
+  const bool ok = trace(nodes, tris, ox, oy, oz, dx, dy, dz, max_dist, h);
+  const float t = ok ? (float)h.t : max_dist;
+  const long long o = (e * n_rays + r) * 3;
+  hits[o] = add_r(ox, mul_r(t, dx));
+  hits[o + 1] = add_r(oy, mul_r(t, dy));
+  hits[o + 2] = add_r(oz, mul_r(t, dz));
+  found[e * n_rays + r] = ok ? 1 : 0;
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: binned-SAH binary build, collapse to 4-wide, upload
 // ---------------------------------------------------------------------------------------------
@@ -450,6 +502,24 @@ int elg_raycast(const ElgMesh* mesh, const float* ray_origins, const float* ray_
                                                                                   num_rays, max_dist, ray_hits, hits_found, hit_distance,
                                                                                   hit_triangle);
   return elg::check_launch("elg_raycast");
+}
+
+int elg_raycast_sensor(const ElgMesh* mesh, const float* pattern_origins, const float* pattern_directions, int32_t num_rays,
+                       const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num_sensors, int yaw_only,
+                       float max_dist, float* ray_hits, uint8_t* hits_found, void* stream) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "Mesh cannot be None");
+  if (num_rays < 0 || num_sensors < 0) return mfail(ELG_ERR_INVALID_ARGUMENT, "negative ray / sensor count");
+  if (num_rays == 0 || num_sensors == 0) return ELG_OK;
+  if (!pattern_origins || !pattern_directions || !sensor_pos || !sensor_quat || !ray_hits || !hits_found)
+    return mfail(ELG_ERR_NULL_POINTER, "a sensor / ray buffer is NULL");
+  if (!(max_dist >= 0.0f)) return mfail(ELG_ERR_INVALID_ARGUMENT, "max_dist must be >= 0");
+  const int threads = 128;
+  const long long blocks = (num_sensors * num_rays + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many rays for one launch");
+  elg::elg_raycast_sensor_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
+      max_dist, ray_hits, hits_found);
+  return elg::check_launch("elg_raycast_sensor");
 }
 
 }  // extern "C"

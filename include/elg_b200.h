@@ -281,6 +281,15 @@ int elg_mesh_info(const ElgMesh* mesh, int32_t* num_triangles, int32_t* num_node
 int elg_raycast(const ElgMesh* mesh, const float* ray_origins, const float* ray_directions, int64_t num_rays, float max_dist,
                 float* ray_hits, uint8_t* hits_found, float* hit_distance, int32_t* hit_triangle, void* stream);
 
+/* RayCaster._update_ray_casting (utils/ray_caster.py:558-594) fused with the ray cast.  pattern_origins / _directions
+ * [num_rays, 3]: one sensor's pattern in the sensor frame (RayCaster.ray_origins[0] / ray_directions[0]); sensor_pos
+ * [*, 3], sensor_quat [*, 4] xyzw (RayCaster.data.pos / .rot); env_ids: the num_sensors rows to update (int64) or NULL
+ * for rows 0..num_sensors-1; yaw_only = cfg.attach_yaw_only.  ray_hits [*, num_rays, 3] and hits_found [*, num_rays]
+ * are written at the selected rows only. */
+int elg_raycast_sensor(const ElgMesh* mesh, const float* pattern_origins, const float* pattern_directions, int32_t num_rays,
+                       const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num_sensors, int yaw_only,
+                       float max_dist, float* ray_hits, uint8_t* hits_found, void* stream);
+
 /* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =
  * fp32(min(hs[i][j], hs[i+1][j], hs[i][j+1])) * vertical_scale for i <= rows-2, j <= cols-2 (0 elsewhere) -- the
  * value the reference computes per height point, tabulated once per (static) terrain so the step kernel gathers one
