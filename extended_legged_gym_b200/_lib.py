@@ -82,6 +82,11 @@ class ElgCloneTable(C.Structure):
                 ("fields", ElgCloneField * MAX_CLONE_FIELDS)]
 
 
+class ElgCamParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("out_width", C.c_int32), ("out_height", C.c_int32), ("buffer_len", C.c_int32),
+                ("resize", C.c_int32), ("max_taps", C.c_int32), ("near_clip", C.c_float), ("far_clip", C.c_float), ("noise_scale", C.c_float)]
+
+
 class ElgError(RuntimeError):
     pass
 
@@ -106,7 +111,7 @@ def load() -> C.CDLL:
     lib.elg_reward_term_name.restype = C.c_char_p
     lib.elg_reward_term_name.argtypes = [C.c_int]
     for fn, st in (("elg_sizeof_dims", ElgDims), ("elg_sizeof_step_params", ElgStepParams), ("elg_sizeof_step_buffers", ElgStepBuffers),
-                   ("elg_sizeof_clone_table", ElgCloneTable)):
+                   ("elg_sizeof_clone_table", ElgCloneTable), ("elg_sizeof_cam_params", ElgCamParams)):
         got = getattr(lib, fn)()
         if got != C.sizeof(st):
             raise ElgError(f"ABI mismatch: {fn}() = {got}, python mirror = {C.sizeof(st)}")
@@ -125,6 +130,8 @@ def load() -> C.CDLL:
     lib.elg_mesh_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     lib.elg_raycast.argtypes = [vp, vp, vp, i64, C.c_float, vp, vp, vp, vp, vp]
     lib.elg_raycast_sensor.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, i64, C.c_int, C.c_float, vp, vp, vp]
+    lib.elg_camera_pose.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
+    lib.elg_depth_camera.argtypes = [vp, C.POINTER(ElgCamParams)] + [vp] * 9 + [i64, vp, vp, vp]
     lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib
     return lib

@@ -224,6 +224,121 @@ elg_raycast_sensor_kernel(const float4* __restrict__ nodes, const float4* __rest
   found[e * n_rays + r] = ok ? 1 : 0;
 }
 
+// isaacgym.torch_utils.quat_mul(a, b) (xyzw), one rounding per torch op
+__device__ __forceinline__ void quat_mul_r(const float x1, const float y1, const float z1, const float w1, const float x2, const float y2,
+                                           const float z2, const float w2, float& x, float& y, float& z, float& w) {
+  const float ww = mul_r(add_r(z1, x1), add_r(x2, y2));
+  const float yy = mul_r(sub_r(w1, y1), add_r(w2, z2));
+  const float zz = mul_r(add_r(w1, y1), sub_r(w2, z2));
+  const float xx = add_r(add_r(ww, yy), zz);
+  const float qq = mul_r(0.5f, add_r(xx, mul_r(sub_r(z1, x1), sub_r(x2, y2))));
+  w = add_r(sub_r(qq, ww), mul_r(sub_r(z1, y1), sub_r(y2, z2)));
+  x = add_r(sub_r(qq, xx), mul_r(add_r(x1, w1), add_r(x2, w2)));
+  y = add_r(sub_r(qq, yy), mul_r(sub_r(w1, x1), add_r(y2, z2)));
+  z = add_r(sub_r(qq, zz), mul_r(add_r(z1, y1), sub_r(w2, x2)));
+}
+
+// DepthCameraWarp.update (utils/depth_camera.py:501-566): camera pose = base pose (x) mounting offset.
+// offset_quat is the 4-vector the reference builds ([w, x, y, z] order) and then feeds to the xyzw quat_mul -- the
+// arithmetic is replicated literally.
+__global__ void __launch_bounds__(128)
+elg_camera_pose_kernel(const float* __restrict__ pos, const float* __restrict__ quat, const int64_t* __restrict__ env_ids, const long long n,
+                       const float ox, const float oy, const float oz, const float q0, const float q1, const float q2, const float q3,
+                       float* __restrict__ cam_pos, float* __restrict__ cam_rot) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const long long e = env_ids ? env_ids[i] : i;
+  const float qx = quat[4 * e], qy = quat[4 * e + 1], qz = quat[4 * e + 2], qw = quat[4 * e + 3];
+  float wx, wy, wz;
+  quat_apply_r(qx, qy, qz, qw, ox, oy, oz, wx, wy, wz);
+  cam_pos[3 * e] = add_r(pos[3 * e], wx);
+  cam_pos[3 * e + 1] = add_r(pos[3 * e + 1], wy);
+  cam_pos[3 * e + 2] = add_r(pos[3 * e + 2], wz);
+  float x, y, z, w;
+  quat_mul_r(qx, qy, qz, qw, q0, q1, q2, q3, x, y, z, w);
+  cam_rot[4 * e] = x; cam_rot[4 * e + 1] = y; cam_rot[4 * e + 2] = z; cam_rot[4 * e + 3] = w;
+}
+
+// ---------------------------------------------------------------------------------------------
+// DepthCameraWarp.update_depth_buffer (utils/depth_camera.py:402-499) + DepthCameraBase.process_depth_image (:84-138)
+// as ONE kernel, one CTA per camera: the ray of every pixel is rotated into the world in registers, cast, turned into
+// -distance (or -far_clip), the image gets its scalar noise, is clipped, resized (separable antialiased bicubic, the
+// taps tabulated by the host from torchvision itself), normalised and pushed into the env's frame ring buffer -- the
+// reference's per-env Python loop (:486-499).  28 bytes per camera in, 4 bytes per output pixel out.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+elg_depth_camera_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const __grid_constant__ ElgCamParams cp,
+                        const float* __restrict__ ray_dirs, const float* __restrict__ cam_pos, const float* __restrict__ cam_rot,
+                        const int64_t* __restrict__ ep_len, const float* __restrict__ noise_u, const int32_t* __restrict__ rx_start,
+                        const float* __restrict__ rx_w, const int32_t* __restrict__ ry_start, const float* __restrict__ ry_w,
+                        float* __restrict__ depth_buffer, float* __restrict__ raw_depth) {
+  extern __shared__ float s_img[];   // [h * w] image, then [h * out_w] horizontally resized rows
+  const int e = blockIdx.x;
+  const int W = cp.width, Hh = cp.height, OW = cp.out_width, OH = cp.out_height;
+  const int npx = W * Hh;
+  const float px = cam_pos[3 * e], py = cam_pos[3 * e + 1], pz = cam_pos[3 * e + 2];
+  const float qx = cam_rot[4 * e], qy = cam_rot[4 * e + 1], qz = cam_rot[4 * e + 2], qw = cam_rot[4 * e + 3];
+  float noise = 0.0f;
+  if (cp.noise_scale != 0.0f && noise_u) noise = mul_r(cp.noise_scale, sub_r(noise_u[e], 0.5f));
+  for (int r = threadIdx.x; r < npx; r += blockDim.x) {
+    float dx, dy, dz;
+    quat_apply_r(qx, qy, qz, qw, ray_dirs[3 * r], ray_dirs[3 * r + 1], ray_dirs[3 * r + 2], dx, dy, dz);
+    Hit h;
+    const bool ok = trace(nodes, tris, px, py, pz, dx, dy, dz, cp.far_clip, h);
+    float d = -cp.far_clip;
+    if (ok) {
+      const float t = (float)h.t;
+      const float hx = add_r(px, mul_r(t, dx)), hy = add_r(py, mul_r(t, dy)), hz = add_r(pz, mul_r(t, dz));
+      d = -norm3_t(sub_r(hx, px), sub_r(hy, py), sub_r(hz, pz));     // torch.norm(hits - camera_pos) (:464)
+    }
+    if (raw_depth) raw_depth[(size_t)e * npx + r] = d;
+    d = add_r(d, noise);
+    d = fminf(fmaxf(d, -cp.far_clip), -cp.near_clip);
+    s_img[r] = d;
+  }
+  __syncthreads();
+  const float* src = s_img;
+  if (cp.resize) {
+    float* tmp = s_img + max(npx, OW * OH);   // [Hh, OW]
+    for (int i = threadIdx.x; i < Hh * OW; i += blockDim.x) {
+      const int y = i / OW, xo = i - y * OW;
+      const int x0 = rx_start[xo];
+      float acc = 0.0f;
+      for (int k = 0; k < cp.max_taps; ++k) {
+        const float wgt = rx_w[xo * cp.max_taps + k];
+        if (wgt != 0.0f) acc = add_r(acc, mul_r(wgt, s_img[y * W + min(x0 + k, W - 1)]));
+      }
+      tmp[i] = acc;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < OH * OW; i += blockDim.x) {
+      const int yo = i / OW, xo = i - yo * OW;
+      const int y0 = ry_start[yo];
+      float acc = 0.0f;
+      for (int k = 0; k < cp.max_taps; ++k) {
+        const float wgt = ry_w[yo * cp.max_taps + k];
+        if (wgt != 0.0f) acc = add_r(acc, mul_r(wgt, tmp[min(y0 + k, Hh - 1) * OW + xo]));
+      }
+      s_img[i] = acc;                  // the original image is dead: reuse its head for the final frame
+    }
+    __syncthreads();
+  }
+  // normalise (:56-69) and push into the ring buffer (:483-499)
+  const int opx = OW * OH;
+  const bool init = ep_len[e] <= 1;
+  const float range = sub_r(cp.far_clip, cp.near_clip);
+  float* buf = depth_buffer + (size_t)e * cp.buffer_len * opx;
+  for (int i = threadIdx.x; i < opx; i += blockDim.x) {
+    const float v = sub_r(div_r(sub_r(mul_r(src[i], -1.0f), cp.near_clip), range), 0.5f);
+    if (init) {
+      for (int k = 0; k < cp.buffer_len; ++k) buf[(size_t)k * opx + i] = v;
+    } else {
+      for (int k = 0; k + 1 < cp.buffer_len; ++k) buf[(size_t)k * opx + i] = buf[(size_t)(k + 1) * opx + i];
+      buf[(size_t)(cp.buffer_len - 1) * opx + i] = v;
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // host: binned-SAH binary build, collapse to 4-wide, upload
 // ---------------------------------------------------------------------------------------------
@@ -520,6 +635,50 @@ int elg_raycast_sensor(const ElgMesh* mesh, const float* pattern_origins, const 
       mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
       max_dist, ray_hits, hits_found);
   return elg::check_launch("elg_raycast_sensor");
+}
+
+int elg_sizeof_cam_params(void) { return (int)sizeof(ElgCamParams); }
+
+int elg_camera_pose(const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num, const float* offset_pos3,
+                    const float* offset_quat4, float* camera_pos, float* camera_rot, void* stream) {
+  if (num < 0) return mfail(ELG_ERR_INVALID_ARGUMENT, "num < 0");
+  if (num == 0) return ELG_OK;
+  if (!sensor_pos || !sensor_quat || !offset_pos3 || !offset_quat4 || !camera_pos || !camera_rot) return mfail(ELG_ERR_NULL_POINTER, "a camera pose buffer is NULL");
+  elg::elg_camera_pose_kernel<<<(unsigned)((num + 127) / 128), 128, 0, (cudaStream_t)stream>>>(
+      sensor_pos, sensor_quat, env_ids, num, offset_pos3[0], offset_pos3[1], offset_pos3[2], offset_quat4[0], offset_quat4[1], offset_quat4[2],
+      offset_quat4[3], camera_pos, camera_rot);
+  return elg::check_launch("elg_camera_pose");
+}
+
+int elg_depth_camera(const ElgMesh* mesh, const ElgCamParams* cam, const float* ray_directions, const float* camera_pos, const float* camera_rot,
+                     const int64_t* episode_length_buf, const float* noise_u, const int32_t* resize_x_start, const float* resize_x_weights,
+                     const int32_t* resize_y_start, const float* resize_y_weights, int64_t num_envs, float* depth_buffer, float* raw_depth,
+                     void* stream) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "No meshes available for ray casting");
+  if (!cam) return mfail(ELG_ERR_NULL_POINTER, "camera params is NULL");
+  if (cam->width < 1 || cam->height < 1 || cam->out_width < 1 || cam->out_height < 1 || cam->buffer_len < 1)
+    return mfail(ELG_ERR_INVALID_ARGUMENT, "image sizes and buffer_len must be >= 1");
+  if (!cam->resize && (cam->width != cam->out_width || cam->height != cam->out_height))
+    return mfail(ELG_ERR_INVALID_ARGUMENT, "original and resized image sizes differ but no resize tables were given");
+  if (cam->resize && (!resize_x_start || !resize_x_weights || !resize_y_start || !resize_y_weights || cam->max_taps < 1))
+    return mfail(ELG_ERR_NULL_POINTER, "resize needs the four tap tables");
+  if (!(cam->far_clip > cam->near_clip)) return mfail(ELG_ERR_INVALID_ARGUMENT, "far_clip must exceed near_clip");
+  if (num_envs < 0) return mfail(ELG_ERR_INVALID_ARGUMENT, "num_envs < 0");
+  if (num_envs == 0) return ELG_OK;
+  if (!ray_directions || !camera_pos || !camera_rot || !episode_length_buf || !depth_buffer) return mfail(ELG_ERR_NULL_POINTER, "a camera buffer is NULL");
+  const size_t in_px = (size_t)cam->width * cam->height, out_px = (size_t)cam->out_width * cam->out_height;
+  const size_t smem = 4 * ((in_px > out_px ? in_px : out_px) + (cam->resize ? (size_t)cam->height * cam->out_width : 0));
+  if (smem > 200 * 1024) return mfail(ELG_ERR_UNSUPPORTED, "image too large for the fused depth kernel (> 200 KB of shared memory)");
+  static size_t smem_set = 0;
+  if (smem > 48 * 1024 && smem > smem_set) {
+    if (cudaFuncSetAttribute(elg::elg_depth_camera_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+      return mfail(ELG_ERR_CUDA, "cannot reserve shared memory for elg_depth_camera_kernel");
+    smem_set = smem;
+  }
+  elg::elg_depth_camera_kernel<<<(unsigned)num_envs, 256, smem, (cudaStream_t)stream>>>(
+      mesh->nodes, mesh->tris, *cam, ray_directions, camera_pos, camera_rot, episode_length_buf, noise_u, resize_x_start, resize_x_weights,
+      resize_y_start, resize_y_weights, depth_buffer, raw_depth);
+  return elg::check_launch("elg_depth_camera");
 }
 
 }  // extern "C"

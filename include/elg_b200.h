@@ -290,6 +290,31 @@ int elg_raycast_sensor(const ElgMesh* mesh, const float* pattern_origins, const 
                        const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num_sensors, int yaw_only,
                        float max_dist, float* ray_hits, uint8_t* hits_found, void* stream);
 
+/* DepthCameraWarp (utils/depth_camera.py:256-571) + DepthCameraBase.process_depth_image (:84-138). */
+typedef struct ElgCamParams {
+  int32_t width, height;         /* cfg.depth.original */
+  int32_t out_width, out_height; /* cfg.depth.resized */
+  int32_t buffer_len;
+  int32_t resize;                /* 1: sizes differ, apply the separable tap tables (antialiased bicubic of torchvision's Resize) */
+  int32_t max_taps;              /* taps per output pixel in the tables */
+  float near_clip, far_clip;
+  float noise_scale;             /* fp32(cfg.depth.dis_noise * 2); 0 or noise_u == NULL: no noise */
+} ElgCamParams;
+int elg_sizeof_cam_params(void);
+/* DepthCameraWarp.update (:501-566): camera_pos = sensor_pos + quat_apply(sensor_quat, offset_pos); camera_rot =
+ * quat_mul(sensor_quat, offset_quat) with the reference's literal argument order.  offset_* are HOST pointers. */
+int elg_camera_pose(const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num, const float* offset_pos3,
+                    const float* offset_quat4, float* camera_pos, float* camera_rot, void* stream);
+/* DepthCameraWarp.update_depth_buffer (:402-499), one launch: cast the [height * width] ray grid of every camera with
+ * max_dist = far_clip, depth = -|hit - camera_pos| or -far_clip, + noise_scale * (noise_u[env] - 0.5), clip to
+ * [-far, -near], resize, normalise to [-0.5, 0.5], then init (episode_length_buf <= 1) or shift-append the env's ring
+ * buffer depth_buffer [num_envs, buffer_len, out_height, out_width].  raw_depth (optional) receives the unprocessed
+ * [num_envs, height, width] image.  resize_*_start [out], resize_*_weights [out, max_taps]. */
+int elg_depth_camera(const ElgMesh* mesh, const ElgCamParams* cam, const float* ray_directions, const float* camera_pos, const float* camera_rot,
+                     const int64_t* episode_length_buf, const float* noise_u, const int32_t* resize_x_start, const float* resize_x_weights,
+                     const int32_t* resize_y_start, const float* resize_y_weights, int64_t num_envs, float* depth_buffer, float* raw_depth,
+                     void* stream);
+
 /* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =
  * fp32(min(hs[i][j], hs[i+1][j], hs[i][j+1])) * vertical_scale for i <= rows-2, j <= cols-2 (0 elsewhere) -- the
  * value the reference computes per height point, tabulated once per (static) terrain so the step kernel gathers one
