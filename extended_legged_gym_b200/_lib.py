@@ -132,6 +132,9 @@ def load() -> C.CDLL:
     lib.elg_raycast_sensor.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, i64, C.c_int, C.c_float, vp, vp, vp]
     lib.elg_camera_pose.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.elg_depth_camera.argtypes = [vp, C.POINTER(ElgCamParams)] + [vp] * 9 + [i64, vp, vp, vp]
+    lib.elg_sdf_query.argtypes = [vp, vp, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp]
+    lib.elg_mesh_mean_edge.argtypes = [vp]
+    lib.elg_mesh_mean_edge.restype = C.c_double
     lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib
     return lib

@@ -340,6 +340,190 @@ elg_depth_camera_kernel(const float4* __restrict__ nodes, const float4* __restri
 }
 
 // ---------------------------------------------------------------------------------------------
+// signed distance: closest point on a triangle (Ericson, Real-Time Collision Detection 5.1.5) in fp64 with
+// individually rounded operations, same expression order as oracle/mesh_oracle.py
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double ddot(double ax, double ay, double az, double bx, double by, double bz) {
+  return dadd(dadd(dmul(ax, bx), dmul(ay, by)), dmul(az, bz));
+}
+struct Closest {
+  double cx, cy, cz;   // closest point
+  double d2;           // squared distance
+};
+__device__ __forceinline__ Closest closest_on_triangle(const double px, const double py, const double pz, const float4 A, const float4 Bv,
+                                                       const float4 Cv) {
+  const double ax = A.x, ay = A.y, az = A.z, bx = A.w, by = Bv.x, bz = Bv.y, cx = Bv.z, cy = Bv.w, cz = Cv.x;
+  const double abx = dsub(bx, ax), aby = dsub(by, ay), abz = dsub(bz, az);
+  const double acx = dsub(cx, ax), acy = dsub(cy, ay), acz = dsub(cz, az);
+  const double apx = dsub(px, ax), apy = dsub(py, ay), apz = dsub(pz, az);
+  const double d1 = ddot(abx, aby, abz, apx, apy, apz), d2 = ddot(acx, acy, acz, apx, apy, apz);
+  const double bpx = dsub(px, bx), bpy = dsub(py, by), bpz = dsub(pz, bz);
+  const double d3 = ddot(abx, aby, abz, bpx, bpy, bpz), d4 = ddot(acx, acy, acz, bpx, bpy, bpz);
+  const double cpx = dsub(px, cx), cpy = dsub(py, cy), cpz = dsub(pz, cz);
+  const double d5 = ddot(abx, aby, abz, cpx, cpy, cpz), d6 = ddot(acx, acy, acz, cpx, cpy, cpz);
+  const double vc = dsub(dmul(d1, d4), dmul(d3, d2));
+  const double vb = dsub(dmul(d5, d2), dmul(d1, d6));
+  const double va = dsub(dmul(d3, d6), dmul(d5, d4));
+  double qx, qy, qz;
+  if (d1 <= 0.0 && d2 <= 0.0) {                                   // vertex A
+    qx = ax; qy = ay; qz = az;
+  } else if (d3 >= 0.0 && d4 <= d3) {                             // vertex B
+    qx = bx; qy = by; qz = bz;
+  } else if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {               // edge AB
+    const double v = d1 / dsub(d1, d3);
+    qx = dadd(ax, dmul(v, abx)); qy = dadd(ay, dmul(v, aby)); qz = dadd(az, dmul(v, abz));
+  } else if (d6 >= 0.0 && d5 <= d6) {                             // vertex C
+    qx = cx; qy = cy; qz = cz;
+  } else if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {               // edge AC
+    const double w = d2 / dsub(d2, d6);
+    qx = dadd(ax, dmul(w, acx)); qy = dadd(ay, dmul(w, acy)); qz = dadd(az, dmul(w, acz));
+  } else if (va <= 0.0 && dsub(d4, d3) >= 0.0 && dsub(d5, d6) >= 0.0) {   // edge BC
+    const double w = dsub(d4, d3) / dadd(dsub(d4, d3), dsub(d5, d6));
+    qx = dadd(bx, dmul(w, dsub(cx, bx))); qy = dadd(by, dmul(w, dsub(cy, by))); qz = dadd(bz, dmul(w, dsub(cz, bz)));
+  } else {                                                        // interior
+    const double denom = 1.0 / dadd(dadd(va, vb), vc);
+    const double v = dmul(vb, denom), w = dmul(vc, denom);
+    qx = dadd(dadd(ax, dmul(abx, v)), dmul(acx, w));
+    qy = dadd(dadd(ay, dmul(aby, v)), dmul(acy, w));
+    qz = dadd(dadd(az, dmul(abz, v)), dmul(acz, w));
+  }
+  Closest r;
+  r.cx = qx; r.cy = qy; r.cz = qz;
+  const double ox = dsub(px, qx), oy = dsub(py, qy), oz = dsub(pz, qz);
+  r.d2 = ddot(ox, oy, oz, ox, oy, oz);
+  return r;
+}
+
+// Visits every triangle whose padded leaf box lies within sqrt(r2) of p, nearest boxes first.  F(tri float4 x3) may
+// shrink r2 (returns the new squared radius, or a negative value to keep it).
+template <typename F>
+__device__ __forceinline__ void visit_near(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float px, const float py,
+                                           const float pz, float r2, F&& f) {
+  int stack_c[kStack];
+  float stack_d[kStack];
+  int sp = 0;
+  stack_c[sp] = 0;
+  stack_d[sp++] = 0.0f;
+  while (sp > 0) {
+    --sp;
+    const int code = stack_c[sp];
+    if (stack_d[sp] > r2) continue;
+    if (code < 0) {
+      const int first = (~code) >> 2, count = ((~code) & 3) + 1;
+      for (int i = 0; i < count; ++i) {
+        const float4* tp = tris + 3 * (size_t)(first + i);
+        const float nr2 = f(__ldg(tp), __ldg(tp + 1), __ldg(tp + 2));
+        if (nr2 >= 0.0f) r2 = nr2;
+      }
+      continue;
+    }
+    const float4* np = nodes + 8 * (size_t)code;
+    const float4 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
+    const int4 ch = __ldg(reinterpret_cast<const int4*>(np + 6));
+    float dn[4];
+    int cc[4] = {ch.x, ch.y, ch.z, ch.w};
+    const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
+    const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float ex = fmaxf(fmaxf(lox[c] - px, px - hix[c]), 0.0f);
+      const float ey = fmaxf(fmaxf(loy[c] - py, py - hiy[c]), 0.0f);
+      const float ez = fmaxf(fmaxf(loz[c] - pz, pz - hiz[c]), 0.0f);
+      const float d = (ex * ex + ey * ey + ez * ez) * 0.999999f;     // lower bound of the squared distance to the box
+      dn[c] = (cc[c] != kEmpty && d <= r2) ? d : FLT_MAX;
+    }
+#define CSWAP(i, j)                                   \
+  if (dn[i] > dn[j]) {                                \
+    const float tt = dn[i]; dn[i] = dn[j]; dn[j] = tt; \
+    const int ct = cc[i]; cc[i] = cc[j]; cc[j] = ct;  \
+  }
+    CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
+#undef CSWAP
+#pragma unroll
+    for (int c = 3; c >= 0; --c)
+      if (dn[c] != FLT_MAX && sp < kStack) {
+        stack_c[sp] = cc[c];
+        stack_d[sp++] = dn[c];
+      }
+  }
+}
+
+// query_sdf_kernel (utils/mesh_sdf.py:38-116) on top of an order-independent statement of
+// wp.mesh_query_point_sign_normal: pass 1 finds the exact minimum distance d_min; pass 2 looks at every face within
+// d_min + epsilon * mean_edge and takes the one whose unit normal is most aligned with the offset (|n . (p - c)|
+// largest, lowest triangle id on ties) -- the face that decides the sign at edges and vertices.
+__global__ void __launch_bounds__(128)
+elg_sdf_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ points, const long long n,
+               const float max_distance, const double eps_abs, float* __restrict__ sdf, float* __restrict__ grad,
+               float* __restrict__ closest, int* __restrict__ face) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float pxf = points[3 * i], pyf = points[3 * i + 1], pzf = points[3 * i + 2];
+  const double px = pxf, py = pyf, pz = pzf;
+  const double D = (double)max_distance;
+  // pass 1: exact minimum squared distance
+  double best = dmul(D, D);
+  bool any = false;
+  visit_near(nodes, tris, pxf, pyf, pzf, __double2float_ru(best) * 1.000001f, [&](const float4 a, const float4 b, const float4 c) -> float {
+    const Closest q = closest_on_triangle(px, py, pz, a, b, c);
+    if (q.d2 <= best) {
+      best = q.d2;
+      any = true;
+      return __double2float_ru(best) * 1.000001f;
+    }
+    return -1.0f;
+  });
+  if (!any) {   // nothing within max_distance (mesh_sdf.py:112-115)
+    sdf[i] = max_distance;
+    grad[3 * i] = grad[3 * i + 1] = grad[3 * i + 2] = 0.0f;
+    if (closest) closest[3 * i] = closest[3 * i + 1] = closest[3 * i + 2] = 0.0f;
+    if (face) face[i] = -1;
+    return;
+  }
+  // pass 2: the deciding face among the near-ties
+  const double dmin = sqrt(best);
+  const double lim = dadd(dmin, eps_abs);
+  const double lim2 = dmul(lim, lim);
+  double score = -1.0, sdot = 0.0, bx = 0.0, by = 0.0, bz = 0.0, bd2 = 0.0, nx = 0.0, ny = 0.0, nz = 0.0;
+  int btri = 0x7fffffff;
+  visit_near(nodes, tris, pxf, pyf, pzf, __double2float_ru(lim2) * 1.000001f, [&](const float4 a, const float4 b, const float4 c) -> float {
+    const Closest q = closest_on_triangle(px, py, pz, a, b, c);
+    if (q.d2 <= lim2) {
+      const double e1x = dsub((double)a.w, (double)a.x), e1y = dsub((double)b.x, (double)a.y), e1z = dsub((double)b.y, (double)a.z);
+      const double e2x = dsub((double)b.z, (double)a.x), e2y = dsub((double)b.w, (double)a.y), e2z = dsub((double)c.x, (double)a.z);
+      const double fx = dsub(dmul(e1y, e2z), dmul(e1z, e2y)), fy = dsub(dmul(e1z, e2x), dmul(e1x, e2z)), fz = dsub(dmul(e1x, e2y), dmul(e1y, e2x));
+      const double fl = sqrt(ddot(fx, fy, fz, fx, fy, fz));
+      const double ox = dsub(px, q.cx), oy = dsub(py, q.cy), oz = dsub(pz, q.cz);
+      const double dt = ddot(fx, fy, fz, ox, oy, oz);
+      const double sc = fl > 0.0 ? fabs(dt) / fl : 0.0;
+      const int tri = __float_as_int(c.y);
+      if (sc > score || (sc == score && tri < btri)) {
+        score = sc; sdot = dt; btri = tri;
+        bx = q.cx; by = q.cy; bz = q.cz; bd2 = q.d2;
+        nx = fx; ny = fy; nz = fz;
+      }
+    }
+    return -1.0f;
+  });
+  const double dist = sqrt(bd2);
+  const double sign = sdot < 0.0 ? -1.0 : 1.0;
+  double gx, gy, gz;
+  if (dist > 1.0e-6) {       // offset direction, flipped inside (mesh_sdf.py:89-94)
+    gx = dsub(px, bx) / dist; gy = dsub(py, by) / dist; gz = dsub(pz, bz) / dist;
+  } else {                   // on the surface: the face normal (:95-107)
+    const double fl = sqrt(ddot(nx, ny, nz, nx, ny, nz));
+    const double il = fl > 0.0 ? 1.0 / fl : 0.0;
+    gx = dmul(nx, il); gy = dmul(ny, il); gz = dmul(nz, il);
+  }
+  sdf[i] = (float)dmul(dist, sign);
+  grad[3 * i] = (float)dmul(gx, sign);
+  grad[3 * i + 1] = (float)dmul(gy, sign);
+  grad[3 * i + 2] = (float)dmul(gz, sign);
+  if (closest) { closest[3 * i] = (float)bx; closest[3 * i + 1] = (float)by; closest[3 * i + 2] = (float)bz; }
+  if (face) face[i] = btri;
+}
+
+// ---------------------------------------------------------------------------------------------
 // host: binned-SAH binary build, collapse to 4-wide, upload
 // ---------------------------------------------------------------------------------------------
 struct Box {
@@ -680,5 +864,23 @@ int elg_depth_camera(const ElgMesh* mesh, const ElgCamParams* cam, const float* 
       resize_y_start, resize_y_weights, depth_buffer, raw_depth);
   return elg::check_launch("elg_depth_camera");
 }
+
+int elg_sdf_query(const ElgMesh* mesh, const float* points, int64_t num_points, float max_distance, float epsilon, float* sdf, float* grad,
+                  float* closest_points, int32_t* closest_face, void* stream) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "No meshes available for SDF queries");
+  if (num_points < 0) return mfail(ELG_ERR_INVALID_ARGUMENT, "num_points < 0");
+  if (num_points == 0) return ELG_OK;
+  if (!points || !sdf || !grad) return mfail(ELG_ERR_NULL_POINTER, "points/sdf/grad is NULL");
+  if (!(max_distance >= 0.0f) || !(epsilon >= 0.0f)) return mfail(ELG_ERR_INVALID_ARGUMENT, "max_distance and epsilon must be >= 0");
+  const int threads = 128;
+  const long long blocks = (num_points + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many points for one launch");
+  elg::elg_sdf_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(mesh->nodes, mesh->tris, points, num_points, max_distance,
+                                                                              (double)epsilon * mesh->avg_edge, sdf, grad, closest_points,
+                                                                              closest_face);
+  return elg::check_launch("elg_sdf_query");
+}
+
+double elg_mesh_mean_edge(const ElgMesh* mesh) { return mesh ? mesh->avg_edge : 0.0; }
 
 }  // extern "C"

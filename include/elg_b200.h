@@ -315,6 +315,16 @@ int elg_depth_camera(const ElgMesh* mesh, const ElgCamParams* cam, const float* 
                      const int32_t* resize_y_start, const float* resize_y_weights, int64_t num_envs, float* depth_buffer, float* raw_depth,
                      void* stream);
 
+/* MeshSDF.query + query_sdf_kernel (utils/mesh_sdf.py:38-116, :230-314): signed distance to the closest point of the mesh
+ * within max_distance and its unit gradient.  Sign and closest face follow wp.mesh_query_point_sign_normal restated
+ * order-independently: among the faces within d_min + epsilon * (mean edge length) of the point, the one whose unit normal
+ * is most aligned with the offset decides (lowest triangle id on ties); sign = sign(n . (p - c)).  gradient = (p - c) / d
+ * flipped inside, or the face normal when d <= 1e-6; nothing within max_distance: sdf = max_distance, gradient 0.
+ * closest_points [n,3] / closest_face [n] are optional (nearest_points without the second query of :316-336). */
+int elg_sdf_query(const ElgMesh* mesh, const float* points, int64_t num_points, float max_distance, float epsilon, float* sdf, float* grad,
+                  float* closest_points, int32_t* closest_face, void* stream);
+double elg_mesh_mean_edge(const ElgMesh* mesh);
+
 /* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =
  * fp32(min(hs[i][j], hs[i+1][j], hs[i][j+1])) * vertical_scale for i <= rows-2, j <= cols-2 (0 elsewhere) -- the
  * value the reference computes per height point, tabulated once per (static) terrain so the step kernel gathers one

@@ -106,8 +106,9 @@ def box_mesh(lo=(-1.0, -1.0, 1.0), hi=(1.0, 1.0, 2.0)):
     x0, y0, z0 = lo
     x1, y1, z1 = hi
     v = np.array([[x0, y0, z0], [x1, y0, z0], [x1, y1, z0], [x0, y1, z0], [x0, y0, z1], [x1, y0, z1], [x1, y1, z1], [x0, y1, z1]], np.float32)
-    t = np.array([[0, 1, 2], [0, 2, 3], [4, 6, 5], [4, 7, 6], [0, 5, 1], [0, 4, 5], [1, 6, 2], [1, 5, 6], [2, 7, 3], [2, 6, 7],
-                  [3, 4, 0], [3, 7, 4]], np.int32)
+    # outward-facing winding: bottom, top, front (y0), right (x1), back (y1), left (x0)
+    t = np.array([[0, 2, 1], [0, 3, 2], [4, 5, 6], [4, 6, 7], [0, 1, 5], [0, 5, 4], [1, 2, 6], [1, 6, 5], [2, 3, 7], [2, 7, 6],
+                  [3, 0, 4], [3, 4, 7]], np.int32)
     return v, t
 
 
@@ -147,3 +148,82 @@ def icosphere(subdivisions=2, radius=1.0):
             nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
         f = nf
     return (np.array(v) * radius).astype(np.float32), np.array(f, np.int32)
+
+
+# ----------------------------------------------------------------------------------------------
+# signed distance (utils/mesh_sdf.py:38-116 on top of wp.mesh_query_point_sign_normal) -- PARITY UNPINNED
+# ----------------------------------------------------------------------------------------------
+def _dot(a, b):
+    return (a[..., 0] * b[..., 0] + a[..., 1] * b[..., 1]) + a[..., 2] * b[..., 2]
+
+
+def closest_on_triangles(p, a, b, c):
+    """Ericson 5.1.5, vectorised: p [R,1,3], a/b/c [1,M,3] float64 -> closest points [R,M,3], squared distances [R,M]."""
+    ab, ac, ap = b - a, c - a, p - a
+    d1, d2 = _dot(ab, ap), _dot(ac, ap)
+    bp = p - b
+    d3, d4 = _dot(ab, bp), _dot(ac, bp)
+    cp = p - c
+    d5, d6 = _dot(ab, cp), _dot(ac, cp)
+    vc = d1 * d4 - d3 * d2
+    vb = d5 * d2 - d1 * d6
+    va = d3 * d6 - d5 * d4
+    with np.errstate(divide="ignore", invalid="ignore"):
+        v_ab = (d1 / (d1 - d3))[..., None]
+        w_ac = (d2 / (d2 - d6))[..., None]
+        w_bc = ((d4 - d3) / ((d4 - d3) + (d5 - d6)))[..., None]
+        denom = 1.0 / ((va + vb) + vc)
+    v_in, w_in = (vb * denom)[..., None], (vc * denom)[..., None]
+    conds = [(d1 <= 0) & (d2 <= 0), (d3 >= 0) & (d4 <= d3), (vc <= 0) & (d1 >= 0) & (d3 <= 0), (d6 >= 0) & (d5 <= d6),
+             (vb <= 0) & (d2 >= 0) & (d6 <= 0), (va <= 0) & ((d4 - d3) >= 0) & ((d5 - d6) >= 0)]
+    cands = [a + 0 * p, b + 0 * p, a + v_ab * ab, c + 0 * p, a + w_ac * ac, b + w_bc * (c - b)]
+    q = (a + ab * v_in) + ac * w_in
+    for cond, cand in zip(reversed(conds), reversed(cands)):       # the first matching region wins
+        q = np.where(cond[..., None], cand, q)
+    off = p - q
+    return q, _dot(off, off)
+
+
+def sdf_query(points, max_distance, vertices, triangles, epsilon=1.0e-3, chunk=128):
+    """Returns sdf [R] f32, grad [R,3] f32, closest [R,3] f32, face [R] (-1: nothing within max_distance)."""
+    P = np.ascontiguousarray(points, dtype=np.float32).reshape(-1, 3).astype(np.float64)
+    V = np.asarray(vertices, dtype=np.float32).astype(np.float64)
+    T = np.asarray(triangles).astype(np.int64)
+    a, b, c = V[T[:, 0]][None], V[T[:, 1]][None], V[T[:, 2]][None]
+    e1, e2 = (b - a)[0], (c - a)[0]
+    fn = np.stack([e1[:, 1] * e2[:, 2] - e1[:, 2] * e2[:, 1], e1[:, 2] * e2[:, 0] - e1[:, 0] * e2[:, 2],
+                   e1[:, 0] * e2[:, 1] - e1[:, 1] * e2[:, 0]], axis=1)
+    fl = np.sqrt(_dot(fn, fn))
+    edges = np.concatenate([np.linalg.norm((b - a)[0], axis=1), np.linalg.norm((c - b)[0], axis=1), np.linalg.norm((a - c)[0], axis=1)])
+    eps_abs = np.float64(np.float32(epsilon)) * (edges.reshape(3, -1).T.sum() / (3.0 * len(T)))
+    D = np.float64(np.float32(max_distance))
+    R = P.shape[0]
+    sdf = np.empty(R, np.float32)
+    grad = np.zeros((R, 3), np.float32)
+    closest = np.zeros((R, 3), np.float32)
+    face = np.full(R, -1, np.int64)
+    for s in range(0, R, chunk):
+        p = P[s:s + chunk, None, :]
+        q, d2 = closest_on_triangles(p, a, b, c)
+        best = np.minimum(d2.min(axis=1), D * D)
+        hit = d2.min(axis=1) <= D * D
+        lim = np.sqrt(best) + eps_abs
+        cand = d2 <= (lim * lim)[:, None]
+        off = p - q
+        dt = _dot(fn[None], off)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            score = np.where(fl[None] > 0, np.abs(dt) / fl[None], 0.0)
+        score = np.where(cand, score, -1.0)
+        k = np.argmax(score, axis=1)                                 # first maximum = lowest triangle id
+        ar = np.arange(len(k))
+        dist = np.sqrt(d2[ar, k])
+        sign = np.where(dt[ar, k] < 0, -1.0, 1.0)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            g_off = off[ar, k] / dist[:, None]
+            g_n = fn[k] * np.where(fl[k] > 0, 1.0 / fl[k], 0.0)[:, None]
+        g = np.where((dist > 1.0e-6)[:, None], g_off, g_n)
+        sdf[s:s + chunk] = np.where(hit, (dist * sign), D).astype(np.float32)
+        grad[s:s + chunk] = np.where(hit[:, None], g * sign[:, None], 0.0).astype(np.float32)
+        closest[s:s + chunk] = np.where(hit[:, None], q[ar, k], 0.0).astype(np.float32)
+        face[s:s + chunk] = np.where(hit, k, -1)
+    return sdf, grad, closest, face
