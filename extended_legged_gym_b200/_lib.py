@@ -135,6 +135,9 @@ def load() -> C.CDLL:
     lib.elg_sdf_query.argtypes = [vp, vp, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp]
     lib.elg_mesh_mean_edge.argtypes = [vp]
     lib.elg_mesh_mean_edge.restype = C.c_double
+    lib.elg_mppi_costs.argtypes = [vp, i64, i64, C.c_int32, vp, vp]
+    lib.elg_mppi_partials.argtypes = [vp, i64, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_float, vp, vp]
+    lib.elg_mppi_finish.argtypes = [vp, i64, C.c_int32, vp, vp]
     lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib
     return lib

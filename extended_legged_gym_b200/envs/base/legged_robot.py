@@ -182,6 +182,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         self.gait_idx = None
         self.gait_prev_foot_z = None
         self.extra_reward = None
+        self.episode_stats = None                 # utils.distributed.ShardedEpisodeStats when envs are sharded over GPUs
         self.noise_u = None                       # set to a [N,O] tensor of U[0,1) for torch.rand_like-parity noise
         self.noise_seed = int(getattr(cfg, "seed", 0) or 0) + 0x5EED
         self._noise_step = 0
@@ -614,6 +615,8 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         self.feet_contact_time[env_ids] = 0.0
         self.episode_length_buf[env_ids] = 0
         self.reset_buf[env_ids] = 1
+        if getattr(self, "episode_stats", None) is not None:    # sharded envs: (sum, count) now, all-reduce later (utils/distributed.py)
+            self.episode_stats.accumulate(self.episode_sums, env_ids, self.terrain_levels if self.cfg.terrain.curriculum else None)
         self.extras["episode"] = {}
         for key in self.episode_sums.keys():
             self.extras["episode"]["rew_" + key] = torch.mean(self.episode_sums[key][env_ids]) / self.max_episode_length_s

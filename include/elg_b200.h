@@ -325,6 +325,17 @@ int elg_sdf_query(const ElgMesh* mesh, const float* points, int64_t num_points, 
                   float* closest_points, int32_t* closest_face, void* stream);
 double elg_mesh_mean_edge(const ElgMesh* mesh);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * MPPI cost-weighted control update, batched over the main envs (in-tree statement: legged_gym/tests/score_sampling/
+ * cmp_mppi_wbfo.py:216-233; the production optimiser is the external traj_sampling package, call sites
+ * envs/batch_rollout/robot_traj_grad_sampling.py:62-69, :222-280).  Split in three so that the sample dimension can be
+ * sharded across GPUs: costs are all-gathered, partial sums all-reduced (host side: utils/mppi.py). */
+int elg_mppi_costs(const float* rewards /*[M,S,T]*/, int64_t num_main, int64_t num_samples, int32_t horizon, float* costs /*[M,S]*/, void* stream);
+int elg_mppi_partials(const float* costs_all /*[M,S_total]*/, int64_t num_main, int32_t samples_total, int32_t first_local_sample,
+                      int32_t samples_local, const float* samples /*[M,S_local,traj_size]*/, int32_t traj_size, float temperature,
+                      float* partial /*[M, 1 + traj_size]: sum_e, sum_e * sample*/, void* stream);
+int elg_mppi_finish(const float* partial, int64_t num_main, int32_t traj_size, float* mean_traj /*[M,traj_size]*/, void* stream);
+
 /* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =
  * fp32(min(hs[i][j], hs[i+1][j], hs[i][j+1])) * vertical_scale for i <= rows-2, j <= cols-2 (0 elsewhere) -- the
  * value the reference computes per height point, tabulated once per (static) terrain so the step kernel gathers one
