@@ -166,6 +166,99 @@ def build_replicas(case, common, n_envs, n_rep, dev):
     return envs
 
 
+# ----------------------------------------------------------------------------------------------
+def secondary_benchmarks(dev, world, rank, dist, quick=False):
+    """The other kernels of the path at the BASELINE configs 4 and 5 (reported next to the headline, not in `value`):
+    depth-camera ray casting (Mrays/s), the main -> rollout clone, the MPPI update (+ its collectives when N > 1)."""
+    import numpy as np
+    from types import SimpleNamespace
+    from extended_legged_gym_b200 import synthetic
+    from extended_legged_gym_b200.utils.depth_camera import DepthCameraWarp
+    from extended_legged_gym_b200.utils.mppi import mppi_update
+    from extended_legged_gym_b200.utils.ray_caster import raycast_mesh
+    out = {}
+
+    def timed(fn, reps, warm=3):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / reps
+
+    # ---- config 4: 1024 cameras x 64 x 48 rays on the default terrain mesh (900 x 900 samples -> 1 616 402 triangles)
+    t0 = time.perf_counter()
+    hf = synthetic.make_height_field(seed=0)
+    v, t = synthetic.heightfield_to_trimesh(hf)
+    n_cam = 1024 // world if world > 1 else 1024
+    g = torch.Generator().manual_seed(100 + rank)
+    pos = torch.stack([torch.rand(n_cam, generator=g) * 36 + 2, torch.rand(n_cam, generator=g) * 36 + 2, torch.zeros(n_cam)], dim=1)
+    ix = ((pos[:, 0] + 25.0) / 0.1).long().clamp(0, 898)
+    iy = ((pos[:, 1] + 25.0) / 0.1).long().clamp(0, 898)
+    pos[:, 2] = hf[ix, iy].float() * 0.005 + 0.55
+    yaw = torch.rand(n_cam, generator=g) * 6.2832
+    quat = torch.stack([torch.randn(n_cam, generator=g) * 0.03, torch.randn(n_cam, generator=g) * 0.03, torch.sin(yaw / 2), torch.cos(yaw / 2)], dim=1)
+    quat = quat / quat.norm(dim=1, keepdim=True)
+    ep = torch.full((n_cam,), 5, dtype=torch.int64, device=dev)
+    depth = {}
+    cam = None
+    for far in (2.0, 10.0):
+        cfg = SimpleNamespace(camera_type="Warp", original=(64, 48), resized=(64, 48), horizontal_fov=100, buffer_len=2, near_clip=0.0,
+                              far_clip=far, dis_noise=0.0, position=[0.5, 0, 0.03], angle=[30, 30])
+        if cam is None:
+            cam = DepthCameraWarp(cfg, dev, n_cam, v, t)
+            build_s = time.perf_counter() - t0
+        else:
+            mesh = cam.meshes
+            cam = DepthCameraWarp(cfg, dev, n_cam, None, None)
+            cam.meshes = mesh
+        cam.update(0.02, pos.to(dev), quat.to(dev))
+        cam.raw_depth = torch.zeros(n_cam, 48, 64, device=dev)
+        sec = timed(lambda: cam.update_depth_buffer(None, ep), 3 if quick else 10)
+        rays = n_cam * 64 * 48
+        hit = float((cam.raw_depth > -far).float().mean())
+        cam.raw_depth = None
+        depth[f"far_clip_{int(far)}m"] = {"value": rays / sec / 1e6, "unit": "Mrays/s", "ms_per_frame_batch": sec * 1e3, "hit_fraction": hit}
+    # API-level cast of the same rays (24 B in, 13 B out per ray; what raycast_mesh callers see)
+    d = cam.ray_directions[:, :].reshape(-1, 3)
+    o = cam.camera_pos.unsqueeze(1).expand(-1, 64 * 48, -1).reshape(-1, 3).contiguous()
+    dirs = torch.nn.functional.normalize(torch.randn(o.shape[0], 3, device=dev) * torch.tensor([1.0, 1.0, 0.3], device=dev) -
+                                         torch.tensor([0.0, 0.0, 0.5], device=dev), dim=1)
+    sec = timed(lambda: raycast_mesh(o, dirs, 10.0, cam.meshes["terrain"]), 3 if quick else 10)
+    out["depth_raycast"] = {"workload": f"{n_cam} cameras x 64x48 rays per GPU, default terrain mesh ({len(t)} triangles), fused depth kernel",
+                            "cameras_per_gpu": n_cam, "rays_per_camera": 64 * 48, "triangles": int(len(t)), "bvh_build_s": build_s, **depth,
+                            "raycast_mesh_incoherent_10m": {"value": o.shape[0] / sec / 1e6, "unit": "Mrays/s"}}
+    del cam
+
+    # ---- config 5: 64 mains x 512 rollouts: state clone, then the cost-weighted update over a 20-step horizon
+    import common
+    from extended_legged_gym_b200.envs import RobotBatchRollout
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    mains, rollouts = 64, 512 // world if world > 1 else 512
+    n = mains * (1 + rollouts)
+    cfg, spec, st = common.make_case_state("anymal_c_rough", n, seed=3)
+    cfg.env.num_envs, cfg.env.rollout_envs = mains, rollouts
+    env = RobotBatchRollout(cfg, None, SyntheticSim(cfg, n, dev, spec=spec, height_samples=hf, state=st), dev, True)
+    env.set_env_state(st)
+    sec = timed(env._sync_main_to_rollout, 20 if quick else 200)
+    row = 4 * (13 + 24 + 12 * 3 + 6 + 9 + 8) + 4
+    peak, _ = peaks()
+    out["clone"] = {"workload": f"{mains} mains x {rollouts} rollouts per GPU, _sync_main_to_rollout", "us_per_sync": sec * 1e6,
+                    "bytes_written": row * mains * rollouts, "achieved_gbs": row * mains * rollouts / sec / 1e9,
+                    "frac_of_hbm_peak": row * mains * rollouts / sec / 1e9 / peak, "note": "12.7 MB working set is L2 resident"}
+    K, D, T = 5, 12, 20
+    r = torch.randn(mains, rollouts, T, device=dev)
+    u = torch.randn(mains, rollouts, K, D, device=dev)
+    sec = timed(lambda: mppi_update(r, u, 0.05), 20 if quick else 100)
+    out["mppi_update"] = {"workload": f"{mains} mains x {rollouts * world} samples (x{world} ranks) x horizon {T}, {K} nodes x {D} dof",
+                          "us_per_update": sec * 1e6, "collectives": "all_gather(costs) + all_reduce(partials)" if world > 1 else "none (1 rank)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -176,6 +269,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the depth / clone / MPPI measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -330,6 +424,13 @@ def main():
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": clk.summary(),
     }
+    if not args.no_secondary:
+        del envs, probe, env
+        torch.cuda.empty_cache()
+        sec = secondary_benchmarks(dev, world, rank, dist, quick=args.steps < 200)
+        if dist:      # max over ranks of every timing-derived figure is overkill here: report rank 0's, name it so
+            sec["note"] = "per-GPU figures measured on rank 0 (each rank runs its own share: cameras / rollouts split over ranks)"
+        line["secondary"] = sec
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         v, med, tot = cpu_reference_run(case, common, n_envs, 20, 3, threads)

@@ -104,7 +104,7 @@ class RobotBatchRollout(LeggedRobot):
     def _sync_main_to_rollout(self):
         if self.num_rollout_per_main == 0:
             return
-        self._clone(_lib.CLONE_SYNC, SYNC_FIELDS, drift=self.cfg.domain_rand.rollout_envs_sync_pos_drift)
+        self._clone(_lib.CLONE_SYNC, SYNC_FIELDS, drift=getattr(self.cfg.domain_rand, "rollout_envs_sync_pos_drift", 0.0))
         self.sim.set_dof_state()
         self.sim.set_root_state()
         self.t_rollout = self.t_main

@@ -150,3 +150,22 @@ def make_state(num_envs: int, num_dof: int, num_bodies: int, feet_indices, penal
 
 def clone_state(st: Dict[str, torch.Tensor], device=None) -> Dict[str, torch.Tensor]:
     return {k: (v.clone() if device is None else v.to(device).clone()) for k, v in st.items()}
+
+
+def heightfield_to_trimesh(height_samples, horizontal_scale: float = 0.1, vertical_scale: float = 0.005, border_size: float = 25.0):
+    """Triangle mesh of an int16 height field with the vertex / triangle layout of
+    ``isaacgym.terrain_utils.convert_heightfield_to_trimesh`` without slope correction (what ``Terrain`` hands to
+    ``gym.add_triangle_mesh``, legged_gym/legged_gym/utils/terrain.py:76-80): vertex (i, j) at
+    (i * hscale - border, j * hscale - border, h * vscale), two triangles per cell -> 900 x 900 samples give
+    810 000 vertices and 1 616 402 triangles."""
+    hf = np.asarray(height_samples.cpu() if torch.is_tensor(height_samples) else height_samples)
+    rows, cols = hf.shape
+    ii, jj = np.meshgrid(np.arange(rows, dtype=np.float32), np.arange(cols, dtype=np.float32), indexing="ij")
+    v = np.stack([ii * np.float32(horizontal_scale) - np.float32(border_size), jj * np.float32(horizontal_scale) - np.float32(border_size),
+                  hf.astype(np.float32) * np.float32(vertical_scale)], axis=-1).reshape(-1, 3).astype(np.float32)
+    idx = np.arange(rows * cols, dtype=np.int32).reshape(rows, cols)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel()
+    t = np.empty((2 * (rows - 1) * (cols - 1), 3), dtype=np.int32)
+    t[0::2] = np.stack([a, d, c], axis=1)
+    t[1::2] = np.stack([a, b, d], axis=1)
+    return v, t
