@@ -87,6 +87,25 @@ class ElgCamParams(C.Structure):
                 ("resize", C.c_int32), ("max_taps", C.c_int32), ("near_clip", C.c_float), ("far_clip", C.c_float), ("noise_scale", C.c_float)]
 
 
+RESET_UNIFORMS = 48
+
+
+class ElgResetParams(C.Structure):
+    _fields_ = [("lin_vel_x", C.c_float * 2), ("lin_vel_y", C.c_float * 2), ("ang_vel_yaw", C.c_float * 2), ("heading", C.c_float * 2),
+                ("heading_command", C.c_int32), ("resample_interval", C.c_int32), ("base_init_state", C.c_float * 13),
+                ("custom_origins", C.c_int32), ("curriculum", C.c_int32), ("env_length_half", C.c_float), ("max_episode_length_s", C.c_float),
+                ("max_terrain_level", C.c_int32), ("terrain_cols", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64)]
+
+
+_RESET_FIELDS = ["reset_buf", "root_states", "dof_state", "commands", "env_origins", "terrain_levels", "terrain_types", "terrain_origins",
+                 "default_dof_pos", "last_dof_vel", "last_root_vel", "feet_air_time", "feet_contact_time", "episode_length_buf", "episode_sums",
+                 "stats", "obs_buf", "measured_heights", "noise_scale_vec", "noise_u", "uniforms"]
+
+
+class ElgResetBuffers(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in _RESET_FIELDS]
+
+
 class ElgError(RuntimeError):
     pass
 
@@ -111,7 +130,8 @@ def load() -> C.CDLL:
     lib.elg_reward_term_name.restype = C.c_char_p
     lib.elg_reward_term_name.argtypes = [C.c_int]
     for fn, st in (("elg_sizeof_dims", ElgDims), ("elg_sizeof_step_params", ElgStepParams), ("elg_sizeof_step_buffers", ElgStepBuffers),
-                   ("elg_sizeof_clone_table", ElgCloneTable), ("elg_sizeof_cam_params", ElgCamParams)):
+                   ("elg_sizeof_clone_table", ElgCloneTable), ("elg_sizeof_cam_params", ElgCamParams), ("elg_sizeof_reset_params", ElgResetParams),
+                   ("elg_sizeof_reset_buffers", ElgResetBuffers)):
         got = getattr(lib, fn)()
         if got != C.sizeof(st):
             raise ElgError(f"ABI mismatch: {fn}() = {got}, python mirror = {C.sizeof(st)}")
@@ -138,6 +158,8 @@ def load() -> C.CDLL:
     lib.elg_mppi_costs.argtypes = [vp, i64, i64, C.c_int32, vp, vp]
     lib.elg_mppi_partials.argtypes = [vp, i64, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_float, vp, vp]
     lib.elg_mppi_finish.argtypes = [vp, i64, C.c_int32, vp, vp]
+    lib.elg_resample_commands.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgResetParams), vp, vp, vp, vp]
+    lib.elg_reset_envs.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgResetParams), C.POINTER(ElgStepParams), C.POINTER(ElgResetBuffers), vp]
     lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib
     return lib

@@ -47,49 +47,58 @@ elg_clone_sync_kernel(const __grid_constant__ ElgCloneTable tb, const float drif
     const uint32_t* row = s_row + w0;
     w0 += rw;
     uint32_t* dst = static_cast<uint32_t*>(tb.fields[f].base) + (main_row + 1) * rw;   // span of R * rw words
-    const long long span = (long long)R * rw;
+    const int span = R * rw;                                                            // < 2^31 (checked by the host)
     const bool drifting = (f == tb.drift_field) && drift > 0.0f;
     // words up to the first 16-byte boundary, vectors, tail
-    long long headw = ((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2;
+    int headw = (int)(((16 - (reinterpret_cast<uintptr_t>(dst) & 15)) & 15) >> 2);
     if (headw > span) headw = span;
-    const long long nvec = (span - headw) >> 2;
-    const long long tailw = span - headw - 4 * nvec;
-    auto value = [&](long long w, int m) -> uint32_t {   // word w of the span, m == w % rw
-      uint32_t v = row[m];
-      if (drifting && m < 3) {
-        const long long r = w / rw;                      // rollout number within this main
-        const long long gi = ((long long)k * R + r) * 3 + m;
-        float u;
-        if (drift_u) {
-          u = drift_u[gi];
-        } else {
-          const uint4 b = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
-                                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-          u = u01(b.x);
-        }
-        v = __float_as_uint(add_r(__uint_as_float(v), mul_r(sub_r(u, 0.5f), drift)));
+    const int nvec = (span - headw) >> 2;
+    const int tailw = span - headw - 4 * nvec;
+    auto drifted = [&](int w, int m, uint32_t v) -> uint32_t {   // word w of the span, m == w % rw < 3: base position + drift
+      const long long gi = ((long long)k * R + w / rw) * 3 + m;
+      float u;
+      if (drift_u) {
+        u = drift_u[gi];
+      } else {
+        const uint4 b = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+        u = u01(b.x);
       }
-      return v;
+      return __float_as_uint(add_r(__uint_as_float(v), mul_r(sub_r(u, 0.5f), drift)));
     };
-    // this CTA's slice of the vectors
-    const long long per = (nvec + gridDim.x - 1) / gridDim.x;
-    const long long v_lo = (long long)blockIdx.x * per, v_hi = min(nvec, v_lo + per);
+    // this CTA's slice of the vectors; the source index advances modulo the row length without divisions
+    const int per = (nvec + gridDim.x - 1) / gridDim.x;
+    const int v_lo = blockIdx.x * per, v_hi = min(nvec, v_lo + per);
     uint4* dv = reinterpret_cast<uint4*>(dst + headw);
-    for (long long v = v_lo + tid; v < v_hi; v += kCloneThreads) {
-      const long long w = headw + 4 * v;
-      int m = (int)(w % rw);
-      uint4 o;
-      o.x = value(w, m);     m = (m + 1 == rw) ? 0 : m + 1;
-      o.y = value(w + 1, m); m = (m + 1 == rw) ? 0 : m + 1;
-      o.z = value(w + 2, m); m = (m + 1 == rw) ? 0 : m + 1;
-      o.w = value(w + 3, m);
+    int v = v_lo + tid;
+    int m = (headw + 4 * v) % rw;
+    const int step = (4 * kCloneThreads) % rw;
+    for (; v < v_hi; v += kCloneThreads) {
+      int m1 = m + 1; m1 = m1 >= rw ? m1 - rw : m1;
+      int m2 = m1 + 1; m2 = m2 >= rw ? m2 - rw : m2;
+      int m3 = m2 + 1; m3 = m3 >= rw ? m3 - rw : m3;
+      uint4 o = make_uint4(row[m], row[m1], row[m2], row[m3]);
+      if (drifting) {
+        const int w = headw + 4 * v;
+        if (m < 3) o.x = drifted(w, m, o.x);
+        if (m1 < 3) o.y = drifted(w + 1, m1, o.y);
+        if (m2 < 3) o.z = drifted(w + 2, m2, o.z);
+        if (m3 < 3) o.w = drifted(w + 3, m3, o.w);
+      }
       dv[v] = o;
+      m += step;
+      m = m >= rw ? m - rw : m;
     }
     if (blockIdx.x == 0) {
-      if (tid < headw) dst[tid] = value(tid, (int)(tid % rw));
+      if (tid < headw) {
+        const int mm = tid % rw;
+        const uint32_t val = row[mm];
+        dst[tid] = (drifting && mm < 3) ? drifted(tid, mm, val) : val;
+      }
       if (tid < tailw) {
-        const long long w = headw + 4 * nvec + tid;
-        dst[w] = value(w, (int)(w % rw));
+        const int w = headw + 4 * nvec + tid, mm = w % rw;
+        const uint32_t val = row[mm];
+        dst[w] = (drifting && mm < 3) ? drifted(w, mm, val) : val;
       }
     }
   }
@@ -199,14 +208,15 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
     if (table->rollouts_per_main == 0) return ELG_OK;   // no rollout envs (robot_batch_rollout.py:1452-1453)
     const int sms = elg::sm_count();
     if (sms <= 0) return cfail(ELG_ERR_CUDA, "cannot query the SM count");
-    // enough CTAs for 4 per SM, but no more slices than 4 KB pieces of the largest span
-    long long slices = (4LL * sms + table->num_main - 1) / table->num_main;
+    // enough CTAs for 2 per SM, but no more slices than 4 KB pieces of the largest span
+    long long slices = (2LL * sms + table->num_main - 1) / table->num_main;
     long long biggest = 0;
     for (int f = 0; f < table->num_fields; ++f) biggest = biggest > table->fields[f].row_bytes ? biggest : table->fields[f].row_bytes;
     const long long cap = ((long long)table->rollouts_per_main * biggest + 4095) / 4096;
     if (slices > cap) slices = cap;
     if (slices < 1) slices = 1;
     if (table->num_main > 65535) return cfail(ELG_ERR_UNSUPPORTED, "more than 65535 main envs");
+    if ((long long)table->rollouts_per_main * biggest / 4 > 0x7fffffffLL / 8) return cfail(ELG_ERR_UNSUPPORTED, "rollouts_per_main * row size too large");
     const dim3 grid((unsigned)slices, (unsigned)table->num_main);
     if (words && staged <= elg::kCloneMaxRowWords)
       elg::elg_clone_sync_kernel<<<grid, elg::kCloneThreads, 0, st>>>(*table, drift, drift_u, seed, offset);

@@ -1,0 +1,223 @@
+// elg_reset.cu -- the sparse, RNG-driven branches of the step as kernels over ALL envs with a per-env predicate,
+// so that a step needs no `nonzero()` and no host synchronisation:
+//
+//   elg_resample_commands   LeggedRobot._post_physics_step_callback's resampling (envs/base/legged_robot.py:389-393)
+//                           + _resample_commands (:405-423) for the envs whose episode clock hits the interval
+//   elg_reset_envs          LeggedRobot.reset_idx (:162-213): _update_terrain_curriculum (:498-518), _reset_dofs
+//                           (:450-465), _reset_root_states (:467-487), _resample_commands, history / timer zeroing,
+//                           the sums behind extras["episode"] (as (sum, count) atomics), and the repair of the
+//                           observation entries that change when an env resets between rewards and observations
+//                           (commands, dof_pos, dof_vel; base velocities and heights stay stale -- App. A-4).
+//
+// Uniform numbers: column c of a per-env table [N, ELG_RESET_UNIFORMS] supplied by the caller (parity tests feed the host
+// path and the kernel the same numbers), or Philox4x32-10 keyed by (seed ^ stream tag) with counter (env, c / 4, step).
+// Column layout: [0, D) dof scale | D, D+1 root xy | D+2 .. D+7 root velocity | D+8 cmd x | D+9 cmd y | D+10 heading or yaw |
+// D+11 terrain level redraw.  torch_rand_float(lo, hi) = (hi - lo) * u + lo with one rounding per op.
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "elg_common.cuh"
+
+namespace elg {
+
+constexpr uint32_t kResetStream = 0x52455345u;   // "RESE": keeps these draws apart from the observation noise stream
+
+struct Uniforms {
+  const float* table;   // [N, ELG_RESET_UNIFORMS] or NULL
+  uint64_t seed, offset;
+  uint32_t env;
+  uint4 blk;
+  int blk_id;
+  __device__ float get(int c) {
+    if (table) return table[(size_t)env * ELG_RESET_UNIFORMS + c];
+    const int b = c >> 2;
+    if (b != blk_id) {
+      blk = philox4x32_10(make_uint4(env, (uint32_t)b, (uint32_t)offset, (uint32_t)(offset >> 32)),
+                          make_uint2((uint32_t)seed ^ kResetStream, (uint32_t)(seed >> 32)));
+      blk_id = b;
+    }
+    const int w = c & 3;
+    return u01(w == 0 ? blk.x : w == 1 ? blk.y : w == 2 ? blk.z : blk.w);
+  }
+};
+__device__ __forceinline__ float rand_range(float lo, float hi, float u) { return add_r(mul_r(sub_r(hi, lo), u), lo); }
+
+// _resample_commands (:405-423) for one env; returns the new (cmd0, cmd1) after the small-command zeroing
+__device__ __forceinline__ void resample_one(const ElgResetParams& rp, float* cmd, Uniforms& U, int D) {
+  float c0 = rand_range(rp.lin_vel_x[0], rp.lin_vel_x[1], U.get(D + 8));
+  float c1 = rand_range(rp.lin_vel_y[0], rp.lin_vel_y[1], U.get(D + 9));
+  if (rp.heading_command) cmd[3] = rand_range(rp.heading[0], rp.heading[1], U.get(D + 10));
+  else cmd[2] = rand_range(rp.ang_vel_yaw[0], rp.ang_vel_yaw[1], U.get(D + 10));
+  const float keep = norm2_t(c0, c1) > 0.2f ? 1.0f : 0.0f;
+  cmd[0] = mul_r(c0, keep);
+  cmd[1] = mul_r(c1, keep);
+}
+
+__global__ void __launch_bounds__(128)
+elg_resample_kernel(const __grid_constant__ ElgResetParams rp, const int N, const int D, const int C, const int64_t* __restrict__ ep_len,
+                    float* __restrict__ commands, const float* __restrict__ uniforms) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= N) return;
+  if ((ep_len[e] + 1) % rp.resample_interval != 0) return;   // the step kernel increments the clock afterwards (:122, :391)
+  Uniforms U{uniforms, rp.seed, rp.offset * 2, (uint32_t)e, make_uint4(0, 0, 0, 0), -1};
+  resample_one(rp, commands + (size_t)e * C, U, D);
+}
+
+// one WARP per env (envs that do not reset leave at once): lane 0 does the scalar work, lanes < D the joints, and all
+// lanes repair the observation row -- commands, dof_pos, dof_vel and the height entries, which depend on the new base
+// height (compute_observations runs after reset_idx on stale measured_heights, App. A-4) -- with the very noise samples
+// the step kernel attached to those entries.
+__global__ void __launch_bounds__(128)
+elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constant__ ElgStepParams pr, const __grid_constant__ ElgResetBuffers rb,
+                 const int N, const int D, const int F, const int C, const int O, const int H) {
+  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (e >= N) return;
+  if (!rb.reset_buf[e]) return;
+  Uniforms U{rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)e, make_uint4(0, 0, 0, 0), -1};
+  float* rs = rb.root_states + (size_t)e * 13;
+  float* cmd = rb.commands + (size_t)e * C;
+  float* org = rb.env_origins + (size_t)e * 3;
+  float* ds = rb.dof_state + (size_t)e * D * 2;
+  if (lane == 0) {
+    // ---- _update_terrain_curriculum (:498-518): old root position, old commands
+    if (rp.curriculum) {
+      const float dist = norm2_t(sub_r(rs[0], org[0]), sub_r(rs[1], org[1]));
+      const bool up = dist > rp.env_length_half;
+      const bool down = (dist < mul_r(mul_r(norm2_t(cmd[0], cmd[1]), rp.max_episode_length_s), 0.5f)) && !up;
+      long long lv = rb.terrain_levels[e] + (up ? 1 : 0) - (down ? 1 : 0);
+      if (lv >= rp.max_terrain_level) {
+        lv = (long long)(U.get(D + 11) * (float)rp.max_terrain_level);
+        if (lv >= rp.max_terrain_level) lv = rp.max_terrain_level - 1;
+      } else if (lv < 0) {
+        lv = 0;
+      }
+      rb.terrain_levels[e] = lv;
+      const float* to = rb.terrain_origins + ((size_t)lv * rp.terrain_cols + rb.terrain_types[e]) * 3;
+      org[0] = to[0]; org[1] = to[1]; org[2] = to[2];
+    }
+    // ---- _reset_root_states (:467-487)
+    for (int k = 0; k < 13; ++k) rs[k] = rp.base_init_state[k];
+    rs[0] = add_r(rs[0], org[0]); rs[1] = add_r(rs[1], org[1]); rs[2] = add_r(rs[2], org[2]);
+    if (rp.custom_origins) {
+      rs[0] = add_r(rs[0], rand_range(-0.5f, 0.5f, U.get(D)));
+      rs[1] = add_r(rs[1], rand_range(-0.5f, 0.5f, U.get(D + 1)));
+    }
+    for (int k = 0; k < 6; ++k) {
+      rs[7 + k] = rand_range(-0.5f, 0.5f, U.get(D + 2 + k));
+      rb.last_root_vel[(size_t)e * 6 + k] = rs[7 + k];              // the history copy after the reset (:150)
+    }
+    // ---- _resample_commands
+    resample_one(rp, cmd, U, D);
+    // ---- timers, episode clock (:191-198)
+    for (int f = 0; f < F; ++f) {
+      rb.feet_air_time[(size_t)e * F + f] = 0.0f;
+      rb.feet_contact_time[(size_t)e * F + f] = 0.0f;
+    }
+    rb.episode_length_buf[e] = 0;
+    atomicAdd(rb.stats + ELG_NUM_REWARD_TERMS, 1.0f);
+  }
+  // ---- _reset_dofs (:450-465); last_dof_vel = new dof_vel (= 0) after the history copy (:149); last_actions already
+  // holds `actions` (zeroed by reset_idx, then overwritten by the history copy :148)
+  for (int j = lane; j < D; j += 32) {
+    ds[2 * j] = mul_r(rb.default_dof_pos[j], rand_range(0.5f, 1.5f, U.get(j)));
+    ds[2 * j + 1] = 0.0f;
+    rb.last_dof_vel[(size_t)e * D + j] = 0.0f;
+  }
+  // ---- extras["episode"] (:200-206): (sum, count) over the reset envs, then zero the sums
+  for (int t = lane; t < ELG_NUM_REWARD_TERMS; t += 32)
+    if ((pr.reward_mask >> t) & 1u) {
+      float* sp = rb.episode_sums + (size_t)t * N + e;
+      atomicAdd(rb.stats + t, *sp);
+      *sp = 0.0f;
+    }
+  __syncwarp();
+  // ---- observation repair (:234-252 evaluated after the reset)
+  if (rb.obs_buf) {
+    const int head = 12 + 3 * D;
+    const int nj = (H + 31) >> 5, hm = (head + 31) >> 5;
+    const bool share = (nj & 7) + hm <= 8;
+    const bool philox = pr.noise_mode == ELG_NOISE_PHILOX;
+    float* ob = rb.obs_buf + (size_t)e * O;
+    auto finish = [&](int k, float v, float s16) {
+      if (pr.noise_mode == ELG_NOISE_TENSOR) v = v + (2.0f * rb.noise_u[(size_t)e * O + k] - 1.0f) * rb.noise_scale_vec[k];
+      else if (philox) v = v + fmaf(s16, 1.0f / 32768.0f, -1.0f) * rb.noise_scale_vec[k];
+      if (pr.clip_observations > 0.0f) v = fminf(fmaxf(v, -pr.clip_observations), pr.clip_observations);
+      ob[k] = v;
+    };
+    auto sample = [](const uint4& b, int sidx) {
+      const uint32_t w = (sidx >> 1) == 0 ? b.x : (sidx >> 1) == 1 ? b.y : (sidx >> 1) == 2 ? b.z : b.w;
+      return (float)((w >> (16 * (sidx & 1))) & 0xffffu);
+    };
+    // head entries k = lane + 32 m: sample (nj % 8) + m of block 1 + nj / 8 when shared, else sample m % 8 of block m / 8
+    for (int m = 0; m < hm; ++m) {
+      const int k = lane + 32 * m;
+      float v;
+      bool touch = false;
+      if (k >= 9 && k < 12) { v = cmd[k - 9] * pr.commands_scale[k - 9]; touch = true; }
+      else if (k >= 12 && k < 12 + D) { v = (ds[2 * (k - 12)] - rb.default_dof_pos[k - 12]) * pr.obs_scale_dof_pos; touch = true; }
+      else if (k >= 12 + D && k < 12 + 2 * D) { v = 0.0f * pr.obs_scale_dof_vel; touch = true; }
+      if (touch) {
+        float s16 = 0.0f;
+        if (philox) s16 = sample(noise_block(pr.noise_seed, pr.noise_offset, e, lane, share ? 1 + (nj >> 3) : (m >> 3)), share ? (nj & 7) + m : (m & 7));
+        finish(k, v, s16);
+      }
+    }
+    // height entries: clip(z - 0.5 - h, -1, 1) * scale with the NEW base height and the stale heights
+    if (H > 0 && rb.measured_heights) {
+      const float zc = sub_r(rs[2], 0.5f);
+      uint4 blk = make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < nj; ++j) {
+        if (philox && (j & 7) == 0) blk = noise_block(pr.noise_seed, pr.noise_offset, e, lane, 1 + (j >> 3));
+        const int p = lane + 32 * j;
+        if (p < H) {
+          const float h = rb.measured_heights[(size_t)e * H + p];
+          const float v = mul_r(fminf(fmaxf(sub_r(zc, h), -1.0f), 1.0f), pr.obs_scale_height);
+          finish(head + p, v, philox ? sample(blk, j & 7) : 0.0f);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace elg
+
+namespace {
+int rfail(int code, const char* msg) { return elg::set_error(code, msg); }
+}  // namespace
+
+extern "C" {
+
+int elg_sizeof_reset_params(void) { return (int)sizeof(ElgResetParams); }
+int elg_sizeof_reset_buffers(void) { return (int)sizeof(ElgResetBuffers); }
+
+int elg_resample_commands(const ElgDims* dims, const ElgResetParams* rp, const int64_t* episode_length_buf, float* commands,
+                          const float* uniforms, void* stream) {
+  if (!dims || !rp) return rfail(ELG_ERR_NULL_POINTER, "dims/params is NULL");
+  if (rp->resample_interval < 1) return rfail(ELG_ERR_INVALID_ARGUMENT, "resample_interval must be >= 1");
+  if (dims->num_dof + 12 > ELG_RESET_UNIFORMS) return rfail(ELG_ERR_UNSUPPORTED, "num_dof + 12 exceeds ELG_RESET_UNIFORMS");
+  if (dims->num_envs == 0) return ELG_OK;
+  if (!episode_length_buf || !commands) return rfail(ELG_ERR_NULL_POINTER, "episode_length_buf/commands is NULL");
+  elg::elg_resample_kernel<<<(dims->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*rp, dims->num_envs, dims->num_dof, dims->num_commands,
+                                                                                         episode_length_buf, commands, uniforms);
+  return elg::check_launch("elg_resample_commands");
+}
+
+int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepParams* prm, const ElgResetBuffers* buf, void* stream) {
+  if (!dims || !rp || !prm || !buf) return rfail(ELG_ERR_NULL_POINTER, "dims/params/buffers is NULL");
+  if (dims->num_dof + 12 > ELG_RESET_UNIFORMS) return rfail(ELG_ERR_UNSUPPORTED, "num_dof + 12 exceeds ELG_RESET_UNIFORMS");
+  if (dims->num_envs == 0) return ELG_OK;
+  if (!buf->reset_buf || !buf->root_states || !buf->dof_state || !buf->commands || !buf->env_origins || !buf->default_dof_pos ||
+      !buf->last_dof_vel || !buf->last_root_vel || !buf->feet_air_time || !buf->feet_contact_time || !buf->episode_length_buf ||
+      !buf->episode_sums || !buf->stats)
+    return rfail(ELG_ERR_NULL_POINTER, "a reset buffer is NULL");
+  if (rp->curriculum && (!buf->terrain_levels || !buf->terrain_types || !buf->terrain_origins || rp->max_terrain_level < 1 || rp->terrain_cols < 1))
+    return rfail(ELG_ERR_INVALID_ARGUMENT, "terrain curriculum needs terrain_levels / types / origins");
+  if (buf->obs_buf && prm->noise_mode != ELG_NOISE_OFF && !buf->noise_scale_vec) return rfail(ELG_ERR_NULL_POINTER, "noise_scale_vec is NULL");
+  if (buf->obs_buf && prm->noise_mode == ELG_NOISE_TENSOR && !buf->noise_u) return rfail(ELG_ERR_NULL_POINTER, "noise_u is NULL");
+  elg::elg_reset_kernel<<<(dims->num_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*rp, *prm, *buf, dims->num_envs, dims->num_dof, dims->num_feet,
+                                                                                      dims->num_commands, dims->num_obs, dims->num_height_points);
+  return elg::check_launch("elg_reset_envs");
+}
+
+}  // extern "C"

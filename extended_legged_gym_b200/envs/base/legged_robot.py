@@ -182,6 +182,12 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         self.gait_idx = None
         self.gait_prev_foot_z = None
         self.extra_reward = None
+        # True: resampling / reset_idx run as predicated kernels with in-kernel Philox (no nonzero(), no host sync);
+        # False: the reference's host-driven structure with torch RNG (what the parity tests pin)
+        self.fused_reset = True
+        self.reset_uniforms = None                # optional [N, 48] uniform table for the fused reset path (tests)
+        self._reset_stats = z(_lib.NUM_REWARD_TERMS + 1)
+        self._episode_means = z(_lib.NUM_REWARD_TERMS)
         self.episode_stats = None                 # utils.distributed.ShardedEpisodeStats when envs are sharded over GPUs
         self.noise_u = None                       # set to a [N,O] tensor of U[0,1) for torch.rand_like-parity noise
         self.noise_seed = int(getattr(cfg, "seed", 0) or 0) + 0x5EED
@@ -470,8 +476,19 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         self.sim.refresh()
         self.common_step_counter += 1
         clip = getattr(self, "_obs_clip_for_step", 0.0)
-        push_now = self._post_physics_step_callback()
         P = _lib
+        dr = self.cfg.domain_rand
+        push_step = bool(dr.push_robots and (self.common_step_counter % dr.push_interval == 0))
+        cmd_curr = bool(self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0))
+        if self.fused_reset and not self._python_terms and not push_step and not cmd_curr and self.episode_stats is None:
+            # the whole step without a host synchronisation: resample -> fused step -> reset (+ observation repair)
+            self._launch_resample()
+            self._launch(P.PHASE_FUSED, clip)
+            self.reset_buf = self._reset_bool
+            self._launch_reset()
+            self._noise_step += 1
+            return
+        push_now = self._post_physics_step_callback()
         if not self._python_terms and not push_now:
             # common case: the whole step is ONE kernel; the reset path below re-runs the cheap POST section
             self._launch(P.PHASE_FUSED, clip)
@@ -495,6 +512,86 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             self.reset_idx(env_ids)
             self._launch(P.PHASE_POST, clip)
         self._noise_step += 1
+
+    # ------------------------------------------------------------------------------------------
+    # fused reset path (csrc/elg_reset.cu): reset_idx / _resample_commands as predicated kernels
+    # ------------------------------------------------------------------------------------------
+    def _native_reset(self):
+        cfg, rp = self.cfg, _lib.ElgResetParams()
+        r = self.command_ranges
+        rp.lin_vel_x[:], rp.lin_vel_y[:] = r["lin_vel_x"], r["lin_vel_y"]
+        rp.ang_vel_yaw[:], rp.heading[:] = r["ang_vel_yaw"], r["heading"]
+        rp.heading_command = int(bool(cfg.commands.heading_command))
+        rp.resample_interval = int(cfg.commands.resampling_time / self.dt)
+        rp.base_init_state[:] = self.base_init_state.tolist()
+        rp.custom_origins = int(bool(self.custom_origins))
+        rp.curriculum = int(bool(cfg.terrain.curriculum and self.init_done))
+        if rp.curriculum:
+            rp.env_length_half = self.terrain.env_length / 2
+            rp.max_terrain_level = int(self.max_terrain_level)
+            rp.terrain_cols = int(self.terrain_origins.shape[1])
+        rp.max_episode_length_s = self.max_episode_length_s
+        rp.seed = self.noise_seed
+        b = _lib.ElgResetBuffers()
+        t = lambda x: None if x is None else x.data_ptr()
+        b.reset_buf, b.root_states, b.dof_state = t(self._reset_bool), t(self.root_states), t(self.dof_state)
+        b.commands, b.env_origins = t(self.commands), t(self.env_origins)
+        if rp.curriculum:
+            b.terrain_levels, b.terrain_types, b.terrain_origins = t(self.terrain_levels), t(self.terrain_types), t(self.terrain_origins)
+        b.default_dof_pos = t(self.default_dof_pos)
+        b.last_dof_vel, b.last_root_vel = t(self.last_dof_vel), t(self.last_root_vel)
+        b.feet_air_time, b.feet_contact_time = t(self.feet_air_time), t(self.feet_contact_time)
+        b.episode_length_buf, b.episode_sums, b.stats = t(self.episode_length_buf), t(self._episode_sums_all), t(self._reset_stats)
+        b.obs_buf, b.noise_scale_vec = t(self.obs_buf), t(self.noise_scale_vec)
+        b.measured_heights = t(self.measured_heights)
+        for name in ("env_origins", "terrain_levels", "terrain_origins", "commands"):
+            x = getattr(self, name, None)
+            if x is not None and not x.is_contiguous():
+                raise _lib.ElgError(f"fused reset: '{name}' must be contiguous")
+        if rp.curriculum and (self.terrain_levels.dtype != torch.int64 or self.terrain_types.dtype != torch.int64):
+            raise _lib.ElgError("fused reset: terrain_levels / terrain_types must be int64")
+        return rp, b
+
+    def _reset_native_synced(self):
+        key = (self._reset_bool.data_ptr(), self.obs_buf.data_ptr(), self.commands.data_ptr(), self.env_origins.data_ptr(),
+               self.root_states.data_ptr(), tuple(self.command_ranges["lin_vel_x"]), self.init_done)
+        if getattr(self, "_reset_key", None) != key:
+            self._reset_rp, self._reset_bufs = self._native_reset()
+            self._reset_key = key
+        self._reset_rp.offset = self._noise_step
+        self._reset_bufs.noise_u = _lib.ptr(self.noise_u)
+        self._reset_bufs.uniforms = _lib.ptr(self.reset_uniforms)
+        return self._reset_rp, self._reset_bufs
+
+    def _launch_resample(self):
+        self._sync_native()
+        rp, b = self._reset_native_synced()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.elg_resample_commands(C.byref(self._dims), C.byref(rp), self.episode_length_buf.data_ptr(), self.commands.data_ptr(),
+                                                   _lib.ptr(self.reset_uniforms), stream), "elg_resample_commands")
+
+    def _launch_reset(self):
+        rp, b = self._reset_native_synced()
+        self._reset_stats.zero_()
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.elg_reset_envs(C.byref(self._dims), C.byref(rp), C.byref(self._params), C.byref(b), stream), "elg_reset_envs")
+        # extras["episode"] (legged_robot.py:200-213) as device tensors: means over the envs that reset this step; steps
+        # without a reset keep the previous values (the reference leaves the dict untouched then)
+        cnt = self._reset_stats[_lib.NUM_REWARD_TERMS]
+        means = self._reset_stats[:_lib.NUM_REWARD_TERMS] / (cnt * self.max_episode_length_s)
+        self._episode_means = torch.where(cnt > 0, means, self._episode_means)
+        ep = {"rew_" + k: self._episode_means[_lib.TERM_ID[k]] for k in self.episode_sums if k in _lib.TERM_ID}
+        if self.cfg.terrain.curriculum:
+            ep["terrain_level"] = torch.mean(self.terrain_levels.float())
+        if self.cfg.commands.curriculum:
+            ep["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+        if self.cfg.rewards.multi_stage_rewards:
+            ep["reward_stage"] = float(self.reward_scales_stage)
+        self.extras["episode"] = ep
+        if self.cfg.env.send_timeouts:
+            self.extras["time_outs"] = self.time_out_buf
+        self.sim.set_dof_state()
+        self.sim.set_root_state()
 
     def _post_physics_step_callback(self):
         """Host part of the callback (legged_robot.py:386-403): sparse command resampling before the

@@ -44,6 +44,7 @@ class RobotBatchRollout(LeggedRobot):
         self.main_env_cache = None
         self.drift_u = None          # [num_rollout, 3] uniform samples for parity with torch.rand_like, else in-kernel Philox
         self._clone_calls = 0
+        self._clone_tables = {}
 
     def _parse_cfg(self, cfg):
         super()._parse_cfg(cfg)
@@ -91,7 +92,14 @@ class RobotBatchRollout(LeggedRobot):
         return tb, keep
 
     def _clone(self, mode, fields, drift=0.0):
-        tb, keep = self._clone_table(fields, with_cache=mode != _lib.CLONE_SYNC)
+        # the table only holds pointers and sizes: rebuilt when a tensor was rebound, otherwise reused (the ctypes fill
+        # costs more host time than the kernel takes)
+        key = tuple(getattr(self, f).data_ptr() for f in fields)
+        cached = self._clone_tables.get(mode)
+        if cached is None or cached[0] != key:
+            cached = (key,) + self._clone_table(fields, with_cache=mode != _lib.CLONE_SYNC)
+            self._clone_tables[mode] = cached
+        tb, keep = cached[1], cached[2]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         du = self.drift_u
         if du is not None and not (du.is_cuda and du.is_contiguous() and du.dtype == torch.float):
@@ -99,7 +107,6 @@ class RobotBatchRollout(LeggedRobot):
         rc = self._lib.elg_clone_rows(C.byref(tb), mode, float(drift), _lib.ptr(du), self.noise_seed, self._clone_calls, stream)
         _lib.check(rc, "elg_clone_rows")
         self._clone_calls += 1
-        del keep
 
     def _sync_main_to_rollout(self):
         if self.num_rollout_per_main == 0:

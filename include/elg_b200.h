@@ -336,6 +336,58 @@ int elg_mppi_partials(const float* costs_all /*[M,S_total]*/, int64_t num_main, 
                       float* partial /*[M, 1 + traj_size]: sum_e, sum_e * sample*/, void* stream);
 int elg_mppi_finish(const float* partial, int64_t num_main, int32_t traj_size, float* mean_traj /*[M,traj_size]*/, void* stream);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Sparse RNG-driven branches as predicated kernels over all envs: no nonzero(), no host synchronisation.
+ * elg_resample_commands: envs/base/legged_robot.py:389-393 + _resample_commands :405-423 for envs with
+ * (episode_length_buf + 1) % resample_interval == 0 (call BEFORE elg_post_physics_step, which increments the clock).
+ * elg_reset_envs: reset_idx :162-213 for envs with reset_buf set (call AFTER the fused step): terrain curriculum :498-518,
+ * _reset_dofs :450-465, _reset_root_states :467-487, _resample_commands, histories / timers / clock, (sum, count) of the
+ * episode sums for extras["episode"] into stats[ELG_NUM_REWARD_TERMS + 1] (atomics; caller zeroes it), episode sums zeroed,
+ * and the command / dof_pos / dof_vel observation entries recomputed (obs_buf may be NULL).
+ * update_command_curriculum (:520-531) stays on the host (it edits Python-side ranges once per max_episode_length steps). */
+#define ELG_RESET_UNIFORMS 48   /* columns of the optional per-env uniform table: see csrc/elg_reset.cu */
+typedef struct ElgResetParams {
+  float lin_vel_x[2], lin_vel_y[2], ang_vel_yaw[2], heading[2];   /* command_ranges */
+  int32_t heading_command;
+  int32_t resample_interval;     /* int(cfg.commands.resampling_time / dt) */
+  float base_init_state[13];
+  int32_t custom_origins;
+  int32_t curriculum;            /* cfg.terrain.curriculum (and init_done) */
+  float env_length_half;         /* terrain.env_length / 2 */
+  float max_episode_length_s;
+  int32_t max_terrain_level;
+  int32_t terrain_cols;          /* second dim of terrain_origins */
+  uint64_t seed, offset;         /* Philox key / step counter when no uniform table is given */
+} ElgResetParams;
+typedef struct ElgResetBuffers {
+  const uint8_t* reset_buf;      /* [N] bool */
+  float* root_states;            /* [N,13] */
+  float* dof_state;              /* [N*D,2] */
+  float* commands;               /* [N,C] */
+  float* env_origins;            /* [N,3] */
+  int64_t* terrain_levels;       /* [N] or NULL */
+  const int64_t* terrain_types;  /* [N] or NULL */
+  const float* terrain_origins;  /* [rows, cols, 3] or NULL */
+  const float* default_dof_pos;  /* [D] */
+  float* last_dof_vel;           /* [N,D] */
+  float* last_root_vel;          /* [N,6] */
+  float* feet_air_time;          /* [N,F] */
+  float* feet_contact_time;      /* [N,F] */
+  int64_t* episode_length_buf;   /* [N] */
+  float* episode_sums;           /* [ELG_NUM_REWARD_TERMS, N] */
+  float* stats;                  /* [ELG_NUM_REWARD_TERMS + 1] */
+  float* obs_buf;                /* [N,O] or NULL */
+  const float* measured_heights; /* [N,H] (stale heights the repaired height observations are built from) or NULL */
+  const float* noise_scale_vec;  /* [O] */
+  const float* noise_u;          /* [N,O] (ELG_NOISE_TENSOR) or NULL */
+  const float* uniforms;         /* [N, ELG_RESET_UNIFORMS] or NULL (Philox) */
+} ElgResetBuffers;
+int elg_sizeof_reset_params(void);
+int elg_sizeof_reset_buffers(void);
+int elg_resample_commands(const ElgDims* dims, const ElgResetParams* rp, const int64_t* episode_length_buf, float* commands,
+                          const float* uniforms, void* stream);
+int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepParams* prm, const ElgResetBuffers* buf, void* stream);
+
 /* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =
  * fp32(min(hs[i][j], hs[i+1][j], hs[i][j+1])) * vertical_scale for i <= rows-2, j <= cols-2 (0 elsewhere) -- the
  * value the reference computes per height point, tabulated once per (static) terrain so the step kernel gathers one

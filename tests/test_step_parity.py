@@ -28,6 +28,7 @@ def make_env(cfg, spec, st, hf, oracle=None):
     sim = SyntheticSim(cfg, n, DEV, spec=spec, height_samples=hf, state={k: v.clone() for k, v in st.items()})
     env = LeggedRobot(cfg, None, sim, DEV, True)
     env.set_env_state(st)
+    env.fused_reset = False      # the parity tests pin the reference's host-driven reset path and its torch RNG stream
     # host RNG hooks draw from the CPU generator so the sparse paths consume the oracle's numbers
     env._rand = lambda lo, hi, shape: ((hi - lo) * torch.rand(*shape) + lo).to(DEV)
     env._randint_like = lambda t, high: torch.randint_like(t.cpu(), high).to(DEV)
