@@ -33,6 +33,17 @@ __device__ __forceinline__ float norm3_t(float x, float y, float z) {
   return __fsqrt_rn(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))));
 }
 
+// IEEE sqrt for operands that are exactly zero most of the time (contact forces of bodies in the air): the special-operand
+// path of sqrt.rn (zero / denormal / inf / NaN) is an out-of-line routine at the far end of the kernel, and one zero lane
+// sends the whole warp there.  Same value for every s >= 0 and NaN.
+__device__ __forceinline__ float sqrt_rn_z(float s) {
+  const float r = __fsqrt_rn(s > 0.0f ? s : 1.0f);
+  return s > 0.0f ? r : s;
+}
+__device__ __forceinline__ float norm2_tz(float x, float y) { return sqrt_rn_z(__fmaf_rn(y, y, __fmul_rn(x, x))); }
+__device__ __forceinline__ float norm3_tz(float x, float y, float z) { return sqrt_rn_z(__fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x)))); }
+__device__ __forceinline__ float sumsq3_t(float x, float y, float z) { return __fmaf_rn(z, z, __fmaf_rn(y, y, __fmul_rn(x, x))); }
+
 // Correctly rounded x / c for a loop-invariant divisor: q0 = x*r, then two residual corrections.
 // This is the tail of the IEEE division sequence the hardware path uses (reciprocal, quotient,
 // two FMA corrections) with r = RN(1/c) supplied by the caller; valid for finite, normal-range
@@ -109,5 +120,20 @@ __device__ __forceinline__ uint4 noise_block(uint64_t seed, uint64_t offset, uin
                        make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
 }
 __device__ __forceinline__ uint32_t pick(const uint4& r, int m) { return m == 0 ? r.x : m == 1 ? r.y : m == 2 ? r.z : r.w; }
+
+// 16-bit uniform sample s (0..7) of a 128-bit Philox block, as a float in [0, 65535]
+__device__ __forceinline__ float sample16(const uint4& r, int s) {   // s known at compile time after unrolling
+  const uint32_t w = (s >> 1) == 0 ? r.x : (s >> 1) == 1 ? r.y : (s >> 1) == 2 ? r.z : r.w;
+  return (float)((s & 1) ? (w >> 16) : (w & 0xffffu));
+}
+__device__ __forceinline__ float sample16_dyn(const uint4& r, int s) {
+  const int i = s >> 1;
+  const uint32_t w = i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
+  return (float)((w >> (16 * (s & 1))) & 0xffffu);
+}
+
+// lean fused step for the common quadruped layout (elg_step_fast.cu): returns 1 when it took the launch (*rc = status)
+int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgStepBuffers* buf, uint32_t phase, int cap_override,
+                     int flags, long long* dbg, void* stream, int* rc);
 
 }  // namespace elg

@@ -28,6 +28,7 @@
 #include <stdio.h>
 
 #include "elg_common.cuh"
+#include "elg_async.cuh"
 
 namespace elg {
 
@@ -88,32 +89,6 @@ __device__ __forceinline__ float cell_height(const int16_t* __restrict__ hs, int
 }
 
 // ---------------------------------------------------------------------------------------------
-// packed fp32 pairs (sm_100a): one instruction, two individually IEEE-rounded results
-// ---------------------------------------------------------------------------------------------
-typedef unsigned long long f32x2;
-__device__ __forceinline__ f32x2 pack2(float x, float y) {
-  f32x2 r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(x), "f"(y));
-  return r;
-}
-__device__ __forceinline__ void unpack2(f32x2 v, float& x, float& y) { asm("mov.b64 {%0, %1}, %2;" : "=f"(x), "=f"(y) : "l"(v)); }
-__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
-  f32x2 r;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
-  return r;
-}
-__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
-  f32x2 r;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
-  return r;
-}
-
-// ---------------------------------------------------------------------------------------------
 // shared-memory plan of one chunk, built by the host (elg_post_physics_step below).
 // Offsets are BYTES from the start of dynamic shared memory; every region starts 128-byte aligned.
 // ---------------------------------------------------------------------------------------------
@@ -137,42 +112,6 @@ struct StepPlan {
   CopyDesc in[kMaxIn];
   CopyDesc out[kMaxOut];
 };
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-// TMA bulk copy global -> this CTA's shared memory; src, dst and bytes must be multiples of 16
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-// TMA bulk copy shared -> global (bulk async-group completion)
-__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
-  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_read_all() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
-__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 // cooperative fallback copies (ragged tail chunk or unaligned caller tensors)
 __device__ __forceinline__ void coop_copy(void* dst, const void* src, uint32_t bytes, int tid, int nthreads) {
@@ -200,18 +139,6 @@ __device__ __forceinline__ float lanes_sum(float v, int n) {   // n = number of 
   if (n > 4) return bfly_sum<8>(v);
   return bfly_sum<4>(v);
 }
-
-// 16-bit uniform sample s (0..7) of a 128-bit Philox block, as a float in [0, 65535]
-__device__ __forceinline__ float sample16(const uint4& r, int s) {   // s known at compile time after unrolling
-  const uint32_t w = (s >> 1) == 0 ? r.x : (s >> 1) == 1 ? r.y : (s >> 1) == 2 ? r.z : r.w;
-  return (float)((s & 1) ? (w >> 16) : (w & 0xffffu));
-}
-__device__ __forceinline__ float sample16_dyn(const uint4& r, int s) {
-  const int i = s >> 1;
-  const uint32_t w = i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
-  return (float)((w >> (16 * (s & 1))) & 0xffffu);
-}
-
 
 // ---------------------------------------------------------------------------------------------
 // the fused kernel.  kD / kF > 0 fix the DOF / foot count at compile time (12 / 4 for every
@@ -750,8 +677,8 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         }
         const f32x2 t = mul2(c_t, bs);          // (tx, ty)
         const f32x2 ts = mul2(c_ts, b);         // (ty, tx)
-        f32x2 pt = add2(b, mul2(c_w, t));       // b + w t
-        pt = add2(pt, mul2(c_u, ts));           // + q_xyz x t = (-zz ty, zz tx)
+        f32x2 pt = madd2_unfused(b, c_w, t);    // b + w t
+        pt = madd2_unfused(pt, c_u, ts);        // + q_xyz x t = (-zz ty, zz tx)
         pt = add2(add2(pt, xy), bord);          // + base xy, + border_size
         // correctly rounded pt / horizontal_scale: q0 = x r, two FMA residual corrections (Markstein)
         f32x2 q = mul2(pt, rr);
@@ -1091,6 +1018,10 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
   const int N = dims->num_envs;
   if (N == 0) return ELG_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_tune.no_fast == 0) {   // common quadruped layout, whole step in one launch: the lean kernel of elg_step_fast.cu
+    int rc = ELG_OK;
+    if (elg::launch_step_fast(dims, prm, buf, phase, g_tune.cap, g_tune.threads, g_step_dbg, stream, &rc)) return rc;
+  }
   const int D = dims->num_dof, F = dims->num_feet, B = dims->num_bodies, H = dims->num_height_points, O = dims->num_obs, C = dims->num_commands;
   const bool do_derive = phase & ELG_PHASE_DERIVE, do_term = phase & ELG_PHASE_TERMINATION, do_reward = phase & ELG_PHASE_REWARD;
   const bool do_obs = phase & ELG_PHASE_OBS, do_hist = phase & ELG_PHASE_HISTORY;
@@ -1275,10 +1206,8 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
 
   const size_t smem = (size_t)L.bytes;
   const bool quad = (D == 12 && F == 4);
-  const bool fast = quad && phase == ELG_PHASE_FUSED && !rollout && L.use_bulk && L.obs_smem && prm->height_points_env_stride == 0 &&
-                    (H == 0 || prm->terrain_is_plane || buf->height_field_min != nullptr) && g_tune.no_fast == 0;
-  auto kern = fast ? elg::elg_step_kernel<12, 4, true> : quad ? elg::elg_step_kernel<12, 4, false> : elg::elg_step_kernel<0, 0, false>;
-  const int which = fast ? 2 : quad ? 1 : 0;
+  auto kern = quad ? elg::elg_step_kernel<12, 4, false> : elg::elg_step_kernel<0, 0, false>;
+  const int which = quad ? 1 : 0;
   static size_t smem_set[3] = {0, 0, 0};
   if (smem > smem_set[which]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -1296,7 +1225,7 @@ int elg_set_step_debug(long long* device_stamps) {
 
 int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm, int disable_bulk) {
   if (envs_per_chunk == 0) {
-    g_tune = StepTune{0, 0, 0, disable_bulk & 1, (disable_bulk >> 1) & 1};
+    g_tune = StepTune{0, threads_per_cta, 0, disable_bulk & 1, (disable_bulk >> 1) & 1};
     return ELG_OK;
   }
   if (envs_per_chunk < 4 || envs_per_chunk > elg::kMaxCap || envs_per_chunk % 4 != 0)

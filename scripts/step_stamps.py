@@ -1,28 +1,33 @@
 #!/usr/bin/env python
-"""In-kernel timeline of the fused step kernel (clock64 stamps of CTA 0) + an empty-kernel launch floor."""
+"""In-kernel timeline of the lean fused step kernel (clock64 stamps of CTA 0) + an empty-kernel launch floor."""
 import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
 from step_sweep import make, lib, dev, _lib
-names = ["entry", "tables done", "after sync0", "loads landed", "items done", "after B1", "scalar done", "rows done (w0)", "after B2",
-         "head done", "stores issued", "stores drained"]
-for n in (4096, 1024):
-    env = make("anymal_c_rough", n, 0)
-    buf = torch.zeros(16, dtype=torch.int64, device=dev)
+names = {0: "entry", 1: "after griddepcontrol.wait", 2: "loads landed (warp 0)", 3: "phase A done (warp 0)", 4: "B1 passed", 5: "row0: gathers issued",
+         6: "row0: scan done", 7: "row0: head done", 8: "assembly warp done", 9: "B2 passed", 10: "stores read out (warp 0)"}
+for case, n in (("anymal_c_rough", 4096), ("anymal_c_rough", 1024), ("anymal_c_flat", 4096)):
+    env = make(case, n, 0)
+    buf = torch.zeros(32, dtype=torch.int64, device=dev)
     lib.elg_set_step_debug.argtypes = [C.c_void_p]
     lib.elg_set_step_debug(buf.data_ptr())
     p = env._params
     p.noise_mode, p.clip_observations = _lib.NOISE_PHILOX, 100.0
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for i in range(5):
         p.noise_offset = i
+        flush.fill_(i)
+        torch.cuda.synchronize()
         _lib.check(lib.elg_post_physics_step(C.byref(env._dims), C.byref(p), C.byref(env._bufs), _lib.PHASE_FUSED, None))
         torch.cuda.synchronize()
     st = buf.cpu().tolist()
-    print(f"N={n}: cycles since entry (x0.509 ns at 1965 MHz)")
-    for i, nm in enumerate(names):
-        print(f"  {nm:18s} {st[i] - st[0]:8d} cyc  {(st[i] - st[0]) / 1965.0:7.2f} us")
+    print(f"{case} N={n}: cycles since entry, cold L2 (1965 MHz)")
+    for i in sorted(names, key=lambda k: st[k]):
+        if st[i]:
+            print(f"  {names[i]:32s} {st[i] - st[0]:8d} cyc  {(st[i] - st[0]) / 1965.0:7.2f} us")
     lib.elg_set_step_debug(None)
+    del flush
 # launch floor: a trivial torch kernel chain in a graph
 x = torch.zeros(148 * 1024, device=dev)
 g = torch.cuda.CUDAGraph()

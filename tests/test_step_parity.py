@@ -134,8 +134,15 @@ def test_fused_equals_split_sections():
         env.reset_buf = env._reset_bool
         torch.cuda.synchronize()
         outs.append(common.snapshot(env))
+    # the fused launch takes the lean kernel (elg_step_fast.cu), the sections the generic one: per-env sums over DOFs /
+    # feet associate differently, so float outputs agree to the fp32 tolerance of the north star; masks, counters and
+    # everything not behind such a sum stay bit-identical
     for k in outs[0]:
-        assert torch.equal(outs[0][k], outs[1][k]), k
+        a, b = outs[0][k], outs[1][k]
+        if a.dtype.is_floating_point and (k.startswith("sum_") or k in ("rew_buf",)):
+            torch.testing.assert_close(a, b, rtol=1e-5, atol=1e-6, msg=k)
+        else:
+            assert torch.equal(a, b), k
 
 
 def test_user_defined_reward_term_and_override():
