@@ -383,6 +383,11 @@ def main():
     value = total_envs * K / t_full
     ms_per_step = t_full / K * 1e3
     peak, peak_src = peaks()
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "step_traffic.json")     # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
+    if os.path.exists(tpath) and args.config == "anymal_c_rough" and n_envs == 4096:
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     t_kernel = t_step_only / K
     achieved = bytes_per_step / t_kernel / 1e9
 
@@ -434,12 +439,12 @@ def main():
                                f"{n_envs} envs per GPU", "num_envs_per_gpu": n_envs, "num_envs_total": total_envs,
                    "sharding": f"envs x{world}, no data-path collective", "height_points": H, "num_obs": O, "reward_terms": R_terms,
                    "l2_policy": f"inputs larger than L2: {n_rep} state replicas x {bytes_per_step / 1e6:.1f} MB rotated per step",
-                   "noise": "in-kernel Philox4x32-10", "launch": "CUDA graph of K steps, 2 kernels per step"},
+                   "noise": "in-kernel Philox4x32-10", "launch": "CUDA graph of K steps, 2 kernels per step, programmatic dependent launch"},
         "gpu_launches": 2 * K,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": args.e2e_steps,
                 "ms_per_step": t_e2e / args.e2e_steps * 1e3, "api": "LeggedRobot._compute_torques + post_physics_step, pinned host state"},
-        "roofline": {"bound": "hbm", "kernel": "elg_step_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                     "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "roofline": {"bound": "hbm", "kernel": "elg_step_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                     "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_step, "bytes_per_env": rd + wr, "us_per_launch": t_kernel * 1e6,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
         "clocks": clk.summary(),

@@ -836,6 +836,8 @@ elg_torques_kernel(const int64_t n_rows, const int D, const int control_type, co
                    const float* __restrict__ default_dof_pos, float* __restrict__ torques,
                    const int64_t* __restrict__ env_ids) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();   // programmatic dependent launch: scheduled while the previous kernel drains, but nothing is
+  pdl_wait();                // read before that kernel's memory is visible
   if (i >= n_rows * D) return;
   const int64_t r = i / D;
   const int j = (int)(i - r * D);
@@ -980,9 +982,17 @@ int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const flo
   const int64_t total = rows * dims->num_dof;
   const int threads = 256;
   const unsigned blocks = (unsigned)((total + threads - 1) / threads);
-  elg::elg_torques_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(
-      rows, dims->num_dof, prm->control_type, prm->action_scale, prm->sim_dt, actions, dof_state, last_dof_vel, p_gains,
-      d_gains, torque_limits, default_dof_pos, torques, env_ids);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(blocks);
+  cfg.blockDim = dim3(threads);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, elg::elg_torques_kernel, rows, (int)dims->num_dof, (int)prm->control_type, prm->action_scale, prm->sim_dt,
+                     actions, dof_state, last_dof_vel, p_gains, d_gains, torque_limits, default_dof_pos, torques, env_ids);
   return check_launch("elg_compute_torques");
 }
 
@@ -1225,7 +1235,7 @@ int elg_set_step_debug(long long* device_stamps) {
 
 int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm, int disable_bulk) {
   if (envs_per_chunk == 0) {
-    g_tune = StepTune{0, threads_per_cta, 0, disable_bulk & 1, (disable_bulk >> 1) & 1};
+    g_tune = StepTune{0, threads_per_cta, ctas_per_sm, disable_bulk & 1, (disable_bulk >> 1) & 1};
     return ELG_OK;
   }
   if (envs_per_chunk < 4 || envs_per_chunk > elg::kMaxCap || envs_per_chunk % 4 != 0)

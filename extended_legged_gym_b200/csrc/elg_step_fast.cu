@@ -52,7 +52,7 @@ struct FastPlan {
   int bytes;
   float r_hscale;  // RN(1 / horizontal_scale)
   float pen_sq, term_sq;   // largest sums of squares whose IEEE sqrt is still <= 0.1 / <= 1.0 (contact thresholds)
-  int flags;       // experiment switches (elg_set_step_tuning): 1 warm constants, 2 tasks from the top warp, 4 F2I-free cells
+  int flags;       // diagnostic switches (elg_set_step_tuning threads_per_cta): 16 = launch without PDL
   long long* dbg;  // diagnostic: clock64 stamps of CTA 0 (elg_set_step_debug), or NULL
   int8_t term_ids[ELG_NUM_REWARD_TERMS];
   FastCopy in[kFastMaxIn];
@@ -106,18 +106,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
 
   if (tid == 0) mbar_init(&s_bar, L.n_in);
   pdl_launch_dependents();
-  // Kernel parameters sit in the constant bank and every launch brings a fresh, cold copy: a first touch of a line costs a
-  // round trip to L2, and the phases below would pay those one after the other on their critical paths.  Touch every line
-  // once here, one line per warp and round, so that the misses overlap each other, the barrier set-up and (under PDL) the
-  // tail of the previous kernel.  The copy-table entry this warp will issue is fetched now for the same reason.
-  if (L.flags & 1) {
-    uint32_t acc = 0;
-    for (int o = warp * 64; o < (int)sizeof(ElgDims); o += nwarps * 64) acc ^= *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(&dm) + o);
-    for (int o = warp * 64; o < (int)sizeof(ElgStepParams); o += nwarps * 64) acc ^= *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(&pr) + o);
-    for (int o = warp * 64; o < (int)sizeof(ElgStepBuffers); o += nwarps * 64) acc ^= *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(&bf) + o);
-    for (int o = warp * 64; o < (int)offsetof(FastPlan, in); o += nwarps * 64) acc ^= *reinterpret_cast<const uint32_t*>(reinterpret_cast<const char*>(&L) + o);
-    asm volatile("" ::"r"(acc));
-  }
+  // the copy-table entries this warp will issue: fetched before the wait so that the constant-bank miss is off the load path
   FastCopy my_in = L.in[warp < L.n_in ? warp : 0];
   FastCopy my_out = L.out[warp < L.n_out ? warp : 0];
   __syncthreads();
@@ -125,18 +114,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   STAMP(1, 0)
 
   // ---- TMA loads: lane 0 of warp w issues copy-table entries w, w + W, ...
-  const bool direct = L.flags & 8;   // experiment: 16-byte cp.async per lane instead of one bulk copy per array
-  if (direct) {
-    for (int i = warp; i < L.n_in; i += nwarps) {
-      const FastCopy d = i == warp ? my_in : L.in[i];
-      const int nvec = (n * d.bpe) >> 4;
-      const uint8_t* src = static_cast<const uint8_t*>(d.g) + (size_t)env0 * d.bpe;
-      const uint32_t dst = smem_u32(smem_raw + d.soff);
-      for (int v = lane; v < nvec; v += 32)
-        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + 16u * v), "l"(src + 16 * (size_t)v) : "memory");
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-  } else if (lane == 0) {
+  if (lane == 0) {
     for (int i = warp; i < L.n_in; i += nwarps) {
       const FastCopy d = i == warp ? my_in : L.in[i];
       const uint32_t bytes = (uint32_t)(n * d.bpe);
@@ -220,7 +198,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   const int genv = env0 + e;
   // Task inputs that do not come through the bulk copies are fetched now, while those are in flight: feet tasks their strided
   // rigid_body_state row (52-byte rows, 6 useful floats), DOF tasks their default angles and soft limits.
-  const int task0 = (L.flags & 2) ? nwarps - 1 - warp : warp;   // first phase-A task of this warp
+  const int task0 = warp;   // first phase-A task of this warp
   const bool lim_terms = on(pr, ELG_REW_DOF_POS_LIMITS) | on(pr, ELG_REW_DOF_VEL_LIMITS) | on(pr, ELG_REW_TORQUE_LIMITS);
   float pre[10] = {0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f};
   auto prefetch = [&](int task) {
@@ -241,13 +219,10 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     }
   };
   prefetch(task0);
-  if (direct) {
-    asm volatile("cp.async.wait_group 0;" ::: "memory");
-    __syncthreads();
-  } else {
-    mbar_wait(&s_bar, 0);
-  }
+  STAMP(11, 0)
+  mbar_wait(&s_bar, 0);
   STAMP(2, 0)
+  STAMP(12, nwarps - 1)
 
 #pragma unroll 1
   for (int task = task0; task < kNumTasks; task += nwarps) {
@@ -490,19 +465,10 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
           q = fma2(er, rr, q);
           float qx, qy;
           unpack2(q, qx, qy);
-          if (L.flags & 4) {
-            // clip(trunc(q), 0, max) == trunc(clip(q, 0, max)); trunc of a float in [0, 2^23) without the conversion
-            // unit: the low mantissa bits of RZ(q + 2^23)
-            qx = __fadd_rz(fminf(fmaxf(qx, 0.0f), (float)rmax), 8388608.0f);
-            qy = __fadd_rz(fminf(fmaxf(qy, 0.0f), (float)cmax), 8388608.0f);
-            const int ix = __float_as_int(qx) & 0x7fffff, iy = __float_as_int(qy) & 0x7fffff;
-            hv[j] = __ldg(hmin + (ix * cols + iy));
-          } else {
           int ix = __float2int_rz(qx), iy = __float2int_rz(qy);
           ix = min(max(ix, 0), rmax);
           iy = min(max(iy, 0), cmax);
           hv[j] = __ldg(hmin + (ix * cols + iy));
-          }
         }
       } else {
 #pragma unroll
@@ -700,17 +666,19 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   if (sms <= 0) return 0;
 
   // ---- chunking: whole quads of envs, one chunk per CTA; small N: one balanced chunk per SM
+  // (measured, scripts/step_large.py: at many chunks per SM the kernel is issue-bound -- smaller CTAs with 3 or 4 resident
+  //  per SM are no faster than one 28-env CTA per SM, so every launch uses the widest chunks that balance)
   const long long Q = (long long)N / 4;
   int cap, nchunks;
   if (cap_override >= 4 && cap_override <= kFastMaxCap && cap_override % 4 == 0) {
     cap = cap_override;
     nchunks = (int)((Q + cap / 4 - 1) / (cap / 4));
-  } else if ((Q + kFastMaxCap / 4 - 1) / (kFastMaxCap / 4) <= sms) {
-    nchunks = (int)(Q < sms ? Q : sms);
-    cap = 4 * (int)((Q + nchunks - 1) / nchunks);
   } else {
-    cap = 12;                         // many chunks: 16-warp CTAs, two resident per SM
-    nchunks = (int)((Q + 2) / 3);
+    const long long per = kFastMaxCap / 4;
+    long long nch = (Q + per - 1) / per;                 // fewest chunks of <= 28 envs ...
+    if (nch < sms) nch = Q < sms ? Q : sms;              // ... but never fewer than one per SM while there are quads to hand out
+    nchunks = (int)nch;
+    cap = 4 * (int)((Q + nchunks - 1) / nchunks);
   }
   FastPlan L{};
   L.cap = cap;
@@ -835,7 +803,7 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
     default: kern = clip ? elg_step_fast_kernel<ELG_NOISE_PHILOX, true> : elg_step_fast_kernel<ELG_NOISE_PHILOX, false>; break;
   }
   const int which = prm->noise_mode * 2 + (clip ? 1 : 0);
-  static size_t smem_set[6] = {0, 0, 0, 0, 0, 0};
+  static size_t smem_set[6] = {};
   if ((size_t)L.bytes > smem_set[which]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes) != cudaSuccess) {
       *rc = set_error(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_step_fast_kernel");
@@ -852,7 +820,7 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = (flags & 16) ? 0 : 1;   // experiment switch: plain stream-ordered launch
   if (cudaLaunchKernelEx(&cfg, kern, *dims, *prm, *buf, L) != cudaSuccess) {
     *rc = check_launch("elg_post_physics_step (fast)");
     if (*rc == ELG_OK) *rc = set_error(ELG_ERR_CUDA, "cudaLaunchKernelEx failed for elg_step_fast_kernel");

@@ -14,6 +14,6 @@ timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/${TAG}
 cat $OUT/${TAG}_bench_ref.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 50 --warmup 3 --e2e-steps 5 --no-cpu-baseline --no-secondary > $OUT/${TAG}_ncu_bench.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:elg_step -s 10 -c 3 -f -o $OUT/${TAG}_step \
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:elg_step_fast -s 10 -c 3 -f -o $OUT/${TAG}_step \
     python bench.py --steps 20 --warmup 3 --e2e-steps 2 --no-cpu-baseline --no-secondary > $OUT/${TAG}_ncu_full.log 2>&1
 ls -la $OUT | tail -20

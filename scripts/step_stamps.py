@@ -6,8 +6,8 @@ sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
 from step_sweep import make, lib, dev, _lib
 names = {0: "entry", 1: "after griddepcontrol.wait", 2: "loads landed (warp 0)", 3: "phase A done (warp 0)", 4: "B1 passed", 5: "row0: gathers issued",
-         6: "row0: scan done", 7: "row0: head done", 8: "assembly warp done", 9: "B2 passed", 10: "stores read out (warp 0)"}
-for case, n in (("anymal_c_rough", 4096), ("anymal_c_rough", 1024), ("anymal_c_flat", 4096)):
+         6: "row0: scan done", 7: "row0: head done", 8: "assembly warp done", 9: "B2 passed", 10: "stores read out (warp 0)", 11: "warp 0 reaches the TMA wait", 12: "loads landed (last warp, idle until then)"}
+for case, n in (("anymal_c_rough", 4096), ("anymal_c_flat", 4096)):
     env = make(case, n, 0)
     buf = torch.zeros(32, dtype=torch.int64, device=dev)
     lib.elg_set_step_debug.argtypes = [C.c_void_p]
