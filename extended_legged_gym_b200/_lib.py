@@ -145,6 +145,7 @@ def load() -> C.CDLL:
     lib.elg_get_heights.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 5 + [vp]
     lib.elg_clone_rows.argtypes = [C.POINTER(ElgCloneTable), C.c_int, C.c_float, vp, C.c_uint64, C.c_uint64, vp]
     lib.elg_set_step_debug.argtypes = [vp]
+    lib.elg_set_clone_tuning.argtypes = [C.c_int]
     lib.elg_mesh_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(vp)]
     lib.elg_mesh_free.argtypes = [vp]
     lib.elg_mesh_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]

@@ -18,6 +18,7 @@
 #include <stdio.h>
 
 #include "elg_common.cuh"
+#include "elg_async.cuh"
 
 namespace elg {
 
@@ -104,6 +105,163 @@ elg_clone_sync_kernel(const __grid_constant__ ElgCloneTable tb, const float drif
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// The same clone with the TMA doing the writing.  For every field the CTA replicates the main row tile_rows times in
+// shared memory -- rotated so that the tile starts at the first 16-byte boundary of the destination span -- and then
+// ONE cp.async.bulk (shared -> global) per field and chunk moves tile_rows * row_bytes bytes: a few instructions per
+// kilobyte instead of one 16-byte store per thread.  grid = (chunk slices, num_main); chunk c of a field covers span
+// words [head + c * tile_words, head + (c + 1) * tile_words).  The <= 3 words in front of the first boundary and the
+// <= 3 behind the last full vector are plain stores.  The drift field (root_states when the position drift is on) gets
+// its tile rebuilt per chunk, the three position words of every row drifted; all other tiles are built once per CTA.
+// No integer division anywhere: a modulo by a run-time row length costs more than a whole tile.
+// ---------------------------------------------------------------------------------------------------------------
+struct CloneBulkPlan {
+  int tile_rows;                        // multiple of 4, <= rollouts_per_main
+  int tile_off[ELG_MAX_CLONE_FIELDS];   // byte offset of the field's tile in dynamic shared memory (16-byte aligned)
+  int row_off[ELG_MAX_CLONE_FIELDS];    // word offset of the field's staged main row
+  int tiles_bytes;                      // staged rows live behind the tiles
+  int debug;                            // measurement switches: 2 = build only (no stores), 4 = stores only (no build)
+};
+
+__global__ void __launch_bounds__(kCloneThreads)
+elg_clone_bulk_kernel(const __grid_constant__ ElgCloneTable tb, const __grid_constant__ CloneBulkPlan pl, const float drift,
+                      const float* __restrict__ drift_u, const uint64_t seed, const uint64_t offset) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  uint32_t* const s_row = reinterpret_cast<uint32_t*>(smem_raw + pl.tiles_bytes);
+  constexpr int kWarps = kCloneThreads / 32;
+  const int k = blockIdx.y;                       // main env
+  const int R = tb.rollouts_per_main, TR = pl.tile_rows;
+  const size_t main_row = (size_t)k * (1 + R);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int nf = tb.num_fields;
+  const bool drift_on = tb.drift_field >= 0 && drift > 0.0f;
+  pdl_launch_dependents();
+  pdl_wait();
+  // stage the main row of every field
+  for (int f = 0; f < nf; ++f) {
+    const int rw = tb.fields[f].row_bytes >> 2;
+    const uint32_t* src = static_cast<const uint32_t*>(tb.fields[f].base) + main_row * rw;
+    for (int i = tid; i < rw; i += kCloneThreads) s_row[pl.row_off[f] + i] = src[i];
+  }
+  __syncthreads();
+  auto head_words = [&](int f) {   // words of the span in front of its first 16-byte boundary
+    const int rw = tb.fields[f].row_bytes >> 2;
+    const uintptr_t dst = reinterpret_cast<uintptr_t>(tb.fields[f].base) + (main_row + 1) * rw * 4;
+    const int h = (int)(((16 - (dst & 15)) & 15) >> 2);
+    return h < R * rw ? h : R * rw;
+  };
+  auto drift_word = [&](int rr, int j, uint32_t v) -> uint32_t {   // position component j of rollout rr of this main
+    const long long gi = ((long long)k * R + rr) * 3 + j;
+    float u;
+    if (drift_u) {
+      u = drift_u[gi];
+    } else {
+      const uint4 b = philox4x32_10(make_uint4((uint32_t)gi, (uint32_t)(gi >> 32), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+      u = u01(b.x);
+    }
+    return __float_as_uint(add_r(__uint_as_float(v), mul_r(sub_r(u, 0.5f), drift)));
+  };
+  // replicated, rotated tiles of the fields that do not drift: tile[i] = row[(head + i) % rw].  Warp w builds (and later
+  // stores) fields w, w + 8, ...
+  if (!(pl.debug & 4))
+  for (int f = warp; f < nf; f += kWarps) {
+    if (drift_on && f == tb.drift_field) continue;
+    const int rw = tb.fields[f].row_bytes >> 2;
+    const uint32_t* row = s_row + pl.row_off[f];
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw + pl.tile_off[f]);
+    const int tw = TR * rw;
+    int m = head_words(f) + lane;
+    while (m >= rw) m -= rw;
+    int step = 32;
+    while (step >= rw) step -= rw;
+    for (int i = lane; i < tw; i += 32) {
+      tile[i] = row[m];
+      m += step;
+      m = m >= rw ? m - rw : m;
+    }
+  }
+  fence_async_smem();
+  __syncthreads();
+  // chunks of this CTA: lane 0 of warp w issues the bulk stores of its fields
+  const int nchunk = (R + TR - 1) / TR;
+  if (lane == 0 && !(pl.debug & 2)) {
+    for (int f = warp; f < nf; f += kWarps) {
+      if (drift_on && f == tb.drift_field) continue;
+      const int rw = tb.fields[f].row_bytes >> 2;
+      const int head = head_words(f), span = R * rw, tw = TR * rw;
+      uint32_t* dst = static_cast<uint32_t*>(tb.fields[f].base) + (main_row + 1) * rw;
+      for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+        const int w0 = head + c * tw;
+        int words = span - w0;
+        words = words < tw ? words : tw;
+        words &= ~3;
+        if (words > 0) bulk_s2g(dst + w0, smem_raw + pl.tile_off[f], (uint32_t)words * 4u);
+      }
+    }
+    bulk_commit();
+  }
+  // the drifting field: one freshly built tile per chunk; lanes over the words of a row, warps over the rows of the chunk
+  if (drift_on) {
+    const int f = tb.drift_field;
+    const int rw = tb.fields[f].row_bytes >> 2;
+    const uint32_t* row = s_row + pl.row_off[f];
+    uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw + pl.tile_off[f]);
+    const int head = head_words(f), span = R * rw, tw = TR * rw;
+    uint32_t* dst = static_cast<uint32_t*>(tb.fields[f].base) + (main_row + 1) * rw;
+    bool pending = false;
+    for (int c = blockIdx.x; c < nchunk; c += gridDim.x) {
+      if (pending) bulk_wait_read_all();   // (thread 0) the previous chunk has left the tile
+      __syncthreads();
+      const int w0 = head + c * tw;
+      int words = span - w0;
+      words = words < tw ? words : tw;
+      words &= ~3;
+      // the chunk covers span words [w0, w0 + words): rows c * TR .. c * TR + TR (the last one partially, by the head words)
+      for (int rl = warp; rl <= TR; rl += kWarps) {
+        const int rr = c * TR + rl;
+        for (int j = lane; j < rw; j += 32) {
+          const int i = rr * rw + j - w0;
+          if (rr < R && i >= 0 && i < words) tile[i] = j < 3 ? drift_word(rr, j, row[j]) : row[j];
+        }
+      }
+      fence_async_smem();
+      __syncthreads();
+      if (tid == 0 && words > 0) {
+        bulk_s2g(dst + w0, tile, (uint32_t)words * 4u);
+        bulk_commit();
+        pending = true;
+      }
+    }
+  }
+  // head and tail words of every span (slice 0): 8 threads per field, thread t < head writes head word t, thread 4 + t tail word t
+  if (blockIdx.x == 0 && tid < 8 * nf) {
+    const int f = tid >> 3, t = tid & 7;
+    const int rw = tb.fields[f].row_bytes >> 2;
+    const uint32_t* row = s_row + pl.row_off[f];
+    uint32_t* dst = static_cast<uint32_t*>(tb.fields[f].base) + (main_row + 1) * rw;
+    const int head = head_words(f), span = R * rw;
+    const int tailw = (span - head) & 3;
+    int w = -1, mm = 0, rr = 0;   // span word, its column, its rollout row
+    if (t < head) {
+      w = t;
+      mm = t;
+      while (mm >= rw) { mm -= rw; ++rr; }
+    } else if (t >= 4 && t < 4 + tailw) {
+      w = span - tailw + (t - 4);
+      mm = (t - 4) - tailw;        // == w (mod rw) because span is a multiple of rw
+      rr = R;
+      while (mm < 0) { mm += rw; --rr; }
+    }
+    if (w >= 0) {
+      uint32_t v = row[mm];
+      if (drift_on && f == tb.drift_field && mm < 3) v = drift_word(rr, mm, v);
+      dst[w] = v;
+    }
+  }
+  if (lane == 0) bulk_wait_read_all();   // shared memory must outlive the reads
+}
+
 // rows whose size is not a multiple of 4 bytes (e.g. last_contacts with F % 4 != 0): byte-wise fallback, all fields
 __global__ void __launch_bounds__(kCloneThreads)
 elg_clone_sync_bytes_kernel(const __grid_constant__ ElgCloneTable tb, const float drift, const float* __restrict__ drift_u,
@@ -178,11 +336,17 @@ elg_clone_cache_kernel(const __grid_constant__ ElgCloneTable tb, const int resto
 
 namespace {
 int cfail(int code, const char* msg) { return elg::set_error(code, msg); }
+int g_clone_tune = 0;   // elg_set_clone_tuning: 1 = per-thread 16-byte stores instead of TMA bulk stores; 2 / 4 = measurement switches
 }  // namespace
 
 extern "C" {
 
 int elg_sizeof_clone_table(void) { return (int)sizeof(ElgCloneTable); }
+
+int elg_set_clone_tuning(int disable_bulk) {
+  g_clone_tune = disable_bulk;
+  return ELG_OK;
+}
 
 int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const float* drift_u, uint64_t seed, uint64_t offset, void* stream) {
   if (!table) return cfail(ELG_ERR_NULL_POINTER, "clone table is NULL");
@@ -217,6 +381,49 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
     if (slices < 1) slices = 1;
     if (table->num_main > 65535) return cfail(ELG_ERR_UNSUPPORTED, "more than 65535 main envs");
     if ((long long)table->rollouts_per_main * biggest / 4 > 0x7fffffffLL / 8) return cfail(ELG_ERR_UNSUPPORTED, "rollouts_per_main * row size too large");
+    // TMA path: word-sized rows, at least 4 rollouts per main; tile of up to 64 rows per field, <= 160 KB of shared memory
+    if (words && staged > 0 && staged <= elg::kCloneMaxRowWords && table->rollouts_per_main >= 4 && (g_clone_tune & 1) == 0) {
+      int tr = table->rollouts_per_main < 64 ? table->rollouts_per_main : 64;
+      const int fit = (160 * 1024 - staged * 4) / (staged * 4);
+      if (tr > fit) tr = fit;
+      tr &= ~3;
+      if (tr >= 4) {
+        elg::CloneBulkPlan pl{};
+        pl.tile_rows = tr;
+        pl.debug = g_clone_tune;
+        int toff = 0, roff = 0;
+        for (int f = 0; f < table->num_fields; ++f) {
+          pl.tile_off[f] = toff;
+          pl.row_off[f] = roff;
+          toff += tr * table->fields[f].row_bytes;   // multiple of 16: tr % 4 == 0, row_bytes % 4 == 0
+          roff += table->fields[f].row_bytes / 4;
+        }
+        pl.tiles_bytes = toff;
+        const size_t smem = (size_t)toff + (size_t)roff * 4;
+        static size_t smem_set = 0;
+        if (smem > smem_set) {
+          if (cudaFuncSetAttribute(elg::elg_clone_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+            return cfail(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_clone_bulk_kernel");
+          smem_set = smem;
+        }
+        const long long nchunk = ((long long)table->rollouts_per_main + tr - 1) / tr;
+        long long sl = (2LL * sms + table->num_main - 1) / table->num_main;   // ~2 CTAs per SM
+        if (sl > nchunk) sl = nchunk;
+        if (sl < 1) sl = 1;
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3((unsigned)sl, (unsigned)table->num_main);
+        cfg.blockDim = dim3(elg::kCloneThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaLaunchKernelEx(&cfg, elg::elg_clone_bulk_kernel, *table, pl, drift, drift_u, seed, offset);
+        return elg::check_launch("elg_clone_rows");
+      }
+    }
     const dim3 grid((unsigned)slices, (unsigned)table->num_main);
     if (words && staged <= elg::kCloneMaxRowWords)
       elg::elg_clone_sync_kernel<<<grid, elg::kCloneThreads, 0, st>>>(*table, drift, drift_u, seed, offset);

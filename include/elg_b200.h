@@ -262,6 +262,9 @@ int elg_sizeof_clone_table(void);
  * samples (= torch.rand_like(base_pos[rollout_env_indices]), robot_batch_rollout.py:1493-1497) or NULL for in-kernel
  * Philox4x32-10 keyed by seed with counter (sample index, offset). */
 int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const float* drift_u, uint64_t seed, uint64_t offset, void* stream);
+/* Diagnostic (no reference counterpart): disable_bulk != 0 makes ELG_CLONE_SYNC write with per-thread 16-byte stores instead
+ * of TMA bulk stores from replicated shared-memory tiles (A/B measurements); 0 restores the default. */
+int elg_set_clone_tuning(int disable_bulk);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Triangle-mesh queries (the reference delegates these to warp-lang 1.7: wp.Mesh / wp.mesh_query_ray /

@@ -11,6 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 import common  # noqa: E402
+from extended_legged_gym_b200 import _lib  # noqa: E402
 from oracle import ref_harness, rollout_oracle as ro  # noqa: E402
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_clone.npz")
@@ -135,6 +136,34 @@ def test_clone_kernel_matches_oracle(m, r, drift):
     torch.cuda.synchronize()
     for k, v in ro.snapshot(o).items():
         assert torch.equal(getattr(env, k).cpu().view(v.shape), v), k
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("m,r,drift", [(9, 37, 0.05), (3, 130, 0.0), (2, 4, 0.2), (150, 8, 0.1)])
+def test_clone_tma_path_equals_per_thread_stores(m, r, drift):
+    """ELG_CLONE_SYNC writes through TMA bulk stores from replicated shared-memory tiles by default; the per-thread
+    16-byte-store kernel (elg_set_clone_tuning(1)) must produce the same bytes, ragged heads / tails and drift included."""
+    lib = _lib.load()
+    outs = []
+    for no_bulk in (0, 1):
+        env, _ = make_rollout_env(m, r, drift=drift, seed=m)
+        o = ro.make_rollout_state(m, r, seed=20 + m)
+        ro.init_env_indices(o)
+        load_into(env, ro.snapshot(o))
+        env.drift_u = torch.rand(m * r, 3, generator=torch.Generator().manual_seed(6)).to(DEV)
+        lib.elg_set_clone_tuning(no_bulk)
+        try:
+            env._sync_main_to_rollout()
+            torch.cuda.synchronize()
+        finally:
+            lib.elg_set_clone_tuning(0)
+        outs.append({k: getattr(env, k).cpu().clone() for k in ro.snapshot(o)})
+        if no_bulk == 0:
+            ro.sync_main_to_rollout(o, drift, env.drift_u.cpu())
+            for k, v in ro.snapshot(o).items():
+                assert torch.equal(outs[0][k].view(v.shape), v), k
+    for k in outs[0]:
+        assert torch.equal(outs[0][k], outs[1][k]), k
 
 
 @pytest.mark.gpu
