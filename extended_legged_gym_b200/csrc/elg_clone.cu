@@ -120,6 +120,7 @@ struct CloneBulkPlan {
   int tile_off[ELG_MAX_CLONE_FIELDS];   // byte offset of the field's tile in dynamic shared memory (16-byte aligned)
   int row_off[ELG_MAX_CLONE_FIELDS];    // word offset of the field's staged main row
   int tiles_bytes;                      // staged rows live behind the tiles
+  int row_words;                        // staged words per main over all fields
   int debug;                            // measurement switches: 2 = build only (no stores), 4 = stores only (no build)
 };
 
@@ -137,13 +138,6 @@ elg_clone_bulk_kernel(const __grid_constant__ ElgCloneTable tb, const __grid_con
   const bool drift_on = tb.drift_field >= 0 && drift > 0.0f;
   pdl_launch_dependents();
   pdl_wait();
-  // stage the main row of every field
-  for (int f = 0; f < nf; ++f) {
-    const int rw = tb.fields[f].row_bytes >> 2;
-    const uint32_t* src = static_cast<const uint32_t*>(tb.fields[f].base) + main_row * rw;
-    for (int i = tid; i < rw; i += kCloneThreads) s_row[pl.row_off[f] + i] = src[i];
-  }
-  __syncthreads();
   auto head_words = [&](int f) {   // words of the span in front of its first 16-byte boundary
     const int rw = tb.fields[f].row_bytes >> 2;
     const uintptr_t dst = reinterpret_cast<uintptr_t>(tb.fields[f].base) + (main_row + 1) * rw * 4;
@@ -162,23 +156,26 @@ elg_clone_bulk_kernel(const __grid_constant__ ElgCloneTable tb, const __grid_con
     }
     return __float_as_uint(add_r(__uint_as_float(v), mul_r(sub_r(u, 0.5f), drift)));
   };
-  // replicated, rotated tiles of the fields that do not drift: tile[i] = row[(head + i) % rw].  Warp w builds (and later
-  // stores) fields w, w + 8, ...
-  if (!(pl.debug & 4))
-  for (int f = warp; f < nf; f += kWarps) {
-    if (drift_on && f == tb.drift_field) continue;
-    const int rw = tb.fields[f].row_bytes >> 2;
-    const uint32_t* row = s_row + pl.row_off[f];
-    uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw + pl.tile_off[f]);
-    const int tw = TR * rw;
-    int m = head_words(f) + lane;
-    while (m >= rw) m -= rw;
-    int step = 32;
-    while (step >= rw) step -= rw;
-    for (int i = lane; i < tw; i += 32) {
-      tile[i] = row[m];
-      m += step;
-      m = m >= rw ? m - rw : m;
+  // Stage the main rows and build the replicated, rotated tiles (tile[i] = row[(head + i) % rw]) in one pass without a
+  // barrier in between: staged word x of the row set belongs to ONE thread pair, which fetches it from global memory
+  // once (all loads of the CTA in flight together), keeps it in a register and writes every copy of it -- a stream of
+  // independent shared-memory stores, copy r to tile word r * rw + j - head.  Thread x + 128 h takes the copies r = h, h + 2, ...
+  for (int x0 = 0; x0 < pl.row_words; x0 += kCloneThreads / 2) {
+    const int x = x0 + (tid & (kCloneThreads / 2 - 1)), half = tid / (kCloneThreads / 2);
+    if (x < pl.row_words) {
+      int f = 0;
+      while (f + 1 < nf && pl.row_off[f + 1] <= x) ++f;
+      const int rw = tb.fields[f].row_bytes >> 2, j = x - pl.row_off[f];
+      const uint32_t v = (static_cast<const uint32_t*>(tb.fields[f].base) + main_row * rw)[j];
+      if (half == 0) s_row[x] = v;
+      if (!(pl.debug & 4) && !(drift_on && f == tb.drift_field)) {
+        uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw + pl.tile_off[f]);
+        const int tw = TR * rw;
+        int i = half * rw + j - head_words(f);
+#pragma unroll 4
+        for (int r = half; r <= TR + 3; r += 2, i += 2 * rw)   // head <= 3 words can span up to 3 one-word rows
+          if (i >= 0 && i < tw) tile[i] = v;
+      }
     }
   }
   fence_async_smem();
@@ -218,7 +215,7 @@ elg_clone_bulk_kernel(const __grid_constant__ ElgCloneTable tb, const __grid_con
       words = words < tw ? words : tw;
       words &= ~3;
       // the chunk covers span words [w0, w0 + words): rows c * TR .. c * TR + TR (the last one partially, by the head words)
-      for (int rl = warp; rl <= TR; rl += kWarps) {
+      for (int rl = warp; rl <= TR + 3; rl += kWarps) {   // (head <= 3 words: up to 3 more rows when rows are short)
         const int rr = c * TR + rl;
         for (int j = lane; j < rw; j += 32) {
           const int i = rr * rw + j - w0;
@@ -399,6 +396,7 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
           roff += table->fields[f].row_bytes / 4;
         }
         pl.tiles_bytes = toff;
+        pl.row_words = roff;
         const size_t smem = (size_t)toff + (size_t)roff * 4;
         static size_t smem_set = 0;
         if (smem > smem_set) {
