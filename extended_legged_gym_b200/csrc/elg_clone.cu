@@ -168,7 +168,7 @@ elg_clone_bulk_kernel(const __grid_constant__ ElgCloneTable tb, const __grid_con
       const int rw = tb.fields[f].row_bytes >> 2, j = x - pl.row_off[f];
       const uint32_t v = (static_cast<const uint32_t*>(tb.fields[f].base) + main_row * rw)[j];
       if (half == 0) s_row[x] = v;
-      if (!(pl.debug & 4) && !(drift_on && f == tb.drift_field)) {
+      if (!(pl.debug & 4)) {
         uint32_t* tile = reinterpret_cast<uint32_t*>(smem_raw + pl.tile_off[f]);
         const int tw = TR * rw;
         int i = half * rw + j - head_words(f);
@@ -198,7 +198,8 @@ elg_clone_bulk_kernel(const __grid_constant__ ElgCloneTable tb, const __grid_con
     }
     bulk_commit();
   }
-  // the drifting field: one freshly built tile per chunk; lanes over the words of a row, warps over the rows of the chunk
+  // the drifting field: its tile was built like the others; per chunk only the three position words of every row change.
+  // One thread per (row of the chunk, component): dense Philox / one load each, written over the tile in place.
   if (drift_on) {
     const int f = tb.drift_field;
     const int rw = tb.fields[f].row_bytes >> 2;
@@ -214,13 +215,11 @@ elg_clone_bulk_kernel(const __grid_constant__ ElgCloneTable tb, const __grid_con
       int words = span - w0;
       words = words < tw ? words : tw;
       words &= ~3;
-      // the chunk covers span words [w0, w0 + words): rows c * TR .. c * TR + TR (the last one partially, by the head words)
-      for (int rl = warp; rl <= TR + 3; rl += kWarps) {   // (head <= 3 words: up to 3 more rows when rows are short)
-        const int rr = c * TR + rl;
-        for (int j = lane; j < rw; j += 32) {
-          const int i = rr * rw + j - w0;
-          if (rr < R && i >= 0 && i < words) tile[i] = j < 3 ? drift_word(rr, j, row[j]) : row[j];
-        }
+      // the chunk covers span words [w0, w0 + words): rows c * TR .. c * TR + TR + (head words' worth)
+      for (int q = tid; q < 3 * (TR + 4); q += kCloneThreads) {
+        const int rl = q / 3, j = q - 3 * rl;      // (constant divisor)
+        const int rr = c * TR + rl, i = rr * rw + j - w0;
+        if (rr < R && i >= 0 && i < words) tile[i] = drift_word(rr, j, row[j]);
       }
       fence_async_smem();
       __syncthreads();
@@ -387,7 +386,7 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
       if (tr >= 4) {
         elg::CloneBulkPlan pl{};
         pl.tile_rows = tr;
-        pl.debug = g_clone_tune;
+        pl.debug = g_clone_tune & 0xff;
         int toff = 0, roff = 0;
         for (int f = 0; f < table->num_fields; ++f) {
           pl.tile_off[f] = toff;
@@ -405,7 +404,10 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
           smem_set = smem;
         }
         const long long nchunk = ((long long)table->rollouts_per_main + tr - 1) / tr;
-        long long sl = (2LL * sms + table->num_main - 1) / table->num_main;   // ~2 CTAs per SM
+        // one chunk per CTA and field while that keeps the grid below ~8 CTAs per SM (measured, scripts/clone_ab.py: at
+        // 64 mains x 512 rollouts 8 slices take 6.6 us, 5 slices 8.5 us, 1 slice 7.9 us)
+        long long sl = (8LL * sms + table->num_main - 1) / table->num_main;
+        if ((g_clone_tune >> 8) > 0) sl = g_clone_tune >> 8;   // measurement override
         if (sl > nchunk) sl = nchunk;
         if (sl < 1) sl = 1;
         cudaLaunchConfig_t cfg{};

@@ -17,7 +17,7 @@ for mains, rollouts, drift in ((64, 512, 0.0), (64, 512, 0.1), (512, 64, 0.0)):
     cfg.domain_rand.rollout_envs_sync_pos_drift = drift
     env = RobotBatchRollout(cfg, None, SyntheticSim(cfg, n, dev, spec=spec, height_samples=hf, state=st), dev, True)
     env.set_env_state(st)
-    for no_bulk in (0, 1, 2, 4, 6):
+    for no_bulk in (0, 1, 1 << 8, 2 << 8, 3 << 8, 4 << 8, 8 << 8):
         lib.elg_set_clone_tuning(no_bulk)
         gs = torch.cuda.Stream(device=dev)
         gr = torch.cuda.CUDAGraph()
@@ -34,6 +34,6 @@ for mains, rollouts, drift in ((64, 512, 0.0), (64, 512, 0.1), (512, 64, 0.0)):
             e1.record(gs); gs.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 200
         b = 388 * mains * rollouts
-        print(f"{mains:5d} mains x {rollouts:4d} rollouts drift={drift}: { {0: 'TMA bulk', 1: 'per-thread', 2: 'TMA: build only', 4: 'TMA: stores only', 6: 'TMA: neither'}[no_bulk]:18s} {us:7.2f} us  {b / us / 1e3:8.1f} GB/s written", flush=True)
+        print(f"{mains:5d} mains x {rollouts:4d} rollouts drift={drift}: { {0: 'TMA bulk', 1: 'per-thread'}.get(no_bulk, 'TMA slices=%d' % (no_bulk >> 8)):18s} {us:7.2f} us  {b / us / 1e3:8.1f} GB/s written", flush=True)
     lib.elg_set_clone_tuning(0)
     del env
