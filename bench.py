@@ -302,9 +302,15 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     dist = None
+    saved_stdout = None
     if world > 1:
         import torch.distributed as dist
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")     # NCCL's version / debug lines must not land in the JSON stream
+        # NCCL writes its version / debug lines to fd 1; they must not land in the JSON stream: stdout points at stderr
+        # until the one result line is due
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(dev))
     W = max(args.warmup, 3)
     K = args.steps
@@ -461,10 +467,14 @@ def main():
         v, med, tot = cpu_reference_run(case, common, n_envs, 20, 3, threads)
         line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                                 "sample": f"full workload: {n_envs} envs x 20 steps (median step {med * 1e3:.1f} ms) of oracle/legged_oracle.py hot_step"}
-    if rank == 0:
-        print(json.dumps(line))
     if dist:
+        dist.barrier()
         dist.destroy_process_group()
+        sys.stdout.flush()
+        os.dup2(saved_stdout, 1)
+        os.close(saved_stdout)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
 
 
 if __name__ == "__main__":
