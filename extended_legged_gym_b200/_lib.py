@@ -71,6 +71,18 @@ class ElgStepBuffers(C.Structure):
 
 MAX_CLONE_FIELDS = 24
 CLONE_SYNC, CLONE_CACHE, CLONE_RESTORE = 0, 1, 2
+# actuator-network weight blob (ELG_ACTNET_* in include/elg_b200.h)
+ACTNET_IN_SCALE, ACTNET_OUT_SCALE, ACTNET_W_IH0 = 0, 2, 4
+ACTNET_W_HH0 = ACTNET_W_IH0 + 64
+ACTNET_B_IH0 = ACTNET_W_HH0 + 256
+ACTNET_B_HH0 = ACTNET_B_IH0 + 32
+ACTNET_W_IH1 = ACTNET_B_HH0 + 32
+ACTNET_W_HH1 = ACTNET_W_IH1 + 256
+ACTNET_B_IH1 = ACTNET_W_HH1 + 256
+ACTNET_B_HH1 = ACTNET_B_IH1 + 32
+ACTNET_W_LIN = ACTNET_B_HH1 + 32
+ACTNET_B_LIN = ACTNET_W_LIN + 8
+ACTNET_WORDS = ACTNET_B_LIN + 4
 
 
 class ElgCloneField(C.Structure):
@@ -146,6 +158,9 @@ def load() -> C.CDLL:
     lib.elg_clone_rows.argtypes = [C.POINTER(ElgCloneTable), C.c_int, C.c_float, vp, C.c_uint64, C.c_uint64, vp]
     lib.elg_set_step_debug.argtypes = [vp]
     lib.elg_set_clone_tuning.argtypes = [C.c_int]
+    if lib.elg_actuator_net_words() != ACTNET_WORDS:
+        raise ElgError(f"ABI mismatch: elg_actuator_net_words() = {lib.elg_actuator_net_words()}, python mirror = {ACTNET_WORDS}")
+    lib.elg_actuator_net_torques.argtypes = [C.POINTER(ElgDims), vp, C.c_float] + [vp] * 7
     lib.elg_mesh_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(vp)]
     lib.elg_mesh_free.argtypes = [vp]
     lib.elg_mesh_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]

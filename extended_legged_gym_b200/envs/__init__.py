@@ -2,14 +2,15 @@
 from .base.legged_robot_config import LeggedRobotCfg, LeggedRobotCfgPPO
 from .base.legged_robot import LeggedRobot
 from .anymal_c.anymal_c_config import AnymalCRoughCfg, AnymalCRoughCfgPPO, AnymalCFlatCfg, AnymalCFlatCfgPPO
+from .anymal_c.anymal import Anymal
 from .a1.a1_config import A1RoughCfg, A1RoughCfgPPO
 from .go2.go2_config import Go2RoughCfg, Go2RoughCfgPPO
 from .batch_rollout.robot_batch_rollout import RobotBatchRollout
 from .batch_rollout.robot_batch_rollout_config import RobotBatchRolloutCfg, RobotBatchRolloutCfgPPO
 
 TASKS = {
-    "anymal_c_rough": (LeggedRobot, AnymalCRoughCfg, AnymalCRoughCfgPPO),
-    "anymal_c_flat": (LeggedRobot, AnymalCFlatCfg, AnymalCFlatCfgPPO),
+    "anymal_c_rough": (Anymal, AnymalCRoughCfg, AnymalCRoughCfgPPO),      # legged_gym/envs/__init__.py registers Anymal for both
+    "anymal_c_flat": (Anymal, AnymalCFlatCfg, AnymalCFlatCfgPPO),
     "a1": (LeggedRobot, A1RoughCfg, A1RoughCfgPPO),
     "go2_rough": (LeggedRobot, Go2RoughCfg, Go2RoughCfgPPO),
 }

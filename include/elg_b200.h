@@ -329,6 +329,35 @@ int elg_sdf_query(const ElgMesh* mesh, const float* points, int64_t num_points, 
 double elg_mesh_mean_edge(const ElgMesh* mesh);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Actuator-network torques (envs/anymal_c/anymal.py:93-105, the default torque path of the anymal_c_* configs:
+ * control.use_actuator_network, mixed_terrains/anymal_c_rough_config.py:68-69).  The TorchScript module
+ * resources/actuator_nets/anydrive_v3_lstm.pt is `LSTMsea`: x * in_scale -> 2-layer LSTM(input 2, hidden 8, batch_first, one
+ * time step) -> Linear(8, 1) -> * out_scale, applied to every (env, dof) row with
+ *   x = (actions * action_scale + default_dof_pos - dof_pos, dof_vel),   gates in torch order (i, f, g, o).
+ * `weights` is a device blob of ELG_ACTNET_WORDS floats in the layout below (host side: Anymal._pack_actuator_net);
+ * hidden / cell are the [2, N*D, 8] state tensors (sea_hidden_state / sea_cell_state), updated in place. */
+#define ELG_ACTNET_HIDDEN 8
+#define ELG_ACTNET_GATES 32
+enum {
+  ELG_ACTNET_IN_SCALE = 0,                                   /* [2]                      */
+  ELG_ACTNET_OUT_SCALE = 2,                                  /* [1] (+ 1 pad)            */
+  ELG_ACTNET_W_IH0 = 4,                                      /* [32, 2]  weight_ih_l0    */
+  ELG_ACTNET_W_HH0 = ELG_ACTNET_W_IH0 + 64,                  /* [32, 8]  weight_hh_l0    */
+  ELG_ACTNET_B_IH0 = ELG_ACTNET_W_HH0 + 256,                 /* [32]                     */
+  ELG_ACTNET_B_HH0 = ELG_ACTNET_B_IH0 + 32,                  /* [32]                     */
+  ELG_ACTNET_W_IH1 = ELG_ACTNET_B_HH0 + 32,                  /* [32, 8]  weight_ih_l1    */
+  ELG_ACTNET_W_HH1 = ELG_ACTNET_W_IH1 + 256,                 /* [32, 8]  weight_hh_l1    */
+  ELG_ACTNET_B_IH1 = ELG_ACTNET_W_HH1 + 256,                 /* [32]                     */
+  ELG_ACTNET_B_HH1 = ELG_ACTNET_B_IH1 + 32,                  /* [32]                     */
+  ELG_ACTNET_W_LIN = ELG_ACTNET_B_HH1 + 32,                  /* [8]      linear.weight   */
+  ELG_ACTNET_B_LIN = ELG_ACTNET_W_LIN + 8,                   /* [1] (+ 3 pad)            */
+  ELG_ACTNET_WORDS = ELG_ACTNET_B_LIN + 4
+};
+int elg_actuator_net_words(void);
+int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float action_scale, const float* actions, const float* dof_state,
+                             const float* default_dof_pos, float* hidden, float* cell, float* torques, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * MPPI cost-weighted control update, batched over the main envs (in-tree statement: legged_gym/tests/score_sampling/
  * cmp_mppi_wbfo.py:216-233; the production optimiser is the external traj_sampling package, call sites
  * envs/batch_rollout/robot_traj_grad_sampling.py:62-69, :222-280).  Split in three so that the sample dimension can be
