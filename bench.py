@@ -270,6 +270,28 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False):
                     "frac_of_hbm_peak": row * mains * rollouts / sec / 1e9 / peak,
                     "kernel": "elg_clone_bulk_kernel (replicated shared-memory tiles, cp.async.bulk stores)",
                     "note": "kernel figure from a CUDA graph of 50 syncs; the 12.7 MB working set is L2 resident"}
+    # the rollout-mode step over all 64 x (1 + rollouts) rows (post_physics_step_rollout, one launch per horizon step of the MPPI loop)
+    env.noise_u = None
+    gs = torch.cuda.Stream(device=dev)
+    gr = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(gs):
+        env.post_physics_step_rollout()
+        gs.synchronize()
+        with torch.cuda.graph(gr, stream=gs):
+            for _ in range(20):
+                env.post_physics_step_rollout()
+        gr.replay()
+        gs.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(gs)
+        for _ in range(4):
+            gr.replay()
+        e1.record(gs)
+        gs.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / 80
+    out["rollout_step"] = {"workload": f"post_physics_step_rollout over {n} envs ({mains} mains x (1 + {rollouts}) rows), anymal_c_rough",
+                           "us_per_step": sec * 1e6, "env_steps_per_s": n / sec,
+                           "note": "lean kernel in rollout mode (measured heights are an input, no termination / episode sums); CUDA graph of 20 steps"}
     del env
     # ---- actuator-network torques (Anymal._compute_torques, the default torque path of the anymal_c configs): 4096 envs x 12 dofs
     from extended_legged_gym_b200.envs import Anymal

@@ -98,7 +98,10 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   constexpr int D = 12, F = 4, head = 12 + 3 * D;
   const float clip_obs = pr.clip_observations;
   const bool need_hsum = on(pr, ELG_REW_BASE_HEIGHT) && H > 0;
-  const bool heights_live = H > 0 && !pr.terrain_is_plane;
+  // rollout mode (post_physics_step_rollout, batch_rollout/robot_batch_rollout.py:763-817): no episode counter, heading command,
+  // height scan (measured_heights is an input), termination or episode sums
+  const bool rollout = pr.rollout_mode != 0;
+  const bool heights_live = H > 0 && !pr.terrain_is_plane && !rollout;
   const bool gait = bf.gait_idx != nullptr && bf.gait_prev_foot_z != nullptr;
   const bool dbg_on = L.dbg != nullptr && blockIdx.x == 0;
 #define STAMP(i, w) if (dbg_on && warp == (w) && lane == 0) L.dbg[i] = clock64();
@@ -327,7 +330,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       // ---------------- yaw frame for the terrain scan, episode counter, heading command, command observations
       const float* rs = s_root + e * 13;
       const Quat q = {rs[3], rs[4], rs[5], rs[6]};
-      if (H > 0) {
+      if (H > 0 && !rollout) {
         // normalize((0,0,qz,qw)): torch's 4-wide norm is the plain sequential sum (no FMA), clamp(min=1e-9)
         float nrm = __fsqrt_rn(add_r(mul_r(q.z, q.z), mul_r(q.w, q.w)));
         nrm = fmaxf(nrm, 1e-9f);
@@ -337,10 +340,10 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         }
       }
       int64_t* const s_ep = reinterpret_cast<int64_t*>(smem_raw + L.ep);
-      if (live) s_ep[e] += 1;   // episode counter (legged_robot.py:122)
+      if (live && !rollout) s_ep[e] += 1;   // episode counter (legged_robot.py:122)
       float* cmd = SM_F(L.cmd) + e * C;
       float cmd2 = cmd[2];
-      if (pr.heading_command) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
+      if (pr.heading_command && !rollout) {   // (legged_robot.py:394-398); forward = quat_apply(q, (1,0,0))
         const float fx = 1.0f + (q.y * (-2.0f * q.y) - q.z * (2.0f * q.z));
         const float fy = q.w * (2.0f * q.z) + (q.z * 0.0f - q.x * (-2.0f * q.y));
         const float heading = atan2f(fy, fx);
@@ -431,11 +434,15 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     const int slot = warp;
     float* const orow = s_obs + slot * O;
     if (H > 0) {
-      const float4 yf = s_yaw[slot];
-      const float rootz = s_yz[slot];
+      float* const mh = SM_F(L.mh) + slot * H;
+      const float4 yf = rollout ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : s_yaw[slot];
+      const float rootz = rollout ? s_root[slot * 13 + 2] : s_yz[slot];
       const float zc = sub_r(rootz, 0.5f);
       float hv[kNJ];
-      if (heights_live) {
+      if (rollout) {
+#pragma unroll
+        for (int j = 0; j < kNJ; ++j) hv[j] = mh[min(lane + 32 * j, H - 1)];   // the heights the main step measured (bulk-copied in)
+      } else if (heights_live) {
         const float zz = yf.x, ww = yf.y;
         const f32x2 rr = pack2(L.r_hscale, L.r_hscale);
         const f32x2 nc = pack2(-pr.horizontal_scale, -pr.horizontal_scale);
@@ -475,14 +482,13 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         for (int j = 0; j < kNJ; ++j) hv[j] = 0.0f;   // plane terrain (legged_robot.py:913-914)
       }
       STAMP(5, 0)
-      float* const mh = SM_F(L.mh) + slot * H;
       float hsum = 0.0f;
 #pragma unroll
       for (int j = 0; j < kNJ; ++j) {
         const int p = lane + 32 * j;
         if (j < kNJ - 1 || p < H) {   // H > 32 (kNJ - 1): only the last round is ragged
           const float h = hv[j];
-          mh[p] = h;
+          if (!rollout) mh[p] = h;
           if (need_hsum) hsum += sub_r(rootz, h);
           float v = mul_r(fminf(fmaxf(sub_r(zc, h), -1.0f), 1.0f), pr.obs_scale_height);
           if (kNoise != ELG_NOISE_OFF) v = v + nz[j];
@@ -524,13 +530,19 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     const float* cmd = SM_F(L.cmd) + e * C;
     const float cmd0 = cmd[0], cmd1 = cmd[1], cmd2 = cmd[2], cmd3 = C > 3 ? cmd[3] : 0.0f;
     const int PT = dm.num_penalised + dm.num_termination;
-    const int64_t ep = reinterpret_cast<const int64_t*>(smem_raw + L.ep)[e];
-    const bool contact_term = (PART(kPTermHit, e) + PART(kPTermHit + 1, e) + PART(kPTermHit + 2, e)) != 0.0f;
-    const bool time_out = ep > pr.max_episode_length;
-    const bool reset = contact_term | time_out;
-    if (live) {
-      bf.reset_buf[genv] = reset ? 1 : 0;
-      bf.time_out_buf[genv] = time_out ? 1 : 0;
+    bool reset, time_out;
+    if (rollout) {   // no check_termination in the rollout step: the termination term reads the flags as they are
+      reset = bf.reset_buf[genv] != 0;
+      time_out = bf.time_out_buf[genv] != 0;
+    } else {
+      const int64_t ep = reinterpret_cast<const int64_t*>(smem_raw + L.ep)[e];
+      const bool contact_term = (PART(kPTermHit, e) + PART(kPTermHit + 1, e) + PART(kPTermHit + 2, e)) != 0.0f;
+      time_out = ep > pr.max_episode_length;
+      reset = contact_term | time_out;
+      if (live) {
+        bf.reset_buf[genv] = reset ? 1 : 0;
+        bf.time_out_buf[genv] = time_out ? 1 : 0;
+      }
     }
     const float cmd_xy = norm2_tz(cmd0, cmd1);
     auto dsum = [&](int k) {
@@ -554,7 +566,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
 #define TERM(T, VALUE)                                   \
     if (on(pr, T)) {                                       \
       const float r_ = (VALUE) * pr.reward_scales[T];      \
-      if (live) s_sums[ti * cap + e] += r_;                \
+      if (live && !rollout) s_sums[ti * cap + e] += r_;    \
       ++ti;                                                \
       if (T == ELG_REW_TERMINATION) r_term = r_;           \
       else total += r_;                                    \
@@ -655,10 +667,12 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   const int N = dims->num_envs, D = dims->num_dof, F = dims->num_feet, B = dims->num_bodies;
   const int H = dims->num_height_points, O = dims->num_obs, C = dims->num_commands;
   const int head = 12 + 3 * D;
-  if (D != 12 || F != 4 || phase != ELG_PHASE_FUSED || prm->rollout_mode != 0) return 0;
+  const bool rollout = prm->rollout_mode != 0;
+  const uint32_t rollout_phase = ELG_PHASE_DERIVE | ELG_PHASE_REWARD | ELG_PHASE_OBS | ELG_PHASE_HISTORY;   // post_physics_step_rollout
+  if (D != 12 || F != 4 || phase != (rollout ? rollout_phase : ELG_PHASE_FUSED)) return 0;
   if (N % 4 != 0 || O != head + H || prm->height_points_env_stride != 0) return 0;
   if (H != 0 && (H <= 32 * (kNJ - 1) || H > 32 * kNJ)) return 0;   // the scan is unrolled for ceil(H / 32) == kNJ
-  if (H > 0 && !prm->terrain_is_plane && buf->height_field_min == nullptr) return 0;
+  if (H > 0 && !rollout && !prm->terrain_is_plane && buf->height_field_min == nullptr) return 0;
   if (C > 8 || B > 64) return 0;
   const bool gait = buf->gait_idx && buf->gait_prev_foot_z;
   const bool air_on = (prm->reward_mask >> ELG_REW_FEET_AIR_TIME) & 1u;
@@ -758,15 +772,17 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   in(buf->feet_air_time, L.air, 16);
   in(buf->feet_contact_time, L.con, 16);
   in(buf->last_contacts, L.lc, 4);
-  in(buf->episode_length_buf, L.ep, 8);
+  if (!rollout) in(buf->episode_length_buf, L.ep, 8);
+  if (rollout && H > 0) in(buf->measured_heights, L.mh, 4 * H);
   if (gait) {
     in(buf->gait_idx, L.gidx, 4);
     in(buf->gait_prev_foot_z, L.gprev, 16);
   }
-  for (int ti = 0; ti < nt; ++ti) in(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
+  if (!rollout)
+    for (int ti = 0; ti < nt; ++ti) in(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
 
   out(buf->obs_buf, L.obs, 4 * O);
-  if (H > 0) out(buf->measured_heights, L.mh, 4 * H);
+  if (H > 0 && !rollout) out(buf->measured_heights, L.mh, 4 * H);
   out(buf->base_lin_vel, L.vec5 + 0 * v3, 12);
   out(buf->base_ang_vel, L.vec5 + 1 * v3, 12);
   out(buf->projected_gravity, L.vec5 + 2 * v3, 12);
@@ -774,14 +790,15 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   out(buf->base_ang_acc, L.vec5 + 4 * v3, 12);
   out(buf->foot_positions, L.fpos, 48);
   out(buf->foot_velocities, L.fvel, 48);
-  if (prm->heading_command) out(buf->commands, L.cmd, 4 * C);
-  out(buf->episode_length_buf, L.ep, 8);
+  if (prm->heading_command && !rollout) out(buf->commands, L.cmd, 4 * C);
+  if (!rollout) out(buf->episode_length_buf, L.ep, 8);
   if (air_on) {
     out(buf->feet_air_time, L.air, 16);
     out(buf->feet_contact_time, L.con, 16);
     out(buf->last_contacts, L.lc, 4);
   }
-  for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
+  if (!rollout)
+    for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
   out(buf->rew_buf, L.rew, 4);
   if (gait) {
     out(buf->gait_idx, L.gidx, 4);

@@ -612,6 +612,23 @@ class LeggedOracle:
         if self.use_gait_scheduler:
             self.gait_step()
 
+    def post_physics_step_rollout(self, noise_u: Optional[Tensor] = None):
+        """RobotBatchRollout.post_physics_step_rollout (envs/batch_rollout/robot_batch_rollout.py:763-817) evaluated on every
+        row (the caller restores the main rows afterwards): base-frame state and feet, compute_reward_rollout (:969-985:
+        the registry WITHOUT episode sums), observations, histories -- no episode counter, no callback (commands,
+        heights: ``_post_physics_step_callback_rollout`` is empty), no termination check (the termination term reads the
+        flags as they are)."""
+        ep, counter = self.episode_length_buf.clone(), self.common_step_counter
+        self.derive()
+        self.episode_length_buf, self.common_step_counter = ep, counter
+        sums = {k: v.clone() for k, v in self.episode_sums.items()}
+        self.compute_reward()
+        self.episode_sums = sums
+        self.compute_observations(noise_u)
+        self.last_actions[:] = self.actions[:]
+        self.last_dof_vel[:] = self.dof_vel[:]
+        self.last_root_vel[:] = self.root_states[:, 7:13]
+
     def step_no_physics(self, actions: Tensor, noise_u: Optional[Tensor] = None, do_reset: bool = True):
         """step() minus PhysX: clip, one torque evaluation, post-physics, obs clip (legged_robot.py:87-111)."""
         ca = self.cfg.normalization.clip_actions

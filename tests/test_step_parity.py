@@ -145,6 +145,39 @@ def test_fused_equals_split_sections():
             assert torch.equal(a, b), k
 
 
+@pytest.mark.parametrize("case,n", [("anymal_c_rough", 1000), ("go2_all_terms_heading", 1028), ("a1_all_terms", 1001), ("anymal_c_flat", 512)])
+def test_rollout_mode_step_matches_oracle(case, n):
+    """post_physics_step_rollout (robot_batch_rollout.py:763-817): one launch with ELG_PHASE_DERIVE | REWARD | OBS | HISTORY and
+    rollout_mode -- measured heights, reset / time-out flags, commands and the episode counter are inputs and stay untouched,
+    episode sums do not accumulate.  n % 4 == 0 takes the lean kernel, 1001 the generic one."""
+    cfg, spec, st = common.make_case_state(case, n, seed=21)
+    hf = synthetic.make_height_field(seed=0)
+    ora = LeggedOracle(common.CASES[case][0](), spec, {k: v.clone() for k, v in st.items()}, hf)
+    env = make_env(cfg, spec, st, hf, ora)
+    g = torch.Generator().manual_seed(3)
+    flags = torch.rand(n, generator=g) < 0.1
+    touts = flags & (torch.rand(n, generator=g) < 0.5)
+    ora.reset_buf, ora.time_out_buf = flags.clone(), touts.clone()
+    env._reset_bool.copy_(flags.to(DEV))
+    env.time_out_buf.copy_(touts.to(DEV))
+    env.reset_buf = env._reset_bool
+    if ora.measure_heights:
+        mh = torch.rand(n, env.num_height_points, generator=g) - 0.5
+        ora.measured_heights = mh.clone()
+        env.measured_heights.copy_(mh.to(DEV))
+    sums_before = {k: v.clone() for k, v in env.episode_sums.items()}
+    u = torch.rand(n, env.num_obs, generator=g)
+    ora.torques = ora.compute_torques(ora.actions).view(ora.torques.shape)
+    ora.post_physics_step_rollout(noise_u=u)
+    env.noise_u = u.to(DEV)
+    env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+    env._launch(_lib.PHASE_DERIVE | _lib.PHASE_REWARD | _lib.PHASE_OBS | _lib.PHASE_HISTORY, rollout=True)
+    torch.cuda.synchronize()
+    common.assert_state_close(common.snapshot(env), common.snapshot(ora), what=f"rollout step {case}")
+    for k, v in sums_before.items():
+        assert torch.equal(env.episode_sums[k], v), f"episode sum {k} moved in rollout mode"
+
+
 def test_user_defined_reward_term_and_override():
     """A subclass adds a Python term and overrides a stock one: both are honoured (registry API)."""
     from extended_legged_gym_b200.envs import LeggedRobot
