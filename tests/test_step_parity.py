@@ -116,6 +116,28 @@ def test_terrain_cells_bit_exact():
     assert torch.equal(env._get_heights().cpu(), want)
 
 
+@pytest.mark.parametrize("n", [4096, 4099])
+def test_fused_step_heights_bit_exact(n):
+    """The height scan inside the fused step (lean kernel for n % 4 == 0, generic otherwise) lands in exactly the reference's
+    terrain cells: measured_heights equal the oracle's bit for bit, robots outside the map and on its border included
+    (every rounding of the cell chain is kept -- see madd2_unfused in csrc/elg_async.cuh)."""
+    cfg, spec, st = common.make_case_state("anymal_c_rough", n, seed=6)
+    st["root_states"][:8, 0] = torch.tensor([-30.0, -25.0, -24.95, 64.9, 65.0, 70.0, 1e6, -1e6])
+    st["root_states"][8:12, 1] = torch.tensor([-26.0, 64.95, 65.05, 3e9])
+    # robots sitting exactly on cell boundaries of the 0.1 m grid
+    st["root_states"][12:512, 0] = (torch.arange(500) * 0.1 + 1.0)
+    st["root_states"][12:512, 1] = (torch.arange(500) * 0.05 + 3.0)
+    hf = synthetic.make_height_field(seed=0)
+    ora = LeggedOracle(cfg, spec, {k: v.clone() for k, v in st.items()}, hf)
+    want = ora.get_heights()
+    env = make_env(cfg, spec, st, hf, ora)
+    env.noise_u = torch.rand(n, env.num_obs, generator=torch.Generator().manual_seed(2)).to(DEV)
+    env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+    env._launch(_lib.PHASE_FUSED)
+    torch.cuda.synchronize()
+    assert torch.equal(env.measured_heights.cpu(), want), "fused-step heights differ from the oracle's cells"
+
+
 def test_fused_equals_split_sections():
     """ONE fused launch == derive | termination | reward | obs | history launched one by one."""
     case, n = "go2_all_terms_heading", 1000
