@@ -48,7 +48,8 @@ struct FastPlan {
   int n_in, n_out, nterms;
   // staged per-env arrays, byte offsets into dynamic shared memory
   int root, dof, act, lact, ldv, tq, cf, lrv, vec5, cmd, air, con, lc, ep, gidx, gprev, fpos, fvel, sums, rew, mh, obs;
-  int part, yaw;   // partial-sum table [rows][32], yaw frames [cap] x (float4 + float)
+  int buf_bytes;   // one staging buffer (everything above); two of them when a CTA handles more than one chunk
+  int part, yaw;   // partial-sum table [rows][32], yaw frames [cap] x (float4 + float): one copy, behind the buffers
   int bytes;
   float r_hscale;  // RN(1 / horizontal_scale)
   float pen_sq, term_sq;   // largest sums of squares whose IEEE sqrt is still <= 0.1 / <= 1.0 (contact thresholds)
@@ -79,21 +80,17 @@ enum {
 __device__ __forceinline__ bool on(const ElgStepParams& pr, int t) { return (pr.reward_mask >> t) & 1u; }
 
 // kNoise: ElgNoiseMode, kClip: clip_observations > 0 -- compile-time so that the per-point code carries no mode tests
-template <int kNoise, bool kClip>
+// kLoop: persistent form (a CTA walks over several chunks, double-buffered staging); false: one chunk per CTA, no loop state
+template <int kNoise, bool kClip, bool kLoop>
 __global__ void __launch_bounds__(32 * (kFastMaxCap + kTaskWarps), 1)
 elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgStepParams pr,
                      const __grid_constant__ ElgStepBuffers bf, const __grid_constant__ FastPlan L) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t s_bar;
+  __shared__ __align__(8) uint64_t s_bar[2];   // one mbarrier per staging buffer
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int nwarps = blockDim.x >> 5;
   const int cap = L.cap;
-  const int chunk = blockIdx.x;
-  const int q_lo = chunk * L.quads_base + min(chunk, L.quads_rem);
-  const int q_n = L.quads_base + (chunk < L.quads_rem ? 1 : 0);
-  const int env0 = q_lo * 4;
-  const int n = min(dm.num_envs, (q_lo + q_n) * 4) - env0;   // multiple of 4 (host guarantees N % 4 == 0)
   const int H = dm.num_height_points, O = dm.num_obs, B = dm.num_bodies, C = dm.num_commands;
   constexpr int D = 12, F = 4, head = 12 + 3 * D;
   const float clip_obs = pr.clip_observations;
@@ -106,8 +103,17 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   const bool dbg_on = L.dbg != nullptr && blockIdx.x == 0;
 #define STAMP(i, w) if (dbg_on && warp == (w) && lane == 0) L.dbg[i] = clock64();
   STAMP(0, 0)
+  auto chunk_range = [&](int chunk, int& env0, int& n) {   // whole quads of envs, balanced to within one quad
+    const int q_lo = chunk * L.quads_base + min(chunk, L.quads_rem);
+    const int q_n = L.quads_base + (chunk < L.quads_rem ? 1 : 0);
+    env0 = q_lo * 4;
+    n = min(dm.num_envs, (q_lo + q_n) * 4) - env0;   // multiple of 4 (host guarantees N % 4 == 0)
+  };
 
-  if (tid == 0) mbar_init(&s_bar, L.n_in);
+  if (tid == 0) {
+    mbar_init(&s_bar[0], L.n_in);
+    mbar_init(&s_bar[1], L.n_in);
+  }
   pdl_launch_dependents();
   // the copy-table entries this warp will issue: fetched before the wait so that the constant-bank miss is off the load path
   FastCopy my_in = L.in[warp < L.n_in ? warp : 0];
@@ -116,21 +122,53 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   pdl_wait();   // nothing above reads or writes global memory
   STAMP(1, 0)
 
-  // ---- TMA loads: lane 0 of warp w issues copy-table entries w, w + W, ...
-  if (lane == 0) {
-    for (int i = warp; i < L.n_in; i += nwarps) {
-      const FastCopy d = i == warp ? my_in : L.in[i];
-      const uint32_t bytes = (uint32_t)(n * d.bpe);
-      mbar_expect_tx(&s_bar, bytes);
-      bulk_g2s(smem_raw + d.soff, static_cast<const uint8_t*>(d.g) + (size_t)env0 * d.bpe, bytes, &s_bar);
+  // ---- TMA loads of one chunk into staging buffer b: lane 0 of warp w issues copy-table entries w, w + W, ...
+  auto issue_loads = [&](int chunk, int b) {
+    if (lane == 0) {
+      int env0, n;
+      chunk_range(chunk, env0, n);
+      for (int i = warp; i < L.n_in; i += nwarps) {
+        const FastCopy d = i == warp ? my_in : L.in[i];
+        const uint32_t bytes = (uint32_t)(n * d.bpe);
+        mbar_expect_tx(&s_bar[b], bytes);
+        bulk_g2s(smem_raw + b * L.buf_bytes + d.soff, static_cast<const uint8_t*>(d.g) + (size_t)env0 * d.bpe, bytes, &s_bar[b]);
+      }
     }
-  }
+  };
+  issue_loads(blockIdx.x, 0);
 
-#define SM_F(off) reinterpret_cast<float*>(smem_raw + (off))
-  float* const s_part = SM_F(L.part);
+  float* const s_part = reinterpret_cast<float*>(smem_raw + L.part);
 #define PART(r, e) s_part[(r) * 32 + (e)]
   float4* const s_yaw = reinterpret_cast<float4*>(smem_raw + L.yaw);   // (zz, ww, X, Y)
-  float* const s_yz = SM_F(L.yaw + cap * 16);                          // Z
+  float* const s_yz = reinterpret_cast<float*>(smem_raw + L.yaw + cap * 16);   // Z
+
+  // this lane's height points p = lane + 32 j: registers for the whole kernel
+  float gx[kNJ], gy[kNJ];
+  const int p_last = min(lane + 32 * (kNJ - 1), H - 1);   // H > 32 (kNJ - 1): only the last round is ragged, its surplus lanes shadow point H - 1
+  if (warp < cap && heights_live) {
+    const float* hp = bf.height_points + 3 * lane;
+#pragma unroll
+    for (int j = 0; j < kNJ - 1; ++j) {
+      gx[j] = __ldg(hp + 96 * j);
+      gy[j] = __ldg(hp + 96 * j + 1);
+    }
+    gx[kNJ - 1] = __ldg(bf.height_points + 3 * p_last);
+    gy[kNJ - 1] = __ldg(bf.height_points + 3 * p_last + 1);
+  }
+
+  // =========================================================================================================
+  // chunks of this CTA: staging buffer it & 1; the loads of the next chunk go out behind barrier B1 of the current one
+  // and land under its terrain scan, the stores of the previous chunk drain under the current phase A
+  // =========================================================================================================
+  bool stores_pending = false;   // (lane 0 of the warps that issue stores)
+#pragma unroll 1
+  for (int it = 0, chunk = blockIdx.x; kLoop ? chunk < L.nchunks : it < 1; ++it, chunk += gridDim.x) {
+  const int bsel = kLoop ? (it & 1) : 0;
+  const uint32_t parity = kLoop ? ((uint32_t)(it >> 1) & 1u) : 0u;
+  uint8_t* const sbuf = smem_raw + bsel * L.buf_bytes;
+  int env0, n;
+  chunk_range(chunk, env0, n);
+#define SM_F(off) reinterpret_cast<float*>(sbuf + (off))
   float* const s_obs = SM_F(L.obs);
   const float* const s_root = SM_F(L.root);
   const float* const s_cf = SM_F(L.cf);
@@ -140,20 +178,9 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   // Philox: 16-bit samples, 8 per 128-bit block; point j uses sample j, head entry k = lane + 32 m sample nj + m of
   // block 1 of (env, lane) (elg_common.cuh).
   const bool row_warp = warp < n;
-  float gx[kNJ], gy[kNJ], nz[kNJ], nzh[2];
+  float nz[kNJ], nzh[2];
   if (row_warp) {
     const int env = env0 + warp;
-    const int p_last = min(lane + 32 * (kNJ - 1), H - 1);   // H > 32 (kNJ - 1): only the last round is ragged, its surplus lanes shadow point H - 1
-    if (heights_live) {
-      const float* hp = bf.height_points + 3 * lane;
-#pragma unroll
-      for (int j = 0; j < kNJ - 1; ++j) {
-        gx[j] = __ldg(hp + 96 * j);
-        gy[j] = __ldg(hp + 96 * j + 1);
-      }
-      gx[kNJ - 1] = __ldg(bf.height_points + 3 * p_last);
-      gy[kNJ - 1] = __ldg(bf.height_points + 3 * p_last + 1);
-    }
     if (kNoise != ELG_NOISE_OFF) {
       const int nj = (H + 31) >> 5;
       float ns[kNJ], nsd[2], u[kNJ], ud[2];
@@ -223,7 +250,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   };
   prefetch(task0);
   STAMP(11, 0)
-  mbar_wait(&s_bar, 0);
+  mbar_wait(&s_bar[bsel], parity);
   STAMP(2, 0)
   STAMP(12, nwarps - 1)
 
@@ -238,7 +265,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       const float* fr = pre;
       float* const s_air = SM_F(L.air);
       float* const s_con = SM_F(L.con);
-      uint8_t* const s_lc = smem_raw + L.lc;
+      uint8_t* const s_lc = sbuf + L.lc;
       const float* cf = s_cf + (e * B + dm.feet_idx[f]) * 3;
       const float fxx = cf[0], fyy = cf[1], fz = cf[2];
       const float pz = fr[2], vx = fr[3], vy = fr[4], vz = fr[5];
@@ -339,7 +366,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
           s_yz[e] = rs[2];
         }
       }
-      int64_t* const s_ep = reinterpret_cast<int64_t*>(smem_raw + L.ep);
+      int64_t* const s_ep = reinterpret_cast<int64_t*>(sbuf + L.ep);
       if (live && !rollout) s_ep[e] += 1;   // episode counter (legged_robot.py:122)
       float* cmd = SM_F(L.cmd) + e * C;
       float cmd2 = cmd[2];
@@ -359,7 +386,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       // (legged_robot_rew_mixin.py:84-114, legged_robot.py:237-244, :148-149)
       const int d = task - kTaskDof;
       if (task != task0) prefetch(task);
-      const float2* s_dof = reinterpret_cast<const float2*>(smem_raw + L.dof);
+      const float2* s_dof = reinterpret_cast<const float2*>(sbuf + L.dof);
       float* const s_act = SM_F(L.act);
       float* const s_lact = SM_F(L.lact);
       float* const s_ldv = SM_F(L.ldv);
@@ -424,8 +451,13 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     }
   }
   STAMP(3, 0)
+  if (kLoop && stores_pending) {   // the previous chunk's stores have read the other staging buffer out (they had phase A to do so)
+    bulk_wait_read_all();
+    stores_pending = false;
+  }
   __syncthreads();   // (B1) derived state, partial sums, raw observation heads, yaw frames are in shared memory
   STAMP(4, 0)
+  if (kLoop && chunk + (int)gridDim.x < L.nchunks) issue_loads(chunk + gridDim.x, bsel ^ 1);
 
   if (row_warp) {
     // =====================================================================================================
@@ -535,7 +567,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       reset = bf.reset_buf[genv] != 0;
       time_out = bf.time_out_buf[genv] != 0;
     } else {
-      const int64_t ep = reinterpret_cast<const int64_t*>(smem_raw + L.ep)[e];
+      const int64_t ep = reinterpret_cast<const int64_t*>(sbuf + L.ep)[e];
       const bool contact_term = (PART(kPTermHit, e) + PART(kPTermHit + 1, e) + PART(kPTermHit + 2, e)) != 0.0f;
       time_out = ep > pr.max_episode_length;
       reset = contact_term | time_out;
@@ -598,8 +630,8 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     TERM(ELG_REW_FOUR_FOOTUP, fsum(kFDown) == 0.0f ? 0.1f : 0.0f)
     TERM(ELG_REW_GAIT_2_STEP, ([&] {
            // gait_2_step (legged_robot_rew_mixin.py:170-206): FL/RR and FR/RL in phase, the rest anti-phase (updated timers)
-           const float4 ar = reinterpret_cast<const float4*>(smem_raw + L.air)[e];
-           const float4 cn = reinterpret_cast<const float4*>(smem_raw + L.con)[e];
+           const float4 ar = reinterpret_cast<const float4*>(sbuf + L.air)[e];
+           const float4 cn = reinterpret_cast<const float4*>(sbuf + L.con)[e];
            auto sq4 = [](float a, float b) { const float d = a - b; return fminf(d * d, 4.0f); };
            const float s = ((sq4(ar.x, ar.w) + sq4(cn.x, cn.w)) + (sq4(ar.y, ar.z) + sq4(cn.y, cn.z))) / 2.0f;
            const float a = ((sq4(ar.x, cn.y) + sq4(cn.x, ar.y)) + (sq4(ar.x, cn.z) + sq4(cn.x, ar.z)) + (sq4(ar.w, cn.z) + sq4(cn.w, ar.z)) +
@@ -631,25 +663,22 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     if (live) SM_F(L.rew)[e] = total;
     STAMP(8, cap)
   }
-#undef PART
-#undef SM_F
-
   // ------------------------------- write back: one cp.async.bulk per output array -------------------------------
   fence_async_smem();   // this thread's generic-proxy writes -> visible to the async (TMA) proxy
-  __syncthreads();
+  __syncthreads();      // (B2)
   STAMP(9, 0)
   if (lane == 0) {
-    bool any = false;
     for (int i = warp; i < L.n_out; i += nwarps) {
       const FastCopy d = i == warp ? my_out : L.out[i];
-      bulk_s2g(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)env0 * d.bpe, smem_raw + d.soff, (uint32_t)(n * d.bpe));
-      any = true;
+      bulk_s2g(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)env0 * d.bpe, sbuf + d.soff, (uint32_t)(n * d.bpe));
+      stores_pending = true;
     }
-    if (any) {
-      bulk_commit();
-      bulk_wait_read_all();   // shared memory must outlive the reads; global visibility comes with kernel completion
-    }
+    if (stores_pending) bulk_commit();
   }
+#undef SM_F
+  }   // chunk loop
+#undef PART
+  if (stores_pending) bulk_wait_read_all();   // shared memory must outlive the reads; global visibility comes with kernel completion
   STAMP(10, 0)
 #undef STAMP
 }
@@ -741,6 +770,9 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   L.rew = take(cap * 4);
   L.mh = take(cap * (H > 0 ? H : 1) * 4);
   L.obs = take(cap * O * 4);
+  L.buf_bytes = off;
+  const int grid = nchunks < sms ? nchunks : sms;   // persistent: one CTA per SM, chunks round-robin
+  if (nchunks > grid) off *= 2;                     // double-buffered staging
   L.part = take(kPRows * 32 * 4);
   L.yaw = take(cap * 20);
   L.bytes = off;
@@ -814,13 +846,18 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   using Kern = void (*)(ElgDims, ElgStepParams, ElgStepBuffers, FastPlan);
   const bool clip = prm->clip_observations > 0.0f;
   Kern kern = nullptr;
+  const bool loop = nchunks > grid;
+#define ELG_PICK(NOISE)                                                                                                          \
+  kern = loop ? (clip ? elg_step_fast_kernel<NOISE, true, true> : elg_step_fast_kernel<NOISE, false, true>)                      \
+              : (clip ? elg_step_fast_kernel<NOISE, true, false> : elg_step_fast_kernel<NOISE, false, false>)
   switch (prm->noise_mode) {
-    case ELG_NOISE_OFF: kern = clip ? elg_step_fast_kernel<ELG_NOISE_OFF, true> : elg_step_fast_kernel<ELG_NOISE_OFF, false>; break;
-    case ELG_NOISE_TENSOR: kern = clip ? elg_step_fast_kernel<ELG_NOISE_TENSOR, true> : elg_step_fast_kernel<ELG_NOISE_TENSOR, false>; break;
-    default: kern = clip ? elg_step_fast_kernel<ELG_NOISE_PHILOX, true> : elg_step_fast_kernel<ELG_NOISE_PHILOX, false>; break;
+    case ELG_NOISE_OFF: ELG_PICK(ELG_NOISE_OFF); break;
+    case ELG_NOISE_TENSOR: ELG_PICK(ELG_NOISE_TENSOR); break;
+    default: ELG_PICK(ELG_NOISE_PHILOX); break;
   }
-  const int which = prm->noise_mode * 2 + (clip ? 1 : 0);
-  static size_t smem_set[6] = {};
+#undef ELG_PICK
+  const int which = (prm->noise_mode * 2 + (clip ? 1 : 0)) * 2 + (loop ? 1 : 0);
+  static size_t smem_set[12] = {};
   if ((size_t)L.bytes > smem_set[which]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes) != cudaSuccess) {
       *rc = set_error(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_step_fast_kernel");
@@ -829,7 +866,7 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
     smem_set[which] = (size_t)L.bytes;
   }
   cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3((unsigned)nchunks);
+  cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3((unsigned)(32 * (cap + kTaskWarps)));
   cfg.dynamicSmemBytes = (size_t)L.bytes;
   cfg.stream = (cudaStream_t)stream;
