@@ -81,7 +81,8 @@ __device__ __forceinline__ bool on(const ElgStepParams& pr, int t) { return (pr.
 
 // kNoise: ElgNoiseMode, kClip: clip_observations > 0 -- compile-time so that the per-point code carries no mode tests
 // kLoop: persistent form (a CTA walks over several chunks, double-buffered staging); false: one chunk per CTA, no loop state
-template <int kNoise, bool kClip, bool kLoop>
+// kRollout: post_physics_step_rollout form (rollout_mode) -- compile-time so that the headline kernel carries none of its tests
+template <int kNoise, bool kClip, bool kLoop, bool kRollout>
 __global__ void __launch_bounds__(32 * (kFastMaxCap + kTaskWarps), 1)
 elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgStepParams pr,
                      const __grid_constant__ ElgStepBuffers bf, const __grid_constant__ FastPlan L) {
@@ -97,7 +98,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   const bool need_hsum = on(pr, ELG_REW_BASE_HEIGHT) && H > 0;
   // rollout mode (post_physics_step_rollout, batch_rollout/robot_batch_rollout.py:763-817): no episode counter, heading command,
   // height scan (measured_heights is an input), termination or episode sums
-  const bool rollout = pr.rollout_mode != 0;
+  constexpr bool rollout = kRollout;
   const bool heights_live = H > 0 && !pr.terrain_is_plane && !rollout;
   const bool gait = bf.gait_idx != nullptr && bf.gait_prev_foot_z != nullptr;
   const bool dbg_on = L.dbg != nullptr && blockIdx.x == 0;
@@ -847,17 +848,21 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   const bool clip = prm->clip_observations > 0.0f;
   Kern kern = nullptr;
   const bool loop = nchunks > grid;
-#define ELG_PICK(NOISE)                                                                                                          \
-  kern = loop ? (clip ? elg_step_fast_kernel<NOISE, true, true> : elg_step_fast_kernel<NOISE, false, true>)                      \
-              : (clip ? elg_step_fast_kernel<NOISE, true, false> : elg_step_fast_kernel<NOISE, false, false>)
+#define ELG_PICK2(NOISE, CLIP)                                                                                          \
+  kern = loop ? (rollout ? elg_step_fast_kernel<NOISE, CLIP, true, true> : elg_step_fast_kernel<NOISE, CLIP, true, false>)  \
+              : (rollout ? elg_step_fast_kernel<NOISE, CLIP, false, true> : elg_step_fast_kernel<NOISE, CLIP, false, false>)
+#define ELG_PICK(NOISE)              \
+  if (clip) { ELG_PICK2(NOISE, true); } \
+  else { ELG_PICK2(NOISE, false); }
   switch (prm->noise_mode) {
     case ELG_NOISE_OFF: ELG_PICK(ELG_NOISE_OFF); break;
     case ELG_NOISE_TENSOR: ELG_PICK(ELG_NOISE_TENSOR); break;
     default: ELG_PICK(ELG_NOISE_PHILOX); break;
   }
+#undef ELG_PICK2
 #undef ELG_PICK
-  const int which = (prm->noise_mode * 2 + (clip ? 1 : 0)) * 2 + (loop ? 1 : 0);
-  static size_t smem_set[12] = {};
+  const int which = ((prm->noise_mode * 2 + (clip ? 1 : 0)) * 2 + (loop ? 1 : 0)) * 2 + (rollout ? 1 : 0);
+  static size_t smem_set[24] = {};
   if ((size_t)L.bytes > smem_set[which]) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes) != cudaSuccess) {
       *rc = set_error(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_step_fast_kernel");

@@ -167,7 +167,8 @@ def test_fused_equals_split_sections():
             assert torch.equal(a, b), k
 
 
-@pytest.mark.parametrize("case,n", [("anymal_c_rough", 1000), ("go2_all_terms_heading", 1028), ("a1_all_terms", 1001), ("anymal_c_flat", 512)])
+@pytest.mark.parametrize("case,n", [("anymal_c_rough", 1000), ("go2_all_terms_heading", 1028), ("a1_all_terms", 1001), ("anymal_c_flat", 512),
+                                    ("anymal_c_rough", 8192)])   # 8192 envs: the persistent (multi-chunk) form
 def test_rollout_mode_step_matches_oracle(case, n):
     """post_physics_step_rollout (robot_batch_rollout.py:763-817): one launch with ELG_PHASE_DERIVE | REWARD | OBS | HISTORY and
     rollout_mode -- measured heights, reset / time-out flags, commands and the episode counter are inputs and stay untouched,
