@@ -505,10 +505,10 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
           q = fma2(er, rr, q);
           float qx, qy;
           unpack2(q, qx, qy);
-          int ix = __float2int_rz(qx), iy = __float2int_rz(qy);
-          ix = min(max(ix, 0), rmax);
-          iy = min(max(iy, 0), cmax);
-          hv[j] = __ldg(hmin + (ix * cols + iy));
+          // .long() truncates toward zero, then clip(0, max): the saturating unsigned conversion already maps everything
+          // below 1 (negatives, NaN) to cell 0 and everything too large to UINT_MAX, so one min finishes the clip
+          const unsigned ix = min(__float2uint_rz(qx), (unsigned)rmax), iy = min(__float2uint_rz(qy), (unsigned)cmax);
+          hv[j] = __ldg(hmin + (ix * (unsigned)cols + iy));
         }
       } else {
 #pragma unroll
