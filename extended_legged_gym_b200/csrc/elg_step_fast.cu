@@ -52,6 +52,7 @@ struct FastPlan {
   int part, yaw;   // partial-sum table [rows][32], yaw frames [cap] x (float4 + float): one copy, behind the buffers
   int bytes;
   float r_hscale;  // RN(1 / horizontal_scale)
+  float r_dt;      // RN(1 / dt)
   float pen_sq, term_sq;   // largest sums of squares whose IEEE sqrt is still <= 0.1 / <= 1.0 (contact thresholds)
   int flags;       // diagnostic switches (elg_set_step_tuning threads_per_cta): 16 = launch without PDL
   long long* dbg;  // diagnostic: clock64 stamps of CTA 0 (elg_set_step_debug), or NULL
@@ -60,8 +61,9 @@ struct FastPlan {
   FastCopy out[kFastMaxOut];
 };
 
-// phase-A tasks (warp == task): feet first, their strided global rows take longest
-enum { kTaskFeet = 0, kTaskRot = 4, kTaskCmd = 9, kTaskDof = 10, kTaskBody = 16, kNumTasks = 19 };
+// phase-A tasks (warp == task): feet first, their strided global rows take longest; a foot is two tasks -- timers / contact
+// logic / gather (kTaskFeet + f) and the force / velocity norms (kTaskFeetB + f) -- because it was the longest chain by far
+enum { kTaskFeet = 0, kTaskRot = 4, kTaskCmd = 9, kTaskDof = 10, kTaskBody = 16, kTaskFeetB = 19, kNumTasks = 23 };
 constexpr int kDofWarps = 6, kBodyWarps = 3;
 constexpr int kBarHsum = 1;   // named barrier (0 is __syncthreads)
 
@@ -109,6 +111,16 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     const int q_n = L.quads_base + (chunk < L.quads_rem ? 1 : 0);
     env0 = q_lo * 4;
     n = min(dm.num_envs, (q_lo + q_n) * 4) - env0;   // multiple of 4 (host guarantees N % 4 == 0)
+  };
+
+  // x / dt as the tail of the IEEE division sequence (q = x r, two FMA residual corrections; r = RN(1 / dt) from the host):
+  // same value as the division for normal-range operands, 5 instructions, no out-of-line special-operand path
+  auto div_dt = [&](float x) {
+    float q = __fmul_rn(x, L.r_dt);
+    float e = __fmaf_rn(-pr.dt, q, x);
+    q = __fmaf_rn(e, L.r_dt, q);
+    e = __fmaf_rn(-pr.dt, q, x);
+    return __fmaf_rn(e, L.r_dt, q);
   };
 
   if (tid == 0) {
@@ -237,6 +249,9 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       const float* row = bf.rigid_body_state + ((size_t)genv * B + dm.feet_idx[task - kTaskFeet]) * 13;
       pre[0] = __ldg(row + 0); pre[1] = __ldg(row + 1); pre[2] = __ldg(row + 2);
       pre[3] = __ldg(row + 7); pre[4] = __ldg(row + 8); pre[5] = __ldg(row + 9);
+    } else if (task >= kTaskFeetB) {
+      const float* row = bf.rigid_body_state + ((size_t)genv * B + dm.feet_idx[task - kTaskFeetB]) * 13;
+      pre[3] = __ldg(row + 7); pre[4] = __ldg(row + 8); pre[5] = __ldg(row + 9);
     } else if (task >= kTaskDof && task < kTaskBody) {
       const int j = 2 * (task - kTaskDof);
       pre[0] = __ldg(bf.default_dof_pos + j);
@@ -268,8 +283,8 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       float* const s_con = SM_F(L.con);
       uint8_t* const s_lc = sbuf + L.lc;
       const float* cf = s_cf + (e * B + dm.feet_idx[f]) * 3;
-      const float fxx = cf[0], fyy = cf[1], fz = cf[2];
-      const float pz = fr[2], vx = fr[3], vy = fr[4], vz = fr[5];
+      const float fz = cf[2];
+      const float pz = fr[2];
       float air = s_air[fi], con = s_con[fi];
       const bool last_c = s_lc[fi] != 0;
       const bool contact = fz > 1.0f;
@@ -293,13 +308,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         lc_after = contact;
       }
       const bool filt2 = contact | lc_after;
-      PART(kPFeet + 4 * kFCf + f, lane) = fmaxf(norm3_tz(fxx, fyy, fz) - pr.max_contact_force, 0.0f);
-      const float vn = norm2_tz(vx, vy);
-      PART(kPFeet + 4 * kFSlip + f, lane) = (filt2 ? 1.0f : 0.0f) * (vn * vn);
-      const bool stumble = norm2_tz(fxx, fyy) > mul_r(5.0f, fabsf(fz));
-      PART(kPFeet + 4 * kFLift + f, lane) = (stumble ? 1.0f : 0.0f) * vz;
       PART(kPFeet + 4 * kFJump + f, lane) = (filt2 ? 0.0f : 1.0f) * (air - 0.5f);
-      PART(kPFeet + 4 * kFStum + f, lane) = stumble ? 1.0f : 0.0f;
       PART(kPFeet + 4 * kFDown + f, lane) = fz < 1.0f ? 0.0f : 1.0f;   // number of feet that are NOT up
       if (gait) {
         float* const s_gprev = SM_F(L.gprev);
@@ -341,9 +350,9 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       float* dst = SM_F(L.vec5) + (r * cap + e) * 3;
       if (r >= 3) {
         const float ema = pr.acc_ema, w1 = pr.acc_ema_c;
-        o.x = dst[0] * ema + (w1 * o.x) / pr.dt;
-        o.y = dst[1] * ema + (w1 * o.y) / pr.dt;
-        o.z = dst[2] * ema + (w1 * o.z) / pr.dt;
+        o.x = dst[0] * ema + div_dt(w1 * o.x);
+        o.y = dst[1] * ema + div_dt(w1 * o.y);
+        o.z = dst[2] * ema + div_dt(w1 * o.z);
       }
       if (live) {
         dst[0] = o.x; dst[1] = o.y; dst[2] = o.z;
@@ -404,7 +413,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         const float la = s_lact[fi], lv = s_ldv[fi], tq = s_tq[fi];
         const float da = la - a;
         q_ar += da * da;
-        const float dv = (lv - vel) / pr.dt;
+        const float dv = div_dt(lv - vel);
         q_da += dv * dv;
         q_dv += vel * vel;
         q_tq += tq * tq;
@@ -432,6 +441,23 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         PART(kPDof + kDofWarps * kDVl + d, lane) = q_vl;
         PART(kPDof + kDofWarps * kDTl + d, lane) = q_tl;
       }
+    } else if (task >= kTaskFeetB) {
+      // ---------------- foot f, second half: contact-force, slip and stumble terms (legged_robot_rew_mixin.py:121-148, :208-212).
+      // filt2 = contact | last_contacts AFTER feet_air_time rebinds it: with that term on it is just `contact`; with it off
+      // last_contacts is not written by the first half, so reading it here does not race.
+      const int f = task - kTaskFeetB, fi = e * F + f;
+      if (task != task0) prefetch(task);
+      const float* cf = s_cf + (e * B + dm.feet_idx[f]) * 3;
+      const float fxx = cf[0], fyy = cf[1], fz = cf[2];
+      const float vx = pre[3], vy = pre[4], vz = pre[5];
+      const bool contact = fz > 1.0f;
+      const bool filt2 = contact | (on(pr, ELG_REW_FEET_AIR_TIME) ? false : (sbuf + L.lc)[fi] != 0);
+      PART(kPFeet + 4 * kFCf + f, lane) = fmaxf(norm3_tz(fxx, fyy, fz) - pr.max_contact_force, 0.0f);
+      const float vn = norm2_tz(vx, vy);
+      PART(kPFeet + 4 * kFSlip + f, lane) = (filt2 ? 1.0f : 0.0f) * (vn * vn);
+      const bool stumble = norm2_tz(fxx, fyy) > mul_r(5.0f, fabsf(fz));
+      PART(kPFeet + 4 * kFLift + f, lane) = (stumble ? 1.0f : 0.0f) * vz;
+      PART(kPFeet + 4 * kFStum + f, lane) = stumble ? 1.0f : 0.0f;
     } else {
       // ---------------- contact bodies g, g + 3, ...: collision count and termination contacts
       // (legged_robot_rew_mixin.py:117-119, legged_robot.py:155-160); penalised bodies first, then termination bodies
@@ -451,6 +477,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
       PART(kPTermHit + g, lane) = thit ? 1.0f : 0.0f;
     }
   }
+  if (dbg_on && lane == 0) L.dbg[32 + warp] = clock64();   // per-warp end of phase A
   STAMP(3, 0)
   if (kLoop && stores_pending) {   // the previous chunk's stores have read the other staging buffer out (they had phase A to do so)
     bulk_wait_read_all();
@@ -730,6 +757,7 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   L.quads_base = (int)(Q / nchunks);
   L.quads_rem = (int)(Q % nchunks);
   L.r_hscale = 1.0f / prm->horizontal_scale;
+  L.r_dt = 1.0f / prm->dt;
   {   // contact thresholds on the sum of squares: the largest float whose correctly rounded sqrt does not exceed t
     auto sq_threshold = [](float t) {
       float s = t * t;

@@ -225,7 +225,7 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
  * element-wise staging path instead of TMA bulk copies.  envs_per_chunk == 0 restores the built-in choice. */
 int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm, int disable_bulk);
 
-/* Diagnostic (no reference counterpart): when set to a device buffer of >= 16 int64, CTA 0 of every following
+/* Diagnostic (no reference counterpart): when set to a device buffer of >= 64 int64, CTA 0 of every following
  * elg_post_physics_step launch records clock64() at its stage boundaries there; NULL switches it off. */
 int elg_set_step_debug(long long* device_stamps);
 

@@ -9,7 +9,7 @@ names = {0: "entry", 1: "after griddepcontrol.wait", 2: "loads landed (warp 0)",
          6: "row0: scan done", 7: "row0: head done", 8: "assembly warp done", 9: "B2 passed", 10: "stores read out (warp 0)", 11: "warp 0 reaches the TMA wait", 12: "loads landed (last warp, idle until then)"}
 for case, n in (("anymal_c_rough", 4096), ("anymal_c_flat", 4096)):
     env = make(case, n, 0)
-    buf = torch.zeros(32, dtype=torch.int64, device=dev)
+    buf = torch.zeros(64, dtype=torch.int64, device=dev)
     lib.elg_set_step_debug.argtypes = [C.c_void_p]
     lib.elg_set_step_debug(buf.data_ptr())
     p = env._params
@@ -26,6 +26,7 @@ for case, n in (("anymal_c_rough", 4096), ("anymal_c_flat", 4096)):
     for i in sorted(names, key=lambda k: st[k]):
         if st[i]:
             print(f"  {names[i]:32s} {st[i] - st[0]:8d} cyc  {(st[i] - st[0]) / 1965.0:7.2f} us")
+    print('  phase A end per warp (us since entry):', ' '.join(f'{(st[32 + w] - st[0]) / 1965.0:.2f}' for w in range(32)))
     lib.elg_set_step_debug(None)
     del flush
 # launch floor: a trivial torch kernel chain in a graph
