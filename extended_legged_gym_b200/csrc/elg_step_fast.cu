@@ -507,35 +507,41 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         const f32x2 rr = pack2(L.r_hscale, L.r_hscale);
         const f32x2 nc = pack2(-pr.horizontal_scale, -pr.horizontal_scale);
         const f32x2 bord = pack2(pr.border_size, pr.border_size);
-        // t = 2 (q x b) = (-2 zz by, 2 zz bx); 2*RN(x) == RN(2x), so the doubling is folded into the multiplier
+        // quat_apply with the yaw-only quaternion (0, 0, zz, ww): t = 2 (q x b) = (-2 zz by, 2 zz bx) (2 RN(x) == RN(2 x), so the
+        // doubling is folded into the multiplier), p = b + ww t + q x t with q x t = (-zz ty, zz tx).  The packed halves are
+        // TWO POINTS of this lane (not x / y of one point): every multiplier is then a plain broadcast, tx / ty are computed
+        // once and serve both coordinates -- 20 packed instructions per two points instead of 26, and no register shuffling.
         const float z2 = mul_r(zz, 2.0f);
-        const f32x2 c_t = pack2(-z2, z2);      // times (by, bx) -> (tx, ty)
-        const f32x2 c_ts = pack2(z2, -z2);     // times (bx, by) -> (ty, tx)
-        const f32x2 c_w = pack2(ww, ww);
-        const f32x2 c_u = pack2(-zz, zz);
-        const f32x2 xy = pack2(yf.z, yf.w);
-        const int cols = pr.hf_cols, rmax = pr.hf_rows - 2, cmax = pr.hf_cols - 2;
+        const f32x2 m_tx = pack2(-z2, -z2), m_ty = pack2(z2, z2), m_w = pack2(ww, ww), m_nz = pack2(-zz, -zz), m_pz = pack2(zz, zz);
+        const f32x2 X2 = pack2(yf.z, yf.z), Y2 = pack2(yf.w, yf.w);
+        const unsigned cols = (unsigned)pr.hf_cols, rmax = (unsigned)(pr.hf_rows - 2), cmax = (unsigned)(pr.hf_cols - 2);
         const float* __restrict__ hmin = bf.height_field_min;
-#pragma unroll
-        for (int j = 0; j < kNJ; ++j) {
-          const f32x2 b = pack2(gx[j], gy[j]), bs = pack2(gy[j], gx[j]);
-          const f32x2 t = mul2(c_t, bs);          // (tx, ty)
-          const f32x2 ts = mul2(c_ts, b);         // (ty, tx)
-          f32x2 pt = madd2_unfused(b, c_w, t);    // b + w t
-          pt = madd2_unfused(pt, c_u, ts);        // + q_xyz x t = (-zz ty, zz tx)
-          pt = add2(add2(pt, xy), bord);          // + base xy, + border_size
-          // correctly rounded pt / horizontal_scale: q0 = x r, two FMA residual corrections (Markstein)
+        auto div_h = [&](f32x2 pt) {   // correctly rounded pt / horizontal_scale: q0 = x r, two FMA residual corrections (Markstein)
           f32x2 q = mul2(pt, rr);
           f32x2 er = fma2(nc, q, pt);
           q = fma2(er, rr, q);
           er = fma2(nc, q, pt);
-          q = fma2(er, rr, q);
-          float qx, qy;
-          unpack2(q, qx, qy);
+          return fma2(er, rr, q);
+        };
+#pragma unroll
+        for (int k = 0; k < kNJ / 2; ++k) {
+          const f32x2 BX = pack2(gx[2 * k], gx[2 * k + 1]), BY = pack2(gy[2 * k], gy[2 * k + 1]);
+          const f32x2 TX = mul2(m_tx, BY), TY = mul2(m_ty, BX);
+          f32x2 PX = madd2_unfused(BX, m_w, TX);     // bx + ww tx
+          PX = madd2_unfused(PX, m_nz, TY);          //    - zz ty
+          PX = add2(add2(PX, X2), bord);             //    + base x, + border_size
+          f32x2 PY = madd2_unfused(BY, m_w, TY);     // by + ww ty
+          PY = madd2_unfused(PY, m_pz, TX);          //    + zz tx
+          PY = add2(add2(PY, Y2), bord);
+          float qx0, qx1, qy0, qy1;
+          unpack2(div_h(PX), qx0, qx1);
+          unpack2(div_h(PY), qy0, qy1);
           // .long() truncates toward zero, then clip(0, max): the saturating unsigned conversion already maps everything
           // below 1 (negatives, NaN) to cell 0 and everything too large to UINT_MAX, so one min finishes the clip
-          const unsigned ix = min(__float2uint_rz(qx), (unsigned)rmax), iy = min(__float2uint_rz(qy), (unsigned)cmax);
-          hv[j] = __ldg(hmin + (ix * (unsigned)cols + iy));
+          const unsigned ix0 = min(__float2uint_rz(qx0), rmax), iy0 = min(__float2uint_rz(qy0), cmax);
+          const unsigned ix1 = min(__float2uint_rz(qx1), rmax), iy1 = min(__float2uint_rz(qy1), cmax);
+          hv[2 * k] = __ldg(hmin + (ix0 * cols + iy0));
+          hv[2 * k + 1] = __ldg(hmin + (ix1 * cols + iy1));
         }
       } else {
 #pragma unroll
