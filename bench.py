@@ -167,7 +167,7 @@ def build_replicas(case, common, n_envs, n_rep, dev):
 
 
 # ----------------------------------------------------------------------------------------------
-def secondary_benchmarks(dev, world, rank, dist, quick=False):
+def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
     """The other kernels of the path at the BASELINE configs 4 and 5 (reported next to the headline, not in `value`):
     depth-camera ray casting (Mrays/s), the main -> rollout clone, the MPPI update (+ its collectives when N > 1)."""
     import numpy as np
@@ -233,6 +233,8 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False):
                             "cameras_per_gpu": n_cam, "rays_per_camera": 64 * 48, "triangles": int(len(t)), "bvh_build_s": build_s, **depth,
                             "raycast_mesh_incoherent_10m": {"value": o.shape[0] / sec / 1e6, "unit": "Mrays/s"}}
     del cam
+    if only_depth:
+        return out
 
     # ---- config 5: 64 mains x 512 rollouts: state clone, then the cost-weighted update over a 20-step horizon
     import common
