@@ -221,8 +221,10 @@ int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const flo
 int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const ElgStepBuffers* buf, uint32_t phase, void* stream);
 
 /* Launch-geometry override of elg_post_physics_step for benchmarking sweeps (no reference counterpart):
- * envs per chunk (multiple of 4, <= 32), threads per CTA, CTAs per SM; disable_bulk != 0 forces the
- * element-wise staging path instead of TMA bulk copies.  envs_per_chunk == 0 restores the built-in choice. */
+ * envs per chunk (multiple of 4; <= 32 for the generic kernel, <= 28 for the lean one), CTAs per SM (generic kernel only);
+ * disable_bulk bit 0 forces the element-wise staging path of the generic kernel instead of TMA bulk copies, bit 1 disables the
+ * lean kernel (elg_step_fast.cu) so that every call takes the generic one.  threads_per_cta is a diagnostic word for the lean
+ * kernel: 16 launches it without programmatic dependent launch.  envs_per_chunk == 0 restores the built-in geometry. */
 int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm, int disable_bulk);
 
 /* Diagnostic (no reference counterpart): when set to a device buffer of >= 64 int64, CTA 0 of every following
