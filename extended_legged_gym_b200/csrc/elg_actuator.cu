@@ -14,9 +14,10 @@
 
 namespace elg {
 
-constexpr int kActThreads = 128;
+constexpr int kActThreads = 64;
 
-__device__ __forceinline__ float sigmoid_f(float x) { return 1.0f / (1.0f + expf(-x)); }
+// 1 / (1 + e^-x): the correctly rounded reciprocal IS the IEEE quotient 1.0f / y, without the general division sequence
+__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + expf(-x)); }
 
 // one LSTM cell step for one row; torch gate order i, f, g, o (rows u, 8 + u, 16 + u, 24 + u)
 template <int kIn>
