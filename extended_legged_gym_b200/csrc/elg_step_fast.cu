@@ -492,7 +492,10 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     // phase B, ROW warp: terrain scan (legged_robot.py:900-938), height observations, observation-head noise
     // =====================================================================================================
     const int slot = warp;
-    float* const orow = s_obs + slot * O;
+    float* const orow = s_obs + slot * O;                                  // raw observation head staged in phase A
+    float* const gobs = bf.obs_buf + (size_t)(env0 + slot) * O;             // final values go straight to global memory:
+    float* const gmh = rollout ? nullptr : bf.measured_heights + (size_t)(env0 + slot) * H;   // 128 contiguous bytes per warp store,
+    // issued as each round finishes (no staging, nothing left to drain through the TMA at the end of the launch)
     if (H > 0) {
       float* const mh = SM_F(L.mh) + slot * H;
       const float4 yf = rollout ? make_float4(0.0f, 0.0f, 0.0f, 0.0f) : s_yaw[slot];
@@ -554,12 +557,12 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         const int p = lane + 32 * j;
         if (j < kNJ - 1 || p < H) {   // H > 32 (kNJ - 1): only the last round is ragged
           const float h = hv[j];
-          if (!rollout) mh[p] = h;
+          if (!rollout) gmh[p] = h;
           if (need_hsum) hsum += sub_r(rootz, h);
           float v = mul_r(fminf(fmaxf(sub_r(zc, h), -1.0f), 1.0f), pr.obs_scale_height);
           if (kNoise != ELG_NOISE_OFF) v = v + nz[j];
           if (kClip) v = fminf(fmaxf(v, -clip_obs), clip_obs);
-          orow[head + p] = v;
+          gobs[head + p] = v;
         }
       }
       if (need_hsum) {
@@ -579,7 +582,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
         float v = orow[k];
         if (kNoise != ELG_NOISE_OFF) v = v + nzh[m];
         if (kClip) v = fminf(fmaxf(v, -clip_obs), clip_obs);
-        orow[k] = v;
+        gobs[k] = v;
       }
     }
     STAMP(7, 0)
@@ -848,8 +851,6 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   if (!rollout)
     for (int ti = 0; ti < nt; ++ti) in(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
 
-  out(buf->obs_buf, L.obs, 4 * O);
-  if (H > 0 && !rollout) out(buf->measured_heights, L.mh, 4 * H);
   out(buf->base_lin_vel, L.vec5 + 0 * v3, 12);
   out(buf->base_ang_vel, L.vec5 + 1 * v3, 12);
   out(buf->projected_gravity, L.vec5 + 2 * v3, 12);
