@@ -45,7 +45,7 @@ struct FastCopy {
 
 struct FastPlan {
   int cap, nchunks, quads_base, quads_rem;
-  int n_in, n_out, nterms;
+  int n_in, n_out, n_out_early, nterms;
   // staged per-env arrays, byte offsets into dynamic shared memory
   int root, dof, act, lact, ldv, tq, cf, lrv, vec5, cmd, air, con, lc, ep, gidx, gprev, fpos, fvel, sums, rew, mh, obs;
   int buf_bytes;   // one staging buffer (everything above); two of them when a CTA handles more than one chunk
@@ -130,7 +130,6 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   pdl_launch_dependents();
   // the copy-table entries this warp will issue: fetched before the wait so that the constant-bank miss is off the load path
   FastCopy my_in = L.in[warp < L.n_in ? warp : 0];
-  FastCopy my_out = L.out[warp < L.n_out ? warp : 0];
   __syncthreads();
   pdl_wait();   // nothing above reads or writes global memory
   STAMP(1, 0)
@@ -483,8 +482,17 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     bulk_wait_read_all();
     stores_pending = false;
   }
+  fence_async_smem();   // phase-A results -> visible to the async (TMA) proxy: the early stores below read them
   __syncthreads();   // (B1) derived state, partial sums, raw observation heads, yaw frames are in shared memory
   STAMP(4, 0)
+  if (warp > cap && lane == 0) {   // the spare warps behind the assembly warp: outputs that phase B does not write any more
+    for (int i = warp - cap - 1; i < L.n_out_early; i += kTaskWarps - 1) {
+      const FastCopy d = L.out[i];
+      bulk_s2g(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)env0 * d.bpe, sbuf + d.soff, (uint32_t)(n * d.bpe));
+      stores_pending = true;
+    }
+    if (stores_pending) bulk_commit();
+  }
   if (kLoop && chunk + (int)gridDim.x < L.nchunks) issue_loads(chunk + gridDim.x, bsel ^ 1);
 
   if (row_warp) {
@@ -705,12 +713,16 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
   __syncthreads();      // (B2)
   STAMP(9, 0)
   if (lane == 0) {
-    for (int i = warp; i < L.n_out; i += nwarps) {
-      const FastCopy d = i == warp ? my_out : L.out[i];
+    bool any = false;
+    for (int i = L.n_out_early + warp; i < L.n_out; i += nwarps) {
+      const FastCopy d = L.out[i];
       bulk_s2g(static_cast<uint8_t*>(const_cast<void*>(d.g)) + (size_t)env0 * d.bpe, sbuf + d.soff, (uint32_t)(n * d.bpe));
+      any = true;
+    }
+    if (any) {
+      bulk_commit();
       stores_pending = true;
     }
-    if (stores_pending) bulk_commit();
   }
 #undef SM_F
   }   // chunk loop
@@ -851,6 +863,7 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   if (!rollout)
     for (int ti = 0; ti < nt; ++ti) in(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
 
+  // outputs that are final when phase A ends come first: they are stored right behind barrier B1, under the scan
   out(buf->base_lin_vel, L.vec5 + 0 * v3, 12);
   out(buf->base_ang_vel, L.vec5 + 1 * v3, 12);
   out(buf->projected_gravity, L.vec5 + 2 * v3, 12);
@@ -865,16 +878,16 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
     out(buf->feet_contact_time, L.con, 16);
     out(buf->last_contacts, L.lc, 4);
   }
-  if (!rollout)
-    for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
-  out(buf->rew_buf, L.rew, 4);
-  if (gait) {
-    out(buf->gait_idx, L.gidx, 4);
-    out(buf->gait_prev_foot_z, L.gprev, 16);
-  }
+  if (gait) out(buf->gait_prev_foot_z, L.gprev, 16);
   out(buf->last_actions, L.lact, 4 * D);
   out(buf->last_dof_vel, L.ldv, 4 * D);
   out(buf->last_root_vel, L.lrv, 24);
+  L.n_out_early = n_out;
+  // written by the reward assembly (phase B): stored behind barrier B2
+  if (!rollout)
+    for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
+  out(buf->rew_buf, L.rew, 4);
+  if (gait) out(buf->gait_idx, L.gidx, 4);
   L.n_in = n_in;
   L.n_out = n_out;
   if (!aligned) return 0;   // TMA bulk staging needs 16-byte aligned array bases
