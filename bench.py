@@ -294,6 +294,20 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
     out["rollout_step"] = {"workload": f"post_physics_step_rollout over {n} envs ({mains} mains x (1 + {rollouts}) rows), anymal_c_rough",
                            "us_per_step": sec * 1e6, "env_steps_per_s": n / sec,
                            "note": "lean kernel in rollout mode (measured heights are an input, no termination / episode sums); CUDA graph of 20 steps"}
+    # one MPPI iteration of BASELINE config 5 through the public API: rollout_batch (sync, 20 x step_rollout with decimation x torques,
+    # rollout-mode step, main-row restore, sync) + the cost-weighted update
+    from extended_legged_gym_b200.utils.mppi import rollout_batch
+    horizon, nodes = 20, 5
+    all_us = torch.randn(mains * rollouts, horizon, 12, device=dev) * 0.3
+    samples = torch.randn(mains, rollouts, nodes, 12, device=dev)
+
+    def mppi_iteration():
+        rew = rollout_batch(env, all_us)
+        return mppi_update(rew.view(mains, rollouts, horizon), samples, 0.05)
+    sec = timed(mppi_iteration, 2 if quick else 5, warm=1)
+    out["mppi_iteration"] = {"workload": f"{mains} mains x {rollouts} rollouts per GPU x horizon {horizon}: rollout_batch + mppi_update (Python API, "
+                                         f"{world} rank{'s' if world > 1 else ''})", "ms_per_iteration": sec * 1e3,
+                             "rollout_env_steps_per_s": mains * rollouts * horizon / sec}
     del env
     # ---- actuator-network torques (Anymal._compute_torques, the default torque path of the anymal_c configs): 4096 envs x 12 dofs
     from extended_legged_gym_b200.envs import Anymal

@@ -143,13 +143,26 @@ class RobotBatchRollout(LeggedRobot):
     # stepping (robot_batch_rollout.py:535-716)
     # ------------------------------------------------------------------------------------------
     def _rows(self, idx, clip_obs):
-        obs = torch.clip(self.obs_buf[idx], -clip_obs, clip_obs)
+        """Rows of the step outputs for the main or the rollout envs.  Main env k is row k (1 + R) and its rollouts sit right
+        behind it (_init_env_indices, robot_batch_rollout.py:119-164), so both selections are strided views: the clip
+        reads them in place and writes the result -- no index gather of the [rows, num_obs] block."""
+        M, R1 = self.num_main_envs, 1 + self.num_rollout_per_main
+        if idx is self.main_env_indices:
+            pick = lambda t: t.view(M, R1, *t.shape[1:])[:, 0].clone()          # (copies, like the reference's index expressions)
+        elif idx is self.rollout_env_indices and self.num_rollout_per_main > 0:
+            pick = lambda t: t.view(M, R1, *t.shape[1:])[:, 1:].clone().view(M * (R1 - 1), *t.shape[1:])
+        else:
+            pick = lambda t: t[idx]
+        if idx is self.rollout_env_indices and self.num_rollout_per_main > 0:
+            obs = torch.clip(self.obs_buf.view(M, R1, -1)[:, 1:], -clip_obs, clip_obs).view(M * (R1 - 1), -1)
+        else:
+            obs = torch.clip(pick(self.obs_buf), -clip_obs, clip_obs)
         priv = None
         if self.privileged_obs_buf is not None:
-            priv = torch.clip(self.privileged_obs_buf[idx], -clip_obs, clip_obs)
-        extras = {k: (v[idx] if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == self.total_num_envs else v)
+            priv = torch.clip(pick(self.privileged_obs_buf), -clip_obs, clip_obs)
+        extras = {k: (pick(v) if isinstance(v, torch.Tensor) and v.dim() > 0 and v.shape[0] == self.total_num_envs else v)
                   for k, v in self.extras.items()}
-        return obs, priv, self.rew_buf[idx], self.reset_buf[idx], extras
+        return obs, priv, pick(self.rew_buf), pick(self.reset_buf), extras
 
     def step(self, actions):
         """actions: [num_main_envs, num_actions]; returns the main-env rows."""
