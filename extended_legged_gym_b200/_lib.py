@@ -85,6 +85,12 @@ ACTNET_B_LIN = ACTNET_W_LIN + 8
 ACTNET_WORDS = ACTNET_B_LIN + 4
 
 
+class ElgNavParams(C.Structure):
+    _fields_ = [("use_2d_nav", C.c_int32), ("use_prev", C.c_int32), ("num_commands", C.c_int32), ("zero_reached", C.c_int32),
+                ("kp_linear", C.c_float), ("kp_angular", C.c_float), ("max_linear_vel", C.c_float), ("max_angular_vel", C.c_float),
+                ("smooth", C.c_float), ("smooth_c", C.c_float), ("tolerance_rad", C.c_float)]
+
+
 class ElgCloneField(C.Structure):
     _fields_ = [("base", C.c_void_p), ("cache", C.c_void_p), ("row_bytes", C.c_int32), ("reserved", C.c_int32)]
 
@@ -143,7 +149,7 @@ def load() -> C.CDLL:
     lib.elg_reward_term_name.argtypes = [C.c_int]
     for fn, st in (("elg_sizeof_dims", ElgDims), ("elg_sizeof_step_params", ElgStepParams), ("elg_sizeof_step_buffers", ElgStepBuffers),
                    ("elg_sizeof_clone_table", ElgCloneTable), ("elg_sizeof_cam_params", ElgCamParams), ("elg_sizeof_reset_params", ElgResetParams),
-                   ("elg_sizeof_reset_buffers", ElgResetBuffers)):
+                   ("elg_sizeof_reset_buffers", ElgResetBuffers), ("elg_sizeof_nav_params", ElgNavParams)):
         got = getattr(lib, fn)()
         if got != C.sizeof(st):
             raise ElgError(f"ABI mismatch: {fn}() = {got}, python mirror = {C.sizeof(st)}")
@@ -158,6 +164,7 @@ def load() -> C.CDLL:
     lib.elg_clone_rows.argtypes = [C.POINTER(ElgCloneTable), C.c_int, C.c_float, vp, C.c_uint64, C.c_uint64, vp]
     lib.elg_set_step_debug.argtypes = [vp]
     lib.elg_set_clone_tuning.argtypes = [C.c_int]
+    lib.elg_nav_commands.argtypes = [C.c_int32, C.c_int32, C.POINTER(ElgNavParams)] + [vp] * 7
     if lib.elg_actuator_net_words() != ACTNET_WORDS:
         raise ElgError(f"ABI mismatch: elg_actuator_net_words() = {lib.elg_actuator_net_words()}, python mirror = {ACTNET_WORDS}")
     lib.elg_actuator_net_torques.argtypes = [C.POINTER(ElgDims), vp, C.c_float] + [vp] * 7

@@ -7,6 +7,8 @@ from .a1.a1_config import A1RoughCfg, A1RoughCfgPPO
 from .go2.go2_config import Go2RoughCfg, Go2RoughCfgPPO
 from .batch_rollout.robot_batch_rollout import RobotBatchRollout
 from .batch_rollout.robot_batch_rollout_config import RobotBatchRolloutCfg, RobotBatchRolloutCfgPPO
+from .batch_rollout.robot_batch_rollout_nav import RobotBatchRolloutNav
+from .batch_rollout.robot_batch_rollout_nav_config import RobotBatchRolloutNavCfg, RobotBatchRolloutNavCfgPPO
 
 TASKS = {
     "anymal_c_rough": (Anymal, AnymalCRoughCfg, AnymalCRoughCfgPPO),      # legged_gym/envs/__init__.py registers Anymal for both

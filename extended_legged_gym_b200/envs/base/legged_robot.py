@@ -483,12 +483,14 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         if self.fused_reset and not self._python_terms and not push_step and not cmd_curr and self.episode_stats is None:
             # the whole step without a host synchronisation: resample -> fused step -> reset (+ observation repair)
             self._launch_resample()
+            self._pre_step_hook()
             self._launch(P.PHASE_FUSED, clip)
             self.reset_buf = self._reset_bool
             self._launch_reset()
             self._noise_step += 1
             return
         push_now = self._post_physics_step_callback()
+        self._pre_step_hook()
         if not self._python_terms and not push_now:
             # common case: the whole step is ONE kernel; the reset path below re-runs the cheap POST section
             self._launch(P.PHASE_FUSED, clip)
@@ -592,6 +594,11 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             self.extras["time_outs"] = self.time_out_buf
         self.sim.set_dof_state()
         self.sim.set_root_state()
+
+    def _pre_step_hook(self):
+        """Called after the command resampling and before the fused step kernel: the place where a subclass's
+        ``_post_physics_step_callback`` additions that feed this step's rewards / observations belong (e.g. the navigation
+        command update of RobotBatchRolloutNav).  The in-kernel heading update and height scan come after it."""
 
     def _post_physics_step_callback(self):
         """Host part of the callback (legged_robot.py:386-403): sparse command resampling before the

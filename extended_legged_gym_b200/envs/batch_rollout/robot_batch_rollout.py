@@ -214,7 +214,11 @@ class RobotBatchRollout(LeggedRobot):
         The kernel runs over every row; main rows are put back by ``_restore_main_env_states`` right after."""
         self.sim.refresh()
         P = _lib
+        self._pre_step_hook_rollout()
         self._launch(P.PHASE_DERIVE | P.PHASE_REWARD | P.PHASE_OBS | P.PHASE_HISTORY, rollout=True)
+
+    def _pre_step_hook_rollout(self):
+        """``_post_physics_step_callback_rollout`` (robot_batch_rollout.py:868: empty in the base class)"""
 
     def check_termination(self):
         """:857-866 -- contact termination everywhere, time-outs only OR-ed into the main rows."""

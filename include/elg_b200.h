@@ -331,6 +331,28 @@ int elg_sdf_query(const ElgMesh* mesh, const float* points, int64_t num_points, 
 double elg_mesh_mean_edge(const ElgMesh* mesh);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Navigation command update of the batch-rollout nav task (envs/batch_rollout/robot_batch_rollout_nav.py:135-247:
+ * _update_navigation_commands followed by _check_goal_reached, both called from _post_physics_step_callback and its
+ * rollout twin).  Env i steers towards goal_positions[i / (1 + rollouts_per_main)]: proportional world-frame velocity
+ * clipped to max_linear_vel, rotated into the base frame; yaw rate towards the goal (2-D mode); exponential smoothing
+ * with prev_commands when use_prev; commands[:, 0:3] overwritten, rows of envs whose goal_reached flag was set by the
+ * PREVIOUS check are zeroed entirely; then goal_reached = distance < tolerance_rad.  One launch instead of two Python
+ * loops over every env. */
+typedef struct ElgNavParams {
+  int32_t use_2d_nav;
+  int32_t use_prev;          /* 0: prev_commands holds nothing yet (reference: prev_commands is None) */
+  int32_t num_commands;      /* row length of commands */
+  int32_t zero_reached;      /* 0: goal_reached holds nothing yet (reference: goal_reached is None) -> no rows are zeroed */
+  float kp_linear, kp_angular, max_linear_vel, max_angular_vel;
+  float smooth, smooth_c;    /* cmd_smooth_factor and fp32(1 - cmd_smooth_factor) */
+  float tolerance_rad;
+} ElgNavParams;
+int elg_sizeof_nav_params(void);
+int elg_nav_commands(int32_t num_main, int32_t rollouts_per_main, const ElgNavParams* prm, const float* root_states /*[N,13]*/,
+                     const float* goal_positions /*[num_main,3]*/, float* commands /*[N,C]*/, float* prev_commands /*[N,3]*/,
+                     uint8_t* goal_reached /*[N] bool*/, float* distance /*[N] or NULL*/, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Actuator-network torques (envs/anymal_c/anymal.py:93-105, the default torque path of the anymal_c_* configs:
  * control.use_actuator_network, mixed_terrains/anymal_c_rough_config.py:68-69).  The TorchScript module
  * resources/actuator_nets/anydrive_v3_lstm.pt is `LSTMsea`: x * in_scale -> 2-layer LSTM(input 2, hidden 8, batch_first, one
