@@ -91,6 +91,17 @@ class ElgNavParams(C.Structure):
                 ("smooth", C.c_float), ("smooth_c", C.c_float), ("tolerance_rad", C.c_float)]
 
 
+class ElgPlanParams(C.Structure):
+    _fields_ = [("num_dof", C.c_int32), ("method", C.c_int32), ("n_substeps", C.c_int32), ("enforce_joint_limits", C.c_int32),
+                ("sub_dt", C.c_float), ("max_base_lin_vel", C.c_float), ("max_base_ang_vel", C.c_float), ("max_joint_vel", C.c_float)]
+
+
+class ElgPlanBuffers(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("integration_base_pos", "integration_base_quat", "integration_dof_pos", "integration_base_lin_vel",
+                                          "integration_base_ang_vel", "integration_dof_vel", "dof_pos_limits", "root_states", "dof_state",
+                                          "base_lin_vel", "base_ang_vel")]
+
+
 class ElgCloneField(C.Structure):
     _fields_ = [("base", C.c_void_p), ("cache", C.c_void_p), ("row_bytes", C.c_int32), ("reserved", C.c_int32)]
 
@@ -149,7 +160,8 @@ def load() -> C.CDLL:
     lib.elg_reward_term_name.argtypes = [C.c_int]
     for fn, st in (("elg_sizeof_dims", ElgDims), ("elg_sizeof_step_params", ElgStepParams), ("elg_sizeof_step_buffers", ElgStepBuffers),
                    ("elg_sizeof_clone_table", ElgCloneTable), ("elg_sizeof_cam_params", ElgCamParams), ("elg_sizeof_reset_params", ElgResetParams),
-                   ("elg_sizeof_reset_buffers", ElgResetBuffers), ("elg_sizeof_nav_params", ElgNavParams)):
+                   ("elg_sizeof_reset_buffers", ElgResetBuffers), ("elg_sizeof_nav_params", ElgNavParams),
+                   ("elg_sizeof_plan_params", ElgPlanParams), ("elg_sizeof_plan_buffers", ElgPlanBuffers)):
         got = getattr(lib, fn)()
         if got != C.sizeof(st):
             raise ElgError(f"ABI mismatch: {fn}() = {got}, python mirror = {C.sizeof(st)}")
@@ -165,6 +177,7 @@ def load() -> C.CDLL:
     lib.elg_set_step_debug.argtypes = [vp]
     lib.elg_set_clone_tuning.argtypes = [C.c_int]
     lib.elg_nav_commands.argtypes = [C.c_int32, C.c_int32, C.POINTER(ElgNavParams)] + [vp] * 7
+    lib.elg_integrate_state_velocities.argtypes = [C.POINTER(ElgPlanParams), C.POINTER(ElgPlanBuffers), vp, vp, i64, vp]
     if lib.elg_actuator_net_words() != ACTNET_WORDS:
         raise ElgError(f"ABI mismatch: elg_actuator_net_words() = {lib.elg_actuator_net_words()}, python mirror = {ACTNET_WORDS}")
     lib.elg_actuator_net_torques.argtypes = [C.POINTER(ElgDims), vp, C.c_float] + [vp] * 7

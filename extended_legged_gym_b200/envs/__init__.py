@@ -9,6 +9,8 @@ from .batch_rollout.robot_batch_rollout import RobotBatchRollout
 from .batch_rollout.robot_batch_rollout_config import RobotBatchRolloutCfg, RobotBatchRolloutCfgPPO
 from .batch_rollout.robot_batch_rollout_nav import RobotBatchRolloutNav
 from .batch_rollout.robot_batch_rollout_nav_config import RobotBatchRolloutNavCfg, RobotBatchRolloutNavCfgPPO
+from .batch_rollout.robot_plan_grad_sampling import KinematicStateIntegration, RobotPlanGradSampling
+from .batch_rollout.robot_plan_grad_sampling_config import RobotPlanGradSamplingCfg, RobotPlanGradSamplingCfgPPO
 
 TASKS = {
     "anymal_c_rough": (Anymal, AnymalCRoughCfg, AnymalCRoughCfgPPO),      # legged_gym/envs/__init__.py registers Anymal for both

@@ -95,10 +95,10 @@ class RobotBatchRollout(LeggedRobot):
         # the table only holds pointers and sizes: rebuilt when a tensor was rebound, otherwise reused (the ctypes fill
         # costs more host time than the kernel takes)
         key = tuple(getattr(self, f).data_ptr() for f in fields)
-        cached = self._clone_tables.get(mode)
+        cached = self._clone_tables.get((mode, fields))
         if cached is None or cached[0] != key:
             cached = (key,) + self._clone_table(fields, with_cache=mode != _lib.CLONE_SYNC)
-            self._clone_tables[mode] = cached
+            self._clone_tables[(mode, fields)] = cached
         tb, keep = cached[1], cached[2]
         stream = torch.cuda.current_stream(self.device).cuda_stream
         du = self.drift_u

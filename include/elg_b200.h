@@ -353,6 +353,41 @@ int elg_nav_commands(int32_t num_main, int32_t rollouts_per_main, const ElgNavPa
                      uint8_t* goal_reached /*[N] bool*/, float* distance /*[N] or NULL*/, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Kinematic state integration of the planning variant (envs/batch_rollout/robot_plan_grad_sampling.py:103-195
+ * _integrate_state_velocities followed by :197-225 _sync_integration_to_sim -- the reference always calls the pair): for the
+ * selected envs clamp the commanded state velocities (3 linear + 3 angular + D joint), integrate base position, base
+ * orientation (angle-axis increment, quat_mul, renormalise) and joint positions over n_substeps of sub_dt (Euler, or the
+ * reference's "rk4" form), optionally clamp the joints to dof_pos_limits, store the velocities, and write the result
+ * through to root_states / dof_state / base_lin_vel / base_ang_vel.  env_ids == NULL: all num_envs rows, state_vels row r
+ * belongs to env r; otherwise state_vels row r belongs to env env_ids[r]. */
+typedef struct ElgPlanParams {
+  int32_t num_dof;
+  int32_t method;            /* 0 euler, 1 rk4 */
+  int32_t n_substeps;        /* ceil(dt / min(dt, max_integration_step)) */
+  int32_t enforce_joint_limits;
+  float sub_dt;              /* dt / n_substeps */
+  float max_base_lin_vel, max_base_ang_vel, max_joint_vel;
+} ElgPlanParams;
+typedef struct ElgPlanBuffers {
+  float* integration_base_pos;      /* [N,3] */
+  float* integration_base_quat;     /* [N,4] */
+  float* integration_dof_pos;       /* [N,D] */
+  float* integration_base_lin_vel;  /* [N,3] */
+  float* integration_base_ang_vel;  /* [N,3] */
+  float* integration_dof_vel;       /* [N,D] */
+  const float* dof_pos_limits;      /* [D,2] or NULL */
+  float* root_states;               /* [N,13] */
+  float* dof_state;                 /* [N*D,2] */
+  float* base_lin_vel;              /* [N,3] */
+  float* base_ang_vel;              /* [N,3] */
+} ElgPlanBuffers;
+int elg_sizeof_plan_params(void);
+int elg_sizeof_plan_buffers(void);
+/* state_vels == NULL: no integration, only the write-through of the stored integration_* state (_sync_integration_to_sim alone). */
+int elg_integrate_state_velocities(const ElgPlanParams* prm, const ElgPlanBuffers* buf, const float* state_vels /*[rows, 6 + D]*/,
+                                   const int64_t* env_ids, int64_t num_rows, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Actuator-network torques (envs/anymal_c/anymal.py:93-105, the default torque path of the anymal_c_* configs:
  * control.use_actuator_network, mixed_terrains/anymal_c_rough_config.py:68-69).  The TorchScript module
  * resources/actuator_nets/anydrive_v3_lstm.pt is `LSTMsea`: x * in_scale -> 2-layer LSTM(input 2, hidden 8, batch_first, one
