@@ -339,6 +339,36 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
                            "bytes_per_call": act_bytes, "achieved_gbs": act_bytes / sec / 1e9, "frac_of_hbm_peak": act_bytes / sec / 1e9 / peak,
                            "note": "CUDA graph of 50 calls on one state (13.6 MB, L2 resident)"}
     del aenv
+    # caller-side fusion: EmpiricalNormalization (training) + write into the rollout-storage slot + reward / done columns
+    from extended_legged_gym_b200.utils.normalizer import EmpiricalNormalization
+    n_obs_rows, n_obs = 4096, 235
+    norm = EmpiricalNormalization(shape=[n_obs], until=int(1e8)).to(dev)
+    norm.train()
+    xo = torch.randn(n_obs_rows, n_obs, device=dev)
+    slot = torch.empty(24, n_obs_rows, n_obs, device=dev)
+    rw, dn = torch.randn(n_obs_rows, device=dev), torch.zeros(n_obs_rows, device=dev, dtype=torch.bool)
+    rws, dns = torch.empty(24, n_obs_rows, 1, device=dev), torch.empty(24, n_obs_rows, 1, device=dev, dtype=torch.uint8)
+    with torch.cuda.stream(gs):
+        norm.forward_into(xo, slot[0], rw, rws[0], dn, dns[0])
+        gs.synchronize()
+        gn = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gn, stream=gs):
+            for i in range(48):
+                norm.forward_into(xo, slot[i % 24], rw, rws[i % 24], dn, dns[i % 24])
+        gn.replay()
+        gs.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(gs)
+        for _ in range(4):
+            gn.replay()
+        e1.record(gs)
+        gs.synchronize()
+    sec = e0.elapsed_time(e1) * 1e-3 / 192
+    nb = n_obs_rows * n_obs * 4 * 2
+    out["obs_normalize_store"] = {"workload": f"{n_obs_rows} x {n_obs} observations: running mean / var update + normalise + write to the storage slot "
+                                              "(+ reward / done columns), 2 launches", "us_per_call": sec * 1e6, "bytes_per_call": nb,
+                                  "achieved_gbs": nb / sec / 1e9, "frac_of_hbm_peak": nb / sec / 1e9 / peak,
+                                  "note": "CUDA graph of 48 calls cycling over 24 storage slots (92 MB of destinations)"}
     K, D, T = 5, 12, 20
     r = torch.randn(mains, rollouts, T, device=dev)
     u = torch.randn(mains, rollouts, K, D, device=dev)

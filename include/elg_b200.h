@@ -388,6 +388,21 @@ int elg_integrate_state_velocities(const ElgPlanParams* prm, const ElgPlanBuffer
                                    const int64_t* env_ids, int64_t num_rows, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
+ * Caller-side fusion of the step outputs: rsl_rl EmpiricalNormalization.forward
+ * (rsl_rl/modules/normalizer.py:43-75) with the normalised rows written directly to their destination -- e.g. the rollout-storage
+ * slot observations[step] (rsl_rl/storage/rollout_storage.py:95) -- and, optionally, the reward / done columns copied to theirs
+ * (:99-100).  training != 0: the batch statistics update mean / var / std / count first (skipped on the device, without a host
+ * read, once count >= until; until < 0: never stops), exactly the reference's update rule:
+ *   count += N; rate = N / count; d = mean_x - mean; mean += rate d; var += rate (var_x - var + d (mean_x - mean)); std = sqrt(var)
+ * then out = (x - mean) / (std + eps).  mean / var / std are the [1, O] buffers of the module, count its int64 scalar (all on
+ * the device).  `scratch` (elg_normalizer_scratch_bytes(N, O) bytes, 16-byte aligned, caller-owned) is only needed when
+ * training.  out may alias x; out == NULL updates the statistics only (EmpiricalNormalization.update). */
+int64_t elg_normalizer_scratch_bytes(int64_t num_rows, int32_t num_cols);
+int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* x, float* mean, float* var, float* std, int64_t* count, float eps,
+                               int64_t until, int32_t training, float* out, void* scratch, const float* rew /*[N] or NULL*/,
+                               float* rew_out, const uint8_t* dones /*[N] or NULL*/, uint8_t* dones_out, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
  * Actuator-network torques (envs/anymal_c/anymal.py:93-105, the default torque path of the anymal_c_* configs:
  * control.use_actuator_network, mixed_terrains/anymal_c_rough_config.py:68-69).  The TorchScript module
  * resources/actuator_nets/anydrive_v3_lstm.pt is `LSTMsea`: x * in_scale -> 2-layer LSTM(input 2, hidden 8, batch_first, one
