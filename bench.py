@@ -301,6 +301,8 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
     all_us = torch.randn(mains * rollouts, horizon, 12, device=dev) * 0.3
     samples = torch.randn(mains, rollouts, nodes, 12, device=dev)
 
+    env._cache_main_env_states()          # what step() leaves behind: the main rows the rollouts restore after every horizon step
+
     def mppi_iteration():
         rew = rollout_batch(env, all_us)
         return mppi_update(rew.view(mains, rollouts, horizon), samples, 0.05)
@@ -402,15 +404,14 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
     dist = None
-    saved_stdout = None
+    # stdout carries exactly one JSON line: anything a library (NCCL's version / debug lines) or a host class prints on the way
+    # goes to stderr -- fd 1 points at stderr until the result line is due
+    sys.stdout.flush()
+    saved_stdout = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
-        # NCCL writes its version / debug lines to fd 1; they must not land in the JSON stream: stdout points at stderr
-        # until the one result line is due
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=torch.device(dev))
     W = max(args.warmup, 3)
     K = args.steps
@@ -570,9 +571,9 @@ def main():
     if dist:
         dist.barrier()
         dist.destroy_process_group()
-        sys.stdout.flush()
-        os.dup2(saved_stdout, 1)
-        os.close(saved_stdout)
+    sys.stdout.flush()
+    os.dup2(saved_stdout, 1)
+    os.close(saved_stdout)
     if rank == 0:
         print(json.dumps(line), flush=True)
 

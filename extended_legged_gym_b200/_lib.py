@@ -52,6 +52,7 @@ class ElgStepParams(C.Structure):
         ("soft_dof_vel_limit", C.c_float), ("soft_torque_limit", C.c_float), ("speed_min", C.c_float),
         ("stand_still_threshold", C.c_float),
         ("gait_increment", C.c_float), ("gait_swing_height", C.c_float), ("gait_foot_phases", C.c_float * MAX_FEET),
+        ("gait_2_step_hexapod", C.c_int32), ("terminate_upside_down", C.c_int32),
         ("noise_seed", C.c_uint64), ("noise_offset", C.c_uint64)]
 
 

@@ -553,7 +553,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       if (do_term) {
         const bool contact_term = PT > 0 && ACC(kTermHit, e) != 0.0f;
         time_out = s_ep[e] > pr.max_episode_length;
-        reset = contact_term | time_out;
+        reset = contact_term | time_out | (pr.terminate_upside_down && pg[2] > 0.0f);      // (elspider.py:340-345)
         bf.reset_buf[genv] = reset ? 1 : 0;
         bf.time_out_buf[genv] = time_out ? 1 : 0;
       } else if (do_reward) {
@@ -595,15 +595,23 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       if (term_on(pr, ELG_REW_FOUR_FOOTUP)) ACC(ELG_REW_FOUR_FOOTUP, e) = ACC(ELG_REW_FOUR_FOOTUP, e) == 0.0f ? 0.1f : 0.0f;
       if (term_on(pr, ELG_REW_GAIT_SCHEDULER) && !gait) ACC(ELG_REW_GAIT_SCHEDULER, e) = 0.0f;
       if (term_on(pr, ELG_REW_GAIT_2_STEP)) {
-        // gait_2_step (legged_robot_rew_mixin.py:170-206): FL/RR and FR/RL in phase, the rest anti-phase
         const float* ar = s_air + e * F;
         const float* cn = s_con + e * F;
-        const float a0 = F > 0 ? ar[0] : 0.0f, a1 = F > 1 ? ar[1] : 0.0f, a2 = F > 2 ? ar[2] : 0.0f, a3 = F > 3 ? ar[3] : 0.0f;
-        const float c0 = F > 0 ? cn[0] : 0.0f, c1 = F > 1 ? cn[1] : 0.0f, c2 = F > 2 ? cn[2] : 0.0f, c3 = F > 3 ? cn[3] : 0.0f;
         auto sq4 = [](float a, float b) { const float d = a - b; return fminf(d * d, 4.0f); };
-        const float s = ((sq4(a0, a3) + sq4(c0, c3)) + (sq4(a1, a2) + sq4(c1, c2))) / 2.0f;
-        const float a = ((sq4(a0, c1) + sq4(c0, a1)) + (sq4(a0, c2) + sq4(c0, a2)) + (sq4(a3, c2) + sq4(c3, a2)) +
-                         (sq4(a3, c1) + sq4(c3, a1))) / 4.0f;
+        auto sync = [&](int i, int j) { return sq4(ar[i], ar[j]) + sq4(cn[i], cn[j]); };
+        auto anti = [&](int i, int j) { return sq4(ar[i], cn[j]) + sq4(cn[i], ar[j]); };
+        float s, a;
+        if (pr.gait_2_step_hexapod) {
+          // ElSpider (elspider.py:365-408): feet LB LF LM RB RF RM; tripods (0,1,5) and (2,3,4) in phase, anti-phase across
+          const float g1 = ((sync(0, 1) + sync(0, 5)) + sync(1, 5)) / 3.0f;
+          const float g2 = ((sync(2, 3) + sync(2, 4)) + sync(3, 4)) / 3.0f;
+          a = ((((((((anti(0, 2) + anti(0, 3)) + anti(0, 4)) + anti(1, 2)) + anti(1, 3)) + anti(1, 4)) + anti(5, 2)) + anti(5, 3)) + anti(5, 4)) / 9.0f;
+          s = (g1 + g2) / 2.0f;
+        } else {
+          // gait_2_step (legged_robot_rew_mixin.py:170-206): FL/RR and FR/RL in phase, the rest anti-phase
+          s = (sync(0, 3) + sync(1, 2)) / 2.0f;
+          a = (((anti(0, 1) + anti(0, 2)) + anti(3, 2)) + anti(3, 1)) / 4.0f;
+        }
         const float yawish = pr.heading_command ? cmd3 : cmd2;
         const bool moving = (cmd_xy > pr.speed_min) | (fabsf(yawish) >= pr.speed_min / 2.0f);
         ACC(ELG_REW_GAIT_2_STEP, e) = (s + a) * (moving ? 1.0f : 0.0f);
@@ -1019,6 +1027,8 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
   }
   if ((prm->reward_mask >> ELG_REW_BASE_HEIGHT) & 1u)
     if (dims->num_height_points <= 0) return fail(ELG_ERR_UNSUPPORTED, "_reward_base_height needs measured heights");
+  if (((prm->reward_mask >> ELG_REW_GAIT_2_STEP) & 1u) && dims->num_feet < (prm->gait_2_step_hexapod ? 6 : 4))
+    return fail(ELG_ERR_INVALID_ARGUMENT, "_reward_gait_2_step indexes feet 0..3 (0..5 for the hexapod form)");
   const uint32_t lim = (1u << ELG_REW_DOF_POS_LIMITS) | (1u << ELG_REW_DOF_VEL_LIMITS) | (1u << ELG_REW_TORQUE_LIMITS);
   if ((prm->reward_mask & lim) && (!buf->dof_pos_limits || !buf->dof_vel_limits || !buf->torque_limits))
     return fail(ELG_ERR_NULL_POINTER, "limit reward terms need dof_pos_limits, dof_vel_limits and torque_limits");

@@ -5,6 +5,8 @@ from .anymal_c.anymal_c_config import AnymalCRoughCfg, AnymalCRoughCfgPPO, Anyma
 from .anymal_c.anymal import Anymal
 from .a1.a1_config import A1RoughCfg, A1RoughCfgPPO
 from .go2.go2_config import Go2RoughCfg, Go2RoughCfgPPO
+from .elspider_air.elspider_air_config import ElSpiderAirRoughCfg, ElSpiderAirRoughCfgPPO
+from .elspider_air.elspider import ElSpider
 from .batch_rollout.robot_batch_rollout import RobotBatchRollout
 from .batch_rollout.robot_batch_rollout_config import RobotBatchRolloutCfg, RobotBatchRolloutCfgPPO
 from .batch_rollout.robot_batch_rollout_nav import RobotBatchRolloutNav
@@ -17,4 +19,5 @@ TASKS = {
     "anymal_c_flat": (Anymal, AnymalCFlatCfg, AnymalCFlatCfgPPO),
     "a1": (LeggedRobot, A1RoughCfg, A1RoughCfgPPO),
     "go2_rough": (LeggedRobot, Go2RoughCfg, Go2RoughCfgPPO),
+    "elspider_air_rough": (ElSpider, ElSpiderAirRoughCfg, ElSpiderAirRoughCfgPPO),
 }

@@ -12,6 +12,7 @@ loop over the mains plus 14 gather/scatter pairs per call is ONE launch of ``elg
   step_rollout(actions)       :602-716    rollout-env actions in, rollout rows out, mains restored
 """
 import ctypes as C
+import warnings
 
 import numpy as np
 import torch
@@ -133,7 +134,7 @@ class RobotBatchRollout(LeggedRobot):
 
     def _restore_main_env_states(self):
         if self.main_env_cache is None:
-            print("Warning: Attempted to restore main environment states without cache.")
+            warnings.warn("Attempted to restore main environment states without cache.")
             return
         self._clone(_lib.CLONE_RESTORE, CACHE_FIELDS)
         self.sim.set_dof_state()

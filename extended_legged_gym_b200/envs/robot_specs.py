@@ -94,7 +94,20 @@ def go2() -> RobotSpec:
     return spec
 
 
-ROBOTS: Dict[str, callable] = {"anymal_c": anymal_c, "a1": a1, "go2": go2}
+def elspider_air() -> RobotSpec:
+    """el_mini.urdf (resources/robots/el_mini/urdf): hexapod, 6 x (HAA, HFE, KFE); the fixed base -> trunk joint keeps ``trunk`` as
+    the body the config terminates on.  Legs in alphabetical order LB LF LM RB RF RM (the foot order ElSpider._reward_gait_2_step
+    documents, elspider.py:366)."""
+    legs = ["LB", "LF", "LM", "RB", "RF", "RM"]
+    bodies = ["base", "trunk"] + [f"{leg}_{seg}" for leg in legs for seg in ("HIP", "THIGH", "SHANK", "FOOT")]
+    dofs = [f"{leg}_{j}" for leg in legs for j in ("HAA", "HFE", "KFE")]
+    lo, up = [-0.785, -0.5233, -0.6978] * 6, [0.785, 3.14, 3.925] * 6
+    x = {"F": 0.3, "M": 0.0, "B": -0.3}
+    offs = [(x[leg[1]], (0.35 if leg[0] == "L" else -0.35) * (1.2 if leg[1] == "M" else 1.0), -0.25) for leg in legs]
+    return RobotSpec("elspider_air", bodies, dofs, lo, up, [21.0] * 18, [33.5] * 18, offs)
+
+
+ROBOTS: Dict[str, callable] = {"anymal_c": anymal_c, "a1": a1, "go2": go2, "elspider_air": elspider_air, "el_mini": elspider_air}
 
 
 def get_robot_spec(name: str) -> RobotSpec:

@@ -53,7 +53,7 @@ class EmpiricalNormalization(nn.Module):
         if training:
             need = lib.elg_normalizer_scratch_bytes(n, o)
             if self._scratch is None or self._scratch.numel() < need or self._scratch.device != x.device:
-                self._scratch = torch.empty(need, dtype=torch.uint8, device=x.device)
+                self._scratch = torch.zeros(need, dtype=torch.uint8, device=x.device)       # tickets start at zero
             scratch = self._scratch
         until = -1 if self.until is None else int(self.until)
         _lib.check(lib.elg_normalize_observations(n, o, x.data_ptr(), self._mean.data_ptr(), self._var.data_ptr(), self._std.data_ptr(),

@@ -148,6 +148,9 @@ typedef struct ElgStepParams {
   float gait_increment;      /* fp32(dt / period) */
   float gait_swing_height;
   float gait_foot_phases[ELG_MAX_FEET];
+  /* hexapod class ElSpider (envs/elspider_air/elspider.py): */
+  int32_t gait_2_step_hexapod;     /* gait_2_step over the tripods (0,1,5) / (2,3,4) of six feet (:365-408) instead of the quadruped pairs */
+  int32_t terminate_upside_down;   /* reset |= projected_gravity.z > 0 (check_termination :340-345) */
   /* in-kernel noise */
   uint64_t noise_seed;
   uint64_t noise_offset;     /* step counter, so successive steps draw fresh numbers */
@@ -395,8 +398,9 @@ int elg_integrate_state_velocities(const ElgPlanParams* prm, const ElgPlanBuffer
  * read, once count >= until; until < 0: never stops), exactly the reference's update rule:
  *   count += N; rate = N / count; d = mean_x - mean; mean += rate d; var += rate (var_x - var + d (mean_x - mean)); std = sqrt(var)
  * then out = (x - mean) / (std + eps).  mean / var / std are the [1, O] buffers of the module, count its int64 scalar (all on
- * the device).  `scratch` (elg_normalizer_scratch_bytes(N, O) bytes, 16-byte aligned, caller-owned) is only needed when
- * training.  out may alias x; out == NULL updates the statistics only (EmpiricalNormalization.update). */
+ * the device).  `scratch` (elg_normalizer_scratch_bytes(N, O) bytes, 16-byte aligned, caller-owned, ZEROED once before its
+ * first use -- its header holds the completion tickets, which every call leaves at zero again) is only needed when
+ * training.  At most 1920 columns.  out may alias x; out == NULL updates the statistics only (EmpiricalNormalization.update). */
 int64_t elg_normalizer_scratch_bytes(int64_t num_rows, int32_t num_cols);
 int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* x, float* mean, float* var, float* std, int64_t* count, float eps,
                                int64_t until, int32_t training, float* out, void* scratch, const float* rew /*[N] or NULL*/,

@@ -189,8 +189,15 @@ def _r_gait_2_step(o):
     def anti(i, j):
         return _pair_sq(air[:, i], con[:, j]) + _pair_sq(con[:, i], air[:, j])
 
-    s = (sync(0, 3) + sync(1, 2)) / 2
-    a = (anti(0, 1) + anti(0, 2) + anti(3, 2) + anti(3, 1)) / 4
+    if o.elspider:
+        # ElSpider._reward_gait_2_step (envs/elspider_air/elspider.py:365-408): feet LB LF LM RB RF RM, tripods (0,1,5) / (2,3,4)
+        g1 = (sync(0, 1) + sync(0, 5) + sync(1, 5)) / 3
+        g2 = (sync(2, 3) + sync(2, 4) + sync(3, 4)) / 3
+        a = (anti(0, 2) + anti(0, 3) + anti(0, 4) + anti(1, 2) + anti(1, 3) + anti(1, 4) + anti(5, 2) + anti(5, 3) + anti(5, 4)) / 9
+        s = (g1 + g2) / 2
+    else:
+        s = (sync(0, 3) + sync(1, 2)) / 2
+        a = (anti(0, 1) + anti(0, 2) + anti(3, 2) + anti(3, 1)) / 4
     re = s + a
     k = 3 if o.cfg.commands.heading_command else 2
     moving = torch.logical_or(torch.norm(o.commands[:, :2], dim=1) > o.speed_min,
@@ -255,6 +262,9 @@ class LeggedOracle:
     def __init__(self, cfg, spec, state: Dict[str, Tensor], height_samples: Optional[Tensor] = None,
                  use_gait_scheduler: bool = False, rand: Callable = default_rand):
         self.cfg, self.spec, self.rand = cfg, spec, rand
+        # the task registry binds the elspider_air configs to the ElSpider class (envs/elspider_air/elspider.py:225-408): hexapod
+        # gait_2_step, upside-down termination, 18-DOF noise slices
+        self.elspider = getattr(cfg.asset, "name", "") == "elspider_air"
         N = state["root_states"].shape[0]
         D, B = spec.num_dof, spec.num_bodies
         self.num_envs, self.num_dof, self.num_bodies = N, D, B
@@ -422,6 +432,12 @@ class LeggedOracle:
         v[3:6] = ns.ang_vel * lvl * os_.ang_vel
         v[6:9] = ns.gravity * lvl
         v[9:12] = 0.0
+        if self.elspider:      # elspider.py:312-332
+            v[12:30] = ns.dof_pos * lvl * os_.dof_pos
+            v[30:48] = ns.dof_vel * lvl * os_.dof_vel
+            if self.cfg.terrain.measure_heights:
+                v[66:253] = ns.height_measurements * lvl * os_.height_measurements
+            return v
         v[12:24] = ns.dof_pos * lvl * os_.dof_pos
         v[24:36] = ns.dof_vel * lvl * os_.dof_vel
         v[36:48] = 0.0
@@ -510,6 +526,8 @@ class LeggedOracle:
         self.reset_buf = torch.any(torch.norm(f, dim=-1) > 1.0, dim=1)
         self.time_out_buf = self.episode_length_buf > self.max_episode_length
         self.reset_buf |= self.time_out_buf
+        if self.elspider:      # elspider.py:340-345
+            self.reset_buf |= self.projected_gravity[:, 2] > 0
 
     # ---- a6: rewards (legged_robot.py:215-232) ----------------------------------------------------
     def compute_reward(self):

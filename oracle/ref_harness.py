@@ -100,8 +100,11 @@ def reference_classes():
     from legged_gym.envs.anymal_c.flat.anymal_c_flat_config import AnymalCFlatCfg
     from legged_gym.envs.a1.a1_config import A1RoughCfg
     from legged_gym.envs.go2.flat.go2_rough_config import Go2RoughCfg
+    from legged_gym.envs.elspider_air.mixed_terrains.elspider_air_rough_config import ElSpiderAirRoughCfg
+    from legged_gym.envs.elspider_air.elspider import ElSpider
     return dict(LeggedRobot=LeggedRobot, LeggedRobotCfg=LeggedRobotCfg, AnymalCRoughCfg=AnymalCRoughCfg,
-                AnymalCFlatCfg=AnymalCFlatCfg, A1RoughCfg=A1RoughCfg, Go2RoughCfg=Go2RoughCfg)
+                AnymalCFlatCfg=AnymalCFlatCfg, A1RoughCfg=A1RoughCfg, Go2RoughCfg=Go2RoughCfg,
+                ElSpiderAirRoughCfg=ElSpiderAirRoughCfg, ElSpider=ElSpider)
 
 
 # ---------------------------------------------------------------------------------------------

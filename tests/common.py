@@ -11,6 +11,7 @@ from extended_legged_gym_b200.envs import robot_specs as rs
 from extended_legged_gym_b200.envs.a1.a1_config import A1RoughCfg
 from extended_legged_gym_b200.envs.anymal_c.anymal_c_config import AnymalCFlatCfg, AnymalCRoughCfg
 from extended_legged_gym_b200.envs.go2.go2_config import Go2RoughCfg
+from extended_legged_gym_b200.envs.elspider_air.elspider_air_config import ElSpiderAirRoughCfg
 
 RTOL, ATOL = 1e-5, 1e-6
 
@@ -41,7 +42,21 @@ def _all_terms(base_cls, heading=False, only_positive=False):
     return Cfg
 
 
+class ElSpiderPDCfg(ElSpiderAirRoughCfg):
+    """the hexapod config on the PD torque path (the actuator-network path has its own tests) at reward stage 1"""
+    class control(ElSpiderAirRoughCfg.control):
+        use_actuator_network = False
+
+    class terrain(ElSpiderAirRoughCfg.terrain):
+        border_size = 25          # the synthetic height field's border (the reference config's 100 m would clip every scan point)
+
+    class rewards(ElSpiderAirRoughCfg.rewards):
+        reward_min_stage = 1
+
+
 A1AllTermsCfg = _all_terms(A1RoughCfg)
+ElSpiderAllTermsCfg = _all_terms(ElSpiderPDCfg, heading=True)
+ElSpiderAllTermsCfg.rewards.multi_stage_rewards = False
 Go2AllTermsHeadingCfg = _all_terms(Go2RoughCfg, heading=True, only_positive=True)
 
 CASES = {
@@ -51,7 +66,11 @@ CASES = {
     "go2_rough": (Go2RoughCfg, rs.go2, "Go2RoughCfg"),
     "a1_all_terms": (A1AllTermsCfg, rs.a1, None),
     "go2_all_terms_heading": (Go2AllTermsHeadingCfg, rs.go2, None),
+    "elspider_air_rough": (ElSpiderPDCfg, rs.elspider_air, None),
+    "elspider_all_terms": (ElSpiderAllTermsCfg, rs.elspider_air, None),
 }
+# reference class the golden generator runs for a case (default: LeggedRobot)
+REF_ENV_CLASS = {"elspider_air_rough": "ElSpider", "elspider_all_terms": "ElSpider"}
 
 STATE_FIELDS = ["obs_buf", "rew_buf", "reset_buf", "time_out_buf", "episode_length_buf", "base_lin_vel", "base_ang_vel",
                 "base_lin_acc", "base_ang_acc", "projected_gravity", "foot_positions", "foot_velocities", "torques", "commands",

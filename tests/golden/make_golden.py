@@ -34,10 +34,23 @@ def reference_cfg_for(case):
     """Reference config instance carrying exactly the values of our case config."""
     cfg_cls, _, ref_name = common.CASES[case]
     rc = rh.reference_classes()
-    base = ref_name or {"a1_all_terms": "A1RoughCfg", "go2_all_terms_heading": "Go2RoughCfg"}[case]
+    base = ref_name or {"a1_all_terms": "A1RoughCfg", "go2_all_terms_heading": "Go2RoughCfg", "elspider_all_terms": "ElSpiderAirRoughCfg",
+                        "elspider_air_rough": "ElSpiderAirRoughCfg"}[case]
     ref_cfg = rc[base]()
     update_class_from_dict(ref_cfg, class_to_dict(cfg_cls()))
     return ref_cfg
+
+
+def reference_env_for(case, spec, st, hf):
+    """the reference's own class for the case (LeggedRobot, or ElSpider for the hexapod cases) on the synthetic state"""
+    cls = rh.reference_classes()[common.REF_ENV_CLASS[case]] if case in common.REF_ENV_CLASS else None
+    env = rh.make_reference_env(reference_cfg_for(case), spec, st, hf, cls=cls)
+    if cls is not None:
+        # ElSpider.post_physics_step (elspider.py:334-338) also advances a GaitScheduler object its skipped __init__ would have
+        # created; the scheduler does not feed any enabled term of these cases, the harness supplies an inert one
+        from types import SimpleNamespace
+        env.gait_scheduler = SimpleNamespace(step=lambda *a, **k: None)
+    return env
 
 
 def height_field():
@@ -48,7 +61,7 @@ def run_reference(case, n_envs=N_ENVS, steps=STEPS, seed=0, adversarial=True):
     cfg, spec, st = common.make_case_state(case, n_envs, seed=seed, adversarial=adversarial)
     inputs = {k: v.clone() for k, v in st.items()}
     hf = height_field()
-    env = rh.make_reference_env(reference_cfg_for(case), spec, st, hf)
+    env = reference_env_for(case, spec, st, hf)
     g = torch.Generator().manual_seed(1000 + seed)
     out = {}
     for s in range(steps):

@@ -187,3 +187,55 @@ def test_gait_scheduler_reward_inside_the_fused_step():
 def LeggedRobot_compute_torques(env):
     from extended_legged_gym_b200.envs import LeggedRobot
     return LeggedRobot._compute_torques(env, env.actions).view(env.torques.shape)
+
+
+@pytest.mark.gpu
+def test_elspider_class_runs_the_network_on_18_dofs_and_resets_upside_down_envs():
+    """ElSpider (envs/elspider_air/elspider.py:225-408): the same LSTMsea on [N * 18] rows, six feet, upside-down termination"""
+    from extended_legged_gym_b200.envs import TASKS, ElSpider
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    assert TASKS["elspider_air_rough"][0] is ElSpider
+    n = 130
+    cfg, spec, st = common.make_case_state("elspider_air_rough", n, seed=6)
+    cfg.env.num_envs = n
+    cfg.control.use_actuator_network = True
+    cfg.control.actuator_net_weights = GOLDEN
+    cfg.domain_rand.push_robots = False
+    hf = synthetic.make_height_field(seed=0)
+    env = ElSpider(cfg, None, SyntheticSim(cfg, n, DEV, spec=spec, height_samples=hf, state={k: v.clone() for k, v in st.items()}), DEV, True)
+    env.set_env_state(st)
+    assert env.sea_hidden_state_per_env.shape == (2, n, 18, 8) and len(env.feet_indices) == 6 and env.num_obs == 253
+    w, _, _, _ = golden()
+    ora = ActuatorNetOracle(w)
+    g = torch.Generator().manual_seed(2)
+    a = torch.randn(n, 18, generator=g)
+    h, c = env.sea_hidden_state.cpu().clone(), env.sea_cell_state.cpu().clone()
+    t = env._compute_torques(a.to(DEV))
+    torch.cuda.synchronize()
+    tw, hw, cw = ora.compute_torques(a, cfg.control.action_scale, env.default_dof_pos.cpu(), env.dof_pos.cpu(), env.dof_vel.cpu(), h, c)
+    torch.testing.assert_close(t.cpu(), tw, rtol=RTOL, atol=ATOL_TORQUE)
+    torch.testing.assert_close(env.sea_hidden_state.cpu(), hw, rtol=RTOL, atol=ATOL)
+    # a full step: envs whose projected gravity points up are reset although nothing touches the ground and no episode timed out
+    env.contact_forces.zero_()
+    env.episode_length_buf.zero_()
+    obs, _, rew, reset, _ = env.step(torch.randn(n, 18, device=DEV))
+    torch.cuda.synchronize()
+    from oracle import torch_utils as tu
+    q = st["root_states"][:, 3:7]
+    up = tu.quat_rotate_inverse(q, torch.tensor([[0.0, 0.0, -1.0]]).repeat(n, 1))[:, 2] > 0
+    assert torch.equal(reset.cpu(), up) and bool(up.any()) and not bool(up.all())
+    assert torch.isfinite(obs).all() and torch.isfinite(rew).all()
+
+
+def test_gait_2_step_needs_its_feet():
+    """the reward indexes feet 0..3 (0..5 in the hexapod form); fewer feet is an IndexError in the reference, an error code here"""
+    import ctypes as C
+    lib = _lib.load()
+    d, p, b = _lib.ElgDims(), _lib.ElgStepParams(), _lib.ElgStepBuffers()
+    d.num_envs, d.num_dof, d.num_bodies, d.num_feet, d.num_obs, d.num_commands = 8, 12, 13, 4, 48, 4
+    p.reward_mask = 1 << _lib.TERM_ID["gait_2_step"]
+    p.gait_2_step_hexapod = 1
+    for f in _lib.ElgStepBuffers._fields_:
+        setattr(b, f[0], 256)
+    rc = lib.elg_post_physics_step(C.byref(d), C.byref(p), C.byref(b), _lib.PHASE_FUSED, None)
+    assert rc == -1 and b"gait_2_step" in lib.elg_last_error()

@@ -5,8 +5,9 @@ module itself; ABI checks.  gpu: elg_normalize_observations / the EmpiricalNorma
 against the oracle at BASELINE's 4096 x 235 and 65 536 x 48, in-place and storage-slot destinations, `until`, eval mode,
 state_dict interchange, run-to-run bit reproducibility.
 
-Tolerances: state (mean / var / std) rtol 1e-5, atol 1e-6.  The output is a 1e-6-accurate centred value divided by (std + eps), so
-its absolute tolerance is 1e-6 / (std + eps) per column (1e-4 for a constant column, where std = 0 and eps = 0.01)."""
+Tolerances: state (mean / var / std) rtol 1e-5, atol 1e-6.  The output (x - mean) / (std + eps) inherits the state's tolerance,
+dm = 1e-6 + 1e-5 |mean| and ds = 1e-6 + 1e-5 std, amplified by the division:  |d out| <= (dm + |out| ds) / (std + eps) + 1e-5 |out|
+(for a constant column, std = 0 and eps = 0.01, that is 1e-4 per unit of dm)."""
 import ctypes as C
 import os
 import sys
@@ -34,8 +35,9 @@ def assert_state(mean, var, std, count, z, tag, s):
     assert int(count) == int(z[f"{tag}__s{s}__count"])
 
 
-def assert_out(got, want, std):
-    tol = ATOL / (std.cpu().view(1, -1) + EPS) + RTOL * want.abs()
+def assert_out(got, want, std, mean):
+    std, mean = std.cpu().view(1, -1), mean.cpu().view(1, -1)
+    tol = ((ATOL + RTOL * mean.abs()) + want.abs() * (ATOL + RTOL * std)) / (std + EPS) + RTOL * want.abs()
     bad = (got.cpu() - want).abs() > tol
     assert not bool(bad.any()), f"{int(bad.sum())} outputs off, worst {float(((got.cpu() - want).abs() / tol).max()):.2f} x tolerance"
 
@@ -47,7 +49,7 @@ def test_oracle_matches_reference_fixture(tag):
     for s, x in enumerate(no.batches(c["seed"], c["n"], c["o"], 4)):
         y = no.forward(st, x, EPS, c["until"], training=s < 3)
         assert_state(st["mean"], st["var"], st["std"], st["count"], z, tag, s)
-        assert_out(y, torch.from_numpy(z[f"{tag}__s{s}__out"]), st["std"])
+        assert_out(y, torch.from_numpy(z[f"{tag}__s{s}__out"]), st["std"], st["mean"])
 
 
 @pytest.mark.skipif(not os.path.exists(mk.REF), reason="the reference checkout is only present in the build container")
@@ -63,8 +65,8 @@ def test_oracle_matches_live_reference_module():
 
 def test_normalizer_abi_argument_checks():
     lib = _lib.load()
-    assert lib.elg_normalizer_scratch_bytes(4096, 235) == 16 + 4 * 235 * (2 + 3 * 128)
-    assert lib.elg_normalizer_scratch_bytes(100, 48) == 16 + 4 * 48 * (2 + 3 * 4)
+    assert lib.elg_normalizer_scratch_bytes(4096, 235) == 256 + 4 * 235 * (4 + 3 * 32)
+    assert lib.elg_normalizer_scratch_bytes(100, 48) == 256 + 4 * 48 * (4 + 3 * 4)
     call = lib.elg_normalize_observations
     assert call(8, 0, 16, 16, 16, 16, 16, 0.01, -1, 1, 16, 16, None, None, None, None, None) == -1
     assert call(8, 4, None, 16, 16, 16, 16, 0.01, -1, 1, 16, 16, None, None, None, None, None) == -4
@@ -93,7 +95,7 @@ def test_kernel_matches_reference_fixture(tag):
         y = m(x.to(DEV))
         torch.cuda.synchronize()
         assert_state(m._mean, m._var, m._std, m.count, z, tag, s)
-        assert_out(y, torch.from_numpy(z[f"{tag}__s{s}__out"]), m._std)
+        assert_out(y, torch.from_numpy(z[f"{tag}__s{s}__out"]), m._std, m._mean)
 
 
 @pytest.mark.gpu
@@ -116,7 +118,7 @@ def test_kernel_matches_oracle_full_size_and_storage_slot(n, o):
         torch.testing.assert_close(m._var.cpu(), st["var"], rtol=RTOL, atol=ATOL)
         torch.testing.assert_close(m._std.cpu(), st["std"], rtol=RTOL, atol=ATOL)
         assert int(m.count) == st["count"]
-        assert_out(storage[s], want, m._std)
+        assert_out(storage[s], want, m._std, m._mean)
         assert torch.equal(rewards[s].cpu().view(-1), rew) and torch.equal(dones[s].cpu().view(-1).bool(), done)
     # in place, eval mode: state frozen, same arithmetic
     m.eval()
@@ -151,7 +153,7 @@ def test_update_only_until_and_reproducibility():
     no.forward(st, xs[1].cpu(), EPS, 5000)
     want = no.forward(st, xs[2].cpu(), EPS, 5000)
     assert st["count"] == 8192
-    assert_out(runs[0][1], want, st["std"])
+    assert_out(runs[0][1], want, st["std"], st["mean"])
 
 
 @pytest.mark.gpu

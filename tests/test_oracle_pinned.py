@@ -73,7 +73,7 @@ def test_oracle_matches_live_reference(case):
     n, seed = 512, 3
     cfg, spec, st = common.make_case_state(case, n, seed=seed, adversarial=True)
     hf = synthetic.make_height_field(seed=0)
-    env = ref_harness.make_reference_env(make_golden.reference_cfg_for(case), spec, {k: v.clone() for k, v in st.items()}, hf)
+    env = make_golden.reference_env_for(case, spec, {k: v.clone() for k, v in st.items()}, hf)
     ora = LeggedOracle(cfg, spec, {k: v.clone() for k, v in st.items()}, hf)
     for s in range(2):
         torch.manual_seed(step_seed(s, seed))
@@ -97,5 +97,11 @@ def test_configs_match_reference():
     for case, (cfg_cls, _, ref_name) in common.CASES.items():
         if ref_name:
             assert class_to_dict(cfg_cls()) == ref_c2d(rc[ref_name]()), case
+    from extended_legged_gym_b200.envs import ElSpiderAirRoughCfg
+    mine, ref = class_to_dict(ElSpiderAirRoughCfg()), ref_c2d(rc["ElSpiderAirRoughCfg"]())
+    for d in (mine, ref):      # machine-local path of the reference config / a key only this repo's terrain class has
+        d["terrain"].pop("terrain_file", None)
+        d["terrain"].pop("confined_terrain_proportions", None)
+    assert mine == ref, "elspider_air_rough"
     from extended_legged_gym_b200.envs.base.legged_robot_config import LeggedRobotCfg
     assert class_to_dict(LeggedRobotCfg()) == ref_c2d(rc["LeggedRobotCfg"]())

@@ -21,12 +21,13 @@ DEV = "cuda:0"
 
 
 def make_env(cfg, spec, st, hf, oracle=None):
-    from extended_legged_gym_b200.envs import LeggedRobot
+    from extended_legged_gym_b200.envs import ElSpider, LeggedRobot
     from extended_legged_gym_b200.sim_backend import SyntheticSim
     n = st["root_states"].shape[0]
     cfg.env.num_envs = n
     sim = SyntheticSim(cfg, n, DEV, spec=spec, height_samples=hf, state={k: v.clone() for k, v in st.items()})
-    env = LeggedRobot(cfg, None, sim, DEV, True)
+    cls = ElSpider if cfg.asset.name == "elspider_air" else LeggedRobot       # the class the task registry binds the config to
+    env = cls(cfg, None, sim, DEV, True)
     env.set_env_state(st)
     env.fused_reset = False      # the parity tests pin the reference's host-driven reset path and its torch RNG stream
     # host RNG hooks draw from the CPU generator so the sparse paths consume the oracle's numbers
