@@ -12,7 +12,8 @@ timeout 600 python bench.py > $OUT/${TAG}_bench.json 2> $OUT/${TAG}_bench.err; e
 cat $OUT/${TAG}_bench.json
 timeout 300 python bench.py --impl reference --steps 20 --warmup 3 > $OUT/${TAG}_bench_ref.json 2>> $OUT/${TAG}_bench.err
 cat $OUT/${TAG}_bench_ref.json
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 200 --csv --log-file $OUT/${TAG}_launches.csv \
+# launch list of the bench command, restricted to this library's kernels (the set-up alone is > 200 ATen fill / copy launches)
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:elg_ -c 400 --csv --log-file $OUT/${TAG}_launches.csv \
     python bench.py --steps 50 --warmup 3 --e2e-steps 5 --no-cpu-baseline --no-secondary > $OUT/${TAG}_ncu_bench.log 2>&1
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:elg_step_fast -s 10 -c 3 -f -o $OUT/${TAG}_step \
     python bench.py --steps 20 --warmup 3 --e2e-steps 2 --no-cpu-baseline --no-secondary > $OUT/${TAG}_ncu_full.log 2>&1
