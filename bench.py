@@ -371,6 +371,58 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
                                               "(+ reward / done columns), 2 launches", "us_per_call": sec * 1e6, "bytes_per_call": nb,
                                   "achieved_gbs": nb / sec / 1e9, "frac_of_hbm_peak": nb / sec / 1e9 / peak,
                                   "note": "CUDA graph of 48 calls cycling over 24 storage slots (92 MB of destinations)"}
+    # navigation commands and kinematic state integration over the 64 x (1 + 512) rows of config 5 (one launch each)
+    import ctypes as C
+    from extended_legged_gym_b200 import _lib as L
+    from extended_legged_gym_b200.envs import KinematicStateIntegration
+    lib = L.load()
+    n_all = mains * (1 + rollouts)
+    root = torch.randn(n_all, 13, device=dev)
+    root[:, 3:7] /= root[:, 3:7].norm(dim=1, keepdim=True)
+    goals = torch.randn(mains, 3, device=dev)
+    cmds, prevc = torch.zeros(n_all, 4, device=dev), torch.zeros(n_all, 3, device=dev)
+    reached, dist_g = torch.zeros(n_all, dtype=torch.bool, device=dev), torch.zeros(n_all, device=dev)
+    npar = L.ElgNavParams(1, 1, 4, 1, 1.0, 2.0, 1.0, 1.0, 0.1, 0.9, 0.5)
+
+    class Plan(KinematicStateIntegration):
+        pass
+    pl = Plan()
+    pl.total_num_envs, pl.num_dof, pl.device = n_all, 12, dev
+    pl.root_states, pl.dof_state = root.clone(), torch.zeros(n_all * 12, 2, device=dev)
+    pl.base_lin_vel, pl.base_ang_vel = torch.zeros(n_all, 3, device=dev), torch.zeros(n_all, 3, device=dev)
+    pl._init_planning_settings(SimpleNamespace(max_base_lin_vel=3.0, max_base_ang_vel=2.0, max_joint_vel=10.0, integration_method="euler",
+                                               max_integration_step=0.01, enforce_joint_limits=False))
+    pl._init_planning_buffers()
+    pl._sync_sim_to_integration()
+    roll_ids = torch.arange(n_all, device=dev).view(mains, 1 + rollouts)[:, 1:].reshape(-1).contiguous()
+    sv = torch.randn(roll_ids.numel(), 18, device=dev)
+
+    def graph_time(fn, reps=50):
+        with torch.cuda.stream(gs):
+            fn()
+            gs.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, stream=gs):
+                for _ in range(reps):
+                    fn()
+            g.replay()
+            gs.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(gs)
+            for _ in range(4):
+                g.replay()
+            b.record(gs)
+            gs.synchronize()
+        return a.elapsed_time(b) * 1e-3 / (4 * reps)
+
+    sec = graph_time(lambda: L.check(lib.elg_nav_commands(mains, rollouts, C.byref(npar), root.data_ptr(), goals.data_ptr(), cmds.data_ptr(),
+                                                          prevc.data_ptr(), reached.data_ptr(), dist_g.data_ptr(),
+                                                          torch.cuda.current_stream().cuda_stream)))
+    out["nav_commands"] = {"workload": f"{n_all} envs ({mains} mains x (1 + {rollouts})): goal-directed commands + goal flags, one launch", "us_per_call": sec * 1e6}
+    sec = graph_time(lambda: pl._integrate_state_velocities(sv, 0.02, roll_ids))
+    pb = roll_ids.numel() * 4 * (18 + 2 * (7 + 12 + 6 + 12) + 13 + 24 + 6)
+    out["plan_integrate"] = {"workload": f"{roll_ids.numel()} rollout envs, 12 dofs: 2 Euler sub-steps + write-through to root / dof state, one launch",
+                             "us_per_call": sec * 1e6, "bytes_per_call": pb, "achieved_gbs": pb / sec / 1e9}
     K, D, T = 5, 12, 20
     r = torch.randn(mains, rollouts, T, device=dev)
     u = torch.randn(mains, rollouts, K, D, device=dev)
