@@ -1,96 +1,93 @@
-"""ElSpider Air (hexapod, 18 DOF, 6 feet) rough-terrain config
-(legged_gym/legged_gym/envs/elspider_air/mixed_terrains/elspider_air_rough_config.py:36-170 of the reference)."""
+"""ElSpider Air (hexapod: 6 legs x (HAA, HFE, KFE) = 18 DOF) rough-terrain config.  Attribute names and values follow
+legged_gym/legged_gym/envs/elspider_air/mixed_terrains/elspider_air_rough_config.py:36-170 of the reference
+(``tests/test_oracle_pinned.py::test_configs_match_reference`` compares the two dictionaries in the build container)."""
 from ..base.legged_robot_config import LeggedRobotCfg, LeggedRobotCfgPPO
 
-_LEGS = ("RF", "RM", "RB", "LF", "LM", "LB")
+_JOINT_ANGLE = {"HAA": 0.0, "HFE": 0.6, "KFE": 0.6}          # default angle per joint type [rad]
+_JOINT_KP, _JOINT_KD = 80.0, 2.0                             # the ANYdrive PD gains
+_ROOT = "{LEGGED_GYM_ROOT_DIR}/resources"
+
+
+def _per_joint(value_by_type, legs=("LB", "LF", "LM", "RB", "RF", "RM")):
+    return {f"{leg}_{joint}": value for joint, value in value_by_type.items() for leg in legs}
 
 
 class ElSpiderAirRoughCfg(LeggedRobotCfg):
     class env(LeggedRobotCfg.env):
-        num_envs = 4096
         num_actions = 18
-        num_observations = 253        # 12 + 3 x 18 + 187
+        num_observations = 12 + 3 * 18 + 187
+        num_envs = 4096
+
+    class init_state(LeggedRobotCfg.init_state):
+        default_joint_angles = _per_joint(_JOINT_ANGLE)
+        pos = [0.0, 0.0, 0.4]
+
+    class control(LeggedRobotCfg.control):
+        use_actuator_network = True
+        actuator_net_file = _ROOT + "/actuator_nets/anydrive_v3_lstm.pt"
+        action_scale = 0.5
+        decimation = 4
+        stiffness = {joint: _JOINT_KP for joint in _JOINT_ANGLE}
+        damping = {joint: _JOINT_KD for joint in _JOINT_ANGLE}
+
+    class asset(LeggedRobotCfg.asset):
+        name = "elspider_air"
+        file = _ROOT + "/robots/el_mini/urdf/el_mini.urdf"
+        foot_name = "FOOT"
+        terminate_after_contacts_on = ["trunk"]
+        penalize_contacts_on = ["THIGH", "HIP"]
+        flip_visual_attachments = False
+        self_collisions = 0
 
     class terrain(LeggedRobotCfg.terrain):
         mesh_type = "trimesh"
-        border_size = 100
-        curriculum = True
         measure_heights = True
-        terrain_proportions = [0.1, 0.1, 0.3, 0.3, 0.2]
+        curriculum = True
         max_init_terrain_level = 0
-        terrain_length = 8.0
-        terrain_width = 8.0
-        num_rows = 10
-        num_cols = 10
-
-    class init_state(LeggedRobotCfg.init_state):
-        pos = [0.0, 0.0, 0.4]
-        default_joint_angles = {**{f"{leg}_HAA": 0.0 for leg in _LEGS}, **{f"{leg}_HFE": 0.6 for leg in _LEGS},
-                                **{f"{leg}_KFE": 0.6 for leg in _LEGS}}
-
-    class control(LeggedRobotCfg.control):
-        stiffness = {"HAA": 80.0, "HFE": 80.0, "KFE": 80.0}
-        damping = {"HAA": 2.0, "HFE": 2.0, "KFE": 2.0}
-        action_scale = 0.5
-        decimation = 4
-        use_actuator_network = True
-        actuator_net_file = "{LEGGED_GYM_ROOT_DIR}/resources/actuator_nets/anydrive_v3_lstm.pt"
-
-    class asset(LeggedRobotCfg.asset):
-        file = "{LEGGED_GYM_ROOT_DIR}/resources/robots/el_mini/urdf/el_mini.urdf"
-        name = "elspider_air"
-        foot_name = "FOOT"
-        penalize_contacts_on = ["THIGH", "HIP"]
-        terminate_after_contacts_on = ["trunk"]
-        self_collisions = 0
-        flip_visual_attachments = False
+        border_size = 100
+        num_rows, num_cols = 10, 10
+        terrain_length, terrain_width = 8.0, 8.0
+        terrain_proportions = [0.1, 0.1, 0.3, 0.3, 0.2]      # smooth slope, rough slope, stairs up, stairs down, discrete
 
     class domain_rand(LeggedRobotCfg.domain_rand):
-        randomize_base_mass = True
         added_mass_range = [-5.0, 5.0]
+        randomize_base_mass = True
 
     class rewards(LeggedRobotCfg.rewards):
-        base_height_target = 0.25
-        max_contact_force = 500.0
         only_positive_rewards = True
-        multi_stage_rewards = True        # list-valued scales are indexed by the reward stage
+        max_contact_force = 500.0
+        base_height_target = 0.25
+        # two reward stages: a list-valued scale holds one value per stage; the stage advances when the mean episode reward
+        # passes the threshold (LeggedRobotRewMixin.update_reward_scales)
+        multi_stage_rewards = True
+        reward_min_stage, reward_max_stage = 0, 1
         reward_stage_threshold = 5.0
-        reward_min_stage = 0
-        reward_max_stage = 1
 
         class scales(LeggedRobotCfg.rewards.scales):
-            termination = -0.0
-            tracking_lin_vel = 1.0
-            tracking_ang_vel = 0.5
-            lin_vel_z = -2.0
-            ang_vel_xy = -0.05
-            torques = -0.00001
-            dof_vel = -0.0
-            dof_acc = -2.5e-8
-            feet_slip = [-0.0, -0.4]
-            feet_air_time = 1.0
-            collision = -1.0
-            feet_stumble = -0.0
-            stand_still = -0.0
-            dof_pos_limits = -1.0
-            orientation = -0.3
-            action_rate = -0.001
-            gait_2_step = -5.0
+            # tracking
+            tracking_lin_vel, tracking_ang_vel = 1.0, 0.5
+            # base motion and posture
+            lin_vel_z, ang_vel_xy, orientation = -2.0, -0.05, -0.3
             base_height = [-2.0, -4.0]
+            # joints
+            torques, dof_acc, dof_pos_limits, action_rate = -0.00001, -2.5e-8, -1.0, -0.001
+            # feet and contacts
+            feet_air_time, collision, gait_2_step = 1.0, -1.0, -5.0
+            feet_slip = [-0.0, -0.4]
+            # present but switched off
+            termination = dof_vel = feet_stumble = stand_still = -0.0
 
-        class async_gait_scheduler:       # weights of the (disabled) async_gait_scheduler term
-            dof_align = 0.5
-            dof_nominal_pos = [0.1, 0.2]
+        class async_gait_scheduler:       # weights of the async_gait_scheduler term (disabled in scales)
             reward_foot_z_align = [0.2, 0.05]
+            dof_nominal_pos = [0.1, 0.2]
+            dof_align = 0.5
 
         class raibert_planner:            # read by the FootTrackElSpider variant only
             planner_type = 0
-            base_pos_track = 1.0
-            base_quat_track = 0.5
-            foot_pos_track = 0.3
+            foot_pos_track, base_quat_track, base_pos_track = 0.3, 0.5, 1.0
 
 
 class ElSpiderAirRoughCfgPPO(LeggedRobotCfgPPO):
     class runner(LeggedRobotCfgPPO.runner):
-        run_name = ""
         experiment_name = "rough_elspider_air"
+        run_name = ""
