@@ -23,11 +23,12 @@ struct RowIter {
   __device__ RowIter(int W) : e(threadIdx.x / W), w(threadIdx.x % W), qe(kPlanThreads / W), qw(kPlanThreads % W) {}
   __device__ void next(int W) { e += qe; w += qw; if (w >= W) { w -= W; ++e; } }
 };
-__device__ __forceinline__ void gather_rows(float* __restrict__ dst, const float* __restrict__ src, const int64_t* s_id, int n, int W) {
-  for (RowIter it(W); it.e < n; it.next(W)) dst[it.e * W + it.w] = src[s_id[it.e] * W + it.w];
+// (the iterator of a row width is built once per thread and copied: its four integer divisions are the expensive part)
+__device__ __forceinline__ void gather_rows(float* __restrict__ dst, const float* __restrict__ src, const int64_t* s_id, int n, int W, RowIter it) {
+  for (; it.e < n; it.next(W)) dst[it.e * W + it.w] = src[s_id[it.e] * W + it.w];
 }
-__device__ __forceinline__ void scatter_rows(float* __restrict__ dst, const float* __restrict__ src, const int64_t* s_id, int n, int W) {
-  for (RowIter it(W); it.e < n; it.next(W)) dst[s_id[it.e] * W + it.w] = src[it.e * W + it.w];
+__device__ __forceinline__ void scatter_rows(float* __restrict__ dst, const float* __restrict__ src, const int64_t* s_id, int n, int W, RowIter it) {
+  for (; it.e < n; it.next(W)) dst[s_id[it.e] * W + it.w] = src[it.e * W + it.w];
 }
 
 __global__ void __launch_bounds__(kPlanThreads)
@@ -54,19 +55,20 @@ elg_plan_integrate_kernel(const __grid_constant__ ElgPlanParams pr, const __grid
   pdl_wait();
   if (t < n) s_id[t] = env_ids ? env_ids[r0 + t] : r0 + t;
   __syncthreads();
+  const RowIter it3(3), it4(4), it13(13), itD(D), it2D(2 * D);
   // state_vels == NULL: write-through only (_sync_integration_to_sim on its own, :197-225) -- the stored velocities, no sub-steps
   const bool integrate = state_vels != nullptr;
   if (integrate) {
     const float* src = state_vels + r0 * SV;      // the rows of this CTA are contiguous
     for (int i = t; i < n * SV; i += kPlanThreads) s_sv[i] = src[i];
   } else {
-    gather_rows(s_lin, bf.integration_base_lin_vel, s_id, n, 3);
-    gather_rows(s_ang, bf.integration_base_ang_vel, s_id, n, 3);
-    gather_rows(s_dv, bf.integration_dof_vel, s_id, n, D);
+    gather_rows(s_lin, bf.integration_base_lin_vel, s_id, n, 3, it3);
+    gather_rows(s_ang, bf.integration_base_ang_vel, s_id, n, 3, it3);
+    gather_rows(s_dv, bf.integration_dof_vel, s_id, n, D, itD);
   }
-  gather_rows(s_pos, bf.integration_base_pos, s_id, n, 3);
-  gather_rows(s_quat, bf.integration_base_quat, s_id, n, 4);
-  gather_rows(s_dp, bf.integration_dof_pos, s_id, n, D);
+  gather_rows(s_pos, bf.integration_base_pos, s_id, n, 3, it3);
+  gather_rows(s_quat, bf.integration_base_quat, s_id, n, 4, it4);
+  gather_rows(s_dp, bf.integration_dof_pos, s_id, n, D, itD);
   __syncthreads();
   if (t < n) {
     const int nsub = integrate ? pr.n_substeps : 0;
@@ -127,8 +129,9 @@ elg_plan_integrate_kernel(const __grid_constant__ ElgPlanParams pr, const __grid
   }
   if (integrate) {
     // joints: one (env, joint) pair per thread and iteration (:162, :178, :181-186)
-    for (int i = t; i < n * D; i += kPlanThreads) {
-      const int e = i / D, j = i - e * D;
+    RowIter it = itD;
+    for (int i = t; i < n * D; i += kPlanThreads, it.next(D)) {
+      const int e = it.e, j = it.w;
       const float jv = fminf(fmaxf(s_sv[e * SV + 6 + j], -pr.max_joint_vel), pr.max_joint_vel);
       float p = s_dp[i];
       for (int s = 0; s < pr.n_substeps; ++s) p += jv * pr.sub_dt;
@@ -139,19 +142,19 @@ elg_plan_integrate_kernel(const __grid_constant__ ElgPlanParams pr, const __grid
   }
   __syncthreads();
   if (integrate) {
-    scatter_rows(bf.integration_base_pos, s_pos, s_id, n, 3);
-    scatter_rows(bf.integration_base_quat, s_quat, s_id, n, 4);
-    scatter_rows(bf.integration_base_lin_vel, s_lin, s_id, n, 3);
-    scatter_rows(bf.integration_base_ang_vel, s_ang, s_id, n, 3);
-    scatter_rows(bf.integration_dof_pos, s_dp, s_id, n, D);
-    scatter_rows(bf.integration_dof_vel, s_dv, s_id, n, D);
+    scatter_rows(bf.integration_base_pos, s_pos, s_id, n, 3, it3);
+    scatter_rows(bf.integration_base_quat, s_quat, s_id, n, 4, it4);
+    scatter_rows(bf.integration_base_lin_vel, s_lin, s_id, n, 3, it3);
+    scatter_rows(bf.integration_base_ang_vel, s_ang, s_id, n, 3, it3);
+    scatter_rows(bf.integration_dof_pos, s_dp, s_id, n, D, itD);
+    scatter_rows(bf.integration_dof_vel, s_dv, s_id, n, D, itD);
   }
-  scatter_rows(bf.root_states, s_root, s_id, n, 13);
-  scatter_rows(bf.base_lin_vel, s_blv, s_id, n, 3);
-  scatter_rows(bf.base_ang_vel, s_bav, s_id, n, 3);
+  scatter_rows(bf.root_states, s_root, s_id, n, 13, it13);
+  scatter_rows(bf.base_lin_vel, s_blv, s_id, n, 3, it3);
+  scatter_rows(bf.base_ang_vel, s_bav, s_id, n, 3, it3);
   {   // dof_state rows: (pos, vel) pairs interleaved, 2 D floats per env
     const int W = 2 * D;
-    for (RowIter it(W); it.e < n; it.next(W)) {
+    for (RowIter it = it2D; it.e < n; it.next(W)) {
       const int j = it.w >> 1;
       bf.dof_state[s_id[it.e] * W + it.w] = (it.w & 1) ? s_dv[it.e * D + j] : s_dp[it.e * D + j];
     }
