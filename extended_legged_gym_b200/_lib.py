@@ -53,6 +53,7 @@ class ElgStepParams(C.Structure):
         ("stand_still_threshold", C.c_float),
         ("gait_increment", C.c_float), ("gait_swing_height", C.c_float), ("gait_foot_phases", C.c_float * MAX_FEET),
         ("gait_2_step_hexapod", C.c_int32), ("terminate_upside_down", C.c_int32),
+        ("rows_per_main", C.c_int32), ("reserved0", C.c_int32),
         ("noise_seed", C.c_uint64), ("noise_offset", C.c_uint64)]
 
 
@@ -124,12 +125,13 @@ class ElgResetParams(C.Structure):
     _fields_ = [("lin_vel_x", C.c_float * 2), ("lin_vel_y", C.c_float * 2), ("ang_vel_yaw", C.c_float * 2), ("heading", C.c_float * 2),
                 ("heading_command", C.c_int32), ("resample_interval", C.c_int32), ("base_init_state", C.c_float * 13),
                 ("custom_origins", C.c_int32), ("curriculum", C.c_int32), ("env_length_half", C.c_float), ("max_episode_length_s", C.c_float),
-                ("max_terrain_level", C.c_int32), ("terrain_cols", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64)]
+                ("max_terrain_level", C.c_int32), ("terrain_cols", C.c_int32), ("seed", C.c_uint64), ("offset", C.c_uint64),
+                ("rows_per_main", C.c_int32), ("root_z_from_terrain", C.c_int32)]
 
 
 _RESET_FIELDS = ["reset_buf", "root_states", "dof_state", "commands", "env_origins", "terrain_levels", "terrain_types", "terrain_origins",
                  "default_dof_pos", "last_dof_vel", "last_root_vel", "feet_air_time", "feet_contact_time", "episode_length_buf", "episode_sums",
-                 "stats", "obs_buf", "measured_heights", "noise_scale_vec", "noise_u", "uniforms"]
+                 "stats", "stats_accum", "obs_buf", "measured_heights", "noise_scale_vec", "noise_u", "uniforms", "height_samples"]
 
 
 class ElgResetBuffers(C.Structure):
@@ -152,9 +154,11 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
-    if not os.path.exists(path) or os.environ.get("ELG_REBUILD") == "1":
-        path = _build.build()
+    # build() returns at once when the source fingerprint matches the stamp next to the library, so a stale .so is never
+    # loaded after a csrc edit
+    path = _build.build(force=os.environ.get("ELG_REBUILD") == "1")
+    if os.environ.get("ELG_LIB_PATH"):       # diagnostics only (A/B runs against another build of the same ABI, scripts/)
+        path = os.environ["ELG_LIB_PATH"]
     lib = C.CDLL(path)
     lib.elg_last_error.restype = C.c_char_p
     lib.elg_reward_term_name.restype = C.c_char_p
@@ -164,7 +168,7 @@ def load() -> C.CDLL:
                    ("elg_sizeof_reset_buffers", ElgResetBuffers), ("elg_sizeof_nav_params", ElgNavParams),
                    ("elg_sizeof_plan_params", ElgPlanParams), ("elg_sizeof_plan_buffers", ElgPlanBuffers)):
         got = getattr(lib, fn)()
-        if got != C.sizeof(st):
+        if got != C.sizeof(st) and not os.environ.get("ELG_LIB_PATH"):
             raise ElgError(f"ABI mismatch: {fn}() = {got}, python mirror = {C.sizeof(st)}")
     for i, name in enumerate(REWARD_TERMS):
         if lib.elg_reward_term_name(i).decode() != name:
@@ -176,6 +180,9 @@ def load() -> C.CDLL:
     lib.elg_get_heights.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 5 + [vp]
     lib.elg_clone_rows.argtypes = [C.POINTER(ElgCloneTable), C.c_int, C.c_float, vp, C.c_uint64, C.c_uint64, vp]
     lib.elg_set_step_debug.argtypes = [vp]
+    if hasattr(lib, "elg_probe_empty"):
+        lib.elg_probe_empty.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
+        lib.elg_probe_roundtrip.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, vp]
     lib.elg_set_clone_tuning.argtypes = [C.c_int]
     lib.elg_nav_commands.argtypes = [C.c_int32, C.c_int32, C.POINTER(ElgNavParams)] + [vp] * 7
     lib.elg_integrate_state_velocities.argtypes = [C.POINTER(ElgPlanParams), C.POINTER(ElgPlanBuffers), vp, vp, i64, vp]
@@ -198,7 +205,15 @@ def load() -> C.CDLL:
     lib.elg_mppi_costs.argtypes = [vp, i64, i64, C.c_int32, vp, vp]
     lib.elg_mppi_partials.argtypes = [vp, i64, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_float, vp, vp]
     lib.elg_mppi_finish.argtypes = [vp, i64, C.c_int32, vp, vp]
-    lib.elg_resample_commands.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgResetParams), vp, vp, vp, vp]
+    if hasattr(lib, "elg_mppi_update"):
+        lib.elg_mppi_partials_ranked.argtypes = [vp, i64, C.c_int32, C.c_int32, C.c_int32, vp, C.c_int32, C.c_float, vp, vp]
+        lib.elg_comm_unique_id.argtypes = [vp]
+        lib.elg_comm_init.argtypes = [vp, C.c_int, C.c_int, C.POINTER(vp)]
+        lib.elg_comm_destroy.argtypes = [vp]
+        lib.elg_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        lib.elg_episode_stats_allreduce.argtypes = [vp, C.c_int32, vp, vp]
+        lib.elg_mppi_update.argtypes = [vp, vp, i64, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp, vp, vp, vp, vp]
+    lib.elg_resample_commands.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgResetParams), vp, vp, vp, vp, vp]
     lib.elg_reset_envs.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgResetParams), C.POINTER(ElgStepParams), C.POINTER(ElgResetBuffers), vp]
     lib.elg_prepare_height_field.argtypes = [vp, C.c_int32, C.c_int32, C.c_float, vp, vp]
     _lib = lib

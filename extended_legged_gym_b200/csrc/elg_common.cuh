@@ -132,6 +132,16 @@ __device__ __forceinline__ float sample16_dyn(const uint4& r, int s) {
   return (float)((w >> (16 * (s & 1))) & 0xffffu);
 }
 
+// 2 u - 1 for the 16-bit sample s of a Philox block, u = s16 / 65536: the same value as fmaf((float)s16, 1 / 32768, -1) without
+// the integer -> float conversion (a quarter-rate pipe): one byte permute drops s16 into the mantissa of 2^23, so the float is
+// 2^23 + s16 exactly; times 2^-15 it is 256 + s16 / 32768 (24 significant bits, exact), minus 257 exact again.
+__device__ __forceinline__ float sym16(const uint4& r, int s) {
+  const int i = s >> 1;
+  const uint32_t w = i == 0 ? r.x : i == 1 ? r.y : i == 2 ? r.z : r.w;
+  const uint32_t bits = __byte_perm(w, 0x4B000000u, (s & 1) ? 0x7632u : 0x7610u);
+  return fmaf(__uint_as_float(bits), 1.0f / 32768.0f, -257.0f);
+}
+
 // lean fused step for the common quadruped layout (elg_step_fast.cu): returns 1 when it took the launch (*rc = status)
 int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgStepBuffers* buf, uint32_t phase, int cap_override,
                      int flags, long long* dbg, void* stream, int* rc);

@@ -61,14 +61,23 @@ elg_mppi_costs_kernel(const float* __restrict__ rewards, const long long rows, c
   costs[i] = s;
 }
 
-// one CTA per main env
+// one CTA per main env.  costs_all is [num_ranks][M][S_rank] (what ncclAllGather leaves: rank-major blocks); the single-tensor form
+// [M, S_total] is num_ranks == 1.  The local samples are columns [s_first, s_first + S_local) of rank block `rank`.
 __global__ void __launch_bounds__(kMppiThreads)
-elg_mppi_partials_kernel(const float* __restrict__ costs_all, const int S_total, const int s_first, const int S_local,
-                         const float* __restrict__ samples, const int KD, const float temp, float* __restrict__ partial) {
+elg_mppi_partials_kernel(const float* __restrict__ costs_all, const int M, const int num_ranks, const int S_rank, const int rank,
+                         const int s_first, const int S_local, const float* __restrict__ samples, const int KD, const float temp,
+                         float* __restrict__ partial) {
   __shared__ float red[32];
-  extern __shared__ float s_e[];   // [S_local] weights of the local samples
+  extern __shared__ float s_e[];   // [S_total] this main env's costs, then the weights of the local samples in place
   const int m = blockIdx.x;
-  const float* c = costs_all + (size_t)m * S_total;
+  const int S_total = num_ranks * S_rank;
+  float* const c = s_e;
+  for (int s = threadIdx.x; s < S_total; s += blockDim.x) {
+    const int r = s / S_rank;
+    c[s] = costs_all[((size_t)r * M + m) * S_rank + (s - r * S_rank)];
+  }
+  __syncthreads();
+  const int first = rank * S_rank + s_first;
   float acc = 0.0f;
   for (int s = threadIdx.x; s < S_total; s += blockDim.x) acc += c[s];
   const float mean = block_sum(acc, red) / (float)S_total;
@@ -83,10 +92,11 @@ elg_mppi_partials_kernel(const float* __restrict__ costs_all, const int S_total,
   for (int s = threadIdx.x; s < S_total; s += blockDim.x) mx = fmaxf(mx, (c[s] - mean) / denom);
   mx = block_max(mx, red);
   acc = 0.0f;
+  float* const w_e = s_e + S_total;   // [S_local]
   for (int s = threadIdx.x; s < S_local; s += blockDim.x) {
-    const float n = (c[s_first + s] - mean) / denom;
+    const float n = (c[first + s] - mean) / denom;
     const float e = expf((n - mx) / temp);
-    s_e[s] = e;
+    w_e[s] = e;
     acc += e;
   }
   const float sum_e = block_sum(acc, red);
@@ -95,7 +105,7 @@ elg_mppi_partials_kernel(const float* __restrict__ costs_all, const int S_total,
   const float* smp = samples + (size_t)m * S_local * KD;
   for (int j = threadIdx.x; j < KD; j += blockDim.x) {
     float a = 0.0f;
-    for (int s = 0; s < S_local; ++s) a += s_e[s] * smp[(size_t)s * KD + j];
+    for (int s = 0; s < S_local; ++s) a += w_e[s] * smp[(size_t)s * KD + j];
     out[1 + j] = a;
   }
 }
@@ -127,16 +137,17 @@ int elg_mppi_costs(const float* rewards, int64_t num_main, int64_t num_samples, 
   return elg::check_launch("elg_mppi_costs");
 }
 
-int elg_mppi_partials(const float* costs_all, int64_t num_main, int32_t samples_total, int32_t first_local_sample, int32_t samples_local,
-                      const float* samples, int32_t traj_size, float temperature, float* partial, void* stream) {
+static int launch_partials(const float* costs_all, int64_t num_main, int32_t num_ranks, int32_t samples_rank, int32_t rank, int32_t first_local_sample,
+                           int32_t samples_local, const float* samples, int32_t traj_size, float temperature, float* partial, void* stream) {
+  const long long samples_total = (long long)num_ranks * samples_rank;
   if (num_main < 0 || samples_total < 1 || samples_local < 0 || traj_size < 1) return pfail(ELG_ERR_INVALID_ARGUMENT, "bad MPPI sizes");
-  if (first_local_sample < 0 || first_local_sample + samples_local > samples_total)
+  if (first_local_sample < 0 || first_local_sample + samples_local > samples_rank || rank < 0 || rank >= num_ranks)
     return pfail(ELG_ERR_INVALID_ARGUMENT, "local sample range outside [0, samples_total)");
   if (!(temperature > 0.0f)) return pfail(ELG_ERR_INVALID_ARGUMENT, "temperature must be > 0");
   if (num_main == 0) return ELG_OK;
   if (!costs_all || !partial || (samples_local > 0 && !samples)) return pfail(ELG_ERR_NULL_POINTER, "an MPPI buffer is NULL");
-  const size_t smem = 4 * (size_t)(samples_local > 0 ? samples_local : 1);
-  if (smem > 160 * 1024) return pfail(ELG_ERR_UNSUPPORTED, "more than 40960 local samples per main env");
+  const size_t smem = 4 * (size_t)(samples_total + (samples_local > 0 ? samples_local : 1));
+  if (smem > 200 * 1024) return pfail(ELG_ERR_UNSUPPORTED, "more than 51200 samples (all ranks + local) per main env");
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
     if (cudaFuncSetAttribute(elg::elg_mppi_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
@@ -144,8 +155,18 @@ int elg_mppi_partials(const float* costs_all, int64_t num_main, int32_t samples_
     smem_set = smem;
   }
   elg::elg_mppi_partials_kernel<<<(unsigned)num_main, elg::kMppiThreads, smem, (cudaStream_t)stream>>>(
-      costs_all, samples_total, first_local_sample, samples_local, samples, traj_size, temperature, partial);
+      costs_all, (int)num_main, num_ranks, samples_rank, rank, first_local_sample, samples_local, samples, traj_size, temperature, partial);
   return elg::check_launch("elg_mppi_partials");
+}
+
+int elg_mppi_partials(const float* costs_all, int64_t num_main, int32_t samples_total, int32_t first_local_sample, int32_t samples_local,
+                      const float* samples, int32_t traj_size, float temperature, float* partial, void* stream) {
+  return launch_partials(costs_all, num_main, 1, samples_total, 0, first_local_sample, samples_local, samples, traj_size, temperature, partial, stream);
+}
+
+int elg_mppi_partials_ranked(const float* costs_ranked, int64_t num_main, int32_t num_ranks, int32_t rank, int32_t samples_local,
+                             const float* samples, int32_t traj_size, float temperature, float* partial, void* stream) {
+  return launch_partials(costs_ranked, num_main, num_ranks, samples_local, rank, 0, samples_local, samples, traj_size, temperature, partial, stream);
 }
 
 int elg_mppi_finish(const float* partial, int64_t num_main, int32_t traj_size, float* mean_traj, void* stream) {

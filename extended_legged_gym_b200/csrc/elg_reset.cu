@@ -55,12 +55,31 @@ __device__ __forceinline__ void resample_one(const ElgResetParams& rp, float* cm
 
 __global__ void __launch_bounds__(128)
 elg_resample_kernel(const __grid_constant__ ElgResetParams rp, const int N, const int D, const int C, const int64_t* __restrict__ ep_len,
-                    float* __restrict__ commands, const float* __restrict__ uniforms) {
+                    float* __restrict__ commands, const float* __restrict__ uniforms, float* __restrict__ stats_to_zero) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (stats_to_zero && e < ELG_NUM_REWARD_TERMS + 2) stats_to_zero[e] = 0.0f;   // this step's extras["episode"] accumulators
   if (e >= N) return;
-  if ((ep_len[e] + 1) % rp.resample_interval != 0) return;   // the step kernel increments the clock afterwards (:122, :391)
-  Uniforms U{uniforms, rp.seed, rp.offset * 2, (uint32_t)e, make_uint4(0, 0, 0, 0), -1};
-  resample_one(rp, commands + (size_t)e * C, U, D);
+  // main / rollout layout: the clock and the random numbers are the MAIN env's; every row of the group ends up with the main's
+  // command row (robot_batch_rollout.py:819-838 resamples main envs and copies `commands[main]` to its rollouts)
+  const int m = rp.rows_per_main > 0 ? (e / rp.rows_per_main) * rp.rows_per_main : e;
+  if ((ep_len[m] + 1) % rp.resample_interval != 0) return;   // the step kernel increments the clock afterwards (:122, :391)
+  Uniforms U{uniforms, rp.seed, rp.offset * 2, (uint32_t)m, make_uint4(0, 0, 0, 0), -1};
+  float* cmd = commands + (size_t)e * C;
+  if (m != e) {   // the column the resampling leaves alone is copied from the main row as well (nobody writes it in this kernel)
+    const int keep = rp.heading_command ? 2 : 3;
+    if (keep < C) cmd[keep] = commands[(size_t)m * C + keep];
+  }
+  resample_one(rp, cmd, U, D);
+}
+
+// main / rollout layout: does any MAIN env reset in this step?  (reset_idx zeroes the episode sums of the reset rows only then,
+// robot_batch_rollout.py:925-931.)  One CTA; the flag is word ELG_NUM_REWARD_TERMS + 1 of the stats vector.
+__global__ void __launch_bounds__(1024)
+elg_main_reset_flag_kernel(const uint8_t* __restrict__ reset_buf, const int num_main, const int rows_per_main, float* __restrict__ stats) {
+  int any = 0;
+  for (int k = threadIdx.x; k < num_main; k += blockDim.x) any |= reset_buf[(size_t)k * rows_per_main];
+  any = __syncthreads_or(any);
+  if (threadIdx.x == 0) stats[ELG_NUM_REWARD_TERMS + 1] = any ? 1.0f : 0.0f;
 }
 
 // one WARP per env (envs that do not reset leave at once): lane 0 does the scalar work, lanes < D the joints, and all
@@ -73,15 +92,47 @@ elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constan
   const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (e >= N) return;
-  if (!rb.reset_buf[e]) return;
+  // main / rollout layout (robot_batch_rollout.py:876-940): any reset row gets new joints / root / histories; the terrain
+  // curriculum, the command resampling and the extras sums belong to MAIN envs, and a main's new commands go to all its rows
+  const int R1 = rp.rows_per_main;
+  const int m = R1 > 0 ? (e / R1) * R1 : e;
+  const bool is_main = m == e;
+  const bool self_reset = rb.reset_buf[e] != 0;
+  const bool main_reset = is_main ? self_reset : rb.reset_buf[m] != 0;
+  if (!self_reset && !main_reset) return;
   Uniforms U{rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)e, make_uint4(0, 0, 0, 0), -1};
   float* rs = rb.root_states + (size_t)e * 13;
   float* cmd = rb.commands + (size_t)e * C;
   float* org = rb.env_origins + (size_t)e * 3;
   float* ds = rb.dof_state + (size_t)e * D * 2;
+  if (!self_reset) {
+    // a rollout row whose main env resets: only its command row (and the observation entries built from it) change
+    if (lane == 0) {
+      Uniforms Um{rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)m, make_uint4(0, 0, 0, 0), -1};
+      const int keep = rp.heading_command ? 2 : 3;
+      if (keep < C) cmd[keep] = rb.commands[(size_t)m * C + keep];
+      resample_one(rp, cmd, Um, D);
+    }
+    __syncwarp();
+    if (rb.obs_buf && lane >= 9 && lane < 12) {
+      const int k = lane;
+      float v = cmd[k - 9] * pr.commands_scale[k - 9];
+      if (pr.noise_mode == ELG_NOISE_TENSOR) v = v + (2.0f * rb.noise_u[(size_t)e * O + k] - 1.0f) * rb.noise_scale_vec[k];
+      else if (pr.noise_mode == ELG_NOISE_PHILOX) {
+        const int nj = (H + 31) >> 5, hm = (12 + 3 * D + 31) >> 5;
+        const bool share = (nj & 7) + hm <= 8;
+        const uint4 b = noise_block(pr.noise_seed, pr.noise_offset, e, lane, share ? 1 + (nj >> 3) : 0);
+        v = v + sym16(b, share ? (nj & 7) : 0) * rb.noise_scale_vec[k];
+      }
+      if (pr.clip_observations > 0.0f) v = fminf(fmaxf(v, -pr.clip_observations), pr.clip_observations);
+      rb.obs_buf[(size_t)e * O + k] = v;
+    }
+    return;
+  }
+  const bool zero_sums = R1 <= 0 || rb.stats[ELG_NUM_REWARD_TERMS + 1] != 0.0f;
   if (lane == 0) {
     // ---- _update_terrain_curriculum (:498-518): old root position, old commands
-    if (rp.curriculum) {
+    if (rp.curriculum && is_main) {
       const float dist = norm2_t(sub_r(rs[0], org[0]), sub_r(rs[1], org[1]));
       const bool up = dist > rp.env_length_half;
       const bool down = (dist < mul_r(mul_r(norm2_t(cmd[0], cmd[1]), rp.max_episode_length_s), 0.5f)) && !up;
@@ -102,20 +153,37 @@ elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constan
     if (rp.custom_origins) {
       rs[0] = add_r(rs[0], rand_range(-0.5f, 0.5f, U.get(D)));
       rs[1] = add_r(rs[1], rand_range(-0.5f, 0.5f, U.get(D + 1)));
+      if (rp.root_z_from_terrain) {   // (robot_batch_rollout.py:1379-1392): .long() truncation, clip to [0, dim - 2], one cell
+        const long long cx = (long long)div_r(add_r(rs[0], pr.border_size), pr.horizontal_scale);
+        const long long cy = (long long)div_r(add_r(rs[1], pr.border_size), pr.horizontal_scale);
+        const long long px = cx < 0 ? 0 : (cx > pr.hf_rows - 2 ? pr.hf_rows - 2 : cx);
+        const long long py = cy < 0 ? 0 : (cy > pr.hf_cols - 2 ? pr.hf_cols - 2 : cy);
+        rs[2] = add_r(mul_r((float)rb.height_samples[px * pr.hf_cols + py], pr.vertical_scale), rp.base_init_state[2]);
+      }
     }
     for (int k = 0; k < 6; ++k) {
       rs[7 + k] = rand_range(-0.5f, 0.5f, U.get(D + 2 + k));
       rb.last_root_vel[(size_t)e * 6 + k] = rs[7 + k];              // the history copy after the reset (:150)
     }
-    // ---- _resample_commands
-    resample_one(rp, cmd, U, D);
+    // ---- _resample_commands: main envs draw, rollout rows take their main's draw when it resets too
+    if (is_main) {
+      resample_one(rp, cmd, U, D);
+    } else if (main_reset) {
+      Uniforms Um{rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)m, make_uint4(0, 0, 0, 0), -1};
+      const int keep = rp.heading_command ? 2 : 3;
+      if (keep < C) cmd[keep] = rb.commands[(size_t)m * C + keep];
+      resample_one(rp, cmd, Um, D);
+    }
     // ---- timers, episode clock (:191-198)
     for (int f = 0; f < F; ++f) {
       rb.feet_air_time[(size_t)e * F + f] = 0.0f;
       rb.feet_contact_time[(size_t)e * F + f] = 0.0f;
     }
     rb.episode_length_buf[e] = 0;
-    atomicAdd(rb.stats + ELG_NUM_REWARD_TERMS, 1.0f);
+    if (is_main) {
+      atomicAdd(rb.stats + ELG_NUM_REWARD_TERMS, 1.0f);
+      if (rb.stats_accum) atomicAdd(rb.stats_accum + ELG_NUM_REWARD_TERMS, 1.0);
+    }
   }
   // ---- _reset_dofs (:450-465); last_dof_vel = new dof_vel (= 0) after the history copy (:149); last_actions already
   // holds `actions` (zeroed by reset_idx, then overwritten by the history copy :148)
@@ -128,8 +196,11 @@ elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constan
   for (int t = lane; t < ELG_NUM_REWARD_TERMS; t += 32)
     if ((pr.reward_mask >> t) & 1u) {
       float* sp = rb.episode_sums + (size_t)t * N + e;
-      atomicAdd(rb.stats + t, *sp);
-      *sp = 0.0f;
+      if (is_main) {
+        atomicAdd(rb.stats + t, *sp);
+        if (rb.stats_accum) atomicAdd(rb.stats_accum + t, (double)*sp);
+      }
+      if (zero_sums) *sp = 0.0f;
     }
   __syncwarp();
   // ---- observation repair (:234-252 evaluated after the reset)
@@ -192,14 +263,16 @@ int elg_sizeof_reset_params(void) { return (int)sizeof(ElgResetParams); }
 int elg_sizeof_reset_buffers(void) { return (int)sizeof(ElgResetBuffers); }
 
 int elg_resample_commands(const ElgDims* dims, const ElgResetParams* rp, const int64_t* episode_length_buf, float* commands,
-                          const float* uniforms, void* stream) {
+                          const float* uniforms, float* stats_to_zero, void* stream) {
   if (!dims || !rp) return rfail(ELG_ERR_NULL_POINTER, "dims/params is NULL");
   if (rp->resample_interval < 1) return rfail(ELG_ERR_INVALID_ARGUMENT, "resample_interval must be >= 1");
   if (dims->num_dof + 12 > ELG_RESET_UNIFORMS) return rfail(ELG_ERR_UNSUPPORTED, "num_dof + 12 exceeds ELG_RESET_UNIFORMS");
+  if (rp->rows_per_main < 0 || (rp->rows_per_main > 0 && dims->num_envs % rp->rows_per_main != 0))
+    return rfail(ELG_ERR_INVALID_ARGUMENT, "rows_per_main must divide num_envs");
   if (dims->num_envs == 0) return ELG_OK;
   if (!episode_length_buf || !commands) return rfail(ELG_ERR_NULL_POINTER, "episode_length_buf/commands is NULL");
   elg::elg_resample_kernel<<<(dims->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*rp, dims->num_envs, dims->num_dof, dims->num_commands,
-                                                                                         episode_length_buf, commands, uniforms);
+                                                                                         episode_length_buf, commands, uniforms, stats_to_zero);
   return elg::check_launch("elg_resample_commands");
 }
 
@@ -213,8 +286,14 @@ int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepP
     return rfail(ELG_ERR_NULL_POINTER, "a reset buffer is NULL");
   if (rp->curriculum && (!buf->terrain_levels || !buf->terrain_types || !buf->terrain_origins || rp->max_terrain_level < 1 || rp->terrain_cols < 1))
     return rfail(ELG_ERR_INVALID_ARGUMENT, "terrain curriculum needs terrain_levels / types / origins");
+  if (rp->root_z_from_terrain && (!buf->height_samples || prm->hf_rows < 2 || prm->hf_cols < 2))
+    return rfail(ELG_ERR_INVALID_ARGUMENT, "root_z_from_terrain needs height_samples and the terrain geometry");
   if (buf->obs_buf && prm->noise_mode != ELG_NOISE_OFF && !buf->noise_scale_vec) return rfail(ELG_ERR_NULL_POINTER, "noise_scale_vec is NULL");
   if (buf->obs_buf && prm->noise_mode == ELG_NOISE_TENSOR && !buf->noise_u) return rfail(ELG_ERR_NULL_POINTER, "noise_u is NULL");
+  if (rp->rows_per_main < 0 || (rp->rows_per_main > 0 && dims->num_envs % rp->rows_per_main != 0))
+    return rfail(ELG_ERR_INVALID_ARGUMENT, "rows_per_main must divide num_envs");
+  if (rp->rows_per_main > 0)
+    elg::elg_main_reset_flag_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(buf->reset_buf, dims->num_envs / rp->rows_per_main, rp->rows_per_main, buf->stats);
   elg::elg_reset_kernel<<<(dims->num_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*rp, *prm, *buf, dims->num_envs, dims->num_dof, dims->num_feet,
                                                                                       dims->num_commands, dims->num_obs, dims->num_height_points);
   return elg::check_launch("elg_reset_envs");

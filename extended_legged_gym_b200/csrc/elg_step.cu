@@ -553,7 +553,9 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       if (do_term) {
         const bool contact_term = PT > 0 && ACC(kTermHit, e) != 0.0f;
         time_out = s_ep[e] > pr.max_episode_length;
-        reset = contact_term | time_out | (pr.terminate_upside_down && pg[2] > 0.0f);      // (elspider.py:340-345)
+        // main / rollout layout (batch_rollout/robot_batch_rollout.py:857-866): time-outs reset the main rows only
+        const bool to_resets = pr.rows_per_main <= 0 || genv % pr.rows_per_main == 0;
+        reset = contact_term | (time_out & to_resets) | (pr.terminate_upside_down && pg[2] > 0.0f);      // (elspider.py:340-345)
         bf.reset_buf[genv] = reset ? 1 : 0;
         bf.time_out_buf[genv] = time_out ? 1 : 0;
       } else if (do_reward) {

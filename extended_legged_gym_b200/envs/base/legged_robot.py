@@ -186,7 +186,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         # False: the reference's host-driven structure with torch RNG (what the parity tests pin)
         self.fused_reset = True
         self.reset_uniforms = None                # optional [N, 48] uniform table for the fused reset path (tests)
-        self._reset_stats = z(_lib.NUM_REWARD_TERMS + 1)
+        self._reset_stats = z(_lib.NUM_REWARD_TERMS + 2)          # per-term sums, count, (main-reset flag of the rollout layout)
         self._episode_means = z(_lib.NUM_REWARD_TERMS)
         self.episode_stats = None                 # utils.distributed.ShardedEpisodeStats when envs are sharded over GPUs
         self.noise_u = None                       # set to a [N,O] tensor of U[0,1) for torch.rand_like-parity noise
@@ -349,6 +349,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             for i, ph in enumerate(gait.foot_phases[:_lib.MAX_FEET]):
                 p.gait_foot_phases[i] = ph
         p.noise_seed = self.noise_seed
+        p.rows_per_main = int(getattr(self, "_rows_per_main", 0))     # main / rollout layout (RobotBatchRollout), 0 = flat
         return p
 
     def _native_buffers(self):
@@ -480,7 +481,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         dr = self.cfg.domain_rand
         push_step = bool(dr.push_robots and (self.common_step_counter % dr.push_interval == 0))
         cmd_curr = bool(self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0))
-        if self.fused_reset and not self._python_terms and not push_step and not cmd_curr and self.episode_stats is None:
+        if self.fused_reset and not self._python_terms and not push_step and not cmd_curr:
             # the whole step without a host synchronisation: resample -> fused step -> reset (+ observation repair)
             self._launch_resample()
             self._pre_step_hook()
@@ -533,6 +534,8 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             rp.max_terrain_level = int(self.max_terrain_level)
             rp.terrain_cols = int(self.terrain_origins.shape[1])
         rp.max_episode_length_s = self.max_episode_length_s
+        rp.rows_per_main = int(getattr(self, "_rows_per_main", 0))
+        rp.root_z_from_terrain = int(bool(getattr(self, "_reset_z_from_terrain", False) and self.custom_origins))
         rp.seed = self.noise_seed
         b = _lib.ElgResetBuffers()
         t = lambda x: None if x is None else x.data_ptr()
@@ -546,6 +549,9 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         b.episode_length_buf, b.episode_sums, b.stats = t(self.episode_length_buf), t(self._episode_sums_all), t(self._reset_stats)
         b.obs_buf, b.noise_scale_vec = t(self.obs_buf), t(self.noise_scale_vec)
         b.measured_heights = t(self.measured_heights)
+        b.height_samples = t(self.height_samples) if rp.root_z_from_terrain else None
+        # sharded envs: the same (sum, count) also goes into the running totals that are all-reduced once per K steps
+        b.stats_accum = t(self.episode_stats.buf) if self.episode_stats is not None else None
         for name in ("env_origins", "terrain_levels", "terrain_origins", "commands"):
             x = getattr(self, name, None)
             if x is not None and not x.is_contiguous():
@@ -556,7 +562,8 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
 
     def _reset_native_synced(self):
         key = (self._reset_bool.data_ptr(), self.obs_buf.data_ptr(), self.commands.data_ptr(), self.env_origins.data_ptr(),
-               self.root_states.data_ptr(), tuple(self.command_ranges["lin_vel_x"]), self.init_done)
+               self.root_states.data_ptr(), tuple(self.command_ranges["lin_vel_x"]), self.init_done,
+               None if self.episode_stats is None else self.episode_stats.buf.data_ptr())
         if getattr(self, "_reset_key", None) != key:
             self._reset_rp, self._reset_bufs = self._native_reset()
             self._reset_key = key
@@ -569,12 +576,12 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         self._sync_native()
         rp, b = self._reset_native_synced()
         stream = torch.cuda.current_stream(self.device).cuda_stream
+        # (the kernel also zeroes this step's extras["episode"] accumulators, which elg_reset_envs adds to after the step)
         _lib.check(self._lib.elg_resample_commands(C.byref(self._dims), C.byref(rp), self.episode_length_buf.data_ptr(), self.commands.data_ptr(),
-                                                   _lib.ptr(self.reset_uniforms), stream), "elg_resample_commands")
+                                                   _lib.ptr(self.reset_uniforms), self._reset_stats.data_ptr(), stream), "elg_resample_commands")
 
     def _launch_reset(self):
         rp, b = self._reset_native_synced()
-        self._reset_stats.zero_()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._lib.elg_reset_envs(C.byref(self._dims), C.byref(rp), C.byref(self._params), C.byref(b), stream), "elg_reset_envs")
         # extras["episode"] (legged_robot.py:200-213) as device tensors: means over the envs that reset this step; steps
@@ -594,6 +601,10 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             self.extras["time_outs"] = self.time_out_buf
         self.sim.set_dof_state()
         self.sim.set_root_state()
+
+    def _stats_rows(self, env_ids):
+        """Rows whose episode returns enter extras["episode"] (all reset envs; the rollout layout narrows it to main envs)."""
+        return env_ids
 
     def _pre_step_hook(self):
         """Called after the command resampling and before the fused step kernel: the place where a subclass's
@@ -720,7 +731,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         self.episode_length_buf[env_ids] = 0
         self.reset_buf[env_ids] = 1
         if getattr(self, "episode_stats", None) is not None:    # sharded envs: (sum, count) now, all-reduce later (utils/distributed.py)
-            self.episode_stats.accumulate(self.episode_sums, env_ids, self.terrain_levels if self.cfg.terrain.curriculum else None)
+            self.episode_stats.accumulate(self._episode_sums_all, self._stats_rows(env_ids))
         self.extras["episode"] = {}
         for key in self.episode_sums.keys():
             self.extras["episode"]["rew_" + key] = torch.mean(self.episode_sums[key][env_ids]) / self.max_episode_length_s

@@ -34,6 +34,11 @@ class RobotBatchRollout(LeggedRobot):
         self.num_rollout_per_main = cfg.env.rollout_envs
         self.total_num_envs = self.num_main_envs * (1 + self.num_rollout_per_main)
         self.original_num_envs = cfg.env.num_envs
+        # main env k is row k (1 + R): the kernels take the group size (time-outs, command resampling, curriculum and episode
+        # statistics belong to main rows -- :819-838, :857-866, :876-940)
+        self._rows_per_main = 1 + self.num_rollout_per_main
+        # _reset_root_states (:1366-1404) puts a reset robot on the terrain surface below its new xy position
+        self._reset_z_from_terrain = cfg.terrain.mesh_type in ("heightfield", "trimesh")
         cfg.env.num_envs = self.total_num_envs          # every per-env tensor covers mains + rollouts (:77-80)
         try:
             super().__init__(cfg, sim_params, physics_engine, sim_device, headless)
@@ -222,10 +227,100 @@ class RobotBatchRollout(LeggedRobot):
         """``_post_physics_step_callback_rollout`` (robot_batch_rollout.py:868: empty in the base class)"""
 
     def check_termination(self):
-        """:857-866 -- contact termination everywhere, time-outs only OR-ed into the main rows."""
+        """:857-866 -- contact termination everywhere, time-outs only OR-ed into the main rows (the kernel section knows
+        the layout through ``ElgStepParams.rows_per_main``)."""
         super().check_termination()
-        contact_only = self.reset_buf & ~self.time_out_buf
-        self.reset_buf[self.rollout_env_indices] = contact_only[self.rollout_env_indices]
+
+    # ------------------------------------------------------------------------------------------
+    # sparse RNG-driven paths of the main / rollout layout, host-driven form (the fused kernels follow the same rules through
+    # ElgResetParams.rows_per_main / root_z_from_terrain)
+    # ------------------------------------------------------------------------------------------
+    def _group_view(self, t):
+        return t.view(self.num_main_envs, 1 + self.num_rollout_per_main, *t.shape[1:])
+
+    def _propagate_commands(self, main_env_ids):
+        """:827-838 / :903-915 -- every rollout row takes the command row of its main env."""
+        if len(main_env_ids) == 0 or self.num_rollout_per_main == 0:
+            return
+        k = torch.div(main_env_ids, 1 + self.num_rollout_per_main, rounding_mode="floor")
+        g = self._group_view(self.commands)
+        g[k, 1:] = g[k, :1]
+
+    def _post_physics_step_callback(self):
+        """:819-850 -- commands are resampled for MAIN envs only and copied to their rollouts; pushes hit main rows only."""
+        interval = int(self.cfg.commands.resampling_time / self.dt)
+        env_ids = ((self.episode_length_buf + 1) % interval == 0).nonzero(as_tuple=False).flatten()
+        main_env_ids = env_ids[self.is_main_env[env_ids]]
+        if len(main_env_ids) > 0:
+            self._resample_commands(main_env_ids)
+            self._propagate_commands(main_env_ids)
+        dr = self.cfg.domain_rand
+        return bool(dr.push_robots and (self.common_step_counter % dr.push_interval == 0))
+
+    def _push_robots(self):
+        """:1406-1413 -- only main envs are pushed."""
+        mv = self.cfg.domain_rand.max_push_vel_xy
+        self.root_states[self.main_env_indices, 7:9] = self._rand(-mv, mv, (self.num_main_envs, 2))
+        self.sim.set_root_state()
+
+    def _reset_root_states(self, env_ids):
+        """:1366-1404 -- like the base class, plus: with custom origins on a heightfield / trimesh terrain the base height is the
+        terrain height under the new xy position (one cell, no min-of-3) + the nominal height."""
+        self.root_states[env_ids] = self.base_init_state
+        self.root_states[env_ids, :3] += self.env_origins[env_ids]
+        if self.custom_origins:
+            self.root_states[env_ids, :2] += self._rand(-0.5, 0.5, (len(env_ids), 2))
+            if self._reset_z_from_terrain:
+                points = self.root_states[env_ids, :2].clone().unsqueeze(1)
+                points += self.cfg.terrain.border_size
+                points = (points / self.cfg.terrain.horizontal_scale).long()
+                px = torch.clip(points[:, :, 0].view(-1), 0, self.height_samples.shape[0] - 2)
+                py = torch.clip(points[:, :, 1].view(-1), 0, self.height_samples.shape[1] - 2)
+                heights = self.height_samples[px, py] * self.cfg.terrain.vertical_scale
+                self.root_states[env_ids, 2] = heights + self.base_init_state[2]
+        self.root_states[env_ids, 7:13] = self._rand(-0.5, 0.5, (len(env_ids), 6))
+        self.sim.set_root_state_indexed(env_ids.to(dtype=torch.int32))
+
+    def _stats_rows(self, env_ids):
+        return env_ids[self.is_main_env[env_ids]]
+
+    def reset_idx(self, env_ids):
+        """:876-940 -- joints, root and histories of every listed row; terrain curriculum, command resampling (+ copy to the
+        rollouts) and the extras["episode"] means for the MAIN envs among them; the episode sums of the listed rows are
+        cleared only when a main env is among them (the reference's statement order)."""
+        if len(env_ids) == 0:
+            return
+        main_env_ids = env_ids[self.is_main_env[env_ids]]
+        if self.cfg.terrain.curriculum and len(main_env_ids) > 0:
+            self._update_terrain_curriculum(main_env_ids)
+        if self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0):
+            self.update_command_curriculum(main_env_ids)
+        self._reset_dofs(env_ids)
+        self._reset_root_states(env_ids)
+        if len(main_env_ids) > 0:
+            self._resample_commands(main_env_ids)
+            self._propagate_commands(main_env_ids)
+        self.last_actions[env_ids] = 0.0
+        self.last_dof_vel[env_ids] = 0.0
+        self.feet_air_time[env_ids] = 0.0
+        self.feet_contact_time[env_ids] = 0.0
+        self.episode_length_buf[env_ids] = 0
+        self.reset_buf[env_ids] = 1
+        if len(main_env_ids) > 0:
+            if getattr(self, "episode_stats", None) is not None:
+                self.episode_stats.accumulate(self._episode_sums_all, main_env_ids)
+            self.extras["episode"] = {}
+            for key in self.episode_sums.keys():
+                self.extras["episode"]["rew_" + key] = torch.mean(self.episode_sums[key][main_env_ids]) / self.max_episode_length_s
+                self.episode_sums[key][env_ids] = 0.0
+            if self.cfg.terrain.curriculum:
+                self.extras["episode"]["terrain_level"] = torch.mean(self.terrain_levels.float())
+            if self.cfg.commands.curriculum:
+                self.extras["episode"]["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+            if self.cfg.rewards.multi_stage_rewards:
+                self.extras["episode"]["reward_stage"] = float(self.reward_scales_stage)
+            if self.cfg.env.send_timeouts:
+                self.extras["time_outs"] = self.time_out_buf
 
     def set_commands(self, main_env_idx, commands):
         lo = int(main_env_idx) * (1 + self.num_rollout_per_main)

@@ -46,12 +46,37 @@ class _CudaOps:
         return out.reshape(M, *traj_shape)
 
 
-def mppi_update(step_rewards, samples, temperature, group=None, ops=None):
+def mppi_update_native(step_rewards, samples, temperature, comm=None):
+    """The whole update as ONE extension call on the current stream (``elg_mppi_update``): local costs -> ncclAllGather ->
+    weights + partial sums -> ncclAllReduce -> mean trajectories.  ``comm``: utils.distributed.ElgComm or None (one rank).
+    No host synchronisation, CUDA-graph capturable."""
+    r = step_rewards if (step_rewards.dtype == torch.float and step_rewards.is_contiguous()) else step_rewards.float().contiguous()
+    if not r.is_cuda:
+        raise _lib.ElgError("mppi_update has no CPU path: tensors must be CUDA tensors")
+    M, S_local, T = r.shape
+    flat = samples.reshape(M, S_local, -1)
+    flat = flat if (flat.dtype == torch.float and flat.is_contiguous()) else flat.float().contiguous()
+    KD = flat.shape[2]
+    world = comm.world if comm is not None else 1
+    costs = torch.empty(world, M, S_local, device=r.device)
+    partial = torch.empty(M, 1 + KD, device=r.device)
+    out = torch.empty(M, KD, device=r.device)
+    rc = _lib.load().elg_mppi_update(r.data_ptr(), flat.data_ptr(), M, S_local, T, KD, float(temperature), costs.data_ptr(), partial.data_ptr(),
+                                     out.data_ptr(), comm.handle if comm is not None else None, torch.cuda.current_stream(r.device).cuda_stream)
+    _lib.check(rc, "elg_mppi_update")
+    return out.reshape(M, *samples.shape[2:])
+
+
+def mppi_update(step_rewards, samples, temperature, group=None, ops=None, comm=None):
     """step_rewards [M, S_local, T] and samples [M, S_local, K, D] are THIS rank's share of the rollouts of every main
     env (ranks hold equal shares, in rank order); returns the updated mean trajectories [M, K, D], identical on all
-    ranks.  ``ops`` replaces the local GPU stages (tests run the collective plumbing on CPU with the oracle's stages)."""
-    ops = ops or _CudaOps
+    ranks.  With ``comm`` (an ``ElgComm``) or on a single rank the update is one extension call with its collectives on
+    the compute stream; ``ops`` replaces the local GPU stages and routes the exchange through ``torch.distributed``
+    (tests run the collective plumbing on CPU over gloo with the oracle's stages)."""
     world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+    if ops is None and (comm is not None or world == 1):
+        return mppi_update_native(step_rewards, samples, temperature, comm)
+    ops = ops or _CudaOps
     rank = dist.get_rank(group) if world > 1 else 0
     costs = ops.costs(step_rewards)                                    # [M, S_local]
     S_local = costs.shape[1]

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ELG_ABI_VERSION 2
+#define ELG_ABI_VERSION 3
 
 #define ELG_MAX_DOF 32
 #define ELG_MAX_FEET 8
@@ -151,6 +151,10 @@ typedef struct ElgStepParams {
   /* hexapod class ElSpider (envs/elspider_air/elspider.py): */
   int32_t gait_2_step_hexapod;     /* gait_2_step over the tripods (0,1,5) / (2,3,4) of six feet (:365-408) instead of the quadruped pairs */
   int32_t terminate_upside_down;   /* reset |= projected_gravity.z > 0 (check_termination :340-345) */
+  /* main / rollout env layout (envs/batch_rollout/robot_batch_rollout.py:119-164): 0 = flat env list; R1 = 1 + rollouts per main:
+     row r is a main env iff r % R1 == 0.  check_termination (:857-866) ORs time-outs into the main rows only. */
+  int32_t rows_per_main;
+  int32_t reserved0;
   /* in-kernel noise */
   uint64_t noise_seed;
   uint64_t noise_offset;     /* step counter, so successive steps draw fresh numbers */
@@ -233,6 +237,12 @@ int elg_set_step_tuning(int envs_per_chunk, int threads_per_cta, int ctas_per_sm
 /* Diagnostic (no reference counterpart): when set to a device buffer of >= 64 int64, CTA 0 of every following
  * elg_post_physics_step launch records clock64() at its stage boundaries there; NULL switches it off. */
 int elg_set_step_debug(long long* device_stamps);
+
+/* Launch-floor probes (no reference counterpart; csrc/elg_probe.cu): an empty kernel and a pure bulk-copy round trip with the
+ * step kernel's launch shape, so that the fixed cost of one launch in a PDL chain / CUDA graph and the cost of moving the
+ * step's bytes with no arithmetic can be measured on the same box as the step itself (profiles/). */
+int elg_probe_empty(int grid, int threads, int smem_bytes, int pdl, void* stream);
+int elg_probe_roundtrip(const void* src, void* dst, int64_t bytes_in_per_cta, int64_t bytes_out_per_cta, int grid, int pdl, void* stream);
 
 /* LeggedRobot._get_heights (envs/base/legged_robot.py:900-938), standalone. cells_out (optional,
  * int32 [N,H,2]) receives the clipped (px, py) terrain cell of every point for index parity tests. */
@@ -445,6 +455,30 @@ int elg_mppi_partials(const float* costs_all /*[M,S_total]*/, int64_t num_main, 
                       int32_t samples_local, const float* samples /*[M,S_local,traj_size]*/, int32_t traj_size, float temperature,
                       float* partial /*[M, 1 + traj_size]: sum_e, sum_e * sample*/, void* stream);
 int elg_mppi_finish(const float* partial, int64_t num_main, int32_t traj_size, float* mean_traj /*[M,traj_size]*/, void* stream);
+/* the same stage over the rank-major cost layout an all-gather leaves: costs_ranked [num_ranks][M][samples_local] */
+int elg_mppi_partials_ranked(const float* costs_ranked, int64_t num_main, int32_t num_ranks, int32_t rank, int32_t samples_local,
+                             const float* samples, int32_t traj_size, float temperature, float* partial, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * Collectives on the compute stream (csrc/elg_nccl.cu).  ElgComm wraps one ncclComm_t per rank; NCCL is
+ * resolved with dlopen at the first call (the copy torch has mapped when there is one), so a single-GPU process never needs
+ * it.  elg_comm_unique_id fills 128 bytes (ncclUniqueId) on rank 0; the host distributes them and every rank calls
+ * elg_comm_init.  All calls enqueue on `stream`, are CUDA-graph capturable and never synchronise the host.
+ *   elg_episode_stats_allreduce  in-place sum of `n` doubles: the (per-term sums, count, ...) vector elg_reset_envs accumulates
+ *                                (ElgResetBuffers.stats_accum) -> extras["episode"] means of legged_robot.py:200-206 over ALL envs
+ *   elg_mppi_update              cmp_mppi_wbfo.py:216-233 with the rollouts of every main env sharded over the ranks (equal
+ *                                shares, rank order): costs -> all-gather -> weights + partial sums -> all-reduce -> mean trajectories.
+ *                                costs_ranked [world, M, samples_local] and partial [M, 1 + traj_size] are caller scratch.
+ *                                comm == NULL: single rank, no collective. */
+typedef struct ElgComm ElgComm;
+int elg_comm_unique_id(void* out128);
+int elg_comm_init(const void* unique_id128, int rank, int world, ElgComm** out);
+int elg_comm_destroy(ElgComm* comm);
+int elg_comm_info(const ElgComm* comm, int* rank, int* world, int* nccl_version);
+int elg_episode_stats_allreduce(double* stats, int32_t n, ElgComm* comm, void* stream);
+int elg_mppi_update(const float* rewards /*[M,S_local,T]*/, const float* samples /*[M,S_local,traj_size]*/, int64_t num_main, int32_t samples_local,
+                    int32_t horizon, int32_t traj_size, float temperature, float* costs_ranked, float* partial, float* mean_traj /*[M,traj_size]*/,
+                    ElgComm* comm, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Sparse RNG-driven branches as predicated kernels over all envs: no nonzero(), no host synchronisation.
@@ -452,7 +486,8 @@ int elg_mppi_finish(const float* partial, int64_t num_main, int32_t traj_size, f
  * (episode_length_buf + 1) % resample_interval == 0 (call BEFORE elg_post_physics_step, which increments the clock).
  * elg_reset_envs: reset_idx :162-213 for envs with reset_buf set (call AFTER the fused step): terrain curriculum :498-518,
  * _reset_dofs :450-465, _reset_root_states :467-487, _resample_commands, histories / timers / clock, (sum, count) of the
- * episode sums for extras["episode"] into stats[ELG_NUM_REWARD_TERMS + 1] (atomics; caller zeroes it), episode sums zeroed,
+ * episode sums for extras["episode"] into stats (atomics; zeroed by elg_resample_commands when it is given the pointer, else by
+ * the caller), episode sums zeroed,
  * and the command / dof_pos / dof_vel observation entries recomputed (obs_buf may be NULL).
  * update_command_curriculum (:520-531) stays on the host (it edits Python-side ranges once per max_episode_length steps). */
 #define ELG_RESET_UNIFORMS 48   /* columns of the optional per-env uniform table: see csrc/elg_reset.cu */
@@ -468,6 +503,14 @@ typedef struct ElgResetParams {
   int32_t max_terrain_level;
   int32_t terrain_cols;          /* second dim of terrain_origins */
   uint64_t seed, offset;         /* Philox key / step counter when no uniform table is given */
+  /* main / rollout env layout (envs/batch_rollout/robot_batch_rollout.py): 0 = flat env list; R1 = 1 + rollouts per main.
+   * Commands are resampled for MAIN envs only (clock / reset flag of the main row) and copied to every row of the group
+   * (:819-838, :900-915); the terrain curriculum and the extras["episode"] sums cover main rows only (:884-887, :925-931);
+   * episode sums of the reset rows are zeroed only when at least one main env resets in the step (:925-931). */
+  int32_t rows_per_main;
+  /* RobotBatchRollout._reset_root_states (:1366-1404): with custom origins on a heightfield / trimesh terrain the new base height is
+   * height_samples[cell(x, y)] * vertical_scale + base_init_state[2] (single cell, no min-of-3; terrain geometry from ElgStepParams) */
+  int32_t root_z_from_terrain;
 } ElgResetParams;
 typedef struct ElgResetBuffers {
   const uint8_t* reset_buf;      /* [N] bool */
@@ -485,17 +528,20 @@ typedef struct ElgResetBuffers {
   float* feet_contact_time;      /* [N,F] */
   int64_t* episode_length_buf;   /* [N] */
   float* episode_sums;           /* [ELG_NUM_REWARD_TERMS, N] */
-  float* stats;                  /* [ELG_NUM_REWARD_TERMS + 1] */
+  float* stats;                  /* [ELG_NUM_REWARD_TERMS + 2]: per-term sums, count; word [NUM + 1] is scratch (main-reset flag) */
+  double* stats_accum;           /* [ELG_NUM_REWARD_TERMS + 1] or NULL: the same (sum, count) added on top of what is there -- the
+                                    running totals a sharded run all-reduces once per K steps (elg_episode_stats_allreduce) */
   float* obs_buf;                /* [N,O] or NULL */
   const float* measured_heights; /* [N,H] (stale heights the repaired height observations are built from) or NULL */
   const float* noise_scale_vec;  /* [O] */
   const float* noise_u;          /* [N,O] (ELG_NOISE_TENSOR) or NULL */
   const float* uniforms;         /* [N, ELG_RESET_UNIFORMS] or NULL (Philox) */
+  const int16_t* height_samples; /* [rows, cols]; only read with root_z_from_terrain */
 } ElgResetBuffers;
 int elg_sizeof_reset_params(void);
 int elg_sizeof_reset_buffers(void);
 int elg_resample_commands(const ElgDims* dims, const ElgResetParams* rp, const int64_t* episode_length_buf, float* commands,
-                          const float* uniforms, void* stream);
+                          const float* uniforms, float* stats_to_zero /* [ELG_NUM_REWARD_TERMS + 2] or NULL */, void* stream);
 int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepParams* prm, const ElgResetBuffers* buf, void* stream);
 
 /* Init-time helper for _get_heights (envs/base/legged_robot.py:932-938): out[i][j] =

@@ -96,3 +96,101 @@ STATE_KEYS = ("root_states", "dof_state", "actions", "last_actions", "last_dof_v
 
 def snapshot(o):
     return {k: getattr(o, k).clone() for k in STATE_KEYS}
+
+
+# =====================================================================================================================
+# the main / rollout variant of the per-step path: RobotBatchRollout.post_physics_step and what it calls
+# (envs/batch_rollout/robot_batch_rollout.py:718-761, :819-850, :857-866, :876-940, :1366-1413, :1644-1651)
+# =====================================================================================================================
+from .legged_oracle import LeggedOracle  # noqa: E402
+
+
+class BatchRolloutOracle(LeggedOracle):
+    """``LeggedOracle`` with the deltas of the reference's ``RobotBatchRollout``: rows are ``num_main`` groups of
+    ``1 + rollouts`` envs (main first).  Commands are resampled for main envs and copied to their rollouts; time-outs reset
+    main rows only; pushes hit main rows only; ``reset_idx`` runs the terrain curriculum / command resampling / extras for
+    the main envs among the reset rows, drops a reset robot onto the terrain surface, and clears episode sums only when a
+    main env resets.  ``tests/test_rollout_step.py`` pins it to the unmodified reference methods (container) and to
+    ``tests/golden/rollout_step.npz``."""
+
+    def __init__(self, cfg, spec, state, height_samples, num_main, rollouts, **kw):
+        super().__init__(cfg, spec, state, height_samples, **kw)
+        import numpy as np
+        self.num_main_envs, self.num_rollout_per_main, self.total_num_envs = num_main, rollouts, self.num_envs
+        assert self.num_envs == num_main * (1 + rollouts)
+        init_env_indices(self)
+        # _parse_cfg (:1644-1651): episode length in whole steps, integer push interval
+        self.max_episode_length_s = self.max_episode_length * self.dt
+        self.push_interval = int(cfg.domain_rand.push_interval_s / self.dt)
+        self.stand_still_threshold = 0.1      # robot_batch_rollout_rew_mixin.py:152 (literal instead of speed_min)
+        self.reset_z_from_terrain = cfg.terrain.mesh_type in ("heightfield", "trimesh")
+
+    def _propagate(self, main_ids):
+        for m in main_ids.tolist():           # (:827-838)
+            self.commands[m + 1:m + 1 + self.num_rollout_per_main] = self.commands[m].clone()
+
+    def callback(self):
+        ids = (self.episode_length_buf % int(self.cfg.commands.resampling_time / self.dt) == 0).nonzero(as_tuple=False).flatten()
+        main_ids = ids[torch.isin(ids, self.main_env_indices)]
+        if len(main_ids) > 0:
+            self.resample_commands(main_ids)
+            self._propagate(main_ids)
+        if self.cfg.commands.heading_command:
+            self.heading_command()
+        if self.measure_heights:
+            self.measured_heights = self.get_heights()
+        if self.cfg.domain_rand.push_robots and (self.common_step_counter % self.push_interval == 0):
+            mv = self.cfg.domain_rand.max_push_vel_xy      # (:1406-1413) main envs only
+            self.root_states[self.main_env_indices, 7:9] = self.rand(-mv, mv, (self.num_main_envs, 2))
+
+    def check_termination(self):
+        f = self.contact_forces[:, self.termination_contact_indices, :]
+        self.reset_buf = torch.any(torch.norm(f, dim=-1) > 1.0, dim=1)
+        self.time_out_buf = self.episode_length_buf > self.max_episode_length
+        self.reset_buf[self.main_env_indices] |= self.time_out_buf[self.main_env_indices]
+
+    def reset_idx(self, env_ids):
+        if len(env_ids) == 0:
+            return
+        main_ids = env_ids[torch.isin(env_ids, self.main_env_indices)]
+        if self.curriculum and len(main_ids) > 0:
+            self._terrain_curriculum(main_ids)
+        if self.cfg.commands.curriculum and (self.common_step_counter % self.max_episode_length == 0):
+            self._command_curriculum(main_ids)
+        n = len(env_ids)
+        self.dof_pos[env_ids] = self.default_dof_pos * self.rand(0.5, 1.5, (n, self.num_dof))
+        self.dof_vel[env_ids] = 0.0
+        self.root_states[env_ids] = self.base_init_state
+        self.root_states[env_ids, :3] += self.env_origins[env_ids]
+        if self.custom_origins:               # (:1369-1390)
+            self.root_states[env_ids, :2] += self.rand(-0.5, 0.5, (n, 2))
+            if self.reset_z_from_terrain:
+                points = self.root_states[env_ids, :2].clone().unsqueeze(1)
+                points += self.cfg.terrain.border_size
+                points = (points / self.cfg.terrain.horizontal_scale).long()
+                px = torch.clip(points[:, :, 0].view(-1), 0, self.height_samples.shape[0] - 2)
+                py = torch.clip(points[:, :, 1].view(-1), 0, self.height_samples.shape[1] - 2)
+                self.root_states[env_ids, 2] = self.height_samples[px, py] * self.cfg.terrain.vertical_scale + self.base_init_state[2]
+        self.root_states[env_ids, 7:13] = self.rand(-0.5, 0.5, (n, 6))
+        if len(main_ids) > 0:
+            self.resample_commands(main_ids)
+            self._propagate(main_ids)
+        self.last_actions[env_ids] = 0.0
+        self.last_dof_vel[env_ids] = 0.0
+        self.feet_air_time[env_ids] = 0.0
+        self.feet_contact_time[env_ids] = 0.0
+        self.episode_length_buf[env_ids] = 0
+        self.reset_buf[env_ids] = 1
+        if len(main_ids) > 0:
+            self.extras["episode"] = {}
+            for key in self.episode_sums.keys():
+                self.extras["episode"]["rew_" + key] = torch.mean(self.episode_sums[key][main_ids]) / self.max_episode_length_s
+                self.episode_sums[key][env_ids] = 0.0
+            if self.curriculum:
+                self.extras["episode"]["terrain_level"] = torch.mean(self.terrain_levels.float())
+            if self.cfg.commands.curriculum:
+                self.extras["episode"]["max_command_x"] = self.command_ranges["lin_vel_x"][1]
+            if self.cfg.rewards.multi_stage_rewards:
+                self.extras["episode"]["reward_stage"] = float(self.cfg.rewards.reward_min_stage)
+            if self.cfg.env.send_timeouts:
+                self.extras["time_outs"] = self.time_out_buf

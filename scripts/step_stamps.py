@@ -4,8 +4,11 @@ import ctypes as C, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "scripts"))
 import torch
+from extended_legged_gym_b200 import build as _build
+# the product library carries no stamp code: build the diagnostic variant and load that one
+os.environ["ELG_LIB_PATH"] = _build.build(defines=("ELG_STEP_STAMPS",), out=os.path.join(_build.PKG_DIR, "libelg_b200_stamps.so"))
 from step_sweep import make, lib, dev, _lib
-names = {0: "entry", 1: "after griddepcontrol.wait", 2: "loads landed (warp 0)", 3: "phase A done (warp 0)", 4: "B1 passed", 5: "row0: gathers issued",
+names = {0: "entry", 1: "after griddepcontrol.wait", 2: "root_states landed (warp 0)", 3: "phase A done (warp 0)", 4: "B1 passed", 5: "row0: gathers issued (before phase A)",
          6: "row0: scan done", 7: "row0: head done", 8: "assembly warp done", 9: "B2 passed", 10: "stores read out (warp 0)", 11: "warp 0 reaches the TMA wait", 12: "loads landed (last warp, idle until then)"}
 for case, n in (("anymal_c_rough", 4096), ("anymal_c_flat", 4096)):
     env = make(case, n, 0)

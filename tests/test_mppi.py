@@ -62,18 +62,21 @@ def _worker(rank, world, port, tag, q):
         got = mppi_update(r[:, lo:hi], u[:, lo:hi], temp, ops=OracleOps)
         full = mo.mppi_update(r[:, :S], u[:, :S], temp)
         ok_mppi = torch.allclose(got, full, rtol=1e-5, atol=1e-6)
-        # episode statistics: 10 envs split 2 ways, different resets per rank
-        N = 10
-        sums = {"a": torch.arange(N, dtype=torch.float) * 1.5, "b": torch.ones(N) * 2}
+        # episode statistics: 10 envs split 2 ways, different resets per rank; SoA [terms, N] like LeggedRobot._episode_sums_all
+        from extended_legged_gym_b200 import _lib
+        N, nt = 10, _lib.NUM_REWARD_TERMS
+        full_sums = torch.zeros(nt, N)
+        full_sums[_lib.TERM_ID["torques"]] = torch.arange(N, dtype=torch.float) * 1.5
+        full_sums[_lib.TERM_ID["dof_acc"]] = 2.0
         lo, hi = shard_range(N, rank, world)
-        local = {k: v[lo:hi].clone() for k, v in sums.items()}
         resets_global = torch.tensor([1, 2, 7, 8, 9])
         mine = resets_global[(resets_global >= lo) & (resets_global < hi)] - lo
-        st = ShardedEpisodeStats(["a", "b"], "cpu")
-        st.accumulate(local, mine, terrain_levels=torch.arange(lo, hi))
-        out = st.reduce(20.0)
-        want_a = sums["a"][resets_global].mean() / 20.0
-        ok_stats = abs(float(out["rew_a"]) - float(want_a)) < 1e-6 and out["num_resets"] == 5 and abs(float(out["terrain_level"]) - 4.5) < 1e-6
+        st = ShardedEpisodeStats("cpu")
+        st.accumulate(full_sums[:, lo:hi].clone(), mine)
+        out = st.reduce(20.0, terrain_levels=torch.arange(lo, hi), names=["torques", "dof_acc"])
+        want_a = full_sums[_lib.TERM_ID["torques"]][resets_global].mean() / 20.0
+        ok_stats = (abs(float(out["rew_torques"]) - float(want_a)) < 1e-6 and abs(float(out["rew_dof_acc"]) - 0.1) < 1e-6 and
+                    int(out["num_resets"]) == 5 and abs(float(out["terrain_level"]) - 4.5) < 1e-6 and float(st.buf.abs().sum()) == 0.0)
         q.put((rank, bool(ok_mppi), bool(ok_stats)))
     finally:
         dist.destroy_process_group()
