@@ -7,17 +7,22 @@ Metric: env-steps/s of the fused post-physics step.  One "step" = one pass of th
 batch of synthetic PhysX state = 1x _compute_torques + the post_physics_step body (derive, heading,
 187-point height scan, termination, the reward registry, observations with in-kernel noise, history)
 -- SURVEY.md section 8d.  Workload at N=1: BASELINE configs[1], anymal_c_rough, 4096 envs, one B200.
-For N>1 the envs shard across ranks with no data-path collective (weak scaling: 4096 envs per GPU);
-episode statistics are reduced with one NCCL all-reduce per timed region.
+For N>1 the envs shard across ranks with no data-path collective (weak scaling: 4096 envs per GPU); the one genuine
+reduction of the path -- the episode statistics -- is an NCCL all-reduce issued by the extension on the compute stream as
+the LAST NODE OF THE TIMED GRAPH (one per K steps).  `secondary` carries BASELINE configs[2]
+(a1 rough, 65 536 envs in total, strong-scaled over the ranks, reset path + statistics all-reduce inside the timed region),
+configs[3] (depth camera) and configs[4] (MPPI: 64 mains x 512 rollouts in total, sharded over the ranks).
 
-  value     device-resident throughput: K steps (2 kernels each) replayed from one CUDA graph, CUDA events,
-            max over ranks.  Every step works on a different replica of the state (R replicas, > 2x L2 in
+  value     device-resident throughput: K steps (2 kernels each) + the statistics all-reduce replayed from one CUDA graph,
+            CUDA events, max over ranks.  Every step works on a different replica of the state (R replicas, > 2x L2 in
             total) so no step finds its inputs in L2.
   e2e       the same step through the public Python API (LeggedRobot._compute_torques + post_physics_step)
-            with the PhysX state in pinned HOST memory: H2D of the state + actions and D2H of obs / rew /
-            reset inside the timed region, every step.
+            with the PhysX state in pinned HOST memory: ONE H2D of the packed state + actions block and ONE D2H of the
+            packed obs / rew / reset block inside the timed region, every step.
   roofline  step kernel alone (same graph technique), algorithmic bytes of SURVEY.md section 8d over its
-            mean launch duration, against MEASURED_PEAKS.json hbm_gbs.
+            mean launch duration, against MEASURED_PEAKS.json hbm_gbs: cold L2 (`frac`) and steady state (one replica,
+            L2-resident, `steady_state`), next to the launch floor measured in the same run (`floor`: an empty PDL kernel and
+            a pure bulk-copy round trip of the step's bytes with the step's launch shape).
   cpu_baseline  the oracle port of the reference's torch-CPU implementation on this box's host cores.
 
 --impl reference runs ONLY that CPU implementation (all host threads) and prints the same line shape.
@@ -70,11 +75,15 @@ class ClockSampler:
 
     def __init__(self, index=0):
         self.index, self.rows, self.proc = index, [], None
+        try:      # CUDA_VISIBLE_DEVICES may renumber the devices: address the GPU by its uuid
+            self.index = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+        except Exception:
+            pass
 
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "10"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
@@ -104,7 +113,7 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "period_ms": 10}
 
 
 # ----------------------------------------------------------------------------------------------
@@ -128,27 +137,58 @@ def cpu_reference_run(case, common, n_envs, steps, warmup, threads):
     return n_envs / med, med, sum(ts)
 
 
+def workload_config(config, n_envs, world, H=None, O=None, R_terms=None, n_rep=None, bytes_per_step=None):
+    """`config` of the JSON line -- the SAME dict for both arms (what differs between them lives outside it)."""
+    return {"workload": f"{config} post-physics step (torques+derive+heights+termination+rewards+obs+noise+history), {n_envs} envs per GPU",
+            "num_envs_per_gpu": n_envs, "num_envs_total": n_envs * world,
+            "sharding": f"envs x{world}, no data-path collective; episode statistics all-reduced once per K steps"}
+
+
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    world = int(os.environ.get("WORLD_SIZE", str(args.gpus)))
     case, common = case_for(args.config)
     threads = os.cpu_count() or 1
     steps = max(args.steps, 3)
     value, med, _ = cpu_reference_run(case, common, args.envs, min(steps, 200), max(args.warmup, 3), threads)
+    sample = (f"{args.envs} envs x {min(steps, 200)} steps, median step, oracle port of the reference's torch-CPU code on {threads} threads" +
+              ("" if world == 1 else f" (a bounded sample: one GPU's share of the {args.envs * world}-env workload; throughput, not the same total work)"))
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": min(steps, 200),
             "warmup": max(args.warmup, 3), "ms_per_step": med * 1e3, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config} post-physics step, {args.envs} envs, torch-CPU (oracle port of the reference)",
-                       "num_envs": args.envs},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
-                             "sample": f"full workload: {args.envs} envs x {min(steps, 200)} steps, median step"},
+            "config": workload_config(args.config, args.envs, world),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
 
 
 # ----------------------------------------------------------------------------------------------
-def build_replicas(case, common, n_envs, n_rep, dev):
+def pin_to_gpu_numa_node(local_rank):
+    """Best effort: run this rank (and first-touch its pinned buffers) on the NUMA node its GPU hangs off."""
+    try:
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = torch.cuda.get_device_properties(local_rank).pci_domain_id
+        dev_id = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev_id:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:
+        return None
+    return None
+
+
+def build_replicas(case, common, n_envs, n_rep, dev, packed=False):
     from extended_legged_gym_b200 import _lib, synthetic
     from extended_legged_gym_b200.envs import LeggedRobot
     from extended_legged_gym_b200.sim_backend import SyntheticSim
@@ -157,8 +197,10 @@ def build_replicas(case, common, n_envs, n_rep, dev):
     for r in range(n_rep):
         cfg, spec, st = common.make_case_state(case, n_envs, seed=r)
         cfg.env.num_envs = n_envs
-        sim = SyntheticSim(cfg, n_envs, dev, spec=spec, height_samples=hf, state=st)
+        sim = SyntheticSim(cfg, n_envs, dev, spec=spec, height_samples=hf, state=st, packed=packed)
         env = LeggedRobot(cfg, None, sim, dev, True)
+        if packed:
+            env.actions = sim.actions_in
         env.set_env_state(st)
         env.noise_u = None           # in-kernel Philox noise (0 algorithmic bytes)
         env._sync_native()
@@ -167,7 +209,7 @@ def build_replicas(case, common, n_envs, n_rep, dev):
 
 
 # ----------------------------------------------------------------------------------------------
-def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
+def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, comm=None, K=200):
     """The other kernels of the path at the BASELINE configs 4 and 5 (reported next to the headline, not in `value`):
     depth-camera ray casting (Mrays/s), the main -> rollout clone, the MPPI update (+ its collectives when N > 1)."""
     import numpy as np
@@ -235,6 +277,81 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
     del cam
     if only_depth:
         return out
+    import ctypes as C
+    from extended_legged_gym_b200 import _lib as L
+    lib = L.load()
+    peak, _ = peaks()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    # ---- config 3: a1 rough, 65 536 envs IN TOTAL, strong-scaled over the ranks (contiguous env blocks).  One timed iteration =
+    # K steps through the public API's sync-free form (torques, command resampling, fused step, in-kernel reset -- whose episode
+    # statistics accumulate on the device) + ONE ncclAllReduce of those statistics on the same stream; all of it one CUDA graph.
+    import common
+    from extended_legged_gym_b200.envs import LeggedRobot
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    from extended_legged_gym_b200.utils.distributed import ShardedEpisodeStats
+    total3 = 65536
+    n3 = total3 // world
+    Ks = min(K, 50)
+    hf_dev = hf.to(dev)
+    rd3, wr3 = algorithmic_bytes_per_env(12, 4, 8, 1, 187, 235, 10, 4, False)
+    bytes3 = (rd3 + wr3) * n3 + hf.numel() * 2
+    n_rep3 = max(1, -(-2 * L2_BYTES // bytes3) + 1) if bytes3 < 2 * L2_BYTES else 3
+    stats3 = ShardedEpisodeStats(dev, comm=comm)
+    envs3 = []
+    for r_ in range(n_rep3):
+        cfg3, spec3, st3 = common.make_case_state("a1_rough", n3, seed=100 + r_ + 17 * rank)
+        cfg3.env.num_envs = n3
+        cfg3.domain_rand.push_robots = False
+        e3 = LeggedRobot(cfg3, None, SyntheticSim(cfg3, n3, dev, spec=spec3, height_samples=hf_dev, state=st3), dev, True)
+        e3.set_env_state(st3)
+        e3.noise_u = None
+        e3.episode_stats = stats3
+        e3._obs_clip_for_step = 100.0
+        envs3.append(e3)
+
+    def step3(i):
+        e = envs3[i % n_rep3]
+        e.torques = e._compute_torques(e.actions).view(e.torques.shape)
+        e.post_physics_step()                      # resample -> fused step -> in-kernel reset (sync-free)
+    gs3 = torch.cuda.Stream(device=dev)
+    g3 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(gs3):
+        for i in range(n_rep3):
+            step3(i)
+        gs3.synchronize()
+        with torch.cuda.graph(g3, stream=gs3):
+            for i in range(Ks):
+                step3(i)
+            if comm is not None:
+                L.check(lib.elg_episode_stats_allreduce(stats3.buf.data_ptr(), stats3.buf.numel(), comm.handle, torch.cuda.current_stream(dev).cuda_stream))
+        g3.replay()
+        gs3.synchronize()
+        ts = []
+        for _ in range(5):
+            if dist:
+                dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(gs3); g3.replay(); e1.record(gs3)
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+    t3 = max_over_ranks(sorted(ts)[2])
+    resets3 = float(stats3.buf[L.NUM_REWARD_TERMS])
+    out["config3_strong"] = {"workload": f"a1 rough, {total3} envs in total = {n3} per GPU x {world}: {Ks} x (torques, resample, fused step, in-kernel reset) "
+                                         f"+ 1 episode-statistics all-reduce per timed graph", "scaling": "strong", "num_envs_total": total3, "steps": Ks,
+                             "value": total3 * Ks / t3, "unit": UNIT, "us_per_step": t3 / Ks * 1e6, "kernels_per_step": 4,
+                             "per_gpu_algorithmic_gbs": bytes3 / (t3 / Ks) / 1e9, "frac_of_hbm_peak_per_gpu": bytes3 / (t3 / Ks) / 1e9 / peak,
+                             "l2_policy": f"{n_rep3} state replicas x {bytes3 / 1e6:.1f} MB rotated per step", "timing": "CUDA events, max over ranks, median of 5 replays",
+                             "collectives_in_timed_region": 1 if comm is not None else 0, "resets_accumulated_since_start_all_ranks": resets3}
+    del envs3, g3, stats3
+    torch.cuda.empty_cache()
 
     # ---- config 5: 64 mains x 512 rollouts: state clone, then the cost-weighted update over a 20-step horizon
     import common
@@ -294,22 +411,52 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
     out["rollout_step"] = {"workload": f"post_physics_step_rollout over {n} envs ({mains} mains x (1 + {rollouts}) rows), anymal_c_rough",
                            "us_per_step": sec * 1e6, "env_steps_per_s": n / sec,
                            "note": "lean kernel in rollout mode (measured heights are an input, no termination / episode sums); CUDA graph of 20 steps"}
-    # one MPPI iteration of BASELINE config 5 through the public API: rollout_batch (sync, 20 x step_rollout with decimation x torques,
-    # rollout-mode step, main-row restore, sync) + the cost-weighted update
-    from extended_legged_gym_b200.utils.mppi import rollout_batch
+    # one MPPI iteration of BASELINE config 5: 64 mains x 512 rollouts IN TOTAL, the rollouts of every main env split over the
+    # ranks.  rollout_batch (sync, 20 x [actions, 4 x torques, rollout-mode step, restore], sync) is ONE CUDA graph; the
+    # cost-weighted update is one extension call (costs -> ncclAllGather -> weights / partial sums -> ncclAllReduce -> means).
+    from extended_legged_gym_b200.envs import RobotTrajGradSampling
     horizon, nodes = 20, 5
-    all_us = torch.randn(mains * rollouts, horizon, 12, device=dev) * 0.3
-    samples = torch.randn(mains, rollouts, nodes, 12, device=dev)
-
+    del env
+    cfg5, spec5, st5 = common.make_case_state("anymal_c_rough", n, seed=3)
+    cfg5.env.num_envs, cfg5.env.rollout_envs = mains, rollouts
+    env = RobotTrajGradSampling(cfg5, None, SyntheticSim(cfg5, n, dev, spec=spec5, height_samples=hf, state=st5), dev, True)
+    env.set_env_state(st5)
+    env.comm = comm
     env._cache_main_env_states()          # what step() leaves behind: the main rows the rollouts restore after every horizon step
+    g5 = torch.Generator().manual_seed(7)
+    us_full = torch.randn(mains, 512, horizon, 12, generator=g5) * 0.3          # the same on every rank; each takes its share
+    smp_full = torch.randn(mains, 512, nodes, 12, generator=g5)
+    lo5 = rank * rollouts
+    all_us = us_full[:, lo5:lo5 + rollouts].reshape(mains * rollouts, horizon, 12).to(dev).contiguous()
+    samples = smp_full[:, lo5:lo5 + rollouts].to(dev).contiguous()
 
     def mppi_iteration():
-        rew = rollout_batch(env, all_us)
-        return mppi_update(rew.view(mains, rollouts, horizon), samples, 0.05)
-    sec = timed(mppi_iteration, 2 if quick else 5, warm=1)
-    out["mppi_iteration"] = {"workload": f"{mains} mains x {rollouts} rollouts per GPU x horizon {horizon}: rollout_batch + mppi_update (Python API, "
-                                         f"{world} rank{'s' if world > 1 else ''})", "ms_per_iteration": sec * 1e3,
-                             "rollout_env_steps_per_s": mains * rollouts * horizon / sec}
+        rew = env.rollout_batch(all_us)
+        return mppi_update(rew.view(mains, rollouts, horizon), samples, 0.05, comm=comm)
+    for _ in range(2):
+        mppi_iteration()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(3 if quick else 7):
+        if dist:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record(); mppi_iteration(); e1.record()
+        torch.cuda.synchronize()
+        ts.append(e0.elapsed_time(e1) * 1e-3)
+    sec = max_over_ranks(sorted(ts)[len(ts) // 2])
+    # correctness of the sharded update on the same data: every rank also runs the single-rank update on the FULL sample set
+    rew_full = torch.randn(mains, 512, horizon, generator=g5).to(dev)
+    smp_dev = smp_full.to(dev)
+    want = mppi_update(rew_full, smp_dev, 0.05)
+    got = mppi_update(rew_full[:, lo5:lo5 + rollouts].contiguous(), samples, 0.05, comm=comm)
+    diff = float((got - want).abs().max())
+    out["mppi_iteration"] = {"workload": f"{mains} mains x 512 rollouts in total ({rollouts} per main on each of {world} rank{'s' if world > 1 else ''}) x horizon "
+                                         f"{horizon}: rollout_batch (one CUDA graph) + elg_mppi_update", "ms_per_iteration": sec * 1e3,
+                             "rollout_env_steps_per_s": mains * 512 * horizon / sec, "timing": "CUDA events, max over ranks, median",
+                             "collectives_per_iteration": 2 if comm is not None else 0,
+                             "sharded_equals_single_rank": bool(torch.allclose(got, want, rtol=1e-4, atol=1e-5)), "max_abs_diff_vs_single_rank": diff}
     del env
     # ---- actuator-network torques (Anymal._compute_torques, the default torque path of the anymal_c configs): 4096 envs x 12 dofs
     from extended_legged_gym_b200.envs import Anymal
@@ -372,10 +519,7 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
                                   "achieved_gbs": nb / sec / 1e9, "frac_of_hbm_peak": nb / sec / 1e9 / peak,
                                   "note": "CUDA graph of 48 calls cycling over 24 storage slots (92 MB of destinations)"}
     # navigation commands and kinematic state integration over the 64 x (1 + 512) rows of config 5 (one launch each)
-    import ctypes as C
-    from extended_legged_gym_b200 import _lib as L
     from extended_legged_gym_b200.envs import KinematicStateIntegration
-    lib = L.load()
     n_all = mains * (1 + rollouts)
     root = torch.randn(n_all, 13, device=dev)
     root[:, 3:7] /= root[:, 3:7].norm(dim=1, keepdim=True)
@@ -426,10 +570,24 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False):
     K, D, T = 5, 12, 20
     r = torch.randn(mains, rollouts, T, device=dev)
     u = torch.randn(mains, rollouts, K, D, device=dev)
-    sec = timed(lambda: mppi_update(r, u, 0.05), 20 if quick else 100)
+    sec = timed(lambda: mppi_update(r, u, 0.05, comm=comm), 20 if quick else 100)
     out["mppi_update"] = {"workload": f"{mains} mains x {rollouts * world} samples (x{world} ranks) x horizon {T}, {K} nodes x {D} dof",
-                          "us_per_update": sec * 1e6, "collectives": "all_gather(costs) + all_reduce(partials)" if world > 1 else "none (1 rank)"}
+                          "us_per_update": max_over_ranks(sec) * 1e6,
+                          "collectives": "ncclAllGather(costs) + ncclAllReduce(partials), issued by the extension on the compute stream" if world > 1 else "none (1 rank)"}
     return out
+
+
+def graph_of(fn, n, stream, warm=3):
+    """Capture n calls of fn(i) on `stream` into one CUDA graph (after `warm` eager calls)."""
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(stream):
+        for i in range(warm):
+            fn(i)
+        stream.synchronize()
+        with torch.cuda.graph(g, stream=stream):
+            for i in range(n):
+                fn(i)
+    return g
 
 
 def main():
@@ -442,7 +600,7 @@ def main():
     ap.add_argument("--envs", type=int, default=4096, help="envs per GPU")
     ap.add_argument("--e2e-steps", type=int, default=200)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-secondary", action="store_true", help="skip the depth / clone / MPPI measurements")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the config 3 / depth / clone / MPPI measurements")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -455,7 +613,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the B200 path has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = f"cuda:{local_rank}"
-    dist = None
+    numa = pin_to_gpu_numa_node(local_rank)
+    dist, comm = None, None
     # stdout carries exactly one JSON line: anything a library (NCCL's version / debug lines) or a host class prints on the way
     # goes to stderr -- fd 1 points at stderr until the result line is due
     sys.stdout.flush()
@@ -463,15 +622,19 @@ def main():
     os.dup2(2, 1)
     if world > 1:
         import torch.distributed as dist
+        from extended_legged_gym_b200.utils.distributed import ElgComm
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device(dev))
+        comm = ElgComm(dev)               # the extension's own communicator: collectives on the compute stream, graph-capturable
+    from extended_legged_gym_b200.utils.distributed import ShardedEpisodeStats
     W = max(args.warmup, 3)
     K = args.steps
     case, common = case_for(args.config)
     lib = _lib.load()
+    cur = lambda: torch.cuda.current_stream(dev).cuda_stream
 
     n_envs = args.envs
-    probe = build_replicas(case, common, n_envs, 1, dev)[0]
+    probe = build_replicas(case, common, n_envs, 1, dev, packed=True)[0]      # replica 0 doubles as the e2e env (packed state block)
     D, F = probe.num_dof, len(probe.feet_indices)
     P, T = len(probe.penalised_contact_indices), len(probe.termination_contact_indices)
     H, O, C_ = probe.num_height_points, probe.num_obs, probe.cfg.commands.num_commands
@@ -481,28 +644,32 @@ def main():
     bytes_per_step = (rd + wr) * n_envs + hf_bytes
     n_rep = max(2, -(-2 * L2_BYTES // bytes_per_step) + 1)
     envs = [probe] + build_replicas(case, common, n_envs, n_rep, dev)[1:]
+    stats = ShardedEpisodeStats(dev, comm=comm)
     stream = torch.cuda.Stream(device=dev)
 
     def enqueue(env, step, with_torques=True):
         p = env._params
         p.noise_mode, p.noise_offset, p.clip_observations = _lib.NOISE_PHILOX, step, 100.0
-        s = torch.cuda.current_stream(dev).cuda_stream
         if with_torques:
             rc = lib.elg_compute_torques(C.byref(env._dims), C.byref(p), env.actions.data_ptr(), env.dof_state.data_ptr(),
                                          env.last_dof_vel.data_ptr(), env.p_gains.data_ptr(), env.d_gains.data_ptr(),
-                                         env.torque_limits.data_ptr(), env.default_dof_pos.data_ptr(), env.torques.data_ptr(), None, 0, s)
+                                         env.torque_limits.data_ptr(), env.default_dof_pos.data_ptr(), env.torques.data_ptr(), None, 0, cur())
             _lib.check(rc)
-        _lib.check(lib.elg_post_physics_step(C.byref(env._dims), C.byref(p), C.byref(env._bufs), _lib.PHASE_FUSED, s))
+        _lib.check(lib.elg_post_physics_step(C.byref(env._dims), C.byref(p), C.byref(env._bufs), _lib.PHASE_FUSED, cur()))
 
-    def capture(n_steps, with_torques):
+    def capture(n_steps, with_torques, reps, with_allreduce):
         g = torch.cuda.CUDAGraph()
         with torch.cuda.stream(stream):
             for i in range(3):
-                enqueue(envs[i % n_rep], i, with_torques)
+                enqueue(envs[i % reps], i, with_torques)
             stream.synchronize()
             with torch.cuda.graph(g, stream=stream):
                 for i in range(n_steps):
-                    enqueue(envs[i % n_rep], i, with_torques)
+                    enqueue(envs[i % reps], i, with_torques)
+                if with_allreduce and comm is not None:
+                    # the one genuine reduction of the path, once per K steps, INSIDE the timed region: the running episode
+                    # statistics (sums per reward term, reset count) of all ranks, NCCL on the capture stream
+                    _lib.check(lib.elg_episode_stats_allreduce(stats._send.data_ptr(), stats._send.numel(), comm.handle, cur()))
         return g
 
     def timed_replay(g, reps=1):
@@ -518,26 +685,35 @@ def main():
             torch.cuda.synchronize()
             if dist:
                 dist.barrier()
-        return e0.elapsed_time(e1) * 1e-3
+        return e0.elapsed_time(e1) * 1e-3 / reps
 
-    g_warm = capture(W, True)
-    g_full = capture(K, True)
-    g_step = capture(K, False)
+    g_warm = capture(W, True, n_rep, True)
+    g_full = capture(K, True, n_rep, True)
+    g_step = capture(K, False, n_rep, False)
+    g_step_warm = capture(K, False, 1, False)      # steady state: one replica, inputs and outputs stay L2-resident
     timed_replay(g_warm)
+    timed_replay(g_full)          # first replay uploads the graph; not a measurement
+    timed_replay(g_step)
+    timed_replay(g_step_warm)
     with ClockSampler(local_rank) as clk:
-        timed_replay(g_full)          # first replay uploads the graph; not a measurement
-        timed_replay(g_step)
-        # several replays keep the sampler busy long enough to see clocks under load; the median is reported
+        # the sampler (10 ms period) needs a busy region of >= 0.5 s to see clocks UNDER LOAD: the timed graph replayed back to back
+        busy = max(1, int(0.6 / max(timed_replay(g_full), 1e-6)))
+        timed_replay(g_full, reps=min(busy, 20000))
         t_fulls = sorted(timed_replay(g_full) for _ in range(7))
         t_steps = sorted(timed_replay(g_step) for _ in range(7))
-    t_full, t_step_only = t_fulls[len(t_fulls) // 2], t_steps[len(t_steps) // 2]
+        t_warms = sorted(timed_replay(g_step_warm) for _ in range(7))
+    t_full, t_step_only, t_step_warm = t_fulls[len(t_fulls) // 2], t_steps[len(t_steps) // 2], t_warms[len(t_warms) // 2]
+    clocks = clk.summary()
     if dist:
-        tt = torch.tensor([t_full, t_step_only], device=dev, dtype=torch.float64)
+        tt = torch.tensor([t_full, t_step_only, t_step_warm], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        t_full, t_step_only = tt.tolist()
-        # episode statistics: the one genuine reduction on this path
-        stats = torch.stack([probe._episode_sums_all.sum(dim=1).double().sum(), torch.tensor(float(n_envs), device=dev, dtype=torch.float64)])
-        dist.all_reduce(stats)
+        t_full, t_step_only, t_step_warm = tt.tolist()
+        allc = [None] * world
+        dist.all_gather_object(allc, clocks)
+        sm = [c["sm_mhz"] for c in allc if c["sm_mhz"]]
+        clocks = {"sm_mhz": min(sm) if sm else None, "sm_max_mhz": max((c["sm_max_mhz"] or 0) for c in allc) or None,
+                  "reasons": sorted(set(r for c in allc for r in c["reasons"])), "samples": sum(c["samples"] for c in allc),
+                  "period_ms": 10, "note": "min over ranks of the per-rank median SM clock under load"}
     total_envs = n_envs * world
     value = total_envs * K / t_full
     ms_per_step = t_full / K * 1e3
@@ -549,34 +725,56 @@ def main():
         traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
     t_kernel = t_step_only / K
     achieved = bytes_per_step / t_kernel / 1e9
+    achieved_warm = bytes_per_step / (t_step_warm / K) / 1e9
 
-    # ---- e2e: public Python API, PhysX state in pinned host memory, H2D + D2H every step
+    # ---- launch floor on this box, same launch shape (csrc/elg_probe.cu): what one launch / the bytes alone cost
+    floor = None
+    if hasattr(lib, "elg_probe_empty"):
+        sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+        epc = -(-n_envs // sms)
+        epc += (-epc) % 4
+        b_in, b_out = (rd * epc + 15) // 16 * 16, (wr * epc + 15) // 16 * 16
+        if max(b_in, b_out) <= 200 * 1024:
+            n_fl = max(2, -(-2 * L2_BYTES // (sms * (b_in + b_out))) + 1)
+            src = [torch.zeros(sms * b_in, dtype=torch.uint8, device=dev) for _ in range(n_fl)]
+            dst = [torch.zeros(sms * b_out, dtype=torch.uint8, device=dev) for _ in range(n_fl)]
+            g_e = graph_of(lambda i: _lib.check(lib.elg_probe_empty(sms, 1024, 90 * 1024, 1, cur())), 200, stream)
+            g_c = graph_of(lambda i: _lib.check(lib.elg_probe_roundtrip(src[i % n_fl].data_ptr(), dst[i % n_fl].data_ptr(), b_in, b_out, sms, 1, cur())), 200, stream)
+            g_w = graph_of(lambda i: _lib.check(lib.elg_probe_roundtrip(src[0].data_ptr(), dst[0].data_ptr(), b_in, b_out, sms, 1, cur())), 200, stream)
+            for g in (g_e, g_c, g_w):
+                timed_replay(g)
+            med = lambda g: sorted(timed_replay(g) for _ in range(5))[2] / 200 * 1e6
+            floor = {"empty_pdl_kernel_us": med(g_e), "bulk_roundtrip_cold_us": med(g_c), "bulk_roundtrip_warm_us": med(g_w),
+                     "bytes_per_launch": sms * (b_in + b_out),
+                     "what": f"{sms} CTAs x 1024 threads, 90 KB smem, PDL, CUDA graph: an empty kernel; one cp.async.bulk of the step's input bytes in and "
+                             "one of its output bytes out per CTA with no arithmetic (cold: rotating buffers > 2x L2; warm: one buffer)"}
+            del src, dst, g_e, g_c, g_w
+
+    # ---- e2e: public Python API, PhysX state in pinned host memory, ONE packed H2D + ONE packed D2H every step
     env = envs[0]
-    host_in = {k: getattr(env, k).detach().cpu().pin_memory() for k in ("root_states", "dof_state", "rigid_body_state", "actions")}
-    host_in["contact_forces"] = env._contact_forces_flat.detach().cpu().pin_memory()
-    dev_in = {"root_states": env.root_states, "dof_state": env.dof_state, "rigid_body_state": env.rigid_body_state,
-              "actions": env.actions, "contact_forces": env._contact_forces_flat}
-    # One CUDA graph holds G consecutive steps, each = copy-in of its inputs (pinned host -> device), the two API calls, copy-out of
-    # obs / rew / reset into that step's own pinned host slot.  The copy-out runs on a second stream, so inside the graph it
-    # overlaps the next step's copy-in (PCIe is full duplex); the next step's kernels wait for it (they overwrite obs_buf).
-    # The host launches the graph, waits for it and reads every step's result.  Measured: 0.266 ms per step for the eager,
-    # serial form, 0.231 ms with the two-stream overlap, 0.225 ms as a graph -- the loop is bound by the copy-in (5.26 MB per
-    # step arrive at ~23 GB/s on these boxes), neither by the host nor by the kernels (10 us).
+    sim = env.sim
+    host_in = sim.state_block.detach().cpu().pin_memory()              # root / dof / contact / rigid-body state + actions, one block
+    # outputs the caller reads back, re-pointed at ONE device block: obs [N, O] | rew [N] | reset flags [N] (bytes, padded)
+    n_out_words = n_envs * O + n_envs + (n_envs + 3) // 4
+    out_block = torch.zeros(n_out_words, dtype=torch.float, device=dev)
+    env.obs_buf = out_block[:n_envs * O].view(n_envs, O)
+    env.rew_buf = out_block[n_envs * O:n_envs * O + n_envs]
+    env._reset_bool = out_block[n_envs * O + n_envs:].view(torch.uint8)[:n_envs].view(torch.bool)
+    # G consecutive steps form one CUDA graph; the copy-out of step i (second stream) overlaps the copy-in of step i + 1 (PCIe is
+    # full duplex); the host launches the graph, waits and reads every step's result.
     G = max(1, min(10, args.e2e_steps))
-    host_out = [{"obs": torch.empty(n_envs, O).pin_memory(), "rew": torch.empty(n_envs).pin_memory(),
-                 "reset": torch.empty(n_envs, dtype=torch.bool).pin_memory()} for _ in range(G)]
-    h2d = sum(t.numel() * t.element_size() for t in host_in.values())
-    d2h = sum(t.numel() * t.element_size() for t in host_out[0].values())
+    host_out = [torch.empty(n_out_words).pin_memory() for _ in range(G)]
+    h2d = host_in.numel() * 4
+    d2h = n_out_words * 4
     env.cfg.domain_rand.push_robots = False
     env._obs_clip_for_step = 100.0
     s_cap, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     checksum = [0.0]
 
     def one_step(slot, prev_out):
-        for k, t in host_in.items():
-            dev_in[k].copy_(t, non_blocking=True)
+        sim.state_block.copy_(host_in, non_blocking=True)
         if prev_out is not None:
-            torch.cuda.current_stream().wait_event(prev_out)      # the previous results have left obs_buf / rew_buf / reset_buf
+            torch.cuda.current_stream().wait_event(prev_out)      # the previous results have left the output block
         env.torques = env._compute_torques(env.actions).view(env.torques.shape)
         env.post_physics_step()
         done = torch.cuda.Event()
@@ -584,9 +782,7 @@ def main():
         s_out.wait_event(done)
         out = torch.cuda.Event()
         with torch.cuda.stream(s_out):
-            host_out[slot]["obs"].copy_(env.obs_buf, non_blocking=True)
-            host_out[slot]["rew"].copy_(env.rew_buf, non_blocking=True)
-            host_out[slot]["reset"].copy_(env.reset_buf, non_blocking=True)
+            host_out[slot].copy_(out_block, non_blocking=True)
             out.record(s_out)
         return out
 
@@ -604,8 +800,8 @@ def main():
     def e2e_block():
         e2e_graph.replay()
         s_cap.synchronize()
-        for slot in range(G):                 # the host reads every step's result
-            checksum[0] += float(host_out[slot]["rew"][0])
+        for slot in range(G):                 # the host reads every step's result (first reward of the step)
+            checksum[0] += float(host_out[slot][n_envs * O])
 
     n_blocks = max(1, args.e2e_steps // G)
     e2e_steps = n_blocks * G
@@ -628,31 +824,41 @@ def main():
         t_e2e = tt.item()
     e2e_value = total_envs * e2e_steps / t_e2e
 
+    cfg_line = workload_config(args.config, n_envs, world)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{args.config} post-physics step (torques+derive+heights+termination+rewards+obs+noise+history), "
-                               f"{n_envs} envs per GPU", "num_envs_per_gpu": n_envs, "num_envs_total": total_envs,
-                   "sharding": f"envs x{world}, no data-path collective", "height_points": H, "num_obs": O, "reward_terms": R_terms,
-                   "l2_policy": f"inputs larger than L2: {n_rep} state replicas x {bytes_per_step / 1e6:.1f} MB rotated per step",
-                   "noise": "in-kernel Philox4x32-10", "launch": "CUDA graph of K steps, 2 kernels per step, programmatic dependent launch"},
+        "config": cfg_line,
+        "workload_detail": {"height_points": H, "num_obs": O, "reward_terms": R_terms,
+                            "l2_policy": f"inputs larger than L2: {n_rep} state replicas x {bytes_per_step / 1e6:.1f} MB rotated per step",
+                            "noise": "in-kernel Philox4x32-10",
+                            "launch": "CUDA graph of K steps, 2 kernels per step (programmatic dependent launch)" +
+                                      (", + 1 ncclAllReduce of the episode statistics (extension, capture stream) as the last node" if comm else ""),
+                            "numa": numa},
         "gpu_launches": 2 * K,
+        "collectives_in_timed_region": 1 if comm is not None else 0,
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-                "ms_per_step": t_e2e / e2e_steps * 1e3, "api": "LeggedRobot._compute_torques + post_physics_step, pinned host state; every step copies its inputs in and its "
-                       f"obs / rew / reset out; {G} steps per CUDA graph, the copy-out of step i (second stream) overlaps the copy-in of "
-                       "step i + 1, the host waits for the graph and reads every step's result"},
+                "ms_per_step": t_e2e / e2e_steps * 1e3,
+                "api": "LeggedRobot._compute_torques + post_physics_step (in-kernel reset path included), simulator state in pinned host memory: "
+                       "every step ONE copy of the packed state + actions block in and ONE copy of the packed obs / rew / reset block out; "
+                       f"{G} steps per CUDA graph, the copy-out of step i (second stream) overlaps the copy-in of step i + 1, the host waits "
+                       "for the graph and reads every step's result"},
         "roofline": {"bound": "hbm", "kernel": "elg_step_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_step, "bytes_per_env": rd + wr, "us_per_launch": t_kernel * 1e6,
+                     "regime": "cold L2 (every launch on a different state replica)",
+                     "steady_state": {"us_per_launch": t_step_warm / K * 1e6, "achieved": achieved_warm, "frac": achieved_warm / peak,
+                                      "regime": "one state replica: inputs and outputs L2-resident, as when the simulator has just written the state"},
+                     "floor": floor,
                      "frac_of_nominal_8TBs": achieved / 8000.0},
-        "clocks": clk.summary(),
+        "clocks": clocks,
     }
     if not args.no_secondary:
-        del envs, probe, env
+        del envs, probe, env, e2e_graph, g_full, g_step, g_step_warm, g_warm
         torch.cuda.empty_cache()
-        sec = secondary_benchmarks(dev, world, rank, dist, quick=args.steps < 200)
-        if dist:      # max over ranks of every timing-derived figure is overkill here: report rank 0's, name it so
-            sec["note"] = "per-GPU figures measured on rank 0 (each rank runs its own share: cameras / rollouts split over ranks)"
+        sec = secondary_benchmarks(dev, world, rank, dist, quick=args.steps < 200, comm=comm, K=K)
+        if dist:
+            sec["note"] = "per-GPU figures measured on rank 0 unless the entry says max over ranks (each rank runs its own share)"
         line["secondary"] = sec
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
@@ -661,6 +867,8 @@ def main():
                                 "sample": f"full workload: {n_envs} envs x 20 steps (median step {med * 1e3:.1f} ms) of oracle/legged_oracle.py hot_step"}
     if dist:
         dist.barrier()
+        if comm is not None:
+            comm.close()
         dist.destroy_process_group()
     sys.stdout.flush()
     os.dup2(saved_stdout, 1)

@@ -53,7 +53,8 @@ class ElgStepParams(C.Structure):
         ("stand_still_threshold", C.c_float),
         ("gait_increment", C.c_float), ("gait_swing_height", C.c_float), ("gait_foot_phases", C.c_float * MAX_FEET),
         ("gait_2_step_hexapod", C.c_int32), ("terminate_upside_down", C.c_int32),
-        ("rows_per_main", C.c_int32), ("reserved0", C.c_int32),
+        ("rows_per_main", C.c_int32), ("rollout_rew_stride", C.c_int32),
+        ("height_obs_bound", C.c_float), ("reserved1", C.c_float),
         ("noise_seed", C.c_uint64), ("noise_offset", C.c_uint64)]
 
 
@@ -64,7 +65,7 @@ _BUF_FIELDS = [
     "last_actions", "last_dof_vel", "last_root_vel", "base_lin_acc", "base_ang_acc", "commands", "feet_air_time",
     "feet_contact_time", "last_contacts", "episode_length_buf", "episode_sums", "gait_idx", "gait_prev_foot_z",
     "base_lin_vel", "base_ang_vel", "projected_gravity", "foot_positions", "foot_velocities", "measured_heights",
-    "reset_buf", "time_out_buf", "rew_buf", "obs_buf"]
+    "reset_buf", "time_out_buf", "rew_buf", "obs_buf", "dof_consts", "step_counter", "rollout_rew_out"]
 
 
 class ElgStepBuffers(C.Structure):
@@ -175,6 +176,8 @@ def load() -> C.CDLL:
             raise ElgError(f"reward registry mismatch at id {i}")
     vp, i64 = C.c_void_p, C.c_int64
     lib.elg_compute_torques.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 9 + [i64, vp]
+    if hasattr(lib, "elg_rollout_actions"):
+        lib.elg_rollout_actions.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp, vp, vp, vp]
     lib.elg_post_physics_step.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams), C.POINTER(ElgStepBuffers), C.c_uint32, vp]
     lib.elg_set_step_tuning.argtypes = [C.c_int] * 4
     lib.elg_get_heights.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 5 + [vp]
@@ -197,9 +200,13 @@ def load() -> C.CDLL:
     lib.elg_mesh_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     lib.elg_raycast.argtypes = [vp, vp, vp, i64, C.c_float, vp, vp, vp, vp, vp]
     lib.elg_raycast_sensor.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, i64, C.c_int, C.c_float, vp, vp, vp]
+    if hasattr(lib, "elg_raycast_sensor_obs"):
+        lib.elg_raycast_sensor_obs.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, i64, C.c_int, C.c_float, vp, vp, vp, C.c_int32, C.c_int32, vp, i64, vp]
     lib.elg_camera_pose.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
     lib.elg_depth_camera.argtypes = [vp, C.POINTER(ElgCamParams)] + [vp] * 9 + [i64, vp, vp, vp]
     lib.elg_sdf_query.argtypes = [vp, vp, i64, C.c_float, C.c_float, vp, vp, vp, vp, vp]
+    if hasattr(lib, "elg_sdf_query_bodies"):
+        lib.elg_sdf_query_bodies.argtypes = [vp, vp, C.c_int32, vp, vp, C.c_int32, vp, i64, C.c_float, C.c_float, vp, i64, vp, vp, vp, vp]
     lib.elg_mesh_mean_edge.argtypes = [vp]
     lib.elg_mesh_mean_edge.restype = C.c_double
     lib.elg_mppi_costs.argtypes = [vp, i64, i64, C.c_int32, vp, vp]

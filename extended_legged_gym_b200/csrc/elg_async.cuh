@@ -78,6 +78,13 @@ __device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volati
 __device__ __forceinline__ void named_bar_arrive(int id, int threads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 
 
+// 4-byte cp.async (LDGSTS): global -> shared without a register round trip; completion by commit / wait groups of the issuing thread
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // programmatic dependent launch (PDL): let the next kernel of the stream start its prologue / wait for the previous
 // kernel's memory before touching anything it may have written
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -212,7 +212,9 @@ __global__ void __launch_bounds__(128)
 elg_raycast_sensor_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ pat_o,
                           const float* __restrict__ pat_d, const int n_rays, const float* __restrict__ pos,
                           const float* __restrict__ quat, const int64_t* __restrict__ env_ids, const long long n_sensors,
-                          const int yaw_only, const float max_dist, float* __restrict__ hits, uint8_t* __restrict__ found) {
+                          const int yaw_only, const float max_dist, float* __restrict__ hits, uint8_t* __restrict__ found,
+                          const float* __restrict__ dist_org, const int dist_stride, const int normalize, float* __restrict__ dist_out,
+                          const long long dist_out_stride) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_sensors * n_rays) return;
   const long long s = i / n_rays;
@@ -237,10 +239,19 @@ elg_raycast_sensor_kernel(const float4* __restrict__ nodes, const float4* __rest
   const bool ok = trace(nodes, tris, ox, oy, oz, dx, dy, dz, max_dist, h);
   const float t = ok ? (float)h.t : max_dist;
   const long long o = (e * n_rays + r) * 3;
-  hits[o] = add_r(ox, mul_r(t, dx));
-  hits[o + 1] = add_r(oy, mul_r(t, dy));
-  hits[o + 2] = add_r(oz, mul_r(t, dz));
+  const float hx = add_r(ox, mul_r(t, dx)), hy = add_r(oy, mul_r(t, dy)), hz = add_r(oz, mul_r(t, dz));
+  hits[o] = hx;
+  hits[o + 1] = hy;
+  hits[o + 2] = hz;
   found[e * n_rays + r] = ok ? 1 : 0;
+  if (dist_out) {
+    // LeggedRobotRayCast._get_raycast_distances (envs/base/legged_robot_raycast.py:262-297): the distance is measured from the
+    // ROBOT BASE (root_states[:, :3]), not from the ray origin; observation = (1 - clamp(d / max, 0, 1)) * found
+    const float* org = dist_org + (size_t)e * dist_stride;
+    float d = norm3_t(sub_r(hx, org[0]), sub_r(hy, org[1]), sub_r(hz, org[2]));
+    if (normalize) d = mul_r(sub_r(1.0f, fminf(fmaxf(div_r(d, max_dist), 0.0f), 1.0f)), ok ? 1.0f : 0.0f);
+    dist_out[e * dist_out_stride + r] = d;
+  }
 }
 
 // isaacgym.torch_utils.quat_mul(a, b) (xyzw), one rounding per torch op
@@ -484,13 +495,10 @@ __device__ __forceinline__ void visit_near(const float4* __restrict__ nodes, con
 // wp.mesh_query_point_sign_normal: pass 1 finds the exact minimum distance d_min; pass 2 looks at every face within
 // d_min + epsilon * mean_edge and takes the one whose unit normal is most aligned with the offset (|n . (p - c)|
 // largest, lowest triangle id on ties) -- the face that decides the sign at edges and vertices.
-__global__ void __launch_bounds__(128)
-elg_sdf_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ points, const long long n,
-               const float max_distance, const double eps_abs, float* __restrict__ sdf, float* __restrict__ grad,
-               float* __restrict__ closest, int* __restrict__ face) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float pxf = points[3 * i], pyf = points[3 * i + 1], pzf = points[3 * i + 2];
+struct SdfResult { float sdf, gx, gy, gz, cx, cy, cz; int face; };
+
+__device__ __forceinline__ SdfResult sdf_at(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float pxf, const float pyf,
+                                            const float pzf, const float max_distance, const double eps_abs) {
   const double px = pxf, py = pyf, pz = pzf;
   const double D = (double)max_distance;
   // pass 1: exact minimum squared distance
@@ -506,11 +514,7 @@ elg_sdf_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris
     return -1.0f;
   });
   if (!any) {   // nothing within max_distance (mesh_sdf.py:112-115)
-    sdf[i] = max_distance;
-    grad[3 * i] = grad[3 * i + 1] = grad[3 * i + 2] = 0.0f;
-    if (closest) closest[3 * i] = closest[3 * i + 1] = closest[3 * i + 2] = 0.0f;
-    if (face) face[i] = -1;
-    return;
+    return SdfResult{max_distance, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, 0.0f, -1};
   }
   // pass 2: the deciding face among the near-ties
   const double dmin = sqrt(best);
@@ -547,12 +551,68 @@ elg_sdf_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris
     const double il = fl > 0.0 ? 1.0 / fl : 0.0;
     gx = dmul(nx, il); gy = dmul(ny, il); gz = dmul(nz, il);
   }
-  sdf[i] = (float)dmul(dist, sign);
-  grad[3 * i] = (float)dmul(gx, sign);
-  grad[3 * i + 1] = (float)dmul(gy, sign);
-  grad[3 * i + 2] = (float)dmul(gz, sign);
-  if (closest) { closest[3 * i] = (float)bx; closest[3 * i + 1] = (float)by; closest[3 * i + 2] = (float)bz; }
-  if (face) face[i] = btri;
+  return SdfResult{(float)dmul(dist, sign), (float)dmul(gx, sign), (float)dmul(gy, sign), (float)dmul(gz, sign), (float)bx, (float)by, (float)bz, btri};
+}
+
+
+__global__ void __launch_bounds__(128)
+elg_sdf_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ points, const long long n,
+               const float max_distance, const double eps_abs, float* __restrict__ sdf, float* __restrict__ grad,
+               float* __restrict__ closest, int* __restrict__ face) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const SdfResult r = sdf_at(nodes, tris, points[3 * i], points[3 * i + 1], points[3 * i + 2], max_distance, eps_abs);
+  sdf[i] = r.sdf;
+  grad[3 * i] = r.gx; grad[3 * i + 1] = r.gy; grad[3 * i + 2] = r.gz;
+  if (closest) { closest[3 * i] = r.cx; closest[3 * i + 1] = r.cy; closest[3 * i + 2] = r.cz; }
+  if (face) face[i] = r.face;
+}
+
+// RobotBatchRolloutPercept._update_sdf_values (envs/batch_rollout/robot_batch_rollout_percept.py:385-441) as ONE launch over
+// (env, query body): the query point is the body position + quat_rotate(body quaternion, collision-sphere offset) (:396-414, one
+// rounding per torch op like isaacgym.torch_utils.quat_rotate), the signed distance / gradient come from the same traversal,
+// and nearest = p - sdf * gradient (utils/mesh_sdf.py:316-336) without the second query the reference runs for it.
+constexpr int kMaxSdfBodies = 16;
+struct SdfBodies {
+  int num_bodies, count;
+  int body_idx[kMaxSdfBodies];
+  float offset[kMaxSdfBodies][3];
+  int has_offset[kMaxSdfBodies];
+};
+__global__ void __launch_bounds__(128)
+elg_sdf_bodies_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ rbs,
+                      const __grid_constant__ SdfBodies sb, const int64_t* __restrict__ env_ids, const long long n_rows,
+                      const float max_distance, const double eps_abs, float* __restrict__ sdf, const long long sdf_row_stride,
+                      float* __restrict__ grad, float* __restrict__ nearest, float* __restrict__ points_out) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_rows * sb.count) return;
+  const long long row = i / sb.count;
+  const int k = (int)(i - row * sb.count);
+  const long long e = env_ids ? env_ids[row] : row;
+  const float* st = rbs + ((size_t)e * sb.num_bodies + sb.body_idx[k]) * 13;
+  float px = st[0], py = st[1], pz = st[2];
+  if (sb.has_offset[k]) {
+    // quat_rotate(q, v) = v (2 w^2 - 1) + 2 w (q_xyz x v) + 2 q_xyz (q_xyz . v)   (dot through bmm: sequential sum)
+    const float qx = st[3], qy = st[4], qz = st[5], qw = st[6];
+    const float vx = sb.offset[k][0], vy = sb.offset[k][1], vz = sb.offset[k][2];
+    const float s = sub_r(mul_r(2.0f, mul_r(qw, qw)), 1.0f);
+    const float cx = sub_r(mul_r(qy, vz), mul_r(qz, vy)), cy = sub_r(mul_r(qz, vx), mul_r(qx, vz)), cz = sub_r(mul_r(qx, vy), mul_r(qy, vx));
+    const float d = add_r(add_r(mul_r(qx, vx), mul_r(qy, vy)), mul_r(qz, vz));
+    const float w2 = mul_r(qw, 2.0f);
+    px = add_r(px, add_r(add_r(mul_r(vx, s), mul_r(cx, w2)), mul_r(mul_r(qx, d), 2.0f)));
+    py = add_r(py, add_r(add_r(mul_r(vy, s), mul_r(cy, w2)), mul_r(mul_r(qy, d), 2.0f)));
+    pz = add_r(pz, add_r(add_r(mul_r(vz, s), mul_r(cz, w2)), mul_r(mul_r(qz, d), 2.0f)));
+  }
+  const SdfResult r = sdf_at(nodes, tris, px, py, pz, max_distance, eps_abs);
+  const long long o = e * sb.count + k;
+  sdf[e * sdf_row_stride + k] = r.sdf;
+  if (grad) { grad[3 * o] = r.gx; grad[3 * o + 1] = r.gy; grad[3 * o + 2] = r.gz; }
+  if (nearest) {
+    nearest[3 * o] = sub_r(px, mul_r(r.sdf, r.gx));
+    nearest[3 * o + 1] = sub_r(py, mul_r(r.sdf, r.gy));
+    nearest[3 * o + 2] = sub_r(pz, mul_r(r.sdf, r.gz));
+  }
+  if (points_out) { points_out[3 * o] = px; points_out[3 * o + 1] = py; points_out[3 * o + 2] = pz; }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -849,8 +909,28 @@ int elg_raycast_sensor(const ElgMesh* mesh, const float* pattern_origins, const 
   if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many rays for one launch");
   elg::elg_raycast_sensor_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
       mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
-      max_dist, ray_hits, hits_found);
+      max_dist, ray_hits, hits_found, nullptr, 0, 0, nullptr, 0);
   return elg::check_launch("elg_raycast_sensor");
+}
+
+int elg_raycast_sensor_obs(const ElgMesh* mesh, const float* pattern_origins, const float* pattern_directions, int32_t num_rays,
+                           const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num_sensors, int yaw_only,
+                           float max_dist, float* ray_hits, uint8_t* hits_found, const float* dist_origins, int32_t dist_origin_stride,
+                           int32_t normalize, float* distances, int64_t distances_row_stride, void* stream) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "Mesh cannot be None");
+  if (distances_row_stride < num_rays) return mfail(ELG_ERR_INVALID_ARGUMENT, "distances_row_stride < num_rays");
+  if (num_rays < 0 || num_sensors < 0) return mfail(ELG_ERR_INVALID_ARGUMENT, "negative ray / sensor count");
+  if (num_rays == 0 || num_sensors == 0) return ELG_OK;
+  if (!pattern_origins || !pattern_directions || !sensor_pos || !sensor_quat || !ray_hits || !hits_found || !dist_origins || !distances)
+    return mfail(ELG_ERR_NULL_POINTER, "a sensor / ray / distance buffer is NULL");
+  if (!(max_dist > 0.0f) || dist_origin_stride < 3) return mfail(ELG_ERR_INVALID_ARGUMENT, "max_dist must be > 0 and the origin stride >= 3");
+  const int threads = 128;
+  const long long blocks = (num_sensors * num_rays + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many rays for one launch");
+  elg::elg_raycast_sensor_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
+      max_dist, ray_hits, hits_found, dist_origins, dist_origin_stride, normalize, distances, (long long)distances_row_stride);
+  return elg::check_launch("elg_raycast_sensor_obs");
 }
 
 int elg_sizeof_cam_params(void) { return (int)sizeof(ElgCamParams); }
@@ -911,6 +991,36 @@ int elg_sdf_query(const ElgMesh* mesh, const float* points, int64_t num_points, 
                                                                               (double)epsilon * mesh->avg_edge, sdf, grad, closest_points,
                                                                               closest_face);
   return elg::check_launch("elg_sdf_query");
+}
+
+int elg_sdf_query_bodies(const ElgMesh* mesh, const float* rigid_body_state, int32_t num_bodies, const int32_t* body_indices,
+                         const float* sphere_offsets, int32_t num_query_bodies, const int64_t* env_ids, int64_t num_rows, float max_distance,
+                         float epsilon, float* sdf, int64_t sdf_row_stride, float* grad, float* nearest_points, float* query_points, void* stream) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "No meshes available for SDF queries");
+  if (num_rows < 0 || num_bodies < 1 || num_query_bodies < 0 || num_query_bodies > elg::kMaxSdfBodies)
+    return mfail(ELG_ERR_INVALID_ARGUMENT, "bad body counts (at most 16 query bodies)");
+  if (num_rows == 0 || num_query_bodies == 0) return ELG_OK;
+  if (!rigid_body_state || !body_indices || !sdf) return mfail(ELG_ERR_NULL_POINTER, "an SDF body buffer is NULL");
+  if (sdf_row_stride < num_query_bodies) return mfail(ELG_ERR_INVALID_ARGUMENT, "sdf_row_stride < num_query_bodies");
+  if (!(max_distance >= 0.0f) || !(epsilon >= 0.0f)) return mfail(ELG_ERR_INVALID_ARGUMENT, "max_distance and epsilon must be >= 0");
+  elg::SdfBodies sb{};
+  sb.num_bodies = num_bodies;
+  sb.count = num_query_bodies;
+  for (int k = 0; k < num_query_bodies; ++k) {
+    if (body_indices[k] < 0 || body_indices[k] >= num_bodies) return mfail(ELG_ERR_INVALID_ARGUMENT, "query body index out of range");
+    sb.body_idx[k] = body_indices[k];
+    sb.has_offset[k] = 0;
+    if (sphere_offsets && sphere_offsets[3 * k] == sphere_offsets[3 * k]) {   // NaN in the first component: no offset for this body
+      sb.has_offset[k] = 1;
+      for (int c = 0; c < 3; ++c) sb.offset[k][c] = sphere_offsets[3 * k + c];
+    }
+  }
+  const long long total = num_rows * num_query_bodies;
+  const int threads = 128;
+  elg::elg_sdf_bodies_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, (cudaStream_t)stream>>>(
+      mesh->nodes, mesh->tris, rigid_body_state, sb, env_ids, num_rows, max_distance, (double)epsilon * mesh->avg_edge, sdf,
+      (long long)sdf_row_stride, grad, nearest_points, query_points);
+  return elg::check_launch("elg_sdf_query_bodies");
 }
 
 double elg_mesh_mean_edge(const ElgMesh* mesh) { return mesh ? mesh->avg_edge : 0.0; }

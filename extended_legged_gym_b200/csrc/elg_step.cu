@@ -523,6 +523,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
     int blk_id = -1;
     const int nj = (H + 31) >> 5;
     const bool philox = do_obs && noise_mode == ELG_NOISE_PHILOX;
+    const uint64_t noise_off = pr.noise_offset + (bf.step_counter ? *bf.step_counter : 0ull);
     const bool obs_to_smem = kFast || L.obs_smem;
     float* const orow = s_obs + slot * (obs_to_smem ? O : head);   // staged observation row (head only when rows are user-extended)
     float* const grow = bf.obs_buf + (size_t)env * O;
@@ -639,6 +640,10 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       if (pr.only_positive_rewards) total = fmaxf(total, 0.0f);
       if (term_on(pr, ELG_REW_TERMINATION)) total += r_term;
       s_rew[e] = total;
+      if (rollout && bf.rollout_rew_out && pr.rows_per_main > 1) {   // column of rollout_batch's reward table (robot_traj_grad_sampling.py:262-266)
+        const int k = genv / pr.rows_per_main, r = genv - k * pr.rows_per_main;
+        if (r > 0) bf.rollout_rew_out[((size_t)k * (pr.rows_per_main - 1) + (r - 1)) * pr.rollout_rew_stride] = total;
+      }
     };
 #pragma unroll 1
     for (int round = 0; round < 2; ++round) {
@@ -706,7 +711,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
       for (int jb = 0; jb < nj; jb += 8) {
         if (philox) {
           blk_id = 1 + (jb >> 3);
-          blk = noise_block(pr.noise_seed, pr.noise_offset, env, lane, blk_id);
+          blk = noise_block(pr.noise_seed, noise_off, env, lane, blk_id);
         }
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
@@ -789,7 +794,7 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         const int k = lane + 32 * m;
         if (philox && ((m & 7) == 0) && !(m == 0 && blk_id == bid)) {
           blk_id = bid + (m >> 3);
-          blk = noise_block(pr.noise_seed, pr.noise_offset, env, lane, blk_id);
+          blk = noise_block(pr.noise_seed, noise_off, env, lane, blk_id);
         }
         if (k < head) {
           float v = orow[k];
@@ -867,6 +872,24 @@ elg_torques_kernel(const int64_t n_rows, const int D, const int control_type, co
   }
   const float lim = __ldg(torque_limits + j);
   torques[e] = fminf(fmaxf(tq, -lim), lim);
+}
+
+// ---------------------------------------------------------------------------------------------
+// step_rollout's action hand-over (robot_batch_rollout.py:643-656; robot_traj_grad_sampling.py:326-345): one thread per value
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+elg_rollout_actions_kernel(const float* __restrict__ src, const int M, const int R, const int A, const float clip,
+                           const float* __restrict__ lower, const float* __restrict__ range, float* __restrict__ actions) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (i >= (int64_t)M * R * A) return;
+  const int64_t row = i / A;
+  const int j = (int)(i - row * A);
+  const int64_t k = row / R;
+  float a = src[i];
+  if (lower) a = add_r(__ldg(lower + j), div_r(mul_r(add_r(fminf(fmaxf(a, -1.0f), 1.0f), 1.0f), __ldg(range + j)), 2.0f));
+  actions[(row + k + 1) * A + j] = fminf(fmaxf(a, -clip), clip);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1004,6 +1027,27 @@ int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const flo
   cudaLaunchKernelEx(&cfg, elg::elg_torques_kernel, rows, (int)dims->num_dof, (int)prm->control_type, prm->action_scale, prm->sim_dt,
                      actions, dof_state, last_dof_vel, p_gains, d_gains, torque_limits, default_dof_pos, torques, env_ids);
   return check_launch("elg_compute_torques");
+}
+
+int elg_rollout_actions(const float* rollout_actions, int32_t num_main, int32_t rollouts_per_main, int32_t num_actions, float clip_actions,
+                        const float* joint_lower, const float* joint_range, float* actions, void* stream) {
+  if (num_main < 0 || rollouts_per_main < 0 || num_actions < 1) return fail(ELG_ERR_INVALID_ARGUMENT, "elg_rollout_actions: bad sizes");
+  if ((joint_lower == nullptr) != (joint_range == nullptr)) return fail(ELG_ERR_INVALID_ARGUMENT, "joint_lower and joint_range go together");
+  const int64_t total = (int64_t)num_main * rollouts_per_main * num_actions;
+  if (total == 0) return ELG_OK;
+  if (!rollout_actions || !actions) return fail(ELG_ERR_NULL_POINTER, "elg_rollout_actions: a buffer is NULL");
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)((total + 255) / 256));
+  cfg.blockDim = dim3(256);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, elg::elg_rollout_actions_kernel, rollout_actions, (int)num_main, (int)rollouts_per_main, (int)num_actions, clip_actions,
+                     joint_lower, joint_range, actions);
+  return check_launch("elg_rollout_actions");
 }
 
 int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const ElgStepBuffers* buf, uint32_t phase, void* stream) {

@@ -58,7 +58,13 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
 
     def __setattr__(self, name, value):
         if name in _TRACKED:
-            object.__setattr__(self, "_ptrs_dirty", True)
+            # step() rebinds torques / reset_buf to the SAME storage every step: the native struct only goes stale when the
+            # device pointer changes
+            old = self.__dict__.get(name)
+            same = (old is value) or (torch.is_tensor(old) and torch.is_tensor(value) and old.data_ptr() == value.data_ptr()
+                                      and old.dtype == value.dtype and old.shape == value.shape)
+            if not same:
+                object.__setattr__(self, "_ptrs_dirty", True)
         object.__setattr__(self, name, value)
 
     # ------------------------------------------------------------------------------------------
@@ -350,6 +356,10 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
                 p.gait_foot_phases[i] = ph
         p.noise_seed = self.noise_seed
         p.rows_per_main = int(getattr(self, "_rows_per_main", 0))     # main / rollout layout (RobotBatchRollout), 0 = flat
+        if self.measure_heights and not self._user_height_points:
+            h0 = 12 + 3 * self.num_dof
+            nmax = float(self.noise_scale_vec[h0:h0 + self.num_height_points].abs().max()) if self.add_noise else 0.0
+            p.height_obs_bound = abs(float(os_.height_measurements)) * 1.0 + nmax
         return p
 
     def _native_buffers(self):
@@ -392,6 +402,14 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         put("episode_sums", self._episode_sums_all, f32)
         put("reset_buf", self._reset_bool, torch.bool)
         put("time_out_buf", self.time_out_buf, torch.bool)
+        # the per-joint constants once more as one block (the lean kernel fetches it with a single bulk copy)
+        key = tuple(t.data_ptr() for t in (self.default_dof_pos, self.dof_pos_limits, self.dof_vel_limits, self.torque_limits))
+        if getattr(self, "_dof_consts_key", None) != key:
+            object.__setattr__(self, "_dof_consts", torch.cat([self.default_dof_pos.view(-1), self.dof_pos_limits.reshape(-1),
+                                                                self.dof_vel_limits.view(-1), self.torque_limits.view(-1)]).contiguous())
+            object.__setattr__(self, "_dof_consts_key", key)
+        put("dof_consts", self._dof_consts, f32)
+        put("step_counter", getattr(self, "_step_counter", None), torch.int64)
         return b
 
     def _height_field_min(self):
@@ -421,7 +439,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             self._bufs = self._native_buffers()
             object.__setattr__(self, "_ptrs_dirty", False)
 
-    def _launch(self, phase: int, clip_obs: float = 0.0, rollout: bool = False):
+    def _launch(self, phase: int, clip_obs: float = 0.0, rollout: bool = False, noise_step: int = 0):
         self._sync_native()
         p = self._params
         p.clip_observations = clip_obs
@@ -430,7 +448,7 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
             p.noise_mode = _lib.NOISE_OFF
         else:
             p.noise_mode = _lib.NOISE_TENSOR if self.noise_u is not None else _lib.NOISE_PHILOX
-        p.noise_offset = self._noise_step
+        p.noise_offset = self._noise_step + noise_step
         stream = torch.cuda.current_stream(self.device).cuda_stream
         rc = self._lib.elg_post_physics_step(C.byref(self._dims), C.byref(p), C.byref(self._bufs), phase, stream)
         _lib.check(rc, "elg_post_physics_step")
@@ -584,6 +602,14 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         rp, b = self._reset_native_synced()
         stream = torch.cuda.current_stream(self.device).cuda_stream
         _lib.check(self._lib.elg_reset_envs(C.byref(self._dims), C.byref(rp), C.byref(self._params), C.byref(b), stream), "elg_reset_envs")
+        if self.episode_stats is not None:
+            # sharded envs: the kernel has added this step's (sum, count) to the running totals; extras["episode"] comes from
+            # episode_stats.reduce() -- one all-reduce per K steps -- instead of per-step means of the local shard
+            if self.cfg.env.send_timeouts:
+                self.extras["time_outs"] = self.time_out_buf
+            self.sim.set_dof_state()
+            self.sim.set_root_state()
+            return
         # extras["episode"] (legged_robot.py:200-213) as device tensors: means over the envs that reset this step; steps
         # without a reset keep the previous values (the reference leaves the dict untouched then)
         cnt = self._reset_stats[_lib.NUM_REWARD_TERMS]

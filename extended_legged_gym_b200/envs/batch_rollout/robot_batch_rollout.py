@@ -214,14 +214,94 @@ class RobotBatchRollout(LeggedRobot):
         self.t_rollout += self.dt
         return out
 
-    def post_physics_step_rollout(self):
+    # ------------------------------------------------------------------------------------------
+    # rollout_batch (robot_traj_grad_sampling.py:249-280): the horizon loop of one MPPI iteration
+    # ------------------------------------------------------------------------------------------
+    def _rollout_actions(self, rollout_actions):
+        """step_rollout's action hand-over (:643-656) as ONE launch: clip + scatter into the rollout rows of ``actions``
+        (subclasses add the joint-target denormalisation through ``_action_denorm``)."""
+        a = rollout_actions
+        if not (a.is_cuda and a.dtype == torch.float and a.is_contiguous()):
+            a = a.to(self.device, torch.float).contiguous()
+        lower, rng = getattr(self, "_action_denorm", (None, None))
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        _lib.check(self._lib.elg_rollout_actions(a.data_ptr(), self.num_main_envs, self.num_rollout_per_main, self.num_actions,
+                                                 float(self.cfg.normalization.clip_actions), _lib.ptr(lower), _lib.ptr(rng),
+                                                 self.actions.data_ptr(), stream), "elg_rollout_actions")
+
+    def _rollout_horizon(self, all_us, rewards):
+        """sync -> horizon x [actions, decimation x torques, rollout-mode step (its reward column written in place), restore]
+        -> sync.  No host synchronisation anywhere: this is what gets captured into a CUDA graph."""
+        horizon = all_us.shape[1]
+        self._sync_main_to_rollout()
+        self._sync_native()
+        for i in range(horizon):
+            self._rollout_actions(all_us[:, i])
+            for _ in range(self.cfg.control.decimation):
+                self.torques = self._compute_torques(self.actions).view(self.torques.shape)
+                self.sim.set_dof_actuation_force(self.torques)
+                self.sim.simulate()
+                self.sim.refresh()
+            self._bufs.rollout_rew_out = rewards.data_ptr() + 4 * i
+            self._params.rollout_rew_stride = horizon
+            try:
+                self.post_physics_step_rollout(noise_step=i)
+            finally:
+                self._bufs.rollout_rew_out = None
+            self._restore_main_env_states()
+            self.t_rollout += self.dt
+        self._sync_main_to_rollout()
+
+    def rollout_batch(self, all_us, use_graph=None):
+        """all_us [num_rollout_envs, horizon, A] -> rewards [num_rollout_envs, horizon]; rollouts are re-synchronised with
+        their mains before and after (RobotTrajGradSampling.rollout_batch).  With a capturable simulator backend (the
+        synthetic one; PhysX is not) the whole loop is ONE CUDA graph, captured at the first call for a given shape and
+        replayed afterwards: ``all_us`` is copied into the graph's input buffer, the returned table is the graph's output
+        buffer (valid until the next call).  In-kernel noise stays fresh across replays through a device-side step counter."""
+        if all_us.dim() != 3 or all_us.shape[0] != len(self.rollout_env_indices) or all_us.shape[2] != self.num_actions:
+            raise ValueError(f"Expected all_us of shape ({len(self.rollout_env_indices)}, horizon, {self.num_actions}), got {tuple(all_us.shape)}")
+        if self.main_env_cache is None:
+            self._cache_main_env_states()
+        if use_graph is None:
+            use_graph = bool(getattr(self.sim, "capturable", False)) and not self._python_terms and \
+                getattr(self.cfg.domain_rand, "rollout_envs_sync_pos_drift", 0.0) <= 0.0
+        horizon = all_us.shape[1]
+        if not use_graph:
+            rewards = torch.zeros((all_us.shape[0], horizon), device=self.device)
+            self._rollout_horizon(all_us.to(self.device, torch.float).contiguous(), rewards)
+            return rewards
+        key = (tuple(all_us.shape), self.root_states.data_ptr(), self.actions.data_ptr(), self.obs_buf.data_ptr())
+        g = getattr(self, "_rollout_graph", None)
+        if g is None or g["key"] != key:
+            g = {"key": key, "us": torch.zeros(all_us.shape, device=self.device), "rew": torch.zeros((all_us.shape[0], horizon), device=self.device)}
+            if getattr(self, "_step_counter", None) is None:
+                self._step_counter = torch.zeros(1, dtype=torch.int64, device=self.device)
+                object.__setattr__(self, "_ptrs_dirty", True)       # the native buffer struct picks the counter up
+            g["us"].copy_(all_us)
+            cur = torch.cuda.current_stream(self.device)
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):
+                self._rollout_horizon(g["us"], g["rew"])        # eager once: lazily built tables exist before the capture
+                side.synchronize()
+                g["graph"] = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g["graph"], stream=side):
+                    self._step_counter.add_(horizon)
+                    self._rollout_horizon(g["us"], g["rew"])
+            cur.wait_stream(side)
+            self._rollout_graph = g
+        g["us"].copy_(all_us)
+        g["graph"].replay()
+        return g["rew"]
+
+    def post_physics_step_rollout(self, noise_step=0):
         """robot_batch_rollout.py:763-817: derive + rewards + observations + histories, no episode counter, no
         termination / reset, no command / height refresh (``_post_physics_step_callback_rollout`` is empty).
         The kernel runs over every row; main rows are put back by ``_restore_main_env_states`` right after."""
         self.sim.refresh()
         P = _lib
         self._pre_step_hook_rollout()
-        self._launch(P.PHASE_DERIVE | P.PHASE_REWARD | P.PHASE_OBS | P.PHASE_HISTORY, rollout=True)
+        self._launch(P.PHASE_DERIVE | P.PHASE_REWARD | P.PHASE_OBS | P.PHASE_HISTORY, rollout=True, noise_step=noise_step)
 
     def _pre_step_hook_rollout(self):
         """``_post_physics_step_callback_rollout`` (robot_batch_rollout.py:868: empty in the base class)"""

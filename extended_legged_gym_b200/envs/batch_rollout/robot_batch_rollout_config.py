@@ -17,6 +17,22 @@ class RobotBatchRolloutCfg(LeggedRobotCfg):
         rollout_envs_sync_pos_drift = 0.0
 
 
+class RobotBatchRolloutPerceptCfg(RobotBatchRolloutCfg):
+    """envs/batch_rollout/robot_batch_rollout_percept_config.py:35-85: the ray caster block of the base config + the SDF block"""
+    class sdf:
+        enable_sdf = False
+        mesh_paths = []
+        max_distance = 10.0
+        enable_caching = True
+        update_freq = 5
+        query_bodies = []                # e.g. ["base", "LF_FOOT", ...]
+        collision_sphere_radius = []
+        collision_sphere_pos = []        # [x, y, z] per query body, body frame
+        compute_gradients = True
+        compute_nearest_points = True
+        include_in_obs = True
+
+
 class RobotBatchRolloutCfgPPO(LeggedRobotCfgPPO):
     class runner(LeggedRobotCfgPPO.runner):
         num_steps_per_env = 24

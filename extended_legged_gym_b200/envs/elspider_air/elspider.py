@@ -8,11 +8,17 @@
   _get_noise_scale_vec()    :312-332  18-DOF slices (the base class here is already generic in the DOF count)
   gait scheduler            :237-252  period 1.4 s, swing height 0.07 m, six phases alternating 0 / 0.5
 
-Both variants run inside the generic step kernel (``ElgStepParams.gait_2_step_hexapod`` / ``terminate_upside_down``); the
-``AsyncGaitScheduler`` reward is commented out in the reference's configs and not implemented.
+  async gait scheduler      :254-266, :351-363  ``_reward_async_gait_scheduler``: three posture terms of ``AsyncGaitScheduler``
+                                      weighted per reward stage by ``cfg.rewards.async_gait_scheduler`` (enabled by the reference's
+                                      pose / foot-track / trajectory-sampling hexapod configs)
+
+gait_2_step and the upside-down check run inside the generic step kernel (``ElgStepParams.gait_2_step_hexapod`` /
+``terminate_upside_down``); the async-scheduler term is a Python-side reward term (torch ops on the device, ``_python_terms``).
 """
 from types import SimpleNamespace
 
+from ...utils.gait_scheduler import AsyncGaitScheduler, AsyncGaitSchedulerCfg
+from ...utils.helpers import class_to_dict
 from ..anymal_c.anymal import Anymal
 from ..base.legged_robot_rew_mixin import _stock
 
@@ -25,6 +31,21 @@ class ElSpider(Anymal):
         # GaitSchedulerCfg defaults for six feet (utils/gait_scheduler.py:18-25) with the overrides of elspider.py:237-240
         self.gait_cfg = SimpleNamespace(dt=self.dt, period=1.4, foot_phases=[0.0, 0.5, 0.0, 0.5, 0.0, 0.5], swing_height=0.07)
         self._params_dirty = True
+        # (:254-266) the scheduler keeps the foot_positions tensor of construction time (see AsyncGaitScheduler's docstring)
+        self.async_gait_scheduler = AsyncGaitScheduler(self.height_samples, self.base_quat, self.base_lin_vel, self.base_ang_vel,
+                                                       self.projected_gravity, self.dof_pos, self.dof_vel, self.foot_positions.clone(),
+                                                       self.foot_velocities.clone(), self.num_envs, self.device, AsyncGaitSchedulerCfg())
+
+    def _reward_async_gait_scheduler(self):
+        """(:351-363) stage-dependent weights from cfg.rewards.async_gait_scheduler"""
+        scales = class_to_dict(self.cfg.rewards.async_gait_scheduler)
+
+        def weight(key, stage):
+            v = scales[key]
+            return v[min(stage, len(v) - 1)] if isinstance(v, list) else v
+        g, st = self.async_gait_scheduler, self.reward_scales_stage
+        return g.reward_dof_align() * weight("dof_align", st) + g.reward_dof_nominal_pos() * weight("dof_nominal_pos", st) + \
+            g.reward_foot_z_align() * weight("reward_foot_z_align", st)
 
     def _native_params(self):
         p = super()._native_params()

@@ -29,6 +29,7 @@ class SimBackend:
     terrain_origins: Optional[torch.Tensor] = None  # [rows, cols, 3]
     dt: float = 0.005
     use_gpu_pipeline: bool = True
+    capturable: bool = False         # True: simulate / refresh / set_* enqueue nothing that breaks a CUDA-graph capture
 
     def simulate(self) -> None: ...
     def refresh(self) -> None: ...
@@ -40,9 +41,10 @@ class SimBackend:
 
 
 class SyntheticSim(SimBackend):
+    capturable = True
     def __init__(self, cfg, num_envs: Optional[int] = None, device: str = "cuda:0", seed: int = 0,
                  spec: Optional[RobotSpec] = None, height_samples: Optional[torch.Tensor] = None,
-                 state: Optional[Dict[str, torch.Tensor]] = None):
+                 state: Optional[Dict[str, torch.Tensor]] = None, packed: bool = False):
         self.cfg = cfg
         self.device = device
         self.spec = spec or get_robot_spec(cfg.asset.name)
@@ -56,10 +58,28 @@ class SyntheticSim(SimBackend):
                                          sp.indices_matching(cfg.asset.terminate_after_contacts_on), q0, sp.foot_offsets,
                                          num_commands=cfg.commands.num_commands, seed=seed)
         self.initial_state = state      # CPU copy (histories included) for the env to seed itself from
-        self.root_states = state["root_states"].to(device).contiguous()
-        self.dof_state = state["dof_state"].to(device).contiguous()
-        self.contact_forces = state["contact_forces"].to(device).contiguous()
-        self.rigid_body_state = state["rigid_body_state"].to(device).contiguous()
+        if packed:
+            # the four simulator tensors (+ one [N, D] action block) as views of ONE device block, 256-byte aligned slices: a host
+            # that keeps the simulator state elsewhere refreshes all of it with a single copy (`state_block.copy_(pinned_block)`)
+            names = ("root_states", "dof_state", "contact_forces", "rigid_body_state")
+            shapes = {k: tuple(state[k].shape) for k in names}
+            shapes["actions"] = (self.num_envs, sp.num_dof)
+            off, self.state_slices = 0, {}
+            for k, shp in shapes.items():
+                n = int(torch.tensor(shp).prod())
+                self.state_slices[k] = (off, n, shp)
+                off += (n + 63) // 64 * 64
+            self.state_block = torch.zeros(off, dtype=torch.float, device=device)
+            for k, (o, n, shp) in self.state_slices.items():
+                v = self.state_block[o:o + n].view(shp)
+                if k in state:
+                    v.copy_(state[k])
+                setattr(self, "actions_in" if k == "actions" else k, v)
+        else:
+            self.root_states = state["root_states"].to(device).contiguous()
+            self.dof_state = state["dof_state"].to(device).contiguous()
+            self.contact_forces = state["contact_forces"].to(device).contiguous()
+            self.rigid_body_state = state["rigid_body_state"].to(device).contiguous()
         needs_hf = cfg.terrain.mesh_type in ("heightfield", "trimesh", "confined_trimesh")
         if needs_hf:
             if height_samples is None:

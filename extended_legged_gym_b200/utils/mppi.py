@@ -94,7 +94,10 @@ def mppi_update(step_rewards, samples, temperature, group=None, ops=None, comm=N
 
 def rollout_batch(env, all_us):
     """RobotTrajGradSampling.rollout_batch (robot_traj_grad_sampling.py:249-280): roll every rollout env through the
-    horizon, rewards [num_rollout_envs, horizon]; rollouts are re-synchronised with their mains before and after."""
+    horizon, rewards [num_rollout_envs, horizon]; rollouts are re-synchronised with their mains before and after.
+    Envs that have the method (RobotBatchRollout) run the loop as one CUDA graph; this is the step-by-step public-API form."""
+    if hasattr(env, "rollout_batch"):
+        return env.rollout_batch(all_us)
     batch, horizon = all_us.shape[0], all_us.shape[1]
     rewards = torch.zeros((batch, horizon), device=all_us.device)
     env._sync_main_to_rollout()

@@ -234,7 +234,14 @@ class RayCaster:
         self.ray_origins = self.ray_directions = None
         self.num_rays = 0
         self._data = RayCasterData()
+        self._distance_sink = None
         self._initialize()
+
+    def attach_distance_output(self, origins, origin_stride, out, out_row_stride, normalize=True):
+        """Fuse LeggedRobotRayCast._get_raycast_distances (envs/base/legged_robot_raycast.py:262-297) into every update: ``out``
+        receives (1 - clamp(|hit - origins[e]| / max_distance, 0, 1)) * found per ray (or the plain distance), rows
+        ``out_row_stride`` floats apart; ``origins`` rows ``origin_stride`` floats apart (root_states: 13).  None detaches."""
+        self._distance_sink = None if out is None else (origins, int(origin_stride), out, int(out_row_stride), bool(normalize))
 
     def _initialize(self):
         if self._is_initialized:
@@ -308,6 +315,15 @@ class RayCaster:
             ids = env_ids.to(torch.int64).contiguous()
             n = len(ids)
         stream = torch.cuda.current_stream(self._data.pos.device).cuda_stream
+        if self._distance_sink is not None:
+            org, ostride, out, rstride, norm = self._distance_sink
+            rc = _lib.load().elg_raycast_sensor_obs(mesh.id, self._pattern_origins.data_ptr(), self._pattern_directions.data_ptr(), self.num_rays,
+                                                    self._data.pos.data_ptr(), self._data.rot.data_ptr(), _lib.ptr(ids), n,
+                                                    int(bool(self.cfg.attach_yaw_only)), float(self.cfg.max_distance),
+                                                    self._data.ray_hits.data_ptr(), self._data.ray_hits_found.data_ptr(),
+                                                    org.data_ptr(), ostride, int(norm), out.data_ptr(), rstride, stream)
+            _lib.check(rc, "elg_raycast_sensor_obs")
+            return
         rc = _lib.load().elg_raycast_sensor(mesh.id, self._pattern_origins.data_ptr(), self._pattern_directions.data_ptr(), self.num_rays,
                                             self._data.pos.data_ptr(), self._data.rot.data_ptr(), _lib.ptr(ids), n,
                                             int(bool(self.cfg.attach_yaw_only)), float(self.cfg.max_distance),

@@ -154,7 +154,12 @@ typedef struct ElgStepParams {
   /* main / rollout env layout (envs/batch_rollout/robot_batch_rollout.py:119-164): 0 = flat env list; R1 = 1 + rollouts per main:
      row r is a main env iff r % R1 == 0.  check_termination (:857-866) ORs time-outs into the main rows only. */
   int32_t rows_per_main;
-  int32_t reserved0;
+  /* rollout mode only: elements between the reward slots of consecutive rollout envs in ElgStepBuffers.rollout_rew_out (= horizon) */
+  int32_t rollout_rew_stride;
+  /* upper bound of |height observation| = obs_scale_height + max height-entry noise scale, or 0 when unknown: lets the kernel drop
+     step()'s clip on those entries when it cannot change a value */
+  float height_obs_bound;
+  float reserved1;
   /* in-kernel noise */
   uint64_t noise_seed;
   uint64_t noise_offset;     /* step counter, so successive steps draw fresh numbers */
@@ -204,6 +209,14 @@ typedef struct ElgStepBuffers {
   uint8_t* time_out_buf;         /* [N] bool */
   float* rew_buf;                /* [N] */
   float* obs_buf;                /* [N,O] */
+  /* ---- optional extras ---- */
+  const float* dof_consts;       /* optional [5 D]: default_dof_pos | dof_pos_limits (2 D) | dof_vel_limits | torque_limits back to back
+                                    (the same values as the four arrays above): one bulk copy per CTA instead of four */
+  const uint64_t* step_counter;  /* device word added to noise_offset, or NULL: lets a CUDA graph that is replayed many times draw fresh
+                                    in-kernel noise (the host-side noise_offset is frozen into a captured launch) */
+  float* rollout_rew_out;        /* rollout mode with rows_per_main > 0, or NULL: the reward of rollout env (main k, rollout r) is ALSO
+                                    written to rollout_rew_out[(k * (rows_per_main - 1) + r) * rollout_rew_stride] -- column i of the
+                                    [num_rollout_envs, horizon] reward table of rollout_batch (robot_traj_grad_sampling.py:262-266) */
 } ElgStepBuffers;
 
 /* ABI self-description so the Python mirror structs can be checked at load time */
@@ -220,6 +233,14 @@ const char* elg_last_error(void);
 int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const float* actions, const float* dof_state,
                         const float* last_dof_vel, const float* p_gains, const float* d_gains, const float* torque_limits,
                         const float* default_dof_pos, float* torques, const int64_t* env_ids, int64_t num_ids, void* stream);
+
+/* RobotBatchRollout.step_rollout's action hand-over (envs/batch_rollout/robot_batch_rollout.py:643-656, with the joint-target
+ * denormalisation of robot_traj_grad_sampling.py:326-345 when joint_lower / joint_range are given): rollout env (main k, rollout r)
+ * takes rollout_actions[k * R + r] -- optionally lower + (clamp(a, -1, 1) + 1) * range / 2 -- clipped to +- clip_actions, written to
+ * row k * (1 + R) + 1 + r of `actions`; main rows are left alone.  One launch instead of clip + index_put. */
+int elg_rollout_actions(const float* rollout_actions /*[M*R, A]*/, int32_t num_main, int32_t rollouts_per_main, int32_t num_actions,
+                        float clip_actions, const float* joint_lower /*[A] or NULL*/, const float* joint_range /*[A] or NULL*/,
+                        float* actions /*[M*(1+R), A]*/, void* stream);
 
 /* LeggedRobot.post_physics_step body (envs/base/legged_robot.py:122-150) with
  * _post_physics_step_callback's heading + heights (:394-401), check_termination (:155-160),
@@ -308,6 +329,16 @@ int elg_raycast_sensor(const ElgMesh* mesh, const float* pattern_origins, const 
                        const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num_sensors, int yaw_only,
                        float max_dist, float* ray_hits, uint8_t* hits_found, void* stream);
 
+/* The same launch with LeggedRobotRayCast._get_raycast_distances (envs/base/legged_robot_raycast.py:262-297) fused in:
+ * distances[e, r] = |hit - dist_origins[e]| measured from the ROBOT BASE (dist_origins = root_states, dist_origin_stride = 13), and
+ * with normalize != 0 the observation (1 - clamp(d / max_dist, 0, 1)) * found -- written where compute_observations (:232-260) would
+ * concatenate it, so the ray observations never exist as a separate tensor. */
+int elg_raycast_sensor_obs(const ElgMesh* mesh, const float* pattern_origins, const float* pattern_directions, int32_t num_rays,
+                           const float* sensor_pos, const float* sensor_quat, const int64_t* env_ids, int64_t num_sensors, int yaw_only,
+                           float max_dist, float* ray_hits, uint8_t* hits_found, const float* dist_origins, int32_t dist_origin_stride,
+                           int32_t normalize, float* distances, int64_t distances_row_stride /* elements between env rows: num_rays for a dense
+                           [N, num_rays] table, num_obs when the rows are the trailing columns of obs_buf */, void* stream);
+
 /* DepthCameraWarp (utils/depth_camera.py:256-571) + DepthCameraBase.process_depth_image (:84-138). */
 typedef struct ElgCamParams {
   int32_t width, height;         /* cfg.depth.original */
@@ -342,6 +373,14 @@ int elg_depth_camera(const ElgMesh* mesh, const ElgCamParams* cam, const float* 
 int elg_sdf_query(const ElgMesh* mesh, const float* points, int64_t num_points, float max_distance, float epsilon, float* sdf, float* grad,
                   float* closest_points, int32_t* closest_face, void* stream);
 double elg_mesh_mean_edge(const ElgMesh* mesh);
+/* RobotBatchRolloutPercept._update_sdf_values (envs/batch_rollout/robot_batch_rollout_percept.py:385-441) as ONE launch over (env,
+ * query body) instead of a Python loop of gather + quat_rotate + one (or two) Warp round trips per body: the query point of body k is
+ * rigid_body_state[env, body_indices[k], 0:3] + quat_rotate(its quaternion, sphere_offsets[k]) (HOST arrays; an offset whose first
+ * component is NaN means "no offset", :401-414); sdf[env * sdf_row_stride + k], grad / nearest_points / query_points [N, K, 3]
+ * (optional) are written for the selected rows only.  nearest = p - sdf * grad (utils/mesh_sdf.py:316-336) from the same traversal. */
+int elg_sdf_query_bodies(const ElgMesh* mesh, const float* rigid_body_state /*[N*B,13]*/, int32_t num_bodies, const int32_t* body_indices,
+                         const float* sphere_offsets, int32_t num_query_bodies, const int64_t* env_ids, int64_t num_rows, float max_distance,
+                         float epsilon, float* sdf, int64_t sdf_row_stride, float* grad, float* nearest_points, float* query_points, void* stream);
 
 /* ---------------------------------------------------------------------------------------------------------------
  * Navigation command update of the batch-rollout nav task (envs/batch_rollout/robot_batch_rollout_nav.py:135-247:

@@ -54,6 +54,18 @@ class ElSpiderPDCfg(ElSpiderAirRoughCfg):
         reward_min_stage = 1
 
 
+def _control(base_cls, mode):
+    """the other two controller types of _compute_torques (legged_robot.py:425-448): velocity targets (its damping term divides
+    by sim_params.dt, not the env dt -- SURVEY App. A-13) and direct torques"""
+    class Cfg(base_cls):
+        class control(base_cls.control):
+            control_type = mode
+    Cfg.__name__ = f"{base_cls.__name__}Control{mode}"
+    return Cfg
+
+
+A1ControlVCfg = _control(A1RoughCfg, "V")
+Go2ControlTCfg = _control(Go2RoughCfg, "T")
 A1AllTermsCfg = _all_terms(A1RoughCfg)
 ElSpiderAllTermsCfg = _all_terms(ElSpiderPDCfg, heading=True)
 ElSpiderAllTermsCfg.rewards.multi_stage_rewards = False
@@ -68,6 +80,8 @@ CASES = {
     "go2_all_terms_heading": (Go2AllTermsHeadingCfg, rs.go2, None),
     "elspider_air_rough": (ElSpiderPDCfg, rs.elspider_air, None),
     "elspider_all_terms": (ElSpiderAllTermsCfg, rs.elspider_air, None),
+    "a1_control_V": (A1ControlVCfg, rs.a1, None),
+    "go2_control_T": (Go2ControlTCfg, rs.go2, None),
 }
 # reference class the golden generator runs for a case (default: LeggedRobot)
 REF_ENV_CLASS = {"elspider_air_rough": "ElSpider", "elspider_all_terms": "ElSpider"}

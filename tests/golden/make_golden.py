@@ -35,7 +35,7 @@ def reference_cfg_for(case):
     cfg_cls, _, ref_name = common.CASES[case]
     rc = rh.reference_classes()
     base = ref_name or {"a1_all_terms": "A1RoughCfg", "go2_all_terms_heading": "Go2RoughCfg", "elspider_all_terms": "ElSpiderAirRoughCfg",
-                        "elspider_air_rough": "ElSpiderAirRoughCfg"}[case]
+                        "elspider_air_rough": "ElSpiderAirRoughCfg", "a1_control_V": "A1RoughCfg", "go2_control_T": "Go2RoughCfg"}[case]
     ref_cfg = rc[base]()
     update_class_from_dict(ref_cfg, class_to_dict(cfg_cls()))
     return ref_cfg
@@ -88,7 +88,10 @@ def run_reference(case, n_envs=N_ENVS, steps=STEPS, seed=0, adversarial=True):
 
 
 def main():
+    only = sys.argv[1:]
     for case in common.CASES:
+        if only and case not in only:
+            continue
         inputs, out = run_reference(case)
         blob = {f"in__{k}": v.numpy() for k, v in inputs.items()}
         blob.update(out)

@@ -153,3 +153,40 @@ def test_rollout_batch_glue():
     nodes = us.view(m, r, horizon, env.num_actions)
     traj = mppi_update(rewards.view(m, r, horizon), nodes, 0.05)
     assert traj.shape == (m, horizon, env.num_actions)
+
+
+@pytest.mark.gpu
+def test_rollout_batch_graph_equals_step_by_step():
+    """RobotBatchRollout.rollout_batch as one CUDA graph (replayed) == horizon x step_rollout through the public API"""
+    import common
+    from extended_legged_gym_b200 import synthetic
+    from extended_legged_gym_b200.envs import RobotTrajGradSampling
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    mains, rollouts, horizon = 8, 24, 6
+    n = mains * (1 + rollouts)
+
+    def build():
+        cfg, spec, st = common.make_case_state("anymal_c_rough", n, seed=3)
+        cfg.env.num_envs, cfg.env.rollout_envs = mains, rollouts
+        env = RobotTrajGradSampling(cfg, None, SyntheticSim(cfg, n, DEV, spec=spec, height_samples=synthetic.make_height_field(seed=0), state=st), DEV, True)
+        env.set_env_state(st)
+        env._cache_main_env_states()
+        return env
+    a, b = build(), build()
+    us = (torch.randn(mains * rollouts, horizon, 12, generator=torch.Generator().manual_seed(1)) * 0.3).to(DEV)
+    want = torch.zeros(mains * rollouts, horizon, device=DEV)
+    b._sync_main_to_rollout()
+    for i in range(horizon):
+        _, _, r, _, _ = b.step_rollout(us[:, i])
+        want[:, i] = r
+    b._sync_main_to_rollout()
+    for rep in range(3):                       # capture, then replays: the result must not drift
+        got = a.rollout_batch(us).clone()
+        torch.cuda.synchronize()
+        if rep == 0:
+            assert torch.allclose(got, want, rtol=1e-5, atol=1e-6), "graph-captured rollout_batch differs from the step_rollout loop"
+            first = got
+    # replays start from the re-synchronised rollouts: with unchanged mains they reproduce the same rewards
+    assert torch.equal(got, first)
+    for k in ("root_states", "dof_state", "last_actions", "feet_air_time"):
+        assert torch.equal(getattr(a, k), getattr(b, k)), f"{k} differs after rollout_batch"
