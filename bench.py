@@ -188,6 +188,25 @@ def pin_to_gpu_numa_node(local_rank):
     return None
 
 
+def write_combined_host_block(like):
+    """Pinned WRITE-COMBINED host memory (cudaHostAllocWriteCombined) holding a copy of `like`: the host only ever writes the
+    inbound block, and the PCIe read of write-combined memory skips the snoop of the CPU caches (scripts/h2d_probe.py: 49 vs
+    39 GB/s at these sizes).  Falls back to ordinary pinned memory."""
+    try:
+        import ctypes
+        rt = ctypes.CDLL("libcudart.so")
+        p = ctypes.c_void_p()
+        nbytes = like.numel() * like.element_size()
+        if rt.cudaHostAlloc(ctypes.byref(p), ctypes.c_size_t(nbytes), ctypes.c_uint(0x04)) != 0:
+            raise RuntimeError("cudaHostAlloc failed")
+        buf = (ctypes.c_uint8 * nbytes).from_address(p.value)
+        t = torch.frombuffer(buf, dtype=torch.uint8).view(like.dtype).view(like.shape)
+        t.copy_(like)
+        return t, "write-combined pinned"
+    except Exception:
+        return like.detach().cpu().pin_memory(), "pinned"
+
+
 def build_replicas(case, common, n_envs, n_rep, dev, packed=False):
     from extended_legged_gym_b200 import _lib, synthetic
     from extended_legged_gym_b200.envs import LeggedRobot
@@ -753,7 +772,7 @@ def main():
     # ---- e2e: public Python API, PhysX state in pinned host memory, ONE packed H2D + ONE packed D2H every step
     env = envs[0]
     sim = env.sim
-    host_in = sim.state_block.detach().cpu().pin_memory()              # root / dof / contact / rigid-body state + actions, one block
+    host_in, host_in_kind = write_combined_host_block(sim.state_block.detach().cpu())   # root / dof / contact / rigid-body state + actions, one block
     # outputs the caller reads back, re-pointed at ONE device block: obs [N, O] | rew [N] | reset flags [N] (bytes, padded)
     n_out_words = n_envs * O + n_envs + (n_envs + 3) // 4
     out_block = torch.zeros(n_out_words, dtype=torch.float, device=dev)
@@ -771,6 +790,8 @@ def main():
     s_cap, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     checksum = [0.0]
 
+    # (measured on B200, profiles/README.md r2: splitting the inbound block into 2 / 4 concurrent copies on side streams is SLOWER --
+    #  0.182 / 0.206 ms per step against 0.159 ms for the single copy; write-combined host memory changes nothing at this size)
     def one_step(slot, prev_out):
         sim.state_block.copy_(host_in, non_blocking=True)
         if prev_out is not None:
@@ -840,7 +861,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "ms_per_step": t_e2e / e2e_steps * 1e3,
                 "api": "LeggedRobot._compute_torques + post_physics_step (in-kernel reset path included), simulator state in pinned host memory: "
-                       "every step ONE copy of the packed state + actions block in and ONE copy of the packed obs / rew / reset block out; "
+                       f"every step ONE copy of the packed state + actions block ({host_in_kind} host memory) in and ONE copy of the packed obs / rew / reset block out; "
                        f"{G} steps per CUDA graph, the copy-out of step i (second stream) overlaps the copy-in of step i + 1, the host waits "
                        "for the graph and reads every step's result"},
         "roofline": {"bound": "hbm", "kernel": "elg_step_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",

@@ -194,6 +194,8 @@ def load() -> C.CDLL:
     lib.elg_normalize_observations.argtypes = [i64, C.c_int32] + [vp] * 5 + [C.c_float, i64, C.c_int32] + [vp] * 7
     if lib.elg_actuator_net_words() != ACTNET_WORDS:
         raise ElgError(f"ABI mismatch: elg_actuator_net_words() = {lib.elg_actuator_net_words()}, python mirror = {ACTNET_WORDS}")
+    if hasattr(lib, "elg_set_actuator_tuning"):
+        lib.elg_set_actuator_tuning.argtypes = [C.c_int]
     lib.elg_actuator_net_torques.argtypes = [C.POINTER(ElgDims), vp, C.c_float] + [vp] * 7
     lib.elg_mesh_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(vp)]
     lib.elg_mesh_free.argtypes = [vp]

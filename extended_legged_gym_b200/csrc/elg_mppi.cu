@@ -102,11 +102,20 @@ elg_mppi_partials_kernel(const float* __restrict__ costs_all, const int M, const
   const float sum_e = block_sum(acc, red);
   float* out = partial + (size_t)m * (1 + KD);
   if (threadIdx.x == 0) out[0] = sum_e;
+  // sum_s w_s * sample[s][j]: the block is 4 sample groups x 64 columns -- consecutive lanes read consecutive floats of one sample
+  // row, every thread runs a quarter of the samples, the four partial sums meet in shared memory (fixed order: reproducible)
+  __shared__ float s_acc[4][64];
   const float* smp = samples + (size_t)m * S_local * KD;
-  for (int j = threadIdx.x; j < KD; j += blockDim.x) {
+  const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+  for (int j0 = 0; j0 < KD; j0 += 64) {
+    const int j = j0 + tx;
     float a = 0.0f;
-    for (int s = 0; s < S_local; ++s) a += w_e[s] * smp[(size_t)s * KD + j];
-    out[1 + j] = a;
+    if (j < KD)
+      for (int s = ty; s < S_local; s += 4) a = fmaf(w_e[s], smp[(size_t)s * KD + j], a);
+    __syncthreads();
+    s_acc[ty][tx] = a;
+    __syncthreads();
+    if (ty == 0 && j < KD) out[1 + j] = (s_acc[0][tx] + s_acc[1][tx]) + (s_acc[2][tx] + s_acc[3][tx]);
   }
 }
 

@@ -270,16 +270,6 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     }
   };
   prefetch(task0);
-#ifdef ELG_OPT_SUMS
-  if (warp == cap && !rollout) {
-    // the assembly warp keeps the books itself: this chunk's episode sums (row t of the [terms, N] table, lane == env: one 128-byte
-    // access per enabled term) arrive by cp.async, issued back to back, and are updated in place after the registry walk --
-    // 2 x nterms fewer bulk copies for the TMA unit to serialise
-    float* const s_sums0 = SM_F(L.sums);
-    for (int ti = 0; ti < L.nterms; ++ti) cp_async4(&s_sums0[ti * cap + e], &bf.episode_sums[(size_t)L.term_ids[ti] * dm.num_envs + genv]);
-    cp_async_commit();
-  }
-#endif
   STAMP(11, 0)
   mbar_wait(&s_bar[bsel], parity);
   STAMP(2, 0)
@@ -587,11 +577,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
           if (need_hsum) hsum += sub_r(rootz, h);
           float v = mul_r(fminf(fmaxf(sub_r(zc, h), -1.0f), 1.0f), pr.obs_scale_height);
           if (kNoise != ELG_NOISE_OFF) v = v + nz[j];
-#ifdef ELG_OPT_CLIP
           if (kClip && (L.flags & 32) == 0) v = fminf(fmaxf(v, -clip_obs), clip_obs);   // (flag 32: the host proved the clip a no-op)
-#else
-          if (kClip) v = fminf(fmaxf(v, -clip_obs), clip_obs);
-#endif
           gobs[head + p] = v;
         }
       }
@@ -664,12 +650,7 @@ elg_step_fast_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__
     float* const s_sums = SM_F(L.sums);
     float total = 0.0f, r_term = 0.0f;
     int ti = 0;
-#ifdef ELG_OPT_SUMS
-    if (!rollout) cp_async_wait_all();
-#define SUM_UPDATE(T, r_) if (live && !rollout) bf.episode_sums[(size_t)(T) * dm.num_envs + genv] = s_sums[ti * cap + e] + (r_);
-#else
 #define SUM_UPDATE(T, r_) if (live && !rollout) s_sums[ti * cap + e] += (r_);
-#endif
 #define TERM(T, VALUE)                                   \
     if (on(pr, T)) {                                       \
       const float r_ = (VALUE) * pr.reward_scales[T];      \
@@ -898,10 +879,8 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
     in(buf->gait_idx, L.gidx, 4);
     in(buf->gait_prev_foot_z, L.gprev, 16);
   }
-#ifndef ELG_OPT_SUMS
   if (!rollout)
     for (int ti = 0; ti < nt; ++ti) in(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
-#endif
 
   // outputs that are final when phase A ends come first: they are stored right behind barrier B1, under the scan
   out(buf->base_lin_vel, L.vec5 + 0 * v3, 12);
@@ -924,10 +903,8 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   out(buf->last_root_vel, L.lrv, 24);
   L.n_out_early = n_out;
   // written by the reward assembly (phase B): stored behind barrier B2
-#ifndef ELG_OPT_SUMS
   if (!rollout)
     for (int ti = 0; ti < nt; ++ti) out(buf->episode_sums + (size_t)L.term_ids[ti] * N, L.sums + ti * cap * 4, 4);
-#endif
   out(buf->rew_buf, L.rew, 4);
   if (gait) out(buf->gait_idx, L.gidx, 4);
   L.n_in = n_in;

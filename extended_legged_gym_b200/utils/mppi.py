@@ -46,6 +46,9 @@ class _CudaOps:
         return out.reshape(M, *traj_shape)
 
 
+_WORKSPACE = {}
+
+
 def mppi_update_native(step_rewards, samples, temperature, comm=None):
     """The whole update as ONE extension call on the current stream (``elg_mppi_update``): local costs -> ncclAllGather ->
     weights + partial sums -> ncclAllReduce -> mean trajectories.  ``comm``: utils.distributed.ElgComm or None (one rank).
@@ -58,8 +61,15 @@ def mppi_update_native(step_rewards, samples, temperature, comm=None):
     flat = flat if (flat.dtype == torch.float and flat.is_contiguous()) else flat.float().contiguous()
     KD = flat.shape[2]
     world = comm.world if comm is not None else 1
-    costs = torch.empty(world, M, S_local, device=r.device)
-    partial = torch.empty(M, 1 + KD, device=r.device)
+    # scratch (costs of all ranks, partial sums) is kept per shape: the call is a handful of microseconds of kernels, two
+    # allocator round trips would double its host time; the result is a fresh tensor
+    key = (world, M, S_local, KD, r.device)
+    ws = _WORKSPACE.get(key)
+    if ws is None or torch.cuda.is_current_stream_capturing():
+        ws = (torch.empty(world, M, S_local, device=r.device), torch.empty(M, 1 + KD, device=r.device))
+        if not torch.cuda.is_current_stream_capturing():
+            _WORKSPACE[key] = ws
+    costs, partial = ws
     out = torch.empty(M, KD, device=r.device)
     rc = _lib.load().elg_mppi_update(r.data_ptr(), flat.data_ptr(), M, S_local, T, KD, float(temperature), costs.data_ptr(), partial.data_ptr(),
                                      out.data_ptr(), comm.handle if comm is not None else None, torch.cuda.current_stream(r.device).cuda_stream)

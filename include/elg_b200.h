@@ -481,6 +481,9 @@ enum {
   ELG_ACTNET_WORDS = ELG_ACTNET_B_LIN + 4
 };
 int elg_actuator_net_words(void);
+/* Diagnostic (no reference counterpart): 0 = one thread per (env, dof) row (default), 1 = eight lanes per row, one hidden unit each
+ * (bit-identical results, 8x the threads; measured slower on B200 at the BASELINE sizes: shared-memory weight traffic). */
+int elg_set_actuator_tuning(int mode);
 int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float action_scale, const float* actions, const float* dof_state,
                              const float* default_dof_pos, float* hidden, float* cell, float* torques, void* stream);
 

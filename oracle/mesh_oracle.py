@@ -205,6 +205,10 @@ def sdf_query(points, max_distance, vertices, triangles, epsilon=1.0e-3, chunk=1
     for s in range(0, R, chunk):
         p = P[s:s + chunk, None, :]
         q, d2 = closest_on_triangles(p, a, b, c)
+        # zero-area triangles (the slope correction of the terrain converters collapses some) can fall through every vertex / edge
+        # region into the interior formula, whose 1 / (va + vb + vc) is then 1 / 0: such an evaluation takes no part (their
+        # edges belong to non-degenerate neighbours as well); the kernel's `d2 <= best` comparison drops the NaN the same way
+        d2 = np.where(np.isnan(d2), np.inf, d2)
         best = np.minimum(d2.min(axis=1), D * D)
         hit = d2.min(axis=1) <= D * D
         lim = np.sqrt(best) + eps_abs

@@ -113,7 +113,7 @@ def test_ray_and_sdf_on_two_layer_confined_mesh(tag, via_obj, tmp_path):
         wh, wf, wd, _ = mo.raycast_mesh(o, d, max_dist, v, t)
         assert np.array_equal(found.cpu().numpy(), wf) and np.array_equal(dist.cpu().numpy(), wd)
         assert np.allclose(hits.cpu().numpy(), wh, rtol=RTOL, atol=ATOL)
-    assert wf.mean() > 0.9            # a closed corridor: nearly every ray of 3 m hits floor or ceiling
+    assert 0.3 < wf.mean() < 1.0      # floor and ceiling over a 2.7 m x 2.1 m patch, open to the sides
     pts = o[:1500]
     s, g = sdf.query(torch.from_numpy(pts).to(DEV))
     ws, wg, _, _ = mo.sdf_query(pts, 1.5, v, t)
@@ -240,7 +240,7 @@ def test_legged_robot_depth_owns_a_camera_with_update_interval():
     first = env.get_depth_images().clone()
     ref = DepthCameraWarp(env.cfg.depth, DEV, n, v, t)
     ref.update(env.dt, env.root_states[:, :3], env.root_states[:, 3:7])
-    ref.update_depth_buffer(None, torch.ones(n, dtype=torch.int64, device=DEV))
+    ref.update_depth_buffer(None, env.episode_length_buf)
     assert torch.equal(first, ref.depth_buffer)
     assert first.shape == (n, 2, 28, 56) and float(first.abs().max()) <= 0.5 and float(first.std()) > 0
     env.root_states[:, 0] += 0.3
@@ -280,5 +280,6 @@ def test_elspider_async_gait_scheduler_term_and_go2_class():
     cfg2.env.num_envs = 32
     g = Go2(cfg2, None, SyntheticSim(cfg2, 32, DEV, spec=spec2, height_samples=synthetic.make_height_field(seed=0), state=st2), DEV, True)
     g.set_env_state(st2)
+    g0 = g.gait_idx.clone()
     g.post_physics_step()
-    assert g.gait_cfg.period == 0.6 and float(g.gait_idx[0]) == pytest.approx(g.dt / 0.6, rel=1e-5)
+    assert g.gait_cfg.period == 0.6 and torch.allclose(g.gait_idx, torch.remainder(g0 + g.dt / 0.6, 1.0), atol=1e-6)
