@@ -300,6 +300,7 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
     from extended_legged_gym_b200 import _lib as L
     lib = L.load()
     peak, _ = peaks()
+    progress("depth done; config 3")
 
     def max_over_ranks(x):
         if dist is None:
@@ -345,7 +346,7 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
         for i in range(n_rep3):
             step3(i)
         gs3.synchronize()
-        with torch.cuda.graph(g3, stream=gs3):
+        with torch.cuda.graph(g3, stream=gs3, capture_error_mode="thread_local"):
             for i in range(Ks):
                 step3(i)
             if comm is not None:
@@ -371,6 +372,7 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
                              "collectives_in_timed_region": 1 if comm is not None else 0, "resets_accumulated_since_start_all_ranks": resets3}
     del envs3, g3, stats3
     torch.cuda.empty_cache()
+    progress("config 3 done; clone / rollout / MPPI")
 
     # ---- config 5: 64 mains x 512 rollouts: state clone, then the cost-weighted update over a 20-step horizon
     import common
@@ -468,7 +470,8 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
     # correctness of the sharded update on the same data: every rank also runs the single-rank update on the FULL sample set
     rew_full = torch.randn(mains, 512, horizon, generator=g5).to(dev)
     smp_dev = smp_full.to(dev)
-    want = mppi_update(rew_full, smp_dev, 0.05)
+    from extended_legged_gym_b200.utils.mppi import mppi_update_native
+    want = mppi_update_native(rew_full, smp_dev, 0.05, comm=None)          # the single-rank update, no collective
     got = mppi_update(rew_full[:, lo5:lo5 + rollouts].contiguous(), samples, 0.05, comm=comm)
     diff = float((got - want).abs().max())
     out["mppi_iteration"] = {"workload": f"{mains} mains x 512 rollouts in total ({rollouts} per main on each of {world} rank{'s' if world > 1 else ''}) x horizon "
@@ -596,6 +599,11 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
     return out
 
 
+def progress(msg):
+    """milestones on stderr (stdout carries only the result line): a multi-rank run that stalls shows where"""
+    print(f"[bench rank {os.environ.get('RANK', '0')}] {msg}", file=sys.stderr, flush=True)
+
+
 def graph_of(fn, n, stream, warm=3):
     """Capture n calls of fn(i) on `stream` into one CUDA graph (after `warm` eager calls)."""
     g = torch.cuda.CUDAGraph()
@@ -682,7 +690,7 @@ def main():
             for i in range(3):
                 enqueue(envs[i % reps], i, with_torques)
             stream.synchronize()
-            with torch.cuda.graph(g, stream=stream):
+            with torch.cuda.graph(g, stream=stream, capture_error_mode="thread_local"):
                 for i in range(n_steps):
                     enqueue(envs[i % reps], i, with_torques)
                 if with_allreduce and comm is not None:
@@ -706,6 +714,7 @@ def main():
                 dist.barrier()
         return e0.elapsed_time(e1) * 1e-3 / reps
 
+    progress("replicas built; capturing graphs")
     g_warm = capture(W, True, n_rep, True)
     g_full = capture(K, True, n_rep, True)
     g_step = capture(K, False, n_rep, False)
@@ -716,13 +725,14 @@ def main():
     timed_replay(g_step_warm)
     with ClockSampler(local_rank) as clk:
         # the sampler (10 ms period) needs a busy region of >= 0.5 s to see clocks UNDER LOAD: the timed graph replayed back to back
-        busy = max(1, int(0.6 / max(timed_replay(g_full), 1e-6)))
-        timed_replay(g_full, reps=min(busy, 20000))
+        # (the replay count must not depend on a rank's own timing: the graph holds a collective)
+        timed_replay(g_full, reps=max(1, min(20000, int(0.6 / (K * 12e-6)))))
         t_fulls = sorted(timed_replay(g_full) for _ in range(7))
         t_steps = sorted(timed_replay(g_step) for _ in range(7))
         t_warms = sorted(timed_replay(g_step_warm) for _ in range(7))
     t_full, t_step_only, t_step_warm = t_fulls[len(t_fulls) // 2], t_steps[len(t_steps) // 2], t_warms[len(t_warms) // 2]
     clocks = clk.summary()
+    progress("headline timed")
     if dist:
         tt = torch.tensor([t_full, t_step_only, t_step_warm], device=dev, dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -769,6 +779,7 @@ def main():
                              "one of its output bytes out per CTA with no arithmetic (cold: rotating buffers > 2x L2; warm: one buffer)"}
             del src, dst, g_e, g_c, g_w
 
+    progress("floor probes done; e2e")
     # ---- e2e: public Python API, PhysX state in pinned host memory, ONE packed H2D + ONE packed D2H every step
     env = envs[0]
     sim = env.sim
@@ -877,7 +888,9 @@ def main():
     if not args.no_secondary:
         del envs, probe, env, e2e_graph, g_full, g_step, g_step_warm, g_warm
         torch.cuda.empty_cache()
+        progress("e2e done; secondary")
         sec = secondary_benchmarks(dev, world, rank, dist, quick=args.steps < 200, comm=comm, K=K)
+        progress("secondary done")
         if dist:
             sec["note"] = "per-GPU figures measured on rank 0 unless the entry says max over ranks (each rank runs its own share)"
         line["secondary"] = sec

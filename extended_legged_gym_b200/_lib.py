@@ -199,6 +199,9 @@ def load() -> C.CDLL:
     lib.elg_actuator_net_torques.argtypes = [C.POINTER(ElgDims), vp, C.c_float] + [vp] * 7
     lib.elg_mesh_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(vp)]
     lib.elg_mesh_free.argtypes = [vp]
+    if hasattr(lib, "elg_mesh_grid_info"):
+        lib.elg_mesh_grid_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
+        lib.elg_set_mesh_tuning.argtypes = [C.c_int]
     lib.elg_mesh_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_float)]
     lib.elg_raycast.argtypes = [vp, vp, vp, i64, C.c_float, vp, vp, vp, vp, vp]
     lib.elg_raycast_sensor.argtypes = [vp, vp, vp, C.c_int32, vp, vp, vp, i64, C.c_int, C.c_float, vp, vp, vp]
@@ -221,6 +224,7 @@ def load() -> C.CDLL:
         lib.elg_comm_destroy.argtypes = [vp]
         lib.elg_comm_info.argtypes = [vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         lib.elg_episode_stats_allreduce.argtypes = [vp, C.c_int32, vp, vp]
+        lib.elg_comm_warmup.argtypes = [vp, vp, C.c_int32, vp]
         lib.elg_mppi_update.argtypes = [vp, vp, i64, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp, vp, vp, vp, vp]
     lib.elg_resample_commands.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgResetParams), vp, vp, vp, vp, vp]
     lib.elg_reset_envs.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgResetParams), C.POINTER(ElgStepParams), C.POINTER(ElgResetBuffers), vp]

@@ -38,6 +38,11 @@ struct ElgMesh {
   float lo[3], hi[3]; // scene bounds
   double avg_edge;    // mean edge length (mesh_query_point_sign_normal's epsilon is relative to it)
   int device;
+  // regular-grid accelerator (height-field-derived meshes, one or more layers over the same xy grid): see GridView
+  int grid_layers, grid_nx, grid_ny;
+  float grid_x0, grid_y0, grid_dx, grid_dy, grid_pad;
+  float2* grid_cellz;   // device [layers][nx-1][ny-1]: (min, max) height of the cell's corners
+  int2* grid_celltri;   // device, same shape: the cell's two triangles as positions in `tris`
 };
 
 namespace elg {
@@ -156,10 +161,13 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
         const float4* tp = tris + 3 * (size_t)(first + i);
         const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
         double t;
-        if (ray_triangle(Ox, Oy, Oz, Dx, Dy, Dz, a, b, c, t) && t < t_best) {
-          t_best = t;
-          best_tri = __float_as_int(c.y);
-          t_cull = __double2float_ru(t);
+        if (ray_triangle(Ox, Oy, Oz, Dx, Dy, Dz, a, b, c, t)) {
+          const int id = __float_as_int(c.y);
+          if (t < t_best || (t == t_best && best_tri >= 0 && id < best_tri)) {   // ties: the lowest triangle id (what argmin picks)
+            t_best = t;
+            best_tri = id;
+            t_cull = __double2float_ru(t);
+          }
         }
       }
     }
@@ -170,10 +178,115 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
 }
 
 // ---------------------------------------------------------------------------------------------
+// Regular-grid fast path.  The terrain meshes of the BASELINE configs are triangulated height fields (utils/terrain.py:76-80;
+// the confined terrain is two of them, ground and ceiling, over the same grid: utils/terrain_confine.py:13-146): vertex (i, j) of
+// a layer sits at (x_i, y_j), every triangle lies inside one cell.  For such a mesh a ray needs no tree: it walks the slabs of
+// its major horizontal axis front to back, in each slab the one or two cells its (padded) footprint touches, skips a cell when
+// the ray's height interval over the slab misses the cell's [min, max], and otherwise runs the SAME fp64 ray / triangle test on
+// the cell's two triangles as the BVH path does.  Slabs are ordered by entry distance, so the walk stops at the first slab that
+// starts behind the best hit.  Every candidate the exact test could accept is visited (footprints are padded by more than the
+// fp32 error of the slab arithmetic), the accepted minimum is taken over the same triangle tests: distances and hit flags are
+// bit-identical to the BVH path (tests/test_raycast.py compares them).
+// ---------------------------------------------------------------------------------------------
+struct GridView {
+  int layers, nx, ny;          // vertices per axis; layers == 0: no grid, use the BVH
+  float x0, y0, dx, dy, pad;
+  const float2* cellz;
+  const int2* celltri;
+};
+
+__device__ __forceinline__ bool trace_grid(const GridView g, const float4* __restrict__ tris, const float ox, const float oy, const float oz,
+                                           const float dx, const float dy, const float dz, const float max_t, Hit& hit) {
+  const double Ox = ox, Oy = oy, Oz = oz, Dx = dx, Dy = dy, Dz = dz;
+  double t_best = (double)max_t;
+  int best_tri = -1;
+  const int cx = g.nx - 1, cy = g.ny - 1;
+  auto test_cell = [&](const int i, const int j, const float zlo, const float zhi, const bool zcull) {
+    for (int l = 0; l < g.layers; ++l) {
+      const size_t c = ((size_t)l * cx + i) * cy + j;
+      if (zcull) {
+        const float2 z = __ldg(g.cellz + c);
+        if (zhi < z.x || zlo > z.y) continue;
+      }
+      const int2 tt = __ldg(g.celltri + c);
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float4* tp = tris + 3 * (size_t)(k == 0 ? tt.x : tt.y);
+        const float4 a = __ldg(tp), b = __ldg(tp + 1), cc = __ldg(tp + 2);
+        double t;
+        if (ray_triangle(Ox, Oy, Oz, Dx, Dy, Dz, a, b, cc, t)) {
+          const int id = __float_as_int(cc.y);
+          if (t < t_best || (t == t_best && best_tri >= 0 && id < best_tri)) {
+            t_best = t;
+            best_tri = id;
+          }
+        }
+      }
+    }
+  };
+  const bool xmajor = fabsf(dx) >= fabsf(dy);
+  const float ou = xmajor ? ox : oy, ov = xmajor ? oy : ox, du = xmajor ? dx : dy, dv = xmajor ? dy : dx;
+  const float U0 = xmajor ? g.x0 : g.y0, V0 = xmajor ? g.y0 : g.x0, DU = xmajor ? g.dx : g.dy, DV = xmajor ? g.dy : g.dx;
+  const int nu = xmajor ? cx : cy, nv = xmajor ? cy : cx;
+  const float iDU = 1.0f / DU, iDV = 1.0f / DV, pad = g.pad;
+  auto cell_range = [](const float lo, const float hi, const float base, const float inv, const int n, int& a, int& b) {
+    // cells [a, b] whose extent meets [lo, hi]; empty (a > b) when the interval lies outside the grid
+    const float fa = floorf((lo - base) * inv), fb = floorf((hi - base) * inv);
+    a = fa < 0.0f ? 0 : (fa > (float)(n - 1) ? n : (int)fa);
+    b = fb < 0.0f ? -1 : (fb > (float)(n - 1) ? n - 1 : (int)fb);
+  };
+  if (!(fabsf(du) * max_t > 4.0f * pad)) {
+    // (near-)vertical ray: its whole footprint is a padded point -- at most 2 x 2 cells, no slab walk
+    const float ext = fabsf(du) * max_t + pad;
+    int ia, ib, ja, jb;
+    cell_range(ou - ext, ou + ext, U0, iDU, nu, ia, ib);
+    cell_range(ov - ext, ov + ext, V0, iDV, nv, ja, jb);
+    for (int i = ia; i <= ib; ++i)
+      for (int j = ja; j <= jb; ++j) test_cell(xmajor ? i : j, xmajor ? j : i, 0.0f, 0.0f, false);
+  } else {
+    const float inv_du = 1.0f / du;
+    const float u_end = ou + du * max_t;
+    int ia, ib;
+    cell_range(fminf(ou, u_end) - pad, fmaxf(ou, u_end) + pad, U0, iDU, nu, ia, ib);
+    const int step = du > 0.0f ? 1 : -1;
+    const float zpad = pad * (1.0f + fabsf(dz * inv_du)), vpad = pad * (1.0f + fabsf(dv * inv_du));
+    for (int i = du > 0.0f ? ia : ib, left = ib - ia + 1; left > 0; --left, i += step) {
+      const float ua = U0 + (float)i * DU - pad, ub = U0 + (float)(i + 1) * DU + pad;
+      float t0 = (ua - ou) * inv_du, t1 = (ub - ou) * inv_du;
+      if (t0 > t1) { const float tt = t0; t0 = t1; t1 = tt; }
+      t0 = fmaxf(t0, 0.0f);
+      t1 = fminf(t1, max_t);
+      if (t0 > t1) continue;
+      if ((double)t0 > t_best) break;          // every later slab starts behind the best hit
+      const float va = ov + t0 * dv, vb = ov + t1 * dv;
+      int ja, jb;
+      cell_range(fminf(va, vb) - vpad, fmaxf(va, vb) + vpad, V0, iDV, nv, ja, jb);
+      const float za = oz + t0 * dz, zb = oz + t1 * dz;
+      const float zlo = fminf(za, zb) - zpad, zhi = fmaxf(za, zb) + zpad;
+      for (int j = ja; j <= jb; ++j) test_cell(xmajor ? i : j, xmajor ? j : i, zlo, zhi, true);
+    }
+  }
+  hit.t = t_best;
+  hit.tri = best_tri;
+  return best_tri >= 0;
+}
+
+// the mesh query every ray kernel calls: grid walk for height-field-derived meshes, BVH otherwise -- a compile-time choice, so that
+// neither instantiation carries the other's registers (the BVH stack, the slab state)
+template <bool kGrid>
+__device__ __forceinline__ bool trace_any(const GridView g, const float4* __restrict__ nodes, const float4* __restrict__ tris, const float ox,
+                                          const float oy, const float oz, const float dx, const float dy, const float dz, const float max_t,
+                                          Hit& hit) {
+  if (kGrid) return trace_grid(g, tris, ox, oy, oz, dx, dy, dz, max_t, hit);
+  return trace(nodes, tris, ox, oy, oz, dx, dy, dz, max_t, hit);
+}
+
+// ---------------------------------------------------------------------------------------------
 // raycast_mesh (utils/ray_caster.py:45-92): one thread per ray
 // ---------------------------------------------------------------------------------------------
+template <bool kGrid>
 __global__ void __launch_bounds__(128)
-elg_raycast_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ origins,
+elg_raycast_kernel(const GridView gv, const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ origins,
                    const float* __restrict__ dirs, const long long n, const float max_dist, float* __restrict__ hits,
                    uint8_t* __restrict__ found, float* __restrict__ dist_out, int* __restrict__ tri_out) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -181,7 +294,7 @@ elg_raycast_kernel(const float4* __restrict__ nodes, const float4* __restrict__ 
   const float ox = origins[3 * i], oy = origins[3 * i + 1], oz = origins[3 * i + 2];
   const float dx = dirs[3 * i], dy = dirs[3 * i + 1], dz = dirs[3 * i + 2];
   Hit h;
-  const bool ok = trace(nodes, tris, ox, oy, oz, dx, dy, dz, max_dist, h);
+  const bool ok = trace_any<kGrid>(gv, nodes, tris, ox, oy, oz, dx, dy, dz, max_dist, h);
   const float t = ok ? (float)h.t : max_dist;   // miss: the ray end point (ray_caster.py:88-92)
   hits[3 * i] = add_r(ox, mul_r(t, dx));
   hits[3 * i + 1] = add_r(oy, mul_r(t, dy));
@@ -208,8 +321,9 @@ __device__ __forceinline__ void quat_apply_r(const float qx, const float qy, con
 // pattern origin / direction by the sensor quaternion, + sensor position -- instead of materialising [N, n, 3]
 // origin and direction tensors.  One thread per (sensor, ray); rays of one sensor share a warp where n >= 32.
 // ---------------------------------------------------------------------------------------------
+template <bool kGrid>
 __global__ void __launch_bounds__(128)
-elg_raycast_sensor_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ pat_o,
+elg_raycast_sensor_kernel(const GridView gv, const float4* __restrict__ nodes, const float4* __restrict__ tris, const float* __restrict__ pat_o,
                           const float* __restrict__ pat_d, const int n_rays, const float* __restrict__ pos,
                           const float* __restrict__ quat, const int64_t* __restrict__ env_ids, const long long n_sensors,
                           const int yaw_only, const float max_dist, float* __restrict__ hits, uint8_t* __restrict__ found,
@@ -236,7 +350,7 @@ elg_raycast_sensor_kernel(const float4* __restrict__ nodes, const float4* __rest
   oz = add_r(oz, pos[3 * e + 2]);
   quat_apply_r(qx, qy, qz, qw, pat_d[3 * r], pat_d[3 * r + 1], pat_d[3 * r + 2], dx, dy, dz);
   Hit h;
-  const bool ok = trace(nodes, tris, ox, oy, oz, dx, dy, dz, max_dist, h);
+  const bool ok = trace_any<kGrid>(gv, nodes, tris, ox, oy, oz, dx, dy, dz, max_dist, h);
   const float t = ok ? (float)h.t : max_dist;
   const long long o = (e * n_rays + r) * 3;
   const float hx = add_r(ox, mul_r(t, dx)), hy = add_r(oy, mul_r(t, dy)), hz = add_r(oz, mul_r(t, dz));
@@ -296,8 +410,9 @@ elg_camera_pose_kernel(const float* __restrict__ pos, const float* __restrict__ 
 // taps tabulated by the host from torchvision itself), normalised and pushed into the env's frame ring buffer -- the
 // reference's per-env Python loop (:486-499).  28 bytes per camera in, 4 bytes per output pixel out.
 // ---------------------------------------------------------------------------------------------
+template <bool kGrid>
 __global__ void __launch_bounds__(256)
-elg_depth_camera_kernel(const float4* __restrict__ nodes, const float4* __restrict__ tris, const __grid_constant__ ElgCamParams cp,
+elg_depth_camera_kernel(const GridView gv, const float4* __restrict__ nodes, const float4* __restrict__ tris, const __grid_constant__ ElgCamParams cp,
                         const float* __restrict__ ray_dirs, const float* __restrict__ cam_pos, const float* __restrict__ cam_rot,
                         const int64_t* __restrict__ ep_len, const float* __restrict__ noise_u, const int32_t* __restrict__ rx_start,
                         const float* __restrict__ rx_w, const int32_t* __restrict__ ry_start, const float* __restrict__ ry_w,
@@ -314,7 +429,7 @@ elg_depth_camera_kernel(const float4* __restrict__ nodes, const float4* __restri
     float dx, dy, dz;
     quat_apply_r(qx, qy, qz, qw, ray_dirs[3 * r], ray_dirs[3 * r + 1], ray_dirs[3 * r + 2], dx, dy, dz);
     Hit h;
-    const bool ok = trace(nodes, tris, px, py, pz, dx, dy, dz, cp.far_clip, h);
+    const bool ok = trace_any<kGrid>(gv, nodes, tris, px, py, pz, dx, dy, dz, cp.far_clip, h);
     float d = -cp.far_clip;
     if (ok) {
       const float t = (float)h.t;
@@ -840,6 +955,81 @@ int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* 
     }
   }
 
+  // ---- regular-grid detection (height-field-derived meshes: GridView above).  V = layers x nx x ny vertices with vertex (l, i, j) at
+  // (xs[i], ys[j]) exactly, xs / ys increasing and uniform to within a small fraction of a cell, every triangle inside one cell of one
+  // layer, exactly two triangles per cell.  Anything else (OBJ scenes, slope-corrected meshes whose vertices were moved sideways)
+  // keeps the BVH walk.
+  std::vector<float> h_cellz;
+  std::vector<int> h_celltri;
+  int g_layers = 0, g_nx = 0, g_ny = 0;
+  float g_x0 = 0, g_y0 = 0, g_dx = 0, g_dy = 0, g_pad = 0;
+  {
+    std::vector<int> pos_of(num_triangles);
+    for (int i = 0; i < num_triangles; ++i) pos_of[B.order[i]] = i;
+    for (int L = 1; L <= 4 && g_layers == 0; ++L) {
+      if (num_vertices % L) continue;
+      const int P = num_vertices / L;
+      int ny = 1;
+      while (ny < P && vertices[3 * (size_t)ny] == vertices[0]) ++ny;
+      if (ny < 2 || P % ny) continue;
+      const int nx = P / ny;
+      if (nx < 2 || (long long)L * (nx - 1) * (ny - 1) * 2 != num_triangles) continue;
+      bool ok = true;
+      for (int l = 0; l < L && ok; ++l)
+        for (int i = 0; i < nx && ok; ++i)
+          for (int j = 0; j < ny; ++j) {
+            const float* v = vertices + 3 * ((size_t)l * P + (size_t)i * ny + j);
+            if (v[0] != vertices[3 * (size_t)i * ny] || v[1] != vertices[3 * (size_t)j + 1]) { ok = false; break; }
+          }
+      if (!ok) continue;
+      const double x0 = vertices[0], y0 = vertices[1];
+      const double dx = ((double)vertices[3 * (size_t)(nx - 1) * ny] - x0) / (nx - 1), dy = ((double)vertices[3 * (size_t)(ny - 1) + 1] - y0) / (ny - 1);
+      if (!(dx > 0.0) || !(dy > 0.0)) continue;
+      double dev = 0.0;
+      for (int i = 0; i < nx; ++i) dev = std::max(dev, fabs((double)vertices[3 * (size_t)i * ny] - (x0 + i * dx)));
+      for (int j = 0; j < ny; ++j) dev = std::max(dev, fabs((double)vertices[3 * (size_t)j + 1] - (y0 + j * dy)));
+      if (dev > 0.01 * std::min(dx, dy)) continue;
+      const size_t ncell = (size_t)L * (nx - 1) * (ny - 1);
+      std::vector<int> tri(2 * ncell, -1);
+      for (int t = 0; t < num_triangles && ok; ++t) {
+        int lmin = INT32_MAX, lmax = -1, imin = INT32_MAX, imax = -1, jmin = INT32_MAX, jmax = -1;
+        for (int k = 0; k < 3; ++k) {
+          const int vi = triangles[3 * (size_t)t + k];
+          const int l = vi / P, r = vi % P, i = r / ny, j = r % ny;
+          lmin = std::min(lmin, l); lmax = std::max(lmax, l);
+          imin = std::min(imin, i); imax = std::max(imax, i);
+          jmin = std::min(jmin, j); jmax = std::max(jmax, j);
+        }
+        if (lmin != lmax || imax - imin > 1 || jmax - jmin > 1 || imin > nx - 2 || jmin > ny - 2) { ok = false; break; }
+        // (a degenerate triangle on one grid line still belongs to the cell at its lower corner)
+        const size_t c = ((size_t)lmin * (nx - 1) + imin) * (ny - 1) + jmin;
+        if (tri[2 * c] < 0) tri[2 * c] = pos_of[t];
+        else if (tri[2 * c + 1] < 0) tri[2 * c + 1] = pos_of[t];
+        else ok = false;
+      }
+      for (size_t c = 0; c < 2 * ncell && ok; ++c) ok = tri[c] >= 0;
+      if (!ok) continue;
+      h_cellz.resize(2 * ncell);
+      for (int l = 0; l < L; ++l)
+        for (int i = 0; i < nx - 1; ++i)
+          for (int j = 0; j < ny - 1; ++j) {
+            float lo = FLT_MAX, hi = -FLT_MAX;
+            for (int a = 0; a < 2; ++a)
+              for (int b = 0; b < 2; ++b) {
+                const float z = vertices[3 * ((size_t)l * P + (size_t)(i + a) * ny + (j + b)) + 2];
+                lo = std::min(lo, z); hi = std::max(hi, z);
+              }
+            const size_t c = ((size_t)l * (nx - 1) + i) * (ny - 1) + j;
+            h_cellz[2 * c] = lo; h_cellz[2 * c + 1] = hi;
+          }
+      h_celltri.swap(tri);
+      g_layers = L; g_nx = nx; g_ny = ny;
+      g_x0 = (float)x0; g_y0 = (float)y0; g_dx = (float)dx; g_dy = (float)dy;
+      // footprint padding: the grid-line deviation + a thousandth of a cell + 16 ulp of the largest coordinate (fp32 slab arithmetic)
+      g_pad = (float)(dev + 1e-3 * std::min(dx, dy)) + 2e-6f * ext + 1e-30f;
+    }
+  }
+
   ElgMesh* m = new ElgMesh();
   m->num_vertices = num_vertices;
   m->num_triangles = num_triangles;
@@ -848,6 +1038,9 @@ int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* 
   for (int k = 0; k < 3; ++k) { m->lo[k] = scene.lo[k]; m->hi[k] = scene.hi[k]; }
   m->nodes = nullptr;
   m->tris = nullptr;
+  m->grid_layers = 0;
+  m->grid_cellz = nullptr;
+  m->grid_celltri = nullptr;
   cudaGetDevice(&m->device);
   if (cudaMalloc(&m->nodes, hn.size() * 4) != cudaSuccess || cudaMalloc(&m->tris, ht.size() * 4) != cudaSuccess ||
       cudaMemcpy(m->nodes, hn.data(), hn.size() * 4, cudaMemcpyHostToDevice) != cudaSuccess ||
@@ -858,7 +1051,44 @@ int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* 
     delete m;
     return mfail(ELG_ERR_CUDA, "elg_mesh_create: cannot allocate / upload the BVH (is a CUDA device present?)");
   }
+  if (g_layers > 0) {      // the accelerator is optional: a failed upload just leaves the BVH walk
+    if (cudaMalloc(&m->grid_cellz, h_cellz.size() * 4) == cudaSuccess && cudaMalloc(&m->grid_celltri, h_celltri.size() * 4) == cudaSuccess &&
+        cudaMemcpy(m->grid_cellz, h_cellz.data(), h_cellz.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess &&
+        cudaMemcpy(m->grid_celltri, h_celltri.data(), h_celltri.size() * 4, cudaMemcpyHostToDevice) == cudaSuccess) {
+      m->grid_layers = g_layers; m->grid_nx = g_nx; m->grid_ny = g_ny;
+      m->grid_x0 = g_x0; m->grid_y0 = g_y0; m->grid_dx = g_dx; m->grid_dy = g_dy; m->grid_pad = g_pad;
+    } else {
+      cudaGetLastError();
+      if (m->grid_cellz) cudaFree(m->grid_cellz);
+      if (m->grid_celltri) cudaFree(m->grid_celltri);
+      m->grid_cellz = nullptr; m->grid_celltri = nullptr;
+    }
+  }
   *out = m;
+  return ELG_OK;
+}
+
+static int g_mesh_no_grid = 0;
+static elg::GridView grid_view(const ElgMesh* m) {
+  elg::GridView g{};
+  if (m->grid_layers > 0 && !g_mesh_no_grid) {
+    g.layers = m->grid_layers; g.nx = m->grid_nx; g.ny = m->grid_ny;
+    g.x0 = m->grid_x0; g.y0 = m->grid_y0; g.dx = m->grid_dx; g.dy = m->grid_dy; g.pad = m->grid_pad;
+    g.cellz = m->grid_cellz; g.celltri = m->grid_celltri;
+  }
+  return g;
+}
+
+int elg_set_mesh_tuning(int disable_grid) {
+  g_mesh_no_grid = disable_grid != 0;
+  return ELG_OK;
+}
+
+int elg_mesh_grid_info(const ElgMesh* mesh, int32_t* layers, int32_t* nx, int32_t* ny) {
+  if (!mesh) return mfail(ELG_ERR_NULL_POINTER, "mesh is NULL");
+  if (layers) *layers = mesh->grid_layers;
+  if (nx) *nx = mesh->grid_nx;
+  if (ny) *ny = mesh->grid_ny;
   return ELG_OK;
 }
 
@@ -866,6 +1096,8 @@ int elg_mesh_free(ElgMesh* mesh) {
   if (!mesh) return ELG_OK;
   cudaFree(mesh->nodes);
   cudaFree(mesh->tris);
+  if (mesh->grid_cellz) cudaFree(mesh->grid_cellz);
+  if (mesh->grid_celltri) cudaFree(mesh->grid_celltri);
   delete mesh;
   return ELG_OK;
 }
@@ -889,9 +1121,9 @@ int elg_raycast(const ElgMesh* mesh, const float* ray_origins, const float* ray_
   const int threads = 128;
   const long long blocks = (num_rays + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many rays for one launch");
-  elg::elg_raycast_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(mesh->nodes, mesh->tris, ray_origins, ray_directions,
-                                                                                  num_rays, max_dist, ray_hits, hits_found, hit_distance,
-                                                                                  hit_triangle);
+  const elg::GridView gv = grid_view(mesh);
+  (gv.layers > 0 ? elg::elg_raycast_kernel<true> : elg::elg_raycast_kernel<false>)<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      gv, mesh->nodes, mesh->tris, ray_origins, ray_directions, num_rays, max_dist, ray_hits, hits_found, hit_distance, hit_triangle);
   return elg::check_launch("elg_raycast");
 }
 
@@ -907,8 +1139,9 @@ int elg_raycast_sensor(const ElgMesh* mesh, const float* pattern_origins, const 
   const int threads = 128;
   const long long blocks = (num_sensors * num_rays + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many rays for one launch");
-  elg::elg_raycast_sensor_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-      mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
+  const elg::GridView gv = grid_view(mesh);
+  (gv.layers > 0 ? elg::elg_raycast_sensor_kernel<true> : elg::elg_raycast_sensor_kernel<false>)<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      gv, mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
       max_dist, ray_hits, hits_found, nullptr, 0, 0, nullptr, 0);
   return elg::check_launch("elg_raycast_sensor");
 }
@@ -927,8 +1160,9 @@ int elg_raycast_sensor_obs(const ElgMesh* mesh, const float* pattern_origins, co
   const int threads = 128;
   const long long blocks = (num_sensors * num_rays + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return mfail(ELG_ERR_UNSUPPORTED, "too many rays for one launch");
-  elg::elg_raycast_sensor_kernel<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
-      mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
+  const elg::GridView gv = grid_view(mesh);
+  (gv.layers > 0 ? elg::elg_raycast_sensor_kernel<true> : elg::elg_raycast_sensor_kernel<false>)<<<(unsigned)blocks, threads, 0, (cudaStream_t)stream>>>(
+      gv, mesh->nodes, mesh->tris, pattern_origins, pattern_directions, num_rays, sensor_pos, sensor_quat, env_ids, num_sensors, yaw_only,
       max_dist, ray_hits, hits_found, dist_origins, dist_origin_stride, normalize, distances, (long long)distances_row_stride);
   return elg::check_launch("elg_raycast_sensor_obs");
 }
@@ -967,12 +1201,14 @@ int elg_depth_camera(const ElgMesh* mesh, const ElgCamParams* cam, const float* 
   if (smem > 200 * 1024) return mfail(ELG_ERR_UNSUPPORTED, "image too large for the fused depth kernel (> 200 KB of shared memory)");
   static size_t smem_set = 0;
   if (smem > 48 * 1024 && smem > smem_set) {
-    if (cudaFuncSetAttribute(elg::elg_depth_camera_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
+    if (cudaFuncSetAttribute(elg::elg_depth_camera_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(elg::elg_depth_camera_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return mfail(ELG_ERR_CUDA, "cannot reserve shared memory for elg_depth_camera_kernel");
     smem_set = smem;
   }
-  elg::elg_depth_camera_kernel<<<(unsigned)num_envs, 256, smem, (cudaStream_t)stream>>>(
-      mesh->nodes, mesh->tris, *cam, ray_directions, camera_pos, camera_rot, episode_length_buf, noise_u, resize_x_start, resize_x_weights,
+  const elg::GridView gv = grid_view(mesh);
+  (gv.layers > 0 ? elg::elg_depth_camera_kernel<true> : elg::elg_depth_camera_kernel<false>)<<<(unsigned)num_envs, 256, smem, (cudaStream_t)stream>>>(
+      gv, mesh->nodes, mesh->tris, *cam, ray_directions, camera_pos, camera_rot, episode_length_buf, noise_u, resize_x_start, resize_x_weights,
       resize_y_start, resize_y_weights, depth_buffer, raw_depth);
   return elg::check_launch("elg_depth_camera");
 }

@@ -116,6 +116,17 @@ int elg_comm_info(const ElgComm* comm, int* rank, int* world, int* nccl_version)
   return ELG_OK;
 }
 
+// one all-gather of `n` floats per rank (+ one float all-reduce) so that NCCL's lazy peer set-up for the collectives of
+// elg_mppi_update happens here, outside any CUDA-graph capture; scratch holds >= 8 * world bytes * n
+int elg_comm_warmup(ElgComm* comm, void* scratch, int32_t n, void* stream) {
+  if (!comm || comm->world == 1) return ELG_OK;
+  if (!scratch || n < 1) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "elg_comm_warmup: scratch is NULL or n < 1");
+  float* f = static_cast<float*>(scratch);
+  if (int rc = nccl_check(g_nccl.AllGather(f + (size_t)comm->rank * n, f, (size_t)n, /*ncclFloat32*/ 7, comm->comm, (cudaStream_t)stream), "ncclAllGather(warm-up)"))
+    return rc;
+  return nccl_check(g_nccl.AllReduce(f, f, (size_t)n, 7, 0, comm->comm, (cudaStream_t)stream), "ncclAllReduce(warm-up)");
+}
+
 int elg_episode_stats_allreduce(double* stats, int32_t n, ElgComm* comm, void* stream) {
   if (n < 0) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "elg_episode_stats_allreduce: negative length");
   if (n == 0 || !comm || comm->world == 1) return ELG_OK;   // one rank: the local sums are the global ones

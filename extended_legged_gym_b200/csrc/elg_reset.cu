@@ -17,6 +17,7 @@
 #include <stdint.h>
 
 #include "elg_common.cuh"
+#include "elg_async.cuh"
 
 namespace elg {
 
@@ -57,6 +58,8 @@ __global__ void __launch_bounds__(128)
 elg_resample_kernel(const __grid_constant__ ElgResetParams rp, const int N, const int D, const int C, const int64_t* __restrict__ ep_len,
                     float* __restrict__ commands, const float* __restrict__ uniforms, float* __restrict__ stats_to_zero) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();   // programmatic dependent launch: the next kernel's prologue may start; nothing is read before the wait
+  pdl_wait();
   if (stats_to_zero && e < ELG_NUM_REWARD_TERMS + 2) stats_to_zero[e] = 0.0f;   // this step's extras["episode"] accumulators
   if (e >= N) return;
   // main / rollout layout: the clock and the random numbers are the MAIN env's; every row of the group ends up with the main's
@@ -76,22 +79,21 @@ elg_resample_kernel(const __grid_constant__ ElgResetParams rp, const int N, cons
 // robot_batch_rollout.py:925-931.)  One CTA; the flag is word ELG_NUM_REWARD_TERMS + 1 of the stats vector.
 __global__ void __launch_bounds__(1024)
 elg_main_reset_flag_kernel(const uint8_t* __restrict__ reset_buf, const int num_main, const int rows_per_main, float* __restrict__ stats) {
+  pdl_launch_dependents();
+  pdl_wait();
   int any = 0;
   for (int k = threadIdx.x; k < num_main; k += blockDim.x) any |= reset_buf[(size_t)k * rows_per_main];
   any = __syncthreads_or(any);
   if (threadIdx.x == 0) stats[ELG_NUM_REWARD_TERMS + 1] = any ? 1.0f : 0.0f;
 }
 
-// one WARP per env (envs that do not reset leave at once): lane 0 does the scalar work, lanes < D the joints, and all
-// lanes repair the observation row -- commands, dof_pos, dof_vel and the height entries, which depend on the new base
-// height (compute_observations runs after reset_idx on stale measured_heights, App. A-4) -- with the very noise samples
-// the step kernel attached to those entries.
-__global__ void __launch_bounds__(128)
-elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constant__ ElgStepParams pr, const __grid_constant__ ElgResetBuffers rb,
-                 const int N, const int D, const int F, const int C, const int O, const int H) {
-  const int e = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (e >= N) return;
+// One warp per 32 consecutive envs: every lane reads the flags of its env (one coalesced load), a ballot finds the few rows that
+// have work, and the WARP then handles those one after the other -- lane 0 does the scalar work, lanes < D the joints, and all
+// lanes repair the observation row: commands, dof_pos, dof_vel and the height entries, which depend on the new base height
+// (compute_observations runs after reset_idx on stale measured_heights, App. A-4), with the very noise samples the step kernel
+// attached to those entries.  (Round 1 launched one warp per env: at 65 536 envs that is 65 536 warps to find ~300 resets.)
+__device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgStepParams& pr, const ElgResetBuffers& rb, const int e, const int lane,
+                                          const int N, const int D, const int F, const int C, const int O, const int H) {
   // main / rollout layout (robot_batch_rollout.py:876-940): any reset row gets new joints / root / histories; the terrain
   // curriculum, the command resampling and the extras sums belong to MAIN envs, and a main's new commands go to all its rows
   const int R1 = rp.rows_per_main;
@@ -251,10 +253,47 @@ elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constan
   }
 }
 
+__global__ void __launch_bounds__(128)
+elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constant__ ElgStepParams pr, const __grid_constant__ ElgResetBuffers rb,
+                 const int N, const int D, const int F, const int C, const int O, const int H) {
+  const int lane = threadIdx.x & 31;
+  const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (base >= N) return;
+  const int mine = base + lane;
+  bool work = false;
+  if (mine < N) {
+    work = rb.reset_buf[mine] != 0;
+    if (!work && rp.rows_per_main > 0) work = rb.reset_buf[(mine / rp.rows_per_main) * rp.rows_per_main] != 0;   // the main env of this row resets
+  }
+  unsigned todo = __ballot_sync(0xffffffffu, work);
+  while (todo) {
+    const int b = __ffs((int)todo) - 1;
+    todo &= todo - 1;
+    reset_env(rp, pr, rb, base + b, lane, N, D, F, C, O, H);
+    __syncwarp();
+  }
+}
+
 }  // namespace elg
 
 namespace {
 int rfail(int code, const char* msg) { return elg::set_error(code, msg); }
+
+template <typename... Params, typename... Args>
+void launch_pdl(void (*k)(Params...), dim3 grid, int threads, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k, Params(args)...);
+}
 }  // namespace
 
 extern "C" {
@@ -271,8 +310,8 @@ int elg_resample_commands(const ElgDims* dims, const ElgResetParams* rp, const i
     return rfail(ELG_ERR_INVALID_ARGUMENT, "rows_per_main must divide num_envs");
   if (dims->num_envs == 0) return ELG_OK;
   if (!episode_length_buf || !commands) return rfail(ELG_ERR_NULL_POINTER, "episode_length_buf/commands is NULL");
-  elg::elg_resample_kernel<<<(dims->num_envs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*rp, dims->num_envs, dims->num_dof, dims->num_commands,
-                                                                                         episode_length_buf, commands, uniforms, stats_to_zero);
+  launch_pdl(elg::elg_resample_kernel, dim3((dims->num_envs + 127) / 128), 128, (cudaStream_t)stream, *rp, (int)dims->num_envs, (int)dims->num_dof,
+             (int)dims->num_commands, episode_length_buf, commands, uniforms, stats_to_zero);
   return elg::check_launch("elg_resample_commands");
 }
 
@@ -293,9 +332,10 @@ int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepP
   if (rp->rows_per_main < 0 || (rp->rows_per_main > 0 && dims->num_envs % rp->rows_per_main != 0))
     return rfail(ELG_ERR_INVALID_ARGUMENT, "rows_per_main must divide num_envs");
   if (rp->rows_per_main > 0)
-    elg::elg_main_reset_flag_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(buf->reset_buf, dims->num_envs / rp->rows_per_main, rp->rows_per_main, buf->stats);
-  elg::elg_reset_kernel<<<(dims->num_envs + 3) / 4, 128, 0, (cudaStream_t)stream>>>(*rp, *prm, *buf, dims->num_envs, dims->num_dof, dims->num_feet,
-                                                                                      dims->num_commands, dims->num_obs, dims->num_height_points);
+    launch_pdl(elg::elg_main_reset_flag_kernel, dim3(1), 1024, (cudaStream_t)stream, buf->reset_buf, (int)(dims->num_envs / rp->rows_per_main),
+               (int)rp->rows_per_main, buf->stats);
+  launch_pdl(elg::elg_reset_kernel, dim3((dims->num_envs + 127) / 128), 128, (cudaStream_t)stream, *rp, *prm, *buf, (int)dims->num_envs, (int)dims->num_dof,
+             (int)dims->num_feet, (int)dims->num_commands, (int)dims->num_obs, (int)dims->num_height_points);
   return elg::check_launch("elg_reset_envs");
 }
 

@@ -42,7 +42,15 @@ class ElgComm:
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
             _lib.check(lib.elg_comm_init(uid, self.rank, self.world, C.byref(handle)), "elg_comm_init")
-        self.handle = handle
+            self.handle = handle
+            # NCCL connects its peers lazily, at the first collective of each kind (allocations, IPC handles, proxy threads):
+            # that must not happen inside a CUDA-graph capture, so both collectives the path uses run once here, eagerly
+            warm = torch.zeros(8 * self.world, dtype=torch.float64, device=self.device)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _lib.check(lib.elg_episode_stats_allreduce(warm.data_ptr(), 8, handle, stream), "elg_episode_stats_allreduce (warm-up)")
+            if hasattr(lib, "elg_comm_warmup"):
+                _lib.check(lib.elg_comm_warmup(handle, warm.data_ptr(), 8, stream), "elg_comm_warmup")
+            torch.cuda.synchronize(self.device)
 
     def close(self):
         if getattr(self, "handle", None):
@@ -63,8 +71,10 @@ class ShardedEpisodeStats:
     rank at the same point, e.g. once per K steps -- is ONE all-reduce of that vector (+ two words for the terrain level)
     and returns the means ``extras['episode']`` would hold on a single GPU owning all envs, as device tensors."""
 
-    def __init__(self, device, comm=None, group=None):
-        self.device, self.comm, self.group = torch.device(device), comm, group
+    def __init__(self, device, comm=None, group=None, use_torch_distributed=False):
+        """comm: an ``ElgComm`` (NCCL on the compute stream); without one the totals stay local unless
+        ``use_torch_distributed`` routes the all-reduce through ``torch.distributed`` (``group``; the gloo CPU tests)."""
+        self.device, self.comm, self.group, self.use_dist = torch.device(device), comm, group, bool(use_torch_distributed)
         self.buf = torch.zeros(_lib.NUM_REWARD_TERMS + 1, dtype=torch.float64, device=device)
         self._send = torch.zeros(_lib.NUM_REWARD_TERMS + 3, dtype=torch.float64, device=device)
 
@@ -90,7 +100,7 @@ class ShardedEpisodeStats:
         if self.comm is not None and self.comm.world > 1:
             stream = torch.cuda.current_stream(self.device).cuda_stream
             _lib.check(_lib.load().elg_episode_stats_allreduce(v.data_ptr(), v.numel(), self.comm.handle, stream), "elg_episode_stats_allreduce")
-        elif dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
+        elif self.use_dist and dist.is_available() and dist.is_initialized() and dist.get_world_size(self.group) > 1:
             dist.all_reduce(v, op=dist.ReduceOp.SUM, group=self.group)         # gloo (CPU tests) / no ElgComm
         means = (v[:nt] / v[nt] / max_episode_length_s).to(torch.float)
         out = {"rew_" + name: means[_lib.TERM_ID[name]] for name in (names if names is not None else _lib.REWARD_TERMS)}

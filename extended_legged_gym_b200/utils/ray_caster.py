@@ -44,6 +44,10 @@ class Mesh:
         _lib.check(self._lib.elg_mesh_info(self.id, C.byref(nt), C.byref(nn), b))
         self.num_nodes = nn.value
         self.bounds = np.array(list(b), dtype=np.float32).reshape(2, 3)
+        # (layers, nx, ny) of the regular-grid accelerator a height-field-derived mesh gets on top of the BVH, else (0, 0, 0)
+        gl, gx, gy = C.c_int32(), C.c_int32(), C.c_int32()
+        _lib.check(self._lib.elg_mesh_grid_info(self.id, C.byref(gl), C.byref(gx), C.byref(gy)))
+        self.grid = (gl.value, gx.value, gy.value)
         # kept for callers that read the geometry back (wp.Mesh exposes .points / .indices)
         self.points = v
         self.indices = t.reshape(-1)

@@ -312,6 +312,12 @@ typedef struct ElgMesh ElgMesh;
 int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, ElgMesh** out);
 int elg_mesh_free(ElgMesh* mesh);
 int elg_mesh_info(const ElgMesh* mesh, int32_t* num_triangles, int32_t* num_nodes, float* bounds6);
+/* Height-field-derived meshes (vertices on a regular xy grid, one or more layers, two triangles per cell -- the terrain meshes of
+ * utils/terrain.py:76-80 and the two-layer confined terrain of utils/terrain_confine.py:13-146 without slope correction) also get a
+ * grid accelerator at creation: rays walk the cells front to back instead of the BVH and run the same exact triangle tests -- identical
+ * hit flags and distances.  elg_mesh_grid_info reports it (layers == 0: none); elg_set_mesh_tuning(1) forces the BVH walk (A/B, tests). */
+int elg_mesh_grid_info(const ElgMesh* mesh, int32_t* layers, int32_t* nx, int32_t* ny);
+int elg_set_mesh_tuning(int disable_grid);
 
 /* raycast_mesh + raycast_mesh_kernel (utils/ray_caster.py:45-167): closest hit with t in [0, max_dist) against both
  * face orientations; ray_hits = origin + t * direction, or the end point origin + max_dist * direction on a miss;
@@ -517,6 +523,7 @@ int elg_comm_unique_id(void* out128);
 int elg_comm_init(const void* unique_id128, int rank, int world, ElgComm** out);
 int elg_comm_destroy(ElgComm* comm);
 int elg_comm_info(const ElgComm* comm, int* rank, int* world, int* nccl_version);
+int elg_comm_warmup(ElgComm* comm, void* scratch /* >= 8 * world * n bytes */, int32_t n, void* stream);   /* first use of every collective kind, eagerly */
 int elg_episode_stats_allreduce(double* stats, int32_t n, ElgComm* comm, void* stream);
 int elg_mppi_update(const float* rewards /*[M,S_local,T]*/, const float* samples /*[M,S_local,traj_size]*/, int64_t num_main, int32_t samples_local,
                     int32_t horizon, int32_t traj_size, float temperature, float* costs_ranked, float* partial, float* mean_traj /*[M,traj_size]*/,

@@ -71,7 +71,7 @@ def _worker(rank, world, port, tag, q):
         lo, hi = shard_range(N, rank, world)
         resets_global = torch.tensor([1, 2, 7, 8, 9])
         mine = resets_global[(resets_global >= lo) & (resets_global < hi)] - lo
-        st = ShardedEpisodeStats("cpu")
+        st = ShardedEpisodeStats("cpu", use_torch_distributed=True)
         st.accumulate(full_sums[:, lo:hi].clone(), mine)
         out = st.reduce(20.0, terrain_levels=torch.arange(lo, hi), names=["torques", "dof_acc"])
         want_a = full_sums[_lib.TERM_ID["torques"]][resets_global].mean() / 20.0

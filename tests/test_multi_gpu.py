@@ -16,19 +16,30 @@ sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
+LOG_DIR = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+
+
 def _worker(rank, world, port, q):
+    os.makedirs(LOG_DIR, exist_ok=True)
+    log = open(os.path.join(LOG_DIR, f"multi_gpu_rank{rank}.log"), "w")
+
+    def say(msg):
+        log.write(msg + "\n")
+        log.flush()
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     torch.cuda.set_device(rank)
     dev = f"cuda:{rank}"
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device(dev))
+    say("process group up")
     try:
         import common
         from extended_legged_gym_b200 import _lib, synthetic
         from extended_legged_gym_b200.envs import LeggedRobot
         from extended_legged_gym_b200.sim_backend import SyntheticSim
         from extended_legged_gym_b200.utils.distributed import ElgComm, ShardedEpisodeStats, shard_range
-        from extended_legged_gym_b200.utils.mppi import mppi_update
+        from extended_legged_gym_b200.utils.mppi import mppi_update, mppi_update_native
         comm = ElgComm(dev)
+        say("ElgComm up")
         # ---- MPPI: same data on every rank (seeded), each takes its share of the samples
         g = torch.Generator().manual_seed(3)
         M, S, T, K, D = 16, 96, 20, 5, 12
@@ -36,8 +47,9 @@ def _worker(rank, world, port, q):
         u = torch.randn(M, S, K, D, generator=g).to(dev)
         lo, hi = shard_range(S, rank, world)
         got = mppi_update(r[:, lo:hi].contiguous(), u[:, lo:hi].contiguous(), 0.05, comm=comm)
-        full = mppi_update(r, u, 0.05)                      # single rank, no collective
+        full = mppi_update_native(r, u, 0.05, comm=None)    # single rank, no collective
         ok_mppi = torch.allclose(got, full, rtol=1e-4, atol=1e-5)
+        say(f"sharded mppi_update: {ok_mppi}")
         # inside a CUDA graph as well (collectives on the capture stream)
         s = torch.cuda.Stream(device=dev)
         gr = torch.cuda.CUDAGraph()
@@ -45,11 +57,12 @@ def _worker(rank, world, port, q):
         with torch.cuda.stream(s):
             mppi_update(rs, us, 0.05, comm=comm)
             s.synchronize()
-            with torch.cuda.graph(gr, stream=s):
+            with torch.cuda.graph(gr, stream=s, capture_error_mode="thread_local"):     # (NCCL's helper threads call CUDA too)
                 out_g = mppi_update(rs, us, 0.05, comm=comm)
             gr.replay()
             s.synchronize()
         ok_graph = torch.allclose(out_g, full, rtol=1e-4, atol=1e-5)
+        say(f"graph-captured sharded mppi_update: {ok_graph}")
         # ---- episode statistics: N envs in one object vs two shards, fused (in-kernel) reset path, same uniforms
         N, case = 512, "anymal_c_rough"
         cfg, spec, st = common.make_case_state(case, N, seed=4, adversarial=True)
@@ -84,10 +97,17 @@ def _worker(rank, world, port, q):
         ok_stats = int(want["num_resets"]) > 0 and int(got_s["num_resets"]) == int(want["num_resets"])
         for k, v in want.items():
             ok_stats = ok_stats and abs(float(got_s[k]) - float(v)) <= 1e-5 * abs(float(v)) + 1e-6
+        say(f"sharded episode statistics: {ok_stats}")
         q.put((rank, bool(ok_mppi), bool(ok_graph), bool(ok_stats)))
         comm.close()
+    except Exception as ex:  # noqa: BLE001
+        import traceback
+        say("FAILED: " + traceback.format_exc())
+        q.put((rank, False, False, False))
     finally:
-        dist.destroy_process_group()
+        say("leaving")
+        log.close()
+        os._exit(0)          # no collective tear-down: a rank that failed must not leave its peer waiting in destroy_process_group
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs")
@@ -95,12 +115,16 @@ def test_sharded_mppi_and_episode_stats_two_ranks_nccl():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
     port = 29000 + os.getpid() % 2000
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q), daemon=True) for r in range(2)]
     for p in procs:
         p.start()
-    res = [q.get(timeout=600) for _ in procs]
-    for p in procs:
-        p.join(timeout=60)
+    try:
+        res = [q.get(timeout=240) for _ in procs]
+    finally:
+        for p in procs:          # never leave a rank behind (a hung child would block the interpreter's exit)
+            p.join(timeout=10)
+            if p.is_alive():
+                p.kill()
     for rank, ok_mppi, ok_graph, ok_stats in res:
         assert ok_mppi, f"rank {rank}: sharded elg_mppi_update differs from the single-rank update"
         assert ok_graph, f"rank {rank}: graph-captured sharded update differs"

@@ -193,3 +193,62 @@ def test_raycast_large_terrain_properties():
     # brute force only against the triangles near each ray would need the BVH; use the full mesh on a small subset
     wh, wf, _, _ = mo.raycast_mesh(o[sel].cpu().numpy(), d[sel].cpu().numpy(), 5.0, v, t, chunk=8)
     assert wf.all() and np.allclose(hits[sel].cpu().numpy(), wh, rtol=RTOL, atol=ATOL)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["terrain", "terrain_offset", "confined_two_layer"])
+def test_grid_walk_is_bit_identical_to_the_bvh_walk(which):
+    """height-field-derived meshes take the regular-grid fast path: same hit flags, same distances, same triangle ids as the BVH
+    walk (elg_set_mesh_tuning(1)), and both equal the float64 brute force"""
+    from extended_legged_gym_b200 import _lib, synthetic
+    from extended_legged_gym_b200.utils.ray_caster import Mesh
+    lib = _lib.load()
+    if which == "confined_two_layer":
+        z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sensor_envs.npz"))
+        v, t = z["confined_a__vertices"], z["confined_a__triangles"]
+        layers = 2
+    else:
+        hf = synthetic.make_height_field(rows=90, cols=70, border=10, tile=25, seed=4)
+        v, t = synthetic.heightfield_to_trimesh(hf, 0.1, 0.005, 1.0 if which == "terrain" else -37.3)
+        layers = 1
+    mesh = Mesh(v, t, DEV)
+    assert mesh.grid[0] == layers, f"grid accelerator not detected: {mesh.grid}"
+    rng = np.random.default_rng(11)
+    lo, hi = v.min(0), v.max(0)
+    n = 6000
+    o = np.stack([rng.uniform(lo[0] - 0.5, hi[0] + 0.5, n), rng.uniform(lo[1] - 0.5, hi[1] + 0.5, n), rng.uniform(lo[2] - 0.2, hi[2] + 0.8, n)], axis=1).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32)
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    # special rays: straight down / up, along grid lines (x and y), exactly through vertices, horizontal, starting outside the grid
+    k = n // 6
+    d[:k] = [0, 0, -1]
+    d[k:k + 200] = [0, 0, 1]
+    xs, ys = np.unique(v[:, 0]), np.unique(v[:, 1])
+    o[k + 200:k + 400, 0] = rng.choice(xs, 200)              # on a grid line x = const ...
+    d[k + 200:k + 300] = [0, 1, 0]                           # ... travelling along it
+    d[k + 300:k + 400] = [0, 0, -1]                          # ... or dropping onto it
+    o[k + 400:k + 600, 0], o[k + 400:k + 600, 1] = rng.choice(xs, 200), rng.choice(ys, 200)      # exactly above vertices
+    d[k + 400:k + 600] = [0, 0, -1]
+    o[k + 600:k + 800, 1] = rng.choice(ys, 200)
+    d[k + 600:k + 800] = [1, 0, 0]
+    d[k + 800:k + 1000, 2] = 0.0
+    d[k + 800:k + 1000] /= np.linalg.norm(d[k + 800:k + 1000], axis=1, keepdims=True) + 1e-12
+    O, D = torch.from_numpy(o).to(DEV), torch.from_numpy(d.astype(np.float32)).to(DEV)
+    for max_dist in (0.7, 3.0, 25.0):
+        out = {}
+        for mode in (0, 1):
+            lib.elg_set_mesh_tuning(mode)
+            hits = torch.empty(n, 3, device=DEV)
+            found = torch.empty(n, dtype=torch.bool, device=DEV)
+            dist = torch.empty(n, device=DEV)
+            tri = torch.empty(n, dtype=torch.int32, device=DEV)
+            _lib.check(lib.elg_raycast(mesh.id, O.data_ptr(), D.data_ptr(), n, max_dist, hits.data_ptr(), found.data_ptr(), dist.data_ptr(),
+                                       tri.data_ptr(), None))
+            torch.cuda.synchronize()
+            out[mode] = (hits.cpu(), found.cpu(), dist.cpu(), tri.cpu())
+        lib.elg_set_mesh_tuning(0)
+        for a, b, name in zip(out[0], out[1], ("hits", "found", "distance", "triangle")):
+            assert torch.equal(a, b), f"{which} max_dist={max_dist}: grid walk and BVH walk differ in {name} ({int((a != b).sum())} entries)"
+        wh, wf, wd, wt = mo.raycast_mesh(o, d.astype(np.float32), max_dist, v, t)
+        assert np.array_equal(out[0][1].numpy(), wf) and np.array_equal(out[0][2].numpy(), wd)
+        assert 0.02 < wf.mean() < 0.99

@@ -93,6 +93,13 @@ def test_ragged_and_large_env_counts(n):
     run_pair("go2_all_terms_heading", n, seed=2, steps=1)
 
 
+@pytest.mark.parametrize("case", ["a1_rough", "go2_rough"])
+def test_step_parity_at_config3_size(case):
+    """BASELINE configs[2]: 65 536 envs -- the persistent, double-buffered many-chunk form of the lean kernel (2 341 chunks
+    over 148 CTAs), two steps so that the second one reads what the first one wrote"""
+    run_pair(case, 65536, seed=3, steps=2)
+
+
 def test_terrain_cells_bit_exact():
     n = 4096
     cfg, spec, st = common.make_case_state("anymal_c_rough", n, seed=5)
