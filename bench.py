@@ -519,26 +519,32 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
     slot = torch.empty(24, n_obs_rows, n_obs, device=dev)
     rw, dn = torch.randn(n_obs_rows, device=dev), torch.zeros(n_obs_rows, device=dev, dtype=torch.bool)
     rws, dns = torch.empty(24, n_obs_rows, 1, device=dev), torch.empty(24, n_obs_rows, 1, device=dev, dtype=torch.uint8)
-    with torch.cuda.stream(gs):
-        norm.forward_into(xo, slot[0], rw, rws[0], dn, dns[0])
-        gs.synchronize()
-        gn = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(gn, stream=gs):
-            for i in range(48):
-                norm.forward_into(xo, slot[i % 24], rw, rws[i % 24], dn, dns[i % 24])
-        gn.replay()
-        gs.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(gs)
-        for _ in range(4):
+    def time_norm():
+        with torch.cuda.stream(gs):
+            norm.forward_into(xo, slot[0], rw, rws[0], dn, dns[0])
+            gs.synchronize()
+            gn = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gn, stream=gs):
+                for i in range(48):
+                    norm.forward_into(xo, slot[i % 24], rw, rws[i % 24], dn, dns[i % 24])
             gn.replay()
-        e1.record(gs)
-        gs.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3 / 192
+            gs.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(gs)
+            for _ in range(4):
+                gn.replay()
+            e1.record(gs)
+            gs.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / 192
+    sec = time_norm()                      # default: ONE launch (rows stay in registers across a grid-wide hand-over)
+    lib.elg_set_normalizer_tuning(1)
+    sec2 = time_norm()                     # the statistics + apply pair that larger batches take
+    lib.elg_set_normalizer_tuning(0)
     nb = n_obs_rows * n_obs * 4 * 2
     out["obs_normalize_store"] = {"workload": f"{n_obs_rows} x {n_obs} observations: running mean / var update + normalise + write to the storage slot "
-                                              "(+ reward / done columns), 2 launches", "us_per_call": sec * 1e6, "bytes_per_call": nb,
+                                              "(+ reward / done columns), 1 launch", "us_per_call": sec * 1e6, "bytes_per_call": nb,
                                   "achieved_gbs": nb / sec / 1e9, "frac_of_hbm_peak": nb / sec / 1e9 / peak,
+                                  "us_per_call_two_launch_form": sec2 * 1e6,
                                   "note": "CUDA graph of 48 calls cycling over 24 storage slots (92 MB of destinations)"}
     # navigation commands and kinematic state integration over the 64 x (1 + 512) rows of config 5 (one launch each)
     from extended_legged_gym_b200.envs import KinematicStateIntegration
@@ -784,50 +790,83 @@ def main():
     env = envs[0]
     sim = env.sim
     host_in, host_in_kind = write_combined_host_block(sim.state_block.detach().cpu())   # root / dof / contact / rigid-body state + actions, one block
-    # outputs the caller reads back, re-pointed at ONE device block: obs [N, O] | rew [N] | reset flags [N] (bytes, padded)
+    # outputs the caller reads back, re-pointed at ONE device block: obs [N, O] | rew [N] | reset flags [N] (bytes, padded); two such
+    # blocks alternate, so that the kernels of step i + 1 need not wait for the copy-out of step i
     n_out_words = n_envs * O + n_envs + (n_envs + 3) // 4
-    out_block = torch.zeros(n_out_words, dtype=torch.float, device=dev)
-    env.obs_buf = out_block[:n_envs * O].view(n_envs, O)
-    env.rew_buf = out_block[n_envs * O:n_envs * O + n_envs]
-    env._reset_bool = out_block[n_envs * O + n_envs:].view(torch.uint8)[:n_envs].view(torch.bool)
+    out_blocks = [torch.zeros(n_out_words, dtype=torch.float, device=dev) for _ in range(2)]
+
+    def point_outputs_at(blk):
+        env.obs_buf = blk[:n_envs * O].view(n_envs, O)
+        env.rew_buf = blk[n_envs * O:n_envs * O + n_envs]
+        env._reset_bool = blk[n_envs * O + n_envs:].view(torch.uint8)[:n_envs].view(torch.bool)
+    point_outputs_at(out_blocks[0])
     # G consecutive steps form one CUDA graph; the copy-out of step i (second stream) overlaps the copy-in of step i + 1 (PCIe is
     # full duplex); the host launches the graph, waits and reads every step's result.
-    G = max(1, min(10, args.e2e_steps))
+    G = max(2, min(20, args.e2e_steps))
+    G -= G % 2                             # (the two staging / output blocks alternate: an even number of steps per graph)
     host_out = [torch.empty(n_out_words).pin_memory() for _ in range(G)]
     h2d = host_in.numel() * 4
     d2h = n_out_words * 4
     env.cfg.domain_rand.push_robots = False
     env._obs_clip_for_step = 100.0
-    s_cap, s_out = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+    s_cap, s_out, s_in = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     checksum = [0.0]
+    # The inbound block lands in one of two device staging blocks on its own stream, so that the copy-in of step i + 1 runs UNDER the
+    # kernels of step i (and next to the copy-out of step i: PCIe is full duplex); the compute stream moves the staged block into the
+    # simulator's state block with one device-to-device copy (5.26 MB, a few us) right before the step's kernels.
+    # (measured on B200, profiles/README.md r2: one copy engine moves this block at 52.7 GB/s alone and at 42.7 GB/s while the
+    #  copy-out runs; an SM-issued copy from mapped host memory -- elg_stage_block, scripts/stage_probe.py -- reaches 49.9 GB/s, no
+    #  better; 2 / 4 concurrent chunked copies on side streams are slower; write-combined host memory changes nothing at this size)
+    stage = [torch.empty_like(sim.state_block) for _ in range(2)]
+    stage_free = [None, None]      # event: the device-to-device copy out of this staging block has run
+    out_free = [None, None]        # event: the copy-out of this output block has run
 
-    # (measured on B200, profiles/README.md r2: splitting the inbound block into 2 / 4 concurrent copies on side streams is SLOWER --
-    #  0.182 / 0.206 ms per step against 0.159 ms for the single copy; write-combined host memory changes nothing at this size)
-    def one_step(slot, prev_out):
-        sim.state_block.copy_(host_in, non_blocking=True)
-        if prev_out is not None:
-            torch.cuda.current_stream().wait_event(prev_out)      # the previous results have left the output block
+    def one_step(slot):
+        cur = torch.cuda.current_stream()
+        b = slot & 1
+        landed = torch.cuda.Event()
+        with torch.cuda.stream(s_in):
+            if stage_free[b] is not None:
+                s_in.wait_event(stage_free[b])
+            stage[b].copy_(host_in, non_blocking=True)
+            landed.record(s_in)
+        cur.wait_event(landed)
+        sim.state_block.copy_(stage[b], non_blocking=True)
+        stage_free[b] = torch.cuda.Event()
+        stage_free[b].record(cur)
+        point_outputs_at(out_blocks[b])
+        if out_free[b] is not None:
+            cur.wait_event(out_free[b])       # the results of two steps ago have left this output block
         env.torques = env._compute_torques(env.actions).view(env.torques.shape)
         env.post_physics_step()
         done = torch.cuda.Event()
-        done.record(torch.cuda.current_stream())
+        done.record(cur)
         s_out.wait_event(done)
-        out = torch.cuda.Event()
+        out_free[b] = torch.cuda.Event()
         with torch.cuda.stream(s_out):
-            host_out[slot].copy_(out_block, non_blocking=True)
-            out.record(s_out)
-        return out
+            host_out[slot].copy_(out_blocks[b], non_blocking=True)
+            out_free[b].record(s_out)
+
+    def join_side_streams():
+        cur = torch.cuda.current_stream()
+        cur.wait_stream(s_out)
+        cur.wait_stream(s_in)
 
     with torch.cuda.stream(s_cap):
-        ev = one_step(0, None)                # eager once: everything lazily created exists before the capture
-        s_cap.wait_event(ev)
+        s_in.wait_stream(s_cap)
+        s_out.wait_stream(s_cap)
+        one_step(0)                           # eager, both output blocks once: everything lazily created exists before the capture
+        one_step(1)
+        join_side_streams()
     s_cap.synchronize()
+    stage_free, out_free = [None, None], [None, None]
     e2e_graph = torch.cuda.CUDAGraph()
     with torch.cuda.graph(e2e_graph, stream=s_cap):
-        ev = None
+        s_in.wait_stream(s_cap)                # fork the copy streams into the capture
+        s_out.wait_stream(s_cap)
         for slot in range(G):
-            ev = one_step(slot, ev)
-        torch.cuda.current_stream().wait_event(ev)     # join the copy-out stream
+            one_step(slot)
+        join_side_streams()
 
     def e2e_block():
         e2e_graph.replay()
@@ -873,8 +912,9 @@ def main():
                 "ms_per_step": t_e2e / e2e_steps * 1e3,
                 "api": "LeggedRobot._compute_torques + post_physics_step (in-kernel reset path included), simulator state in pinned host memory: "
                        f"every step ONE copy of the packed state + actions block ({host_in_kind} host memory) in and ONE copy of the packed obs / rew / reset block out; "
-                       f"{G} steps per CUDA graph, the copy-out of step i (second stream) overlaps the copy-in of step i + 1, the host waits "
-                       "for the graph and reads every step's result"},
+                       f"{G} steps per CUDA graph; the copy-in of step i + 1 (own stream, into one of two device staging blocks; one device-to-device "
+                       "copy hands it to the state block) runs under the kernels and the copy-out (third stream, two alternating output blocks) "
+                       "of step i; the host waits for the graph and reads every step's result"},
         "roofline": {"bound": "hbm", "kernel": "elg_step_fast_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": bytes_per_step, "bytes_per_env": rd + wr, "us_per_launch": t_kernel * 1e6,

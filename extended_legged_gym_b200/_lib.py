@@ -186,11 +186,13 @@ def load() -> C.CDLL:
     if hasattr(lib, "elg_probe_empty"):
         lib.elg_probe_empty.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, vp]
         lib.elg_probe_roundtrip.argtypes = [vp, vp, i64, i64, C.c_int, C.c_int, vp]
+    lib.elg_stage_block.argtypes = [vp, vp, i64, C.c_int, C.c_int, vp]
     lib.elg_set_clone_tuning.argtypes = [C.c_int]
     lib.elg_nav_commands.argtypes = [C.c_int32, C.c_int32, C.POINTER(ElgNavParams)] + [vp] * 7
     lib.elg_integrate_state_velocities.argtypes = [C.POINTER(ElgPlanParams), C.POINTER(ElgPlanBuffers), vp, vp, i64, vp]
     lib.elg_normalizer_scratch_bytes.restype = i64
     lib.elg_normalizer_scratch_bytes.argtypes = [i64, C.c_int32]
+    lib.elg_set_normalizer_tuning.argtypes = [C.c_int]
     lib.elg_normalize_observations.argtypes = [i64, C.c_int32] + [vp] * 5 + [C.c_float, i64, C.c_int32] + [vp] * 7
     if lib.elg_actuator_net_words() != ACTNET_WORDS:
         raise ElgError(f"ABI mismatch: elg_actuator_net_words() = {lib.elg_actuator_net_words()}, python mirror = {ACTNET_WORDS}")

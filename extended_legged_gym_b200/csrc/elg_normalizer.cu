@@ -4,7 +4,12 @@
 // (the rollout-storage slot, rsl_rl/storage/rollout_storage.py:95-100) together with the reward / done columns, so the
 // observations go from the step kernel's output to the policy's input buffer in one pass.
 //
-// Two launches, chained by programmatic dependent launch, bit-reproducible:
+// Batches whose rows fit the registers of ONE wave of CTAs (<= 32 rows per thread, <= one CTA per SM: 4096 x 235 and 65 536 x 48
+// both do) take elg_norm_fused_kernel: ONE launch in which every CTA keeps its rows in registers across a grid-wide hand-over --
+// per-CTA moments -> the last CTA to arrive merges them in block order, applies the update rule and publishes mean / (std + eps)
+// -> every CTA normalises the rows it still holds.  [N, O] is read ONCE (4 N O bytes in, 4 N O out) and the second launch with its
+// dependent-launch gap is gone.  Larger batches (and elg_set_normalizer_tuning(1)) take
+// two launches, chained by programmatic dependent launch, bit-reproducible:
 //   elg_norm_stats_kernel  (<= 32 row blocks) x (column tiles of 64): a thread owns one column of a few rows, forms their
 //                          (count, mean, M2) exactly in registers, the CTA tree-merges its row groups (Chan et al.) and
 //                          stores one triple per column; the LAST CTA of a column tile to finish (one atomic ticket -- it
@@ -192,6 +197,176 @@ elg_norm_apply_kernel(const __grid_constant__ NormGeom g, const float* __restric
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// single-launch form.  Header words (uint32, from byte 16; all zero between calls): [0] arrivals, [1] published flag, [2] consumers.
+// All CTAs of the grid must be resident together (they wait for each other): the host launches it only with <= one CTA per SM.
+// ---------------------------------------------------------------------------------------------------------------
+struct FusedGeom {
+  int64_t rows;
+  int cols;
+  int cslots;          // power of two >= cols (<= 1024): column slots of a CTA
+  int rows_per_cta;
+};
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// per-CTA moments of the single-launch form: doubles [cta][2][cols] (mean, M2) behind the four float vectors; the row count of a CTA
+// follows from the geometry.  Sums run in double and in a fixed order -- partial means of a few rows each would otherwise carry
+// half an ulp of the MEAN into every (mean_i - mean)^2, which is large against a small variance.
+__device__ __forceinline__ double* scr_dpart(void* s, int cols, int cta, int which) {
+  return reinterpret_cast<double*>(reinterpret_cast<char*>(s) + kNormHeader + (size_t)cols * 16) + ((size_t)cta * 2 + which) * cols;
+}
+
+template <int kC>      // rows a thread keeps in registers
+__global__ void __launch_bounds__(kNormThreads)
+elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var,
+                      float* __restrict__ stdv, int64_t* __restrict__ count, const float eps, const int64_t until, float* __restrict__ out,
+                      void* __restrict__ scratch, const float* __restrict__ rew, float* __restrict__ rew_out, const uint8_t* __restrict__ dones,
+                      uint8_t* __restrict__ dones_out) {
+  __shared__ double sd[kNormThreads];
+  __shared__ int s_last;
+  const int cpt = g.cslots, c = threadIdx.x & (cpt - 1), rs = threadIdx.x / cpt, rsub = kNormThreads / cpt;
+  const bool live = c < g.cols;
+  const int P = gridDim.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t old_count = *count;
+  const bool learn = !(until >= 0 && old_count >= until);          // (normalizer.py:62-63)
+  const int64_t r0 = (int64_t)blockIdx.x * g.rows_per_cta;
+  const int nrows = (int)max((int64_t)0, min((int64_t)g.rows_per_cta, g.rows - r0));
+  const float* xb = x + r0 * g.cols + c;
+  float v[kC];
+#pragma unroll
+  for (int k = 0; k < kC; ++k) {
+    const int r = rs + k * rsub;
+    v[k] = (live && r < nrows) ? xb[(uint32_t)(r * g.cols)] : 0.0f;
+  }
+  // reward / done columns of this CTA's rows ride along
+  for (int r = threadIdx.x; r < nrows; r += kNormThreads) {
+    if (rew_out) rew_out[r0 + r] = rew[r0 + r];
+    if (dones_out) dones_out[r0 + r] = dones[r0 + r];
+  }
+  // sum over the row groups of column slot c, in group order (every thread of the column forms the identical sum)
+  auto column_sum = [&](double mine) {
+    __syncthreads();
+    sd[threadIdx.x] = mine;
+    __syncthreads();
+    double t = 0.0;
+    for (int q = 0; q < rsub; ++q) t += sd[q * cpt + c];
+    return t;
+  };
+  float m_use, den;
+  if (learn) {
+    // CTA moments, two passes over the registers: mean first, then the squared deviations from it
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) s += (rs + k * rsub < nrows) ? (double)v[k] : 0.0;
+    const double m_cta = column_sum(s) / (double)nrows;
+    double q2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) { const double d = (double)v[k] - m_cta; q2 += (rs + k * rsub < nrows) ? d * d : 0.0; }
+    const double m2_cta = column_sum(q2);
+    if (rs == 0 && live) {
+      scr_dpart(scratch, g.cols, blockIdx.x, 0)[c] = m_cta;
+      scr_dpart(scratch, g.cols, blockIdx.x, 1)[c] = m2_cta;
+    }
+    unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + 16);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(words, 1u) == (unsigned)(P - 1);
+    __syncthreads();
+    if (s_last) {
+      // the last CTA to arrive: every pair is in L2.  Batch moments in block order -- independent loads, plain sums --, the update
+      // rule (normalizer.py:65-75), the state, and mean / std + eps for everybody
+      __threadfence();
+      auto rows_of = [&](int p) { return (double)min((int64_t)g.rows_per_cta, g.rows - (int64_t)p * g.rows_per_cta); };
+      double a = 0.0;
+      if (live) {
+#pragma unroll 8
+        for (int p = rs; p < P; p += rsub) a += rows_of(p) * __ldcg(scr_dpart(scratch, g.cols, p, 0) + c);
+      }
+      const double mean_x_d = column_sum(a) / (double)g.rows;
+      double b = 0.0;
+      if (live) {
+#pragma unroll 8
+        for (int p = rs; p < P; p += rsub) {
+          const double d = __ldcg(scr_dpart(scratch, g.cols, p, 0) + c) - mean_x_d;
+          b += __ldcg(scr_dpart(scratch, g.cols, p, 1) + c) + rows_of(p) * (d * d);
+        }
+      }
+      const double m2_x_d = column_sum(b);
+      if (rs == 0 && live) {
+        const int64_t new_count = old_count + g.rows;
+        const float rate = (float)g.rows / (float)new_count;
+        const float mean_x = (float)mean_x_d, var_x = (float)(m2_x_d / (double)g.rows);
+        const float m_old = mean[c], v_old = var[c];
+        const float delta = mean_x - m_old;
+        const float m_new = m_old + rate * delta;
+        const float v_new = v_old + rate * (var_x - v_old + delta * (mean_x - m_new));
+        const float s_new = __fsqrt_rn(v_new);
+        mean[c] = m_new; var[c] = v_new; stdv[c] = s_new;
+        if (c == 0) *count = new_count;
+        scr_vec(scratch, g.cols, 2)[c] = m_new;
+        scr_vec(scratch, g.cols, 3)[c] = s_new + eps;
+      }
+      __threadfence();
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        if (P > 1) st_release_u32(words + 1, 1u);
+        else words[0] = 0u;                                   // nobody waits: leave the header zeroed
+      }
+    } else {
+      if (threadIdx.x == 0) {
+        while (ld_acquire_u32(words + 1) == 0u) __nanosleep(20);
+        // the consumer that brings the count to P - 1 is the last reader of the flag: it zeroes the header for the next call
+        if (atomicAdd(words + 2, 1u) == (unsigned)(P - 2)) { words[0] = 0u; words[2] = 0u; st_release_u32(words + 1, 0u); }
+      }
+      __syncthreads();
+    }
+    m_use = live ? __ldcg(scr_vec(scratch, g.cols, 2) + c) : 0.0f;
+    den = live ? __ldcg(scr_vec(scratch, g.cols, 3) + c) : 1.0f;
+  } else {
+    m_use = live ? mean[c] : 0.0f;
+    den = live ? stdv[c] + eps : 1.0f;
+  }
+  if (live && out) {
+    float* ob = out + r0 * g.cols + c;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) {
+      const int r = rs + k * rsub;
+      if (r < nrows) ob[(uint32_t)(r * g.cols)] = (v[k] - m_use) / den;
+    }
+  }
+}
+
+// geometry of the single-launch form, or cslots == 0 when the batch does not fit one wave of register-resident rows
+static FusedGeom make_fused_geom(int64_t rows, int cols, int sms) {
+  FusedGeom g{};
+  g.rows = rows;
+  g.cols = cols;
+  if (cols > kNormThreads || sms < 1) return g;
+  int cs = 32;
+  while (cs < cols) cs <<= 1;
+  const int rsub = kNormThreads / cs;
+  int ctas = sms > kNormParts * 4 ? kNormParts * 4 : sms;      // parts of the scratch layout: make_geom reserves >= this many
+  // power-of-two CTA counts keep the per-thread row count a small power of two as well (4096 rows -> 128 CTAs x 32 rows)
+  int p2 = 1;
+  while (p2 * 2 <= ctas) p2 <<= 1;
+  int64_t rpc = (rows + p2 - 1) / p2;
+  if (rpc < rsub) rpc = rsub;
+  const int64_t per_thread = (rpc + rsub - 1) / rsub;
+  if (per_thread > 32) return g;
+  if (rpc * cols >= ((int64_t)1 << 31)) return g;
+  g.cslots = cs;
+  g.rows_per_cta = (int)rpc;
+  return g;
+}
+
 static NormGeom make_geom(int64_t rows, int cols) {
   NormGeom g{};
   g.rows = rows;
@@ -219,14 +394,26 @@ static void launch_pdl(void (*k)(Args...), dim3 grid, int threads, cudaStream_t 
   cudaLaunchKernelEx(&cfg, k, args...);
 }
 
+// 0: single launch when the batch fits one wave (default), 1: always the two-launch form (A/B runs, tests)
+int g_norm_mode = 0;
+
 }  // namespace elg
 
 extern "C" {
 
+int elg_set_normalizer_tuning(int mode) {
+  if (mode < 0 || mode > 1) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer tuning mode must be 0 or 1");
+  elg::g_norm_mode = mode;
+  return ELG_OK;
+}
+
 int64_t elg_normalizer_scratch_bytes(int64_t num_rows, int32_t num_cols) {
   if (num_rows < 0 || num_cols < 1) return 0;
   const elg::NormGeom g = elg::make_geom(num_rows > 0 ? num_rows : 1, num_cols);
-  return elg::kNormHeader + (int64_t)sizeof(float) * num_cols * (4 + 3 * (int64_t)g.parts);
+  // the single-launch form stores (mean, M2) as doubles for each of its <= 128 CTAs in the same region
+  int64_t part_bytes = (int64_t)12 * num_cols * g.parts;
+  if (part_bytes < (int64_t)16 * num_cols * 4 * elg::kNormParts) part_bytes = (int64_t)16 * num_cols * 4 * elg::kNormParts;
+  return elg::kNormHeader + (int64_t)16 * num_cols + part_bytes;
 }
 
 int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* x, float* mean, float* var, float* std, int64_t* count, float eps,
@@ -245,6 +432,21 @@ int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* 
   // 32-bit row offsets inside one row block / one apply block
   if ((int64_t)g.rows_per_part * num_cols >= ((int64_t)1 << 31)) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
+  if (training && elg::g_norm_mode == 0) {
+    const elg::FusedGeom fg = elg::make_fused_geom(num_rows, num_cols, elg::sm_count());
+    if (fg.cslots > 0) {
+      const int rsub = elg::kNormThreads / fg.cslots;
+      const int per_thread = (fg.rows_per_cta + rsub - 1) / rsub;
+      const dim3 grid((unsigned)((num_rows + fg.rows_per_cta - 1) / fg.rows_per_cta));
+      if (per_thread <= 8)
+        elg::launch_pdl(elg::elg_norm_fused_kernel<8>, grid, elg::kNormThreads, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+      else if (per_thread <= 16)
+        elg::launch_pdl(elg::elg_norm_fused_kernel<16>, grid, elg::kNormThreads, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+      else
+        elg::launch_pdl(elg::elg_norm_fused_kernel<32>, grid, elg::kNormThreads, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+      return elg::check_launch("elg_normalize_observations");
+    }
+  }
   if (training) {
     const dim3 grid((unsigned)g.parts, (unsigned)((num_cols + g.cpt_s - 1) / g.cpt_s));
     const int per_thread = (g.rows_per_part + (elg::kNormThreads / g.cpt_s) - 1) / (elg::kNormThreads / g.cpt_s);

@@ -54,6 +54,35 @@ __device__ __forceinline__ void resample_one(const ElgResetParams& rp, float* cm
   cmd[1] = mul_r(c1, keep);
 }
 
+// the same numbers, one column per lane: lane c holds column c of the env's uniform row (and column c + 32 when the row is longer),
+// a warp-uniform column index fetches its value with one shuffle -- one Philox evaluation per lane instead of one per access
+struct LaneUniforms { float lo, hi; };
+__device__ __forceinline__ float uniform_col(const float* table, uint64_t seed, uint64_t offset, uint32_t env, int c) {
+  if (table) return table[(size_t)env * ELG_RESET_UNIFORMS + c];
+  const uint4 blk = philox4x32_10(make_uint4(env, (uint32_t)(c >> 2), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                  make_uint2((uint32_t)seed ^ kResetStream, (uint32_t)(seed >> 32)));
+  const int w = c & 3;
+  return u01(w == 0 ? blk.x : w == 1 ? blk.y : w == 2 ? blk.z : blk.w);
+}
+__device__ __forceinline__ LaneUniforms lane_uniforms(const float* table, uint64_t seed, uint64_t offset, uint32_t env, int lane, int ncols) {
+  LaneUniforms u{0.0f, 0.0f};
+  if (lane < ncols) u.lo = uniform_col(table, seed, offset, env, lane);
+  if (lane + 32 < ncols) u.hi = uniform_col(table, seed, offset, env, lane + 32);
+  return u;
+}
+__device__ __forceinline__ float uget(const LaneUniforms& u, int c) {   // c: warp-uniform, all lanes call
+  return c < 32 ? __shfl_sync(0xffffffffu, u.lo, c) : __shfl_sync(0xffffffffu, u.hi, c - 32);
+}
+// _resample_commands (:405-423) on values: (u_x, u_y, u_third) -> cmd0, cmd1 after the small-command zeroing, heading or yaw rate
+__device__ __forceinline__ void resample_vals(const ElgResetParams& rp, float ux, float uy, float ut, float& cmd0, float& cmd1, float& third) {
+  const float c0 = rand_range(rp.lin_vel_x[0], rp.lin_vel_x[1], ux);
+  const float c1 = rand_range(rp.lin_vel_y[0], rp.lin_vel_y[1], uy);
+  third = rp.heading_command ? rand_range(rp.heading[0], rp.heading[1], ut) : rand_range(rp.ang_vel_yaw[0], rp.ang_vel_yaw[1], ut);
+  const float keep = norm2_t(c0, c1) > 0.2f ? 1.0f : 0.0f;
+  cmd0 = mul_r(c0, keep);
+  cmd1 = mul_r(c1, keep);
+}
+
 __global__ void __launch_bounds__(128)
 elg_resample_kernel(const __grid_constant__ ElgResetParams rp, const int N, const int D, const int C, const int64_t* __restrict__ ep_len,
                     float* __restrict__ commands, const float* __restrict__ uniforms, float* __restrict__ stats_to_zero) {
@@ -102,7 +131,6 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
   const bool self_reset = rb.reset_buf[e] != 0;
   const bool main_reset = is_main ? self_reset : rb.reset_buf[m] != 0;
   if (!self_reset && !main_reset) return;
-  Uniforms U{rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)e, make_uint4(0, 0, 0, 0), -1};
   float* rs = rb.root_states + (size_t)e * 13;
   float* cmd = rb.commands + (size_t)e * C;
   float* org = rb.env_origins + (size_t)e * 3;
@@ -131,50 +159,90 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
     }
     return;
   }
+  // Everything scalar about the env is computed by ALL lanes from broadcast loads and warp-shuffled random numbers (column c of the
+  // env's uniform row lives in lane c), in registers: the loads go out together, nothing is read back from global memory, and lane 0
+  // stores the results at the end.  (The first form did the scalar work in lane 0 with read-modify-write chains through global
+  // memory -- some twenty dependent round trips: 24.7 us per launch at 65 536 envs whatever the number of resets.)
   const bool zero_sums = R1 <= 0 || rb.stats[ELG_NUM_REWARD_TERMS + 1] != 0.0f;
+  const LaneUniforms U = lane_uniforms(rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)e, lane, D + 12);
+  float o0 = org[0], o1 = org[1], o2 = org[2];
+  float cm0 = cmd[0], cm1 = cmd[1], cm2 = C > 2 ? cmd[2] : 0.0f;
+  // ---- _update_terrain_curriculum (:498-518): old root position, old commands
+  long long lv = 0;
+  const bool curr = rp.curriculum && is_main;
+  if (curr) {
+    const float r0 = rs[0], r1 = rs[1];
+    const long long lv0 = rb.terrain_levels[e], ty = rb.terrain_types[e];
+    const float dist = norm2_t(sub_r(r0, o0), sub_r(r1, o1));
+    const bool up = dist > rp.env_length_half;
+    const bool down = (dist < mul_r(mul_r(norm2_t(cm0, cm1), rp.max_episode_length_s), 0.5f)) && !up;
+    lv = lv0 + (up ? 1 : 0) - (down ? 1 : 0);
+    if (lv >= rp.max_terrain_level) {
+      lv = (long long)(uget(U, D + 11) * (float)rp.max_terrain_level);
+      if (lv >= rp.max_terrain_level) lv = rp.max_terrain_level - 1;
+    } else if (lv < 0) {
+      lv = 0;
+    }
+    const float* to = rb.terrain_origins + ((size_t)lv * rp.terrain_cols + ty) * 3;
+    o0 = to[0]; o1 = to[1]; o2 = to[2];
+  }
+  // ---- _reset_root_states (:467-487)
+  float r[13];
+#pragma unroll
+  for (int k = 0; k < 13; ++k) r[k] = rp.base_init_state[k];
+  r[0] = add_r(r[0], o0); r[1] = add_r(r[1], o1); r[2] = add_r(r[2], o2);
+  if (rp.custom_origins) {
+    r[0] = add_r(r[0], rand_range(-0.5f, 0.5f, uget(U, D)));
+    r[1] = add_r(r[1], rand_range(-0.5f, 0.5f, uget(U, D + 1)));
+    if (rp.root_z_from_terrain) {   // (robot_batch_rollout.py:1379-1392): .long() truncation, clip to [0, dim - 2], one cell
+      const long long cx = (long long)div_r(add_r(r[0], pr.border_size), pr.horizontal_scale);
+      const long long cy = (long long)div_r(add_r(r[1], pr.border_size), pr.horizontal_scale);
+      const long long px = cx < 0 ? 0 : (cx > pr.hf_rows - 2 ? pr.hf_rows - 2 : cx);
+      const long long py = cy < 0 ? 0 : (cy > pr.hf_cols - 2 ? pr.hf_cols - 2 : cy);
+      r[2] = add_r(mul_r((float)rb.height_samples[px * pr.hf_cols + py], pr.vertical_scale), rp.base_init_state[2]);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) r[7 + k] = rand_range(-0.5f, 0.5f, uget(U, D + 2 + k));
+  // ---- _resample_commands: main envs draw, rollout rows take their main's draw when it resets too
+  const int keep = rp.heading_command ? 2 : 3;
+  bool new_cmd = false, copy_keep = false;
+  float keep_val = 0.0f, third = 0.0f;
+  if (is_main) {
+    resample_vals(rp, uget(U, D + 8), uget(U, D + 9), uget(U, D + 10), cm0, cm1, third);
+    new_cmd = true;
+  } else if (main_reset) {
+    const LaneUniforms Um = lane_uniforms(rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)m, lane, D + 12);
+    if (keep < C) { keep_val = rb.commands[(size_t)m * C + keep]; copy_keep = true; }
+    resample_vals(rp, uget(Um, D + 8), uget(Um, D + 9), uget(Um, D + 10), cm0, cm1, third);
+    new_cmd = true;
+  }
+  if (copy_keep && keep == 2) cm2 = keep_val;
+  if (new_cmd && !rp.heading_command) cm2 = third;
+  // ---- _reset_dofs (:450-465); last_dof_vel = new dof_vel (= 0) after the history copy (:149); last_actions already
+  // holds `actions` (zeroed by reset_idx, then overwritten by the history copy :148).  D <= 32: dof j is lane j's.
+  float newpos = 0.0f;
+  if (lane < D) newpos = mul_r(rb.default_dof_pos[lane], rand_range(0.5f, 1.5f, U.lo));
+  __syncwarp();   // every lane has read the old state: lane 0 may overwrite it
+  if (lane < D) {
+    ds[2 * lane] = newpos;
+    ds[2 * lane + 1] = 0.0f;
+    rb.last_dof_vel[(size_t)e * D + lane] = 0.0f;
+  }
   if (lane == 0) {
-    // ---- _update_terrain_curriculum (:498-518): old root position, old commands
-    if (rp.curriculum && is_main) {
-      const float dist = norm2_t(sub_r(rs[0], org[0]), sub_r(rs[1], org[1]));
-      const bool up = dist > rp.env_length_half;
-      const bool down = (dist < mul_r(mul_r(norm2_t(cmd[0], cmd[1]), rp.max_episode_length_s), 0.5f)) && !up;
-      long long lv = rb.terrain_levels[e] + (up ? 1 : 0) - (down ? 1 : 0);
-      if (lv >= rp.max_terrain_level) {
-        lv = (long long)(U.get(D + 11) * (float)rp.max_terrain_level);
-        if (lv >= rp.max_terrain_level) lv = rp.max_terrain_level - 1;
-      } else if (lv < 0) {
-        lv = 0;
-      }
+    if (curr) {
       rb.terrain_levels[e] = lv;
-      const float* to = rb.terrain_origins + ((size_t)lv * rp.terrain_cols + rb.terrain_types[e]) * 3;
-      org[0] = to[0]; org[1] = to[1]; org[2] = to[2];
+      org[0] = o0; org[1] = o1; org[2] = o2;
     }
-    // ---- _reset_root_states (:467-487)
-    for (int k = 0; k < 13; ++k) rs[k] = rp.base_init_state[k];
-    rs[0] = add_r(rs[0], org[0]); rs[1] = add_r(rs[1], org[1]); rs[2] = add_r(rs[2], org[2]);
-    if (rp.custom_origins) {
-      rs[0] = add_r(rs[0], rand_range(-0.5f, 0.5f, U.get(D)));
-      rs[1] = add_r(rs[1], rand_range(-0.5f, 0.5f, U.get(D + 1)));
-      if (rp.root_z_from_terrain) {   // (robot_batch_rollout.py:1379-1392): .long() truncation, clip to [0, dim - 2], one cell
-        const long long cx = (long long)div_r(add_r(rs[0], pr.border_size), pr.horizontal_scale);
-        const long long cy = (long long)div_r(add_r(rs[1], pr.border_size), pr.horizontal_scale);
-        const long long px = cx < 0 ? 0 : (cx > pr.hf_rows - 2 ? pr.hf_rows - 2 : cx);
-        const long long py = cy < 0 ? 0 : (cy > pr.hf_cols - 2 ? pr.hf_cols - 2 : cy);
-        rs[2] = add_r(mul_r((float)rb.height_samples[px * pr.hf_cols + py], pr.vertical_scale), rp.base_init_state[2]);
-      }
-    }
-    for (int k = 0; k < 6; ++k) {
-      rs[7 + k] = rand_range(-0.5f, 0.5f, U.get(D + 2 + k));
-      rb.last_root_vel[(size_t)e * 6 + k] = rs[7 + k];              // the history copy after the reset (:150)
-    }
-    // ---- _resample_commands: main envs draw, rollout rows take their main's draw when it resets too
-    if (is_main) {
-      resample_one(rp, cmd, U, D);
-    } else if (main_reset) {
-      Uniforms Um{rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)m, make_uint4(0, 0, 0, 0), -1};
-      const int keep = rp.heading_command ? 2 : 3;
-      if (keep < C) cmd[keep] = rb.commands[(size_t)m * C + keep];
-      resample_one(rp, cmd, Um, D);
+#pragma unroll
+    for (int k = 0; k < 13; ++k) rs[k] = r[k];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rb.last_root_vel[(size_t)e * 6 + k] = r[7 + k];              // the history copy after the reset (:150)
+    if (copy_keep) cmd[keep] = keep_val;
+    if (new_cmd) {
+      cmd[0] = cm0; cmd[1] = cm1;
+      if (rp.heading_command) cmd[3] = third;
+      else cmd[2] = third;
     }
     // ---- timers, episode clock (:191-198)
     for (int f = 0; f < F; ++f) {
@@ -187,13 +255,6 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
       if (rb.stats_accum) atomicAdd(rb.stats_accum + ELG_NUM_REWARD_TERMS, 1.0);
     }
   }
-  // ---- _reset_dofs (:450-465); last_dof_vel = new dof_vel (= 0) after the history copy (:149); last_actions already
-  // holds `actions` (zeroed by reset_idx, then overwritten by the history copy :148)
-  for (int j = lane; j < D; j += 32) {
-    ds[2 * j] = mul_r(rb.default_dof_pos[j], rand_range(0.5f, 1.5f, U.get(j)));
-    ds[2 * j + 1] = 0.0f;
-    rb.last_dof_vel[(size_t)e * D + j] = 0.0f;
-  }
   // ---- extras["episode"] (:200-206): (sum, count) over the reset envs, then zero the sums
   for (int t = lane; t < ELG_NUM_REWARD_TERMS; t += 32)
     if ((pr.reward_mask >> t) & 1u) {
@@ -204,7 +265,6 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
       }
       if (zero_sums) *sp = 0.0f;
     }
-  __syncwarp();
   // ---- observation repair (:234-252 evaluated after the reset)
   if (rb.obs_buf) {
     const int head = 12 + 3 * D;
@@ -223,22 +283,23 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
       return (float)((w >> (16 * (sidx & 1))) & 0xffffu);
     };
     // head entries k = lane + 32 m: sample (nj % 8) + m of block 1 + nj / 8 when shared, else sample m % 8 of block m / 8
-    for (int m = 0; m < hm; ++m) {
-      const int k = lane + 32 * m;
+    for (int mm = 0; mm < hm; ++mm) {
+      const int k = lane + 32 * mm;
+      const float pos_k = __shfl_sync(0xffffffffu, newpos, (k - 12) & 31);      // the new position of dof k - 12 (lane k - 12 drew it)
       float v;
       bool touch = false;
-      if (k >= 9 && k < 12) { v = cmd[k - 9] * pr.commands_scale[k - 9]; touch = true; }
-      else if (k >= 12 && k < 12 + D) { v = (ds[2 * (k - 12)] - rb.default_dof_pos[k - 12]) * pr.obs_scale_dof_pos; touch = true; }
+      if (k >= 9 && k < 12) { v = (k == 9 ? cm0 : k == 10 ? cm1 : cm2) * pr.commands_scale[k - 9]; touch = true; }
+      else if (k >= 12 && k < 12 + D) { v = (pos_k - rb.default_dof_pos[k - 12]) * pr.obs_scale_dof_pos; touch = true; }
       else if (k >= 12 + D && k < 12 + 2 * D) { v = 0.0f * pr.obs_scale_dof_vel; touch = true; }
       if (touch) {
         float s16 = 0.0f;
-        if (philox) s16 = sample(noise_block(pr.noise_seed, pr.noise_offset, e, lane, share ? 1 + (nj >> 3) : (m >> 3)), share ? (nj & 7) + m : (m & 7));
+        if (philox) s16 = sample(noise_block(pr.noise_seed, pr.noise_offset, e, lane, share ? 1 + (nj >> 3) : (mm >> 3)), share ? (nj & 7) + mm : (mm & 7));
         finish(k, v, s16);
       }
     }
     // height entries: clip(z - 0.5 - h, -1, 1) * scale with the NEW base height and the stale heights
     if (H > 0 && rb.measured_heights) {
-      const float zc = sub_r(rs[2], 0.5f);
+      const float zc = sub_r(r[2], 0.5f);
       uint4 blk = make_uint4(0, 0, 0, 0);
       for (int j = 0; j < nj; ++j) {
         if (philox && (j & 7) == 0) blk = noise_block(pr.noise_seed, pr.noise_offset, e, lane, 1 + (j >> 3));
@@ -318,6 +379,7 @@ int elg_resample_commands(const ElgDims* dims, const ElgResetParams* rp, const i
 int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepParams* prm, const ElgResetBuffers* buf, void* stream) {
   if (!dims || !rp || !prm || !buf) return rfail(ELG_ERR_NULL_POINTER, "dims/params/buffers is NULL");
   if (dims->num_dof + 12 > ELG_RESET_UNIFORMS) return rfail(ELG_ERR_UNSUPPORTED, "num_dof + 12 exceeds ELG_RESET_UNIFORMS");
+  if (dims->num_dof > 32) return rfail(ELG_ERR_UNSUPPORTED, "elg_reset_envs: more than 32 dofs (one lane per joint)");
   if (dims->num_envs == 0) return ELG_OK;
   if (!buf->reset_buf || !buf->root_states || !buf->dof_state || !buf->commands || !buf->env_origins || !buf->default_dof_pos ||
       !buf->last_dof_vel || !buf->last_root_vel || !buf->feet_air_time || !buf->feet_contact_time || !buf->episode_length_buf ||

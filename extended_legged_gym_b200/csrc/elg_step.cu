@@ -874,6 +874,47 @@ elg_torques_kernel(const int64_t n_rows, const int D, const int control_type, co
   torques[e] = fminf(fmaxf(tq, -lim), lim);
 }
 
+// the same arithmetic, four consecutive (env, dof) values per thread with 16-byte accesses (all envs, D % 4 == 0, 16-byte aligned
+// arrays, < 2^31 values): one 32-bit remainder per thread instead of a 64-bit division per value
+__global__ void __launch_bounds__(256)
+elg_torques4_kernel(const uint32_t n4, const uint32_t D, const int control_type, const float action_scale, const float sim_dt,
+                    const float4* __restrict__ actions, const float4* __restrict__ dof_state, const float4* __restrict__ last_dof_vel,
+                    const float* __restrict__ p_gains, const float* __restrict__ d_gains, const float* __restrict__ torque_limits,
+                    const float* __restrict__ default_dof_pos, float4* __restrict__ torques) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  pdl_launch_dependents();
+  pdl_wait();
+  if (i >= n4) return;
+  const uint32_t j = (4u * i) % D;
+  const float4 a4 = actions[i];
+  const float4 lim4 = __ldg(reinterpret_cast<const float4*>(torque_limits + j));
+  const float a[4] = {mul_r(a4.x, action_scale), mul_r(a4.y, action_scale), mul_r(a4.z, action_scale), mul_r(a4.w, action_scale)};
+  const float lim[4] = {lim4.x, lim4.y, lim4.z, lim4.w};
+  float tq[4];
+  if (control_type == ELG_CONTROL_T) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k) tq[k] = a[k];
+  } else {
+    const float4 s0 = dof_state[2 * i], s1 = dof_state[2 * i + 1];
+    const float pos[4] = {s0.x, s0.z, s1.x, s1.z}, vel[4] = {s0.y, s0.w, s1.y, s1.w};
+    const float4 pg4 = __ldg(reinterpret_cast<const float4*>(p_gains + j)), dg4 = __ldg(reinterpret_cast<const float4*>(d_gains + j));
+    const float pg[4] = {pg4.x, pg4.y, pg4.z, pg4.w}, dg[4] = {dg4.x, dg4.y, dg4.z, dg4.w};
+    if (control_type == ELG_CONTROL_P) {
+      const float4 q4 = __ldg(reinterpret_cast<const float4*>(default_dof_pos + j));
+      const float q0[4] = {q4.x, q4.y, q4.z, q4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tq[k] = sub_r(mul_r(pg[k], sub_r(add_r(a[k], q0[k]), pos[k])), mul_r(dg[k], vel[k]));
+    } else {
+      const float4 l4 = last_dof_vel[i];
+      const float lv[4] = {l4.x, l4.y, l4.z, l4.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) tq[k] = sub_r(mul_r(pg[k], sub_r(a[k], vel[k])), div_r(mul_r(dg[k], sub_r(vel[k], lv[k])), sim_dt));
+    }
+  }
+  torques[i] = make_float4(fminf(fmaxf(tq[0], -lim[0]), lim[0]), fminf(fmaxf(tq[1], -lim[1]), lim[1]), fminf(fmaxf(tq[2], -lim[2]), lim[2]),
+                           fminf(fmaxf(tq[3], -lim[3]), lim[3]));
+}
+
 // ---------------------------------------------------------------------------------------------
 // step_rollout's action hand-over (robot_batch_rollout.py:643-656; robot_traj_grad_sampling.py:326-345): one thread per value
 // ---------------------------------------------------------------------------------------------
@@ -1024,6 +1065,18 @@ int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const flo
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
+  auto a16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  const bool pv = prm->control_type != ELG_CONTROL_T;
+  if (!env_ids && dims->num_dof % 4 == 0 && total < ((int64_t)1 << 31) && a16(actions) && a16(torques) && a16(torque_limits) &&
+      (!pv || (a16(dof_state) && a16(p_gains) && a16(d_gains) && a16(default_dof_pos))) &&
+      (prm->control_type != ELG_CONTROL_V || a16(last_dof_vel))) {
+    const uint32_t n4 = (uint32_t)(total / 4);
+    cfg.gridDim = dim3((n4 + threads - 1) / threads);
+    cudaLaunchKernelEx(&cfg, elg::elg_torques4_kernel, n4, (uint32_t)dims->num_dof, (int)prm->control_type, prm->action_scale, prm->sim_dt,
+                       reinterpret_cast<const float4*>(actions), reinterpret_cast<const float4*>(dof_state), reinterpret_cast<const float4*>(last_dof_vel),
+                       p_gains, d_gains, torque_limits, default_dof_pos, reinterpret_cast<float4*>(torques));
+    return check_launch("elg_compute_torques");
+  }
   cudaLaunchKernelEx(&cfg, elg::elg_torques_kernel, rows, (int)dims->num_dof, (int)prm->control_type, prm->action_scale, prm->sim_dt,
                      actions, dof_state, last_dof_vel, p_gains, d_gains, torque_limits, default_dof_pos, torques, env_ids);
   return check_launch("elg_compute_torques");

@@ -265,6 +265,12 @@ int elg_set_step_debug(long long* device_stamps);
 int elg_probe_empty(int grid, int threads, int smem_bytes, int pdl, void* stream);
 int elg_probe_roundtrip(const void* src, void* dst, int64_t bytes_in_per_cta, int64_t bytes_out_per_cta, int grid, int pdl, void* stream);
 
+/* SM-issued block copy between pinned (mapped) host memory and device memory (csrc/elg_stage.cu; no reference counterpart: the
+ * reference's tensors live where PhysX puts them).  The end-to-end step uses it for its ONE packed host->device transfer: thousands of
+ * PCIe reads outstanding at once instead of one copy engine's request window.  dst / src / bytes: multiples of 16.  mode 0: 16-byte
+ * load / store kernel; mode 1: TMA bulk pieces through shared memory.  grid <= 0: default. */
+int elg_stage_block(void* dst, const void* src, int64_t bytes, int mode, int grid, void* stream);
+
 /* LeggedRobot._get_heights (envs/base/legged_robot.py:900-938), standalone. cells_out (optional,
  * int32 [N,H,2]) receives the clipped (px, py) terrain cell of every point for index parity tests. */
 int elg_get_heights(const ElgDims* dims, const ElgStepParams* prm, const float* root_states, const int16_t* height_samples,
@@ -315,9 +321,10 @@ int elg_mesh_info(const ElgMesh* mesh, int32_t* num_triangles, int32_t* num_node
 /* Height-field-derived meshes (vertices on a regular xy grid, one or more layers, two triangles per cell -- the terrain meshes of
  * utils/terrain.py:76-80 and the two-layer confined terrain of utils/terrain_confine.py:13-146 without slope correction) also get a
  * grid accelerator at creation: rays walk the cells front to back instead of the BVH and run the same exact triangle tests -- identical
- * hit flags and distances.  elg_mesh_grid_info reports it (layers == 0: none); elg_set_mesh_tuning(1) forces the BVH walk (A/B, tests). */
+ * hit flags, distances and triangle ids.  Measured slower than the 4-wide BVH on B200 (it cannot skip empty air), so it is opt-in:
+ * elg_set_mesh_tuning(1) selects it (A/B runs, tests), 0 (default) the BVH.  elg_mesh_grid_info reports it (layers == 0: none). */
 int elg_mesh_grid_info(const ElgMesh* mesh, int32_t* layers, int32_t* nx, int32_t* ny);
-int elg_set_mesh_tuning(int disable_grid);
+int elg_set_mesh_tuning(int use_grid);
 
 /* raycast_mesh + raycast_mesh_kernel (utils/ray_caster.py:45-167): closest hit with t in [0, max_dist) against both
  * face orientations; ray_hits = origin + t * direction, or the end point origin + max_dist * direction on a miss;
@@ -457,6 +464,7 @@ int elg_integrate_state_velocities(const ElgPlanParams* prm, const ElgPlanBuffer
  * first use -- its header holds the completion tickets, which every call leaves at zero again) is only needed when
  * training.  At most 1920 columns.  out may alias x; out == NULL updates the statistics only (EmpiricalNormalization.update). */
 int64_t elg_normalizer_scratch_bytes(int64_t num_rows, int32_t num_cols);
+int elg_set_normalizer_tuning(int mode);   /* 0: single launch when the batch fits one wave of CTAs (default); 1: always two launches (A/B, tests) */
 int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* x, float* mean, float* var, float* std, int64_t* count, float eps,
                                int64_t until, int32_t training, float* out, void* scratch, const float* rew /*[N] or NULL*/,
                                float* rew_out, const uint8_t* dones /*[N] or NULL*/, uint8_t* dones_out, void* stream);

@@ -65,8 +65,9 @@ def test_oracle_matches_live_reference_module():
 
 def test_normalizer_abi_argument_checks():
     lib = _lib.load()
-    assert lib.elg_normalizer_scratch_bytes(4096, 235) == 256 + 4 * 235 * (4 + 3 * 32)
-    assert lib.elg_normalizer_scratch_bytes(100, 48) == 256 + 4 * 48 * (4 + 3 * 4)
+    assert lib.elg_normalizer_scratch_bytes(4096, 235) == 256 + 16 * 235 + 16 * 235 * 128      # (mean, M2) doubles per CTA of the single-launch form
+    assert lib.elg_normalizer_scratch_bytes(100, 48) == 256 + 16 * 48 + 16 * 48 * 128
+    assert lib.elg_normalizer_scratch_bytes(10_000_000, 48) > 256 + 4 * 48 * (4 + 3 * 31)
     call = lib.elg_normalize_observations
     assert call(8, 0, 16, 16, 16, 16, 16, 0.01, -1, 1, 16, 16, None, None, None, None, None) == -1
     assert call(8, 4, None, 16, 16, 16, 16, 0.01, -1, 1, 16, 16, None, None, None, None, None) == -4
@@ -98,9 +99,19 @@ def test_kernel_matches_reference_fixture(tag):
         assert_out(y, torch.from_numpy(z[f"{tag}__s{s}__out"]), m._std, m._mean)
 
 
+@pytest.fixture(params=[0, 1], ids=["single_launch", "two_launches"])
+def launch_form(request):
+    """both forms of the training-mode call: one launch with a grid-wide hand-over (default, batches that fit one wave of CTAs)
+    and the statistics + apply pair (larger batches; forced here with elg_set_normalizer_tuning(1))"""
+    lib = _lib.load()
+    lib.elg_set_normalizer_tuning(request.param)
+    yield request.param
+    lib.elg_set_normalizer_tuning(0)
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,o", [(4096, 235), (65536, 48), (4099, 235), (31, 300), (1, 7)])
-def test_kernel_matches_oracle_full_size_and_storage_slot(n, o):
+@pytest.mark.parametrize("n,o", [(4096, 235), (65536, 48), (4099, 235), (31, 300), (1, 7), (32832, 235), (16384, 235), (300, 1024)])
+def test_kernel_matches_oracle_full_size_and_storage_slot(n, o, launch_form):
     m = make_module(o, until=int(1e8))
     m.train()
     st = no.new_state(o)
@@ -133,7 +144,7 @@ def test_kernel_matches_oracle_full_size_and_storage_slot(n, o):
 
 
 @pytest.mark.gpu
-def test_update_only_until_and_reproducibility():
+def test_update_only_until_and_reproducibility(launch_form):
     n, o = 4096, 235
     xs = [x.to(DEV) for x in no.batches(2, n, o, 3)]
     runs = []

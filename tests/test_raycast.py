@@ -198,8 +198,8 @@ def test_raycast_large_terrain_properties():
 @pytest.mark.gpu
 @pytest.mark.parametrize("which", ["terrain", "terrain_offset", "confined_two_layer"])
 def test_grid_walk_is_bit_identical_to_the_bvh_walk(which):
-    """height-field-derived meshes take the regular-grid fast path: same hit flags, same distances, same triangle ids as the BVH
-    walk (elg_set_mesh_tuning(1)), and both equal the float64 brute force"""
+    """height-field-derived meshes carry a regular-grid accelerator (opt-in, elg_set_mesh_tuning(1): measured slower than the BVH):
+    same hit flags, same distances, same triangle ids as the default BVH walk, and both equal the float64 brute force"""
     from extended_legged_gym_b200 import _lib, synthetic
     from extended_legged_gym_b200.utils.ray_caster import Mesh
     lib = _lib.load()

@@ -242,7 +242,7 @@ def test_legged_robot_depth_owns_a_camera_with_update_interval():
     ref.update(env.dt, env.root_states[:, :3], env.root_states[:, 3:7])
     ref.update_depth_buffer(None, env.episode_length_buf)
     assert torch.equal(first, ref.depth_buffer)
-    assert first.shape == (n, 2, 28, 56) and float(first.abs().max()) <= 0.5 and float(first.std()) > 0
+    assert first.shape == (n, 2, 28, 56) and float(first.abs().max()) <= 0.6 and float(first.std()) > 0   # (bicubic taps overshoot +-0.5)
     env.root_states[:, 0] += 0.3
     env.step(torch.zeros(n, 12, device=DEV))                 # counter 1: skipped
     assert torch.equal(env.get_depth_images(), first)
