@@ -583,7 +583,14 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
                self.root_states.data_ptr(), tuple(self.command_ranges["lin_vel_x"]), self.init_done,
                None if self.episode_stats is None else self.episode_stats.buf.data_ptr())
         if getattr(self, "_reset_key", None) != key:
-            self._reset_rp, self._reset_bufs = self._native_reset()
+            # a few recent bindings are kept: a caller alternating between output blocks (double-buffered copy-out) must not rebuild
+            # the structs -- reading base_init_state back is a host synchronisation -- inside a CUDA-graph capture
+            cache = self.__dict__.setdefault("_reset_cache", {})
+            if key not in cache:
+                if len(cache) >= 8:
+                    cache.clear()
+                cache[key] = self._native_reset()
+            self._reset_rp, self._reset_bufs = cache[key]
             self._reset_key = key
         self._reset_rp.offset = self._noise_step
         self._reset_bufs.noise_u = _lib.ptr(self.noise_u)

@@ -30,3 +30,44 @@ for i in range(6):
     env.post_physics_step()
 torch.cuda.synchronize()
 print("resets in the last step:", int(env.reset_buf.sum()))
+
+# in-graph (warm instruction cache, programmatic dependent launch) time of every kernel of the step at this size
+def graph_time(fn, reps=20):
+    s = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(s):
+        fn()
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for _ in range(reps):
+                fn()
+        g.replay()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(5):
+            g.replay()
+        e1.record(s)
+        s.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / (5 * reps)
+
+
+from extended_legged_gym_b200 import _lib  # noqa: E402
+flags = env._reset_bool.clone()
+print("in-graph us per launch at", n, "envs:")
+print("  torques ", round(graph_time(lambda: env._compute_torques(env.actions)), 2))
+print("  resample", round(graph_time(env._launch_resample), 2))
+print("  step    ", round(graph_time(lambda: env._launch(_lib.PHASE_FUSED, 100.0)), 2))
+env._reset_bool.copy_(flags)
+nres = int(env._reset_bool.sum())
+
+
+def reset_only():
+    rp, b = env._reset_native_synced()
+    _lib.check(env._lib.elg_reset_envs(__import__("ctypes").byref(env._dims), __import__("ctypes").byref(rp), __import__("ctypes").byref(env._params),
+                                       __import__("ctypes").byref(b), torch.cuda.current_stream(dev).cuda_stream), "elg_reset_envs")
+
+
+print(f"  reset    {round(graph_time(reset_only), 2)}  ({nres} flagged envs)")
+env._reset_bool.zero_()
+print(f"  reset    {round(graph_time(reset_only), 2)}  (no env flagged)")
