@@ -108,6 +108,21 @@ __device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
   }
   return ctr;
 }
+// the same function for code that a FEW warps run once per launch (reset path): one out-of-line copy with the rounds rolled, so a
+// kernel that needs several blocks fetches ~30 instructions once instead of ~120 per use (single-warp straight-line code is bound
+// by instruction fetch, not by issue)
+static __device__ __noinline__ uint4 philox4x32_10_cold(uint4 ctr, uint2 key) {
+  constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll 1
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+    const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+    ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+    key.x += W0;
+    key.y += W1;
+  }
+  return ctr;
+}
 __device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
 
 // In-kernel observation noise: lane `lane` of the warp that owns env draws 128-bit blocks

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(kNormThreads)
 elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var,
                       float* __restrict__ stdv, int64_t* __restrict__ count, const float eps, const int64_t until, float* __restrict__ out,
                       void* __restrict__ scratch, const float* __restrict__ rew, float* __restrict__ rew_out, const uint8_t* __restrict__ dones,
-                      uint8_t* __restrict__ dones_out) {
+                      uint8_t* __restrict__ dones_out, const int debug) {
   __shared__ double sd[kNormThreads];
   __shared__ int s_last;
   const int cpt = g.cslots, c = threadIdx.x & (cpt - 1), rs = threadIdx.x / cpt, rsub = kNormThreads / cpt;
@@ -236,7 +236,7 @@ elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restri
   pdl_launch_dependents();
   pdl_wait();
   const int64_t old_count = *count;
-  const bool learn = !(until >= 0 && old_count >= until);          // (normalizer.py:62-63)
+  const bool learn = !(until >= 0 && old_count >= until) && !(debug & 8);          // (normalizer.py:62-63)
   const int64_t r0 = (int64_t)blockIdx.x * g.rows_per_cta;
   const int nrows = (int)max((int64_t)0, min((int64_t)g.rows_per_cta, g.rows - r0));
   const float* xb = x + r0 * g.cols + c;
@@ -322,7 +322,9 @@ elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restri
       }
     } else {
       if (threadIdx.x == 0) {
-        while (ld_acquire_u32(words + 1) == 0u) __nanosleep(20);
+        while (ld_acquire_u32(words + 1) == 0u && !(debug & 4)) {
+          if (!(debug & 16)) __nanosleep(20);
+        }
         // the consumer that brings the count to P - 1 is the last reader of the flag: it zeroes the header for the next call
         if (atomicAdd(words + 2, 1u) == (unsigned)(P - 2)) { words[0] = 0u; words[2] = 0u; st_release_u32(words + 1, 0u); }
       }
@@ -394,15 +396,31 @@ static void launch_pdl(void (*k)(Args...), dim3 grid, int threads, cudaStream_t 
   cudaLaunchKernelEx(&cfg, k, args...);
 }
 
-// 0: single launch when the batch fits one wave (default), 1: always the two-launch form (A/B runs, tests)
+// 0: single launch when the batch fits one wave (default), 1: always the two-launch form (A/B runs, tests).  Measurement bits
+// (results invalid): 2 = launch the single-launch form without programmatic dependent launch, 4 = consumers do not wait,
+// 8 = no statistics, 16 = spin without nanosleep
 int g_norm_mode = 0;
+
+template <typename K, typename... Args>
+static void launch_fused(K k, dim3 grid, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(kNormThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = (g_norm_mode & 2) ? 0 : 1;
+  cudaLaunchKernelEx(&cfg, k, args..., (int)g_norm_mode);
+}
 
 }  // namespace elg
 
 extern "C" {
 
 int elg_set_normalizer_tuning(int mode) {
-  if (mode < 0 || mode > 1) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer tuning mode must be 0 or 1");
+  if (mode < 0 || mode > 31) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer tuning mode must be 0 or 1 (+ measurement bits)");
   elg::g_norm_mode = mode;
   return ELG_OK;
 }
@@ -432,18 +450,18 @@ int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* 
   // 32-bit row offsets inside one row block / one apply block
   if ((int64_t)g.rows_per_part * num_cols >= ((int64_t)1 << 31)) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
-  if (training && elg::g_norm_mode == 0) {
+  if (training && (elg::g_norm_mode & 1) == 0) {
     const elg::FusedGeom fg = elg::make_fused_geom(num_rows, num_cols, elg::sm_count());
     if (fg.cslots > 0) {
       const int rsub = elg::kNormThreads / fg.cslots;
       const int per_thread = (fg.rows_per_cta + rsub - 1) / rsub;
       const dim3 grid((unsigned)((num_rows + fg.rows_per_cta - 1) / fg.rows_per_cta));
       if (per_thread <= 8)
-        elg::launch_pdl(elg::elg_norm_fused_kernel<8>, grid, elg::kNormThreads, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+        elg::launch_fused(elg::elg_norm_fused_kernel<8>, grid, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
       else if (per_thread <= 16)
-        elg::launch_pdl(elg::elg_norm_fused_kernel<16>, grid, elg::kNormThreads, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+        elg::launch_fused(elg::elg_norm_fused_kernel<16>, grid, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
       else
-        elg::launch_pdl(elg::elg_norm_fused_kernel<32>, grid, elg::kNormThreads, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+        elg::launch_fused(elg::elg_norm_fused_kernel<32>, grid, s, fg, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
       return elg::check_launch("elg_normalize_observations");
     }
   }

@@ -59,19 +59,29 @@ __device__ __forceinline__ void resample_one(const ElgResetParams& rp, float* cm
 struct LaneUniforms { float lo, hi; };
 __device__ __forceinline__ float uniform_col(const float* table, uint64_t seed, uint64_t offset, uint32_t env, int c) {
   if (table) return table[(size_t)env * ELG_RESET_UNIFORMS + c];
-  const uint4 blk = philox4x32_10(make_uint4(env, (uint32_t)(c >> 2), (uint32_t)offset, (uint32_t)(offset >> 32)),
-                                  make_uint2((uint32_t)seed ^ kResetStream, (uint32_t)(seed >> 32)));
+  const uint4 blk = philox4x32_10_cold(make_uint4(env, (uint32_t)(c >> 2), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                                       make_uint2((uint32_t)seed ^ kResetStream, (uint32_t)(seed >> 32)));
   const int w = c & 3;
   return u01(w == 0 ? blk.x : w == 1 ? blk.y : w == 2 ? blk.z : blk.w);
 }
 __device__ __forceinline__ LaneUniforms lane_uniforms(const float* table, uint64_t seed, uint64_t offset, uint32_t env, int lane, int ncols) {
   LaneUniforms u{0.0f, 0.0f};
-  if (lane < ncols) u.lo = uniform_col(table, seed, offset, env, lane);
-  if (lane + 32 < ncols) u.hi = uniform_col(table, seed, offset, env, lane + 32);
+#pragma unroll 1
+  for (int h = 0; h < 2; ++h) {      // (rolled: one copy of the code)
+    const int c = lane + 32 * h;
+    const float v = c < ncols ? uniform_col(table, seed, offset, env, c) : 0.0f;
+    if (h == 0) u.lo = v;
+    else u.hi = v;
+    if (ncols <= 32) break;
+  }
   return u;
 }
+__device__ __forceinline__ uint4 noise_block_cold(uint64_t seed, uint64_t offset, uint32_t env, uint32_t lane, uint32_t chunk) {
+  return philox4x32_10_cold(make_uint4(env, lane | (chunk << 5), (uint32_t)offset, (uint32_t)(offset >> 32)),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
 __device__ __forceinline__ float uget(const LaneUniforms& u, int c) {   // c: warp-uniform, all lanes call
-  return c < 32 ? __shfl_sync(0xffffffffu, u.lo, c) : __shfl_sync(0xffffffffu, u.hi, c - 32);
+  return __shfl_sync(0xffffffffu, c < 32 ? u.lo : u.hi, c & 31);   // (c is uniform: every lane offers the same member)
 }
 // _resample_commands (:405-423) on values: (u_x, u_y, u_third) -> cmd0, cmd1 after the small-command zeroing, heading or yaw rate
 __device__ __forceinline__ void resample_vals(const ElgResetParams& rp, float ux, float uy, float ut, float& cmd0, float& cmd1, float& third) {
@@ -137,21 +147,28 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
   float* ds = rb.dof_state + (size_t)e * D * 2;
   if (!self_reset) {
     // a rollout row whose main env resets: only its command row (and the observation entries built from it) change
-    if (lane == 0) {
-      Uniforms Um{rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)m, make_uint4(0, 0, 0, 0), -1};
-      const int keep = rp.heading_command ? 2 : 3;
-      if (keep < C) cmd[keep] = rb.commands[(size_t)m * C + keep];
-      resample_one(rp, cmd, Um, D);
-    }
+    const LaneUniforms Um = lane_uniforms(rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)m, lane, D + 12);
+    const int keep = rp.heading_command ? 2 : 3;
+    float c0, c1, third, c2 = C > 2 ? cmd[2] : 0.0f;
+    const float keep_val = keep < C ? rb.commands[(size_t)m * C + keep] : 0.0f;
+    resample_vals(rp, uget(Um, D + 8), uget(Um, D + 9), uget(Um, D + 10), c0, c1, third);
+    if (keep == 2 && keep < C) c2 = keep_val;
+    if (!rp.heading_command) c2 = third;
     __syncwarp();
+    if (lane == 0) {
+      if (keep < C) cmd[keep] = keep_val;
+      cmd[0] = c0; cmd[1] = c1;
+      if (rp.heading_command) cmd[3] = third;
+      else cmd[2] = third;
+    }
     if (rb.obs_buf && lane >= 9 && lane < 12) {
       const int k = lane;
-      float v = cmd[k - 9] * pr.commands_scale[k - 9];
+      float v = (k == 9 ? c0 : k == 10 ? c1 : c2) * pr.commands_scale[k - 9];
       if (pr.noise_mode == ELG_NOISE_TENSOR) v = v + (2.0f * rb.noise_u[(size_t)e * O + k] - 1.0f) * rb.noise_scale_vec[k];
       else if (pr.noise_mode == ELG_NOISE_PHILOX) {
         const int nj = (H + 31) >> 5, hm = (12 + 3 * D + 31) >> 5;
         const bool share = (nj & 7) + hm <= 8;
-        const uint4 b = noise_block(pr.noise_seed, pr.noise_offset, e, lane, share ? 1 + (nj >> 3) : 0);
+        const uint4 b = noise_block_cold(pr.noise_seed, pr.noise_offset, e, lane, share ? 1 + (nj >> 3) : 0);
         v = v + sym16(b, share ? (nj & 7) : 0) * rb.noise_scale_vec[k];
       }
       if (pr.clip_observations > 0.0f) v = fminf(fmaxf(v, -pr.clip_observations), pr.clip_observations);
@@ -282,27 +299,30 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
       const uint32_t w = (sidx >> 1) == 0 ? b.x : (sidx >> 1) == 1 ? b.y : (sidx >> 1) == 2 ? b.z : b.w;
       return (float)((w >> (16 * (sidx & 1))) & 0xffffu);
     };
-    // head entries k = lane + 32 m: sample (nj % 8) + m of block 1 + nj / 8 when shared, else sample m % 8 of block m / 8
+    // head entries k = lane + 32 m: sample (nj % 8) + m of block 1 + nj / 8 when shared, else sample m % 8 of block m / 8.
+    // (One Philox block per lane serves every entry of the usual layout -- nj = 6 height rounds + 2 head rounds = 8 samples.)
+    uint4 blk = make_uint4(0, 0, 0, 0);
+    int blk_id = -1;
+    auto block = [&](int id) {
+      if (philox && id != blk_id) { blk = noise_block_cold(pr.noise_seed, pr.noise_offset, e, lane, id); blk_id = id; }
+    };
+#pragma unroll 1
     for (int mm = 0; mm < hm; ++mm) {
       const int k = lane + 32 * mm;
       const float pos_k = __shfl_sync(0xffffffffu, newpos, (k - 12) & 31);      // the new position of dof k - 12 (lane k - 12 drew it)
+      block(share ? 1 + (nj >> 3) : (mm >> 3));
       float v;
       bool touch = false;
       if (k >= 9 && k < 12) { v = (k == 9 ? cm0 : k == 10 ? cm1 : cm2) * pr.commands_scale[k - 9]; touch = true; }
       else if (k >= 12 && k < 12 + D) { v = (pos_k - rb.default_dof_pos[k - 12]) * pr.obs_scale_dof_pos; touch = true; }
       else if (k >= 12 + D && k < 12 + 2 * D) { v = 0.0f * pr.obs_scale_dof_vel; touch = true; }
-      if (touch) {
-        float s16 = 0.0f;
-        if (philox) s16 = sample(noise_block(pr.noise_seed, pr.noise_offset, e, lane, share ? 1 + (nj >> 3) : (mm >> 3)), share ? (nj & 7) + mm : (mm & 7));
-        finish(k, v, s16);
-      }
+      if (touch) finish(k, v, philox ? sample(blk, share ? (nj & 7) + mm : (mm & 7)) : 0.0f);
     }
     // height entries: clip(z - 0.5 - h, -1, 1) * scale with the NEW base height and the stale heights
     if (H > 0 && rb.measured_heights) {
       const float zc = sub_r(r[2], 0.5f);
-      uint4 blk = make_uint4(0, 0, 0, 0);
       for (int j = 0; j < nj; ++j) {
-        if (philox && (j & 7) == 0) blk = noise_block(pr.noise_seed, pr.noise_offset, e, lane, 1 + (j >> 3));
+        block(1 + (j >> 3));
         const int p = lane + 32 * j;
         if (p < H) {
           const float h = rb.measured_heights[(size_t)e * H + p];

@@ -6,9 +6,15 @@ sys.path.insert(0, ROOT)
 import torch
 from extended_legged_gym_b200.utils.normalizer import EmpiricalNormalization
 
+from extended_legged_gym_b200 import _lib
+lib = _lib.load()
 dev = "cuda:0"
+# modes of elg_set_normalizer_tuning: 0 single launch (default), 1 two launches; measurement bits (results invalid): 2 no PDL,
+# 16 spin without nanosleep, 8 no statistics, 4 consumers do not wait (leaves the scratch header dirty: last)
+MODES = (0, 1, 2, 16, 8, 4) if "--modes" in sys.argv else (0, 1)
 for n, o in ((4096, 235), (4096, 48), (65536, 48), (32832, 235)):
-    for training in (True, False):
+    for training, mode in [(True, m) for m in MODES] + [(False, 0)]:
+        lib.elg_set_normalizer_tuning(mode)
         norm = EmpiricalNormalization(shape=[o], until=int(1e12)).to(dev)
         norm.train(training)
         x = torch.randn(n, o, device=dev)
@@ -29,4 +35,5 @@ for n, o in ((4096, 235), (4096, 48), (65536, 48), (32832, 235)):
                 g.replay()
             e1.record(gs); gs.synchronize()
         us = e0.elapsed_time(e1) * 1e3 / 192
-        print(f"{n} x {o} training={training}: {us:.2f} us/call, {n * o * 8 / us / 1e3:.0f} GB/s", flush=True)
+        lib.elg_set_normalizer_tuning(0)
+        print(f"{n} x {o} training={training} mode={mode}: {us:.2f} us/call, {n * o * 8 / us / 1e3:.0f} GB/s", flush=True)
