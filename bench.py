@@ -536,7 +536,7 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
             e1.record(gs)
             gs.synchronize()
         return e0.elapsed_time(e1) * 1e-3 / 192
-    sec = time_norm()                      # default: ONE launch (rows stay in registers across a grid-wide hand-over)
+    sec = time_norm()                      # default: ONE launch (a CTA owns four columns and all their rows, which stay in registers)
     lib.elg_set_normalizer_tuning(1)
     sec2 = time_norm()                     # the statistics + apply pair that larger batches take
     lib.elg_set_normalizer_tuning(0)

@@ -215,15 +215,15 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 }
 __device__ __forceinline__ void st_release_u32(unsigned* p, unsigned v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// per-CTA moments of the single-launch form: doubles [cta][2][cols] (mean, M2) behind the four float vectors; the row count of a CTA
-// follows from the geometry.  Sums run in double and in a fixed order -- partial means of a few rows each would otherwise carry
-// half an ulp of the MEAN into every (mean_i - mean)^2, which is large against a small variance.
+// per-CTA sums of the single-launch form: doubles [cta][2][cols] (sum of x - pivot, sum of its square) behind the four float vectors.
+// Sums run in double and in a fixed order -- float partial means of a few rows each would carry half an ulp of the MEAN into every
+// (mean_i - mean)^2, which is large against a small variance (seen: 300 x 1024, 1.6e-6 on a std of 0.019).
 __device__ __forceinline__ double* scr_dpart(void* s, int cols, int cta, int which) {
   return reinterpret_cast<double*>(reinterpret_cast<char*>(s) + kNormHeader + (size_t)cols * 16) + ((size_t)cta * 2 + which) * cols;
 }
 
 template <int kC>      // rows a thread keeps in registers
-__global__ void __launch_bounds__(kNormThreads)
+__global__ void __launch_bounds__(kNormThreads, 1)
 elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var,
                       float* __restrict__ stdv, int64_t* __restrict__ count, const float eps, const int64_t until, float* __restrict__ out,
                       void* __restrict__ scratch, const float* __restrict__ rew, float* __restrict__ rew_out, const uint8_t* __restrict__ dones,
@@ -262,18 +262,21 @@ elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restri
   };
   float m_use, den;
   if (learn) {
-    // CTA moments, two passes over the registers: mean first, then the squared deviations from it
-    double s = 0.0;
+    // CTA sums of (x - pivot) and (x - pivot)^2 in double, pivot = the column's entry in row 0 of the batch: a value of the data's
+    // own scale, so the final  M2 = S2 - S1^2 / N  cancels a few bits of 53, whatever the mean / std ratio of the column
+    const double pivot = live ? (double)__ldg(x + c) : 0.0;
+    double s = 0.0, q2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < kC; ++k) s += (rs + k * rsub < nrows) ? (double)v[k] : 0.0;
-    const double m_cta = column_sum(s) / (double)nrows;
-    double q2 = 0.0;
-#pragma unroll
-    for (int k = 0; k < kC; ++k) { const double d = (double)v[k] - m_cta; q2 += (rs + k * rsub < nrows) ? d * d : 0.0; }
-    const double m2_cta = column_sum(q2);
+    for (int k = 0; k < kC; ++k) {
+      const double d = (double)v[k] - pivot;
+      const bool ok = rs + k * rsub < nrows;
+      s += ok ? d : 0.0;
+      q2 += ok ? d * d : 0.0;
+    }
+    const double s_cta = column_sum(s), q_cta = column_sum(q2);
     if (rs == 0 && live) {
-      scr_dpart(scratch, g.cols, blockIdx.x, 0)[c] = m_cta;
-      scr_dpart(scratch, g.cols, blockIdx.x, 1)[c] = m2_cta;
+      scr_dpart(scratch, g.cols, blockIdx.x, 0)[c] = s_cta;
+      scr_dpart(scratch, g.cols, blockIdx.x, 1)[c] = q_cta;
     }
     unsigned* words = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + 16);
     __threadfence();
@@ -281,25 +284,28 @@ elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restri
     if (threadIdx.x == 0) s_last = atomicAdd(words, 1u) == (unsigned)(P - 1);
     __syncthreads();
     if (s_last) {
-      // the last CTA to arrive: every pair is in L2.  Batch moments in block order -- independent loads, plain sums --, the update
-      // rule (normalizer.py:65-75), the state, and mean / std + eps for everybody
+      // the last CTA to arrive: every pair is in L2.  Plain sums in block order -- the loads of a batch go out together (a loop that
+      // consumes each value before it asks for the next pays the L2 latency once per CTA: measured 24 us at 128 CTAs) --, then the
+      // update rule (normalizer.py:65-75), the state, and mean / std + eps for everybody
       __threadfence();
-      auto rows_of = [&](int p) { return (double)min((int64_t)g.rows_per_cta, g.rows - (int64_t)p * g.rows_per_cta); };
-      double a = 0.0;
+      constexpr int kB = 8;
+      double a1 = 0.0, a2 = 0.0;
       if (live) {
-#pragma unroll 8
-        for (int p = rs; p < P; p += rsub) a += rows_of(p) * __ldcg(scr_dpart(scratch, g.cols, p, 0) + c);
-      }
-      const double mean_x_d = column_sum(a) / (double)g.rows;
-      double b = 0.0;
-      if (live) {
-#pragma unroll 8
-        for (int p = rs; p < P; p += rsub) {
-          const double d = __ldcg(scr_dpart(scratch, g.cols, p, 0) + c) - mean_x_d;
-          b += __ldcg(scr_dpart(scratch, g.cols, p, 1) + c) + rows_of(p) * (d * d);
+        for (int p0 = rs; p0 < P; p0 += kB * rsub) {
+          double sv[kB], qv[kB];
+#pragma unroll
+          for (int u = 0; u < kB; ++u) {
+            const int p = p0 + u * rsub;
+            sv[u] = p < P ? __ldcg(scr_dpart(scratch, g.cols, p, 0) + c) : 0.0;
+            qv[u] = p < P ? __ldcg(scr_dpart(scratch, g.cols, p, 1) + c) : 0.0;
+          }
+#pragma unroll
+          for (int u = 0; u < kB; ++u) { a1 += sv[u]; a2 += qv[u]; }
         }
       }
-      const double m2_x_d = column_sum(b);
+      const double S1 = column_sum(a1), S2 = column_sum(a2);
+      const double mean_x_d = pivot + S1 / (double)g.rows;
+      const double m2_x_d = fmax(S2 - S1 * S1 / (double)g.rows, 0.0);
       if (rs == 0 && live) {
         const int64_t new_count = old_count + g.rows;
         const float rate = (float)g.rows / (float)new_count;
@@ -346,6 +352,103 @@ elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restri
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// column-parallel single launch: a CTA owns FOUR columns and every row of them (<= 32 values per thread: up to 8192 rows), so the
+// batch statistics of its columns need no other CTA -- no grid-wide hand-over, no second launch, the rows stay in registers from the
+// load to the normalised store.  Four consecutive lanes read the 16 contiguous bytes of a row (half a sector: the other half is
+// the neighbour CTA's and comes out of L2).  Sums of (x - pivot) and (x - pivot)^2 in double (pivot: the column's entry in row 0),
+// reduced in a fixed order: shuffles inside a warp, warp totals in shared memory, one thread per column adds them in warp order.
+// The CTA that finishes last (one ticket) stores the new count -- every CTA has read the old one by then.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kColsPerCta = 4;
+template <int kC>
+__global__ void __launch_bounds__(kNormThreads, 1)
+elg_norm_cols_kernel(const int64_t rows, const int cols, const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var,
+                     float* __restrict__ stdv, int64_t* __restrict__ count, const float eps, const int64_t until, float* __restrict__ out,
+                     void* __restrict__ scratch, const float* __restrict__ rew, float* __restrict__ rew_out, const uint8_t* __restrict__ dones,
+                     uint8_t* __restrict__ dones_out) {
+  constexpr int kRowsPerPass = kNormThreads / kColsPerCta;   // 256
+  __shared__ double s_w[2][kNormThreads / 32][kColsPerCta];
+  __shared__ float s_mean[kColsPerCta], s_den[kColsPerCta];
+  const int c4 = threadIdx.x & (kColsPerCta - 1), rb = threadIdx.x / kColsPerCta;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int col = blockIdx.x * kColsPerCta + c4;
+  const bool live = col < cols;
+  pdl_launch_dependents();
+  pdl_wait();
+  const int64_t old_count = *count;
+  const bool learn = !(until >= 0 && old_count >= until);          // (normalizer.py:62-63)
+  const float* xb = x + col;
+  float v[kC];
+#pragma unroll
+  for (int k = 0; k < kC; ++k) {
+    const int64_t r = rb + (int64_t)k * kRowsPerPass;
+    v[k] = (live && r < rows) ? xb[r * cols] : 0.0f;
+  }
+  {      // reward / done columns: this CTA's share of the rows
+    const int64_t per = (rows + gridDim.x - 1) / gridDim.x, lo = (int64_t)blockIdx.x * per, hi = min(rows, lo + per);
+    for (int64_t r = lo + threadIdx.x; r < hi; r += kNormThreads) {
+      if (rew_out) rew_out[r] = rew[r];
+      if (dones_out) dones_out[r] = dones[r];
+    }
+  }
+  if (learn) {
+    const double pivot = live ? (double)__ldg(xb) : 0.0;
+    double s = 0.0, q = 0.0;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) {
+      const double d = (double)v[k] - pivot;
+      const bool ok = rb + (int64_t)k * kRowsPerPass < rows;
+      s += ok ? d : 0.0;
+      q += ok ? d * d : 0.0;
+    }
+#pragma unroll
+    for (int o = kColsPerCta; o < 32; o <<= 1) {      // lanes of one column: lane & 3
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    if (lane < kColsPerCta) { s_w[0][warp][lane] = s; s_w[1][warp][lane] = q; }
+    __syncthreads();
+    if (threadIdx.x < kColsPerCta && live) {
+      double S1 = 0.0, S2 = 0.0;
+      for (int w = 0; w < kNormThreads / 32; ++w) { S1 += s_w[0][w][c4]; S2 += s_w[1][w][c4]; }
+      const double mean_x_d = pivot + S1 / (double)rows;
+      const double m2_x_d = fmax(S2 - S1 * S1 / (double)rows, 0.0);
+      const int64_t new_count = old_count + rows;      // (normalizer.py:65-75)
+      const float rate = (float)rows / (float)new_count;
+      const float mean_x = (float)mean_x_d, var_x = (float)(m2_x_d / (double)rows);
+      const float m_old = mean[col], v_old = var[col];
+      const float delta = mean_x - m_old;
+      const float m_new = m_old + rate * delta;
+      const float v_new = v_old + rate * (var_x - v_old + delta * (mean_x - m_new));
+      const float s_new = __fsqrt_rn(v_new);
+      mean[col] = m_new; var[col] = v_new; stdv[col] = s_new;
+      s_mean[c4] = m_new;
+      s_den[c4] = s_new + eps;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {      // the last CTA to get here stores the new count: every CTA has read the old one
+      unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + 16);
+      if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+        *count = old_count + rows;
+        *ticket = 0u;
+      }
+    }
+  } else {
+    if (threadIdx.x < kColsPerCta && live) { s_mean[c4] = mean[col]; s_den[c4] = stdv[col] + eps; }
+    __syncthreads();
+  }
+  if (live && out) {
+    const float m = s_mean[c4], den = s_den[c4];
+    float* ob = out + col;
+#pragma unroll
+    for (int k = 0; k < kC; ++k) {
+      const int64_t r = rb + (int64_t)k * kRowsPerPass;
+      if (r < rows) ob[r * cols] = (v[k] - m) / den;
+    }
+  }
+}
+
 // geometry of the single-launch form, or cslots == 0 when the batch does not fit one wave of register-resident rows
 static FusedGeom make_fused_geom(int64_t rows, int cols, int sms) {
   FusedGeom g{};
@@ -355,8 +458,8 @@ static FusedGeom make_fused_geom(int64_t rows, int cols, int sms) {
   int cs = 32;
   while (cs < cols) cs <<= 1;
   const int rsub = kNormThreads / cs;
-  int ctas = sms > kNormParts * 4 ? kNormParts * 4 : sms;      // parts of the scratch layout: make_geom reserves >= this many
-  // power-of-two CTA counts keep the per-thread row count a small power of two as well (4096 rows -> 128 CTAs x 32 rows)
+  int ctas = sms > kNormParts * 2 ? kNormParts * 2 : sms;      // <= 64 CTAs: the last one sums one (S1, S2) pair per CTA and column
+  // power-of-two CTA counts keep the per-thread row count a small power of two as well (4096 rows -> 64 CTAs x 64 rows)
   int p2 = 1;
   while (p2 * 2 <= ctas) p2 <<= 1;
   int64_t rpc = (rows + p2 - 1) / p2;
@@ -396,9 +499,10 @@ static void launch_pdl(void (*k)(Args...), dim3 grid, int threads, cudaStream_t 
   cudaLaunchKernelEx(&cfg, k, args...);
 }
 
-// 0: single launch when the batch fits one wave (default), 1: always the two-launch form (A/B runs, tests).  Measurement bits
-// (results invalid): 2 = launch the single-launch form without programmatic dependent launch, 4 = consumers do not wait,
-// 8 = no statistics, 16 = spin without nanosleep
+// 0 (default): the column-parallel single launch for batches of <= 8192 rows, the statistics + apply pair otherwise; 1: always the
+// pair; 2: the row-parallel single launch with a grid-wide hand-over (measured slower than the pair: 14.8 vs 11.0 us at 4096 x 235;
+// kept for A/B runs).  Measurement bits of form 2 (results invalid): 4 = consumers do not wait, 8 = no statistics, 16 = spin
+// without nanosleep
 int g_norm_mode = 0;
 
 template <typename K, typename... Args>
@@ -411,8 +515,8 @@ static void launch_fused(K k, dim3 grid, cudaStream_t stream, Args... args) {
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = (g_norm_mode & 2) ? 0 : 1;
-  cudaLaunchKernelEx(&cfg, k, args..., (int)g_norm_mode);
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, k, args..., (int)(g_norm_mode & ~3));
 }
 
 }  // namespace elg
@@ -450,7 +554,18 @@ int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* 
   // 32-bit row offsets inside one row block / one apply block
   if ((int64_t)g.rows_per_part * num_cols >= ((int64_t)1 << 31)) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
-  if (training && (elg::g_norm_mode & 1) == 0) {
+  if (training && elg::g_norm_mode == 0 && num_rows <= 32 * (elg::kNormThreads / elg::kColsPerCta)) {
+    const int per_thread = (int)((num_rows + elg::kNormThreads / elg::kColsPerCta - 1) / (elg::kNormThreads / elg::kColsPerCta));
+    const dim3 grid((unsigned)((num_cols + elg::kColsPerCta - 1) / elg::kColsPerCta));
+    if (per_thread <= 8)
+      elg::launch_pdl(elg::elg_norm_cols_kernel<8>, grid, elg::kNormThreads, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+    else if (per_thread <= 16)
+      elg::launch_pdl(elg::elg_norm_cols_kernel<16>, grid, elg::kNormThreads, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+    else
+      elg::launch_pdl(elg::elg_norm_cols_kernel<32>, grid, elg::kNormThreads, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+    return elg::check_launch("elg_normalize_observations");
+  }
+  if (training && (elg::g_norm_mode & 2)) {      // the grid-wide hand-over form: measured slower than the pair below (A/B only)
     const elg::FusedGeom fg = elg::make_fused_geom(num_rows, num_cols, elg::sm_count());
     if (fg.cslots > 0) {
       const int rsub = elg::kNormThreads / fg.cslots;

@@ -181,6 +181,36 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
   // stores the results at the end.  (The first form did the scalar work in lane 0 with read-modify-write chains through global
   // memory -- some twenty dependent round trips: 24.7 us per launch at 65 536 envs whatever the number of resets.)
   const bool zero_sums = R1 <= 0 || rb.stats[ELG_NUM_REWARD_TERMS + 1] != 0.0f;
+  // Every global value the rest of the function reads is requested HERE, before the first store: the stores below may alias the
+  // loads as far as the compiler knows, so a load written after them waits for its own DRAM round trip -- the height entries alone
+  // were six such trips in a row (profiles/README.md r2o: 18 us per launch, 60 % of the samples on the first use of a loaded value).
+  constexpr int kMaxNJ = 8, kMaxHM = 4;      // H <= 256, head = 12 + 3 D <= 108 (checked by the host)
+  static_assert(ELG_NUM_REWARD_TERMS <= 32, "one lane per reward term");
+  const int head = 12 + 3 * D;
+  const int nj = (H + 31) >> 5, hm = (head + 31) >> 5;
+  const bool repair = rb.obs_buf != nullptr;
+  const bool philox = pr.noise_mode == ELG_NOISE_PHILOX, tensor_noise = pr.noise_mode == ELG_NOISE_TENSOR;
+  const bool noisy = philox || tensor_noise;
+  float hv[kMaxNJ], nsv[kMaxNJ], nuv[kMaxNJ], nsh[kMaxHM], nuh[kMaxHM];
+#pragma unroll
+  for (int j = 0; j < kMaxNJ; ++j) {
+    const int p = lane + 32 * j;
+    const bool ok = repair && rb.measured_heights && j < nj && p < H;
+    hv[j] = ok ? rb.measured_heights[(size_t)e * H + p] : 0.0f;
+    nsv[j] = (ok && noisy) ? rb.noise_scale_vec[head + p] : 0.0f;
+    nuv[j] = (ok && tensor_noise) ? rb.noise_u[(size_t)e * O + head + p] : 0.0f;
+  }
+#pragma unroll
+  for (int mm = 0; mm < kMaxHM; ++mm) {
+    const int k = lane + 32 * mm;
+    const bool ok = repair && mm < hm && k >= 9 && k < 12 + 2 * D;
+    nsh[mm] = (ok && noisy) ? rb.noise_scale_vec[k] : 0.0f;
+    nuh[mm] = (ok && tensor_noise) ? rb.noise_u[(size_t)e * O + k] : 0.0f;
+  }
+  const float defpos = lane < D ? rb.default_dof_pos[lane] : 0.0f;
+  const bool term_on = lane < ELG_NUM_REWARD_TERMS && ((pr.reward_mask >> lane) & 1u);
+  float* const sum_ptr = rb.episode_sums + (size_t)(term_on ? lane : 0) * N + e;
+  const float sum_mine = term_on ? *sum_ptr : 0.0f;
   const LaneUniforms U = lane_uniforms(rb.uniforms, rp.seed, rp.offset * 2 + 1, (uint32_t)e, lane, D + 12);
   float o0 = org[0], o1 = org[1], o2 = org[2];
   float cm0 = cmd[0], cm1 = cmd[1], cm2 = C > 2 ? cmd[2] : 0.0f;
@@ -239,7 +269,7 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
   // ---- _reset_dofs (:450-465); last_dof_vel = new dof_vel (= 0) after the history copy (:149); last_actions already
   // holds `actions` (zeroed by reset_idx, then overwritten by the history copy :148).  D <= 32: dof j is lane j's.
   float newpos = 0.0f;
-  if (lane < D) newpos = mul_r(rb.default_dof_pos[lane], rand_range(0.5f, 1.5f, U.lo));
+  if (lane < D) newpos = mul_r(defpos, rand_range(0.5f, 1.5f, U.lo));
   __syncwarp();   // every lane has read the old state: lane 0 may overwrite it
   if (lane < D) {
     ds[2 * lane] = newpos;
@@ -272,26 +302,21 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
       if (rb.stats_accum) atomicAdd(rb.stats_accum + ELG_NUM_REWARD_TERMS, 1.0);
     }
   }
-  // ---- extras["episode"] (:200-206): (sum, count) over the reset envs, then zero the sums
-  for (int t = lane; t < ELG_NUM_REWARD_TERMS; t += 32)
-    if ((pr.reward_mask >> t) & 1u) {
-      float* sp = rb.episode_sums + (size_t)t * N + e;
-      if (is_main) {
-        atomicAdd(rb.stats + t, *sp);
-        if (rb.stats_accum) atomicAdd(rb.stats_accum + t, (double)*sp);
-      }
-      if (zero_sums) *sp = 0.0f;
+  // ---- extras["episode"] (:200-206): (sum, count) over the reset envs, then zero the sums (lane t owns term t)
+  if (term_on) {
+    if (is_main) {
+      atomicAdd(rb.stats + lane, sum_mine);
+      if (rb.stats_accum) atomicAdd(rb.stats_accum + lane, (double)sum_mine);
     }
+    if (zero_sums) *sum_ptr = 0.0f;
+  }
   // ---- observation repair (:234-252 evaluated after the reset)
-  if (rb.obs_buf) {
-    const int head = 12 + 3 * D;
-    const int nj = (H + 31) >> 5, hm = (head + 31) >> 5;
+  if (repair) {
     const bool share = (nj & 7) + hm <= 8;
-    const bool philox = pr.noise_mode == ELG_NOISE_PHILOX;
     float* ob = rb.obs_buf + (size_t)e * O;
-    auto finish = [&](int k, float v, float s16) {
-      if (pr.noise_mode == ELG_NOISE_TENSOR) v = v + (2.0f * rb.noise_u[(size_t)e * O + k] - 1.0f) * rb.noise_scale_vec[k];
-      else if (philox) v = v + fmaf(s16, 1.0f / 32768.0f, -1.0f) * rb.noise_scale_vec[k];
+    auto finish = [&](int k, float v, float s16, float ns, float nu) {
+      if (tensor_noise) v = v + (2.0f * nu - 1.0f) * ns;
+      else if (philox) v = v + fmaf(s16, 1.0f / 32768.0f, -1.0f) * ns;
       if (pr.clip_observations > 0.0f) v = fminf(fmaxf(v, -pr.clip_observations), pr.clip_observations);
       ob[k] = v;
     };
@@ -306,28 +331,33 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
     auto block = [&](int id) {
       if (philox && id != blk_id) { blk = noise_block_cold(pr.noise_seed, pr.noise_offset, e, lane, id); blk_id = id; }
     };
-#pragma unroll 1
-    for (int mm = 0; mm < hm; ++mm) {
-      const int k = lane + 32 * mm;
-      const float pos_k = __shfl_sync(0xffffffffu, newpos, (k - 12) & 31);      // the new position of dof k - 12 (lane k - 12 drew it)
-      block(share ? 1 + (nj >> 3) : (mm >> 3));
-      float v;
-      bool touch = false;
-      if (k >= 9 && k < 12) { v = (k == 9 ? cm0 : k == 10 ? cm1 : cm2) * pr.commands_scale[k - 9]; touch = true; }
-      else if (k >= 12 && k < 12 + D) { v = (pos_k - rb.default_dof_pos[k - 12]) * pr.obs_scale_dof_pos; touch = true; }
-      else if (k >= 12 + D && k < 12 + 2 * D) { v = 0.0f * pr.obs_scale_dof_vel; touch = true; }
-      if (touch) finish(k, v, philox ? sample(blk, share ? (nj & 7) + mm : (mm & 7)) : 0.0f);
+#pragma unroll
+    for (int mm = 0; mm < kMaxHM; ++mm) {
+      if (mm < hm) {      // (warp-uniform)
+        const int k = lane + 32 * mm;
+        const float pos_k = __shfl_sync(0xffffffffu, newpos, (k - 12) & 31);      // dof k - 12: lane k - 12 drew its new position
+        const float def_k = __shfl_sync(0xffffffffu, defpos, (k - 12) & 31);
+        block(share ? 1 + (nj >> 3) : (mm >> 3));
+        float v;
+        bool touch = false;
+        if (k >= 9 && k < 12) { v = (k == 9 ? cm0 : k == 10 ? cm1 : cm2) * pr.commands_scale[k - 9]; touch = true; }
+        else if (k >= 12 && k < 12 + D) { v = (pos_k - def_k) * pr.obs_scale_dof_pos; touch = true; }
+        else if (k >= 12 + D && k < 12 + 2 * D) { v = 0.0f * pr.obs_scale_dof_vel; touch = true; }
+        if (touch) finish(k, v, philox ? sample(blk, share ? (nj & 7) + mm : (mm & 7)) : 0.0f, nsh[mm], nuh[mm]);
+      }
     }
     // height entries: clip(z - 0.5 - h, -1, 1) * scale with the NEW base height and the stale heights
     if (H > 0 && rb.measured_heights) {
       const float zc = sub_r(r[2], 0.5f);
-      for (int j = 0; j < nj; ++j) {
-        block(1 + (j >> 3));
-        const int p = lane + 32 * j;
-        if (p < H) {
-          const float h = rb.measured_heights[(size_t)e * H + p];
-          const float v = mul_r(fminf(fmaxf(sub_r(zc, h), -1.0f), 1.0f), pr.obs_scale_height);
-          finish(head + p, v, philox ? sample(blk, j & 7) : 0.0f);
+#pragma unroll
+      for (int j = 0; j < kMaxNJ; ++j) {
+        if (j < nj) {
+          block(1 + (j >> 3));
+          const int p = lane + 32 * j;
+          if (p < H) {
+            const float v = mul_r(fminf(fmaxf(sub_r(zc, hv[j]), -1.0f), 1.0f), pr.obs_scale_height);
+            finish(head + p, v, philox ? sample(blk, j & 7) : 0.0f, nsv[j], nuv[j]);
+          }
         }
       }
     }
@@ -400,6 +430,7 @@ int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepP
   if (!dims || !rp || !prm || !buf) return rfail(ELG_ERR_NULL_POINTER, "dims/params/buffers is NULL");
   if (dims->num_dof + 12 > ELG_RESET_UNIFORMS) return rfail(ELG_ERR_UNSUPPORTED, "num_dof + 12 exceeds ELG_RESET_UNIFORMS");
   if (dims->num_dof > 32) return rfail(ELG_ERR_UNSUPPORTED, "elg_reset_envs: more than 32 dofs (one lane per joint)");
+  if (buf->obs_buf && dims->num_height_points > 256) return rfail(ELG_ERR_UNSUPPORTED, "elg_reset_envs: more than 256 height points");
   if (dims->num_envs == 0) return ELG_OK;
   if (!buf->reset_buf || !buf->root_states || !buf->dof_state || !buf->commands || !buf->env_origins || !buf->default_dof_pos ||
       !buf->last_dof_vel || !buf->last_root_vel || !buf->feet_air_time || !buf->feet_contact_time || !buf->episode_length_buf ||

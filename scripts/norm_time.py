@@ -9,9 +9,9 @@ from extended_legged_gym_b200.utils.normalizer import EmpiricalNormalization
 from extended_legged_gym_b200 import _lib
 lib = _lib.load()
 dev = "cuda:0"
-# modes of elg_set_normalizer_tuning: 0 single launch (default), 1 two launches; measurement bits (results invalid): 2 no PDL,
-# 16 spin without nanosleep, 8 no statistics, 4 consumers do not wait (leaves the scratch header dirty: last)
-MODES = (0, 1, 2, 16, 8, 4) if "--modes" in sys.argv else (0, 1)
+# modes of elg_set_normalizer_tuning: 0 default (column-parallel single launch up to 8192 rows), 1 two launches, 2 row-parallel single
+# launch with a grid-wide hand-over
+MODES = (0, 1, 2)
 for n, o in ((4096, 235), (4096, 48), (65536, 48), (32832, 235)):
     for training, mode in [(True, m) for m in MODES] + [(False, 0)]:
         lib.elg_set_normalizer_tuning(mode)

@@ -99,10 +99,10 @@ def test_kernel_matches_reference_fixture(tag):
         assert_out(y, torch.from_numpy(z[f"{tag}__s{s}__out"]), m._std, m._mean)
 
 
-@pytest.fixture(params=[0, 1], ids=["single_launch", "two_launches"])
+@pytest.fixture(params=[0, 1, 2], ids=["default", "two_launches", "grid_handover"])
 def launch_form(request):
-    """both forms of the training-mode call: one launch with a grid-wide hand-over (default, batches that fit one wave of CTAs)
-    and the statistics + apply pair (larger batches; forced here with elg_set_normalizer_tuning(1))"""
+    """the forms of the training-mode call: 0 = column-parallel single launch up to 8192 rows, else the statistics + apply pair;
+    1 = always the pair; 2 = row-parallel single launch with a grid-wide hand-over (A/B form, batches that fit one wave of CTAs)"""
     lib = _lib.load()
     lib.elg_set_normalizer_tuning(request.param)
     yield request.param
