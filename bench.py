@@ -802,7 +802,7 @@ def main():
     point_outputs_at(out_blocks[0])
     # G consecutive steps form one CUDA graph; the copy-out of step i (second stream) overlaps the copy-in of step i + 1 (PCIe is
     # full duplex); the host launches the graph, waits and reads every step's result.
-    G = max(2, min(20, args.e2e_steps))
+    G = max(2, min(40, args.e2e_steps))
     G -= G % 2                             # (the two staging / output blocks alternate: an even number of steps per graph)
     host_out = [torch.empty(n_out_words).pin_memory() for _ in range(G)]
     h2d = host_in.numel() * 4

@@ -364,25 +364,38 @@ __device__ __forceinline__ void reset_env(const ElgResetParams& rp, const ElgSte
   }
 }
 
-__global__ void __launch_bounds__(128)
+// A CTA of eight warps owns 256 consecutive envs: every thread reads the flag of its env (coalesced), ballots + one shared counter
+// collect the rows that have work into a shared list, and the warps take the list entries round-robin -- one row per warp at a
+// time.  (One warp per 32 envs handling ITS rows one after the other took as long as its unluckiest warp: at 65 536 envs and ~390
+// resets some warp always holds three -- 14.3 us per launch against 6.3 us with at most one per warp, profiles/README.md r2q.)
+constexpr int kResetThreads = 256;
+__global__ void __launch_bounds__(kResetThreads)
 elg_reset_kernel(const __grid_constant__ ElgResetParams rp, const __grid_constant__ ElgStepParams pr, const __grid_constant__ ElgResetBuffers rb,
                  const int N, const int D, const int F, const int C, const int O, const int H) {
-  const int lane = threadIdx.x & 31;
-  const int base = ((blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32;
+  __shared__ int s_list[kResetThreads];
+  __shared__ int s_n;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int mine = blockIdx.x * kResetThreads + threadIdx.x;
+  if (threadIdx.x == 0) s_n = 0;
   pdl_launch_dependents();
   pdl_wait();
-  if (base >= N) return;
-  const int mine = base + lane;
   bool work = false;
   if (mine < N) {
     work = rb.reset_buf[mine] != 0;
     if (!work && rp.rows_per_main > 0) work = rb.reset_buf[(mine / rp.rows_per_main) * rp.rows_per_main] != 0;   // the main env of this row resets
   }
-  unsigned todo = __ballot_sync(0xffffffffu, work);
-  while (todo) {
-    const int b = __ffs((int)todo) - 1;
-    todo &= todo - 1;
-    reset_env(rp, pr, rb, base + b, lane, N, D, F, C, O, H);
+  __syncthreads();
+  const unsigned todo = __ballot_sync(0xffffffffu, work);
+  if (todo) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(&s_n, __popc(todo));
+    base = __shfl_sync(0xffffffffu, base, 0);
+    if (work) s_list[base + __popc(todo & ((1u << lane) - 1u))] = mine;
+  }
+  __syncthreads();
+  const int n = s_n;
+  for (int i = warp; i < n; i += kResetThreads / 32) {
+    reset_env(rp, pr, rb, s_list[i], lane, N, D, F, C, O, H);
     __syncwarp();
   }
 }
@@ -447,7 +460,7 @@ int elg_reset_envs(const ElgDims* dims, const ElgResetParams* rp, const ElgStepP
   if (rp->rows_per_main > 0)
     launch_pdl(elg::elg_main_reset_flag_kernel, dim3(1), 1024, (cudaStream_t)stream, buf->reset_buf, (int)(dims->num_envs / rp->rows_per_main),
                (int)rp->rows_per_main, buf->stats);
-  launch_pdl(elg::elg_reset_kernel, dim3((dims->num_envs + 127) / 128), 128, (cudaStream_t)stream, *rp, *prm, *buf, (int)dims->num_envs, (int)dims->num_dof,
+  launch_pdl(elg::elg_reset_kernel, dim3((dims->num_envs + elg::kResetThreads - 1) / elg::kResetThreads), elg::kResetThreads, (cudaStream_t)stream, *rp, *prm, *buf, (int)dims->num_envs, (int)dims->num_dof,
              (int)dims->num_feet, (int)dims->num_commands, (int)dims->num_obs, (int)dims->num_height_points);
   return elg::check_launch("elg_reset_envs");
 }

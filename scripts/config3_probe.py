@@ -70,4 +70,13 @@ def reset_only():
 
 print(f"  reset    {round(graph_time(reset_only), 2)}  ({nres} flagged envs)")
 env._reset_bool.zero_()
+env._reset_bool[::170] = True          # the same number of resets, but never two in one warp's 32 envs
+print(f"  reset    {round(graph_time(reset_only), 2)}  ({int(env._reset_bool.sum())} flagged envs, at most one per 32-env group)")
+env._reset_bool.zero_()
+env._reset_bool[:96:32] = True
+print(f"  reset    {round(graph_time(reset_only), 2)}  (3 flagged envs in 3 groups)")
+env._reset_bool.zero_()
+env._reset_bool[:3] = True
+print(f"  reset    {round(graph_time(reset_only), 2)}  (3 flagged envs in one group)")
+env._reset_bool.zero_()
 print(f"  reset    {round(graph_time(reset_only), 2)}  (no env flagged)")
