@@ -397,7 +397,8 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
         pl.tiles_bytes = toff;
         pl.row_words = roff;
         const size_t smem = (size_t)toff + (size_t)roff * 4;
-        static size_t smem_set = 0;
+        static elg::SmemCache smem_cache = {};
+  size_t& smem_set = elg::smem_slot(smem_cache);
         if (smem > smem_set) {
           if (cudaFuncSetAttribute(elg::elg_clone_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
             return cfail(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_clone_bulk_kernel");

@@ -13,6 +13,12 @@ constexpr int kWarp = 32;
 int set_error(int code, const char* msg);   // records msg for elg_last_error(), returns code
 int check_launch(const char* what);         // cudaGetLastError() -> ELG_OK / ELG_ERR_CUDA
 int sm_count();                             // SMs of the current device (0 on failure)
+// Host-side caches are kept PER DEVICE: a process may drive several GPUs (one env object each), and the dynamic shared-memory
+// opt-in of a kernel (cudaFuncSetAttribute) as well as the SM count belong to the device that is current at the call.
+constexpr int kMaxDevices = 32;
+int device_index();                         // current device, clamped to [0, kMaxDevices)
+struct SmemCache { size_t bytes[kMaxDevices]; };
+inline size_t& smem_slot(SmemCache& c) { return c.bytes[device_index()]; }
 
 // ---------------------------------------------------------------------------------------------
 // Individually rounded fp32 ops.  torch evaluates the reference expression one ATen op at a

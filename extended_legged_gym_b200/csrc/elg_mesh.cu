@@ -1203,7 +1203,8 @@ int elg_depth_camera(const ElgMesh* mesh, const ElgCamParams* cam, const float* 
   const size_t in_px = (size_t)cam->width * cam->height, out_px = (size_t)cam->out_width * cam->out_height;
   const size_t smem = 4 * ((in_px > out_px ? in_px : out_px) + (cam->resize ? (size_t)cam->height * cam->out_width : 0));
   if (smem > 200 * 1024) return mfail(ELG_ERR_UNSUPPORTED, "image too large for the fused depth kernel (> 200 KB of shared memory)");
-  static size_t smem_set = 0;
+  static elg::SmemCache smem_cache = {};
+  size_t& smem_set = elg::smem_slot(smem_cache);
   if (smem > 48 * 1024 && smem > smem_set) {
     if (cudaFuncSetAttribute(elg::elg_depth_camera_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(elg::elg_depth_camera_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)

@@ -157,7 +157,8 @@ static int launch_partials(const float* costs_all, int64_t num_main, int32_t num
   if (!costs_all || !partial || (samples_local > 0 && !samples)) return pfail(ELG_ERR_NULL_POINTER, "an MPPI buffer is NULL");
   const size_t smem = 4 * (size_t)(samples_total + (samples_local > 0 ? samples_local : 1));
   if (smem > 200 * 1024) return pfail(ELG_ERR_UNSUPPORTED, "more than 51200 samples (all ranks + local) per main env");
-  static size_t smem_set = 0;
+  static elg::SmemCache smem_cache = {};
+  size_t& smem_set = elg::smem_slot(smem_cache);
   if (smem > 48 * 1024 && smem > smem_set) {
     if (cudaFuncSetAttribute(elg::elg_mppi_partials_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return pfail(ELG_ERR_CUDA, "cannot reserve shared memory for elg_mppi_partials_kernel");

@@ -183,7 +183,8 @@ int elg_integrate_state_velocities(const ElgPlanParams* prm, const ElgPlanBuffer
   if ((reinterpret_cast<uintptr_t>(buf->dof_state) & 7u) != 0) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "dof_state must be 8-byte aligned");
   if (num_rows == 0) return ELG_OK;
   const size_t smem = elg::plan_smem_bytes(prm->num_dof);
-  static size_t smem_set = 0;
+  static elg::SmemCache smem_cache = {};
+  size_t& smem_set = elg::smem_slot(smem_cache);
   if (smem > smem_set) {
     cudaFuncSetAttribute(elg::elg_plan_integrate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     smem_set = smem;

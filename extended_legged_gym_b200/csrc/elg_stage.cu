@@ -1,11 +1,11 @@
-// elg_stage.cu -- SM-issued block copy between pinned (mapped) host memory and device memory.
+// elg_stage.cu -- SM-issued block copy between pinned (mapped) host memory and device memory: a measurement, not the product path.
 //
 // The end-to-end step moves ONE packed block of simulator state in (5.26 MB at 4096 anymal_c envs) and one packed block of
-// observations / rewards / reset flags out.  A cudaMemcpyAsync of that size runs on one copy engine at 32-39 GB/s on these boxes
-// (scripts/h2d_probe.py; 55 GB/s only at 64 MB); this kernel issues the same transfer from the SMs -- thousands of 16-byte
-// (mode 0) or multi-KB TMA (mode 1) reads outstanding over PCIe at once -- so that the link, not the engine's request window, sets
-// the rate.  It IS the host->device copy of the step (device destination in HBM, consumed by the next kernel in the stream), not
-// a zero-copy read by the step kernel.  No reference counterpart (the reference's tensors live where PhysX puts them).
+// observations / rewards / reset flags out.  Question: does a kernel that issues the transfer from the SMs -- thousands of 16-byte
+// (mode 0) or 16 KB TMA (mode 1) reads outstanding over PCIe at once -- beat one copy engine's cudaMemcpyAsync?  Measured on B200
+// (scripts/stage_probe.py, profiles/README.md r2j): copy engine 52.7 GB/s alone / 42.7 GB/s while the copy-out runs; this kernel
+// 49.9 GB/s at every grid size, both modes, and 36-39 GB/s next to the copy-out.  No: the link sets the rate, bench.py keeps the
+// copy engine (and pipelines the copy-in under the previous step instead).  Kept as a probe.  No reference counterpart.
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -96,11 +96,12 @@ int elg_stage_block(void* dst, const void* src, int64_t bytes, int mode, int gri
   cfg.numAttrs = 1;
   if (mode == 1) {
     const int tile = 16 * 1024;
-    static bool set = false;
-    if (!set) {
+    static elg::SmemCache smem_cache = {};
+    size_t& have = elg::smem_slot(smem_cache);
+    if (have == 0) {
       if (cudaFuncSetAttribute(elg::elg_stage_bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, elg::kStageDepth * tile) != cudaSuccess)
         return elg::set_error(ELG_ERR_CUDA, "elg_stage_block: cannot reserve shared memory");
-      set = true;
+      have = (size_t)elg::kStageDepth * tile;
     }
     const int64_t ntiles = (bytes + tile - 1) / tile;
     int g = grid > 0 ? grid : sms;

@@ -991,14 +991,22 @@ int check_launch(const char* what) {
   }
   return ELG_OK;
 }
+int device_index() {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 0;
+  return dev;
+}
 int sm_count() {
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 0;
-    sms = v;
+  static int sms[kMaxDevices] = {};
+  int dev = 0, v = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  const int slot = (dev >= 0 && dev < kMaxDevices) ? dev : 0;
+  if (sms[slot] == 0 || dev != slot) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) return 0;
+    if (dev != slot) return v;
+    sms[slot] = v;
   }
-  return sms;
+  return sms[slot];
 }
 }  // namespace elg
 
@@ -1327,11 +1335,12 @@ int elg_post_physics_step(const ElgDims* dims, const ElgStepParams* prm, const E
   const bool quad = (D == 12 && F == 4);
   auto kern = quad ? elg::elg_step_kernel<12, 4, false> : elg::elg_step_kernel<0, 0, false>;
   const int which = quad ? 1 : 0;
-  static size_t smem_set[3] = {0, 0, 0};
-  if (smem > smem_set[which]) {
+  static elg::SmemCache smem_cache[3] = {};
+  size_t& smem_have = elg::smem_slot(smem_cache[which]);
+  if (smem > smem_have) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
       return fail(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_step_kernel");
-    smem_set[which] = smem;
+    smem_have = smem;
   }
   kern<<<grid, threads, smem, st>>>(*dims, *prm, *buf, L, phase);
   return check_launch("elg_post_physics_step");

@@ -929,13 +929,14 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
 #undef ELG_PICK2
 #undef ELG_PICK
   const int which = ((prm->noise_mode * 2 + (clip ? 1 : 0)) * 2 + (loop ? 1 : 0)) * 2 + (rollout ? 1 : 0);
-  static size_t smem_set[24] = {};
-  if ((size_t)L.bytes > smem_set[which]) {
+  static SmemCache smem_cache[24] = {};
+  size_t& smem_have = smem_slot(smem_cache[which]);
+  if ((size_t)L.bytes > smem_have) {
     if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L.bytes) != cudaSuccess) {
       *rc = set_error(ELG_ERR_CUDA, "cannot reserve dynamic shared memory for elg_step_fast_kernel");
       return 1;
     }
-    smem_set[which] = (size_t)L.bytes;
+    smem_have = (size_t)L.bytes;
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);

@@ -265,10 +265,9 @@ int elg_set_step_debug(long long* device_stamps);
 int elg_probe_empty(int grid, int threads, int smem_bytes, int pdl, void* stream);
 int elg_probe_roundtrip(const void* src, void* dst, int64_t bytes_in_per_cta, int64_t bytes_out_per_cta, int grid, int pdl, void* stream);
 
-/* SM-issued block copy between pinned (mapped) host memory and device memory (csrc/elg_stage.cu; no reference counterpart: the
- * reference's tensors live where PhysX puts them).  The end-to-end step uses it for its ONE packed host->device transfer: thousands of
- * PCIe reads outstanding at once instead of one copy engine's request window.  dst / src / bytes: multiples of 16.  mode 0: 16-byte
- * load / store kernel; mode 1: TMA bulk pieces through shared memory.  grid <= 0: default. */
+/* Probe (csrc/elg_stage.cu; no reference counterpart): SM-issued block copy between pinned (mapped) host memory and device memory,
+ * measured against the copy engine for the end-to-end step's packed transfers (no faster: the PCIe link sets the rate).  dst / src /
+ * bytes: multiples of 16.  mode 0: 16-byte load / store kernel; mode 1: TMA bulk pieces through shared memory.  grid <= 0: default. */
 int elg_stage_block(void* dst, const void* src, int64_t bytes, int mode, int grid, void* stream);
 
 /* LeggedRobot._get_heights (envs/base/legged_robot.py:900-938), standalone. cells_out (optional,
