@@ -362,6 +362,14 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
             e0.record(gs3); g3.replay(); e1.record(gs3)
             torch.cuda.synchronize()
             ts.append(e0.elapsed_time(e1) * 1e-3)
+        # what the all-reduce delivers: the number of resets of ONE timed graph, summed over the ranks (the running totals are
+        # zeroed first: replaying the in-place all-reduce without the reduce() / zero cycle of real use sums the sums)
+        stats3.buf.zero_()
+        gs3.synchronize()
+        if dist:
+            dist.barrier()
+        g3.replay()
+        gs3.synchronize()
     t3 = max_over_ranks(sorted(ts)[2])
     resets3 = float(stats3.buf[L.NUM_REWARD_TERMS])
     out["config3_strong"] = {"workload": f"a1 rough, {total3} envs in total = {n3} per GPU x {world}: {Ks} x (torques, resample, fused step, in-kernel reset) "
@@ -369,7 +377,7 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
                              "value": total3 * Ks / t3, "unit": UNIT, "us_per_step": t3 / Ks * 1e6, "kernels_per_step": 4,
                              "per_gpu_algorithmic_gbs": bytes3 / (t3 / Ks) / 1e9, "frac_of_hbm_peak_per_gpu": bytes3 / (t3 / Ks) / 1e9 / peak,
                              "l2_policy": f"{n_rep3} state replicas x {bytes3 / 1e6:.1f} MB rotated per step", "timing": "CUDA events, max over ranks, median of 5 replays",
-                             "collectives_in_timed_region": 1 if comm is not None else 0, "resets_accumulated_since_start_all_ranks": resets3}
+                             "collectives_in_timed_region": 1 if comm is not None else 0, "resets_in_one_timed_graph_all_ranks": resets3}
     del envs3, g3, stats3
     torch.cuda.empty_cache()
     progress("config 3 done; clone / rollout / MPPI")

@@ -30,6 +30,7 @@
 #include <vector>
 
 #include "elg_common.cuh"
+#include "elg_async.cuh"
 
 struct ElgMesh {
   int32_t num_vertices, num_triangles, num_nodes;
@@ -95,11 +96,10 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
   double t_best = (double)max_t;
   float t_cull = max_t;
   int best_tri = -1;
-  int stack_c[kStack];
-  float stack_t[kStack];
+  // one 8-byte stack entry per node: (child code, entry distance) -- one local store per push, one load per pop
+  int2 stack[kStack];
   int sp = 0;
-  stack_c[sp] = 0;
-  stack_t[sp++] = 0.0f;
+  stack[sp++] = make_int2(0, __float_as_int(0.0f));
   // Warp-coherent "while-while" traversal: every ray still visits its nodes and triangles in exactly its own stack order (so
   // hits are what the one-loop form returns, bit for bit), but the warp alternates between a NODE phase, in which the lanes
   // that are still searching expand inner nodes until they pop a leaf, and a LEAF phase, in which all lanes holding a leaf run
@@ -107,6 +107,10 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
   // (One loop with "leaf or node" per iteration kept 17 of 32 lanes busy on the depth-camera workload.  Leaving the node
   // phase earlier -- while 1/16 ... all of the lanes still search -- was measured and is monotonically slower:
   // depth camera 5.21 Grays/s with this rule, 5.14 / 4.81 / 4.66 / 4.58 / 4.45 at 2 / 4 / 8 / 16 / 32 thirty-seconds.)
+  // The slab planes of two children at a time go through the packed fp32 pipe (FADD2 / FMUL2: one instruction, two individually
+  // rounded results -- the same values as the scalar form): 24 packed instead of 48 scalar instructions per node.
+  const f32x2 nox = pack2(-ox, -ox), noy = pack2(-oy, -oy), noz = pack2(-oz, -oz);
+  const f32x2 ix2 = pack2(ix, ix), iy2 = pack2(iy, iy), iz2 = pack2(iz, iz);
   const unsigned wmask = __activemask();
   int pending = 0;   // leaf code waiting for its triangle tests (leaf codes are negative)
   for (;;) {
@@ -115,30 +119,36 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
       if (!__any_sync(wmask, searching)) break;
       if (!searching) continue;
       --sp;
-      const int code = stack_c[sp];
-      if (stack_t[sp] > t_cull) continue;
+      const int2 top = stack[sp];
+      const int code = top.x;
+      if (__int_as_float(top.y) > t_cull) continue;
       if (code < 0) {
         pending = code;
         continue;
       }
-      const float4* np = nodes + 8 * (size_t)code;
-      const float4 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
+      const ulonglong2* np = reinterpret_cast<const ulonglong2*>(nodes + 8 * (size_t)code);
+      const ulonglong2 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
       const int4 ch = __ldg(reinterpret_cast<const int4*>(np + 6));
+      float ax[4], bx[4], ay[4], by[4], az[4], bz[4];
+      // (lo - o) * inv per plane, children (0, 1) and (2, 3) packed; a - b == a + (-b) exactly
+      unpack2(mul2(add2(lx.x, nox), ix2), ax[0], ax[1]); unpack2(mul2(add2(lx.y, nox), ix2), ax[2], ax[3]);
+      unpack2(mul2(add2(hx.x, nox), ix2), bx[0], bx[1]); unpack2(mul2(add2(hx.y, nox), ix2), bx[2], bx[3]);
+      unpack2(mul2(add2(ly.x, noy), iy2), ay[0], ay[1]); unpack2(mul2(add2(ly.y, noy), iy2), ay[2], ay[3]);
+      unpack2(mul2(add2(hy.x, noy), iy2), by[0], by[1]); unpack2(mul2(add2(hy.y, noy), iy2), by[2], by[3]);
+      unpack2(mul2(add2(lz.x, noz), iz2), az[0], az[1]); unpack2(mul2(add2(lz.y, noz), iz2), az[2], az[3]);
+      unpack2(mul2(add2(hz.x, noz), iz2), bz[0], bz[1]); unpack2(mul2(add2(hz.y, noz), iz2), bz[2], bz[3]);
       float tn[4];
       int cc[4] = {ch.x, ch.y, ch.z, ch.w};
-      const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
-      const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         // slab test; fminf / fmaxf drop the NaN of 0 * inf when the origin lies on a slab plane of an axis-parallel ray
-        const float ax = (lox[c] - ox) * ix, bx = (hix[c] - ox) * ix;
-        const float ay = (loy[c] - oy) * iy, by = (hiy[c] - oy) * iy;
-        const float az = (loz[c] - oz) * iz, bz = (hiz[c] - oz) * iz;
-        const float t0 = fmaxf(fmaxf(fminf(ax, bx), fminf(ay, by)), fmaxf(fminf(az, bz), 0.0f));
-        const float t1 = fminf(fminf(fmaxf(ax, bx), fmaxf(ay, by)), fminf(fmaxf(az, bz), t_cull)) * 1.0000005f;
+        const float t0 = fmaxf(fmaxf(fminf(ax[c], bx[c]), fminf(ay[c], by[c])), fmaxf(fminf(az[c], bz[c]), 0.0f));
+        const float t1 = fminf(fminf(fmaxf(ax[c], bx[c]), fmaxf(ay[c], by[c])), fminf(fmaxf(az[c], bz[c]), t_cull)) * 1.0000005f;
         tn[c] = (cc[c] != kEmpty && t0 <= t1) ? t0 : FLT_MAX;
       }
-      // sort the four children by entry distance (5-comparator network), push far to near
+      // sort the four children by entry distance (5-comparator network), push far to near.  (Measured in SASS: 32-bit keys --
+      // distance bits with the child slot in the two low mantissa bits -- sorted with integer min / max need 10 instructions for
+      // the network but a slot -> child select and a branch per push: 165 instructions per node step against 156 for this form.)
 #define CSWAP(i, j)                                   \
   if (tn[i] > tn[j]) {                                \
     const float tt = tn[i]; tn[i] = tn[j]; tn[j] = tt; \
@@ -148,10 +158,7 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
 #undef CSWAP
 #pragma unroll
       for (int c = 3; c >= 0; --c)
-        if (tn[c] != FLT_MAX && sp < kStack) {
-          stack_c[sp] = cc[c];
-          stack_t[sp++] = tn[c];
-        }
+        if (tn[c] != FLT_MAX && sp < kStack) stack[sp++] = make_int2(cc[c], __float_as_int(tn[c]));
     }
     if (!__any_sync(wmask, pending != 0 || sp > 0)) break;
     if (pending != 0) {   // leaf
