@@ -497,25 +497,32 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
     aenv = Anymal(cfg, None, SyntheticSim(cfg, n_act, dev, spec=spec, height_samples=hf, state=st), dev, True)
     aenv.set_env_state(st)
     gs = torch.cuda.Stream(device=dev)
-    gr = torch.cuda.CUDAGraph()
-    with torch.cuda.stream(gs):
-        aenv._compute_torques(aenv.actions)
-        gs.synchronize()
-        with torch.cuda.graph(gr, stream=gs):
-            for _ in range(50):
-                aenv._compute_torques(aenv.actions)
-        gr.replay()
-        gs.synchronize()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(gs)
-        for _ in range(4):
+
+    def time_act():
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(gs):
+            aenv._compute_torques(aenv.actions)
+            gs.synchronize()
+            with torch.cuda.graph(gr, stream=gs):
+                for _ in range(50):
+                    aenv._compute_torques(aenv.actions)
             gr.replay()
-        e1.record(gs)
-        gs.synchronize()
-    sec = e0.elapsed_time(e1) * 1e-3 / 200
+            gs.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(gs)
+            for _ in range(4):
+                gr.replay()
+            e1.record(gs)
+            gs.synchronize()
+        return e0.elapsed_time(e1) * 1e-3 / 200
+    sec = time_act()                       # default: the bound blob's weights come from the constant bank
+    lib.elg_set_actuator_tuning(2)
+    sec_smem = time_act()                  # weights staged in shared memory (round 1's form)
+    lib.elg_set_actuator_tuning(0)
     act_bytes = n_act * 12 * (2 * 2 * 8 * 4 * 2 + 8 + 4 + 4)        # 4 state planes of 8 floats in + out, dof pos/vel, action, torque
     out["actuator_net"] = {"workload": f"{n_act} envs x 12 dofs, LSTMsea (2 -> 8 x 2 layers -> 1) per row, state in place", "us_per_call": sec * 1e6,
                            "bytes_per_call": act_bytes, "achieved_gbs": act_bytes / sec / 1e9, "frac_of_hbm_peak": act_bytes / sec / 1e9 / peak,
+                           "us_per_call_weights_in_shared_memory": sec_smem * 1e6,
                            "note": "CUDA graph of 50 calls on one state (13.6 MB, L2 resident)"}
     del aenv
     # caller-side fusion: EmpiricalNormalization (training) + write into the rollout-storage slot + reward / done columns

@@ -19,10 +19,17 @@ constexpr int kActThreads = 64;
 // 1 / (1 + e^-x): the correctly rounded reciprocal IS the IEEE quotient 1.0f / y, without the general division sequence
 __device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + expf(-x)); }
 
-// one LSTM cell step for one row; torch gate order i, f, g, o (rows u, 8 + u, 16 + u, 24 + u)
-template <int kIn>
-__device__ __forceinline__ void lstm_cell(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
-                                          const float* __restrict__ b_hh, const float (&x)[kIn], float (&h)[8], float (&c)[8]) {
+// The 973 parameters of the bound network (elg_actuator_net_bind) in the constant bank: every weight is a warp-uniform operand
+// with a compile-time offset, i.e. an immediate constant-bank operand of the FFMA itself -- no shared-memory load, no register.
+__constant__ float c_actw[ELG_ACTNET_WORDS];
+
+// weight word i: constant bank (kConst) or the CTA's shared-memory copy
+template <bool kConst>
+__device__ __forceinline__ float actw(const float* __restrict__ s_w, int i) { return kConst ? c_actw[i] : s_w[i]; }
+
+// one LSTM cell step for one row; torch gate order i, f, g, o (rows u, 8 + u, 16 + u, 24 + u); offsets are words of the blob
+template <int kIn, bool kConst, int kWih, int kWhh, int kBih, int kBhh>
+__device__ __forceinline__ void lstm_cell(const float* __restrict__ s_w, const float (&x)[kIn], float (&h)[8], float (&c)[8]) {
   float hn[8];
 #pragma unroll
   for (int u = 0; u < 8; ++u) {
@@ -30,12 +37,12 @@ __device__ __forceinline__ void lstm_cell(const float* __restrict__ w_ih, const 
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int r = 8 * q + u;
-      float a = b_ih[r];
+      float a = actw<kConst>(s_w, kBih + r);
 #pragma unroll
-      for (int k = 0; k < kIn; ++k) a = fmaf(w_ih[r * kIn + k], x[k], a);
-      float b = b_hh[r];
+      for (int k = 0; k < kIn; ++k) a = fmaf(actw<kConst>(s_w, kWih + r * kIn + k), x[k], a);
+      float b = actw<kConst>(s_w, kBhh + r);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) b = fmaf(w_hh[r * 8 + k], h[k], b);
+      for (int k = 0; k < 8; ++k) b = fmaf(actw<kConst>(s_w, kWhh + r * 8 + k), h[k], b);
       g[q] = a + b;
     }
     const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanhf(g[2]), og = sigmoid_f(g[3]);
@@ -46,23 +53,26 @@ __device__ __forceinline__ void lstm_cell(const float* __restrict__ w_ih, const 
   for (int u = 0; u < 8; ++u) h[u] = hn[u];
 }
 
+template <bool kConst>
 __global__ void __launch_bounds__(kActThreads)
 elg_actuator_kernel(const int64_t rows, const int D, const float action_scale, const float* __restrict__ weights,
                     const float* __restrict__ actions, const float* __restrict__ dof_state, const float* __restrict__ default_dof_pos,
                     float* __restrict__ hidden, float* __restrict__ cell, float* __restrict__ torques) {
-  __shared__ __align__(16) float s_w[ELG_ACTNET_WORDS];
+  __shared__ __align__(16) float s_w[kConst ? 4 : ELG_ACTNET_WORDS];
   pdl_launch_dependents();
   pdl_wait();
-  for (int i = threadIdx.x; i < ELG_ACTNET_WORDS / 4; i += kActThreads)
-    reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
-  __syncthreads();
+  if (!kConst) {
+    for (int i = threadIdx.x; i < ELG_ACTNET_WORDS / 4; i += kActThreads)
+      reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
+    __syncthreads();
+  }
   const int64_t r = (int64_t)blockIdx.x * kActThreads + threadIdx.x;
   if (r >= rows) return;
   const int j = (int)(r % D);
   const float2 pv = *reinterpret_cast<const float2*>(dof_state + 2 * r);
   float x[2];
-  x[0] = (actions[r] * action_scale + __ldg(default_dof_pos + j) - pv.x) * s_w[ELG_ACTNET_IN_SCALE];
-  x[1] = pv.y * s_w[ELG_ACTNET_IN_SCALE + 1];
+  x[0] = (actions[r] * action_scale + __ldg(default_dof_pos + j) - pv.x) * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE);
+  x[1] = pv.y * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE + 1);
   float h0[8], c0[8], h1[8], c1[8];
   auto load8 = [&](const float* base, float (&v)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(base), b = *reinterpret_cast<const float4*>(base + 4);
@@ -77,12 +87,12 @@ elg_actuator_kernel(const int64_t rows, const int D, const float action_scale, c
   load8(cell + r * 8, c0);
   load8(hidden + plane + r * 8, h1);
   load8(cell + plane + r * 8, c1);
-  lstm_cell<2>(s_w + ELG_ACTNET_W_IH0, s_w + ELG_ACTNET_W_HH0, s_w + ELG_ACTNET_B_IH0, s_w + ELG_ACTNET_B_HH0, x, h0, c0);
-  lstm_cell<8>(s_w + ELG_ACTNET_W_IH1, s_w + ELG_ACTNET_W_HH1, s_w + ELG_ACTNET_B_IH1, s_w + ELG_ACTNET_B_HH1, h0, h1, c1);
-  float y = s_w[ELG_ACTNET_B_LIN];
+  lstm_cell<2, kConst, ELG_ACTNET_W_IH0, ELG_ACTNET_W_HH0, ELG_ACTNET_B_IH0, ELG_ACTNET_B_HH0>(s_w, x, h0, c0);
+  lstm_cell<8, kConst, ELG_ACTNET_W_IH1, ELG_ACTNET_W_HH1, ELG_ACTNET_B_IH1, ELG_ACTNET_B_HH1>(s_w, h0, h1, c1);
+  float y = actw<kConst>(s_w, ELG_ACTNET_B_LIN);
 #pragma unroll
-  for (int k = 0; k < 8; ++k) y = fmaf(s_w[ELG_ACTNET_W_LIN + k], h1[k], y);
-  torques[r] = s_w[ELG_ACTNET_OUT_SCALE] * y;
+  for (int k = 0; k < 8; ++k) y = fmaf(actw<kConst>(s_w, ELG_ACTNET_W_LIN + k), h1[k], y);
+  torques[r] = actw<kConst>(s_w, ELG_ACTNET_OUT_SCALE) * y;
   store8(hidden + r * 8, h0);
   store8(cell + r * 8, c0);
   store8(hidden + plane + r * 8, h1);
@@ -181,6 +191,7 @@ elg_actuator_unit_kernel(const int64_t rows, const int D, const float action_sca
 // 13.5 us -- with eight distinct units per warp every weight load from shared memory serves 4 rows instead of 32, and the kernel
 // turns LDS-bound; the row-per-thread form stays the product path, this one stays selectable for larger networks.
 int g_act_mode = 0;
+const float* g_act_bound[kMaxDevices] = {};   // the device blob whose contents sit in this device's constant bank
 
 }  // namespace elg
 
@@ -189,8 +200,20 @@ extern "C" {
 int elg_actuator_net_words(void) { return ELG_ACTNET_WORDS; }
 
 int elg_set_actuator_tuning(int mode) {
-  if (mode < 0 || mode > 1) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "actuator tuning mode must be 0 or 1");
+  if (mode < 0 || mode > 2) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "actuator tuning mode must be 0, 1 or 2");
   elg::g_act_mode = mode;
+  return ELG_OK;
+}
+
+int elg_actuator_net_bind(const float* weights, void* stream) {
+  if (!weights) {      // unbind: the next calls read the weights through shared memory again
+    elg::g_act_bound[elg::device_index()] = nullptr;
+    return ELG_OK;
+  }
+  if ((reinterpret_cast<uintptr_t>(weights) & 15u) != 0) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "actuator net: weights must be 16-byte aligned");
+  if (cudaMemcpyToSymbolAsync(elg::c_actw, weights, sizeof(float) * ELG_ACTNET_WORDS, 0, cudaMemcpyDeviceToDevice, (cudaStream_t)stream) != cudaSuccess)
+    return elg::check_launch("elg_actuator_net_bind");
+  elg::g_act_bound[elg::device_index()] = weights;
   return ELG_OK;
 }
 
@@ -220,8 +243,11 @@ int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float ac
   if (unit)
     cudaLaunchKernelEx(&cfg, elg::elg_actuator_unit_kernel, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
                        hidden, cell, torques);
+  else if (elg::g_act_bound[elg::device_index()] == weights && elg::g_act_mode != 2)
+    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<true>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
+                       hidden, cell, torques);
   else
-    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
+    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<false>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
                        hidden, cell, torques);
   return elg::check_launch("elg_actuator_net_torques");
 }

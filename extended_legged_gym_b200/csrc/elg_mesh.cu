@@ -418,7 +418,7 @@ elg_camera_pose_kernel(const float* __restrict__ pos, const float* __restrict__ 
 // reference's per-env Python loop (:486-499).  28 bytes per camera in, 4 bytes per output pixel out.
 // ---------------------------------------------------------------------------------------------
 template <bool kGrid>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 elg_depth_camera_kernel(const GridView gv, const float4* __restrict__ nodes, const float4* __restrict__ tris, const __grid_constant__ ElgCamParams cp,
                         const float* __restrict__ ray_dirs, const float* __restrict__ cam_pos, const float* __restrict__ cam_rot,
                         const int64_t* __restrict__ ep_len, const float* __restrict__ noise_u, const int32_t* __restrict__ rx_start,

@@ -56,6 +56,10 @@ class Anymal(LeggedRobot):
         self.actuator_net_blob = None
         if self.cfg.control.use_actuator_network:
             self.actuator_net_blob = self._pack_actuator_net(load_actuator_net_weights(self.cfg.control))
+            # the parameters never change after this: keep them in the constant bank (immediate operands of the kernel's FMAs)
+            with torch.cuda.device(self.device):
+                _lib.check(self._lib.elg_actuator_net_bind(self.actuator_net_blob.data_ptr(), torch.cuda.current_stream(self.device).cuda_stream),
+                           "elg_actuator_net_bind")
         # gait scheduler (anymal.py:60-77): period 0.6 s, trot phases, 0.15 m swing height -- state lives in two env buffers,
         # the update and the foot-z tracking reward run inside the step kernel
         self.gait_cfg = SimpleNamespace(dt=self.dt, period=0.6, foot_phases=[0.0, 0.5, 0.5, 0.0], swing_height=0.15)

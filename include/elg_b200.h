@@ -497,7 +497,11 @@ enum {
 int elg_actuator_net_words(void);
 /* Diagnostic (no reference counterpart): 0 = one thread per (env, dof) row (default), 1 = eight lanes per row, one hidden unit each
  * (bit-identical results, 8x the threads; measured slower on B200 at the BASELINE sizes: shared-memory weight traffic). */
-int elg_set_actuator_tuning(int mode);
+int elg_set_actuator_tuning(int mode);   /* (2: row-per-thread kernel with the weights in shared memory even when a blob is bound) */
+/* Optional: copy the blob into the device's constant bank (stream-ordered).  Calls of elg_actuator_net_torques that pass the SAME
+ * `weights` pointer afterwards read every weight as an immediate constant operand instead of a shared-memory load; call it again after
+ * changing the blob's contents, or with NULL to unbind.  One bound blob per device. */
+int elg_actuator_net_bind(const float* weights, void* stream);
 int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float action_scale, const float* actions, const float* dof_state,
                              const float* default_dof_pos, float* hidden, float* cell, float* torques, void* stream);
 
