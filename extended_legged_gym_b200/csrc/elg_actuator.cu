@@ -187,6 +187,102 @@ elg_actuator_unit_kernel(const int64_t rows, const int D, const float action_sca
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// unit-split form: FOUR WARPS per 32 rows, warp p owns hidden units 2p, 2p + 1 of both layers of the rows lane = row.  Every weight
+// a warp touches is still warp-uniform (constant bank through the uniform datapath, or a shared-memory broadcast), nothing is computed
+// twice, and the chip holds 4x the warps of the row-per-thread form -- which sits at 10 warps per SM with a ~3000-instruction
+// dependent chain each.  The 8-vectors a unit needs from the other warps (layer-0 output, layer-1 output) cross through shared
+// memory ([unit][row]: conflict-free) at two CTA barriers.  Same expressions per unit as lstm_cell: bit-identical results.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int kSplitParts = 4, kSplitUnits = 8 / kSplitParts;
+
+template <int kIn, bool kConst>
+__device__ __forceinline__ void lstm_units(const float* __restrict__ s_w, const int wih, const int whh, const int bih, const int bhh, const int u0,
+                                           const float (&x)[kIn], const float (&h)[8], float (&c)[kSplitUnits], float (&hn)[kSplitUnits]) {
+#pragma unroll
+  for (int uu = 0; uu < kSplitUnits; ++uu) {
+    const int u = u0 + uu;      // warp-uniform
+    float g[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int r = 8 * q + u;
+      float a = actw<kConst>(s_w, bih + r);
+#pragma unroll
+      for (int k = 0; k < kIn; ++k) a = fmaf(actw<kConst>(s_w, wih + r * kIn + k), x[k], a);
+      float b = actw<kConst>(s_w, bhh + r);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) b = fmaf(actw<kConst>(s_w, whh + r * 8 + k), h[k], b);
+      g[q] = a + b;
+    }
+    const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanhf(g[2]), og = sigmoid_f(g[3]);
+    c[uu] = fg * c[uu] + ig * gg;
+    hn[uu] = og * tanhf(c[uu]);
+  }
+}
+
+template <bool kConst>
+__global__ void __launch_bounds__(32 * kSplitParts)
+elg_actuator_split_kernel(const int64_t rows, const int D, const float action_scale, const float* __restrict__ weights,
+                          const float* __restrict__ actions, const float* __restrict__ dof_state, const float* __restrict__ default_dof_pos,
+                          float* __restrict__ hidden, float* __restrict__ cell, float* __restrict__ torques) {
+  __shared__ __align__(16) float s_w[kConst ? 4 : ELG_ACTNET_WORDS];
+  __shared__ float s_h[2][8][32];      // new layer-0 / layer-1 outputs, [unit][row]
+  pdl_launch_dependents();
+  pdl_wait();
+  if (!kConst)
+    for (int i = threadIdx.x; i < ELG_ACTNET_WORDS / 4; i += 32 * kSplitParts)
+      reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
+  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5, u0 = part * kSplitUnits;
+  const int64_t r = (int64_t)blockIdx.x * 32 + lane;
+  const bool live = r < rows;
+  const int64_t rr = live ? r : rows - 1;      // surplus lanes shadow the last row (loads stay in range, stores are guarded)
+  const int64_t plane = rows * 8;              // layer stride of the [2, rows, 8] state tensors
+  auto load8 = [&](const float* base, float (&v)[8]) {
+    const float4 a = *reinterpret_cast<const float4*>(base), b = *reinterpret_cast<const float4*>(base + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+  };
+  float h0[8], h1[8], c0[kSplitUnits], c1[kSplitUnits];
+  load8(hidden + rr * 8, h0);
+  load8(hidden + plane + rr * 8, h1);
+  {
+    const float2 a = *reinterpret_cast<const float2*>(cell + rr * 8 + u0), b = *reinterpret_cast<const float2*>(cell + plane + rr * 8 + u0);
+    c0[0] = a.x; c0[1] = a.y; c1[0] = b.x; c1[1] = b.y;
+  }
+  const int j = (int)(rr % D);
+  const float2 pv = *reinterpret_cast<const float2*>(dof_state + 2 * rr);
+  const float act = actions[rr], q0 = __ldg(default_dof_pos + j);
+  if (!kConst) __syncthreads();      // the weights
+  float x[2];
+  x[0] = (act * action_scale + q0 - pv.x) * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE);
+  x[1] = pv.y * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE + 1);
+  float hn[kSplitUnits];
+  lstm_units<2, kConst>(s_w, ELG_ACTNET_W_IH0, ELG_ACTNET_W_HH0, ELG_ACTNET_B_IH0, ELG_ACTNET_B_HH0, u0, x, h0, c0, hn);
+  s_h[0][u0][lane] = hn[0];
+  s_h[0][u0 + 1][lane] = hn[1];
+  if (live) {
+    *reinterpret_cast<float2*>(hidden + r * 8 + u0) = make_float2(hn[0], hn[1]);
+    *reinterpret_cast<float2*>(cell + r * 8 + u0) = make_float2(c0[0], c0[1]);
+  }
+  __syncthreads();
+  float x1[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x1[k] = s_h[0][k][lane];
+  lstm_units<8, kConst>(s_w, ELG_ACTNET_W_IH1, ELG_ACTNET_W_HH1, ELG_ACTNET_B_IH1, ELG_ACTNET_B_HH1, u0, x1, h1, c1, hn);
+  s_h[1][u0][lane] = hn[0];
+  s_h[1][u0 + 1][lane] = hn[1];
+  if (live) {
+    *reinterpret_cast<float2*>(hidden + plane + r * 8 + u0) = make_float2(hn[0], hn[1]);
+    *reinterpret_cast<float2*>(cell + plane + r * 8 + u0) = make_float2(c1[0], c1[1]);
+  }
+  __syncthreads();
+  if (part == 0 && live) {
+    float y = actw<kConst>(s_w, ELG_ACTNET_B_LIN);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) y = fmaf(actw<kConst>(s_w, ELG_ACTNET_W_LIN + k), s_h[1][k][lane], y);
+    torques[r] = actw<kConst>(s_w, ELG_ACTNET_OUT_SCALE) * y;
+  }
+}
+
 // 0: one thread per row (default), 1: eight lanes per row.  Measured on B200 at 4096 envs x 12 dofs (profiles/README.md r2): 10.9 us vs
 // 13.5 us -- with eight distinct units per warp every weight load from shared memory serves 4 rows instead of 32, and the kernel
 // turns LDS-bound; the row-per-thread form stays the product path, this one stays selectable for larger networks.
@@ -200,7 +296,7 @@ extern "C" {
 int elg_actuator_net_words(void) { return ELG_ACTNET_WORDS; }
 
 int elg_set_actuator_tuning(int mode) {
-  if (mode < 0 || mode > 2) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "actuator tuning mode must be 0, 1 or 2");
+  if (mode < 0 || mode > 4) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "actuator tuning mode must be 0 ... 4");
   elg::g_act_mode = mode;
   return ELG_OK;
 }
@@ -229,8 +325,10 @@ int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float ac
   const int64_t rows = (int64_t)dims->num_envs * dims->num_dof;
   if (rows == 0) return ELG_OK;
   const bool unit = elg::g_act_mode == 1;
-  const int threads = unit ? elg::kAct8Threads : elg::kActThreads;
-  const int64_t nthreads = unit ? rows * 8 : rows;
+  const bool split = elg::g_act_mode == 0 || elg::g_act_mode == 4;      // default
+  const int threads = unit ? elg::kAct8Threads : split ? 32 * elg::kSplitParts : elg::kActThreads;
+  const int64_t nthreads = unit ? rows * 8 : split ? ((rows + 31) / 32) * 32 * elg::kSplitParts : rows;
+  const bool bound = elg::g_act_bound[elg::device_index()] == weights;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)((nthreads + threads - 1) / threads));
   cfg.blockDim = dim3(threads);
@@ -243,7 +341,13 @@ int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float ac
   if (unit)
     cudaLaunchKernelEx(&cfg, elg::elg_actuator_unit_kernel, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
                        hidden, cell, torques);
-  else if (elg::g_act_bound[elg::device_index()] == weights && elg::g_act_mode != 2)
+  else if (split && bound && elg::g_act_mode != 4)
+    cudaLaunchKernelEx(&cfg, elg::elg_actuator_split_kernel<true>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
+                       hidden, cell, torques);
+  else if (split)
+    cudaLaunchKernelEx(&cfg, elg::elg_actuator_split_kernel<false>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
+                       hidden, cell, torques);
+  else if (bound && elg::g_act_mode != 2)
     cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<true>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
                        hidden, cell, torques);
   else

@@ -495,9 +495,11 @@ enum {
   ELG_ACTNET_WORDS = ELG_ACTNET_B_LIN + 4
 };
 int elg_actuator_net_words(void);
-/* Diagnostic (no reference counterpart): 0 = one thread per (env, dof) row (default), 1 = eight lanes per row, one hidden unit each
- * (bit-identical results, 8x the threads; measured slower on B200 at the BASELINE sizes: shared-memory weight traffic). */
-int elg_set_actuator_tuning(int mode);   /* (2: row-per-thread kernel with the weights in shared memory even when a blob is bound) */
+/* Kernel selection (no reference counterpart; every form returns bit-identical results): 0 (default) = four warps per 32 rows, two
+ * hidden units per warp, weights warp-uniform; 1 = eight lanes per row, one hidden unit each (measured slower: shared-memory weight
+ * traffic); 2 / 3 = one thread per (env, dof) row with the weights in shared memory / the constant bank when bound (round 1's form);
+ * 4 = form 0 with the weights in shared memory even when a blob is bound. */
+int elg_set_actuator_tuning(int mode);
 /* Optional: copy the blob into the device's constant bank (stream-ordered).  Calls of elg_actuator_net_torques that pass the SAME
  * `weights` pointer afterwards read every weight as an immediate constant operand instead of a shared-memory load; call it again after
  * changing the blob's contents, or with NULL to unbind.  One bound blob per device. */

@@ -120,6 +120,33 @@ def test_actuator_kernel_matches_golden_vectors():
 
 
 @pytest.mark.gpu
+def test_every_kernel_form_returns_the_same_bits():
+    """elg_set_actuator_tuning: the unit-split default (constant-bank / shared-memory weights), eight lanes per row and the
+    row-per-thread forms evaluate the same expressions per hidden unit -- torques and states must agree bit for bit"""
+    n = 1000
+    env, cfg, spec, st, hf = make_anymal("anymal_c_rough", n, 5)
+    g = torch.Generator().manual_seed(9)
+    h = (torch.randn(2, n * 12, 8, generator=g) * 0.5).to(DEV)
+    c = torch.randn(2, n * 12, 8, generator=g).to(DEV)
+    a = (torch.randn(n, 12, generator=g) * 2).to(DEV)
+    lib = _lib.load()
+    outs = []
+    try:
+        for mode in (0, 1, 2, 3, 4):
+            lib.elg_set_actuator_tuning(mode)
+            env.sea_hidden_state.copy_(h)
+            env.sea_cell_state.copy_(c)
+            t = env._compute_torques(a).clone()
+            torch.cuda.synchronize()
+            outs.append((t, env.sea_hidden_state.clone(), env.sea_cell_state.clone()))
+    finally:
+        lib.elg_set_actuator_tuning(0)
+    for mode, o in enumerate(outs[1:], start=1):
+        for x, y, what in zip(outs[0], o, ("torques", "hidden", "cell")):
+            assert torch.equal(x, y), f"actuator kernel form {mode} differs from the default in {what}"
+
+
+@pytest.mark.gpu
 @pytest.mark.parametrize("n", [1, 37, 4096])
 def test_actuator_kernel_matches_oracle_ragged_and_full_size(n):
     w, _, _, _ = golden()
