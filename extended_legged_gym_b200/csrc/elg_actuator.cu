@@ -196,12 +196,14 @@ elg_actuator_unit_kernel(const int64_t rows, const int D, const float action_sca
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSplitParts = 4, kSplitUnits = 8 / kSplitParts;
 
-template <int kIn, bool kConst>
-__device__ __forceinline__ void lstm_units(const float* __restrict__ s_w, const int wih, const int whh, const int bih, const int bhh, const int u0,
-                                           const float (&x)[kIn], const float (&h)[8], float (&c)[kSplitUnits], float (&hn)[kSplitUnits]) {
+template <int kIn, bool kConst, int kU0, int kWih, int kWhh, int kBih, int kBhh>
+__device__ __forceinline__ void lstm_units(const float* __restrict__ s_w, const float (&x)[kIn], const float (&h)[8], float (&c)[kSplitUnits],
+                                           float (&hn)[kSplitUnits]) {
+  constexpr int wih = kWih, whh = kWhh, bih = kBih, bhh = kBhh;
 #pragma unroll
   for (int uu = 0; uu < kSplitUnits; ++uu) {
-    const int u = u0 + uu;      // warp-uniform
+    constexpr int u0 = kU0;
+    const int u = u0 + uu;      // compile-time after unrolling: every weight offset is an immediate
     float g[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
@@ -220,19 +222,14 @@ __device__ __forceinline__ void lstm_units(const float* __restrict__ s_w, const 
   }
 }
 
-template <bool kConst>
-__global__ void __launch_bounds__(32 * kSplitParts)
-elg_actuator_split_kernel(const int64_t rows, const int D, const float action_scale, const float* __restrict__ weights,
-                          const float* __restrict__ actions, const float* __restrict__ dof_state, const float* __restrict__ default_dof_pos,
-                          float* __restrict__ hidden, float* __restrict__ cell, float* __restrict__ torques) {
-  __shared__ __align__(16) float s_w[kConst ? 4 : ELG_ACTNET_WORDS];
-  __shared__ float s_h[2][8][32];      // new layer-0 / layer-1 outputs, [unit][row]
-  pdl_launch_dependents();
-  pdl_wait();
-  if (!kConst)
-    for (int i = threadIdx.x; i < ELG_ACTNET_WORDS / 4; i += 32 * kSplitParts)
-      reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
-  const int lane = threadIdx.x & 31, part = threadIdx.x >> 5, u0 = part * kSplitUnits;
+// everything a warp does once its part is known at compile time (the kernel dispatches on the warp index: four instantiations, each
+// warp runs one; the CTA barriers inside are the same two in every instantiation)
+template <bool kConst, int kPart>
+__device__ __forceinline__ void split_body(const float* __restrict__ s_w, float (*s_h)[8][32], const int lane, const int64_t rows, const int D,
+                                           const float action_scale, const float* __restrict__ actions, const float* __restrict__ dof_state,
+                                           const float* __restrict__ default_dof_pos, float* __restrict__ hidden, float* __restrict__ cell,
+                                           float* __restrict__ torques) {
+  constexpr int u0 = kPart * kSplitUnits;
   const int64_t r = (int64_t)blockIdx.x * 32 + lane;
   const bool live = r < rows;
   const int64_t rr = live ? r : rows - 1;      // surplus lanes shadow the last row (loads stay in range, stores are guarded)
@@ -256,7 +253,7 @@ elg_actuator_split_kernel(const int64_t rows, const int D, const float action_sc
   x[0] = (act * action_scale + q0 - pv.x) * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE);
   x[1] = pv.y * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE + 1);
   float hn[kSplitUnits];
-  lstm_units<2, kConst>(s_w, ELG_ACTNET_W_IH0, ELG_ACTNET_W_HH0, ELG_ACTNET_B_IH0, ELG_ACTNET_B_HH0, u0, x, h0, c0, hn);
+  lstm_units<2, kConst, u0, ELG_ACTNET_W_IH0, ELG_ACTNET_W_HH0, ELG_ACTNET_B_IH0, ELG_ACTNET_B_HH0>(s_w, x, h0, c0, hn);
   s_h[0][u0][lane] = hn[0];
   s_h[0][u0 + 1][lane] = hn[1];
   if (live) {
@@ -267,7 +264,7 @@ elg_actuator_split_kernel(const int64_t rows, const int D, const float action_sc
   float x1[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) x1[k] = s_h[0][k][lane];
-  lstm_units<8, kConst>(s_w, ELG_ACTNET_W_IH1, ELG_ACTNET_W_HH1, ELG_ACTNET_B_IH1, ELG_ACTNET_B_HH1, u0, x1, h1, c1, hn);
+  lstm_units<8, kConst, u0, ELG_ACTNET_W_IH1, ELG_ACTNET_W_HH1, ELG_ACTNET_B_IH1, ELG_ACTNET_B_HH1>(s_w, x1, h1, c1, hn);
   s_h[1][u0][lane] = hn[0];
   s_h[1][u0 + 1][lane] = hn[1];
   if (live) {
@@ -275,11 +272,33 @@ elg_actuator_split_kernel(const int64_t rows, const int D, const float action_sc
     *reinterpret_cast<float2*>(cell + plane + r * 8 + u0) = make_float2(c1[0], c1[1]);
   }
   __syncthreads();
-  if (part == 0 && live) {
+  if (kPart == 0 && live) {
     float y = actw<kConst>(s_w, ELG_ACTNET_B_LIN);
 #pragma unroll
     for (int k = 0; k < 8; ++k) y = fmaf(actw<kConst>(s_w, ELG_ACTNET_W_LIN + k), s_h[1][k][lane], y);
     torques[r] = actw<kConst>(s_w, ELG_ACTNET_OUT_SCALE) * y;
+  }
+}
+
+template <bool kConst>
+__global__ void __launch_bounds__(32 * kSplitParts)
+elg_actuator_split_kernel(const int64_t rows, const int D, const float action_scale, const float* __restrict__ weights,
+                          const float* __restrict__ actions, const float* __restrict__ dof_state, const float* __restrict__ default_dof_pos,
+                          float* __restrict__ hidden, float* __restrict__ cell, float* __restrict__ torques) {
+  __shared__ __align__(16) float s_w[kConst ? 4 : ELG_ACTNET_WORDS];
+  __shared__ float s_h[2][8][32];      // new layer-0 / layer-1 outputs, [unit][row]
+  pdl_launch_dependents();
+  pdl_wait();
+  if (!kConst)
+    for (int i = threadIdx.x; i < ELG_ACTNET_WORDS / 4; i += 32 * kSplitParts)
+      reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
+  const int lane = threadIdx.x & 31;
+  static_assert(kSplitParts == 4, "the dispatch below lists four parts");
+  switch (threadIdx.x >> 5) {
+    case 0: split_body<kConst, 0>(s_w, s_h, lane, rows, D, action_scale, actions, dof_state, default_dof_pos, hidden, cell, torques); break;
+    case 1: split_body<kConst, 1>(s_w, s_h, lane, rows, D, action_scale, actions, dof_state, default_dof_pos, hidden, cell, torques); break;
+    case 2: split_body<kConst, 2>(s_w, s_h, lane, rows, D, action_scale, actions, dof_state, default_dof_pos, hidden, cell, torques); break;
+    default: split_body<kConst, 3>(s_w, s_h, lane, rows, D, action_scale, actions, dof_state, default_dof_pos, hidden, cell, torques); break;
   }
 }
 
