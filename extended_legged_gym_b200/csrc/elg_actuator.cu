@@ -188,10 +188,12 @@ elg_actuator_unit_kernel(const int64_t rows, const int D, const float action_sca
 }
 
 // ---------------------------------------------------------------------------------------------------------------
-// unit-split form: FOUR WARPS per 32 rows, warp p owns hidden units 2p, 2p + 1 of both layers of the rows lane = row.  Every weight
-// a warp touches is still warp-uniform (constant bank through the uniform datapath, or a shared-memory broadcast), nothing is computed
-// twice, and the chip holds 4x the warps of the row-per-thread form -- which sits at 10 warps per SM with a ~3000-instruction
-// dependent chain each.  The 8-vectors a unit needs from the other warps (layer-0 output, layer-1 output) cross through shared
+// unit-split form (measured, not the default): FOUR WARPS per 32 rows, warp p owns hidden units 2p, 2p + 1 of both layers of the rows
+// lane = row.  Every weight a warp touches is still warp-uniform (constant bank through the uniform datapath, or a shared-memory
+// broadcast), nothing is computed twice, and the chip holds 4x the warps of the row-per-thread form -- which sits at 10 warps per SM
+// with a ~3000-instruction dependent chain each.  On B200 at 4096 envs x 12 dofs it takes 11.6 us against 10.5-10.8 us for the
+// row-per-thread form with the same constant-bank weights (profiles/README.md r2x): the extra warps buy nothing, the redundant state
+// loads, two CTA barriers and four code copies cost a little.  The 8-vectors a unit needs from the other warps (layer-0 output, layer-1 output) cross through shared
 // memory ([unit][row]: conflict-free) at two CTA barriers.  Same expressions per unit as lstm_cell: bit-identical results.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kSplitParts = 4, kSplitUnits = 8 / kSplitParts;
@@ -302,7 +304,8 @@ elg_actuator_split_kernel(const int64_t rows, const int D, const float action_sc
   }
 }
 
-// 0: one thread per row (default), 1: eight lanes per row.  Measured on B200 at 4096 envs x 12 dofs (profiles/README.md r2): 10.9 us vs
+// 0: one thread per row, weights from the constant bank when bound (default); 2: the same with shared-memory weights; 3 / 4: the
+// unit-split form (constant bank / shared memory); 1: eight lanes per row.  Measured on B200 at 4096 envs x 12 dofs (profiles/README.md r2): 10.9 us vs
 // 13.5 us -- with eight distinct units per warp every weight load from shared memory serves 4 rows instead of 32, and the kernel
 // turns LDS-bound; the row-per-thread form stays the product path, this one stays selectable for larger networks.
 int g_act_mode = 0;
@@ -344,7 +347,7 @@ int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float ac
   const int64_t rows = (int64_t)dims->num_envs * dims->num_dof;
   if (rows == 0) return ELG_OK;
   const bool unit = elg::g_act_mode == 1;
-  const bool split = elg::g_act_mode == 0 || elg::g_act_mode == 4;      // default
+  const bool split = elg::g_act_mode == 3 || elg::g_act_mode == 4;
   const int threads = unit ? elg::kAct8Threads : split ? 32 * elg::kSplitParts : elg::kActThreads;
   const int64_t nthreads = unit ? rows * 8 : split ? ((rows + 31) / 32) * 32 * elg::kSplitParts : rows;
   const bool bound = elg::g_act_bound[elg::device_index()] == weights;
