@@ -231,3 +231,97 @@ def sdf_query(points, max_distance, vertices, triangles, epsilon=1.0e-3, chunk=1
         closest[s:s + chunk] = np.where(hit[:, None], q[ar, k], 0.0).astype(np.float32)
         face[s:s + chunk] = np.where(hit, k, -1)
     return sdf, grad, closest, face
+
+
+# ----------------------------------------------------------------------------------------------
+# the sign rule Warp documents for mesh_query_point_sign_normal, restated for COMPARISON with the rule above
+# (tests/test_sdf_sign_rule.py): angle-weighted pseudo-normal of the closest feature (Baerentzen & Aanaes 2005) --
+# face interior: the face normal; edge: sum of the unit normals of the faces sharing it; vertex: sum over the incident
+# faces of (interior angle at the vertex) x (unit normal).  Not used by the product path or by the parity tests.
+# ----------------------------------------------------------------------------------------------
+def torus_mesh(major=1.0, minor=0.4, nu=24, nv=12):
+    """closed manifold torus around the z axis: its inner ring is made of saddle vertices and saddle edges"""
+    u = np.arange(nu) * (2 * np.pi / nu)
+    w = np.arange(nv) * (2 * np.pi / nv)
+    uu, ww = np.meshgrid(u, w, indexing="ij")
+    v = np.stack([(major + minor * np.cos(ww)) * np.cos(uu), (major + minor * np.cos(ww)) * np.sin(uu), minor * np.sin(ww)], axis=-1)
+    idx = np.arange(nu * nv).reshape(nu, nv)
+    a, b = idx, np.roll(idx, -1, axis=0)
+    c, d = np.roll(idx, -1, axis=1), np.roll(np.roll(idx, -1, axis=0), -1, axis=1)
+    t = np.concatenate([np.stack([a.ravel(), b.ravel(), d.ravel()], axis=1), np.stack([a.ravel(), d.ravel(), c.ravel()], axis=1)])
+    return v.reshape(-1, 3).astype(np.float32), t.astype(np.int32)
+
+
+def points_inside_by_parity(points, vertices, triangles, direction=(0.3713, 0.5127, 0.7741)):
+    """ground truth for a CLOSED mesh: a point is inside iff a ray from it crosses the surface an odd number of times"""
+    P = np.asarray(points, np.float64).reshape(-1, 3)
+    V = np.asarray(vertices, np.float32).astype(np.float64)
+    T = np.asarray(triangles).astype(np.int64)
+    d = np.asarray(direction, np.float64)
+    d = d / np.linalg.norm(d)
+    a, e1, e2 = V[T[:, 0]], V[T[:, 1]] - V[T[:, 0]], V[T[:, 2]] - V[T[:, 0]]
+    pv = np.cross(d, e2)
+    det = (e1 * pv).sum(-1)
+    inside = np.zeros(len(P), bool)
+    for i, p in enumerate(P):
+        s = p - a
+        with np.errstate(divide="ignore", invalid="ignore"):
+            u = (s * pv).sum(-1) / det
+            q = np.cross(s, e1)
+            v = (q @ d) / det
+            t = (e2 * q).sum(-1) / det
+        inside[i] = (np.count_nonzero((u >= 0) & (v >= 0) & (u + v <= 1) & (t > 0)) & 1) == 1
+    return inside
+
+
+def sdf_sign_pseudonormal(points, vertices, triangles, tol=1.0e-9):
+    """sign (+1 outside / -1 inside) by the angle-weighted pseudo-normal of the closest feature; exhaustive closest-point search"""
+    P = np.asarray(points, np.float32).reshape(-1, 3).astype(np.float64)
+    V = np.asarray(vertices, np.float32).astype(np.float64)
+    T = np.asarray(triangles).astype(np.int64)
+    # weld vertices that share a position (fixture meshes may duplicate them)
+    _, weld = np.unique(np.round(V, 9), axis=0, return_inverse=True)
+    W = weld.reshape(-1)[T]
+    a, b, c = V[T[:, 0]], V[T[:, 1]], V[T[:, 2]]
+    fn = np.cross(b - a, c - a)
+    fl = np.linalg.norm(fn, axis=1)
+    un = fn / np.where(fl > 0, fl, 1.0)[:, None]
+
+    def angle(p, q, r):      # interior angle at p
+        x, y = q - p, r - p
+        cs = (x * y).sum(-1) / np.maximum(np.linalg.norm(x, axis=1) * np.linalg.norm(y, axis=1), 1e-300)
+        return np.arccos(np.clip(cs, -1.0, 1.0))
+    ang = np.stack([angle(a, b, c), angle(b, c, a), angle(c, a, b)], axis=1)
+    nvert = int(W.max()) + 1
+    vert_n = np.zeros((nvert, 3))
+    for k in range(3):
+        np.add.at(vert_n, W[:, k], ang[:, k:k + 1] * un)
+    edge_n = {}
+    for f in range(len(T)):
+        for i, j in ((0, 1), (1, 2), (2, 0)):
+            key = (min(W[f, i], W[f, j]), max(W[f, i], W[f, j]))
+            edge_n[key] = edge_n.get(key, 0.0) + un[f]
+    sign = np.ones(len(P))
+    A, B, C = a[None], b[None], c[None]
+    for s in range(0, len(P), 64):
+        p = P[s:s + 64, None, :]
+        q, d2 = closest_on_triangles(p, A, B, C)
+        d2 = np.where(np.isnan(d2), np.inf, d2)
+        k = np.argmin(d2, axis=1)
+        for r, f in enumerate(k):
+            qq = q[r, f]
+            corners = (a[f], b[f], c[f])
+            near = [np.linalg.norm(qq - x) <= tol * (1.0 + np.linalg.norm(x)) for x in corners]
+            if any(near):
+                n = vert_n[W[f, int(np.argmax(near))]]
+            else:
+                n = un[f]
+                for i, j in ((0, 1), (1, 2), (2, 0)):
+                    x, y = corners[i], corners[j]
+                    e = y - x
+                    tt = np.dot(qq - x, e) / np.dot(e, e)
+                    if np.linalg.norm(x + tt * e - qq) <= tol * (1.0 + np.linalg.norm(qq)):
+                        n = edge_n[(min(W[f, i], W[f, j]), max(W[f, i], W[f, j]))]
+                        break
+            sign[s + r] = -1.0 if np.dot(P[s + r] - qq, n) < 0 else 1.0
+    return sign
