@@ -377,9 +377,11 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
     if (slices < 1) slices = 1;
     if (table->num_main > 65535) return cfail(ELG_ERR_UNSUPPORTED, "more than 65535 main envs");
     if ((long long)table->rollouts_per_main * biggest / 4 > 0x7fffffffLL / 8) return cfail(ELG_ERR_UNSUPPORTED, "rollouts_per_main * row size too large");
-    // TMA path: word-sized rows, at least 4 rollouts per main; tile of up to 64 rows per field, <= 160 KB of shared memory
+    // TMA path: word-sized rows, at least 4 rollouts per main; tile of up to 32 rows per field, <= 160 KB of shared memory
     if (words && staged > 0 && staged <= elg::kCloneMaxRowWords && table->rollouts_per_main >= 4 && (g_clone_tune & 1) == 0) {
-      int tr = table->rollouts_per_main < 64 ? table->rollouts_per_main : 64;
+      int tr_cap = 32;      // (scripts/clone_ab.py --tiles, 64 mains x 512 rollouts: tiles of 32 / 64 / 128 / 256 rows -> 6.1-6.3 / 6.6 / 7.7 / 7.9 us)
+      if (((g_clone_tune >> 16) & 0xfff) > 0) tr_cap = (g_clone_tune >> 16) & 0xfff;   // measurement override: rows per tile
+      int tr = table->rollouts_per_main < tr_cap ? table->rollouts_per_main : tr_cap;
       const int fit = (160 * 1024 - staged * 4) / (staged * 4);
       if (tr > fit) tr = fit;
       tr &= ~3;
@@ -408,7 +410,7 @@ int elg_clone_rows(const ElgCloneTable* table, int mode, float drift, const floa
         // one chunk per CTA and field while that keeps the grid below ~8 CTAs per SM (measured, scripts/clone_ab.py: at
         // 64 mains x 512 rollouts 8 slices take 6.6 us, 5 slices 8.5 us, 1 slice 7.9 us)
         long long sl = (8LL * sms + table->num_main - 1) / table->num_main;
-        if ((g_clone_tune >> 8) > 0) sl = g_clone_tune >> 8;   // measurement override
+        if (((g_clone_tune >> 8) & 0xff) > 0) sl = (g_clone_tune >> 8) & 0xff;   // measurement override
         if (sl > nchunk) sl = nchunk;
         if (sl < 1) sl = 1;
         cudaLaunchConfig_t cfg{};
