@@ -126,8 +126,8 @@ elg_main_reset_flag_kernel(const uint8_t* __restrict__ reset_buf, const int num_
   if (threadIdx.x == 0) stats[ELG_NUM_REWARD_TERMS + 1] = any ? 1.0f : 0.0f;
 }
 
-// One warp per 32 consecutive envs: every lane reads the flags of its env (one coalesced load), a ballot finds the few rows that
-// have work, and the WARP then handles those one after the other -- lane 0 does the scalar work, lanes < D the joints, and all
+// One flagged row, handled by one WARP (elg_reset_kernel hands the rows of a 256-env CTA to its warps round-robin): all lanes compute
+// the scalar part redundantly from broadcast loads and shuffled uniforms, lane j draws joint j, lane t owns reward term t, and all
 // lanes repair the observation row: commands, dof_pos, dof_vel and the height entries, which depend on the new base height
 // (compute_observations runs after reset_idx on stale measured_heights, App. A-4), with the very noise samples the step kernel
 // attached to those entries.  (Round 1 launched one warp per env: at 65 536 envs that is 65 536 warps to find ~300 resets.)
