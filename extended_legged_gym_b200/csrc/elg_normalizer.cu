@@ -4,11 +4,11 @@
 // (the rollout-storage slot, rsl_rl/storage/rollout_storage.py:95-100) together with the reward / done columns, so the
 // observations go from the step kernel's output to the policy's input buffer in one pass.
 //
-// Batches whose rows fit the registers of ONE wave of CTAs (<= 32 rows per thread, <= one CTA per SM: 4096 x 235 and 65 536 x 48
-// both do) take elg_norm_fused_kernel: ONE launch in which every CTA keeps its rows in registers across a grid-wide hand-over --
-// per-CTA moments -> the last CTA to arrive merges them in block order, applies the update rule and publishes mean / (std + eps)
-// -> every CTA normalises the rows it still holds.  [N, O] is read ONCE (4 N O bytes in, 4 N O out) and the second launch with its
-// dependent-launch gap is gone.  Larger batches (and elg_set_normalizer_tuning(1)) take
+// Batches of <= 32 768 rows take ONE launch (elg_norm_cols_kernel): a CTA owns four columns, its rows stay in registers from the load
+// to the normalised store, and the rows of a column group are split over a thread-block cluster of 1 / 2 / 4 CTAs whose partial
+// sums cross through distributed shared memory.  [N, O] is read ONCE (4 N O bytes in, 4 N O out).  Kept as an A/B form
+// (elg_set_normalizer_tuning(2)): elg_norm_fused_kernel, a row-parallel single launch with a grid-wide hand-over through global
+// memory -- measured slower than the pair below.  Larger batches (and elg_set_normalizer_tuning(1)) take
 // two launches, chained by programmatic dependent launch, bit-reproducible:
 //   elg_norm_stats_kernel  (<= 32 row blocks) x (column tiles of 64): a thread owns one column of a few rows, forms their
 //                          (count, mean, M2) exactly in registers, the CTA tree-merges its row groups (Chan et al.) and
@@ -17,6 +17,7 @@
 //   elg_norm_apply_kernel  applies the reference's update rule (every CTA computes the identical new mean / std from the batch
 //                          moments; CTA 0 stores the state) and normalises its rows.
 // [N, O] fp32 is read twice (second time from L2) and written once: 8 N O bytes of HBM traffic for the pair.
+#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -361,18 +362,26 @@ elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restri
 // The CTA that finishes last (one ticket) stores the new count -- every CTA has read the old one by then.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kColsPerCta = 4;
+// The rows of a column group may be split over the CTAs of a THREAD-BLOCK CLUSTER (1, 2 or 4 CTAs: launch attribute): CTA `rank`
+// takes the row passes p = k * cluster_size + rank, forms its partial sums, and the partials cross through DISTRIBUTED SHARED MEMORY
+// (one cluster barrier; every CTA reads all partials in rank order and arrives at the identical totals).  4096 x 235 then runs on
+// 118 or 236 CTAs with 8 or 4 values per thread instead of 59 CTAs with 16.
 template <int kC>
 __global__ void __launch_bounds__(kNormThreads, 1)
 elg_norm_cols_kernel(const int64_t rows, const int cols, const float* __restrict__ x, float* __restrict__ mean, float* __restrict__ var,
                      float* __restrict__ stdv, int64_t* __restrict__ count, const float eps, const int64_t until, float* __restrict__ out,
                      void* __restrict__ scratch, const float* __restrict__ rew, float* __restrict__ rew_out, const uint8_t* __restrict__ dones,
                      uint8_t* __restrict__ dones_out) {
+  namespace cg = cooperative_groups;
   constexpr int kRowsPerPass = kNormThreads / kColsPerCta;   // 256
   __shared__ double s_w[2][kNormThreads / 32][kColsPerCta];
+  __shared__ double s_part[2][kColsPerCta];                  // this CTA's partial sums: read by the other CTAs of the cluster
   __shared__ float s_mean[kColsPerCta], s_den[kColsPerCta];
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned cs = cluster.num_blocks(), rank = cluster.block_rank();
   const int c4 = threadIdx.x & (kColsPerCta - 1), rb = threadIdx.x / kColsPerCta;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int col = blockIdx.x * kColsPerCta + c4;
+  const int col = (blockIdx.x / cs) * kColsPerCta + c4;
   const bool live = col < cols;
   pdl_launch_dependents();
   pdl_wait();
@@ -382,7 +391,7 @@ elg_norm_cols_kernel(const int64_t rows, const int cols, const float* __restrict
   float v[kC];
 #pragma unroll
   for (int k = 0; k < kC; ++k) {
-    const int64_t r = rb + (int64_t)k * kRowsPerPass;
+    const int64_t r = rb + (int64_t)(k * cs + rank) * kRowsPerPass;
     v[k] = (live && r < rows) ? xb[r * cols] : 0.0f;
   }
   {      // reward / done columns: this CTA's share of the rows
@@ -398,7 +407,7 @@ elg_norm_cols_kernel(const int64_t rows, const int cols, const float* __restrict
 #pragma unroll
     for (int k = 0; k < kC; ++k) {
       const double d = (double)v[k] - pivot;
-      const bool ok = rb + (int64_t)k * kRowsPerPass < rows;
+      const bool ok = rb + (int64_t)(k * cs + rank) * kRowsPerPass < rows;
       s += ok ? d : 0.0;
       q += ok ? d * d : 0.0;
     }
@@ -409,9 +418,20 @@ elg_norm_cols_kernel(const int64_t rows, const int cols, const float* __restrict
     }
     if (lane < kColsPerCta) { s_w[0][warp][lane] = s; s_w[1][warp][lane] = q; }
     __syncthreads();
+    if (threadIdx.x < kColsPerCta) {
+      double p1 = 0.0, p2 = 0.0;
+      for (int w = 0; w < kNormThreads / 32; ++w) { p1 += s_w[0][w][c4]; p2 += s_w[1][w][c4]; }
+      s_part[0][c4] = p1;
+      s_part[1][c4] = p2;
+    }
+    cluster.sync();      // every CTA's partials are in its shared memory (a plain CTA barrier when the cluster is one CTA)
     if (threadIdx.x < kColsPerCta && live) {
       double S1 = 0.0, S2 = 0.0;
-      for (int w = 0; w < kNormThreads / 32; ++w) { S1 += s_w[0][w][c4]; S2 += s_w[1][w][c4]; }
+      for (unsigned r = 0; r < cs; ++r) {      // rank order: every CTA of the cluster forms the identical totals
+        const double* remote = cluster.map_shared_rank(&s_part[0][0], r);
+        S1 += remote[c4];
+        S2 += remote[kColsPerCta + c4];
+      }
       const double mean_x_d = pivot + S1 / (double)rows;
       const double m2_x_d = fmax(S2 - S1 * S1 / (double)rows, 0.0);
       const int64_t new_count = old_count + rows;      // (normalizer.py:65-75)
@@ -422,11 +442,15 @@ elg_norm_cols_kernel(const int64_t rows, const int cols, const float* __restrict
       const float m_new = m_old + rate * delta;
       const float v_new = v_old + rate * (var_x - v_old + delta * (mean_x - m_new));
       const float s_new = __fsqrt_rn(v_new);
-      mean[col] = m_new; var[col] = v_new; stdv[col] = s_new;
       s_mean[c4] = m_new;
       s_den[c4] = s_new + eps;
+      // (the CTAs of a cluster read the old state here and rank 0 writes the new one after the second barrier)
+      if (rank == 0) { s_w[0][0][c4] = (double)v_new; s_w[1][0][c4] = (double)s_new; }
     }
-    __syncthreads();
+    cluster.sync();      // the partials have been read (a CTA may leave), s_mean / s_den are visible
+    if (rank == 0 && threadIdx.x < kColsPerCta && live) {
+      mean[col] = s_mean[c4]; var[col] = (float)s_w[0][0][c4]; stdv[col] = (float)s_w[1][0][c4];
+    }
     if (threadIdx.x == 0) {      // the last CTA to get here stores the new count: every CTA has read the old one
       unsigned* ticket = reinterpret_cast<unsigned*>(reinterpret_cast<char*>(scratch) + 16);
       if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
@@ -443,10 +467,28 @@ elg_norm_cols_kernel(const int64_t rows, const int cols, const float* __restrict
     float* ob = out + col;
 #pragma unroll
     for (int k = 0; k < kC; ++k) {
-      const int64_t r = rb + (int64_t)k * kRowsPerPass;
+      const int64_t r = rb + (int64_t)(k * cs + rank) * kRowsPerPass;
       if (r < rows) ob[r * cols] = (v[k] - m) / den;
     }
   }
+}
+
+template <typename K, typename... Args>
+static void launch_cols(K k, unsigned col_groups, unsigned cluster, cudaStream_t stream, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(col_groups * cluster);
+  cfg.blockDim = dim3(kNormThreads);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  attr[1].id = cudaLaunchAttributeClusterDimension;
+  attr[1].val.clusterDim.x = cluster;
+  attr[1].val.clusterDim.y = 1;
+  attr[1].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = cluster > 1 ? 2 : 1;
+  cudaLaunchKernelEx(&cfg, k, args...);
 }
 
 // geometry of the single-launch form, or cslots == 0 when the batch does not fit one wave of register-resident rows
@@ -499,10 +541,10 @@ static void launch_pdl(void (*k)(Args...), dim3 grid, int threads, cudaStream_t 
   cudaLaunchKernelEx(&cfg, k, args...);
 }
 
-// 0 (default): the column-parallel single launch for batches of <= 8192 rows, the statistics + apply pair otherwise; 1: always the
-// pair; 2: the row-parallel single launch with a grid-wide hand-over (measured slower than the pair: 14.8 vs 11.0 us at 4096 x 235;
-// kept for A/B runs).  Measurement bits of form 2 (results invalid): 4 = consumers do not wait, 8 = no statistics, 16 = spin
-// without nanosleep
+// bits 0-1: 0 (default) = the column-parallel single launch for batches of <= 32 768 rows, the statistics + apply pair otherwise;
+// 1 = always the pair; 2 = the row-parallel single launch with a grid-wide hand-over (measured slower than the pair: 14.8 vs 11.0 us
+// at 4096 x 235; kept for A/B runs).  Bits 2-3: force the cluster size of form 0 (1 -> 1 CTA, 2 -> 2, 3 -> 4).  Bits 4+: measurement
+// switches of form 2 (results invalid): 16 = consumers do not wait, 32 = no statistics, 64 = spin without nanosleep
 int g_norm_mode = 0;
 
 template <typename K, typename... Args>
@@ -516,7 +558,7 @@ static void launch_fused(K k, dim3 grid, cudaStream_t stream, Args... args) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k, args..., (int)(g_norm_mode & ~3));
+  cudaLaunchKernelEx(&cfg, k, args..., (int)((g_norm_mode >> 4) << 2));
 }
 
 }  // namespace elg
@@ -524,7 +566,7 @@ static void launch_fused(K k, dim3 grid, cudaStream_t stream, Args... args) {
 extern "C" {
 
 int elg_set_normalizer_tuning(int mode) {
-  if (mode < 0 || mode > 31) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer tuning mode must be 0 or 1 (+ measurement bits)");
+  if (mode < 0 || mode > 127) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer tuning mode must be 0 or 1 (+ measurement bits)");
   elg::g_norm_mode = mode;
   return ELG_OK;
 }
@@ -554,18 +596,28 @@ int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* 
   // 32-bit row offsets inside one row block / one apply block
   if ((int64_t)g.rows_per_part * num_cols >= ((int64_t)1 << 31)) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
-  if (training && elg::g_norm_mode == 0 && num_rows <= 32 * (elg::kNormThreads / elg::kColsPerCta)) {
-    const int per_thread = (int)((num_rows + elg::kNormThreads / elg::kColsPerCta - 1) / (elg::kNormThreads / elg::kColsPerCta));
-    const dim3 grid((unsigned)((num_cols + elg::kColsPerCta - 1) / elg::kColsPerCta));
-    if (per_thread <= 8)
-      elg::launch_pdl(elg::elg_norm_cols_kernel<8>, grid, elg::kNormThreads, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+  const int norm_form = elg::g_norm_mode & 3;
+  if (training && (norm_form == 0 || norm_form == 3) && num_rows <= 4 * 32 * (elg::kNormThreads / elg::kColsPerCta)) {
+    const int passes = (int)((num_rows + elg::kNormThreads / elg::kColsPerCta - 1) / (elg::kNormThreads / elg::kColsPerCta));
+    // thread-block cluster over the rows: as many CTAs (1, 2, 4) as keep >= 4 row passes per thread -- and enough of them for <= 32
+    // passes per thread; bits 2-3 of the tuning word force a size (measurement)
+    unsigned cluster = passes >= 16 ? 4u : passes >= 8 ? 2u : 1u;
+    const int forced = (elg::g_norm_mode >> 2) & 3;
+    if (forced) cluster = forced == 3 ? 4u : (unsigned)forced;
+    while (passes > 32 * (int)cluster && cluster < 4u) cluster *= 2u;
+    const int per_thread = (passes + (int)cluster - 1) / (int)cluster;
+    const unsigned groups = (unsigned)((num_cols + elg::kColsPerCta - 1) / elg::kColsPerCta);
+    if (per_thread <= 4)
+      elg::launch_cols(elg::elg_norm_cols_kernel<4>, groups, cluster, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+    else if (per_thread <= 8)
+      elg::launch_cols(elg::elg_norm_cols_kernel<8>, groups, cluster, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
     else if (per_thread <= 16)
-      elg::launch_pdl(elg::elg_norm_cols_kernel<16>, grid, elg::kNormThreads, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+      elg::launch_cols(elg::elg_norm_cols_kernel<16>, groups, cluster, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
     else
-      elg::launch_pdl(elg::elg_norm_cols_kernel<32>, grid, elg::kNormThreads, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
+      elg::launch_cols(elg::elg_norm_cols_kernel<32>, groups, cluster, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
     return elg::check_launch("elg_normalize_observations");
   }
-  if (training && (elg::g_norm_mode & 2)) {      // the grid-wide hand-over form: measured slower than the pair below (A/B only)
+  if (training && norm_form == 2) {      // the grid-wide hand-over form: measured slower than the pair below (A/B only)
     const elg::FusedGeom fg = elg::make_fused_geom(num_rows, num_cols, elg::sm_count());
     if (fg.cslots > 0) {
       const int rsub = elg::kNormThreads / fg.cslots;

@@ -463,8 +463,9 @@ int elg_integrate_state_velocities(const ElgPlanParams* prm, const ElgPlanBuffer
  * first use -- its header holds the completion tickets, which every call leaves at zero again) is only needed when
  * training.  At most 1920 columns.  out may alias x; out == NULL updates the statistics only (EmpiricalNormalization.update). */
 int64_t elg_normalizer_scratch_bytes(int64_t num_rows, int32_t num_cols);
-int elg_set_normalizer_tuning(int mode);   /* 0: column-parallel single launch up to 8192 rows, else two launches (default); 1: always two launches;
-                                             2: row-parallel single launch with a grid-wide hand-over (A/B, tests) */
+int elg_set_normalizer_tuning(int mode);   /* bits 0-1: 0 = column-parallel single launch (thread-block cluster over the rows) up to
+                                             32 768 rows, else two launches (default); 1 = always two launches; 2 = row-parallel single
+                                             launch with a grid-wide hand-over (A/B, tests); bits 2-3: force the cluster size (1, 2, 3 -> 4) */
 int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* x, float* mean, float* var, float* std, int64_t* count, float eps,
                                int64_t until, int32_t training, float* out, void* scratch, const float* rew /*[N] or NULL*/,
                                float* rew_out, const uint8_t* dones /*[N] or NULL*/, uint8_t* dones_out, void* stream);
