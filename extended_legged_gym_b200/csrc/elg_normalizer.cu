@@ -4,8 +4,8 @@
 // (the rollout-storage slot, rsl_rl/storage/rollout_storage.py:95-100) together with the reward / done columns, so the
 // observations go from the step kernel's output to the policy's input buffer in one pass.
 //
-// Batches of <= 32 768 rows take ONE launch (elg_norm_cols_kernel): a CTA owns four columns, its rows stay in registers from the load
-// to the normalised store, and the rows of a column group are split over a thread-block cluster of 1 / 2 / 4 CTAs whose partial
+// Batches of <= 65 536 rows take ONE launch (elg_norm_cols_kernel): a CTA owns four columns, its rows stay in registers from the load
+// to the normalised store, and the rows of a column group are split over a thread-block cluster of 1 / 2 / 4 / 8 CTAs whose partial
 // sums cross through distributed shared memory.  [N, O] is read ONCE (4 N O bytes in, 4 N O out).  Kept as an A/B form
 // (elg_set_normalizer_tuning(2)): elg_norm_fused_kernel, a row-parallel single launch with a grid-wide hand-over through global
 // memory -- measured slower than the pair below.  Larger batches (and elg_set_normalizer_tuning(1)) take
@@ -362,7 +362,7 @@ elg_norm_fused_kernel(const __grid_constant__ FusedGeom g, const float* __restri
 // The CTA that finishes last (one ticket) stores the new count -- every CTA has read the old one by then.
 // ---------------------------------------------------------------------------------------------------------------
 constexpr int kColsPerCta = 4;
-// The rows of a column group may be split over the CTAs of a THREAD-BLOCK CLUSTER (1, 2 or 4 CTAs: launch attribute): CTA `rank`
+// The rows of a column group may be split over the CTAs of a THREAD-BLOCK CLUSTER (1, 2, 4 or 8 CTAs: launch attribute): CTA `rank`
 // takes the row passes p = k * cluster_size + rank, forms its partial sums, and the partials cross through DISTRIBUTED SHARED MEMORY
 // (one cluster barrier; every CTA reads all partials in rank order and arrives at the identical totals).  4096 x 235 then runs on
 // 118 or 236 CTAs with 8 or 4 values per thread instead of 59 CTAs with 16.
@@ -541,10 +541,10 @@ static void launch_pdl(void (*k)(Args...), dim3 grid, int threads, cudaStream_t 
   cudaLaunchKernelEx(&cfg, k, args...);
 }
 
-// bits 0-1: 0 (default) = the column-parallel single launch for batches of <= 32 768 rows, the statistics + apply pair otherwise;
+// bits 0-1: 0 (default) = the column-parallel single launch for batches of <= 65 536 rows, the statistics + apply pair otherwise;
 // 1 = always the pair; 2 = the row-parallel single launch with a grid-wide hand-over (measured slower than the pair: 14.8 vs 11.0 us
-// at 4096 x 235; kept for A/B runs).  Bits 2-3: force the cluster size of form 0 (1 -> 1 CTA, 2 -> 2, 3 -> 4).  Bits 4+: measurement
-// switches of form 2 (results invalid): 16 = consumers do not wait, 32 = no statistics, 64 = spin without nanosleep
+// at 4096 x 235; kept for A/B runs).  Bits 2-4: force the cluster size of form 0 (1 -> 1 CTA, 2 -> 2, 3 -> 4, 4 -> 8).  Bits 5+:
+// measurement switches of form 2 (results invalid): 32 = consumers do not wait, 64 = no statistics, 128 = spin without nanosleep
 int g_norm_mode = 0;
 
 template <typename K, typename... Args>
@@ -558,7 +558,7 @@ static void launch_fused(K k, dim3 grid, cudaStream_t stream, Args... args) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, k, args..., (int)((g_norm_mode >> 4) << 2));
+  cudaLaunchKernelEx(&cfg, k, args..., (int)((g_norm_mode >> 5) << 2));
 }
 
 }  // namespace elg
@@ -566,7 +566,7 @@ static void launch_fused(K k, dim3 grid, cudaStream_t stream, Args... args) {
 extern "C" {
 
 int elg_set_normalizer_tuning(int mode) {
-  if (mode < 0 || mode > 127) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer tuning mode must be 0 or 1 (+ measurement bits)");
+  if (mode < 0 || mode > 255) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer tuning mode must be 0 or 1 (+ measurement bits)");
   elg::g_norm_mode = mode;
   return ELG_OK;
 }
@@ -597,16 +597,19 @@ int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* 
   if ((int64_t)g.rows_per_part * num_cols >= ((int64_t)1 << 31)) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: batch too large");
   cudaStream_t s = (cudaStream_t)stream;
   const int norm_form = elg::g_norm_mode & 3;
-  if (training && (norm_form == 0 || norm_form == 3) && num_rows <= 4 * 32 * (elg::kNormThreads / elg::kColsPerCta)) {
+  if (training && (norm_form == 0 || norm_form == 3) && num_rows <= 8 * 32 * (elg::kNormThreads / elg::kColsPerCta)) {
     const int passes = (int)((num_rows + elg::kNormThreads / elg::kColsPerCta - 1) / (elg::kNormThreads / elg::kColsPerCta));
-    // thread-block cluster over the rows: as many CTAs (1, 2, 4) as keep >= 4 row passes per thread -- and enough of them for <= 32
-    // passes per thread; bits 2-3 of the tuning word force a size (measurement)
-    unsigned cluster = passes >= 16 ? 4u : passes >= 8 ? 2u : 1u;
-    const int forced = (elg::g_norm_mode >> 2) & 3;
-    if (forced) cluster = forced == 3 ? 4u : (unsigned)forced;
-    while (passes > 32 * (int)cluster && cluster < 4u) cluster *= 2u;
-    const int per_thread = (passes + (int)cluster - 1) / (int)cluster;
+    // thread-block cluster over the rows: the largest of 1 / 2 / 4 / 8 CTAs that keeps the grid within one CTA per SM (measured at
+    // 4096 x 235, 59 column groups: 9.4 / 7.1 / 10.3 us with 1 / 2 / 4 CTAs per cluster -- 236 CTAs no longer fit one per SM; at
+    // 4096 x 48, 12 groups: 8.1 / 6.4 / 5.1 us) and leaves every CTA at least one row pass; bits 2-4 of the tuning word force a size
     const unsigned groups = (unsigned)((num_cols + elg::kColsPerCta - 1) / elg::kColsPerCta);
+    const int sms = elg::sm_count();
+    unsigned cluster = 1u;
+    while (cluster < 8u && groups * cluster * 2u <= (unsigned)(sms > 0 ? sms : 1) && (int)(cluster * 2u) <= passes) cluster *= 2u;
+    const int forced = (elg::g_norm_mode >> 2) & 7;
+    if (forced >= 1 && forced <= 4) cluster = 1u << (forced - 1);
+    while (passes > 32 * (int)cluster && cluster < 8u) cluster *= 2u;
+    const int per_thread = (passes + (int)cluster - 1) / (int)cluster;
     if (per_thread <= 4)
       elg::launch_cols(elg::elg_norm_cols_kernel<4>, groups, cluster, s, num_rows, (int)num_cols, x, mean, var, std, count, eps, until, out, scratch, rew, rew_out, dones, dones_out);
     else if (per_thread <= 8)

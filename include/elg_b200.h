@@ -464,8 +464,9 @@ int elg_integrate_state_velocities(const ElgPlanParams* prm, const ElgPlanBuffer
  * training.  At most 1920 columns.  out may alias x; out == NULL updates the statistics only (EmpiricalNormalization.update). */
 int64_t elg_normalizer_scratch_bytes(int64_t num_rows, int32_t num_cols);
 int elg_set_normalizer_tuning(int mode);   /* bits 0-1: 0 = column-parallel single launch (thread-block cluster over the rows) up to
-                                             32 768 rows, else two launches (default); 1 = always two launches; 2 = row-parallel single
-                                             launch with a grid-wide hand-over (A/B, tests); bits 2-3: force the cluster size (1, 2, 3 -> 4) */
+                                             65 536 rows, else two launches (default); 1 = always two launches; 2 = row-parallel single
+                                             launch with a grid-wide hand-over (A/B, tests); bits 2-4: force the cluster size
+                                             (1 -> 1 CTA, 2 -> 2, 3 -> 4, 4 -> 8) */
 int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* x, float* mean, float* var, float* std, int64_t* count, float eps,
                                int64_t until, int32_t training, float* out, void* scratch, const float* rew /*[N] or NULL*/,
                                float* rew_out, const uint8_t* dones /*[N] or NULL*/, uint8_t* dones_out, void* stream);

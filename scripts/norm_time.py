@@ -11,7 +11,7 @@ lib = _lib.load()
 dev = "cuda:0"
 # modes of elg_set_normalizer_tuning: 0 default (column-parallel single launch up to 8192 rows), 1 two launches, 2 row-parallel single
 # launch with a grid-wide hand-over
-MODES = (0, 1, 2, 4, 8, 12)      # (4 / 8 / 12: form 0 with the cluster size forced to 1 / 2 / 4)
+MODES = (0, 1, 2, 4, 8, 12, 16)      # (4 / 8 / 12 / 16: form 0 with the cluster size forced to 1 / 2 / 4 / 8)
 for n, o in ((4096, 235), (4096, 48), (65536, 48), (32832, 235)):
     for training, mode in [(True, m) for m in MODES] + [(False, 0)]:
         lib.elg_set_normalizer_tuning(mode)

@@ -99,11 +99,11 @@ def test_kernel_matches_reference_fixture(tag):
         assert_out(y, torch.from_numpy(z[f"{tag}__s{s}__out"]), m._std, m._mean)
 
 
-@pytest.fixture(params=[0, 1, 2, 4, 8, 12], ids=["default", "two_launches", "grid_handover", "cluster_of_1", "cluster_of_2", "cluster_of_4"])
+@pytest.fixture(params=[0, 1, 2, 4, 8, 12, 16], ids=["default", "two_launches", "grid_handover", "cluster_of_1", "cluster_of_2", "cluster_of_4", "cluster_of_8"])
 def launch_form(request):
     """the forms of the training-mode call: 0 = column-parallel single launch (rows of a column group split over a thread-block
-    cluster, partial sums through distributed shared memory) up to 32 768 rows, else the statistics + apply pair; 1 = always the
-    pair; 2 = row-parallel single launch with a grid-wide hand-over (A/B form); 4 / 8 / 12 = form 0 with the cluster size forced"""
+    cluster, partial sums through distributed shared memory) up to 65 536 rows, else the statistics + apply pair; 1 = always the
+    pair; 2 = row-parallel single launch with a grid-wide hand-over (A/B form); 4 / 8 / 12 / 16 = form 0 with the cluster size forced"""
     lib = _lib.load()
     lib.elg_set_normalizer_tuning(request.param)
     yield request.param
