@@ -177,7 +177,7 @@ def load() -> C.CDLL:
     vp, i64 = C.c_void_p, C.c_int64
     lib.elg_compute_torques.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 9 + [i64, vp]
     if hasattr(lib, "elg_rollout_actions"):
-        lib.elg_rollout_actions.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, C.c_float, vp, vp, vp, vp]
+        lib.elg_rollout_actions.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32, i64, C.c_float, vp, vp, vp, vp]
     lib.elg_post_physics_step.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams), C.POINTER(ElgStepBuffers), C.c_uint32, vp]
     lib.elg_set_step_tuning.argtypes = [C.c_int] * 4
     lib.elg_get_heights.argtypes = [C.POINTER(ElgDims), C.POINTER(ElgStepParams)] + [vp] * 5 + [vp]

@@ -919,7 +919,7 @@ elg_torques4_kernel(const uint32_t n4, const uint32_t D, const int control_type,
 // step_rollout's action hand-over (robot_batch_rollout.py:643-656; robot_traj_grad_sampling.py:326-345): one thread per value
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-elg_rollout_actions_kernel(const float* __restrict__ src, const int M, const int R, const int A, const float clip,
+elg_rollout_actions_kernel(const float* __restrict__ src, const int M, const int R, const int A, const int64_t src_stride, const float clip,
                            const float* __restrict__ lower, const float* __restrict__ range, float* __restrict__ actions) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   pdl_launch_dependents();
@@ -928,7 +928,7 @@ elg_rollout_actions_kernel(const float* __restrict__ src, const int M, const int
   const int64_t row = i / A;
   const int j = (int)(i - row * A);
   const int64_t k = row / R;
-  float a = src[i];
+  float a = src[row * src_stride + j];
   if (lower) a = add_r(__ldg(lower + j), div_r(mul_r(add_r(fminf(fmaxf(a, -1.0f), 1.0f), 1.0f), __ldg(range + j)), 2.0f));
   actions[(row + k + 1) * A + j] = fminf(fmaxf(a, -clip), clip);
 }
@@ -1090,9 +1090,11 @@ int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const flo
   return check_launch("elg_compute_torques");
 }
 
-int elg_rollout_actions(const float* rollout_actions, int32_t num_main, int32_t rollouts_per_main, int32_t num_actions, float clip_actions,
-                        const float* joint_lower, const float* joint_range, float* actions, void* stream) {
+int elg_rollout_actions(const float* rollout_actions, int32_t num_main, int32_t rollouts_per_main, int32_t num_actions, int64_t src_row_stride,
+                        float clip_actions, const float* joint_lower, const float* joint_range, float* actions, void* stream) {
   if (num_main < 0 || rollouts_per_main < 0 || num_actions < 1) return fail(ELG_ERR_INVALID_ARGUMENT, "elg_rollout_actions: bad sizes");
+  if (src_row_stride == 0) src_row_stride = num_actions;
+  if (src_row_stride < num_actions) return fail(ELG_ERR_INVALID_ARGUMENT, "elg_rollout_actions: src_row_stride < num_actions");
   if ((joint_lower == nullptr) != (joint_range == nullptr)) return fail(ELG_ERR_INVALID_ARGUMENT, "joint_lower and joint_range go together");
   const int64_t total = (int64_t)num_main * rollouts_per_main * num_actions;
   if (total == 0) return ELG_OK;
@@ -1106,8 +1108,8 @@ int elg_rollout_actions(const float* rollout_actions, int32_t num_main, int32_t 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  cudaLaunchKernelEx(&cfg, elg::elg_rollout_actions_kernel, rollout_actions, (int)num_main, (int)rollouts_per_main, (int)num_actions, clip_actions,
-                     joint_lower, joint_range, actions);
+  cudaLaunchKernelEx(&cfg, elg::elg_rollout_actions_kernel, rollout_actions, (int)num_main, (int)rollouts_per_main, (int)num_actions, src_row_stride,
+                     clip_actions, joint_lower, joint_range, actions);
   return check_launch("elg_rollout_actions");
 }
 

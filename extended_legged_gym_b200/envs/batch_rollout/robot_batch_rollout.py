@@ -221,11 +221,12 @@ class RobotBatchRollout(LeggedRobot):
         """step_rollout's action hand-over (:643-656) as ONE launch: clip + scatter into the rollout rows of ``actions``
         (subclasses add the joint-target denormalisation through ``_action_denorm``)."""
         a = rollout_actions
-        if not (a.is_cuda and a.dtype == torch.float and a.is_contiguous()):
+        # rows may be strided (step i of an [M * R, horizon, A] plan is all_us[:, i]): the kernel takes the row stride, no copy
+        if not (a.is_cuda and a.dtype == torch.float and a.dim() == 2 and a.stride(1) == 1 and a.stride(0) >= a.shape[1]):
             a = a.to(self.device, torch.float).contiguous()
         lower, rng = getattr(self, "_action_denorm", (None, None))
         stream = torch.cuda.current_stream(self.device).cuda_stream
-        _lib.check(self._lib.elg_rollout_actions(a.data_ptr(), self.num_main_envs, self.num_rollout_per_main, self.num_actions,
+        _lib.check(self._lib.elg_rollout_actions(a.data_ptr(), self.num_main_envs, self.num_rollout_per_main, self.num_actions, int(a.stride(0)),
                                                  float(self.cfg.normalization.clip_actions), _lib.ptr(lower), _lib.ptr(rng),
                                                  self.actions.data_ptr(), stream), "elg_rollout_actions")
 

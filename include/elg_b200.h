@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define ELG_ABI_VERSION 3
+#define ELG_ABI_VERSION 4
 
 #define ELG_MAX_DOF 32
 #define ELG_MAX_FEET 8
@@ -237,10 +237,11 @@ int elg_compute_torques(const ElgDims* dims, const ElgStepParams* prm, const flo
 /* RobotBatchRollout.step_rollout's action hand-over (envs/batch_rollout/robot_batch_rollout.py:643-656, with the joint-target
  * denormalisation of robot_traj_grad_sampling.py:326-345 when joint_lower / joint_range are given): rollout env (main k, rollout r)
  * takes rollout_actions[k * R + r] -- optionally lower + (clamp(a, -1, 1) + 1) * range / 2 -- clipped to +- clip_actions, written to
- * row k * (1 + R) + 1 + r of `actions`; main rows are left alone.  One launch instead of clip + index_put. */
-int elg_rollout_actions(const float* rollout_actions /*[M*R, A]*/, int32_t num_main, int32_t rollouts_per_main, int32_t num_actions,
-                        float clip_actions, const float* joint_lower /*[A] or NULL*/, const float* joint_range /*[A] or NULL*/,
-                        float* actions /*[M*(1+R), A]*/, void* stream);
+ * row k * (1 + R) + 1 + r of `actions`; main rows are left alone.  One launch instead of clip + index_put (+ the copy that makes a
+ * strided slice of the action plan contiguous). */
+int elg_rollout_actions(const float* rollout_actions /*[M*R, A], rows src_row_stride floats apart*/, int32_t num_main, int32_t rollouts_per_main,
+                        int32_t num_actions, int64_t src_row_stride /* 0: dense (= num_actions); e.g. horizon * A for step i of an [M*R, horizon, A] plan */,
+                        float clip_actions, const float* joint_lower, const float* joint_range, float* actions, void* stream);
 
 /* LeggedRobot.post_physics_step body (envs/base/legged_robot.py:122-150) with
  * _post_physics_step_callback's heading + heights (:394-401), check_termination (:155-160),

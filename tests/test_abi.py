@@ -37,7 +37,7 @@ def test_library_contains_sm100a_code():
 
 def test_struct_mirrors_and_registry_order():
     lib = _lib.load()
-    assert lib.elg_abi_version() == 3
+    assert lib.elg_abi_version() == 4
     assert lib.elg_sizeof_dims() == C.sizeof(_lib.ElgDims)
     assert lib.elg_sizeof_step_params() == C.sizeof(_lib.ElgStepParams)
     assert lib.elg_sizeof_step_buffers() == C.sizeof(_lib.ElgStepBuffers)
