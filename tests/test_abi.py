@@ -65,3 +65,25 @@ def test_argument_validation_fails_loudly():
     assert rc == -1
     with pytest.raises(NameError):
         _lib.check(rc)
+
+
+@pytest.mark.gpu
+def test_stage_block_probe_copies_both_ways_in_both_modes():
+    """elg_stage_block (the SM-issued host <-> device copy measured against the copy engine): exact bytes, ragged tail, both modes"""
+    import torch
+    from extended_legged_gym_b200 import _lib
+    lib = _lib.load()
+    n = 16 * 40001                                     # not a multiple of the 16 KB pieces of mode 1
+    host = torch.arange(n, dtype=torch.int64).to(torch.uint8).pin_memory()
+    for mode in (0, 1):
+        dev = torch.zeros(n, dtype=torch.uint8, device="cuda:0")
+        s = torch.cuda.current_stream().cuda_stream
+        _lib.check(lib.elg_stage_block(dev.data_ptr(), host.data_ptr(), n, mode, 0, s), "elg_stage_block")
+        torch.cuda.synchronize()
+        assert torch.equal(dev.cpu(), host)
+        back = torch.zeros(n, dtype=torch.uint8).pin_memory()
+        _lib.check(lib.elg_stage_block(back.data_ptr(), dev.data_ptr(), n, mode, 7, s), "elg_stage_block")
+        torch.cuda.synchronize()
+        assert torch.equal(back, host)
+    assert lib.elg_stage_block(None, host.data_ptr(), 16, 0, 0, None) == -4
+    assert lib.elg_stage_block(host.data_ptr(), host.data_ptr(), 24, 0, 0, None) == -1
