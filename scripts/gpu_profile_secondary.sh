@@ -6,7 +6,7 @@ mkdir -p $OUT
 timeout 600 python scripts/secondary_driver.py > $OUT/${TAG}_secondary.json 2> $OUT/${TAG}_secondary.err; echo "driver rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:elg_ -c 400 --csv --log-file $OUT/${TAG}_secondary_launches.csv \
     python scripts/secondary_driver.py > /dev/null 2>&1
-for k in elg_depth_camera_kernel elg_raycast_kernel elg_sdf_kernel elg_clone_bulk_kernel elg_actuator_kernel elg_mppi_partials_kernel elg_norm_stats_kernel elg_norm_apply_kernel; do
+for k in ${KERNELS:-elg_depth_camera_kernel elg_raycast_kernel elg_sdf_kernel elg_clone_bulk_kernel elg_actuator_kernel elg_norm_cols_kernel elg_reset_kernel elg_torques4_kernel}; do
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:$k -s 2 -c 1 -f -o $OUT/${TAG}_$k python scripts/secondary_driver.py > /dev/null 2>&1
   echo "$k rc=$?"
 done
