@@ -516,31 +516,29 @@ __device__ __forceinline__ Closest closest_on_triangle(const double px, const do
   const double vc = dsub(dmul(d1, d4), dmul(d3, d2));
   const double vb = dsub(dmul(d5, d2), dmul(d1, d6));
   const double va = dsub(dmul(d3, d6), dmul(d5, d4));
-  // Every region's candidate is formed (the same individually rounded expressions as the branchy statement of Ericson 5.1.5 and as
-  // the oracle's vectorised form) and the first matching region wins by selection, in reverse priority: the seven-way branch left
-  // 8.4 of 32 lanes active in elg_sdf_kernel (profiles/r3d); an unselected candidate may hold inf / NaN (0 / 0 of a degenerate edge),
-  // which no selected one does.
-  const double v_ab = d1 / dsub(d1, d3);
-  const double w_ac = d2 / dsub(d2, d6);
-  const double d43 = dsub(d4, d3), d56 = dsub(d5, d6);
-  const double w_bc = d43 / dadd(d43, d56);
-  const double denom = 1.0 / dadd(dadd(va, vb), vc);
-  const double vi = dmul(vb, denom), wi = dmul(vc, denom);
-  double qx = dadd(dadd(ax, dmul(abx, vi)), dmul(acx, wi));      // interior
-  double qy = dadd(dadd(ay, dmul(aby, vi)), dmul(acy, wi));
-  double qz = dadd(dadd(az, dmul(abz, vi)), dmul(acz, wi));
-  if (va <= 0.0 && d43 >= 0.0 && d56 >= 0.0) {                    // edge BC
-    qx = dadd(bx, dmul(w_bc, dsub(cx, bx))); qy = dadd(by, dmul(w_bc, dsub(cy, by))); qz = dadd(bz, dmul(w_bc, dsub(cz, bz)));
+  double qx, qy, qz;
+  if (d1 <= 0.0 && d2 <= 0.0) {                                   // vertex A
+    qx = ax; qy = ay; qz = az;
+  } else if (d3 >= 0.0 && d4 <= d3) {                             // vertex B
+    qx = bx; qy = by; qz = bz;
+  } else if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {               // edge AB
+    const double v = d1 / dsub(d1, d3);
+    qx = dadd(ax, dmul(v, abx)); qy = dadd(ay, dmul(v, aby)); qz = dadd(az, dmul(v, abz));
+  } else if (d6 >= 0.0 && d5 <= d6) {                             // vertex C
+    qx = cx; qy = cy; qz = cz;
+  } else if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {               // edge AC
+    const double w = d2 / dsub(d2, d6);
+    qx = dadd(ax, dmul(w, acx)); qy = dadd(ay, dmul(w, acy)); qz = dadd(az, dmul(w, acz));
+  } else if (va <= 0.0 && dsub(d4, d3) >= 0.0 && dsub(d5, d6) >= 0.0) {   // edge BC
+    const double w = dsub(d4, d3) / dadd(dsub(d4, d3), dsub(d5, d6));
+    qx = dadd(bx, dmul(w, dsub(cx, bx))); qy = dadd(by, dmul(w, dsub(cy, by))); qz = dadd(bz, dmul(w, dsub(cz, bz)));
+  } else {                                                        // interior
+    const double denom = 1.0 / dadd(dadd(va, vb), vc);
+    const double v = dmul(vb, denom), w = dmul(vc, denom);
+    qx = dadd(dadd(ax, dmul(abx, v)), dmul(acx, w));
+    qy = dadd(dadd(ay, dmul(aby, v)), dmul(acy, w));
+    qz = dadd(dadd(az, dmul(abz, v)), dmul(acz, w));
   }
-  if (vb <= 0.0 && d2 >= 0.0 && d6 <= 0.0) {                      // edge AC
-    qx = dadd(ax, dmul(w_ac, acx)); qy = dadd(ay, dmul(w_ac, acy)); qz = dadd(az, dmul(w_ac, acz));
-  }
-  if (d6 >= 0.0 && d5 <= d6) { qx = cx; qy = cy; qz = cz; }      // vertex C
-  if (vc <= 0.0 && d1 >= 0.0 && d3 <= 0.0) {                      // edge AB
-    qx = dadd(ax, dmul(v_ab, abx)); qy = dadd(ay, dmul(v_ab, aby)); qz = dadd(az, dmul(v_ab, abz));
-  }
-  if (d3 >= 0.0 && d4 <= d3) { qx = bx; qy = by; qz = bz; }      // vertex B
-  if (d1 <= 0.0 && d2 <= 0.0) { qx = ax; qy = ay; qz = az; }      // vertex A
   Closest r;
   r.cx = qx; r.cy = qy; r.cz = qz;
   const double ox = dsub(px, qx), oy = dsub(py, qy), oz = dsub(pz, qz);
