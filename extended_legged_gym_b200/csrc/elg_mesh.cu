@@ -107,6 +107,10 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
   // (One loop with "leaf or node" per iteration kept 17 of 32 lanes busy on the depth-camera workload.  Leaving the node
   // phase earlier -- while 1/16 ... all of the lanes still search -- was measured and is monotonically slower:
   // depth camera 5.21 Grays/s with this rule, 5.14 / 4.81 / 4.66 / 4.58 / 4.45 at 2 / 4 / 8 / 16 / 32 thirty-seconds.)
+  // (Round 2 also measured a STREAMING form for the depth camera -- one warp works through a block of pixels and a lane whose ray is
+  //  finished takes the next pixel when fewer than k lanes are still busy: bit-identical images, but 4.1-5.1 / 2.3-3.2 Grays/s
+  //  (far clip 2 / 10 m) for k = 1 ... 33 against 5.9 / 4.3 for one trace() per pixel round: new rays start at the root while the
+  //  others are deep in the tree, and the per-lane ray state kept across the loop costs registers.  profiles/r3i_depth_refill.txt.)
   // The slab planes of two children at a time go through the packed fp32 pipe (FADD2 / FMUL2: one instruction, two individually
   // rounded results -- the same values as the scalar form): 24 packed instead of 48 scalar instructions per node.
   const f32x2 nox = pack2(-ox, -ox), noy = pack2(-oy, -oy), noz = pack2(-oz, -oz);
@@ -182,119 +186,6 @@ __device__ __forceinline__ bool trace(const float4* __restrict__ nodes, const fl
   hit.t = t_best;
   hit.tri = best_tri;
   return best_tri >= 0;
-}
-
-// ---------------------------------------------------------------------------------------------
-// The same traversal over a STREAM of rays (one warp, rays first .. last - 1): a lane whose ray is finished takes the next ray of the
-// stream at once instead of idling until the slowest ray of its round is done (the depth camera casts 12 rays per thread: with one
-// trace() per ray, 20.6 of 32 lanes were busy).  Every ray still visits its own nodes and triangles in its own stack order, so hits
-// are bit-identical to trace().  fetch(id, ox, oy, oz, dx, dy, dz) supplies ray `id`; emit(id, found, t, tri, dx, dy, dz) takes its
-// result.  All 32 lanes of the warp must call.
-// ---------------------------------------------------------------------------------------------
-template <typename Fetch, typename Emit>
-__device__ __forceinline__ void trace_stream(const float4* __restrict__ nodes, const float4* __restrict__ tris, const int first, const int last,
-                                             const float max_t, Fetch&& fetch, Emit&& emit) {
-  constexpr unsigned kFull = 0xffffffffu;
-  const unsigned lane_lt = (1u << (threadIdx.x & 31)) - 1u;
-  int next = first;      // warp-uniform: the next ray nobody has taken
-  int my = -1;           // this lane's ray, or -1
-  float ox = 0.0f, oy = 0.0f, oz = 0.0f, dx = 1.0f, dy = 1.0f, dz = 1.0f;
-  double t_best = (double)max_t;
-  float t_cull = max_t;
-  int best_tri = -1;
-  int2 stack[kStack];
-  int sp = 0;
-  int pending = 0;
-  f32x2 nox = 0, noy = 0, noz = 0, ix2 = 0, iy2 = 0, iz2 = 0;
-  for (;;) {
-    // replenish: idle lanes take the next rays of the stream, in lane order (neighbouring lanes hold neighbouring rays)
-    const bool idle = my < 0;
-    const unsigned need = __ballot_sync(kFull, idle);
-    if (need != 0u && next < last) {
-      const int take = next + __popc(need & lane_lt);
-      if (idle && take < last) {
-        my = take;
-        fetch(my, ox, oy, oz, dx, dy, dz);
-        const float ix = 1.0f / dx, iy = 1.0f / dy, iz = 1.0f / dz;
-        nox = pack2(-ox, -ox); noy = pack2(-oy, -oy); noz = pack2(-oz, -oz);
-        ix2 = pack2(ix, ix); iy2 = pack2(iy, iy); iz2 = pack2(iz, iz);
-        t_best = (double)max_t;
-        t_cull = max_t;
-        best_tri = -1;
-        pending = 0;
-        sp = 0;
-        stack[sp++] = make_int2(0, __float_as_int(0.0f));
-      }
-      next = min(last, next + __popc(need));
-    }
-    if (!__any_sync(kFull, my >= 0)) break;
-    // node phase: the lanes that are still searching expand inner nodes until they pop a leaf
-    for (;;) {
-      const bool searching = my >= 0 && pending == 0 && sp > 0;
-      if (!__any_sync(kFull, searching)) break;
-      if (!searching) continue;
-      --sp;
-      const int2 top = stack[sp];
-      const int code = top.x;
-      if (__int_as_float(top.y) > t_cull) continue;
-      if (code < 0) {
-        pending = code;
-        continue;
-      }
-      const ulonglong2* np = reinterpret_cast<const ulonglong2*>(nodes + 8 * (size_t)code);
-      const ulonglong2 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
-      const int4 ch = __ldg(reinterpret_cast<const int4*>(np + 6));
-      float ax[4], bx[4], ay[4], by[4], az[4], bz[4];
-      unpack2(mul2(add2(lx.x, nox), ix2), ax[0], ax[1]); unpack2(mul2(add2(lx.y, nox), ix2), ax[2], ax[3]);
-      unpack2(mul2(add2(hx.x, nox), ix2), bx[0], bx[1]); unpack2(mul2(add2(hx.y, nox), ix2), bx[2], bx[3]);
-      unpack2(mul2(add2(ly.x, noy), iy2), ay[0], ay[1]); unpack2(mul2(add2(ly.y, noy), iy2), ay[2], ay[3]);
-      unpack2(mul2(add2(hy.x, noy), iy2), by[0], by[1]); unpack2(mul2(add2(hy.y, noy), iy2), by[2], by[3]);
-      unpack2(mul2(add2(lz.x, noz), iz2), az[0], az[1]); unpack2(mul2(add2(lz.y, noz), iz2), az[2], az[3]);
-      unpack2(mul2(add2(hz.x, noz), iz2), bz[0], bz[1]); unpack2(mul2(add2(hz.y, noz), iz2), bz[2], bz[3]);
-      float tn[4];
-      int cc[4] = {ch.x, ch.y, ch.z, ch.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float t0 = fmaxf(fmaxf(fminf(ax[c], bx[c]), fminf(ay[c], by[c])), fmaxf(fminf(az[c], bz[c]), 0.0f));
-        const float t1 = fminf(fminf(fmaxf(ax[c], bx[c]), fmaxf(ay[c], by[c])), fminf(fmaxf(az[c], bz[c]), t_cull)) * 1.0000005f;
-        tn[c] = (cc[c] != kEmpty && t0 <= t1) ? t0 : FLT_MAX;
-      }
-#define CSWAP(i, j)                                   \
-  if (tn[i] > tn[j]) {                                \
-    const float tt = tn[i]; tn[i] = tn[j]; tn[j] = tt; \
-    const int ct = cc[i]; cc[i] = cc[j]; cc[j] = ct;  \
-  }
-      CSWAP(0, 1) CSWAP(2, 3) CSWAP(0, 2) CSWAP(1, 3) CSWAP(1, 2)
-#undef CSWAP
-#pragma unroll
-      for (int c = 3; c >= 0; --c)
-        if (tn[c] != FLT_MAX && sp < kStack) stack[sp++] = make_int2(cc[c], __float_as_int(tn[c]));
-    }
-    // leaf phase: all lanes holding a leaf run the fp64 triangle tests together
-    if (pending != 0) {
-      const int lfirst = (~pending) >> 2, count = ((~pending) & 3) + 1;
-      pending = 0;
-      const double Ox = ox, Oy = oy, Oz = oz, Dx = dx, Dy = dy, Dz = dz;
-      for (int i = 0; i < count; ++i) {
-        const float4* tp = tris + 3 * (size_t)(lfirst + i);
-        const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
-        double t;
-        if (ray_triangle(Ox, Oy, Oz, Dx, Dy, Dz, a, b, c, t)) {
-          const int id = __float_as_int(c.y);
-          if (t < t_best || (t == t_best && best_tri >= 0 && id < best_tri)) {
-            t_best = t;
-            best_tri = id;
-            t_cull = __double2float_ru(t);
-          }
-        }
-      }
-    }
-    // a ray whose stack is empty is done: hand its result over, the lane takes a new ray at the top of the loop
-    if (my >= 0 && pending == 0 && sp == 0) {
-      emit(my, best_tri >= 0, t_best, best_tri, dx, dy, dz);
-      my = -1;
-    }
-  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -545,10 +436,14 @@ elg_depth_camera_kernel(const GridView gv, const float4* __restrict__ nodes, con
   const float qx = cam_rot[4 * e], qy = cam_rot[4 * e + 1], qz = cam_rot[4 * e + 2], qw = cam_rot[4 * e + 3];
   float noise = 0.0f;
   if (cp.noise_scale != 0.0f && noise_u) noise = mul_r(cp.noise_scale, sub_r(noise_u[e], 0.5f));
-  auto finish_pixel = [&](const int r, const bool ok, const double t_hit, const float dx, const float dy, const float dz) {
+  for (int r = threadIdx.x; r < npx; r += blockDim.x) {
+    float dx, dy, dz;
+    quat_apply_r(qx, qy, qz, qw, ray_dirs[3 * r], ray_dirs[3 * r + 1], ray_dirs[3 * r + 2], dx, dy, dz);
+    Hit h;
+    const bool ok = trace_any<kGrid>(gv, nodes, tris, px, py, pz, dx, dy, dz, cp.far_clip, h);
     float d = -cp.far_clip;
     if (ok) {
-      const float t = (float)t_hit;
+      const float t = (float)h.t;
       const float hx = add_r(px, mul_r(t, dx)), hy = add_r(py, mul_r(t, dy)), hz = add_r(pz, mul_r(t, dz));
       d = -norm3_t(sub_r(hx, px), sub_r(hy, py), sub_r(hz, pz));     // torch.norm(hits - camera_pos) (:464)
     }
@@ -556,29 +451,6 @@ elg_depth_camera_kernel(const GridView gv, const float4* __restrict__ nodes, con
     d = add_r(d, noise);
     d = fminf(fmaxf(d, -cp.far_clip), -cp.near_clip);
     s_img[r] = d;
-  };
-  if (kGrid) {
-    for (int r = threadIdx.x; r < npx; r += blockDim.x) {
-      float dx, dy, dz;
-      quat_apply_r(qx, qy, qz, qw, ray_dirs[3 * r], ray_dirs[3 * r + 1], ray_dirs[3 * r + 2], dx, dy, dz);
-      Hit h;
-      const bool ok = trace_any<kGrid>(gv, nodes, tris, px, py, pz, dx, dy, dz, cp.far_clip, h);
-      finish_pixel(r, ok, h.t, dx, dy, dz);
-    }
-  } else {
-    // every warp streams a contiguous block of the image's pixels through the traversal: a lane that finishes a ray takes the next
-    // pixel of its warp's block at once
-    const int nwarps = blockDim.x >> 5, warp = threadIdx.x >> 5;
-    const int per = (npx + nwarps - 1) / nwarps;
-    const int first = min(npx, warp * per), last = min(npx, first + per);
-    trace_stream(nodes, tris, first, last, cp.far_clip,
-                 [&](const int r, float& ox, float& oy, float& oz, float& dx, float& dy, float& dz) {
-                   ox = px; oy = py; oz = pz;
-                   quat_apply_r(qx, qy, qz, qw, ray_dirs[3 * r], ray_dirs[3 * r + 1], ray_dirs[3 * r + 2], dx, dy, dz);
-                 },
-                 [&](const int r, const bool ok, const double t_hit, const int, const float dx, const float dy, const float dz) {
-                   finish_pixel(r, ok, t_hit, dx, dy, dz);
-                 });
   }
   __syncthreads();
   const float* src = s_img;
