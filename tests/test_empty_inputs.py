@@ -44,8 +44,11 @@ def test_step_torques_reset_with_zero_envs_leave_everything_untouched():
     rp, rb = env._reset_native_synced()
     assert lib.elg_resample_commands(C.byref(dims0), C.byref(rp), env.episode_length_buf.data_ptr(), env.commands.data_ptr(), None, None, s) == 0
     assert lib.elg_reset_envs(C.byref(dims0), C.byref(rp), C.byref(env._params), C.byref(rb), s) == 0
-    # an env-id list of length zero (reset_idx / _compute_torques on no envs)
-    ids = torch.zeros(0, dtype=torch.int64, device=DEV)
+    # an env-id list of length zero (a non-NULL pointer with num_ids == 0; NULL means "all envs" in this ABI, and torch hands out NULL
+    # for an empty tensor, which is why the host classes return before the call when the index tensor is empty)
+    ids1 = torch.zeros(1, dtype=torch.int64, device=DEV)
+    ids = ids1[:0]
+    assert ids.data_ptr() == ids1.data_ptr() != 0
     assert lib.elg_compute_torques(C.byref(env._dims), C.byref(env._params), env.actions.data_ptr(), env.dof_state.data_ptr(), env.last_dof_vel.data_ptr(),
                                    env.p_gains.data_ptr(), env.d_gains.data_ptr(), env.torque_limits.data_ptr(), env.default_dof_pos.data_ptr(),
                                    env.torques.data_ptr(), ids.data_ptr(), 0, s) == 0
