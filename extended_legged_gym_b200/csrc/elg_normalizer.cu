@@ -586,12 +586,12 @@ int elg_normalize_observations(int64_t num_rows, int32_t num_cols, const float* 
   if (num_rows < 0 || num_cols < 1) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: num_rows < 0 or num_cols < 1");
   if (num_cols > 32 * elg::kNormMaxTiles) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: more than 1920 columns");
   if (num_rows * (int64_t)num_cols >= ((int64_t)1 << 40)) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: batch too large");
+  // (an empty batch first: torch hands out NULL for the storage of an empty tensor)
+  if (num_rows == 0) return training ? elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: an empty batch cannot update the statistics") : ELG_OK;
   if (!x || !mean || !var || !std || !count) return elg::set_error(ELG_ERR_NULL_POINTER, "normalizer: x / mean / var / std / count is NULL");
   if (training && !scratch) return elg::set_error(ELG_ERR_NULL_POINTER, "normalizer: training mode needs the scratch buffer");
   if (scratch && (reinterpret_cast<uintptr_t>(scratch) & 15u) != 0) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: scratch must be 16-byte aligned");
   if ((rew_out && !rew) || (dones_out && !dones)) return elg::set_error(ELG_ERR_NULL_POINTER, "normalizer: reward / done destination without a source");
-  if (training && num_rows == 0) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: an empty batch cannot update the statistics");
-  if (num_rows == 0) return ELG_OK;
   const elg::NormGeom g = elg::make_geom(num_rows, num_cols);
   // 32-bit row offsets inside one row block / one apply block
   if ((int64_t)g.rows_per_part * num_cols >= ((int64_t)1 << 31)) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "normalizer: batch too large");
