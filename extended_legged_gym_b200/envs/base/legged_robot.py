@@ -430,6 +430,15 @@ class LeggedRobot(BaseTask, LeggedRobotRewMixin):
         return self._hmin
 
     def _sync_native(self):
+        # the library launches on the CURRENT device (its per-device caches and the kernels' pointers must agree with the stream)
+        idx = self.__dict__.get("_device_index")
+        if idx is None:
+            idx = torch.device(self.device).index
+            idx = torch.cuda.current_device() if idx is None else idx
+            object.__setattr__(self, "_device_index", idx)
+        if torch.cuda.current_device() != idx:
+            raise _lib.ElgError(f"this env lives on cuda:{idx} but cuda:{torch.cuda.current_device()} is the current device: "
+                                f"wrap the call in `with torch.cuda.device({idx!r}):` (one env object per GPU, one process per GPU is the intended use)")
         if getattr(self, "_dims", None) is None:
             self._dims = self._native_dims()
         if getattr(self, "_params_dirty", True):
