@@ -557,12 +557,14 @@ __device__ __forceinline__ Closest closest_on_triangle(const double px, const do
 template <typename F>
 __device__ __forceinline__ void visit_near(const float4* __restrict__ nodes, const float4* __restrict__ tris, const float px, const float py,
                                            const float pz, float r2, F&& f) {
-  int stack_c[kStack];
-  float stack_d[kStack];
+  int2 stack[kStack];      // (child code, lower bound of the squared distance): one 8-byte local store per push
   int sp = 0;
-  stack_c[sp] = 0;
-  stack_d[sp++] = 0.0f;
-  // warp-coherent while-while, as in trace(): node phase until no lane searches, then all pending leaves together
+  stack[sp++] = make_int2(0, __float_as_int(0.0f));
+  // warp-coherent while-while, as in trace(): node phase until no lane searches, then all pending leaves together.  The box
+  // distances of two children at a time go through the packed fp32 pipe (same individually rounded values as the scalar form).
+  const f32x2 pxp = pack2(px, px), pyp = pack2(py, py), pzp = pack2(pz, pz);
+  const f32x2 pxn = pack2(-px, -px), pyn = pack2(-py, -py), pzn = pack2(-pz, -pz);
+  const f32x2 neg1 = pack2(-1.0f, -1.0f);
   const unsigned wmask = __activemask();
   int pending = 0;
   for (;;) {
@@ -571,24 +573,31 @@ __device__ __forceinline__ void visit_near(const float4* __restrict__ nodes, con
       if (!__any_sync(wmask, searching)) break;
       if (!searching) continue;
       --sp;
-      const int code = stack_c[sp];
-      if (stack_d[sp] > r2) continue;
+      const int2 top = stack[sp];
+      const int code = top.x;
+      if (__int_as_float(top.y) > r2) continue;
       if (code < 0) {
         pending = code;
         continue;
       }
-      const float4* np = nodes + 8 * (size_t)code;
-      const float4 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
+      const ulonglong2* np = reinterpret_cast<const ulonglong2*>(nodes + 8 * (size_t)code);
+      const ulonglong2 lx = __ldg(np), ly = __ldg(np + 1), lz = __ldg(np + 2), hx = __ldg(np + 3), hy = __ldg(np + 4), hz = __ldg(np + 5);
       const int4 ch = __ldg(reinterpret_cast<const int4*>(np + 6));
       float dn[4];
       int cc[4] = {ch.x, ch.y, ch.z, ch.w};
-      const float lox[4] = {lx.x, lx.y, lx.z, lx.w}, loy[4] = {ly.x, ly.y, ly.z, ly.w}, loz[4] = {lz.x, lz.y, lz.z, lz.w};
-      const float hix[4] = {hx.x, hx.y, hx.z, hx.w}, hiy[4] = {hy.x, hy.y, hy.z, hy.w}, hiz[4] = {hz.x, hz.y, hz.z, hz.w};
+      // lo - p and p - hi per axis (p - hi == (-1) * hi + p would fuse: it is formed as p + (-hi) with an exact negation)
+      float lxm[4], hxm[4], lym[4], hym[4], lzm[4], hzm[4];
+      unpack2(add2(lx.x, pxn), lxm[0], lxm[1]); unpack2(add2(lx.y, pxn), lxm[2], lxm[3]);
+      unpack2(add2(mul2(hx.x, neg1), pxp), hxm[0], hxm[1]); unpack2(add2(mul2(hx.y, neg1), pxp), hxm[2], hxm[3]);
+      unpack2(add2(ly.x, pyn), lym[0], lym[1]); unpack2(add2(ly.y, pyn), lym[2], lym[3]);
+      unpack2(add2(mul2(hy.x, neg1), pyp), hym[0], hym[1]); unpack2(add2(mul2(hy.y, neg1), pyp), hym[2], hym[3]);
+      unpack2(add2(lz.x, pzn), lzm[0], lzm[1]); unpack2(add2(lz.y, pzn), lzm[2], lzm[3]);
+      unpack2(add2(mul2(hz.x, neg1), pzp), hzm[0], hzm[1]); unpack2(add2(mul2(hz.y, neg1), pzp), hzm[2], hzm[3]);
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const float ex = fmaxf(fmaxf(lox[c] - px, px - hix[c]), 0.0f);
-        const float ey = fmaxf(fmaxf(loy[c] - py, py - hiy[c]), 0.0f);
-        const float ez = fmaxf(fmaxf(loz[c] - pz, pz - hiz[c]), 0.0f);
+        const float ex = fmaxf(fmaxf(lxm[c], hxm[c]), 0.0f);
+        const float ey = fmaxf(fmaxf(lym[c], hym[c]), 0.0f);
+        const float ez = fmaxf(fmaxf(lzm[c], hzm[c]), 0.0f);
         const float d = (ex * ex + ey * ey + ez * ez) * 0.999999f;     // lower bound of the squared distance to the box
         dn[c] = (cc[c] != kEmpty && d <= r2) ? d : FLT_MAX;
       }
@@ -601,10 +610,7 @@ __device__ __forceinline__ void visit_near(const float4* __restrict__ nodes, con
 #undef CSWAP
 #pragma unroll
       for (int c = 3; c >= 0; --c)
-        if (dn[c] != FLT_MAX && sp < kStack) {
-          stack_c[sp] = cc[c];
-          stack_d[sp++] = dn[c];
-        }
+        if (dn[c] != FLT_MAX && sp < kStack) stack[sp++] = make_int2(cc[c], __float_as_int(dn[c]));
     }
     if (!__any_sync(wmask, pending != 0 || sp > 0)) break;
     if (pending != 0) {
