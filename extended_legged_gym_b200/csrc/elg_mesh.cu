@@ -421,6 +421,7 @@ elg_camera_pose_kernel(const float* __restrict__ pos, const float* __restrict__ 
 // taps tabulated by the host from torchvision itself), normalised and pushed into the env's frame ring buffer -- the
 // reference's per-env Python loop (:486-499).  28 bytes per camera in, 4 bytes per output pixel out.
 // ---------------------------------------------------------------------------------------------
+// (register cap: 72 registers / 3 CTAs per SM 5.74 Grays/s, 64 / 4 CTAs 5.94-6.01, 48 / 5 CTAs 5.44 -- far clip 2 m, r2v / r3q)
 template <bool kGrid>
 __global__ void __launch_bounds__(256, 4)
 elg_depth_camera_kernel(const GridView gv, const float4* __restrict__ nodes, const float4* __restrict__ tris, const __grid_constant__ ElgCamParams cp,
