@@ -7,7 +7,7 @@
 //   utils/depth_camera.py:402-499 DepthCameraWarp.update_depth_buffer                 -> elg_depth_camera (fused)
 //   utils/mesh_sdf.py:38-116    query_sdf_kernel (wp.mesh_query_point_sign_normal)    -> elg_sdf_query
 //
-// Data structure: a 4-wide BVH.  The host builds a binary tree top-down with binned SAH (16 bins, leaves of <= 4
+// Data structure: a 4-wide BVH.  The host builds a binary tree top-down with binned SAH (16 bins, leaves of <= 3
 // triangles -- the terrain is static, the build runs once at init), collapses it to 4 children per node and uploads
 //   nodes   128 bytes each: child boxes as SoA float4 rows (lo.x[4], lo.y[4], lo.z[4], hi.x[4], hi.y[4], hi.z[4]),
 //           int4 child codes (>= 0 inner node, < 0 leaf: ~(first << 2 | count - 1), INT_MIN empty)
@@ -24,6 +24,7 @@
 #include <math.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -796,6 +797,12 @@ struct Builder {
     std::vector<Job> todo;
     todo.push_back({0, 0, M});
     constexpr int kBins = 16;
+    // triangles per leaf (<= 4: the leaf code holds count - 1 in two bits); ELG_BVH_LEAF overrides it for measurements.  Measured on
+    // the 1.6 M-triangle terrain (profiles/r3r_bvh_leaf.txt; depth camera far clip 2 m / 10 m / incoherent rays, Mrays/s):
+    // 1: 5348 / 3606 / 2969, 2: 6599 / 4734 / 3595, 3: 6716 / 4830 / 3626, 4: 6149 / 4264 / 3408 -- an fp64 triangle test costs about as much
+    // as a node step, so smaller leaves win until the tree gets a level deeper for nothing
+    int leaf_max = 3;
+    if (const char* ev = getenv("ELG_BVH_LEAF")) { const int v = atoi(ev); if (v >= 1 && v <= 4) leaf_max = v; }
     while (!todo.empty()) {
       const Job j = todo.back();
       todo.pop_back();
@@ -811,7 +818,7 @@ struct Builder {
       N.left = N.right = -1;
       N.first = j.first;
       N.count = j.count;
-      if (j.count <= 4) continue;
+      if (j.count <= leaf_max) continue;
       // best binned split over the three axes
       int best_axis = -1, best_bin = -1;
       double best_cost = DBL_MAX;
