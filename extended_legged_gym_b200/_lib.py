@@ -201,6 +201,7 @@ def load() -> C.CDLL:
     lib.elg_actuator_net_torques.argtypes = [C.POINTER(ElgDims), vp, C.c_float] + [vp] * 7
     lib.elg_actuator_net_bind.argtypes = [vp, vp]
     lib.elg_mesh_create.argtypes = [vp, C.c_int32, vp, C.c_int32, C.POINTER(vp)]
+    lib.elg_mesh_create_ex.argtypes = [vp, C.c_int32, vp, C.c_int32, C.c_int32, C.POINTER(vp)]
     lib.elg_mesh_free.argtypes = [vp]
     if hasattr(lib, "elg_mesh_grid_info"):
         lib.elg_mesh_grid_info.argtypes = [vp, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]

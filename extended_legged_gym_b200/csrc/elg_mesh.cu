@@ -774,6 +774,7 @@ struct Builder {
   const float* V;
   const int32_t* T;
   int M;
+  int leaf_triangles = 0;   // 0: default
   std::vector<Box> tbox;
   std::vector<float> cen;   // 3 per triangle
   std::vector<int> order;
@@ -801,7 +802,8 @@ struct Builder {
     // the 1.6 M-triangle terrain (profiles/r3r_bvh_leaf.txt; depth camera far clip 2 m / 10 m / incoherent rays, Mrays/s):
     // 1: 5348 / 3606 / 2969, 2: 6599 / 4734 / 3595, 3: 6716 / 4830 / 3626, 4: 6149 / 4264 / 3408 -- an fp64 triangle test costs about as much
     // as a node step, so smaller leaves win until the tree gets a level deeper for nothing
-    int leaf_max = 3;
+    // (closest-point queries prefer 4: SDF 300 vs 266 Mpoints/s -- elg_mesh_create_ex lets the caller say which queries the mesh serves)
+    int leaf_max = leaf_triangles > 0 ? leaf_triangles : 3;
     if (const char* ev = getenv("ELG_BVH_LEAF")) { const int v = atoi(ev); if (v >= 1 && v <= 4) leaf_max = v; }
     while (!todo.empty()) {
       const Job j = todo.back();
@@ -883,8 +885,10 @@ int mfail(int code, const char* msg) { return elg::set_error(code, msg); }
 
 extern "C" {
 
-int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, ElgMesh** out) {
+int elg_mesh_create_ex(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, int32_t leaf_triangles,
+                       ElgMesh** out) {
   if (!out) return mfail(ELG_ERR_NULL_POINTER, "out is NULL");
+  if (leaf_triangles < 0 || leaf_triangles > 4) return mfail(ELG_ERR_INVALID_ARGUMENT, "leaf_triangles must be 0 (default) or 1 ... 4");
   *out = nullptr;
   if (!vertices || !triangles) return mfail(ELG_ERR_NULL_POINTER, "vertices/triangles is NULL (host pointers expected)");
   if (num_vertices < 3 || num_triangles < 1) return mfail(ELG_ERR_INVALID_ARGUMENT, "a mesh needs >= 3 vertices and >= 1 triangle");
@@ -898,6 +902,7 @@ int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* 
   B.V = vertices;
   B.T = triangles;
   B.M = num_triangles;
+  B.leaf_triangles = leaf_triangles;
   B.run();
 
   // collapse: every 4-wide node adopts grandchildren, widest-area child first
@@ -1108,6 +1113,10 @@ static elg::GridView grid_view(const ElgMesh* m) {
     g.cellz = m->grid_cellz; g.celltri = m->grid_celltri;
   }
   return g;
+}
+
+int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, ElgMesh** out) {
+  return elg_mesh_create_ex(vertices, num_vertices, triangles, num_triangles, 0, out);
 }
 
 int elg_set_mesh_tuning(int use_grid) {

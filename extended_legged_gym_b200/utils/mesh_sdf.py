@@ -51,9 +51,9 @@ class MeshSDF:
                     print(f"Failed to load mesh {path}: file not found")
                     continue
                 v, f = load_obj(path)
-                self.meshes[path] = Mesh(v, f, self.device)
+                self.meshes[path] = Mesh(v, f, self.device, leaf_triangles=4)
         elif self.cfg.vertices is not None and self.cfg.triangles is not None:
-            self.meshes["custom_mesh"] = Mesh(self.cfg.vertices, self.cfg.triangles, self.device)
+            self.meshes["custom_mesh"] = Mesh(self.cfg.vertices, self.cfg.triangles, self.device, leaf_triangles=4)
         else:
             raise ValueError("No mesh paths or vertices/triangles provided for SDF calculation.")
         if not self.meshes:

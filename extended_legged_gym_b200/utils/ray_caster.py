@@ -26,7 +26,8 @@ from .. import _lib
 class Mesh:
     """Device-resident BVH of one static triangle mesh (the counterpart of ``wp.Mesh``)."""
 
-    def __init__(self, vertices, triangles, device="cuda:0"):
+    def __init__(self, vertices, triangles, device="cuda:0", leaf_triangles=0):
+        """leaf_triangles: triangles per BVH leaf, 0 = the library's default (3, best for ray casts); MeshSDF asks for 4"""
         v = np.ascontiguousarray(np.asarray(vertices.cpu() if torch.is_tensor(vertices) else vertices), dtype=np.float32).reshape(-1, 3)
         t = np.ascontiguousarray(np.asarray(triangles.cpu() if torch.is_tensor(triangles) else triangles), dtype=np.int32).reshape(-1, 3)
         self.device = torch.device(device)
@@ -36,8 +37,8 @@ class Mesh:
         self.num_vertices, self.num_triangles = len(v), len(t)
         handle = C.c_void_p()
         with torch.cuda.device(self.device):
-            rc = self._lib.elg_mesh_create(v.ctypes.data, len(v), t.ctypes.data, len(t), C.byref(handle))
-        _lib.check(rc, "elg_mesh_create")
+            rc = self._lib.elg_mesh_create_ex(v.ctypes.data, len(v), t.ctypes.data, len(t), int(leaf_triangles), C.byref(handle))
+        _lib.check(rc, "elg_mesh_create_ex")
         self.id = handle.value
         nt, nn = C.c_int32(), C.c_int32()
         b = (C.c_float * 6)()

@@ -316,6 +316,10 @@ typedef struct ElgMesh ElgMesh;
 /* vertices [V,3] fp32 and triangles [M,3] int32 are HOST pointers (the reference also builds from numpy arrays); the
  * BVH is built on the host once and uploaded to the current CUDA device. */
 int elg_mesh_create(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, ElgMesh** out);
+/* The same with the leaf size of the BVH chosen by the caller: leaf_triangles = 0 (default: 3, best for ray casts on B200) or 1 ... 4
+ * (4 is best for closest-point / SDF queries, where a leaf's triangles are all evaluated anyway).  Results do not depend on it. */
+int elg_mesh_create_ex(const float* vertices, int32_t num_vertices, const int32_t* triangles, int32_t num_triangles, int32_t leaf_triangles,
+                       ElgMesh** out);
 int elg_mesh_free(ElgMesh* mesh);
 int elg_mesh_info(const ElgMesh* mesh, int32_t* num_triangles, int32_t* num_nodes, float* bounds6);
 /* Height-field-derived meshes (vertices on a regular xy grid, one or more layers, two triangles per cell -- the terrain meshes of
