@@ -380,6 +380,50 @@ def secondary_benchmarks(dev, world, rank, dist, quick=False, only_depth=False, 
                              "collectives_in_timed_region": 1 if comm is not None else 0, "resets_in_one_timed_graph_all_ranks": resets3}
     del envs3, g3, stats3
     torch.cuda.empty_cache()
+    # ---- config 1 (BASELINE configs[0], the reference's CPU-runnable case): anymal_c_flat, 4096 envs, no height scan -- the same
+    # two kernels per step as the headline, every step on a different state replica
+    n1 = 4096
+    rd1, wr1 = algorithmic_bytes_per_env(12, 4, 17, 4, 0, 48, 9, 4, False)
+    bytes1 = (rd1 + wr1) * n1
+    n_rep1 = max(2, -(-2 * L2_BYTES // bytes1) + 1)
+    envs1 = []
+    for r_ in range(n_rep1):
+        cfg1, spec1, st1 = common.make_case_state("anymal_c_flat", n1, seed=300 + r_)
+        cfg1.env.num_envs = n1
+        e1 = LeggedRobot(cfg1, None, SyntheticSim(cfg1, n1, dev, spec=spec1, height_samples=hf_dev, state=st1), dev, True)
+        e1.set_env_state(st1)
+        e1.noise_u = None
+        e1._sync_native()
+        envs1.append(e1)
+
+    def step1(i):
+        e = envs1[i % n_rep1]
+        e.torques = e._compute_torques(e.actions).view(e.torques.shape)
+        e._launch(L.PHASE_FUSED, 100.0, noise_step=i)
+    gs1 = torch.cuda.Stream(device=dev)
+    g1 = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(gs1):
+        for i in range(n_rep1):
+            step1(i)
+        gs1.synchronize()
+        with torch.cuda.graph(g1, stream=gs1):
+            for i in range(200):
+                step1(i)
+        g1.replay()
+        gs1.synchronize()
+        ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ea.record(gs1)
+        for _ in range(5):
+            g1.replay()
+        eb.record(gs1)
+        gs1.synchronize()
+    t1 = ea.elapsed_time(eb) * 1e-3 / 1000
+    out["config1_flat"] = {"workload": f"anymal_c_flat post-physics step (torques + fused step, no height scan, 48 observations), {n1} envs per GPU",
+                           "us_per_step": t1 * 1e6, "env_steps_per_s": n1 / t1, "algorithmic_bytes_per_step": bytes1,
+                           "achieved_gbs": bytes1 / t1 / 1e9, "frac_of_hbm_peak": bytes1 / t1 / 1e9 / peak,
+                           "l2_policy": f"{n_rep1} state replicas x {bytes1 / 1e6:.1f} MB rotated per step", "timing": "CUDA graph of 200 steps, 5 replays"}
+    del envs1, g1
+    torch.cuda.empty_cache()
     progress("config 3 done; clone / rollout / MPPI")
 
     # ---- config 5: 64 mains x 512 rollouts: state clone, then the cost-weighted update over a 20-step horizon
