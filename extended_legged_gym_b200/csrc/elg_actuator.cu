@@ -16,8 +16,42 @@ namespace elg {
 
 constexpr int kActThreads = 64;
 
-// 1 / (1 + e^-x): the correctly rounded reciprocal IS the IEEE quotient 1.0f / y, without the general division sequence
-__device__ __forceinline__ float sigmoid_f(float x) { return __frcp_rn(1.0f + expf(-x)); }
+// Gate activations.  The row's ~3000 instructions used to be 55 % libdevice expf / tanhf / __frcp_rn (range checks, an out-of-line
+// special-operand path per reciprocal, a divergent two-branch tanhf): every one of them a scheduling barrier between the eight
+// independent hidden units.  These forms are branch-free and stay inside the north-star tolerance with margin (float32 emulation
+// with every MUFU result perturbed by its documented error, tests/golden/actuator_net.npz: <= 0.45 of the 1e-5 / 1e-6 bar, the
+// libdevice forms 0.30 -- evaluation-order noise of the float32 graph itself):
+//   * MUFU.EX2 on x * log2(e) (2 ulp + the rounding of the product; the sensitivity of both functions to it is t / (1 + t)^k < 1),
+//   * 1 / y as MUFU.RCP + one Newton step (<= 1 ulp for y in [1, 1e38]),
+//   * tanh below 0.55 as the odd minimax polynomial x + x^3 P(x^2) (< 0.9 ulp), above it 1 - 2 / (e^{2|x|} + 1).
+// NaN inputs come out as NaN (the selects below are written so that an unordered compare keeps the NaN operand).
+__device__ __forceinline__ float ex2_approx(float a) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
+}
+__device__ __forceinline__ float rcp_newton(float y) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(y));
+  return fmaf(r, fmaf(-y, r, 1.0f), r);
+}
+__device__ __forceinline__ float sigmoid_f(float x) {
+  float y = 1.0f + ex2_approx(x * -1.4426950408889634f);
+  y = y > 1e38f ? 1e38f : y;   // e^-x overflows below x = -88.7: keep the Newton step finite (result 0)
+  return rcp_newton(y);
+}
+__device__ __forceinline__ float tanh_f(float x) {
+  const float ax = fabsf(x), x2 = x * x;
+  float p = -0.006715521216392517f;
+  p = fmaf(p, x2, 0.02136712521314621f);
+  p = fmaf(p, x2, -0.05391916632652283f);
+  p = fmaf(p, x2, 0.13333165645599365f);
+  p = fmaf(p, x2, -0.3333333134651184f);
+  const float small = fmaf(x * x2, p, x);
+  const float t = ex2_approx((ax > 10.0f ? 10.0f : ax) * 2.8853900817779268f);   // tanh(10) rounds to 1
+  const float big = copysignf(fmaf(-2.0f, rcp_newton(t + 1.0f), 1.0f), x);
+  return ax >= 0.55f ? big : small;   // NaN: the compare is false, the polynomial propagates it
+}
 
 // The 973 parameters of the bound network (elg_actuator_net_bind) in the constant bank: every weight is a warp-uniform operand
 // with a compile-time offset, i.e. an immediate constant-bank operand of the FFMA itself -- no shared-memory load, no register.
@@ -45,34 +79,36 @@ __device__ __forceinline__ void lstm_cell(const float* __restrict__ s_w, const f
       for (int k = 0; k < 8; ++k) b = fmaf(actw<kConst>(s_w, kWhh + r * 8 + k), h[k], b);
       g[q] = a + b;
     }
-    const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanhf(g[2]), og = sigmoid_f(g[3]);
+    const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanh_f(g[2]), og = sigmoid_f(g[3]);
     c[u] = fg * c[u] + ig * gg;
-    hn[u] = og * tanhf(c[u]);
+    hn[u] = og * tanh_f(c[u]);
   }
 #pragma unroll
   for (int u = 0; u < 8; ++u) h[u] = hn[u];
 }
 
-template <bool kConst>
+// kEarly (shared-memory weights of the BOUND blob, whose contents the caller has declared frozen -- elg_actuator_net_bind): the
+// weights are staged before griddepcontrol.wait, i.e. under the tail of the preceding kernel of the stream.  The state loads are
+// requested before the barrier that publishes the weights, so the two round trips overlap.
+template <bool kConst, bool kEarly>
 __global__ void __launch_bounds__(kActThreads)
 elg_actuator_kernel(const int64_t rows, const int D, const float action_scale, const float* __restrict__ weights,
                     const float* __restrict__ actions, const float* __restrict__ dof_state, const float* __restrict__ default_dof_pos,
                     float* __restrict__ hidden, float* __restrict__ cell, float* __restrict__ torques) {
   __shared__ __align__(16) float s_w[kConst ? 4 : ELG_ACTNET_WORDS];
   pdl_launch_dependents();
-  pdl_wait();
+  if (!kEarly) pdl_wait();
   if (!kConst) {
     for (int i = threadIdx.x; i < ELG_ACTNET_WORDS / 4; i += kActThreads)
       reinterpret_cast<float4*>(s_w)[i] = __ldg(reinterpret_cast<const float4*>(weights) + i);
-    __syncthreads();
   }
+  if (kEarly) pdl_wait();
   const int64_t r = (int64_t)blockIdx.x * kActThreads + threadIdx.x;
-  if (r >= rows) return;
-  const int j = (int)(r % D);
-  const float2 pv = *reinterpret_cast<const float2*>(dof_state + 2 * r);
-  float x[2];
-  x[0] = (actions[r] * action_scale + __ldg(default_dof_pos + j) - pv.x) * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE);
-  x[1] = pv.y * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE + 1);
+  const bool live = r < rows;
+  const int64_t rr = live ? r : rows - 1;   // surplus threads of the last CTA shadow the last row (they reach the barrier, store nothing)
+  const int j = (int)(rr % D);
+  const float2 pv = *reinterpret_cast<const float2*>(dof_state + 2 * rr);
+  const float act = actions[rr], q0 = __ldg(default_dof_pos + j);
   float h0[8], c0[8], h1[8], c1[8];
   auto load8 = [&](const float* base, float (&v)[8]) {
     const float4 a = *reinterpret_cast<const float4*>(base), b = *reinterpret_cast<const float4*>(base + 4);
@@ -83,15 +119,20 @@ elg_actuator_kernel(const int64_t rows, const int D, const float action_scale, c
     *reinterpret_cast<float4*>(base + 4) = make_float4(v[4], v[5], v[6], v[7]);
   };
   const int64_t plane = rows * 8;   // layer stride of the [2, rows, 8] state tensors
-  load8(hidden + r * 8, h0);
-  load8(cell + r * 8, c0);
-  load8(hidden + plane + r * 8, h1);
-  load8(cell + plane + r * 8, c1);
+  load8(hidden + rr * 8, h0);
+  load8(cell + rr * 8, c0);
+  load8(hidden + plane + rr * 8, h1);
+  load8(cell + plane + rr * 8, c1);
+  if (!kConst) __syncthreads();   // the weights
+  float x[2];
+  x[0] = (act * action_scale + q0 - pv.x) * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE);
+  x[1] = pv.y * actw<kConst>(s_w, ELG_ACTNET_IN_SCALE + 1);
   lstm_cell<2, kConst, ELG_ACTNET_W_IH0, ELG_ACTNET_W_HH0, ELG_ACTNET_B_IH0, ELG_ACTNET_B_HH0>(s_w, x, h0, c0);
   lstm_cell<8, kConst, ELG_ACTNET_W_IH1, ELG_ACTNET_W_HH1, ELG_ACTNET_B_IH1, ELG_ACTNET_B_HH1>(s_w, h0, h1, c1);
   float y = actw<kConst>(s_w, ELG_ACTNET_B_LIN);
 #pragma unroll
   for (int k = 0; k < 8; ++k) y = fmaf(actw<kConst>(s_w, ELG_ACTNET_W_LIN + k), h1[k], y);
+  if (!live) return;
   torques[r] = actw<kConst>(s_w, ELG_ACTNET_OUT_SCALE) * y;
   store8(hidden + r * 8, h0);
   store8(cell + r * 8, c0);
@@ -125,9 +166,9 @@ __device__ __forceinline__ void lstm_unit(const float* __restrict__ w_ih, const 
     for (int k = 0; k < 8; ++k) b = fmaf(w_hh[r * 8 + k], h[k], b);
     g[q] = a + b;
   }
-  const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanhf(g[2]), og = sigmoid_f(g[3]);
+  const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanh_f(g[2]), og = sigmoid_f(g[3]);
   c_u = fg * c_u + ig * gg;
-  h_u = og * tanhf(c_u);
+  h_u = og * tanh_f(c_u);
 }
 
 __global__ void __launch_bounds__(kAct8Threads)
@@ -218,9 +259,9 @@ __device__ __forceinline__ void lstm_units(const float* __restrict__ s_w, const 
       for (int k = 0; k < 8; ++k) b = fmaf(actw<kConst>(s_w, whh + r * 8 + k), h[k], b);
       g[q] = a + b;
     }
-    const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanhf(g[2]), og = sigmoid_f(g[3]);
+    const float ig = sigmoid_f(g[0]), fg = sigmoid_f(g[1]), gg = tanh_f(g[2]), og = sigmoid_f(g[3]);
     c[uu] = fg * c[uu] + ig * gg;
-    hn[uu] = og * tanhf(c[uu]);
+    hn[uu] = og * tanh_f(c[uu]);
   }
 }
 
@@ -304,10 +345,14 @@ elg_actuator_split_kernel(const int64_t rows, const int D, const float action_sc
   }
 }
 
-// 0: one thread per row, weights from the constant bank when bound (default); 2: the same with shared-memory weights; 3 / 4: the
-// unit-split form (constant bank / shared memory); 1: eight lanes per row.  Measured on B200 at 4096 envs x 12 dofs (profiles/README.md r2): 10.9 us vs
-// 13.5 us -- with eight distinct units per warp every weight load from shared memory serves 4 rows instead of 32, and the kernel
-// turns LDS-bound; the row-per-thread form stays the product path, this one stays selectable for larger networks.
+// 0 (default): one thread per row, shared-memory weights -- staged before the grid-dependency wait when the blob is the bound one;
+// 2: the same, always staged after the wait; 5: the weights as constant-bank operands (needs a bound blob); 3 / 4: the unit-split
+// form (constant bank / shared memory); 1: eight lanes per row.  Measured on B200 at 4096 envs x 12 dofs (profiles/README.md r4): with
+// libdevice expf / tanhf / __frcp_rn the row forms took 10.6 (constant bank) / 11.0 us and forms 3 / 1 12.4 / 13.5 us; with the
+// branch-free activations (3312 -> 2296 instructions per row) and the state loads requested ahead of the weight barrier forms
+// 0 / 2 / 5 / 3 take 8.6 / 9.3 / 8.6 / 9.0 us.  A form with the gate sums as packed FFMA2 on gate-interleaved weights (1912
+// instructions, bit-identical) took 10.9 us -- FFMA2 occupies the FP32 pipe for both halves, the kernel is bound by that pipe and by
+// dependent-issue latency, not by issue slots -- and was removed.
 int g_act_mode = 0;
 const float* g_act_bound[kMaxDevices] = {};   // the device blob whose contents sit in this device's constant bank
 
@@ -318,7 +363,7 @@ extern "C" {
 int elg_actuator_net_words(void) { return ELG_ACTNET_WORDS; }
 
 int elg_set_actuator_tuning(int mode) {
-  if (mode < 0 || mode > 4) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "actuator tuning mode must be 0 ... 4");
+  if (mode < 0 || mode > 5) return elg::set_error(ELG_ERR_INVALID_ARGUMENT, "actuator tuning mode must be 0 ... 5");
   elg::g_act_mode = mode;
   return ELG_OK;
 }
@@ -369,11 +414,14 @@ int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float ac
   else if (split)
     cudaLaunchKernelEx(&cfg, elg::elg_actuator_split_kernel<false>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
                        hidden, cell, torques);
-  else if (bound && elg::g_act_mode != 2)
-    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<true>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
+  else if (bound && elg::g_act_mode == 5)
+    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<true, false>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
+                       hidden, cell, torques);
+  else if (bound && elg::g_act_mode == 0)
+    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<false, true>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
                        hidden, cell, torques);
   else
-    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<false>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
+    cudaLaunchKernelEx(&cfg, elg::elg_actuator_kernel<false, false>, rows, (int)dims->num_dof, action_scale, weights, actions, dof_state, default_dof_pos,
                        hidden, cell, torques);
   return elg::check_launch("elg_actuator_net_torques");
 }

@@ -503,13 +503,14 @@ enum {
 };
 int elg_actuator_net_words(void);
 /* Kernel selection (no reference counterpart; every form returns bit-identical results): 0 (default) = one thread per (env, dof) row,
- * weights from the constant bank when a blob is bound (elg_actuator_net_bind), else from shared memory; 2 = the same, always shared
- * memory; 1 = eight lanes per row, one hidden unit each; 3 / 4 = four warps per 32 rows, two hidden units per warp (constant bank /
- * shared memory).  Measured on B200 at 4096 envs x 12 dofs: 10.5-10.8 / 11.0 / 13.5 / 11.6 us for forms 0 / 2 / 1 / 3. */
+ * shared-memory weights (staged before the grid-dependency wait when the blob is the bound one); 2 = the same, staged after the wait;
+ * 5 = the weights as constant-bank operands (bound blob only); 1 = eight lanes per row, one hidden unit each; 3 / 4 = four warps per
+ * 32 rows, two hidden units per warp (constant bank / shared memory).  B200, 4096 envs x 12 dofs: DESIGN.md 4.2b. */
 int elg_set_actuator_tuning(int mode);
-/* Optional: copy the blob into the device's constant bank (stream-ordered).  Calls of elg_actuator_net_torques that pass the SAME
- * `weights` pointer afterwards read every weight as an immediate constant operand instead of a shared-memory load; call it again after
- * changing the blob's contents, or with NULL to unbind.  One bound blob per device. */
+/* Optional: declare the blob's contents FROZEN and copy them into the device's constant bank (stream-ordered).  Calls of
+ * elg_actuator_net_torques that pass the SAME `weights` pointer afterwards may read the blob before the grid-dependency wait of a
+ * programmatic dependent launch (i.e. while the preceding kernel of the stream is still running), and forms 3 / 5 take the weights
+ * as constant operands; call it again after changing the blob's contents, or with NULL to unbind.  One bound blob per device. */
 int elg_actuator_net_bind(const float* weights, void* stream);
 int elg_actuator_net_torques(const ElgDims* dims, const float* weights, float action_scale, const float* actions, const float* dof_state,
                              const float* default_dof_pos, float* hidden, float* cell, float* torques, void* stream);

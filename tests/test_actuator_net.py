@@ -121,8 +121,9 @@ def test_actuator_kernel_matches_golden_vectors():
 
 @pytest.mark.gpu
 def test_every_kernel_form_returns_the_same_bits():
-    """elg_set_actuator_tuning: the unit-split default (constant-bank / shared-memory weights), eight lanes per row and the
-    row-per-thread forms evaluate the same expressions per hidden unit -- torques and states must agree bit for bit"""
+    """elg_set_actuator_tuning: the row-per-thread forms (shared-memory weights staged before / after the grid-dependency wait,
+    constant-bank weights), eight lanes per row and the unit-split forms evaluate the same expressions per hidden unit -- torques
+    and states must agree bit for bit"""
     n = 1000
     env, cfg, spec, st, hf = make_anymal("anymal_c_rough", n, 5)
     g = torch.Generator().manual_seed(9)
@@ -132,7 +133,7 @@ def test_every_kernel_form_returns_the_same_bits():
     lib = _lib.load()
     outs = []
     try:
-        for mode in (0, 1, 2, 3, 4):
+        for mode in (0, 1, 2, 3, 4, 5):
             lib.elg_set_actuator_tuning(mode)
             env.sea_hidden_state.copy_(h)
             env.sea_cell_state.copy_(c)
