@@ -67,6 +67,78 @@ def test_oracle_matches_live_torchscript_module_and_fixture_weights():
     torch.testing.assert_close(c2, c_ref, rtol=RTOL, atol=ATOL)
 
 
+def _emulated_activations(rng):
+    """float32 restatement of the kernel's gate activations (csrc/elg_actuator.cu: sigmoid_f / tanh_f) with every MUFU result moved
+    by up to its documented error bound (ex2.approx 2 ulp, rcp.approx 1 ulp; the Newton step leaves <= 1 ulp) -- the error budget the
+    branch-free forms were admitted on."""
+    f32 = np.float32
+    l2e = f32(1.4426950408889634)
+
+    def nudge(x, ulps):
+        return (x.view(np.int32) + rng.integers(-ulps, ulps + 1, size=x.shape).astype(np.int32)).view(np.float32)
+
+    def ex2(a):
+        return nudge(np.exp2(a.astype(np.float64)).astype(f32), 2)
+
+    def rcp(y):
+        return nudge((1.0 / y.astype(np.float64)).astype(f32), 1)
+
+    def sigmoid(x):
+        y = (f32(1) + ex2((x * -l2e).astype(f32))).astype(f32)
+        return rcp(np.minimum(y, f32(1e38)))
+
+    coef = [f32(c) for c in (-0.3333333134651184, 0.13333165645599365, -0.05391916632652283, 0.02136712521314621, -0.006715521216392517)]
+
+    def tanh(x):
+        x = x.astype(f32)
+        ax, x2 = np.abs(x), (x * x).astype(f32)
+        p = coef[4]
+        for c in coef[3::-1]:
+            p = (p.astype(np.float64) * x2 + c).astype(f32)          # fmaf
+        small = ((x * x2).astype(f32).astype(np.float64) * p + x).astype(f32)
+        t = ex2((np.minimum(ax, f32(10)) * f32(2.8853900817779268)).astype(f32))
+        big = np.copysign((f32(1) - f32(2) * rcp((t + f32(1)).astype(f32))).astype(f32), x)
+        return np.where(ax >= f32(0.55), big, small).astype(f32)
+
+    return sigmoid, tanh
+
+
+def test_kernel_activation_forms_stay_inside_the_tolerance_budget():
+    """The kernel replaces libdevice expf / tanhf / __frcp_rn by MUFU-based branch-free forms.  Their worst-case error against float64
+    and, through the whole LSTMsea over the three carried steps of the golden fixture, against the TorchScript module's outputs must
+    leave at least half of the 1e-5 / 1e-6 bar unused."""
+    rng = np.random.default_rng(0)
+    sigmoid, tanh = _emulated_activations(rng)
+    x = np.linspace(-30, 30, 600001).astype(np.float32)
+    x64 = x.astype(np.float64)
+    assert np.abs(tanh(x) - np.tanh(x64)).max() < 2.5e-7
+    err_s = np.abs(sigmoid(x) - 1 / (1 + np.exp(-x64)))
+    assert err_s.max() < 2.5e-7 and (err_s / (1 / (1 + np.exp(-x64)))).max() < 3e-6
+    assert np.isnan(tanh(np.array([np.nan], np.float32))).all()
+    z = np.load(GOLDEN)
+    f32 = np.float32
+
+    def cell(xx, h, c, wih, whh, bih, bhh):
+        g = ((xx @ wih.T + bih) + (h @ whh.T + bhh)).astype(f32)
+        i, f, gg, o = np.split(g, 4, axis=1)
+        c2 = (sigmoid(f) * c + sigmoid(i) * tanh(gg)).astype(f32)
+        return (sigmoid(o) * tanh(c2)).astype(f32), c2
+
+    h = np.zeros((2, 768, 8), f32)
+    c = np.zeros((2, 768, 8), f32)
+    worst = 0.0
+    for s in range(3):
+        a, q, qd = z[f"s{s}__actions"], z[f"s{s}__dof_pos"], z[f"s{s}__dof_vel"]
+        xin = np.stack([(a * z["action_scale"][0] + z["default_dof_pos"] - q).reshape(-1), qd.reshape(-1)], 1).astype(f32) * z["in_scale"][None]
+        h0, c0 = cell(xin, h[0], c[0], z["lstm.weight_ih_l0"], z["lstm.weight_hh_l0"], z["lstm.bias_ih_l0"], z["lstm.bias_hh_l0"])
+        h1, c1 = cell(h0, h[1], c[1], z["lstm.weight_ih_l1"], z["lstm.weight_hh_l1"], z["lstm.bias_ih_l1"], z["lstm.bias_hh_l1"])
+        t = (z["out_scale"] * (h1 @ z["linear.weight"].T + z["linear.bias"])[:, 0]).astype(f32)
+        h, c = np.stack([h0, h1]), np.stack([c0, c1])
+        for got, ref, atol in ((t.reshape(64, 12), z[f"s{s}__torques"], ATOL_TORQUE), (h, z[f"s{s}__hidden"], ATOL), (c, z[f"s{s}__cell"], ATOL)):
+            worst = max(worst, float((np.abs(got - ref) / (atol + RTOL * np.abs(ref))).max()))
+    assert worst < 0.5, worst
+
+
 def test_actuator_abi_layout_and_argument_checks():
     lib = _lib.load()
     assert lib.elg_actuator_net_words() == _lib.ACTNET_WORDS == 976
