@@ -556,7 +556,10 @@ elg_step_kernel(const __grid_constant__ ElgDims dm, const __grid_constant__ ElgS
         time_out = s_ep[e] > pr.max_episode_length;
         // main / rollout layout (batch_rollout/robot_batch_rollout.py:857-866): time-outs reset the main rows only
         const bool to_resets = pr.rows_per_main <= 0 || genv % pr.rows_per_main == 0;
-        reset = contact_term | (time_out & to_resets) | (pr.terminate_upside_down && pg[2] > 0.0f);      // (elspider.py:340-345)
+        // upside-down robots: every row (1: elspider.py:340-345, elspider_air_batch_rollout.py:176) or the main rows of the
+        // main / rollout layout only (2: anymal_c_batch_rollout.py:192-199, go2_batch_rollout.py:200)
+        const bool upside_down = pr.terminate_upside_down != 0 && pg[2] > 0.0f && (pr.terminate_upside_down != 2 || to_resets);
+        reset = contact_term | (time_out & to_resets) | upside_down;
         bf.reset_buf[genv] = reset ? 1 : 0;
         bf.time_out_buf[genv] = time_out ? 1 : 0;
       } else if (do_reward) {

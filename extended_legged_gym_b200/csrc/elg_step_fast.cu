@@ -767,7 +767,9 @@ int launch_step_fast(const ElgDims* dims, const ElgStepParams* prm, const ElgSte
   if (H != 0 && (H <= 32 * (kNJ - 1) || H > 32 * kNJ)) return 0;   // the scan is unrolled for ceil(H / 32) == kNJ
   if (H > 0 && !rollout && !prm->terrain_is_plane && buf->height_field_min == nullptr) return 0;
   if (C > 8 || B > 64) return 0;
-  if (prm->terminate_upside_down || prm->gait_2_step_hexapod) return 0;   // ElSpider variants live in the generic kernel
+  // upside-down termination and the hexapod gait pattern live in the generic kernel (the rollout-mode step has no termination:
+  // the robot-specific main / rollout classes keep the lean kernel for their horizon loop)
+  if ((prm->terminate_upside_down && !rollout) || prm->gait_2_step_hexapod) return 0;
   const bool gait = buf->gait_idx && buf->gait_prev_foot_z;
   const bool air_on = (prm->reward_mask >> ELG_REW_FEET_AIR_TIME) & 1u;
   const int sms = sm_count();

@@ -14,6 +14,8 @@ from .batch_rollout.robot_batch_rollout import RobotBatchRollout
 from .batch_rollout.robot_batch_rollout_config import RobotBatchRolloutCfg, RobotBatchRolloutCfgPPO, RobotBatchRolloutPerceptCfg
 from .batch_rollout.robot_batch_rollout_percept import RobotBatchRolloutPercept
 from .batch_rollout.robot_traj_grad_sampling import RobotTrajGradSampling
+from .anymal_c.batch_rollout.anymal_c_batch_rollout import AnymalCBatchRollout
+from .anymal_c.batch_rollout.anymal_c_batch_rollout_config import AnymalCBatchRolloutCfg, AnymalCBatchRolloutCfgPPO
 from .batch_rollout.robot_traj_grad_sampling_config import RobotTrajGradSamplingCfg, RobotTrajGradSamplingCfgPPO
 from .batch_rollout.robot_batch_rollout_nav import RobotBatchRolloutNav
 from .batch_rollout.robot_batch_rollout_nav_config import RobotBatchRolloutNavCfg, RobotBatchRolloutNavCfgPPO
@@ -26,4 +28,5 @@ TASKS = {
     "a1": (LeggedRobot, A1RoughCfg, A1RoughCfgPPO),
     "go2_rough": (Go2, Go2RoughCfg, Go2RoughCfgPPO),                      # legged_gym/envs/__init__.py:66
     "elspider_air_rough": (ElSpider, ElSpiderAirRoughCfg, ElSpiderAirRoughCfgPPO),
+    "anymal_c_batch_rollout": (AnymalCBatchRollout, AnymalCBatchRolloutCfg, AnymalCBatchRolloutCfgPPO),   # legged_gym/envs/__init__.py
 }

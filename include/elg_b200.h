@@ -150,7 +150,7 @@ typedef struct ElgStepParams {
   float gait_foot_phases[ELG_MAX_FEET];
   /* hexapod class ElSpider (envs/elspider_air/elspider.py): */
   int32_t gait_2_step_hexapod;     /* gait_2_step over the tripods (0,1,5) / (2,3,4) of six feet (:365-408) instead of the quadruped pairs */
-  int32_t terminate_upside_down;   /* reset |= projected_gravity.z > 0 (check_termination :340-345) */
+  int32_t terminate_upside_down;   /* reset |= projected_gravity.z > 0: 1 = every row (elspider.py:340-345), 2 = main rows of the main / rollout layout only (anymal_c_batch_rollout.py:192-199) */
   /* main / rollout env layout (envs/batch_rollout/robot_batch_rollout.py:119-164): 0 = flat env list; R1 = 1 + rollouts per main:
      row r is a main env iff r % R1 == 0.  check_termination (:857-866) ORs time-outs into the main rows only. */
   int32_t rows_per_main;

@@ -194,3 +194,36 @@ class BatchRolloutOracle(LeggedOracle):
                 self.extras["episode"]["reward_stage"] = float(self.cfg.rewards.reward_min_stage)
             if self.cfg.env.send_timeouts:
                 self.extras["time_outs"] = self.time_out_buf
+
+
+class RobotBatchRolloutOracle(BatchRolloutOracle):
+    """``BatchRolloutOracle`` with the deltas of the reference's robot-specific main / rollout classes
+    (envs/anymal_c/batch_rollout/anymal_c_batch_rollout.py:49-225, envs/go2/batch_rollout/go2_batch_rollout.py:49-230; the hexapod
+    variant envs/elspider_air/batch_rollout/elspider_air_batch_rollout.py:176 flags every row):
+
+      check_termination  (:192-199)  upside-down robots (projected_gravity.z > 0) are reset -- ``upside_down_rows`` = "main" (ANYmal,
+                                     Go2: main rows only) or "all" (hexapod)
+      gait scheduler     (:143-150)  stepped AFTER the env step with the env clock: gait_idx = remainder(t / period, 1) for every
+                                     row (utils/gait_scheduler.py:63-72 with ``t`` given), t = t_main before the caller advances it
+
+    Pinned to the unmodified ``AnymalCBatchRollout`` methods by tests/golden/rollout_step_anymal.npz
+    (tests/golden/make_rollout_step_golden.py --robot)."""
+
+    def __init__(self, cfg, spec, state, height_samples, num_main, rollouts, upside_down_rows="main", gait_period=1.0, **kw):
+        super().__init__(cfg, spec, state, height_samples, num_main, rollouts, **kw)
+        assert upside_down_rows in ("main", "all")
+        self.upside_down_rows = upside_down_rows
+        self.gait_period = gait_period
+        self.t_main = 0.0
+        self.gait_idx = torch.zeros(self.num_envs)
+
+    def check_termination(self):
+        super().check_termination()
+        if self.upside_down_rows == "main":
+            self.reset_buf[self.main_env_indices] |= self.projected_gravity[self.main_env_indices, 2] > 0
+        else:
+            self.reset_buf |= self.projected_gravity[:, 2] > 0
+
+    def post_physics_step(self, noise_u=None, do_reset=True):
+        super().post_physics_step(noise_u, do_reset)
+        self.gait_idx = torch.remainder(self.t_main / self.gait_period * torch.ones(self.num_envs, dtype=torch.float), 1.0)

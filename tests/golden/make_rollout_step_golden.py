@@ -8,7 +8,12 @@ The reference class cannot run its __init__ (it creates the simulator), so the e
 object's class is then switched to RobotBatchRollout, and the rollout class's own _parse_cfg / _init_env_indices /
 _prepare_reward_function run on it.  Every per-step method that runs afterwards is the rollout class's, unmodified.
 
-    python tests/golden/make_rollout_step_golden.py
+    python tests/golden/make_rollout_step_golden.py            # rollout_step.npz (tags a, b: RobotBatchRollout)
+    python tests/golden/make_rollout_step_golden.py --robot    # rollout_step_anymal.npz (tag c: AnymalCBatchRollout)
+
+Tag c switches the object's class to the robot-specific ``AnymalCBatchRollout`` (envs/anymal_c/batch_rollout/
+anymal_c_batch_rollout.py:49-225: upside-down MAIN rows terminate :192-199, the gait scheduler follows the env clock :143-150)
+on the anymal_c_rough state, with a few main and rollout robots turned upside down.
 """
 import os
 import sys
@@ -33,9 +38,18 @@ CASES = {   # tag: (case, mains, rollouts, seed, steps, step counter before the 
 }
 
 
-def reference_rollout_env(case, num_main, rollouts, spec, st, hf):
+ROBOT_CASES = {   # tag: (case, mains, rollouts, seed, steps, step counter before the first step)
+    "c": ("anymal_c_rough", 8, 7, 3, 3, 0),
+}
+UPSIDE_DOWN_ROWS = (0, 3, 8, 21, 40, 42)      # mains 0, 8, 40 (rows k * 8) and rollout rows 3, 21, 42
+
+
+def reference_rollout_env(case, num_main, rollouts, spec, st, hf, robot=False):
     rh.install()
-    from legged_gym.envs.batch_rollout.robot_batch_rollout import RobotBatchRollout as Ref
+    if robot:
+        from legged_gym.envs.anymal_c.batch_rollout.anymal_c_batch_rollout import AnymalCBatchRollout as Ref
+    else:
+        from legged_gym.envs.batch_rollout.robot_batch_rollout import RobotBatchRollout as Ref
     env = rh.make_reference_env(mg.reference_cfg_for(case), spec, st, hf)
     keep = {k: getattr(env, k).clone() for k in ("commands",)}
     env.__class__ = Ref
@@ -45,6 +59,13 @@ def reference_rollout_env(case, num_main, rollouts, spec, st, hf):
     env._init_env_indices()                 # (:119-164)
     env._prepare_reward_function()          # (:1676-1703) binds the ROLLOUT reward mixin, episode sums over all rows
     env.commands[:] = keep["commands"]
+    if robot:      # what AnymalCBatchRollout.__init__ adds (:58-98): the reference's own scheduler object with the class's config
+        from legged_gym.utils import GaitScheduler
+        from legged_gym.envs.anymal_c.batch_rollout.anymal_c_batch_rollout_config import AnymalCBatchRolloutCfg
+        env.gait_scheduler = GaitScheduler(None, env.base_quat, env.base_lin_vel, env.base_ang_vel, env.projected_gravity, env.dof_pos,
+                                           env.dof_vel, env.foot_positions, env.foot_velocities, env.total_num_envs, env.device,
+                                           gait_cfg=AnymalCBatchRolloutCfg.gait_scheduler)
+        env.t_main = 0.0
     return env
 
 
@@ -58,12 +79,15 @@ def snapshot(env):
     return snap, names
 
 
-def run_reference(case, num_main, rollouts, seed, steps, counter0):
+def run_reference(case, num_main, rollouts, seed, steps, counter0, robot=False):
     n = num_main * (1 + rollouts)
     cfg, spec, st = common.make_case_state(case, n, seed=seed, adversarial=True)
+    if robot:
+        for row in UPSIDE_DOWN_ROWS:      # half a turn about the body x axis (xyzw): projected_gravity.z = +1
+            st["root_states"][row, 3:7] = torch.tensor([1.0, 0.0, 0.0, 0.0])
     inputs = {k: v.clone() for k, v in st.items()}
     hf = mg.height_field()
-    env = reference_rollout_env(case, num_main, rollouts, spec, st, hf)
+    env = reference_rollout_env(case, num_main, rollouts, spec, st, hf, robot=robot)
     env.common_step_counter = counter0
     g = torch.Generator().manual_seed(2000 + seed)
     out = {}
@@ -78,6 +102,9 @@ def run_reference(case, num_main, rollouts, seed, steps, counter0):
         finally:
             torch.rand_like = orig
         snap, names = snapshot(env)
+        if robot:
+            snap["gait_idx"] = env.gait_scheduler.gait_idx.clone()
+            env.t_main += env.dt          # (RobotBatchRollout.step :597, after post_physics_step)
         for k, v in snap.items():
             out[f"s{s}__{k}"] = v.numpy()
         out[f"s{s}__noise_u"] = noise_u.numpy()
@@ -89,14 +116,15 @@ def run_reference(case, num_main, rollouts, seed, steps, counter0):
 
 def main():
     blob = {}
-    for tag, (case, m, r, seed, steps, c0) in CASES.items():
-        inputs, out, env = run_reference(case, m, r, seed, steps, c0)
+    robot = "--robot" in sys.argv
+    for tag, (case, m, r, seed, steps, c0) in (ROBOT_CASES if robot else CASES).items():
+        inputs, out, env = run_reference(case, m, r, seed, steps, c0, robot=robot)
         for k, v in inputs.items():
             blob[f"{tag}__in__{k}"] = v.numpy()
         for k, v in out.items():
             blob[f"{tag}__{k}"] = v
         blob[f"{tag}__meta"] = np.array([m, r, seed, steps, c0], dtype=np.int64)
-    path = os.path.join(HERE, "rollout_step.npz")
+    path = os.path.join(HERE, "rollout_step_anymal.npz" if robot else "rollout_step.npz")
     np.savez_compressed(path, **blob)
     print("wrote", path, os.path.getsize(path) // 1024, "KiB")
 

@@ -1,0 +1,200 @@
+"""Robot-specific main / rollout classes (envs/anymal_c/batch_rollout/anymal_c_batch_rollout.py:49-225,
+envs/go2/batch_rollout/go2_batch_rollout.py:49-230 in /root/reference/legged_gym/legged_gym): ``RobotBatchRolloutPercept`` plus the
+actuator-network torque path, the gait scheduler on the env clock and the reset of upside-down MAIN robots.
+not-gpu: ``RobotBatchRolloutOracle`` bit-identical to tests/golden/rollout_step_anymal.npz (generated from the unmodified
+``AnymalCBatchRollout``: tests/golden/make_rollout_step_golden.py --robot); the configs against the reference's.
+gpu: ``AnymalCBatchRollout.post_physics_step`` against the same fixture (host-driven and fused reset paths), ``step`` /
+``step_rollout`` / ``rollout_batch`` with the actuator network."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+import common  # noqa: E402
+from oracle.rollout_oracle import RobotBatchRolloutOracle  # noqa: E402
+from oracle import ref_harness as rh  # noqa: E402
+from extended_legged_gym_b200 import _lib, synthetic  # noqa: E402
+import test_rollout_step as trs  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_step_anymal.npz")
+ACTNET = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "actuator_net.npz")
+DEV = "cuda:0"
+CASE = "anymal_c_rough"
+
+
+def load(tag="c"):
+    old = trs.GOLDEN
+    trs.GOLDEN = GOLDEN
+    try:
+        return trs.load(tag)
+    finally:
+        trs.GOLDEN = old
+
+
+def test_robot_rollout_oracle_matches_reference_fixture():
+    m, r, seed, c0, inputs, outs, names = load()
+    cfg_cls, spec_fn, _ = common.CASES[CASE]
+    ora = RobotBatchRolloutOracle(cfg_cls(), spec_fn(), {k: v.clone() for k, v in inputs.items()}, synthetic.make_height_field(seed=0), m, r)
+    ora.common_step_counter = c0
+    main_flip = rollout_flip_kept = False
+    for s, want in enumerate(outs):
+        torch.manual_seed(5000 + 17 * s + seed)
+        ora.torques = ora.compute_torques(ora.actions).view(ora.torques.shape)
+        ora.post_physics_step(noise_u=want["noise_u"])
+        snap = trs.snapshot(ora)
+        snap["gait_idx"] = ora.gait_idx
+        trs.check(snap, want, f"c step {s}", exact=True)
+        sums = torch.stack([ora.episode_sums[k] for k in names])
+        assert torch.equal(sums, want["episode_sums"]), f"c step {s}: episode sums differ"
+        ora.t_main += ora.dt
+        rb, up = want["reset_buf"].bool(), want["projected_gravity"][:, 2] > 0
+        rollout_flip_kept |= bool((up & ~rb)[ora.rollout_env_indices].any())
+        main_flip |= s == 0 and bool(rb[40])
+    # the fixture holds an upside-down main robot that is reset and an upside-down rollout robot that is not
+    assert main_flip and rollout_flip_kept
+
+
+@pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
+def test_robot_rollout_configs_match_the_reference():
+    rh.install()
+    from legged_gym.envs.anymal_c.batch_rollout.anymal_c_batch_rollout_config import AnymalCBatchRolloutCfg as RefA
+    from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg
+    from extended_legged_gym_b200.utils.helpers import class_to_dict
+    for ours, ref in ((AnymalCBatchRolloutCfg, RefA),):
+        a, b = class_to_dict(ours), class_to_dict(ref)
+        for block in ("gait_scheduler", "control", "init_state", "commands"):
+            for k, v in b[block].items():
+                assert a[block][k] == v, f"{ours.__name__}.{block}.{k}: {a[block][k]} != {v}"
+        assert a["rewards"]["scales"] == b["rewards"]["scales"], ours.__name__
+        for k in ("max_contact_force", "base_height_target", "only_positive_rewards"):
+            assert a["rewards"][k] == b["rewards"][k], k
+        for k in ("name", "foot_name", "penalize_contacts_on", "terminate_after_contacts_on", "self_collisions"):
+            assert a["asset"][k] == b["asset"][k], k
+        for k in ("num_observations", "num_actions", "episode_length_s"):
+            assert a["env"][k] == b["env"][k], k
+        for k in ("mesh_type", "measure_heights", "curriculum"):
+            assert a["terrain"][k] == b["terrain"][k], k
+
+
+def make_env(fused, inputs, m, r):
+    from extended_legged_gym_b200.envs import AnymalCBatchRollout
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    cfg_cls, spec_fn, _ = common.CASES[CASE]
+    cfg, spec = cfg_cls(), spec_fn()
+    cfg.env.num_envs, cfg.env.rollout_envs = m, r
+    cfg.control.use_actuator_network = False          # the fixture's torques are the PD controller's (anymal_c_batch_rollout_config.py: off)
+    from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg
+    cfg.gait_scheduler = AnymalCBatchRolloutCfg.gait_scheduler      # the scheduler config the fixture's reference object was given
+    n = m * (1 + r)
+    hf = synthetic.make_height_field(seed=0)
+    ora = RobotBatchRolloutOracle(cfg_cls(), spec_fn(), {k: v.clone() for k, v in inputs.items()}, hf, m, r)    # terrain bookkeeping only
+    env = AnymalCBatchRollout(cfg, None, SyntheticSim(cfg, n, DEV, spec=spec, height_samples=hf, state={k: v.clone() for k, v in inputs.items()}), DEV, True)
+    env.set_env_state(inputs)
+    env.fused_reset = fused
+    env._rand = lambda lo, hi, shape: ((hi - lo) * torch.rand(*shape) + lo).to(DEV)
+    env._randint_like = lambda t, high: torch.randint_like(t.cpu(), high).to(DEV)
+    if getattr(ora, "custom_origins", False):
+        env.terrain_levels = ora.terrain_levels.clone().to(DEV)
+        env.terrain_types = ora.terrain_types.clone().to(DEV)
+        env.terrain_origins = ora.terrain_origins.clone().to(DEV)
+        env.env_origins = ora.env_origins.clone().to(DEV)
+    return env
+
+
+@pytest.mark.gpu
+def test_anymal_rollout_env_matches_reference_fixture():
+    m, r, seed, c0, inputs, outs, names = load()
+    env = make_env(False, inputs, m, r)
+    env.common_step_counter = c0
+    assert env._native_params().terminate_upside_down == 2
+    for s, want in enumerate(outs):
+        torch.manual_seed(5000 + 17 * s + seed)
+        env.noise_u = want["noise_u"].to(DEV)
+        env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+        env.post_physics_step()
+        torch.cuda.synchronize()
+        snap = trs.snapshot(env)
+        snap["gait_idx"] = env.gait_idx
+        trs.check(snap, want, f"c step {s}", exact=False)
+        sums = torch.stack([env.episode_sums[k] for k in names]).cpu()
+        assert torch.allclose(sums, want["episode_sums"], rtol=1e-5, atol=1e-6), f"c step {s}: episode sums differ"
+        env.t_main += env.dt
+    rb = env.reset_buf.cpu().bool()
+    up = env.projected_gravity[:, 2].cpu() > 0
+    assert bool((up & ~rb)[env.rollout_env_indices.cpu()].any())      # the upside-down rollout robot stays
+
+
+@pytest.mark.gpu
+def test_anymal_rollout_fused_reset_equals_host_path():
+    """in-kernel termination (upside-down main rows included) + in-kernel reset == the host-driven path under shared uniforms"""
+    from test_fused_reset import feed_host_path_from_table
+    m, r = 12, 5
+    n = m * (1 + r)
+    _, _, st = common.make_case_state(CASE, n, seed=9, adversarial=True)
+    for row in (0, 7, 6 * 3, 6 * 3 + 2, 6 * 7):
+        st["root_states"][row, 3:7] = torch.tensor([1.0, 0.0, 0.0, 0.0])
+    U = torch.rand(n, _lib.RESET_UNIFORMS, generator=torch.Generator().manual_seed(13)).to(DEV)
+    a, b = make_env(True, st, m, r), make_env(False, st, m, r)
+    for e in (a, b):
+        e.cfg.domain_rand.push_robots = False
+    a.reset_uniforms = U
+    feed_host_path_from_table(b, U)
+    g = torch.Generator().manual_seed(5)
+    for step in range(2):
+        u = torch.rand(n, a.num_obs, generator=g).to(DEV)
+        for env in (a, b):
+            env.noise_u = u
+            env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+            env._obs_clip_for_step = 100.0
+            env.post_physics_step()
+        torch.cuda.synchronize()
+        sa, sb = trs.snapshot(a), trs.snapshot(b)
+        for k in sb:
+            if sb[k] is not None:
+                assert torch.equal(sa[k].cpu(), sb[k].cpu()), f"step {step}: fused vs host path differ in {k}"
+        if step == 0:
+            rb = b.reset_buf.cpu().bool()
+            assert bool(rb[0]) and bool(rb[18]) and bool(rb[42])        # upside-down mains
+    assert torch.equal(a.gait_idx.cpu(), b.gait_idx.cpu())
+
+
+@pytest.mark.gpu
+def test_anymal_rollout_steps_with_the_actuator_network():
+    """step / step_rollout / rollout_batch of the robot class with the LSTM torque path on every row (``_compute_torques`` with
+    and without ``env_ids``), network state cleared for reset rows, the lean kernel kept for the rollout-mode step"""
+    from extended_legged_gym_b200.envs import AnymalCBatchRollout, AnymalCBatchRolloutCfg
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    from extended_legged_gym_b200.envs import robot_specs
+    cfg = AnymalCBatchRolloutCfg()
+    cfg.env.num_envs, cfg.env.rollout_envs = 6, 7
+    cfg.control.use_actuator_network = True
+    cfg.control.actuator_net_weights = ACTNET
+    m, r = 6, 7
+    n = m * (1 + r)
+    spec = robot_specs.anymal_c()
+    env = AnymalCBatchRollout(cfg, None, SyntheticSim(cfg, n, DEV, spec=spec, seed=4), DEV, True)
+    env.root_states[8, 3:7] = torch.tensor([1.0, 0.0, 0.0, 0.0], device=DEV)       # main 1 upside down (its rollouts follow at the sync)
+    assert env.sea_hidden_state.shape == (2, n * 12, 8) and env.num_obs == 48
+    g = torch.Generator().manual_seed(1)
+    a_main = torch.randn(m, 12, generator=g).to(DEV)
+    env.sea_hidden_state.normal_(generator=None)
+    obs, _, rew, reset, extras = env.step(a_main)
+    torch.cuda.synchronize()
+    assert obs.shape == (m, 48) and rew.shape == (m,) and reset.shape == (m,)
+    assert bool(reset[1])                                               # the upside-down main env terminated ...
+    assert float(env.sea_hidden_state_per_env[:, 8].abs().max()) == 0.0   # ... and its network state was cleared
+    t_all = env._compute_torques(env.actions).clone()
+    ids = torch.tensor([3, 9, 20], device=DEV)
+    env.sea_hidden_state.zero_(); env.sea_cell_state.zero_()
+    t_ref = env._compute_torques(env.actions).clone()
+    env.sea_hidden_state.zero_(); env.sea_cell_state.zero_()
+    assert torch.equal(env._compute_torques(env.actions, env_ids=ids), t_ref[ids]) and t_all.shape == (n, 12)
+    obs_r, _, rew_r, reset_r, _ = env.step_rollout(torch.randn(m * r, 12, generator=g).to(DEV))
+    assert obs_r.shape == (m * r, 48) and rew_r.shape == (m * r,)
+    assert abs(float(env.gait_idx[0]) - np.fmod(np.float32(env.t_rollout - env.dt) / np.float32(1.0), 1.0)) < 1e-6
+    rewards = env.rollout_batch(torch.randn(m * r, 5, 12, generator=g).to(DEV) * 0.3)
+    torch.cuda.synchronize()
+    assert rewards.shape == (m * r, 5) and bool(torch.isfinite(rewards).all())
