@@ -61,9 +61,10 @@ def test_robot_rollout_oracle_matches_reference_fixture():
 def test_robot_rollout_configs_match_the_reference():
     rh.install()
     from legged_gym.envs.anymal_c.batch_rollout.anymal_c_batch_rollout_config import AnymalCBatchRolloutCfg as RefA
-    from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg
+    from legged_gym.envs.go2.batch_rollout.go2_batch_rollout_config import Go2BatchRolloutCfg as RefG
+    from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg, Go2BatchRolloutCfg
     from extended_legged_gym_b200.utils.helpers import class_to_dict
-    for ours, ref in ((AnymalCBatchRolloutCfg, RefA),):
+    for ours, ref in ((AnymalCBatchRolloutCfg, RefA), (Go2BatchRolloutCfg, RefG)):
         a, b = class_to_dict(ours), class_to_dict(ref)
         for block in ("gait_scheduler", "control", "init_state", "commands"):
             for k, v in b[block].items():
@@ -198,3 +199,28 @@ def test_anymal_rollout_steps_with_the_actuator_network():
     rewards = env.rollout_batch(torch.randn(m * r, 5, 12, generator=g).to(DEV) * 0.3)
     torch.cuda.synchronize()
     assert rewards.shape == (m * r, 5) and bool(torch.isfinite(rewards).all())
+
+
+@pytest.mark.gpu
+def test_go2_rollout_class_steps_on_a_plane():
+    """Go2BatchRollout (envs/go2/batch_rollout/go2_batch_rollout.py:49-230) with its own config -- multi-stage reward scales, gait
+    scheduler period 0.6 s on the env clock, upside-down main robots reset -- on flat ground with the sensors switched off (the
+    config's terrain OBJ is a file of the author's machine)"""
+    from extended_legged_gym_b200.envs import Go2BatchRollout, Go2BatchRolloutCfg, robot_specs
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    cfg = Go2BatchRolloutCfg()
+    cfg.env.num_envs, cfg.env.rollout_envs, cfg.env.num_observations = 5, 3, 48
+    cfg.terrain.mesh_type, cfg.terrain.use_terrain_obj = "plane", False
+    cfg.raycaster.enable_raycast = False
+    cfg.sdf.enable_sdf = False
+    n = 5 * 4
+    env = Go2BatchRollout(cfg, None, SyntheticSim(cfg, n, DEV, spec=robot_specs.go2(), seed=2), DEV, True)
+    assert env._native_params().terminate_upside_down == 2
+    assert "feet_slip" not in env.reward_scales and "dof_pos_limits" in env.reward_scales      # stage 0 of [-0.0, -0.4] is off
+    env.root_states[4, 3:7] = torch.tensor([1.0, 0.0, 0.0, 0.0], device=DEV)                    # main 1 upside down
+    obs, _, rew, reset, _ = env.step(torch.zeros(5, 12, device=DEV))
+    torch.cuda.synchronize()
+    assert obs.shape == (5, 48) and bool(reset[1]) and bool(torch.isfinite(rew).all())
+    assert float(env.gait_idx[0]) == 0.0                                                        # remainder(t_main = 0 / 0.6, 1)
+    env.step(torch.zeros(5, 12, device=DEV))
+    assert abs(float(env.gait_idx[7]) - float(np.float32(env.dt / 0.6))) < 1e-7
