@@ -16,6 +16,8 @@ from .batch_rollout.robot_batch_rollout_percept import RobotBatchRolloutPercept
 from .batch_rollout.robot_traj_grad_sampling import RobotTrajGradSampling
 from .anymal_c.batch_rollout.anymal_c_batch_rollout import AnymalCBatchRollout
 from .anymal_c.batch_rollout.anymal_c_batch_rollout_config import AnymalCBatchRolloutCfg, AnymalCBatchRolloutCfgPPO
+from .anymal_c.batch_rollout.anymal_c_traj_grad_sampling import AnymalCTrajGradSampling
+from .anymal_c.batch_rollout.anymal_c_traj_grad_sampling_config import AnymalCTrajGradSamplingCfg, AnymalCTrajGradSamplingCfgPPO
 from .go2.batch_rollout.go2_batch_rollout import Go2BatchRollout
 from .go2.batch_rollout.go2_batch_rollout_config import Go2BatchRolloutCfg, Go2BatchRolloutCfgPPO
 from .batch_rollout.robot_traj_grad_sampling_config import RobotTrajGradSamplingCfg, RobotTrajGradSamplingCfgPPO
@@ -32,4 +34,5 @@ TASKS = {
     "elspider_air_rough": (ElSpider, ElSpiderAirRoughCfg, ElSpiderAirRoughCfgPPO),
     "anymal_c_batch_rollout": (AnymalCBatchRollout, AnymalCBatchRolloutCfg, AnymalCBatchRolloutCfgPPO),   # legged_gym/envs/__init__.py
     "go2_batch_rollout": (Go2BatchRollout, Go2BatchRolloutCfg, Go2BatchRolloutCfgPPO),
+    "anymal_c_traj_grad_sampling": (AnymalCTrajGradSampling, AnymalCTrajGradSamplingCfg, AnymalCTrajGradSamplingCfgPPO),
 }

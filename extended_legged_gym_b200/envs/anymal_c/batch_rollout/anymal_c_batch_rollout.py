@@ -29,35 +29,24 @@ from ...batch_rollout.robot_batch_rollout_percept import RobotBatchRolloutPercep
 from ..anymal import Anymal
 
 
-class AnymalCBatchRollout(Anymal, RobotBatchRolloutPercept):
-    UPSIDE_DOWN_ROWS = 2        # ElgStepParams.terminate_upside_down: main rows of the main / rollout layout only
+class GaitClockMixin:
+    """The gait scheduler of the robot-specific main / rollout classes: ``cfg.gait_scheduler`` for the phases and the swing height,
+    stepped after every env step WITH THE ENV CLOCK -- ``GaitScheduler.step(foot_positions, foot_velocities, commands, t)``
+    (utils/gait_scheduler.py:63-72): gait_idx = remainder(t / period, 1) on every row, t_main after a main step, t_rollout after a
+    rollout step (anymal_c_batch_rollout.py:143-150, anymal_c_traj_grad_sampling.py:324-331).  The step kernels keep the feet heights
+    and evaluate the foot-height tracking term; the phase is one fill behind the launch."""
 
-    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True):
-        super().__init__(cfg, sim_params, physics_engine, sim_device, headless)
+    def _init_gait_clock(self):
         g = getattr(self.cfg, "gait_scheduler", None)
-        if g is not None:          # (:66-81) the class's own scheduler config instead of Anymal's training values
+        if g is not None:
             self.gait_cfg = SimpleNamespace(dt=g.dt, period=g.period, foot_phases=list(g.foot_phases), swing_height=g.swing_height)
-            self._params_dirty = True
-        a = getattr(self.cfg, "async_gait_scheduler", None)
-        if a is not None and not hasattr(a, "dof_align_sets_idx"):
-            a = a() if isinstance(a, type) else AsyncGaitSchedulerCfg()
-        # (:84-98) like the reference object, the scheduler keeps the foot tensors of construction time (see AsyncGaitScheduler)
-        self.async_gait_scheduler = AsyncGaitScheduler(self.height_samples, self.base_quat, self.base_lin_vel, self.base_ang_vel,
-                                                       self.projected_gravity, self.dof_pos, self.dof_vel, self.foot_positions.clone(),
-                                                       self.foot_velocities.clone(), self.total_num_envs, self.device, a)
+        elif getattr(self, "gait_cfg", None) is None:
+            return
+        if self.gait_idx is None:
+            self.gait_idx = torch.zeros(self.num_envs, device=self.device)
+            self.gait_prev_foot_z = torch.zeros(self.num_envs, len(self.feet_indices), device=self.device)
+        self._params_dirty = True
 
-    def _native_params(self):
-        p = super()._native_params()
-        p.terminate_upside_down = self.UPSIDE_DOWN_ROWS
-        return p
-
-    def _compute_torques(self, actions, env_ids=None):
-        torques = super()._compute_torques(actions)
-        return torques if env_ids is None else torques[env_ids]
-
-    # ------------------------------------------------------------------------------------------
-    # gait scheduler on the env clock (utils/gait_scheduler.py:63-72 with ``t`` given)
-    # ------------------------------------------------------------------------------------------
     def _gait_follow_clock(self, t):
         if self.gait_idx is None:
             return
@@ -80,6 +69,32 @@ class AnymalCBatchRollout(Anymal, RobotBatchRolloutPercept):
         if use_graph is None and "gait_scheduler" in self.reward_scales:
             use_graph = False      # the phase of every horizon step comes from the host clock
         return super().rollout_batch(all_us, use_graph=use_graph)
+
+    _reward_gait_scheduler = Anymal._reward_gait_scheduler      # (stock term: the kernel evaluates it inside step())
+
+
+class AnymalCBatchRollout(GaitClockMixin, Anymal, RobotBatchRolloutPercept):
+    UPSIDE_DOWN_ROWS = 2        # ElgStepParams.terminate_upside_down: main rows of the main / rollout layout only
+
+    def __init__(self, cfg, sim_params=None, physics_engine=None, sim_device="cuda:0", headless=True):
+        super().__init__(cfg, sim_params, physics_engine, sim_device, headless)
+        self._init_gait_clock()        # (:66-81) the class's own scheduler config instead of Anymal's training values
+        a = getattr(self.cfg, "async_gait_scheduler", None)
+        if a is not None and not hasattr(a, "dof_align_sets_idx"):
+            a = a() if isinstance(a, type) else AsyncGaitSchedulerCfg()
+        # (:84-98) like the reference object, the scheduler keeps the foot tensors of construction time (see AsyncGaitScheduler)
+        self.async_gait_scheduler = AsyncGaitScheduler(self.height_samples, self.base_quat, self.base_lin_vel, self.base_ang_vel,
+                                                       self.projected_gravity, self.dof_pos, self.dof_vel, self.foot_positions.clone(),
+                                                       self.foot_velocities.clone(), self.total_num_envs, self.device, a)
+
+    def _native_params(self):
+        p = super()._native_params()
+        p.terminate_upside_down = self.UPSIDE_DOWN_ROWS
+        return p
+
+    def _compute_torques(self, actions, env_ids=None):
+        torques = super()._compute_torques(actions)
+        return torques if env_ids is None else torques[env_ids]
 
     def _reward_async_gait_scheduler(self):
         """(:208-221) stage-dependent weights from cfg.rewards.async_gait_scheduler"""

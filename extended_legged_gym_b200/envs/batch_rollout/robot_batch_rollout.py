@@ -302,6 +302,21 @@ class RobotBatchRollout(LeggedRobot):
         self.sim.refresh()
         P = _lib
         self._pre_step_hook_rollout()
+        if self._python_terms:
+            # subclass terms written in Python read the derived state: derive first, evaluate them with torch (no episode sums in
+            # the rollout step: compute_reward_rollout :969-985), then the registry / observations / histories
+            self._launch(P.PHASE_DERIVE, rollout=True, noise_step=noise_step)
+            rew_out = self._bufs.rollout_rew_out          # (rollout_batch points this at its reward column; a struct rebuild drops it)
+            if self.extra_reward is None or self.extra_reward.shape[0] != self.num_envs:
+                self.extra_reward = torch.zeros(self.num_envs, device=self.device)
+            extra = self.extra_reward                     # accumulated in place: the native struct keeps its pointer
+            extra.zero_()
+            for name in self._python_terms:
+                extra += getattr(self, "_reward_" + name)() * self.reward_scales[name]
+            self._sync_native()
+            self._bufs.rollout_rew_out = rew_out
+            self._launch(P.PHASE_REWARD | P.PHASE_OBS | P.PHASE_HISTORY, rollout=True, noise_step=noise_step)
+            return
         self._launch(P.PHASE_DERIVE | P.PHASE_REWARD | P.PHASE_OBS | P.PHASE_HISTORY, rollout=True, noise_step=noise_step)
 
     def _pre_step_hook_rollout(self):

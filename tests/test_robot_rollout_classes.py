@@ -224,3 +224,134 @@ def test_go2_rollout_class_steps_on_a_plane():
     assert float(env.gait_idx[0]) == 0.0                                                        # remainder(t_main = 0 / 0.6, 1)
     env.step(torch.zeros(5, 12, device=DEV))
     assert abs(float(env.gait_idx[7]) - float(np.float32(env.dt / 0.6))) < 1e-7
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# AnymalCTrajGradSampling: the DIAL-MPC reward set against the unmodified reference methods (CPU, bit for bit)
+# ---------------------------------------------------------------------------------------------------------------
+DIAL_TERMS = ("gaits", "air_time", "pos", "upright", "yaw", "vel", "ang_vel", "height", "energy", "alive", "no_fly")
+
+
+def _dial_fake_self(cls, n, seed, heading, flags_dtype):
+    """a bare object of ``cls`` carrying the tensors the terms read (the classes' __init__ needs a simulator / a GPU)"""
+    from types import SimpleNamespace
+    g = torch.Generator().manual_seed(seed)
+    o = object.__new__(cls)
+    d = o.__dict__
+    d["device"], d["total_num_envs"], d["num_envs"] = "cpu", n, n
+    d["dt"], d["t_main"], d["t_rollout"] = 0.02, 1.3, 1.46
+    d["feet_indices"] = torch.tensor([4, 8, 12, 16])
+    q = torch.randn(n, 4, generator=g)
+    rs = torch.randn(n, 13, generator=g)
+    rs[:, 3:7] = q / q.norm(dim=1, keepdim=True)
+    d["root_states"] = rs
+    d["base_quat"] = rs[:, 3:7]
+    d["commands"] = torch.randn(n, 4, generator=g)
+    d["foot_positions"] = torch.rand(n, 4, 3, generator=g) * 0.2
+    d["contact_forces"] = torch.randn(n, 17, 3, generator=g) * 2.0
+    d["last_contacts"] = torch.rand(n, 4, generator=g) < 0.5
+    d["feet_air_time"] = torch.rand(n, 4, generator=g) * (torch.rand(n, 4, generator=g) < 0.7)
+    d["projected_gravity"] = torch.randn(n, 3, generator=g)
+    d["base_lin_vel"] = torch.randn(n, 3, generator=g)
+    d["base_ang_vel"] = torch.randn(n, 3, generator=g)
+    d["torques"] = torch.randn(n, 12, generator=g) * 30
+    d["dof_vel"] = torch.randn(n, 12, generator=g) * 3
+    d["reset_buf"] = (torch.rand(n, generator=g) < 0.3).to(flags_dtype)
+    d["cfg"] = SimpleNamespace(commands=SimpleNamespace(heading_command=heading), rewards=SimpleNamespace(base_height_target=0.5))
+    return o
+
+
+@pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
+@pytest.mark.parametrize("heading", [False, True])
+def test_dial_mpc_reward_terms_equal_the_reference_methods(heading):
+    rh.install()
+    from legged_gym.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling import AnymalCTrajGradSampling as Ref
+    from extended_legged_gym_b200.envs import AnymalCTrajGradSampling
+    from extended_legged_gym_b200.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling import DialMpcRewardMixin
+    n = 257
+    for gait in ("trot", "walk", "gallop", "stand"):
+        ours = _dial_fake_self(AnymalCTrajGradSampling, n, 5, heading, torch.long)
+        ref = _dial_fake_self(Ref, n, 5, heading, torch.long)
+        ours._init_dial_mpc()
+        ours._gait = gait
+        # the tables of the reference's __init__ (:40-57), built by its own statements' values
+        ref._gait = gait
+        ref._gait_phase = {k: (torch.zeros(4) if k == "stand" else torch.tensor(v)) for k, v in DialMpcRewardMixin.GAIT_PHASES.items()}
+        ref._gait_params = {k: torch.tensor(v) for k, v in DialMpcRewardMixin.GAIT_PARAMS.items()}
+        for name in DIAL_TERMS:
+            got, want = getattr(ours, "_reward_" + name)(), getattr(ref, "_reward_" + name)()
+            assert got.shape == want.shape == (n,) and torch.equal(got.float(), want.float()), f"{name} ({gait})"
+        # the bookkeeping of air_time went through both objects the same way
+        assert torch.equal(ours.feet_air_time, ref.feet_air_time) and torch.equal(ours.last_contacts, ref.last_contacts)
+    # flags are bool in this framework: alive is then 1 - flag (the reference's expression raises on a bool tensor)
+    ours = _dial_fake_self(AnymalCTrajGradSampling, n, 6, heading, torch.bool)
+    assert torch.equal(ours._reward_alive(), (~ours.reset_buf).float())
+
+
+@pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
+def test_traj_grad_sampling_config_matches_the_reference():
+    rh.install()
+    from legged_gym.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling_config import AnymalCTrajGradSamplingCfg as Ref
+    from extended_legged_gym_b200.envs import AnymalCTrajGradSamplingCfg
+    from extended_legged_gym_b200.utils.helpers import class_to_dict
+    # (the reference's trajectory_opt / rl_warmstart blocks derive from the absent traj_sampling package -- a stub here: only the
+    # blocks defined in the tree are walked, trajectory_opt by attribute)
+    a = class_to_dict(AnymalCTrajGradSamplingCfg)
+    b = {k: class_to_dict(getattr(Ref, k)) for k in ("gait_scheduler", "control", "init_state", "commands", "rewards", "asset", "env")}
+    for block in ("gait_scheduler", "control", "init_state", "commands"):
+        for k, v in b[block].items():
+            assert a[block][k] == v, f"{block}.{k}: {a[block][k]} != {v}"
+    assert a["rewards"]["scales"] == b["rewards"]["scales"]
+    for k in ("max_contact_force", "base_height_target", "only_positive_rewards", "tracking_sigma"):
+        assert a["rewards"][k] == b["rewards"][k], k
+    for k in ("name", "foot_name", "penalize_contacts_on", "terminate_after_contacts_on", "self_collisions"):
+        assert a["asset"][k] == b["asset"][k], k
+    for k in ("num_envs", "rollout_envs", "num_observations", "num_actions", "episode_length_s"):
+        assert a["env"][k] == b["env"][k], k
+    # trajectory_opt: its base class lives in traj_sampling, so the class statement yields a stub -- the values are read off the source
+    import ast
+    import inspect
+    import re
+    src = inspect.getsource(sys.modules[Ref.__module__])
+    block = src[src.index("class trajectory_opt("):src.index("class rl_warmstart(")]
+    ref_to = {m.group(1): ast.literal_eval(m.group(2).strip()) for m in re.finditer(r"^\s+(\w+) = ([^#\n]+)", block, re.M)}
+    assert len(ref_to) >= 12
+    for k, v in ref_to.items():
+        assert a["trajectory_opt"][k] == v, f"trajectory_opt.{k}: {a['trajectory_opt'][k]} != {v}"
+
+
+@pytest.mark.gpu
+def test_anymal_traj_grad_sampling_class_on_the_device():
+    """AnymalCTrajGradSampling with its default config (stock terms only: one MPPI iteration through the CUDA-graph horizon loop),
+    and with two DIAL-MPC terms switched on: the rollout step's reward is then the stock reward plus the scaled Python terms, and
+    rollout_batch (eager with Python terms) still fills every column of its reward table"""
+    from extended_legged_gym_b200.envs import AnymalCTrajGradSampling, AnymalCTrajGradSamplingCfg, robot_specs
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    m, r = 3, 8
+    n = m * (1 + r)
+
+    def make(extra_scales=None):
+        cfg = AnymalCTrajGradSamplingCfg()
+        cfg.env.num_envs, cfg.env.rollout_envs = m, r
+        for k, v in (extra_scales or {}).items():
+            setattr(cfg.rewards.scales, k, v)
+        return AnymalCTrajGradSampling(cfg, None, SyntheticSim(cfg, n, DEV, spec=robot_specs.anymal_c(), seed=6), DEV, True)
+
+    a = make()
+    assert not a._python_terms and a.traj_opt_enabled and a.horizon_samples == 16
+    a.optimize_all_trajectories()
+    torch.cuda.synchronize()
+    assert a.node_trajectories.shape == (m, 5, 12) and bool(torch.isfinite(a.node_trajectories).all())
+    a2, b = make(), make({"upright": 0.7, "energy": 0.2})
+    assert sorted(b._python_terms) == ["energy", "upright"]
+    acts = torch.randn(m * r, 12, generator=torch.Generator().manual_seed(3)).to(DEV)
+    rew_a = a2.step_rollout(acts)[2]
+    rew_b = b.step_rollout(acts)[2]
+    torch.cuda.synchronize()
+    want = ((b._reward_upright() * 0.7 + b._reward_energy() * 0.2) * b.dt)[b.rollout_env_indices]
+    assert torch.allclose(rew_b - rew_a, want, rtol=1e-4, atol=1e-5), float((rew_b - rew_a - want).abs().max())
+    assert abs(float(a2.gait_idx[5]) - float(np.remainder(np.float32((a2.t_rollout - a2.dt) / 1.0), np.float32(1.0)))) < 1e-7
+    us = torch.randn(m * r, 4, 12, generator=torch.Generator().manual_seed(4)).to(DEV) * 0.3
+    tab = b.rollout_batch(us)
+    torch.cuda.synchronize()
+    assert tab.shape == (m * r, 4) and bool(torch.isfinite(tab).all()) and bool((tab != 0).all())
