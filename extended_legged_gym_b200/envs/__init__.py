@@ -20,6 +20,8 @@ from .anymal_c.batch_rollout.anymal_c_traj_grad_sampling import AnymalCTrajGradS
 from .anymal_c.batch_rollout.anymal_c_traj_grad_sampling_config import AnymalCTrajGradSamplingCfg, AnymalCTrajGradSamplingCfgPPO
 from .go2.batch_rollout.go2_batch_rollout import Go2BatchRollout
 from .go2.batch_rollout.go2_batch_rollout_config import Go2BatchRolloutCfg, Go2BatchRolloutCfgPPO
+from .go2.batch_rollout.go2_traj_grad_sampling import Go2TrajGradSampling
+from .go2.batch_rollout.go2_traj_grad_sampling_config import Go2TrajGradSamplingCfg, Go2TrajGradSamplingCfgPPO
 from .batch_rollout.robot_traj_grad_sampling_config import RobotTrajGradSamplingCfg, RobotTrajGradSamplingCfgPPO
 from .batch_rollout.robot_batch_rollout_nav import RobotBatchRolloutNav
 from .batch_rollout.robot_batch_rollout_nav_config import RobotBatchRolloutNavCfg, RobotBatchRolloutNavCfgPPO
@@ -35,4 +37,5 @@ TASKS = {
     "anymal_c_batch_rollout": (AnymalCBatchRollout, AnymalCBatchRolloutCfg, AnymalCBatchRolloutCfgPPO),   # legged_gym/envs/__init__.py
     "go2_batch_rollout": (Go2BatchRollout, Go2BatchRolloutCfg, Go2BatchRolloutCfgPPO),
     "anymal_c_traj_grad_sampling": (AnymalCTrajGradSampling, AnymalCTrajGradSamplingCfg, AnymalCTrajGradSamplingCfgPPO),
+    "go2_traj_grad_sampling": (Go2TrajGradSampling, Go2TrajGradSamplingCfg, Go2TrajGradSamplingCfgPPO),
 }

@@ -262,11 +262,16 @@ def _dial_fake_self(cls, n, seed, heading, flags_dtype):
 
 
 @pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
+@pytest.mark.parametrize("robot", ["anymal_c", "go2"])
 @pytest.mark.parametrize("heading", [False, True])
-def test_dial_mpc_reward_terms_equal_the_reference_methods(heading):
+def test_dial_mpc_reward_terms_equal_the_reference_methods(heading, robot):
     rh.install()
-    from legged_gym.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling import AnymalCTrajGradSampling as Ref
-    from extended_legged_gym_b200.envs import AnymalCTrajGradSampling
+    if robot == "anymal_c":
+        from legged_gym.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling import AnymalCTrajGradSampling as Ref
+        from extended_legged_gym_b200.envs import AnymalCTrajGradSampling
+    else:
+        from legged_gym.envs.go2.batch_rollout.go2_traj_grad_sampling import Go2TrajGradSampling as Ref
+        from extended_legged_gym_b200.envs import Go2TrajGradSampling as AnymalCTrajGradSampling
     from extended_legged_gym_b200.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling import DialMpcRewardMixin
     n = 257
     for gait in ("trot", "walk", "gallop", "stand"):
@@ -279,6 +284,9 @@ def test_dial_mpc_reward_terms_equal_the_reference_methods(heading):
         ref._gait_phase = {k: (torch.zeros(4) if k == "stand" else torch.tensor(v)) for k, v in DialMpcRewardMixin.GAIT_PHASES.items()}
         ref._gait_params = {k: torch.tensor(v) for k, v in DialMpcRewardMixin.GAIT_PARAMS.items()}
         for name in DIAL_TERMS:
+            if not hasattr(ref, "_reward_" + name):      # (no_fly exists in the ANYmal file only)
+                assert robot == "go2" and name == "no_fly"
+                continue
             got, want = getattr(ours, "_reward_" + name)(), getattr(ref, "_reward_" + name)()
             assert got.shape == want.shape == (n,) and torch.equal(got.float(), want.float()), f"{name} ({gait})"
         # the bookkeeping of air_time went through both objects the same way
@@ -286,13 +294,21 @@ def test_dial_mpc_reward_terms_equal_the_reference_methods(heading):
     # flags are bool in this framework: alive is then 1 - flag (the reference's expression raises on a bool tensor)
     ours = _dial_fake_self(AnymalCTrajGradSampling, n, 6, heading, torch.bool)
     assert torch.equal(ours._reward_alive(), (~ours.reset_buf).float())
+    if robot == "go2":      # (its reference expression converts the flags: bool works there too)
+        ref = _dial_fake_self(Ref, n, 6, heading, torch.bool)
+        assert torch.equal(ours._reward_alive(), ref._reward_alive())
 
 
 @pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
-def test_traj_grad_sampling_config_matches_the_reference():
+@pytest.mark.parametrize("robot", ["anymal_c", "go2"])
+def test_traj_grad_sampling_config_matches_the_reference(robot):
     rh.install()
-    from legged_gym.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling_config import AnymalCTrajGradSamplingCfg as Ref
-    from extended_legged_gym_b200.envs import AnymalCTrajGradSamplingCfg
+    if robot == "anymal_c":
+        from legged_gym.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling_config import AnymalCTrajGradSamplingCfg as Ref
+        from extended_legged_gym_b200.envs import AnymalCTrajGradSamplingCfg
+    else:
+        from legged_gym.envs.go2.batch_rollout.go2_traj_grad_sampling_config import Go2TrajGradSamplingCfg as Ref
+        from extended_legged_gym_b200.envs import Go2TrajGradSamplingCfg as AnymalCTrajGradSamplingCfg
     from extended_legged_gym_b200.utils.helpers import class_to_dict
     # (the reference's trajectory_opt / rl_warmstart blocks derive from the absent traj_sampling package -- a stub here: only the
     # blocks defined in the tree are walked, trajectory_opt by attribute)
@@ -355,3 +371,25 @@ def test_anymal_traj_grad_sampling_class_on_the_device():
     tab = b.rollout_batch(us)
     torch.cuda.synchronize()
     assert tab.shape == (m * r, 4) and bool(torch.isfinite(tab).all()) and bool((tab != 0).all())
+
+
+@pytest.mark.gpu
+def test_go2_traj_grad_sampling_rewards_are_the_python_terms():
+    """Go2TrajGradSampling with its default config: six DIAL-MPC terms and no stock term -- the rollout step's reward is exactly
+    their scaled sum (evaluated between the DERIVE launch and the registry launch), rollout_batch fills its table"""
+    from extended_legged_gym_b200.envs import Go2TrajGradSampling, Go2TrajGradSamplingCfg, robot_specs
+    from extended_legged_gym_b200.sim_backend import SyntheticSim
+    cfg = Go2TrajGradSamplingCfg()
+    cfg.env.num_envs, cfg.env.rollout_envs = 2, 5
+    env = Go2TrajGradSampling(cfg, None, SyntheticSim(cfg, 12, DEV, spec=robot_specs.go2(), seed=8), DEV, True)
+    scales = {"gaits": 0.1, "upright": 0.5, "yaw": 0.3, "vel": 1.0, "ang_vel": 0.3, "height": 10.0}
+    assert not env._kernel_terms and sorted(env._python_terms) == sorted(scales)
+    rew = env.step_rollout(torch.randn(10, 12, generator=torch.Generator().manual_seed(2)).to(DEV))[2]
+    torch.cuda.synchronize()
+    env.t_rollout -= env.dt            # the terms saw the clock before step_rollout advanced it
+    want = sum(getattr(env, "_reward_" + k)() * s for k, s in scales.items()) * env.dt
+    env.t_rollout += env.dt
+    assert torch.allclose(rew, want[env.rollout_env_indices], rtol=1e-5, atol=1e-6), float((rew - want[env.rollout_env_indices]).abs().max())
+    tab = env.rollout_batch(torch.randn(10, 3, 12, generator=torch.Generator().manual_seed(3)).to(DEV) * 0.3)
+    torch.cuda.synchronize()
+    assert tab.shape == (10, 3) and bool(torch.isfinite(tab).all()) and bool((tab != 0).all())
