@@ -21,6 +21,8 @@ from .anymal_c.batch_rollout.anymal_c_traj_grad_sampling_config import AnymalCTr
 from .go2.batch_rollout.go2_batch_rollout import Go2BatchRollout
 from .go2.batch_rollout.go2_batch_rollout_config import Go2BatchRolloutCfg, Go2BatchRolloutCfgPPO
 from .go2.batch_rollout.go2_traj_grad_sampling import Go2TrajGradSampling
+from .elspider_air.batch_rollout.elspider_air_batch_rollout import ElSpiderAirBatchRollout
+from .elspider_air.batch_rollout.elspider_air_batch_rollout_config import ElSpiderAirBatchRolloutCfg, ElSpiderAirBatchRolloutCfgPPO
 from .go2.batch_rollout.go2_traj_grad_sampling_config import Go2TrajGradSamplingCfg, Go2TrajGradSamplingCfgPPO
 from .batch_rollout.robot_traj_grad_sampling_config import RobotTrajGradSamplingCfg, RobotTrajGradSamplingCfgPPO
 from .batch_rollout.robot_batch_rollout_nav import RobotBatchRolloutNav
@@ -38,4 +40,5 @@ TASKS = {
     "go2_batch_rollout": (Go2BatchRollout, Go2BatchRolloutCfg, Go2BatchRolloutCfgPPO),
     "anymal_c_traj_grad_sampling": (AnymalCTrajGradSampling, AnymalCTrajGradSamplingCfg, AnymalCTrajGradSamplingCfgPPO),
     "go2_traj_grad_sampling": (Go2TrajGradSampling, Go2TrajGradSamplingCfg, Go2TrajGradSamplingCfgPPO),
+    "elspider_air_batch_rollout": (ElSpiderAirBatchRollout, ElSpiderAirBatchRolloutCfg, ElSpiderAirBatchRolloutCfgPPO),
 }

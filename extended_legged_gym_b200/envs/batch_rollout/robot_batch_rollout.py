@@ -57,6 +57,9 @@ class RobotBatchRollout(LeggedRobot):
         # robot_batch_rollout.py:1646-1651: episode length in whole steps, integer push interval
         self.max_episode_length_s = self.max_episode_length * self.dt
         self.cfg.domain_rand.push_interval = int(self.cfg.domain_rand.push_interval_s / self.dt)
+        # (:1657-1659) the rollout class starts from the STAGE-0 scales of a multi-stage config (``_get_reward_scales()`` with its
+        # default argument) while reward_scales_stage is reward_min_stage -- kept as it is
+        self.reward_scales = self._get_reward_scales()
 
     # ------------------------------------------------------------------------------------------
     # env layout (robot_batch_rollout.py:119-164) -- closed form instead of the reference's loops

@@ -107,7 +107,8 @@ def elspider_air() -> RobotSpec:
     return RobotSpec("elspider_air", bodies, dofs, lo, up, [21.0] * 18, [33.5] * 18, offs)
 
 
-ROBOTS: Dict[str, callable] = {"anymal_c": anymal_c, "a1": a1, "go2": go2, "elspider_air": elspider_air, "el_mini": elspider_air}
+ROBOTS: Dict[str, callable] = {"anymal_c": anymal_c, "a1": a1, "go2": go2, "elspider_air": elspider_air, "el_mini": elspider_air,
+                               "elspider": elspider_air}      # (asset.name of the hexapod's main / rollout configs)
 
 
 def get_robot_spec(name: str) -> RobotSpec:

@@ -253,6 +253,8 @@ REWARD_TERMS: Dict[str, Callable] = {
 
 # ----------------------------------------------------------------------------------------------
 class LeggedOracle:
+    INITIAL_SCALES_STAGE = None      # multi-stage reward scales start at cfg.rewards.reward_min_stage (legged_robot.py:_parse_cfg)
+
     """State + per-step methods of the reference ``LeggedRobot`` restated on torch-CPU.
 
     ``state`` uses the PhysX layouts of ``extended_legged_gym_b200.synthetic.make_state``; the
@@ -273,7 +275,7 @@ class LeggedOracle:
         # _parse_cfg (legged_robot.py:847-860)
         self.dt = cfg.control.decimation * self.sim_dt
         self.obs_scales = cfg.normalization.obs_scales
-        self.reward_scales = self._stage_scales(cfg.rewards.reward_min_stage)
+        self.reward_scales = self._stage_scales(cfg.rewards.reward_min_stage if self.INITIAL_SCALES_STAGE is None else self.INITIAL_SCALES_STAGE)
         self.command_ranges = sorted_public_dict(cfg.commands.ranges)
         self.curriculum = cfg.terrain.curriculum and cfg.terrain.mesh_type in ("heightfield", "trimesh", "confined_trimesh")
         self.max_episode_length_s = cfg.env.episode_length_s

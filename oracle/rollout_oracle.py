@@ -110,8 +110,11 @@ class BatchRolloutOracle(LeggedOracle):
     ``1 + rollouts`` envs (main first).  Commands are resampled for main envs and copied to their rollouts; time-outs reset
     main rows only; pushes hit main rows only; ``reset_idx`` runs the terrain curriculum / command resampling / extras for
     the main envs among the reset rows, drops a reset robot onto the terrain surface, and clears episode sums only when a
-    main env resets.  ``tests/test_rollout_step.py`` pins it to the unmodified reference methods (container) and to
+    main env resets.  Multi-stage reward scales: the rollout class's ``_parse_cfg`` takes the STAGE-0 scales whatever
+    ``reward_min_stage`` says (robot_batch_rollout.py:1657-1659: ``_get_reward_scales()`` with its default argument).  ``tests/test_rollout_step.py`` pins it to the unmodified reference methods (container) and to
     ``tests/golden/rollout_step.npz``."""
+
+    INITIAL_SCALES_STAGE = 0
 
     def __init__(self, cfg, spec, state, height_samples, num_main, rollouts, **kw):
         super().__init__(cfg, spec, state, height_samples, **kw)
@@ -206,10 +209,12 @@ class RobotBatchRolloutOracle(BatchRolloutOracle):
       gait scheduler     (:143-150)  stepped AFTER the env step with the env clock: gait_idx = remainder(t / period, 1) for every
                                      row (utils/gait_scheduler.py:63-72 with ``t`` given), t = t_main before the caller advances it
 
-    Pinned to the unmodified ``AnymalCBatchRollout`` methods by tests/golden/rollout_step_anymal.npz
-    (tests/golden/make_rollout_step_golden.py --robot)."""
+    Pinned to the unmodified ``AnymalCBatchRollout`` (tag c) and ``ElSpiderAirBatchRollout`` (tag d) methods by
+    tests/golden/rollout_step_anymal.npz (tests/golden/make_rollout_step_golden.py --robot)."""
 
     def __init__(self, cfg, spec, state, height_samples, num_main, rollouts, upside_down_rows="main", gait_period=1.0, **kw):
+        """``gait_period`` None: the hexapod class, whose main step does not touch its scheduler (it is advanced by
+        post_physics_step_rollout only, elspider_air_batch_rollout.py:132-135)"""
         super().__init__(cfg, spec, state, height_samples, num_main, rollouts, **kw)
         assert upside_down_rows in ("main", "all")
         self.upside_down_rows = upside_down_rows
@@ -226,4 +231,5 @@ class RobotBatchRolloutOracle(BatchRolloutOracle):
 
     def post_physics_step(self, noise_u=None, do_reset=True):
         super().post_physics_step(noise_u, do_reset)
-        self.gait_idx = torch.remainder(self.t_main / self.gait_period * torch.ones(self.num_envs, dtype=torch.float), 1.0)
+        if self.gait_period is not None:
+            self.gait_idx = torch.remainder(self.t_main / self.gait_period * torch.ones(self.num_envs, dtype=torch.float), 1.0)

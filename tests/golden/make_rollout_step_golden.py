@@ -39,14 +39,18 @@ CASES = {   # tag: (case, mains, rollouts, seed, steps, step counter before the 
 
 
 ROBOT_CASES = {   # tag: (case, mains, rollouts, seed, steps, step counter before the first step)
-    "c": ("anymal_c_rough", 8, 7, 3, 3, 0),
+    "c": ("anymal_c_rough", 8, 7, 3, 3, 0),         # AnymalCBatchRollout: upside-down MAIN rows reset, gait scheduler on the env clock
+    "d": ("elspider_air_rough", 6, 4, 5, 3, 0),     # ElSpiderAirBatchRollout (elspider_air_batch_rollout.py:46-230): EVERY upside-down row resets
 }
-UPSIDE_DOWN_ROWS = (0, 3, 8, 21, 40, 42)      # mains 0, 8, 40 (rows k * 8) and rollout rows 3, 21, 42
+UPSIDE_DOWN_ROWS = {"c": (0, 3, 8, 21, 40, 42),      # mains 0, 8, 40 (rows k * 8) and rollout rows 3, 21, 42
+                    "d": (0, 2, 10, 13, 27)}          # mains 0, 10 (rows k * 5) and rollout rows 2, 13, 27
 
 
 def reference_rollout_env(case, num_main, rollouts, spec, st, hf, robot=False):
     rh.install()
-    if robot:
+    if robot == "d":
+        from legged_gym.envs.elspider_air.batch_rollout.elspider_air_batch_rollout import ElSpiderAirBatchRollout as Ref
+    elif robot:
         from legged_gym.envs.anymal_c.batch_rollout.anymal_c_batch_rollout import AnymalCBatchRollout as Ref
     else:
         from legged_gym.envs.batch_rollout.robot_batch_rollout import RobotBatchRollout as Ref
@@ -59,7 +63,14 @@ def reference_rollout_env(case, num_main, rollouts, spec, st, hf, robot=False):
     env._init_env_indices()                 # (:119-164)
     env._prepare_reward_function()          # (:1676-1703) binds the ROLLOUT reward mixin, episode sums over all rows
     env.commands[:] = keep["commands"]
-    if robot:      # what AnymalCBatchRollout.__init__ adds (:58-98): the reference's own scheduler object with the class's config
+    if robot == "d":      # what ElSpiderAirBatchRollout._init_buffers adds (:143-150): the actuator-network state reset_idx clears
+        n, A = env.total_num_envs, env.num_actions
+        env.sea_hidden_state = torch.zeros(2, n * A, 8)
+        env.sea_cell_state = torch.zeros(2, n * A, 8)
+        env.sea_hidden_state_per_env = env.sea_hidden_state.view(2, n, A, 8)
+        env.sea_cell_state_per_env = env.sea_cell_state.view(2, n, A, 8)
+        env.noise_scale_vec = env._get_noise_scale_vec(env.cfg)      # the class's own 18-DOF slices (:94-117; the harness ran the base class's)
+    if robot == "c":      # what AnymalCBatchRollout.__init__ adds (:58-98): the reference's own scheduler object with the class's config
         from legged_gym.utils import GaitScheduler
         from legged_gym.envs.anymal_c.batch_rollout.anymal_c_batch_rollout_config import AnymalCBatchRolloutCfg
         env.gait_scheduler = GaitScheduler(None, env.base_quat, env.base_lin_vel, env.base_ang_vel, env.projected_gravity, env.dof_pos,
@@ -83,7 +94,7 @@ def run_reference(case, num_main, rollouts, seed, steps, counter0, robot=False):
     n = num_main * (1 + rollouts)
     cfg, spec, st = common.make_case_state(case, n, seed=seed, adversarial=True)
     if robot:
-        for row in UPSIDE_DOWN_ROWS:      # half a turn about the body x axis (xyzw): projected_gravity.z = +1
+        for row in UPSIDE_DOWN_ROWS[robot]:      # half a turn about the body x axis (xyzw): projected_gravity.z = +1
             st["root_states"][row, 3:7] = torch.tensor([1.0, 0.0, 0.0, 0.0])
     inputs = {k: v.clone() for k, v in st.items()}
     hf = mg.height_field()
@@ -102,7 +113,7 @@ def run_reference(case, num_main, rollouts, seed, steps, counter0, robot=False):
         finally:
             torch.rand_like = orig
         snap, names = snapshot(env)
-        if robot:
+        if robot == "c":
             snap["gait_idx"] = env.gait_scheduler.gait_idx.clone()
             env.t_main += env.dt          # (RobotBatchRollout.step :597, after post_physics_step)
         for k, v in snap.items():
@@ -118,7 +129,7 @@ def main():
     blob = {}
     robot = "--robot" in sys.argv
     for tag, (case, m, r, seed, steps, c0) in (ROBOT_CASES if robot else CASES).items():
-        inputs, out, env = run_reference(case, m, r, seed, steps, c0, robot=robot)
+        inputs, out, env = run_reference(case, m, r, seed, steps, c0, robot=tag if robot else False)
         for k, v in inputs.items():
             blob[f"{tag}__in__{k}"] = v.numpy()
         for k, v in out.items():

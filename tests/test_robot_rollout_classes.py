@@ -34,27 +34,38 @@ def load(tag="c"):
         trs.GOLDEN = old
 
 
-def test_robot_rollout_oracle_matches_reference_fixture():
-    m, r, seed, c0, inputs, outs, names = load()
-    cfg_cls, spec_fn, _ = common.CASES[CASE]
-    ora = RobotBatchRolloutOracle(cfg_cls(), spec_fn(), {k: v.clone() for k, v in inputs.items()}, synthetic.make_height_field(seed=0), m, r)
+ROBOT_TAGS = {"c": ("anymal_c_rough", dict(upside_down_rows="main", gait_period=1.0)),
+              "d": ("elspider_air_rough", dict(upside_down_rows="all", gait_period=None))}
+
+
+@pytest.mark.parametrize("tag", list(ROBOT_TAGS))
+def test_robot_rollout_oracle_matches_reference_fixture(tag):
+    m, r, seed, c0, inputs, outs, names = load(tag)
+    case, kw = ROBOT_TAGS[tag]
+    cfg_cls, spec_fn, _ = common.CASES[case]
+    ora = RobotBatchRolloutOracle(cfg_cls(), spec_fn(), {k: v.clone() for k, v in inputs.items()}, synthetic.make_height_field(seed=0), m, r, **kw)
     ora.common_step_counter = c0
-    main_flip = rollout_flip_kept = False
+    flipped_rollout_reset = flipped_rollout_kept = flipped_main_reset = False
     for s, want in enumerate(outs):
         torch.manual_seed(5000 + 17 * s + seed)
         ora.torques = ora.compute_torques(ora.actions).view(ora.torques.shape)
+        up_before = ora.root_states[:, 3] == 1.0                 # the rows the generator turned over (quaternion (1, 0, 0, 0))
         ora.post_physics_step(noise_u=want["noise_u"])
         snap = trs.snapshot(ora)
-        snap["gait_idx"] = ora.gait_idx
-        trs.check(snap, want, f"c step {s}", exact=True)
+        if tag == "c":
+            snap["gait_idx"] = ora.gait_idx
+        trs.check(snap, want, f"{tag} step {s}", exact=True)
         sums = torch.stack([ora.episode_sums[k] for k in names])
-        assert torch.equal(sums, want["episode_sums"]), f"c step {s}: episode sums differ"
+        assert torch.equal(sums, want["episode_sums"]), f"{tag} step {s}: episode sums differ"
         ora.t_main += ora.dt
         rb, up = want["reset_buf"].bool(), want["projected_gravity"][:, 2] > 0
-        rollout_flip_kept |= bool((up & ~rb)[ora.rollout_env_indices].any())
-        main_flip |= s == 0 and bool(rb[40])
-    # the fixture holds an upside-down main robot that is reset and an upside-down rollout robot that is not
-    assert main_flip and rollout_flip_kept
+        to = want["time_out_buf"].bool()
+        flipped_rollout_kept |= bool((up & ~rb)[ora.rollout_env_indices].any())
+        flipped_rollout_reset |= bool((up_before & rb & ~to)[ora.rollout_env_indices].any())
+        flipped_main_reset |= bool((up_before & rb)[ora.main_env_indices].any())
+    assert flipped_main_reset
+    # ANYmal: an upside-down rollout robot is left alone; hexapod: it is reset like every other row
+    assert flipped_rollout_kept if tag == "c" else flipped_rollout_reset
 
 
 @pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
@@ -62,9 +73,10 @@ def test_robot_rollout_configs_match_the_reference():
     rh.install()
     from legged_gym.envs.anymal_c.batch_rollout.anymal_c_batch_rollout_config import AnymalCBatchRolloutCfg as RefA
     from legged_gym.envs.go2.batch_rollout.go2_batch_rollout_config import Go2BatchRolloutCfg as RefG
-    from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg, Go2BatchRolloutCfg
+    from legged_gym.envs.elspider_air.batch_rollout.elspider_air_batch_rollout_config import ElSpiderAirBatchRolloutCfg as RefE
+    from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg, Go2BatchRolloutCfg, ElSpiderAirBatchRolloutCfg
     from extended_legged_gym_b200.utils.helpers import class_to_dict
-    for ours, ref in ((AnymalCBatchRolloutCfg, RefA), (Go2BatchRolloutCfg, RefG)):
+    for ours, ref in ((AnymalCBatchRolloutCfg, RefA), (Go2BatchRolloutCfg, RefG), (ElSpiderAirBatchRolloutCfg, RefE)):
         a, b = class_to_dict(ours), class_to_dict(ref)
         for block in ("gait_scheduler", "control", "init_state", "commands"):
             for k, v in b[block].items():
@@ -80,19 +92,22 @@ def test_robot_rollout_configs_match_the_reference():
             assert a["terrain"][k] == b["terrain"][k], k
 
 
-def make_env(fused, inputs, m, r):
-    from extended_legged_gym_b200.envs import AnymalCBatchRollout
+def make_env(fused, inputs, m, r, tag="c"):
+    from extended_legged_gym_b200.envs import AnymalCBatchRollout, ElSpiderAirBatchRollout
     from extended_legged_gym_b200.sim_backend import SyntheticSim
-    cfg_cls, spec_fn, _ = common.CASES[CASE]
+    case, kw = ROBOT_TAGS[tag]
+    cfg_cls, spec_fn, _ = common.CASES[case]
     cfg, spec = cfg_cls(), spec_fn()
     cfg.env.num_envs, cfg.env.rollout_envs = m, r
-    cfg.control.use_actuator_network = False          # the fixture's torques are the PD controller's (anymal_c_batch_rollout_config.py: off)
-    from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg
-    cfg.gait_scheduler = AnymalCBatchRolloutCfg.gait_scheduler      # the scheduler config the fixture's reference object was given
+    cfg.control.use_actuator_network = False          # the fixtures' torques are the PD controller's (the classes' configs: off)
+    if tag == "c":
+        from extended_legged_gym_b200.envs import AnymalCBatchRolloutCfg
+        cfg.gait_scheduler = AnymalCBatchRolloutCfg.gait_scheduler      # the scheduler config the fixture's reference object was given
     n = m * (1 + r)
     hf = synthetic.make_height_field(seed=0)
-    ora = RobotBatchRolloutOracle(cfg_cls(), spec_fn(), {k: v.clone() for k, v in inputs.items()}, hf, m, r)    # terrain bookkeeping only
-    env = AnymalCBatchRollout(cfg, None, SyntheticSim(cfg, n, DEV, spec=spec, height_samples=hf, state={k: v.clone() for k, v in inputs.items()}), DEV, True)
+    ora = RobotBatchRolloutOracle(cfg_cls(), spec_fn(), {k: v.clone() for k, v in inputs.items()}, hf, m, r, **kw)    # terrain bookkeeping only
+    cls = AnymalCBatchRollout if tag == "c" else ElSpiderAirBatchRollout
+    env = cls(cfg, None, SyntheticSim(cfg, n, DEV, spec=spec, height_samples=hf, state={k: v.clone() for k, v in inputs.items()}), DEV, True)
     env.set_env_state(inputs)
     env.fused_reset = fused
     env._rand = lambda lo, hi, shape: ((hi - lo) * torch.rand(*shape) + lo).to(DEV)
@@ -393,3 +408,31 @@ def test_go2_traj_grad_sampling_rewards_are_the_python_terms():
     tab = env.rollout_batch(torch.randn(10, 3, 12, generator=torch.Generator().manual_seed(3)).to(DEV) * 0.3)
     torch.cuda.synchronize()
     assert tab.shape == (10, 3) and bool(torch.isfinite(tab).all()) and bool((tab != 0).all())
+
+
+@pytest.mark.gpu
+def test_elspider_rollout_env_matches_reference_fixture():
+    """ElSpiderAirBatchRollout.post_physics_step (generic kernel, 18 DOF / 6 feet, main / rollout layout) against the fixture of the
+    unmodified reference class: every upside-down row resets, the main step leaves the gait scheduler alone"""
+    m, r, seed, c0, inputs, outs, names = load("d")
+    env = make_env(False, inputs, m, r, tag="d")
+    env.common_step_counter = c0
+    assert env._native_params().terminate_upside_down == 1 and env.num_dof == 18
+    env.gait_idx.fill_(0.37)
+    env.gait_prev_foot_z.fill_(0.011)
+    saw = False
+    for s, want in enumerate(outs):
+        torch.manual_seed(5000 + 17 * s + seed)
+        env.noise_u = want["noise_u"].to(DEV)
+        env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+        up_before = (env.root_states[:, 3] == 1.0).cpu()
+        env.post_physics_step()
+        torch.cuda.synchronize()
+        trs.check(trs.snapshot(env), want, f"d step {s}", exact=False)
+        sums = torch.stack([env.episode_sums[k] for k in names]).cpu()
+        assert torch.allclose(sums, want["episode_sums"], rtol=1e-5, atol=1e-6), f"d step {s}: episode sums differ"
+        rb, to = env.reset_buf.cpu().bool(), env.time_out_buf.cpu().bool()
+        saw |= bool((up_before & rb & ~to)[env.rollout_env_indices.cpu()].any())
+        env.t_main += env.dt
+    assert saw                                                            # an upside-down ROLLOUT robot was reset
+    assert bool((env.gait_idx == 0.37).all()) and bool((env.gait_prev_foot_z == 0.011).all())
