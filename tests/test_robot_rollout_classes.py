@@ -245,6 +245,9 @@ def test_go2_rollout_class_steps_on_a_plane():
 # AnymalCTrajGradSampling: the DIAL-MPC reward set against the unmodified reference methods (CPU, bit for bit)
 # ---------------------------------------------------------------------------------------------------------------
 DIAL_TERMS = ("gaits", "air_time", "pos", "upright", "yaw", "vel", "ang_vel", "height", "energy", "alive", "no_fly")
+DIAL_GAITS = ("trot", "walk", "gallop", "stand")
+DIAL_N = 257
+DIAL_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dial_mpc_terms.npz")
 
 
 def _dial_fake_self(cls, n, seed, heading, flags_dtype):
@@ -276,6 +279,29 @@ def _dial_fake_self(cls, n, seed, heading, flags_dtype):
     return o
 
 
+@pytest.mark.parametrize("robot", ["anymal_c", "go2"])
+@pytest.mark.parametrize("heading", [False, True])
+def test_dial_mpc_reward_terms_match_the_reference_fixture(heading, robot):
+    """tests/golden/dial_mpc_terms.npz holds the unmodified reference methods' outputs on the seeded tensors of _dial_fake_self
+    (tests/golden/make_dial_golden.py): the fixture travels to the GPU box, the reference does not"""
+    from extended_legged_gym_b200.envs import AnymalCTrajGradSampling, Go2TrajGradSampling
+    cls = AnymalCTrajGradSampling if robot == "anymal_c" else Go2TrajGradSampling
+    z = np.load(DIAL_GOLDEN)
+    checked = 0
+    for gait in DIAL_GAITS:
+        ours = _dial_fake_self(cls, DIAL_N, 5, heading, torch.long)
+        ours._init_dial_mpc()
+        ours._gait = gait
+        for name in DIAL_TERMS:
+            key = f"{robot}__{int(heading)}__{gait}__{name}"
+            if key in z.files:
+                assert torch.equal(getattr(ours, "_reward_" + name)().float(), torch.from_numpy(z[key])), key
+                checked += 1
+        assert torch.equal(ours.feet_air_time, torch.from_numpy(z[f"{robot}__{int(heading)}__{gait}__feet_air_time"]))
+        assert torch.equal(ours.last_contacts, torch.from_numpy(z[f"{robot}__{int(heading)}__{gait}__last_contacts"]))
+    assert checked == len(DIAL_GAITS) * (11 if robot == "anymal_c" else 10)
+
+
 @pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
 @pytest.mark.parametrize("robot", ["anymal_c", "go2"])
 @pytest.mark.parametrize("heading", [False, True])
@@ -288,8 +314,8 @@ def test_dial_mpc_reward_terms_equal_the_reference_methods(heading, robot):
         from legged_gym.envs.go2.batch_rollout.go2_traj_grad_sampling import Go2TrajGradSampling as Ref
         from extended_legged_gym_b200.envs import Go2TrajGradSampling as AnymalCTrajGradSampling
     from extended_legged_gym_b200.envs.anymal_c.batch_rollout.anymal_c_traj_grad_sampling import DialMpcRewardMixin
-    n = 257
-    for gait in ("trot", "walk", "gallop", "stand"):
+    n = DIAL_N
+    for gait in DIAL_GAITS:
         ours = _dial_fake_self(AnymalCTrajGradSampling, n, 5, heading, torch.long)
         ref = _dial_fake_self(Ref, n, 5, heading, torch.long)
         ours._init_dial_mpc()
