@@ -54,8 +54,13 @@ class GaitClockMixin:
             # a captured horizon (rollout_batch) would freeze the value of its capture; the graph is only taken while the
             # scheduler's reward is off (rollout_batch below), and the first eager step afterwards sets the phase from the clock again
             return
-        x = np.float32(t / self.gait_cfg.period) * np.float32(1.0)
-        self.gait_idx.fill_(float(np.remainder(x, np.float32(1.0))))
+        self.gait_idx.fill_(self.clock_phase(t, self.gait_cfg.period))
+
+    @staticmethod
+    def clock_phase(t, period):
+        """``torch.remainder(t / period * ones(float32), 1.0)`` (utils/gait_scheduler.py:66-67) for Python floats t, period: the
+        quotient is formed in double, rounded to float32 by the multiplication with the float32 tensor, then reduced"""
+        return float(np.remainder(np.float32(t / period) * np.float32(1.0), np.float32(1.0)))
 
     def post_physics_step(self):
         super().post_physics_step()

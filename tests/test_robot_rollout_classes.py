@@ -92,6 +92,27 @@ def test_robot_rollout_configs_match_the_reference():
             assert a["terrain"][k] == b["terrain"][k], k
 
 
+def test_gait_clock_phase_equals_the_schedulers_expression():
+    """GaitClockMixin.clock_phase against GaitScheduler.step(..., t) (utils/gait_scheduler.py:63-72): the torch expression of the
+    reference on 80 000 clock values accumulated like t_main / t_rollout (+= dt), and -- in the container -- the reference object"""
+    from extended_legged_gym_b200.envs.anymal_c.batch_rollout.anymal_c_batch_rollout import GaitClockMixin
+    sched = None
+    if rh.available():
+        rh.install()
+        from legged_gym.utils.gait_scheduler import GaitScheduler, GaitSchedulerCfg
+        sched = GaitScheduler(None, *([None] * 8), 3, "cpu", gait_cfg=GaitSchedulerCfg())
+    for period, dt in ((1.0, 0.02), (0.6, 0.005 * 4), (1.4, 0.02), (0.37, 0.017)):
+        t = 0.0
+        for i in range(20000):
+            want = torch.remainder(t / period * torch.ones(3, dtype=torch.float), 1.0)
+            assert GaitClockMixin.clock_phase(t, period) == float(want[0]), (period, i)
+            if sched is not None and i % 997 == 0:
+                sched.gait_cfg.period = period
+                sched.step(None, None, None, t)
+                assert torch.equal(sched.gait_idx, want)
+            t += dt
+
+
 def make_env(fused, inputs, m, r, tag="c"):
     from extended_legged_gym_b200.envs import AnymalCBatchRollout, ElSpiderAirBatchRollout
     from extended_legged_gym_b200.sim_backend import SyntheticSim
