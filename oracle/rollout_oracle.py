@@ -233,3 +233,13 @@ class RobotBatchRolloutOracle(BatchRolloutOracle):
         super().post_physics_step(noise_u, do_reset)
         if self.gait_period is not None:
             self.gait_idx = torch.remainder(self.t_main / self.gait_period * torch.ones(self.num_envs, dtype=torch.float), 1.0)
+
+    def post_physics_step_rollout(self, noise_u=None, t_rollout=None, gait_increment=(0.005, 1.4)):
+        """the robot classes' post_physics_step_rollout: the base step, then the scheduler -- on the rollout clock (ANYmal / Go2,
+        anymal_c_batch_rollout.py:143-146) or by one increment dt / period of ``cfg.gait_scheduler`` (hexapod,
+        elspider_air_batch_rollout.py:132-135 -> utils/gait_scheduler.py:68-69)"""
+        super().post_physics_step_rollout(noise_u)
+        if self.gait_period is not None:
+            self.gait_idx = torch.remainder(t_rollout / self.gait_period * torch.ones(self.num_envs, dtype=torch.float), 1.0)
+        else:
+            self.gait_idx = torch.remainder(self.gait_idx + gait_increment[0] / gait_increment[1], 1.0)

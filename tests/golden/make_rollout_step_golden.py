@@ -9,7 +9,8 @@ object's class is then switched to RobotBatchRollout, and the rollout class's ow
 _prepare_reward_function run on it.  Every per-step method that runs afterwards is the rollout class's, unmodified.
 
     python tests/golden/make_rollout_step_golden.py            # rollout_step.npz (tags a, b: RobotBatchRollout)
-    python tests/golden/make_rollout_step_golden.py --robot    # rollout_step_anymal.npz (tag c: AnymalCBatchRollout)
+    python tests/golden/make_rollout_step_golden.py --robot    # rollout_step_anymal.npz (tags c, d: AnymalCBatchRollout, ElSpiderAirBatchRollout)
+    python tests/golden/make_rollout_step_golden.py --rollout-mode   # rollout_mode_step.npz: post_physics_step_rollout (:763-817) of all four
 
 Tag c switches the object's class to the robot-specific ``AnymalCBatchRollout`` (envs/anymal_c/batch_rollout/
 anymal_c_batch_rollout.py:49-225: upside-down MAIN rows terminate :192-199, the gait scheduler follows the env clock :143-150)
@@ -125,7 +126,64 @@ def run_reference(case, num_main, rollouts, seed, steps, counter0, robot=False):
     return inputs, out, env
 
 
+def run_reference_rollout_mode(tag, case, num_main, rollouts, seed, counter0, robot):
+    """one main step (as in run_reference), fresh actions, torques, then the class's own ``post_physics_step_rollout``
+    (robot_batch_rollout.py:763-817 + the robot classes' scheduler call): the state of the ROLLOUT rows afterwards"""
+    n = num_main * (1 + rollouts)
+    cfg, spec, st = common.make_case_state(case, n, seed=seed, adversarial=True)
+    if robot:
+        for row in UPSIDE_DOWN_ROWS[robot]:
+            st["root_states"][row, 3:7] = torch.tensor([1.0, 0.0, 0.0, 0.0])
+    inputs = {k: v.clone() for k, v in st.items()}
+    env = reference_rollout_env(case, num_main, rollouts, spec, st, mg.height_field(), robot=robot)
+    env.common_step_counter = counter0
+    if robot == "d":      # ElSpiderAirBatchRollout.__init__ (:64-78): the reference scheduler object with the class's config
+        from legged_gym.utils import GaitScheduler
+        from legged_gym.envs.elspider_air.batch_rollout.elspider_air_batch_rollout_config import ElSpiderAirBatchRolloutCfg
+        env.gait_scheduler = GaitScheduler(None, env.base_quat, env.base_lin_vel, env.base_ang_vel, env.projected_gravity, env.dof_pos,
+                                           env.dof_vel, env.foot_positions, env.foot_velocities, env.total_num_envs, env.device,
+                                           gait_cfg=ElSpiderAirBatchRolloutCfg.gait_scheduler)
+    g = torch.Generator().manual_seed(2000 + seed)
+    u_main, u_roll = torch.rand(n, env.num_obs, generator=g), torch.rand(n, env.num_obs, generator=g)
+    new_actions = torch.randn(n, env.num_actions, generator=g)
+    orig = torch.rand_like
+    out = {"noise_u_main": u_main.numpy(), "noise_u_rollout": u_roll.numpy(), "actions_rollout": new_actions.numpy()}
+    try:
+        torch.manual_seed(5000 + seed)
+        torch.rand_like = lambda t, *a, **k: u_main.clone() if t.shape == u_main.shape else orig(t, *a, **k)
+        env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+        env.post_physics_step()
+        if robot == "c":
+            env.t_main += env.dt
+        env.t_rollout = getattr(env, "t_main", 0.0)
+        env.actions[:] = new_actions
+        torch.rand_like = lambda t, *a, **k: u_roll.clone() if t.shape == u_roll.shape else orig(t, *a, **k)
+        env.torques = env._compute_torques(env.actions).view(env.torques.shape)
+        env.post_physics_step_rollout()
+    finally:
+        torch.rand_like = orig
+    snap, names = snapshot(env)
+    if robot:
+        snap["gait_idx"] = env.gait_scheduler.gait_idx.clone()
+    for k, v in snap.items():
+        out[k] = v.numpy()
+    return inputs, out
+
+
 def main():
+    if "--rollout-mode" in sys.argv:
+        blob = {}
+        for tag, (case, m, r, seed, steps, c0) in {**CASES, **ROBOT_CASES}.items():
+            inputs, out = run_reference_rollout_mode(tag, case, m, r, seed, c0, tag if tag in ROBOT_CASES else False)
+            for k, v in inputs.items():
+                blob[f"{tag}__in__{k}"] = v.numpy()
+            for k, v in out.items():
+                blob[f"{tag}__out__{k}"] = v
+            blob[f"{tag}__meta"] = np.array([m, r, seed, steps, c0], dtype=np.int64)
+        path = os.path.join(HERE, "rollout_mode_step.npz")
+        np.savez_compressed(path, **blob)
+        print("wrote", path, os.path.getsize(path) // 1024, "KiB")
+        return
     blob = {}
     robot = "--robot" in sys.argv
     for tag, (case, m, r, seed, steps, c0) in (ROBOT_CASES if robot else CASES).items():

@@ -92,6 +92,60 @@ def test_robot_rollout_configs_match_the_reference():
             assert a["terrain"][k] == b["terrain"][k], k
 
 
+ROLLOUT_MODE_GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rollout_mode_step.npz")
+
+
+@pytest.mark.parametrize("tag", ["a", "b", "c", "d"])
+def test_rollout_mode_step_oracle_matches_reference_fixture(tag):
+    """``post_physics_step_rollout`` (envs/batch_rollout/robot_batch_rollout.py:763-817 and the robot classes' scheduler call) -- the
+    step the horizon loop of the sampling-based optimiser repeats -- as the oracles restate it, against the unmodified reference
+    methods' output after one main step (tests/golden/make_rollout_step_golden.py --rollout-mode): rollout rows, bit for bit.  (The
+    reference refreshes the derived state of the rollout rows only; main rows are put back by _restore_main_env_states.)"""
+    from oracle.rollout_oracle import BatchRolloutOracle
+    z = np.load(ROLLOUT_MODE_GOLDEN)
+    m, r, seed, steps, c0 = (int(x) for x in z[f"{tag}__meta"])
+    inputs = {k[len(tag) + 6:]: torch.from_numpy(z[k]) for k in z.files if k.startswith(f"{tag}__in__")}
+    want = {k[len(tag) + 7:]: torch.from_numpy(np.asarray(z[k])) for k in z.files if k.startswith(f"{tag}__out__")}
+    case = {**trs.TAGS, **{t: c for t, (c, _) in ROBOT_TAGS.items()}}[tag]
+    cfg_cls, spec_fn, _ = common.CASES[case]
+    hf = synthetic.make_height_field(seed=0)
+    st = {k: v.clone() for k, v in inputs.items()}
+    if tag in ROBOT_TAGS:
+        ora = RobotBatchRolloutOracle(cfg_cls(), spec_fn(), st, hf, m, r, **ROBOT_TAGS[tag][1])
+    else:
+        ora = BatchRolloutOracle(cfg_cls(), spec_fn(), st, hf, m, r)
+    ora.common_step_counter = c0
+    torch.manual_seed(5000 + seed)
+    ora.torques = ora.compute_torques(ora.actions).view(ora.torques.shape)
+    ora.post_physics_step(noise_u=want["noise_u_main"])
+    t_rollout = 0.0
+    if tag == "c":
+        ora.t_main += ora.dt
+        t_rollout = ora.t_main
+    ora.actions[:] = want["actions_rollout"]
+    ora.torques = ora.compute_torques(ora.actions).view(ora.torques.shape)
+    if tag in ROBOT_TAGS:
+        ora.post_physics_step_rollout(noise_u=want["noise_u_rollout"], t_rollout=t_rollout)
+    else:
+        ora.post_physics_step_rollout(noise_u=want["noise_u_rollout"])
+    snap = trs.snapshot(ora)
+    if tag in ROBOT_TAGS:
+        snap["gait_idx"] = ora.gait_idx
+    rows = ora.rollout_env_indices
+    checked = 0
+    for k, w in want.items():
+        if k in ("noise_u_main", "noise_u_rollout", "actions_rollout", "episode_sums") or k.startswith("extras__"):
+            continue
+        g = snap[k]
+        if g.dim() > 0 and g.shape[0] == ora.num_envs * ora.num_dof:       # dof_state [N * D, 2]
+            g, w = g.view(ora.num_envs, -1), w.view(ora.num_envs, -1)
+        if g.dim() > 0 and g.shape[0] == ora.num_envs:
+            g, w = g[rows], w[rows]
+        assert torch.equal(g.to(w.dtype), w), f"{tag}: {k} differs from the reference's rollout-mode step"
+        checked += 1
+    assert checked >= 20
+
+
 def test_gait_clock_phase_equals_the_schedulers_expression():
     """GaitClockMixin.clock_phase against GaitScheduler.step(..., t) (utils/gait_scheduler.py:63-72): the torch expression of the
     reference on 80 000 clock values accumulated like t_main / t_rollout (+= dt), and -- in the container -- the reference object"""
