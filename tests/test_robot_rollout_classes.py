@@ -537,3 +537,29 @@ def test_elspider_rollout_env_matches_reference_fixture():
         env.t_main += env.dt
     assert saw                                                            # an upside-down ROLLOUT robot was reset
     assert bool((env.gait_idx == 0.37).all()) and bool((env.gait_prev_foot_z == 0.011).all())
+
+
+@pytest.mark.skipif(not rh.available(), reason="the reference checkout is only present in the build container")
+def test_action_normalisation_equals_the_reference_methods():
+    """RobotTrajGradSampling._normalize_actions / _denormalize_actions (robot_traj_grad_sampling.py:307-345) against the unmodified
+    reference methods on the same limits, normalisation on and off (CPU, bit for bit)"""
+    rh.install()
+    from legged_gym.envs.batch_rollout.robot_traj_grad_sampling import RobotTrajGradSampling as Ref
+    from extended_legged_gym_b200.envs import RobotTrajGradSampling
+    g = torch.Generator().manual_seed(12)
+    lower = -torch.rand(12, generator=g) - 0.2
+    upper = torch.rand(12, generator=g) + 0.3
+    x = torch.randn(300, 12, generator=g) * 1.5
+    for on in (True, False):
+        objs = []
+        for cls in (RobotTrajGradSampling, Ref):
+            o = object.__new__(cls)
+            o.__dict__.update(use_action_normalization=on, joint_lower_limits=lower.clone(), joint_upper_limits=upper.clone(),
+                              joint_ranges=upper - lower, joint_mid_points=(upper + lower) / 2.0)
+            objs.append(o)
+        ours, ref = objs
+        assert torch.equal(ours._normalize_actions(x), ref._normalize_actions(x))
+        assert torch.equal(ours._denormalize_actions(x), ref._denormalize_actions(x))
+        if on:      # a round trip inside the limits is the identity up to rounding
+            inside = lower + (upper - lower) * torch.rand(300, 12, generator=g)
+            assert torch.allclose(ours._denormalize_actions(ours._normalize_actions(inside)), inside, atol=1e-6)
